@@ -1,0 +1,172 @@
+/*
+ * sbs_b200.h — C ABI of the B200-native XPBD hot path (libsbsb200.so).
+ *
+ * The reference ("sbs", Q-Minh/soft-body-simulator) has no FFI: its plug-in points are C++
+ * virtual interfaces and the predict/commit loops are inline in timestep_t::step, so the
+ * replaceable unit is "a simulation_t plus timestep_t::step" (SURVEY.md §8b).  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference
+ * root).  The C++ facade in soft-body-simulator_b200/cpp/sbs/ re-creates the reference's
+ * class names on top of these calls; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 (SBSB200_OK) or a negative error code, except the add_*
+ *     functions, which return the new body index (>= 0) or a negative error code;
+ *   - sbsb200_last_error() gives a message for the most recent failure on that context
+ *     (pass NULL for failures of sbsb200_create);
+ *   - host arrays are caller-owned and copied during the call; the context owns all device
+ *     memory; no device pointer escapes;
+ *   - one context per GPU; a context is not thread-safe;
+ *   - there is NO CPU fallback: every call fails with SBSB200_ERR_CUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef SBS_B200_H
+#define SBS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBSB200_OK 0
+#define SBSB200_ERR_INVALID (-1)  /* bad argument / wrong call order */
+#define SBSB200_ERR_CUDA (-2)     /* CUDA runtime failure, message in last_error */
+#define SBSB200_ERR_STATE (-3)    /* e.g. step before finalize */
+#define SBSB200_ERR_CAPACITY (-4) /* more colours / contacts than supported */
+
+/* arithmetic of the device path: the production build is fp32, the validation build fp64
+ * (include/sbs/aliases.h:9 uses double throughout). */
+#define SBSB200_FP32 32
+#define SBSB200_FP64 64
+
+/* detect_mode of sbsb200_step */
+#define SBSB200_DETECT_PER_FRAME 0   /* reference semantics: timestep.cpp:29-30 */
+#define SBSB200_DETECT_PER_SUBSTEP 1 /* == `substeps` calls of step() with substeps=1 */
+
+/* schedule selection (sbsb200_set_schedule) */
+#define SBSB200_SCHED_AUTO 0
+#define SBSB200_SCHED_GRAPH 1      /* one kernel per colour, whole frame in a CUDA graph */
+#define SBSB200_SCHED_PERSISTENT 2 /* one cooperative kernel per substep, region-resident state */
+
+typedef struct sbsb200_ctx sbsb200_ctx;
+
+typedef struct sbsb200_stats
+{
+    int32_t n_bodies;
+    int32_t n_sdfs;
+    int64_t n_vertices;
+    int64_t n_tets;
+    int64_t n_distance;
+    int64_t n_surface_vertices;
+    int32_t n_green_colours;
+    int32_t n_distance_colours;
+    int32_t schedule;           /* SBSB200_SCHED_* actually in use */
+    int32_t n_regions;          /* persistent schedule: regions (= CTAs) */
+    int64_t n_interface_vertices;
+    int64_t kernels_launched;   /* kernels of this library launched since create */
+    int64_t frames;             /* sbsb200_step calls since create */
+    int64_t last_contact_count; /* contacts found by the most recent detection */
+    double last_step_ms;        /* device time of the most recent sbsb200_step (CUDA events) */
+} sbsb200_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* simulation_t{} (include/sbs/physics/simulation.h:15-45) bound to one GPU. */
+int sbsb200_create(int device, int precision, sbsb200_ctx** out);
+void sbsb200_destroy(sbsb200_ctx* ctx);
+const char* sbsb200_last_error(const sbsb200_ctx* ctx);
+
+/* Run on a caller-provided cudaStream_t (e.g. the framework's current stream); default is a
+ * stream owned by the context.  Must be called before finalize. */
+int sbsb200_set_stream(sbsb200_ctx* ctx, void* cuda_stream);
+int sbsb200_set_schedule(sbsb200_ctx* ctx, int schedule);
+
+/* simulation_parameters_t::collision_compliance (include/sbs/physics/xpbd/simulation_parameters.h:24) */
+int sbsb200_set_collision_compliance(sbsb200_ctx* ctx, double alpha);
+
+/* ---- scene description (before finalize) ----------------------------------------------- */
+
+/* tetrahedral_body_t(simulation, id, geometry) (src/physics/tetrahedral_body.cpp:29-83) plus
+ * one green_constraint_t(alpha, beta, sim, body, v1..v4, E, nu) per tet in tet order
+ * (src/physics/xpbd/green_constraint.cpp:11-47, main.cpp:37-54).
+ * x0: 3*nV doubles; mass: nV doubles or NULL (= 1, particle.cpp:7; 0 pins the vertex,
+ * particle.cpp:39-49); tets: 4*nT vertex indices local to the body. */
+int sbsb200_add_tet_body(sbsb200_ctx* ctx, int64_t nV, const double* x0, const double* mass,
+                         int64_t nT, const uint32_t* tets, double young_modulus,
+                         double poisson_ratio, double alpha, double beta);
+
+/* distance_constraint_t(alpha, beta, sim, b1, b2, v1, v2) (xpbd/distance_constraint.cpp:8-22),
+ * n constraints, pairs = 2*n body-local vertex indices (v1 in b1, v2 in b2). */
+int sbsb200_add_distance_constraints(sbsb200_ctx* ctx, int b1, int b2, int64_t n,
+                                     const uint32_t* pairs, double alpha, double beta);
+
+/* environment_body_t(sim, id, geometry, sdf_model_t) (src/physics/environment_body.cpp:80-88)
+ * with sdf_model_t::from_plane (src/physics/collision/sdf_model.cpp:52-64) or an analytic
+ * sdf_model_t (sdf_model.h:18-23).  volume = englobing AABB {min xyz, max xyz}
+ * (collision_model.h:39-40).  Each takes one body slot, like simulation_t::add_body. */
+int sbsb200_add_sdf_plane(sbsb200_ctx* ctx, const double normal[3], const double point[3],
+                          const double volume[6]);
+int sbsb200_add_sdf_sphere(sbsb200_ctx* ctx, const double centre[3], double radius,
+                           const double volume[6]);
+int sbsb200_add_sdf_box(sbsb200_ctx* ctx, const double box_min[3], const double box_max[3],
+                        const double volume[6]);
+
+/* Boundary extraction, graph colouring, region partition, SoA upload, BVH build.  Replaces
+ * the incremental topology build (src/physics/topology.cpp:904-956) and
+ * tetrahedral_mesh_boundary_t::extract_boundary_surface
+ * (src/physics/tetrahedral_mesh_boundary.cpp:65-120). */
+int sbsb200_finalize(sbsb200_ctx* ctx);
+
+/* ---- introspection (after finalize) ---------------------------------------------------- */
+
+/* Number of elastic constraints (green + distance), i.e. simulation_t::constraints().size(). */
+int64_t sbsb200_constraint_count(const sbsb200_ctx* ctx);
+
+/* The serial Gauss-Seidel order equivalent to the GPU schedule: order[i] = insertion index
+ * (position in simulation_t::constraints_, src/physics/simulation.cpp:29-32) of the i-th
+ * projected constraint.  Feeding this permutation to the reference/oracle reproduces the
+ * GPU result ("the reference run with constraints permuted into the same colour order"). */
+int sbsb200_get_constraint_order(const sbsb200_ctx* ctx, uint32_t* order, int64_t n);
+
+/* tetrahedral_mesh_boundary_t::surface_to_tetrahedral_mesh_index_map()
+ * (tetrahedral_mesh_boundary.cpp:49-58).  Pass map=NULL to query the count. */
+int64_t sbsb200_get_surface_map(const sbsb200_ctx* ctx, int body, uint32_t* map, int64_t cap);
+
+int sbsb200_get_stats(const sbsb200_ctx* ctx, sbsb200_stats* out);
+
+/* ---- state ----------------------------------------------------------------------------- */
+
+/* Overwrite x (and v, NULL = 0) of a body; xi = xn = x as tetrahedral_body_t::transform
+ * leaves them (tetrahedral_body.cpp:121-132); refreshes the surface copy. 3*nV doubles. */
+int sbsb200_upload(sbsb200_ctx* ctx, int body, const double* x, const double* v);
+/* particle_t::x(), v() of every vertex of a body (either may be NULL). */
+int sbsb200_download(sbsb200_ctx* ctx, int body, double* x, double* v);
+/* particle_t::mass() = m (main.cpp:158-165 toggles 1 <-> 0 between frames). */
+int sbsb200_set_mass(sbsb200_ctx* ctx, int body, int64_t vertex, double mass);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+
+/* timestep_t::step(simulation_t&) (src/physics/timestep.cpp:20-70): detection, then
+ * `substeps` x (predict, `iterations` Gauss-Seidel sweeps, commit), then surface/BVH
+ * update.  Asynchronous on the context's stream. */
+int sbsb200_step(sbsb200_ctx* ctx, double dt, int substeps, int iterations, int detect_mode);
+
+/* Same, with HOST buffers either side: uploads x_in/v_in (3*nV doubles each, v_in may be
+ * NULL) for `body`, steps, downloads x_out/v_out and returns when they are valid. */
+int sbsb200_step_host(sbsb200_ctx* ctx, int body, const double* x_in, const double* v_in,
+                      double dt, int substeps, int iterations, int detect_mode, double* x_out,
+                      double* v_out);
+
+int sbsb200_synchronize(sbsb200_ctx* ctx);
+
+/* Contacts of the most recent detection, as the arguments handed to
+ * xpbd::contact_handler_t::handle (xpbd/contact_handler.cpp:14-54): tet body, tet-mesh vertex
+ * (after from_surface_vertex), sdf body, contact point, unit normal.  Order is unspecified.
+ * Pass NULL buffers to query the count.  Returns the count (>= 0) or an error. */
+int64_t sbsb200_get_contacts(sbsb200_ctx* ctx, int64_t cap, int32_t* body, uint32_t* vertex,
+                             int32_t* sdf_body, double* point, double* normal);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBS_B200_H */

@@ -1,0 +1,225 @@
+"""sbs-b200: host-side binding of the B200-native XPBD hot path (libsbsb200.so).
+
+The product is the C-ABI library (include/sbs_b200.h) plus the C++ facade under cpp/sbs/.
+This module is the thin ctypes plumbing tests and bench.py use to reach the C ABI; it holds
+no physics.  It fails loudly when the CUDA library is missing: there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsbsb200.so")
+
+FP32, FP64 = 32, 64
+DETECT_PER_FRAME, DETECT_PER_SUBSTEP = 0, 1
+SCHED_AUTO, SCHED_GRAPH, SCHED_PERSISTENT = 0, 1, 2
+
+_dp = C.POINTER(C.c_double)
+_u32p = C.POINTER(C.c_uint32)
+_i32p = C.POINTER(C.c_int32)
+
+EXPORTS = [
+    "sbsb200_create", "sbsb200_destroy", "sbsb200_last_error", "sbsb200_set_stream", "sbsb200_set_schedule",
+    "sbsb200_set_collision_compliance", "sbsb200_add_tet_body", "sbsb200_add_distance_constraints",
+    "sbsb200_add_sdf_plane", "sbsb200_add_sdf_sphere", "sbsb200_add_sdf_box", "sbsb200_finalize",
+    "sbsb200_constraint_count", "sbsb200_get_constraint_order", "sbsb200_get_surface_map", "sbsb200_get_stats",
+    "sbsb200_upload", "sbsb200_download", "sbsb200_set_mass", "sbsb200_step", "sbsb200_step_host",
+    "sbsb200_synchronize", "sbsb200_get_contacts",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_bodies", C.c_int32), ("n_sdfs", C.c_int32), ("n_vertices", C.c_int64), ("n_tets", C.c_int64),
+                ("n_distance", C.c_int64), ("n_surface_vertices", C.c_int64), ("n_green_colours", C.c_int32),
+                ("n_distance_colours", C.c_int32), ("schedule", C.c_int32), ("n_regions", C.c_int32),
+                ("n_interface_vertices", C.c_int64), ("kernels_launched", C.c_int64), ("frames", C.c_int64),
+                ("last_contact_count", C.c_int64), ("last_step_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SbsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libsbsb200.so and declare its prototypes.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SbsError("libsbsb200.so is not built (%s); run __graft_entry__.build(). "
+                       "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.sbsb200_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    L.sbsb200_destroy.argtypes = [vp]
+    L.sbsb200_destroy.restype = None
+    L.sbsb200_last_error.argtypes = [vp]
+    L.sbsb200_last_error.restype = C.c_char_p
+    L.sbsb200_set_stream.argtypes = [vp, vp]
+    L.sbsb200_set_schedule.argtypes = [vp, C.c_int]
+    L.sbsb200_set_collision_compliance.argtypes = [vp, C.c_double]
+    L.sbsb200_add_tet_body.argtypes = [vp, C.c_int64, _dp, _dp, C.c_int64, _u32p, C.c_double, C.c_double,
+                                       C.c_double, C.c_double]
+    L.sbsb200_add_distance_constraints.argtypes = [vp, C.c_int, C.c_int, C.c_int64, _u32p, C.c_double, C.c_double]
+    L.sbsb200_add_sdf_plane.argtypes = [vp, _dp, _dp, _dp]
+    L.sbsb200_add_sdf_sphere.argtypes = [vp, _dp, C.c_double, _dp]
+    L.sbsb200_add_sdf_box.argtypes = [vp, _dp, _dp, _dp]
+    L.sbsb200_finalize.argtypes = [vp]
+    L.sbsb200_constraint_count.argtypes = [vp]
+    L.sbsb200_constraint_count.restype = C.c_int64
+    L.sbsb200_get_constraint_order.argtypes = [vp, _u32p, C.c_int64]
+    L.sbsb200_get_surface_map.argtypes = [vp, C.c_int, _u32p, C.c_int64]
+    L.sbsb200_get_surface_map.restype = C.c_int64
+    L.sbsb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.sbsb200_upload.argtypes = [vp, C.c_int, _dp, _dp]
+    L.sbsb200_download.argtypes = [vp, C.c_int, _dp, _dp]
+    L.sbsb200_set_mass.argtypes = [vp, C.c_int, C.c_int64, C.c_double]
+    L.sbsb200_step.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_int]
+    L.sbsb200_step_host.argtypes = [vp, C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]
+    L.sbsb200_synchronize.argtypes = [vp]
+    L.sbsb200_get_contacts.argtypes = [vp, C.c_int64, _i32p, _u32p, _i32p, _dp, _dp]
+    L.sbsb200_get_contacts.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Simulation:
+    """One sbsb200 context == the reference's simulation_t + timestep_t on one GPU."""
+
+    def __init__(self, device=0, precision=FP32, stream=None, schedule=SCHED_AUTO):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.sbsb200_create(device, precision, C.byref(h))
+        if rc:
+            raise SbsError("sbsb200_create: %s" % self._L.sbsb200_last_error(None).decode())
+        self._h = h
+        self._nv = {}
+        if stream is not None:
+            self._ck(self._L.sbsb200_set_stream(self._h, C.c_void_p(stream)))
+        if schedule != SCHED_AUTO:
+            self._ck(self._L.sbsb200_set_schedule(self._h, schedule))
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise SbsError("sbsb200 error %d: %s" % (rc, self._L.sbsb200_last_error(self._h).decode()))
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sbsb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_collision_compliance(self, alpha):
+        self._ck(self._L.sbsb200_set_collision_compliance(self._h, alpha))
+
+    def add_tet_body(self, x0, tets, mass=None, young=1e6, poisson=0.3, alpha=1e-4, beta=0.0):
+        x0 = _f64(x0).reshape(-1, 3)
+        tets = np.ascontiguousarray(tets, dtype=np.uint32).reshape(-1, 4)
+        m = None if mass is None else _f64(mass)
+        b = self._ck(self._L.sbsb200_add_tet_body(self._h, x0.shape[0], _d(x0), None if m is None else _d(m),
+                                                  tets.shape[0], tets.ctypes.data_as(_u32p), young, poisson,
+                                                  alpha, beta))
+        self._nv[b] = x0.shape[0]
+        return b
+
+    def add_distance_constraints(self, b1, b2, pairs, alpha=1e-4, beta=0.0):
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        self._ck(self._L.sbsb200_add_distance_constraints(self._h, b1, b2, pairs.shape[0],
+                                                          pairs.ctypes.data_as(_u32p), alpha, beta))
+
+    def add_sdf_plane(self, normal, point, volume):
+        return self._ck(self._L.sbsb200_add_sdf_plane(self._h, _d(_f64(normal)), _d(_f64(point)),
+                                                      _d(_f64(volume).reshape(6))))
+
+    def add_sdf_sphere(self, centre, radius, volume):
+        return self._ck(self._L.sbsb200_add_sdf_sphere(self._h, _d(_f64(centre)), radius,
+                                                       _d(_f64(volume).reshape(6))))
+
+    def add_sdf_box(self, bmin, bmax, volume):
+        return self._ck(self._L.sbsb200_add_sdf_box(self._h, _d(_f64(bmin)), _d(_f64(bmax)),
+                                                    _d(_f64(volume).reshape(6))))
+
+    def finalize(self):
+        self._ck(self._L.sbsb200_finalize(self._h))
+
+    def constraint_count(self):
+        return self._ck(self._L.sbsb200_constraint_count(self._h))
+
+    def constraint_order(self):
+        n = self.constraint_count()
+        order = np.empty(n, np.uint32)
+        self._ck(self._L.sbsb200_get_constraint_order(self._h, order.ctypes.data_as(_u32p), n))
+        return order
+
+    def surface_map(self, body):
+        n = self._ck(self._L.sbsb200_get_surface_map(self._h, body, None, 0))
+        m = np.empty(max(n, 1), np.uint32)
+        self._ck(self._L.sbsb200_get_surface_map(self._h, body, m.ctypes.data_as(_u32p), n))
+        return m[:n]
+
+    def stats(self):
+        s = Stats()
+        self._ck(self._L.sbsb200_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def upload(self, body, x, v=None):
+        x = _f64(x)
+        vv = None if v is None else _f64(v)
+        self._ck(self._L.sbsb200_upload(self._h, body, _d(x), None if vv is None else _d(vv)))
+
+    def download(self, body):
+        n = self._nv[body]
+        x = np.empty((n, 3))
+        v = np.empty((n, 3))
+        self._ck(self._L.sbsb200_download(self._h, body, _d(x), _d(v)))
+        return x, v
+
+    def set_mass(self, body, vertex, mass):
+        self._ck(self._L.sbsb200_set_mass(self._h, body, vertex, mass))
+
+    def step(self, dt, substeps, iterations, detect_every_substep=False):
+        self._ck(self._L.sbsb200_step(self._h, dt, substeps, iterations,
+                                      DETECT_PER_SUBSTEP if detect_every_substep else DETECT_PER_FRAME))
+
+    def step_host(self, body, x_in, v_in, dt, substeps, iterations, detect_every_substep, x_out, v_out):
+        """x_in/v_in/x_out/v_out: C-contiguous float64 host arrays [nV, 3] (v_in may be None)."""
+        self._ck(self._L.sbsb200_step_host(self._h, body, _d(x_in), None if v_in is None else _d(v_in), dt,
+                                           substeps, iterations,
+                                           DETECT_PER_SUBSTEP if detect_every_substep else DETECT_PER_FRAME,
+                                           _d(x_out), _d(v_out)))
+
+    def synchronize(self):
+        self._ck(self._L.sbsb200_synchronize(self._h))
+
+    def contacts(self):
+        n = self._ck(self._L.sbsb200_get_contacts(self._h, 0, None, None, None, None, None))
+        body = np.empty(max(n, 1), np.int32)
+        vert = np.empty(max(n, 1), np.uint32)
+        sdf = np.empty(max(n, 1), np.int32)
+        pt = np.empty((max(n, 1), 3))
+        nr = np.empty((max(n, 1), 3))
+        self._ck(self._L.sbsb200_get_contacts(self._h, n, body.ctypes.data_as(_i32p), vert.ctypes.data_as(_u32p),
+                                              sdf.ctypes.data_as(_i32p), _d(pt), _d(nr)))
+        return body[:n], vert[:n], sdf[:n], pt[:n], nr[:n]

@@ -1,0 +1,1005 @@
+// libsbsb200.so — C ABI (include/sbs_b200.h) over the sm_100a XPBD kernels.
+//
+// There is no CPU path in this file: every entry point that computes goes through CUDA and
+// fails with SBSB200_ERR_CUDA when the device is unusable.
+#include "../../include/sbs_b200.h"
+
+#include "scene_build.h"
+#include "xpbd_kernels.cuh"
+#include "xpbd_persistent.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+using namespace sbsb200;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaError
+{
+    std::string msg;
+};
+
+#define CK(expr)                                                                                   \
+    do                                                                                             \
+    {                                                                                              \
+        cudaError_t const e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                                    \
+            throw CudaError{std::string(#expr) + ": " + cudaGetErrorString(e__)};                  \
+    } while (0)
+
+template <typename T>
+struct DevBuf
+{
+    T* p      = nullptr;
+    size_t n  = 0;
+    DevBuf()  = default;
+    DevBuf(DevBuf const&) = delete;
+    DevBuf& operator=(DevBuf const&) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        CK(cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1)));
+    }
+    void upload(std::vector<T> const& h, cudaStream_t st)
+    {
+        alloc(h.size());
+        if (!h.empty())
+            CK(cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, st));
+    }
+};
+
+struct EngineBase
+{
+    virtual ~EngineBase() = default;
+    virtual void build(sbsb200_ctx& c)                                                     = 0;
+    virtual void step(sbsb200_ctx& c, double dt, int substeps, int iterations, int detect) = 0;
+    virtual void upload(sbsb200_ctx& c, int body, double const* x, double const* v)        = 0;
+    virtual void download(sbsb200_ctx& c, int body, double* x, double* v)                  = 0;
+    virtual void set_mass(sbsb200_ctx& c, int64_t gv, double m)                             = 0;
+    virtual int64_t contacts(sbsb200_ctx& c, int64_t cap, int32_t* body, uint32_t* vertex,
+                             int32_t* sdf_body, double* point, double* normal)             = 0;
+    virtual void invalidate_graphs()                                                       = 0;
+};
+
+} // namespace
+
+struct sbsb200_ctx
+{
+    int device        = 0;
+    int precision     = SBSB200_FP32;
+    cudaStream_t stream = nullptr;
+    bool own_stream   = false;
+    std::string err;
+    HostScene scene;
+    bool finalized          = false;
+    int schedule_request    = SBSB200_SCHED_AUTO;
+    int schedule            = SBSB200_SCHED_GRAPH;
+    double collision_alpha  = 1e-8; // simulation_parameters.h:24
+    ColourClass green_cc, dist_cc;
+    RegionPlan plan;
+    std::vector<uint32_t> order; // exported serial order (insertion indices)
+    std::vector<int32_t> vertex_body;
+    std::unique_ptr<EngineBase> engine;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed            = false;
+    int64_t kernels       = 0;
+    int64_t frames        = 0;
+    int64_t last_contacts = 0;
+    int sm_count          = 0;
+    int64_t n_surface     = 0;
+    bool any_damping      = false;
+};
+
+namespace {
+
+// rounding-exact helpers: predict/commit must match the reference bit for bit in the fp64
+// build, so they are kept free of FMA contraction there (see k_predict / k_integrate).
+
+template <typename R>
+struct Engine final : EngineBase
+{
+    DeviceScene<R> d{};
+    DevBuf<Real4<R>> pos, prev, vel, tet_r0, tet_r1, tet_r2, materials, dist_p, surf_pos, contact_q, contact_n;
+    DevBuf<uint4> tet_v;
+    DevBuf<uint2> dist_v;
+    DevBuf<R> tet_lambda, dist_lambda;
+    DevBuf<uint32_t> surf_v, contact_v, contact_count;
+    DevBuf<int32_t> surf_body;
+    DevBuf<typename DeviceScene<R>::Sdf> sdf;
+    PersistentPlan<R> pp; // persistent schedule resources (may be inactive)
+    std::map<std::tuple<double, int, int, int>, cudaGraphExec_t> graphs;
+    std::map<std::tuple<double, int, int, int>, int64_t> graph_kernels;
+
+    ~Engine() override { invalidate_graphs(); }
+
+    void invalidate_graphs() override
+    {
+        for (auto& kv : graphs)
+            cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+        graph_kernels.clear();
+    }
+
+    void build(sbsb200_ctx& c) override
+    {
+        HostScene const& h = c.scene;
+        cudaStream_t st    = c.stream;
+        int64_t const V = h.n_vertices(), T = h.n_tets(), D = h.n_dist();
+
+        std::vector<Real4<R>> hpos(static_cast<size_t>(V)), hprev(static_cast<size_t>(V)),
+            hvel(static_cast<size_t>(V), Real4<R>{R(0), R(0), R(0), R(0)});
+        for (int64_t i = 0; i < V; ++i)
+        {
+            double const m  = h.mass[static_cast<size_t>(i)];
+            double const iw = m > 0. ? 1. / m : 0.; // particle.cpp:39-44
+            hpos[static_cast<size_t>(i)]  = {R(h.x0[3 * i]), R(h.x0[3 * i + 1]), R(h.x0[3 * i + 2]), R(iw)};
+            hprev[static_cast<size_t>(i)] = {R(h.x0[3 * i]), R(h.x0[3 * i + 1]), R(h.x0[3 * i + 2]), R(0)};
+        }
+        pos.upload(hpos, st);
+        prev.upload(hprev, st);
+        vel.upload(hvel, st);
+
+        // green constraints in schedule order
+        std::vector<uint4> hv(static_cast<size_t>(T));
+        std::vector<Real4<R>> r0(static_cast<size_t>(T)), r1(static_cast<size_t>(T)), r2(static_cast<size_t>(T));
+        for (int64_t p = 0; p < T; ++p)
+        {
+            uint32_t const t  = c.green_cc.order[static_cast<size_t>(p)];
+            uint32_t const* v = &h.tets[4 * static_cast<size_t>(t)];
+            hv[static_cast<size_t>(p)] = make_uint4(v[0], v[1], v[2], v[3]);
+            // Dm columns x0_1-x0_4, x0_2-x0_4, x0_3-x0_4 (green_constraint.cpp:38-41)
+            double m[9];
+            for (int r = 0; r < 3; ++r)
+                for (int col = 0; col < 3; ++col)
+                    m[3 * r + col] = h.x0[3 * static_cast<size_t>(v[col]) + r] - h.x0[3 * static_cast<size_t>(v[3]) + r];
+            double const det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                               m[2] * (m[3] * m[7] - m[4] * m[6]);
+            double const id = 1.0 / det;
+            double inv[9]   = {(m[4] * m[8] - m[5] * m[7]) * id, (m[2] * m[7] - m[1] * m[8]) * id,
+                               (m[1] * m[5] - m[2] * m[4]) * id, (m[5] * m[6] - m[3] * m[8]) * id,
+                               (m[0] * m[8] - m[2] * m[6]) * id, (m[2] * m[3] - m[0] * m[5]) * id,
+                               (m[3] * m[7] - m[4] * m[6]) * id, (m[1] * m[6] - m[0] * m[7]) * id,
+                               (m[0] * m[4] - m[1] * m[3]) * id};
+            double const V0 = det / 6.0; // :44
+            r0[static_cast<size_t>(p)] = {R(inv[0]), R(inv[1]), R(inv[2]), R(inv[3])};
+            r1[static_cast<size_t>(p)] = {R(inv[4]), R(inv[5]), R(inv[6]), R(inv[7])};
+            R matv;
+            int const mi = h.tet_material[t];
+            if (sizeof(R) == 4)
+            {
+                float f;
+                std::memcpy(&f, &mi, 4);
+                matv = R(f);
+            }
+            else
+                matv = R(mi);
+            r2[static_cast<size_t>(p)] = {R(inv[8]), R(V0), matv, R(0)};
+        }
+        tet_v.upload(hv, st);
+        tet_r0.upload(r0, st);
+        tet_r1.upload(r1, st);
+        tet_r2.upload(r2, st);
+        tet_lambda.alloc(static_cast<size_t>(T));
+        CK(cudaMemsetAsync(tet_lambda.p, 0, sizeof(R) * std::max<int64_t>(T, 1), st));
+        std::vector<Real4<R>> hm(h.materials.size());
+        for (size_t i = 0; i < hm.size(); ++i)
+            hm[i] = {R(h.materials[i].mu), R(h.materials[i].lambda), R(h.materials[i].alpha), R(h.materials[i].beta)};
+        materials.upload(hm, st);
+
+        // distance constraints in schedule order
+        std::vector<uint2> dv(static_cast<size_t>(D));
+        std::vector<Real4<R>> dp(static_cast<size_t>(D));
+        for (int64_t p = 0; p < D; ++p)
+        {
+            uint32_t const i = c.dist_cc.order[static_cast<size_t>(p)];
+            dv[static_cast<size_t>(p)] = make_uint2(h.dist_pairs[2 * static_cast<size_t>(i)], h.dist_pairs[2 * static_cast<size_t>(i) + 1]);
+            dp[static_cast<size_t>(p)] = {R(h.dist_rest[i]), R(h.dist_alpha[i]), R(h.dist_beta[i]), R(0)};
+        }
+        dist_v.upload(dv, st);
+        dist_p.upload(dp, st);
+        dist_lambda.alloc(static_cast<size_t>(D));
+        CK(cudaMemsetAsync(dist_lambda.p, 0, sizeof(R) * std::max<int64_t>(D, 1), st));
+
+        // surfaces + SDFs
+        std::vector<uint32_t> sv;
+        std::vector<int32_t> sb;
+        std::vector<typename DeviceScene<R>::Sdf> hs;
+        for (size_t b = 0; b < h.bodies.size(); ++b)
+        {
+            HostBody const& hb = h.bodies[b];
+            if (hb.kind == BodyKind::tet)
+                for (uint32_t lv : hb.surf_to_tet)
+                {
+                    sv.push_back(static_cast<uint32_t>(hb.v_offset + lv));
+                    sb.push_back(static_cast<int32_t>(b));
+                }
+            else
+            {
+                typename DeviceScene<R>::Sdf f{};
+                f.kind = static_cast<int32_t>(hb.sdf_kind);
+                f.body = static_cast<int32_t>(b);
+                for (int k = 0; k < 3; ++k)
+                {
+                    f.a[k] = R(hb.a[k]);
+                    f.b[k] = R(hb.b[k]);
+                }
+                f.r = R(hb.r);
+                hs.push_back(f);
+            }
+        }
+        int64_t const Vs = static_cast<int64_t>(sv.size());
+        surf_v.upload(sv, st);
+        surf_body.upload(sb, st);
+        surf_pos.alloc(static_cast<size_t>(Vs));
+        sdf.upload(hs, st);
+        int64_t const cap = Vs * static_cast<int64_t>(hs.size());
+        contact_v.alloc(static_cast<size_t>(cap));
+        contact_q.alloc(static_cast<size_t>(cap));
+        contact_n.alloc(static_cast<size_t>(cap));
+        contact_count.alloc(1);
+        CK(cudaMemsetAsync(contact_count.p, 0, sizeof(uint32_t), st));
+
+        d.n_vertices      = V;
+        d.pos             = pos.p;
+        d.prev            = prev.p;
+        d.vel             = vel.p;
+        d.n_tets          = T;
+        d.tet_v           = tet_v.p;
+        d.tet_r0          = tet_r0.p;
+        d.tet_r1          = tet_r1.p;
+        d.tet_r2          = tet_r2.p;
+        d.tet_lambda      = tet_lambda.p;
+        d.materials       = materials.p;
+        d.n_dist          = D;
+        d.dist_v          = dist_v.p;
+        d.dist_p          = dist_p.p;
+        d.dist_lambda     = dist_lambda.p;
+        d.n_surface       = Vs;
+        d.surf_v          = surf_v.p;
+        d.surf_body       = surf_body.p;
+        d.surf_pos        = surf_pos.p;
+        d.n_sdf           = static_cast<int32_t>(hs.size());
+        d.sdf             = sdf.p;
+        d.contact_cap     = cap;
+        d.contact_v       = contact_v.p;
+        d.contact_q       = contact_q.p;
+        d.contact_n       = contact_n.p;
+        d.contact_count   = contact_count.p;
+        d.collision_alpha = R(c.collision_alpha);
+        c.n_surface       = Vs;
+
+        if (Vs > 0)
+        {
+            k_surface_gather<R><<<static_cast<unsigned>((Vs + 255) / 256), 256, 0, st>>>(d);
+            ++c.kernels;
+        }
+        if (c.schedule == SBSB200_SCHED_PERSISTENT)
+            pp.build(c.scene, c.green_cc, c.plan, d, st, c.sm_count);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+    }
+
+    // enqueue one frame; returns number of kernels enqueued
+    int64_t enqueue(sbsb200_ctx& c, double dt_frame, int substeps, int iterations, int detect, cudaStream_t st)
+    {
+        int64_t launched     = 0;
+        R const dt           = R(dt_frame / static_cast<double>(substeps)); // timestep.cpp:22
+        int64_t const V      = d.n_vertices;
+        unsigned const gridV = static_cast<unsigned>((V + 255) / 256);
+        bool const collide   = d.n_sdf > 0 && d.n_surface > 0;
+        unsigned const gridS = static_cast<unsigned>((d.n_surface + 255) / 256);
+        unsigned const gridC = static_cast<unsigned>((d.contact_cap + 255) / 256);
+        d.collision_alpha    = R(c.collision_alpha);
+
+        auto detect_now = [&] {
+            if (!collide)
+                return;
+            CK(cudaMemsetAsync(d.contact_count, 0, sizeof(uint32_t), st));
+            k_detect_all<R><<<gridS, 256, 0, st>>>(d);
+            ++launched;
+        };
+        if (detect == SBSB200_DETECT_PER_FRAME)
+            detect_now(); // timestep.cpp:29-30
+        for (int s = 0; s < substeps; ++s)
+        {
+            if (detect == SBSB200_DETECT_PER_SUBSTEP)
+                detect_now();
+            if (c.schedule == SBSB200_SCHED_PERSISTENT)
+            {
+                launched += pp.substep(d, dt, iterations, collide, c.any_damping, st);
+            }
+            else
+            {
+                if (V > 0)
+                {
+                    k_predict<R><<<gridV, 256, 0, st>>>(d, dt);
+                    ++launched;
+                }
+                for (int k = 0; k < iterations; ++k)
+                {
+                    int const first = k == 0;
+                    if (collide)
+                    { // gauss_seidel_solver.cpp:28-31
+                        k_project_collision<R><<<gridC, 256, 0, st>>>(d, dt, first);
+                        ++launched;
+                    }
+                    // gauss_seidel_solver.cpp:32-35 in the exported colour order
+                    for (int32_t col = 0; col < c.green_cc.n_colours; ++col)
+                    {
+                        int64_t const b = c.green_cc.offsets[col], e = c.green_cc.offsets[col + 1];
+                        if (e == b)
+                            continue;
+                        unsigned const g = static_cast<unsigned>((e - b + 127) / 128);
+                        if (c.any_damping)
+                            k_project_green<R, true><<<g, 128, 0, st>>>(d, b, static_cast<int32_t>(e - b), dt, first);
+                        else
+                            k_project_green<R, false><<<g, 128, 0, st>>>(d, b, static_cast<int32_t>(e - b), dt, first);
+                        ++launched;
+                    }
+                    for (int32_t col = 0; col < c.dist_cc.n_colours; ++col)
+                    {
+                        int64_t const b = c.dist_cc.offsets[col], e = c.dist_cc.offsets[col + 1];
+                        if (e == b)
+                            continue;
+                        k_project_distance<R><<<static_cast<unsigned>((e - b + 127) / 128), 128, 0, st>>>(
+                            d, b, static_cast<int32_t>(e - b), dt, first);
+                        ++launched;
+                    }
+                }
+                if (V > 0)
+                {
+                    k_integrate<R><<<gridV, 256, 0, st>>>(d, dt);
+                    ++launched;
+                }
+            }
+            if (detect == SBSB200_DETECT_PER_SUBSTEP && d.n_surface > 0)
+            {
+                k_surface_gather<R><<<gridS, 256, 0, st>>>(d);
+                ++launched;
+            }
+        }
+        if (detect == SBSB200_DETECT_PER_FRAME && d.n_surface > 0)
+        { // timestep.cpp:60-66
+            k_surface_gather<R><<<gridS, 256, 0, st>>>(d);
+            ++launched;
+        }
+        CK(cudaGetLastError());
+        return launched;
+    }
+
+    void step(sbsb200_ctx& c, double dt, int substeps, int iterations, int detect) override
+    {
+        cudaStream_t st = c.stream;
+        CK(cudaEventRecord(c.ev0, st));
+        auto const key = std::make_tuple(dt, substeps, iterations, detect);
+        auto it        = graphs.find(key);
+        if (it == graphs.end())
+        {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int64_t n = 0;
+            try
+            {
+                n = enqueue(c, dt, substeps, iterations, detect, st);
+            }
+            catch (...)
+            {
+                cudaStreamEndCapture(st, &graph);
+                if (graph)
+                    cudaGraphDestroy(graph);
+                throw;
+            }
+            CK(cudaStreamEndCapture(st, &graph));
+            cudaGraphExec_t exec = nullptr;
+            cudaError_t const e  = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess)
+                throw CudaError{std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)};
+            it                 = graphs.emplace(key, exec).first;
+            graph_kernels[key] = n;
+        }
+        CK(cudaGraphLaunch(it->second, st));
+        c.kernels += graph_kernels[key];
+        CK(cudaEventRecord(c.ev1, st));
+        c.timed = true;
+    }
+
+    void upload(sbsb200_ctx& c, int body, double const* x, double const* v) override
+    {
+        HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
+        int64_t const n    = hb.n_vertices;
+        std::vector<Real4<R>> hp(static_cast<size_t>(n)), hx(static_cast<size_t>(n)), hv(static_cast<size_t>(n));
+        // keep inverse masses: read them back
+        CK(cudaMemcpyAsync(hp.data(), pos.p + hb.v_offset, sizeof(Real4<R>) * n, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        for (int64_t i = 0; i < n; ++i)
+        {
+            hp[static_cast<size_t>(i)].x = R(x[3 * i]);
+            hp[static_cast<size_t>(i)].y = R(x[3 * i + 1]);
+            hp[static_cast<size_t>(i)].z = R(x[3 * i + 2]);
+            hx[static_cast<size_t>(i)]   = {R(x[3 * i]), R(x[3 * i + 1]), R(x[3 * i + 2]), R(0)};
+            hv[static_cast<size_t>(i)]   = v ? Real4<R>{R(v[3 * i]), R(v[3 * i + 1]), R(v[3 * i + 2]), R(0)}
+                                             : Real4<R>{R(0), R(0), R(0), R(0)};
+        }
+        CK(cudaMemcpyAsync(pos.p + hb.v_offset, hp.data(), sizeof(Real4<R>) * n, cudaMemcpyHostToDevice, c.stream));
+        CK(cudaMemcpyAsync(prev.p + hb.v_offset, hx.data(), sizeof(Real4<R>) * n, cudaMemcpyHostToDevice, c.stream));
+        CK(cudaMemcpyAsync(vel.p + hb.v_offset, hv.data(), sizeof(Real4<R>) * n, cudaMemcpyHostToDevice, c.stream));
+        if (d.n_surface > 0)
+        {
+            k_surface_gather<R><<<static_cast<unsigned>((d.n_surface + 255) / 256), 256, 0, c.stream>>>(d);
+            ++c.kernels;
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c.stream));
+    }
+
+    void download(sbsb200_ctx& c, int body, double* x, double* v) override
+    {
+        HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
+        int64_t const n    = hb.n_vertices;
+        std::vector<Real4<R>> hx(static_cast<size_t>(n)), hv(static_cast<size_t>(n));
+        if (x)
+            CK(cudaMemcpyAsync(hx.data(), prev.p + hb.v_offset, sizeof(Real4<R>) * n, cudaMemcpyDeviceToHost, c.stream));
+        if (v)
+            CK(cudaMemcpyAsync(hv.data(), vel.p + hb.v_offset, sizeof(Real4<R>) * n, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        for (int64_t i = 0; i < n; ++i)
+        {
+            if (x)
+            {
+                x[3 * i]     = double(hx[static_cast<size_t>(i)].x);
+                x[3 * i + 1] = double(hx[static_cast<size_t>(i)].y);
+                x[3 * i + 2] = double(hx[static_cast<size_t>(i)].z);
+            }
+            if (v)
+            {
+                v[3 * i]     = double(hv[static_cast<size_t>(i)].x);
+                v[3 * i + 1] = double(hv[static_cast<size_t>(i)].y);
+                v[3 * i + 2] = double(hv[static_cast<size_t>(i)].z);
+            }
+        }
+    }
+
+    void set_mass(sbsb200_ctx& c, int64_t gv, double m) override
+    {
+        R const iw = R(m > 0. ? 1. / m : 0.);
+        CK(cudaMemcpyAsync(&pos.p[gv].w, &iw, sizeof(R), cudaMemcpyHostToDevice, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+    }
+
+    int64_t contacts(sbsb200_ctx& c, int64_t cap, int32_t* body, uint32_t* vertex, int32_t* sdf_body,
+                     double* point, double* normal) override
+    {
+        uint32_t n = 0;
+        CK(cudaMemcpyAsync(&n, contact_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        n                 = static_cast<uint32_t>(std::min<int64_t>(n, d.contact_cap));
+        c.last_contacts   = n;
+        int64_t const m   = std::min<int64_t>(n, cap);
+        if (m <= 0 || !vertex)
+            return n;
+        std::vector<uint32_t> hv(static_cast<size_t>(m));
+        std::vector<Real4<R>> hq(static_cast<size_t>(m)), hn(static_cast<size_t>(m));
+        CK(cudaMemcpyAsync(hv.data(), contact_v.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(hq.data(), contact_q.p, sizeof(Real4<R>) * m, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(hn.data(), contact_n.p, sizeof(Real4<R>) * m, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        for (int64_t i = 0; i < m; ++i)
+        {
+            uint32_t const gv = hv[static_cast<size_t>(i)] & 0x7fffffffu;
+            int32_t const b   = c.vertex_body[gv];
+            if (body)
+                body[i] = b;
+            vertex[i] = static_cast<uint32_t>(gv - c.scene.bodies[static_cast<size_t>(b)].v_offset);
+            if (sdf_body)
+            {
+                if (sizeof(R) == 4)
+                {
+                    float f = float(hn[static_cast<size_t>(i)].w);
+                    int32_t k;
+                    std::memcpy(&k, &f, 4);
+                    sdf_body[i] = k;
+                }
+                else
+                    sdf_body[i] = static_cast<int32_t>(hn[static_cast<size_t>(i)].w);
+            }
+            if (point)
+            {
+                point[3 * i]     = double(hq[static_cast<size_t>(i)].x);
+                point[3 * i + 1] = double(hq[static_cast<size_t>(i)].y);
+                point[3 * i + 2] = double(hq[static_cast<size_t>(i)].z);
+            }
+            if (normal)
+            {
+                normal[3 * i]     = double(hn[static_cast<size_t>(i)].x);
+                normal[3 * i + 1] = double(hn[static_cast<size_t>(i)].y);
+                normal[3 * i + 2] = double(hn[static_cast<size_t>(i)].z);
+            }
+        }
+        return n;
+    }
+};
+
+int fail(sbsb200_ctx* c, int code, std::string const& msg)
+{
+    if (c)
+        c->err = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+template <typename F>
+int guarded(sbsb200_ctx* c, F&& f)
+{
+    try
+    {
+        return f();
+    }
+    catch (CudaError const& e)
+    {
+        return fail(c, SBSB200_ERR_CUDA, e.msg);
+    }
+    catch (std::exception const& e)
+    {
+        return fail(c, SBSB200_ERR_INVALID, e.what());
+    }
+}
+
+bool is_tet_body(sbsb200_ctx const* c, int b)
+{
+    return b >= 0 && b < static_cast<int>(c->scene.bodies.size()) &&
+           c->scene.bodies[static_cast<size_t>(b)].kind == BodyKind::tet;
+}
+
+int add_sdf(sbsb200_ctx* c, SdfKind kind, double const a[3], double const b[3], double r, double const volume[6])
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "scene already finalized");
+    if (!a || !volume)
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    HostBody hb;
+    hb.kind     = BodyKind::sdf;
+    hb.sdf_kind = kind;
+    std::memcpy(hb.a, a, sizeof hb.a);
+    if (b)
+        std::memcpy(hb.b, b, sizeof hb.b);
+    hb.r = r;
+    std::memcpy(hb.volume, volume, sizeof hb.volume);
+    c->scene.bodies.push_back(hb);
+    return static_cast<int>(c->scene.bodies.size()) - 1;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int sbsb200_create(int device, int precision, sbsb200_ctx** out)
+{
+    if (!out || (precision != SBSB200_FP32 && precision != SBSB200_FP64))
+        return fail(nullptr, SBSB200_ERR_INVALID, "bad arguments to sbsb200_create");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count)
+        return fail(nullptr, SBSB200_ERR_CUDA,
+                    std::string("no usable CUDA device (there is no CPU fallback): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range"));
+    cudaDeviceProp prop{};
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, SBSB200_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, SBSB200_ERR_CUDA,
+                    "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                        "; this library contains sm_100a code only");
+    auto* c      = new sbsb200_ctx();
+    c->device    = device;
+    c->precision = precision;
+    c->sm_count  = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess)
+    {
+        delete c;
+        return fail(nullptr, SBSB200_ERR_CUDA, "stream/event creation failed");
+    }
+    c->own_stream = true;
+    *out          = c;
+    return SBSB200_OK;
+}
+
+void sbsb200_destroy(sbsb200_ctx* c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    if (c->stream)
+        cudaStreamSynchronize(c->stream);
+    c->engine.reset();
+    if (c->ev0)
+        cudaEventDestroy(c->ev0);
+    if (c->ev1)
+        cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream)
+        cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* sbsb200_last_error(const sbsb200_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int sbsb200_set_stream(sbsb200_ctx* c, void* cuda_stream)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "set_stream must precede finalize");
+    if (c->own_stream && c->stream)
+        cudaStreamDestroy(c->stream);
+    c->stream     = static_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
+    return SBSB200_OK;
+}
+
+int sbsb200_set_schedule(sbsb200_ctx* c, int schedule)
+{
+    if (!c || schedule < SBSB200_SCHED_AUTO || schedule > SBSB200_SCHED_PERSISTENT)
+        return fail(c, SBSB200_ERR_INVALID, "bad schedule");
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "set_schedule must precede finalize");
+    c->schedule_request = schedule;
+    return SBSB200_OK;
+}
+
+int sbsb200_set_collision_compliance(sbsb200_ctx* c, double alpha)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    c->collision_alpha = alpha;
+    if (c->engine)
+        c->engine->invalidate_graphs();
+    return SBSB200_OK;
+}
+
+int sbsb200_add_tet_body(sbsb200_ctx* c, int64_t nV, const double* x0, const double* mass, int64_t nT,
+                         const uint32_t* tets, double E, double nu, double alpha, double beta)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "scene already finalized");
+    if (nV < 0 || nT < 0 || (nV > 0 && !x0) || (nT > 0 && !tets))
+        return fail(c, SBSB200_ERR_INVALID, "null or negative-sized geometry");
+    HostScene& h = c->scene;
+    if (h.n_vertices() + nV >= (int64_t{1} << 31) || static_cast<int64_t>(h.n_constraints) + nT >= (int64_t{1} << 32))
+        return fail(c, SBSB200_ERR_CAPACITY, "scene too large for 32-bit indices");
+    for (int64_t i = 0; i < 4 * nT; ++i)
+        if (tets[i] >= static_cast<uint64_t>(nV))
+            return fail(c, SBSB200_ERR_INVALID, "tet vertex index out of range");
+    HostBody hb;
+    hb.kind       = BodyKind::tet;
+    hb.v_offset   = h.n_vertices();
+    hb.n_vertices = nV;
+    hb.t_offset   = h.n_tets();
+    hb.n_tets     = nT;
+    extract_boundary(nV, nT, tets, hb.surf_to_tet, nullptr);
+    h.x0.insert(h.x0.end(), x0, x0 + 3 * nV);
+    if (mass)
+        h.mass.insert(h.mass.end(), mass, mass + nV);
+    else
+        h.mass.insert(h.mass.end(), static_cast<size_t>(nV), 1.0); // particle.cpp:7
+    Material const m{E / (2. * (1 + nu)), (E * nu) / ((1 + nu) * (1 - 2 * nu)), alpha, beta}; // :45-46
+    size_t mi = 0;
+    while (mi < h.materials.size() && !(h.materials[mi] == m))
+        ++mi;
+    if (mi == h.materials.size())
+    {
+        if (mi >= 65535)
+            return fail(c, SBSB200_ERR_CAPACITY, "too many distinct materials");
+        h.materials.push_back(m);
+    }
+    for (int64_t t = 0; t < nT; ++t)
+    {
+        for (int a = 0; a < 4; ++a)
+            h.tets.push_back(static_cast<uint32_t>(hb.v_offset + tets[4 * t + a]));
+        h.tet_insertion.push_back(h.n_constraints++);
+        h.tet_material.push_back(static_cast<uint16_t>(mi));
+    }
+    h.bodies.push_back(std::move(hb));
+    return static_cast<int>(h.bodies.size()) - 1;
+}
+
+int sbsb200_add_distance_constraints(sbsb200_ctx* c, int b1, int b2, int64_t n, const uint32_t* pairs,
+                                     double alpha, double beta)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "scene already finalized");
+    if (!is_tet_body(c, b1) || !is_tet_body(c, b2) || n < 0 || (n > 0 && !pairs))
+        return fail(c, SBSB200_ERR_INVALID, "bad body index or null pairs");
+    HostScene& h        = c->scene;
+    HostBody const& hb1 = h.bodies[static_cast<size_t>(b1)];
+    HostBody const& hb2 = h.bodies[static_cast<size_t>(b2)];
+    for (int64_t i = 0; i < n; ++i)
+        if (pairs[2 * i] >= static_cast<uint64_t>(hb1.n_vertices) || pairs[2 * i + 1] >= static_cast<uint64_t>(hb2.n_vertices))
+            return fail(c, SBSB200_ERR_INVALID, "distance constraint vertex out of range");
+    for (int64_t i = 0; i < n; ++i)
+    {
+        uint32_t const g1 = static_cast<uint32_t>(hb1.v_offset + pairs[2 * i]);
+        uint32_t const g2 = static_cast<uint32_t>(hb2.v_offset + pairs[2 * i + 1]);
+        double s          = 0;
+        for (int k = 0; k < 3; ++k)
+        {
+            double const dlt = h.x0[3 * static_cast<size_t>(g1) + k] - h.x0[3 * static_cast<size_t>(g2) + k];
+            s += dlt * dlt;
+        }
+        h.dist_pairs.push_back(g1);
+        h.dist_pairs.push_back(g2);
+        h.dist_rest.push_back(std::sqrt(s)); // distance_constraint.cpp:21
+        h.dist_alpha.push_back(alpha);
+        h.dist_beta.push_back(beta);
+        h.dist_insertion.push_back(h.n_constraints++);
+    }
+    return SBSB200_OK;
+}
+
+int sbsb200_add_sdf_plane(sbsb200_ctx* c, const double n[3], const double pt[3], const double volume[6])
+{
+    if (!n || !pt)
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    // Eigen::Hyperplane(n, e): offset = -n.e (sdf_model.cpp:56-61 uses signedDistance / normal)
+    return add_sdf(c, SdfKind::plane, n, nullptr, -(n[0] * pt[0] + n[1] * pt[1] + n[2] * pt[2]), volume);
+}
+int sbsb200_add_sdf_sphere(sbsb200_ctx* c, const double centre[3], double radius, const double volume[6])
+{
+    return add_sdf(c, SdfKind::sphere, centre, nullptr, radius, volume);
+}
+int sbsb200_add_sdf_box(sbsb200_ctx* c, const double bmin[3], const double bmax[3], const double volume[6])
+{
+    if (!bmax)
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    return add_sdf(c, SdfKind::box, bmin, bmax, 0., volume);
+}
+
+int sbsb200_finalize(sbsb200_ctx* c)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "scene already finalized");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        HostScene& h    = c->scene;
+        int64_t const V = h.n_vertices(), T = h.n_tets(), D = h.n_dist();
+        c->vertex_body.assign(static_cast<size_t>(V), -1);
+        int64_t s_off = 0;
+        for (size_t b = 0; b < h.bodies.size(); ++b)
+            if (h.bodies[b].kind == BodyKind::tet)
+            {
+                h.bodies[b].s_offset = s_off;
+                s_off += static_cast<int64_t>(h.bodies[b].surf_to_tet.size());
+                for (int64_t i = 0; i < h.bodies[b].n_vertices; ++i)
+                    c->vertex_body[static_cast<size_t>(h.bodies[b].v_offset + i)] = static_cast<int32_t>(b);
+            }
+        c->any_damping = false;
+        for (Material const& m : h.materials)
+            c->any_damping = c->any_damping || m.beta != 0.;
+
+        std::vector<uint64_t> tkeys, dkeys;
+        morton_keys(T, 4, h.tets.data(), h.x0.data(), V, tkeys);
+        morton_keys(D, 2, h.dist_pairs.data(), h.x0.data(), V, dkeys);
+
+        // schedule choice
+        c->schedule = c->schedule_request == SBSB200_SCHED_AUTO ? SBSB200_SCHED_GRAPH : c->schedule_request;
+        if (c->schedule == SBSB200_SCHED_PERSISTENT && (D > 0 || T == 0))
+            c->schedule = SBSB200_SCHED_GRAPH; // distance constraints are not region-partitioned
+
+        int32_t const* region = nullptr;
+        if (c->schedule == SBSB200_SCHED_PERSISTENT)
+        {
+            plan_regions(h, tkeys, PersistentPlan<float>::regions_for(c->sm_count, T), c->plan);
+            region = c->plan.tet_region.data();
+        }
+        if (!colour_constraints(V, T, 4, h.tets.data(), tkeys.data(), region, 256, c->green_cc))
+            return fail(c, SBSB200_ERR_CAPACITY, "more than 256 colours needed for the tet mesh");
+        if (!colour_constraints(V, D, 2, h.dist_pairs.data(), dkeys.data(), nullptr, 256, c->dist_cc))
+            return fail(c, SBSB200_ERR_CAPACITY, "more than 256 colours needed for the distance constraints");
+
+        // exported serial order: green colours, then distance colours
+        c->order.clear();
+        c->order.reserve(static_cast<size_t>(T + D));
+        for (uint32_t t : c->green_cc.order)
+            c->order.push_back(h.tet_insertion[t]);
+        for (uint32_t i : c->dist_cc.order)
+            c->order.push_back(h.dist_insertion[i]);
+
+        if (c->precision == SBSB200_FP32)
+            c->engine.reset(new Engine<float>());
+        else
+            c->engine.reset(new Engine<double>());
+        c->engine->build(*c);
+        c->finalized = true;
+        return SBSB200_OK;
+    });
+}
+
+int64_t sbsb200_constraint_count(const sbsb200_ctx* c) { return c ? static_cast<int64_t>(c->scene.n_constraints) : static_cast<int64_t>(SBSB200_ERR_INVALID); }
+
+int sbsb200_get_constraint_order(const sbsb200_ctx* c, uint32_t* order, int64_t n)
+{
+    if (!c || !order)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized || n != static_cast<int64_t>(c->order.size()))
+        return SBSB200_ERR_STATE;
+    std::memcpy(order, c->order.data(), sizeof(uint32_t) * c->order.size());
+    return SBSB200_OK;
+}
+
+int64_t sbsb200_get_surface_map(const sbsb200_ctx* c, int body, uint32_t* map, int64_t cap)
+{
+    if (!c || !is_tet_body(c, body))
+        return SBSB200_ERR_INVALID;
+    auto const& m = c->scene.bodies[static_cast<size_t>(body)].surf_to_tet;
+    if (map)
+        std::memcpy(map, m.data(), sizeof(uint32_t) * static_cast<size_t>(std::min<int64_t>(cap, static_cast<int64_t>(m.size()))));
+    return static_cast<int64_t>(m.size());
+}
+
+int sbsb200_get_stats(const sbsb200_ctx* cc, sbsb200_stats* out)
+{
+    if (!cc || !out)
+        return SBSB200_ERR_INVALID;
+    auto* c = const_cast<sbsb200_ctx*>(cc);
+    std::memset(out, 0, sizeof *out);
+    out->n_bodies = static_cast<int32_t>(c->scene.bodies.size());
+    for (auto const& b : c->scene.bodies)
+        out->n_sdfs += b.kind == BodyKind::sdf;
+    out->n_vertices           = c->scene.n_vertices();
+    out->n_tets               = c->scene.n_tets();
+    out->n_distance           = c->scene.n_dist();
+    out->n_surface_vertices   = c->n_surface;
+    out->n_green_colours      = c->green_cc.n_colours;
+    out->n_distance_colours   = c->dist_cc.n_colours;
+    out->schedule             = c->schedule;
+    out->n_regions            = c->plan.n_regions;
+    out->n_interface_vertices = c->plan.n_interface;
+    out->kernels_launched     = c->kernels;
+    out->frames               = c->frames;
+    out->last_contact_count   = c->last_contacts;
+    if (c->timed)
+    {
+        cudaSetDevice(c->device);
+        float ms = 0.f;
+        if (cudaEventSynchronize(c->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+            out->last_step_ms = ms;
+    }
+    return SBSB200_OK;
+}
+
+int sbsb200_upload(sbsb200_ctx* c, int body, const double* x, const double* v)
+{
+    if (!c || !x)
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "upload before finalize");
+    if (!is_tet_body(c, body))
+        return fail(c, SBSB200_ERR_INVALID, "not a tetrahedral body");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->upload(*c, body, x, v);
+        return SBSB200_OK;
+    });
+}
+
+int sbsb200_download(sbsb200_ctx* c, int body, double* x, double* v)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "download before finalize");
+    if (!is_tet_body(c, body))
+        return fail(c, SBSB200_ERR_INVALID, "not a tetrahedral body");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->download(*c, body, x, v);
+        return SBSB200_OK;
+    });
+}
+
+int sbsb200_set_mass(sbsb200_ctx* c, int body, int64_t vertex, double mass)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (!is_tet_body(c, body) || vertex < 0 || vertex >= c->scene.bodies[static_cast<size_t>(body)].n_vertices)
+        return fail(c, SBSB200_ERR_INVALID, "bad body or vertex");
+    int64_t const gv = c->scene.bodies[static_cast<size_t>(body)].v_offset + vertex;
+    c->scene.mass[static_cast<size_t>(gv)] = mass;
+    if (!c->finalized)
+        return SBSB200_OK;
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->set_mass(*c, gv, mass);
+        return SBSB200_OK;
+    });
+}
+
+int sbsb200_step(sbsb200_ctx* c, double dt, int substeps, int iterations, int detect_mode)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "step before finalize");
+    if (!(dt > 0.) || substeps <= 0 || iterations < 0 ||
+        (detect_mode != SBSB200_DETECT_PER_FRAME && detect_mode != SBSB200_DETECT_PER_SUBSTEP))
+        return fail(c, SBSB200_ERR_INVALID, "bad step arguments");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->step(*c, dt, substeps, iterations, detect_mode);
+        ++c->frames;
+        return SBSB200_OK;
+    });
+}
+
+int sbsb200_step_host(sbsb200_ctx* c, int body, const double* x_in, const double* v_in, double dt, int substeps,
+                      int iterations, int detect_mode, double* x_out, double* v_out)
+{
+    int rc = sbsb200_upload(c, body, x_in, v_in);
+    if (rc)
+        return rc;
+    rc = sbsb200_step(c, dt, substeps, iterations, detect_mode);
+    if (rc)
+        return rc;
+    return sbsb200_download(c, body, x_out, v_out);
+}
+
+int sbsb200_synchronize(sbsb200_ctx* c)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        return SBSB200_OK;
+    });
+}
+
+int64_t sbsb200_get_contacts(sbsb200_ctx* c, int64_t cap, int32_t* body, uint32_t* vertex, int32_t* sdf_body,
+                             double* point, double* normal)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "get_contacts before finalize");
+    int64_t n = 0;
+    int const rc = guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        n = c->engine->contacts(*c, cap, body, vertex, sdf_body, point, normal);
+        return SBSB200_OK;
+    });
+    return rc ? rc : n;
+}
+
+} // extern "C"

@@ -1,0 +1,107 @@
+// Host-side scene compilation for the B200 XPBD path: boundary extraction, graph colouring,
+// spatial ordering / region partition.  Pure C++ (no CUDA), so it is unit-testable on CPU.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace sbsb200 {
+
+struct Material
+{
+    double mu, lambda, alpha, beta; // green_constraint.cpp:45-46 + constraint_t alpha/beta
+    bool operator==(Material const& o) const
+    {
+        return mu == o.mu && lambda == o.lambda && alpha == o.alpha && beta == o.beta;
+    }
+};
+
+enum class BodyKind : int { tet = 0, sdf = 1 };
+enum class SdfKind : int { plane = 0, sphere = 1, box = 2 };
+
+struct HostBody
+{
+    BodyKind kind = BodyKind::tet;
+    // tet body
+    int64_t v_offset = 0, n_vertices = 0;
+    int64_t t_offset = 0, n_tets = 0;       // range in HostScene::tets (insertion order)
+    int64_t s_offset = 0;                   // range in the global surface-vertex list
+    std::vector<uint32_t> surf_to_tet;      // body-local tet-mesh vertex of surface vertex i
+    // sdf body
+    SdfKind sdf_kind = SdfKind::plane;
+    double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, r = 0; // plane: a=n, r=offset; sphere: a=c, r; box: a=min, b=max
+    double volume[6] = {0, 0, 0, 0, 0, 0};
+};
+
+struct HostScene
+{
+    std::vector<HostBody> bodies;
+    std::vector<double> x0;   // 3*V rest positions (global vertex order = bodies concatenated)
+    std::vector<double> mass; // V
+    // green constraints, insertion order
+    std::vector<uint32_t> tets;          // 4*T global vertex ids
+    std::vector<uint32_t> tet_insertion; // T: index in simulation_t::constraints_
+    std::vector<uint16_t> tet_material;  // T
+    std::vector<Material> materials;
+    // distance constraints, insertion order
+    std::vector<uint32_t> dist_pairs;     // 2*D global vertex ids
+    std::vector<double> dist_rest;        // D
+    std::vector<double> dist_alpha, dist_beta;
+    std::vector<uint32_t> dist_insertion; // D
+    uint32_t n_constraints = 0;           // running insertion counter
+
+    int64_t n_vertices() const { return static_cast<int64_t>(mass.size()); }
+    int64_t n_tets() const { return static_cast<int64_t>(tet_insertion.size()); }
+    int64_t n_dist() const { return static_cast<int64_t>(dist_insertion.size()); }
+};
+
+// Surface of a tet mesh in the reference's numbering: boundary triangles are those with a
+// number of incident tets != 2, visited in first-insertion order of the triangle; surface
+// vertices are numbered in first-seen order (tetrahedral_mesh_boundary.cpp:84-119).
+void extract_boundary(int64_t n_vertices, int64_t n_tets, uint32_t const* tets,
+                      std::vector<uint32_t>& surf_to_tet, std::vector<uint32_t>* triangles);
+
+struct ColourClass
+{
+    int32_t n_colours = 0;
+    std::vector<uint32_t> order;   // sorted position -> constraint index (insertion-order index within its type)
+    std::vector<int64_t> offsets;  // n_colours+1 prefix offsets into `order`
+};
+
+// Vertex-disjoint greedy colouring of k-vertex constraints (k = 4 tets, k = 2 edges), then a
+// stable sort by (colour, region, spatial key).  region may be null.
+// Returns false if more than max_colours would be needed.
+bool colour_constraints(int64_t n_vertices, int64_t n, int k, uint32_t const* verts,
+                        uint64_t const* spatial_key, int32_t const* region, int max_colours,
+                        ColourClass& out);
+
+// 30-bit Morton key per constraint from the centroid of its rest positions.
+void morton_keys(int64_t n, int k, uint32_t const* verts, double const* x0, int64_t n_vertices,
+                 std::vector<uint64_t>& keys);
+
+// Region partition for the persistent schedule.  Tets are split into `n_regions` spatially
+// compact, equal-count parts (contiguous ranges of the Morton order).  A vertex is interior
+// to region r when every incident tet (and no other constraint) lies in r; otherwise it is
+// an interface vertex and lives in global memory.
+struct RegionPlan
+{
+    int32_t n_regions = 0;
+    std::vector<int32_t> tet_region;        // T (insertion order)
+    std::vector<int32_t> vertex_region;     // V: owning region of interior vertex, or -1 (interface / untouched)
+    std::vector<uint32_t> vertex_slot;      // V: slot in the owning region's shared-memory array
+    std::vector<int64_t> region_vtx_offsets;// R+1 into region_vtx
+    std::vector<uint32_t> region_vtx;       // interior vertices grouped by region (slot order)
+    std::vector<int32_t> nbr_offsets;       // R+1 into nbr
+    std::vector<int32_t> nbr;               // neighbour regions (share >= 1 interface vertex)
+    int64_t n_interface = 0;
+    int64_t max_region_vertices = 0;
+};
+
+void plan_regions(HostScene const& scene, std::vector<uint64_t> const& tet_keys, int32_t n_regions,
+                  RegionPlan& plan);
+
+// Validation helper: true when no two constraints of the same colour share a vertex.
+bool colouring_is_valid(int64_t n_vertices, int k, uint32_t const* verts, ColourClass const& cc);
+
+} // namespace sbsb200

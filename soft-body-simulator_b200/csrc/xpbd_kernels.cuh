@@ -1,0 +1,397 @@
+// Kernels of the "graph" schedule: one launch per stage / colour, thread per work item.
+// (The persistent, region-resident schedule lives in xpbd_persistent.cuh.)
+#pragma once
+
+#include "xpbd_math.cuh"
+
+namespace sbsb200 {
+
+// Device view of the scene.  Everything is SoA of 16-byte (fp32) / 32-byte (fp64) records so a
+// thread's gather is one vector transaction per record.
+template <typename R>
+struct DeviceScene
+{
+    // vertices
+    int64_t n_vertices;
+    Real4<R>* pos;  // (xi.x, xi.y, xi.z, inverse mass)        particle_t::xi_, invmass()
+    Real4<R>* prev; // (xn.x, xn.y, xn.z, unused)               particle_t::xn_ (== x_ between substeps)
+    Real4<R>* vel;  // (v.x, v.y, v.z, unused)                  particle_t::v_
+    // green constraints, colour-major
+    int64_t n_tets;
+    uint4 const* tet_v;     // 4 global vertex ids
+    Real4<R> const* tet_r0; // DmInv row 0, d10
+    Real4<R> const* tet_r1; // d11 d12 d20 d21
+    Real4<R> const* tet_r2; // d22, signed V0, material id (as value), unused
+    R* tet_lambda;
+    Real4<R> const* materials; // (mu, lambda, alpha, beta)
+    // distance constraints, colour-major
+    int64_t n_dist;
+    uint2 const* dist_v;
+    Real4<R> const* dist_p; // (rest length, alpha, beta, unused)
+    R* dist_lambda;
+    // collision
+    int64_t n_surface;
+    uint32_t const* surf_v;    // global vertex id of surface vertex i
+    int32_t const* surf_body;  // body of surface vertex i
+    Real4<R>* surf_pos;        // visual-model copy the detection reads (tetrahedral_body.cpp:157-165)
+    int32_t n_sdf;
+    struct Sdf
+    {
+        int32_t kind, body;
+        R a[3], b[3], r;
+    };
+    Sdf const* sdf;
+    int64_t contact_cap;
+    uint32_t* contact_v;   // global vertex id | 0x80000000 when first contact of its vertex
+    Real4<R>* contact_q;   // (qs.x, qs.y, qs.z, lambda)
+    Real4<R>* contact_n;   // (n.x, n.y, n.z, sdf body as value)
+    uint32_t* contact_count;
+    R collision_alpha;
+};
+
+// timestep.cpp:35-43.  a = f * invmass with f = (0, -9.81, 0) accumulated once per substep
+// (f is zeroed by the commit loop, :55).  Only the y component has a non-zero force.
+template <typename R>
+__device__ __forceinline__ void predict_vertex(Real4<R>& p, Real4<R> const& x, Real4<R>& v, R dt)
+{
+    R const fy = R(0) - R(9.81);
+    v.y        = add_rn(v.y, mul_rn(mul_rn(fy, p.w), dt));
+    p.x        = add_rn(x.x, mul_rn(v.x, dt));
+    p.y        = add_rn(x.y, mul_rn(v.y, dt));
+    p.z        = add_rn(x.z, mul_rn(v.z, dt));
+}
+// timestep.cpp:48-57
+template <typename R>
+__device__ __forceinline__ void commit_vertex(Real4<R> const& p, Real4<R>& xn, Real4<R>& v, R dt)
+{
+    v.x  = div_rn(sub_rn(p.x, xn.x), dt);
+    v.y  = div_rn(sub_rn(p.y, xn.y), dt);
+    v.z  = div_rn(sub_rn(p.z, xn.z), dt);
+    xn.x = p.x;
+    xn.y = p.y;
+    xn.z = p.z;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_predict(DeviceScene<R> s, R dt)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= s.n_vertices)
+        return;
+    Real4<R> p       = ld4(&s.pos[i]);
+    Real4<R> const x = ld4(&s.prev[i]);
+    Real4<R> v       = ld4(&s.vel[i]);
+    predict_vertex(p, x, v, dt);
+    st4(&s.vel[i], v);
+    st4(&s.pos[i], p);
+}
+
+// timestep.cpp:48-57
+template <typename R>
+__global__ void __launch_bounds__(256) k_integrate(DeviceScene<R> s, R dt)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= s.n_vertices)
+        return;
+    Real4<R> const p = ld4(&s.pos[i]);
+    Real4<R> xn      = ld4(&s.prev[i]);
+    Real4<R> v       = ld4(&s.vel[i]);
+    commit_vertex(p, xn, v, dt);
+    st4(&s.vel[i], v);
+    st4(&s.prev[i], xn);
+}
+
+// One Green projection given gathered data; returns updated positions/lambda through refs.
+// Steps 10-13 of green_constraint.cpp (:123-157).
+template <typename R, bool kDamped>
+SBS_HD void green_project(Real4<R>& p1, Real4<R>& p2, Real4<R>& p3, Real4<R>& p4,
+                                              Vec3<R> xn1, Vec3<R> xn2, Vec3<R> xn3, Vec3<R> xn4,
+                                              Real4<R> r0, Real4<R> r1, Real4<R> r2, Real4<R> mat,
+                                              R dt, R& lambda)
+{
+    Vec3<R> const x1 = {p1.x, p1.y, p1.z}, x2 = {p2.x, p2.y, p2.z}, x3 = {p3.x, p3.y, p3.z},
+                  x4 = {p4.x, p4.y, p4.z};
+    GreenOut<R> const g =
+        green_gradients<R>(x1, x2, x3, x4, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, mat.x, mat.y);
+    Vec3<R> const f4 = {-(g.f1.x + g.f2.x + g.f3.x), -(g.f1.y + g.f2.y + g.f3.y), -(g.f1.z + g.f2.z + g.f3.z)};
+    R const S = p1.w * dot(g.f1, g.f1) + p2.w * dot(g.f2, g.f2) + p3.w * dot(g.f3, g.f3) + p4.w * dot(f4, f4);
+    if (S < R(1e-20)) // :67, :130-131
+        return;
+    R const dt2 = dt * dt;
+    R const at  = mat.z / dt2;
+    R num       = -(g.C + at * lambda);
+    R den       = S + at;
+    if (kDamped)
+    {
+        R const bt  = mat.w * dt2;
+        R const gam = at * bt / dt;
+        R const gd  = dot(g.f1, x1 - xn1) + dot(g.f2, x2 - xn2) + dot(g.f3, x3 - xn3) + dot(f4, x4 - xn4);
+        num += gam * gd;
+        den = (R(1) + gam) * S + at;
+    }
+    R const dl = num / den;
+    lambda += dl;
+    R const k1 = -p1.w * dl, k2 = -p2.w * dl, k3 = -p3.w * dl, k4 = -p4.w * dl;
+    p1.x += k1 * g.f1.x; p1.y += k1 * g.f1.y; p1.z += k1 * g.f1.z;
+    p2.x += k2 * g.f2.x; p2.y += k2 * g.f2.y; p2.z += k2 * g.f2.z;
+    p3.x += k3 * g.f3.x; p3.y += k3 * g.f3.y; p3.z += k3 * g.f3.z;
+    p4.x += k4 * f4.x;   p4.y += k4 * f4.y;   p4.z += k4 * f4.z;
+}
+
+__device__ __forceinline__ int mat_index(float v) { return __float_as_int(v); }
+__device__ __forceinline__ int mat_index(double v) { return static_cast<int>(v); }
+
+// One colour of Green constraints: thread per tet.  first_iteration folds the lambda reset of
+// constraint_t::prepare_for_projection (constraint.cpp:12-16) into the first sweep.
+template <typename R, bool kDamped>
+__global__ void __launch_bounds__(128)
+k_project_green(DeviceScene<R> s, int64_t first, int32_t count, R dt, int first_iteration)
+{
+    int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    int64_t const t  = first + i;
+    uint4 const v    = __ldg(&s.tet_v[t]);
+    Real4<R> const r0 = ld4_ro(&s.tet_r0[t]);
+    Real4<R> const r1 = ld4_ro(&s.tet_r1[t]);
+    Real4<R> const r2 = ld4_ro(&s.tet_r2[t]);
+    Real4<R> p1 = ld4(&s.pos[v.x]), p2 = ld4(&s.pos[v.y]), p3 = ld4(&s.pos[v.z]), p4 = ld4(&s.pos[v.w]);
+    Real4<R> const mat = ld4_ro(&s.materials[mat_index(r2.z)]);
+    R lambda           = first_iteration ? R(0) : s.tet_lambda[t];
+    Vec3<R> xn1{}, xn2{}, xn3{}, xn4{};
+    if (kDamped)
+    {
+        Real4<R> const a = ld4(&s.prev[v.x]), b = ld4(&s.prev[v.y]), c = ld4(&s.prev[v.z]), d = ld4(&s.prev[v.w]);
+        xn1 = {a.x, a.y, a.z};
+        xn2 = {b.x, b.y, b.z};
+        xn3 = {c.x, c.y, c.z};
+        xn4 = {d.x, d.y, d.z};
+    }
+    R const lambda_in = lambda;
+    green_project<R, kDamped>(p1, p2, p3, p4, xn1, xn2, xn3, xn4, r0, r1, r2, mat, dt, lambda);
+    if (lambda != lambda_in || first_iteration)
+        s.tet_lambda[t] = lambda;
+    if (lambda != lambda_in)
+    {
+        st4(&s.pos[v.x], p1);
+        st4(&s.pos[v.y], p2);
+        st4(&s.pos[v.z], p3);
+        st4(&s.pos[v.w], p4);
+    }
+}
+
+// distance_constraint.cpp:24-53, one colour, thread per constraint
+template <typename R>
+__global__ void __launch_bounds__(128)
+k_project_distance(DeviceScene<R> s, int64_t first, int32_t count, R dt, int first_iteration)
+{
+    int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    int64_t const c  = first + i;
+    uint2 const v    = __ldg(&s.dist_v[c]);
+    Real4<R> const q = ld4_ro(&s.dist_p[c]);
+    Real4<R> p1 = ld4(&s.pos[v.x]), p2 = ld4(&s.pos[v.y]);
+    Real4<R> const n1 = ld4(&s.prev[v.x]), n2 = ld4(&s.prev[v.y]);
+    R lambda          = first_iteration ? R(0) : s.dist_lambda[c];
+    Vec3<R> const diff = {p1.x - p2.x, p1.y - p2.y, p1.z - p2.z};
+    R const len        = sqrt_(dot(diff, diff));
+    Vec3<R> const n    = {diff.x / len, diff.y / len, diff.z / len};
+    R const C          = len - q.x;
+    R const S          = p1.w + p2.w;
+    R const dt2        = dt * dt;
+    R const at = q.y / dt2, bt = q.z * dt2;
+    Vec3<R> const d1 = {p1.x - n1.x, p1.y - n1.y, p1.z - n1.z}, d2 = {p2.x - n2.x, p2.y - n2.y, p2.z - n2.z};
+    R const gd  = dot(n, d1) - dot(n, d2);
+    R const gam = at * bt / dt;
+    R const dl  = (-(C + at * lambda) + gam * gd) / ((R(1) + gam) * S + at);
+    lambda += dl;
+    s.dist_lambda[c] = lambda;
+    R const k1 = p1.w * dl, k2 = -p2.w * dl;
+    p1.x += k1 * n.x; p1.y += k1 * n.y; p1.z += k1 * n.z;
+    p2.x += k2 * n.x; p2.y += k2 * n.y; p2.z += k2 * n.z;
+    st4(&s.pos[v.x], p1);
+    st4(&s.pos[v.y], p2);
+}
+
+// sdf_model_t::evaluate (sdf_model.cpp:66-75) for the analytic kinds: signed distance + gradient
+template <typename R>
+__device__ __forceinline__ R sdf_eval(typename DeviceScene<R>::Sdf const& f, Vec3<R> p, Vec3<R>& g)
+{
+    if (f.kind == 0)
+    { // plane: Eigen::Hyperplane::signedDistance = n.p + offset (sdf_model.cpp:56-61)
+        g = {f.a[0], f.a[1], f.a[2]};
+        return f.a[0] * p.x + f.a[1] * p.y + f.a[2] * p.z + f.r;
+    }
+    if (f.kind == 1)
+    { // sphere
+        Vec3<R> const d = {p.x - f.a[0], p.y - f.a[1], p.z - f.a[2]};
+        R const len     = sqrt_(dot(d, d));
+        if (len > R(0))
+            g = {d.x / len, d.y / len, d.z / len};
+        else
+            g = {R(0), R(1), R(0)};
+        return len - f.r;
+    }
+    // box
+    R const pc[3] = {p.x, p.y, p.z};
+    R q[3], c[3], out2 = R(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        c[i]      = R(0.5) * (f.a[i] + f.b[i]);
+        R const h = R(0.5) * (f.b[i] - f.a[i]);
+        q[i]      = abs_(pc[i] - c[i]) - h;
+        if (q[i] > R(0))
+            out2 += q[i] * q[i];
+    }
+    R gg[3] = {R(0), R(0), R(0)};
+    R sd;
+    if (out2 > R(0))
+    {
+        R const len = sqrt_(out2);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            gg[i] = q[i] > R(0) ? (pc[i] >= c[i] ? q[i] : -q[i]) / len : R(0);
+        sd = len;
+    }
+    else
+    {
+        int ax = 0;
+        if (q[1] > q[ax]) ax = 1;
+        if (q[2] > q[ax]) ax = 2;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (i == ax)
+                gg[i] = pc[i] >= c[i] ? R(1) : R(-1);
+        sd = q[ax];
+    }
+    g = {gg[0], gg[1], gg[2]};
+    return sd;
+}
+
+__device__ __forceinline__ float as_real(float, int v) { return __int_as_float(v); }
+__device__ __forceinline__ double as_real(double, int v) { return static_cast<double>(v); }
+
+// Narrowphase + contact handling (bvh_model.cpp:66-96, xpbd/contact_handler.cpp:14-54):
+// thread per surface vertex, every SDF in body order, warp-aggregated append so that the
+// contacts of one vertex are contiguous and ordered by SDF body.
+template <typename R>
+__global__ void __launch_bounds__(256) k_detect_all(DeviceScene<R> s)
+{
+    int64_t const i   = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    bool const valid  = i < s.n_surface;
+    int32_t n_mine    = 0;
+    Vec3<R> p         = {R(0), R(0), R(0)};
+    int32_t body      = -1;
+    if (valid)
+    {
+        Real4<R> const q = ld4(&s.surf_pos[i]);
+        p                = {q.x, q.y, q.z};
+        body             = s.surf_body[i];
+        for (int32_t k = 0; k < s.n_sdf; ++k)
+        {
+            Vec3<R> g;
+            if (sdf_eval<R>(s.sdf[k], p, g) < R(0))
+                ++n_mine;
+        }
+    }
+    // warp-aggregated reservation
+    unsigned const lane = threadIdx.x & 31u;
+    int32_t incl        = n_mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        int32_t const o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= static_cast<unsigned>(d))
+            incl += o;
+    }
+    int32_t const total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base       = 0;
+    if (lane == 31 && total > 0)
+        base = atomicAdd(s.contact_count, static_cast<uint32_t>(total));
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (!valid || n_mine == 0)
+        return;
+    uint32_t slot      = base + static_cast<uint32_t>(incl - n_mine);
+    uint32_t const gv  = s.surf_v[i];
+    bool first         = true;
+    for (int32_t k = 0; k < s.n_sdf; ++k)
+    {
+        Vec3<R> g;
+        R const sd = sdf_eval<R>(s.sdf[k], p, g);
+        if (!(sd < R(0)))
+            continue;
+        R const inv       = R(1) / sqrt_(dot(g, g)); // grad.normalized() (bvh_model.cpp:82)
+        Vec3<R> const n   = {g.x * inv, g.y * inv, g.z * inv};
+        R const a         = abs_(sd);
+        if (slot < s.contact_cap)
+        {
+            s.contact_v[slot] = gv | (first ? 0x80000000u : 0u);
+            st4(&s.contact_q[slot], Real4<R>{p.x + a * n.x, p.y + a * n.y, p.z + a * n.z, R(0)}); // :83-84
+            st4(&s.contact_n[slot], Real4<R>{n.x, n.y, n.z, as_real(R(0), s.sdf[k].body)});
+        }
+        first = false;
+        ++slot;
+    }
+    (void)body;
+}
+
+// collision_constraint.cpp:21-48.  The thread owning the first contact of a vertex walks the
+// vertex's contacts in order, so several SDFs touching one vertex are applied sequentially as
+// in the reference's serial sweep.
+template <typename R>
+__global__ void __launch_bounds__(256) k_project_collision(DeviceScene<R> s, R dt, int first_iteration)
+{
+    int64_t const i   = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    uint32_t const n  = min(*s.contact_count, static_cast<uint32_t>(s.contact_cap));
+    if (i >= n)
+        return;
+    uint32_t const tag = s.contact_v[i];
+    if (!(tag & 0x80000000u))
+        return;
+    uint32_t const gv = tag & 0x7fffffffu;
+    Real4<R> p        = ld4(&s.pos[gv]);
+    R const at        = s.collision_alpha / (dt * dt);
+    bool moved        = false;
+    for (int64_t j = i; j < n; ++j)
+    {
+        if (j > i && s.contact_v[j] != gv)
+            break;
+        Real4<R> q       = ld4(&s.contact_q[j]);
+        Real4<R> const m = ld4(&s.contact_n[j]);
+        R lambda         = first_iteration ? R(0) : q.w;
+        R const C        = (p.x - q.x) * m.x + (p.y - q.y) * m.y + (p.z - q.z) * m.z;
+        if (C >= R(0))
+        {
+            if (first_iteration)
+            {
+                q.w = R(0);
+                st4(&s.contact_q[j], q);
+            }
+            continue;
+        }
+        R const dl = -(C + at * lambda) / (p.w + at);
+        lambda += dl;
+        p.x += p.w * m.x * dl;
+        p.y += p.w * m.y * dl;
+        p.z += p.w * m.z * dl;
+        q.w = lambda;
+        st4(&s.contact_q[j], q);
+        moved = true;
+    }
+    if (moved)
+        st4(&s.pos[gv], p);
+}
+
+// tetrahedral_body_t::update_visual_model (tetrahedral_body.cpp:157-165): surface copy of x
+template <typename R>
+__global__ void __launch_bounds__(256) k_surface_gather(DeviceScene<R> s)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= s.n_surface)
+        return;
+    st4(&s.surf_pos[i], ld4(&s.prev[s.surf_v[i]]));
+}
+
+} // namespace sbsb200

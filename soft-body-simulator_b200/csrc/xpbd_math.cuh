@@ -1,0 +1,294 @@
+// Device math of the XPBD hot path, templated on the arithmetic type (float = production,
+// double = validation build).  No reference code here: the algebra is derived in DESIGN.md
+// ("Green projection without a general SVD") from src/physics/xpbd/green_constraint.cpp:49-158.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// math that is also compiled for the host by the test-only harness tests/host_math.cu
+#define SBS_HD __host__ __device__ __forceinline__
+
+namespace sbsb200 {
+
+template <typename R>
+struct alignas(4 * sizeof(R) > 16 ? 16 : 4 * sizeof(R)) Real4
+{
+    R x, y, z, w;
+};
+static_assert(sizeof(Real4<float>) == 16 && alignof(Real4<float>) == 16, "float4 layout");
+static_assert(sizeof(Real4<double>) == 32, "double4 layout");
+
+template <typename R>
+struct Vec3
+{
+    R x, y, z;
+};
+
+template <typename R>
+SBS_HD Vec3<R> operator-(Vec3<R> a, Vec3<R> b)
+{
+    return {a.x - b.x, a.y - b.y, a.z - b.z};
+}
+template <typename R>
+SBS_HD R dot(Vec3<R> a, Vec3<R> b)
+{
+    return a.x * b.x + a.y * b.y + a.z * b.z;
+}
+template <typename R>
+SBS_HD Vec3<R> cross(Vec3<R> a, Vec3<R> b)
+{
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+SBS_HD float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+SBS_HD double rsqrt_(double x) { return 1.0 / sqrt(x); }
+SBS_HD float sqrt_(float x) { return sqrtf(x); }
+SBS_HD double sqrt_(double x) { return sqrt(x); }
+SBS_HD float abs_(float x) { return fabsf(x); }
+SBS_HD double abs_(double x) { return fabs(x); }
+SBS_HD float max_(float a, float b) { return fmaxf(a, b); }
+SBS_HD double max_(double a, double b) { return fmax(a, b); }
+
+// Rounding-exact arithmetic (never contracted into FMA): predict/commit are order-independent
+// stages that must match the fp64 reference bit for bit in the validation build.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// vector loads/stores of (x, y, z, w) records
+__device__ __forceinline__ Real4<float> ld4(Real4<float> const* p)
+{
+    float4 const v = *reinterpret_cast<float4 const*>(p);
+    return {v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ void st4(Real4<float>* p, Real4<float> v)
+{
+    *reinterpret_cast<float4*>(p) = make_float4(v.x, v.y, v.z, v.w);
+}
+__device__ __forceinline__ Real4<double> ld4(Real4<double> const* p)
+{
+    double2 const a = reinterpret_cast<double2 const*>(p)[0];
+    double2 const b = reinterpret_cast<double2 const*>(p)[1];
+    return {a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void st4(Real4<double>* p, Real4<double> v)
+{
+    reinterpret_cast<double2*>(p)[0] = make_double2(v.x, v.y);
+    reinterpret_cast<double2*>(p)[1] = make_double2(v.z, v.w);
+}
+// read-only (non-coherent) path for per-constraint constants
+__device__ __forceinline__ Real4<float> ld4_ro(Real4<float> const* p)
+{
+    float4 const v = __ldg(reinterpret_cast<float4 const*>(p));
+    return {v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ Real4<double> ld4_ro(Real4<double> const* p)
+{
+    double2 const a = __ldg(reinterpret_cast<double2 const*>(p));
+    double2 const b = __ldg(reinterpret_cast<double2 const*>(p) + 1);
+    return {a.x, a.y, b.x, b.y};
+}
+
+template <typename R>
+struct Eps;
+template <>
+struct Eps<float>
+{
+    static constexpr float off_rel = 1e-13f; // off^2 <= off_rel * diag^2  (~ (3e-7)^2)
+    static constexpr int max_sweeps = 6;
+};
+template <>
+struct Eps<double>
+{
+    static constexpr double off_rel = 1e-30;
+    static constexpr int max_sweeps = 12;
+};
+
+// One Jacobi rotation on the symmetric matrix (app, aqq, apq, arp, arq) and the eigenvector
+// columns p, q.  r is the third index.
+template <typename R>
+SBS_HD void jacobi_rotate(R& app, R& aqq, R& apq, R& arp, R& arq, Vec3<R>& vp,
+                                              Vec3<R>& vq)
+{
+    if (apq == R(0))
+        return;
+    R const d   = aqq - app;
+    R const den = abs_(d) + sqrt_(d * d + R(4) * apq * apq);
+    R const t   = (d >= R(0) ? R(2) : R(-2)) * apq / den;
+    R const c   = rsqrt_(R(1) + t * t);
+    R const s   = t * c;
+    app -= t * apq;
+    aqq += t * apq;
+    apq = R(0);
+    R const rp = c * arp - s * arq;
+    R const rq = s * arp + c * arq;
+    arp        = rp;
+    arq        = rq;
+    Vec3<R> const np = {c * vp.x - s * vq.x, c * vp.y - s * vq.y, c * vp.z - s * vq.z};
+    Vec3<R> const nq = {s * vp.x + c * vq.x, s * vp.y + c * vq.y, s * vp.z + c * vq.z};
+    vp               = np;
+    vq               = nq;
+}
+
+// Eigen-decomposition of the symmetric 3x3 A (a00 a11 a22 a01 a02 a12): cyclic Jacobi.
+// Output: eigenvalues l0 >= l1 >= l2 and a PROPER rotation (v0 v1 v2) of eigenvectors.
+template <typename R>
+SBS_HD void sym_eig3(R a00, R a11, R a22, R a01, R a02, R a12, R& l0, R& l1,
+                                         R& l2, Vec3<R>& v0, Vec3<R>& v1, Vec3<R>& v2)
+{
+    v0 = {R(1), R(0), R(0)};
+    v1 = {R(0), R(1), R(0)};
+    v2 = {R(0), R(0), R(1)};
+#pragma unroll 1
+    for (int sweep = 0; sweep < Eps<R>::max_sweeps; ++sweep)
+    {
+        R const off2  = a01 * a01 + a02 * a02 + a12 * a12;
+        R const diag2 = a00 * a00 + a11 * a11 + a22 * a22;
+        if (off2 <= Eps<R>::off_rel * diag2)
+            break;
+        jacobi_rotate(a00, a11, a01, a02, a12, v0, v1); // (p,q) = (0,1), r = 2
+        jacobi_rotate(a00, a22, a02, a01, a12, v0, v2); // (0,2), r = 1
+        jacobi_rotate(a11, a22, a12, a01, a02, v1, v2); // (1,2), r = 0
+    }
+    l0 = a00;
+    l1 = a11;
+    l2 = a22;
+    // sort descending; a swap followed by one negation keeps det(V) = +1
+    auto swap_cols = [](R& la, R& lb, Vec3<R>& va, Vec3<R>& vb) {
+        R const tl = la;
+        la         = lb;
+        lb         = tl;
+        Vec3<R> const tv = va;
+        va               = vb;
+        vb               = {-tv.x, -tv.y, -tv.z};
+    };
+    if (l0 < l1)
+        swap_cols(l0, l1, v0, v1);
+    if (l0 < l2)
+        swap_cols(l0, l2, v0, v2);
+    if (l1 < l2)
+        swap_cols(l1, l2, v1, v2);
+}
+
+template <typename R>
+struct GreenOut
+{
+    Vec3<R> f1, f2, f3; // negative gradients at vertices 1..3 (f4 = -(f1+f2+f3))
+    R C;                // |V0| * psi
+};
+
+// Steps 2-9 of green_constraint_t::project_positions (green_constraint.cpp:61-120) for one
+// tet: D = DmInv (row-major d00..d22), V0s = signed rest volume.
+//
+// Instead of a general SVD F = U S V^T we diagonalise F^T F = V S^2 V^T (V a proper rotation,
+// sigma sorted descending) and rebuild U' = (F v1/|.|, F v2/|.| orthogonalised, u1 x u2).
+// With that U', U' V^T is always a proper rotation, which is exactly what the reference's
+// "if inverted: sigma3 -> -sigma3, U.col(2) -> -U.col(2)" produces; the flipped sigma3 is
+// negative and is therefore always clamped to 0.577 (green_constraint.cpp:92-102).
+template <typename R>
+SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3,
+                                                       Vec3<R> x4, R d00, R d01, R d02, R d10,
+                                                       R d11, R d12, R d20, R d21, R d22, R V0s,
+                                                       R mu, R lam)
+{
+    Vec3<R> const e1 = x1 - x4, e2 = x2 - x4, e3 = x3 - x4; // columns of Ds (:69-72)
+    // sign of det(Ds) vs sign of V0 (:61-65); >= 0 counts as positive
+    R const detDs       = dot(e1, cross(e2, e3));
+    bool const inverted = (detDs >= R(0)) != (V0s >= R(0));
+
+    // F = Ds * DmInv, stored by columns c0 c1 c2 (:74)
+    Vec3<R> const c0 = {e1.x * d00 + e2.x * d10 + e3.x * d20, e1.y * d00 + e2.y * d10 + e3.y * d20,
+                        e1.z * d00 + e2.z * d10 + e3.z * d20};
+    Vec3<R> const c1 = {e1.x * d01 + e2.x * d11 + e3.x * d21, e1.y * d01 + e2.y * d11 + e3.y * d21,
+                        e1.z * d01 + e2.z * d11 + e3.z * d21};
+    Vec3<R> const c2 = {e1.x * d02 + e2.x * d12 + e3.x * d22, e1.y * d02 + e2.y * d12 + e3.y * d22,
+                        e1.z * d02 + e2.z * d12 + e3.z * d22};
+
+    R l0, l1, l2;
+    Vec3<R> v0, v1, v2;
+    sym_eig3(dot(c0, c0), dot(c1, c1), dot(c2, c2), dot(c0, c1), dot(c0, c2), dot(c1, c2), l0, l1,
+             l2, v0, v1, v2);
+
+    // U' columns
+    auto Fv = [&](Vec3<R> v) -> Vec3<R> {
+        return {c0.x * v.x + c1.x * v.y + c2.x * v.z, c0.y * v.x + c1.y * v.y + c2.y * v.z,
+                c0.z * v.x + c1.z * v.y + c2.z * v.z};
+    };
+    Vec3<R> u0 = Fv(v0);
+    R n0       = dot(u0, u0);
+    if (n0 > R(0))
+    {
+        R const s = rsqrt_(n0);
+        u0        = {u0.x * s, u0.y * s, u0.z * s};
+    }
+    else
+        u0 = {R(1), R(0), R(0)};
+    Vec3<R> u1 = Fv(v1);
+    {
+        R const p = dot(u1, u0);
+        u1        = {u1.x - p * u0.x, u1.y - p * u0.y, u1.z - p * u0.z};
+    }
+    R const n1 = dot(u1, u1);
+    if (n1 > l0 * R(sizeof(R) == 4 ? 1e-12 : 1e-28))
+    {
+        R const s = rsqrt_(n1);
+        u1        = {u1.x * s, u1.y * s, u1.z * s};
+    }
+    else
+    { // rank <= 1: any unit vector orthogonal to u0
+        Vec3<R> const ax = abs_(u0.x) < R(0.6) ? Vec3<R>{R(1), R(0), R(0)} : Vec3<R>{R(0), R(1), R(0)};
+        u1               = cross(u0, ax);
+        R const s        = rsqrt_(dot(u1, u1));
+        u1               = {u1.x * s, u1.y * s, u1.z * s};
+    }
+    Vec3<R> const u2 = cross(u0, u1);
+
+    // clamped principal stretches (:92-102)
+    R const smin = R(0.577);
+    R const s0   = max_(sqrt_(max_(l0, R(0))), smin);
+    R const s1   = max_(sqrt_(max_(l1, R(0))), smin);
+    R const s2   = inverted ? smin : max_(sqrt_(max_(l2, R(0))), smin);
+
+    // Ehat, Piolahat (:104-106)
+    R const eh0 = R(0.5) * (s0 * s0 - R(1)), eh1 = R(0.5) * (s1 * s1 - R(1)),
+            eh2  = R(0.5) * (s2 * s2 - R(1));
+    R const ehtr = eh0 + eh1 + eh2;
+    R const ph0 = s0 * (R(2) * mu * eh0 + lam * ehtr), ph1 = s1 * (R(2) * mu * eh1 + lam * ehtr),
+            ph2 = s2 * (R(2) * mu * eh2 + lam * ehtr);
+
+    // psi from E = U Ehat V^T (:108-110): |E|_F^2 = sum ehat_i^2, tr E = sum ehat_i (u_i . v_i)
+    R const Etr = eh0 * dot(u0, v0) + eh1 * dot(u1, v1) + eh2 * dot(u2, v2);
+    R const psi = mu * (eh0 * eh0 + eh1 * eh1 + eh2 * eh2) + R(0.5) * lam * Etr * Etr;
+
+    // P = U Piolahat V^T (:112), rows pr0 pr1 pr2
+    Vec3<R> const a0 = {ph0 * u0.x, ph0 * u0.y, ph0 * u0.z};
+    Vec3<R> const a1 = {ph1 * u1.x, ph1 * u1.y, ph1 * u1.z};
+    Vec3<R> const a2 = {ph2 * u2.x, ph2 * u2.y, ph2 * u2.z};
+    // P[r][k] = a0[r] v0[k] + a1[r] v1[k] + a2[r] v2[k]
+    Vec3<R> const pk0 = {a0.x * v0.x + a1.x * v1.x + a2.x * v2.x, a0.y * v0.x + a1.y * v1.x + a2.y * v2.x,
+                         a0.z * v0.x + a1.z * v1.x + a2.z * v2.x}; // column k=0 of P
+    Vec3<R> const pk1 = {a0.x * v0.y + a1.x * v1.y + a2.x * v2.y, a0.y * v0.y + a1.y * v1.y + a2.y * v2.y,
+                         a0.z * v0.y + a1.z * v1.y + a2.z * v2.y};
+    Vec3<R> const pk2 = {a0.x * v0.z + a1.x * v1.z + a2.x * v2.z, a0.y * v0.z + a1.y * v1.z + a2.y * v2.z,
+                         a0.z * v0.z + a1.z * v1.z + a2.z * v2.z};
+
+    // H = -|V0| P DmInv^T (:115-116): column c of H = -|V0| * sum_k P[:,k] DmInv[c][k]
+    R const nv = -abs_(V0s);
+    GreenOut<R> o;
+    o.f1 = {nv * (pk0.x * d00 + pk1.x * d01 + pk2.x * d02), nv * (pk0.y * d00 + pk1.y * d01 + pk2.y * d02),
+            nv * (pk0.z * d00 + pk1.z * d01 + pk2.z * d02)};
+    o.f2 = {nv * (pk0.x * d10 + pk1.x * d11 + pk2.x * d12), nv * (pk0.y * d10 + pk1.y * d11 + pk2.y * d12),
+            nv * (pk0.z * d10 + pk1.z * d11 + pk2.z * d12)};
+    o.f3 = {nv * (pk0.x * d20 + pk1.x * d21 + pk2.x * d22), nv * (pk0.y * d20 + pk1.y * d21 + pk2.y * d22),
+            nv * (pk0.z * d20 + pk1.z * d21 + pk2.z * d22)};
+    o.C  = abs_(V0s) * psi; // :133
+    return o;
+}
+
+} // namespace sbsb200

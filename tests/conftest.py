@@ -1,0 +1,31 @@
+import importlib
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def sbs():
+    """The product's host binding (ctypes over libsbsb200.so)."""
+    return importlib.import_module("soft-body-simulator_b200")
+
+
+@pytest.fixture(scope="session")
+def scenes():
+    return importlib.import_module("soft-body-simulator_b200.scenes")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.build()
+    return O
