@@ -125,6 +125,7 @@ struct Engine final : EngineBase
     DevBuf<uint32_t> surf_v, contact_v, contact_count;
     DevBuf<int32_t> surf_body;
     DevBuf<typename DeviceScene<R>::Sdf> sdf;
+    DevBuf<double> stage_x, stage_v; // raw host-format staging for upload/download
     PersistentPlan<R> pp; // persistent schedule resources (may be inactive)
     std::map<std::tuple<double, int, int, int>, cudaGraphExec_t> graphs;
     std::map<std::tuple<double, int, int, int>, int64_t> graph_kernels;
@@ -423,60 +424,55 @@ struct Engine final : EngineBase
         c.timed = true;
     }
 
+    // Host arrays cross PCIe as raw doubles (a single DMA each when the caller's memory is
+    // pinned); the conversion to the device layout runs on the GPU.
+    void ensure_staging(int64_t n)
+    {
+        if (static_cast<int64_t>(stage_x.n) < 3 * n)
+        {
+            stage_x.alloc(static_cast<size_t>(3 * n));
+            stage_v.alloc(static_cast<size_t>(3 * n));
+        }
+    }
+
     void upload(sbsb200_ctx& c, int body, double const* x, double const* v) override
     {
         HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
         int64_t const n    = hb.n_vertices;
-        std::vector<Real4<R>> hp(static_cast<size_t>(n)), hx(static_cast<size_t>(n)), hv(static_cast<size_t>(n));
-        // keep inverse masses: read them back
-        CK(cudaMemcpyAsync(hp.data(), pos.p + hb.v_offset, sizeof(Real4<R>) * n, cudaMemcpyDeviceToHost, c.stream));
-        CK(cudaStreamSynchronize(c.stream));
-        for (int64_t i = 0; i < n; ++i)
-        {
-            hp[static_cast<size_t>(i)].x = R(x[3 * i]);
-            hp[static_cast<size_t>(i)].y = R(x[3 * i + 1]);
-            hp[static_cast<size_t>(i)].z = R(x[3 * i + 2]);
-            hx[static_cast<size_t>(i)]   = {R(x[3 * i]), R(x[3 * i + 1]), R(x[3 * i + 2]), R(0)};
-            hv[static_cast<size_t>(i)]   = v ? Real4<R>{R(v[3 * i]), R(v[3 * i + 1]), R(v[3 * i + 2]), R(0)}
-                                             : Real4<R>{R(0), R(0), R(0), R(0)};
-        }
-        CK(cudaMemcpyAsync(pos.p + hb.v_offset, hp.data(), sizeof(Real4<R>) * n, cudaMemcpyHostToDevice, c.stream));
-        CK(cudaMemcpyAsync(prev.p + hb.v_offset, hx.data(), sizeof(Real4<R>) * n, cudaMemcpyHostToDevice, c.stream));
-        CK(cudaMemcpyAsync(vel.p + hb.v_offset, hv.data(), sizeof(Real4<R>) * n, cudaMemcpyHostToDevice, c.stream));
+        if (n == 0)
+            return;
+        ensure_staging(n);
+        CK(cudaMemcpyAsync(stage_x.p, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+        if (v)
+            CK(cudaMemcpyAsync(stage_v.p, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+        k_unpack_state<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(
+            d, hb.v_offset, n, stage_x.p, v ? stage_v.p : nullptr);
+        ++c.kernels;
         if (d.n_surface > 0)
         {
             k_surface_gather<R><<<static_cast<unsigned>((d.n_surface + 255) / 256), 256, 0, c.stream>>>(d);
             ++c.kernels;
         }
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(c.stream));
+        CK(cudaStreamSynchronize(c.stream)); // the caller may reuse x / v as soon as we return
     }
 
     void download(sbsb200_ctx& c, int body, double* x, double* v) override
     {
         HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
         int64_t const n    = hb.n_vertices;
-        std::vector<Real4<R>> hx(static_cast<size_t>(n)), hv(static_cast<size_t>(n));
+        if (n == 0 || (!x && !v))
+            return;
+        ensure_staging(n);
+        k_pack_state<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(
+            d, hb.v_offset, n, x ? stage_x.p : nullptr, v ? stage_v.p : nullptr);
+        ++c.kernels;
+        CK(cudaGetLastError());
         if (x)
-            CK(cudaMemcpyAsync(hx.data(), prev.p + hb.v_offset, sizeof(Real4<R>) * n, cudaMemcpyDeviceToHost, c.stream));
+            CK(cudaMemcpyAsync(x, stage_x.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c.stream));
         if (v)
-            CK(cudaMemcpyAsync(hv.data(), vel.p + hb.v_offset, sizeof(Real4<R>) * n, cudaMemcpyDeviceToHost, c.stream));
+            CK(cudaMemcpyAsync(v, stage_v.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c.stream));
         CK(cudaStreamSynchronize(c.stream));
-        for (int64_t i = 0; i < n; ++i)
-        {
-            if (x)
-            {
-                x[3 * i]     = double(hx[static_cast<size_t>(i)].x);
-                x[3 * i + 1] = double(hx[static_cast<size_t>(i)].y);
-                x[3 * i + 2] = double(hx[static_cast<size_t>(i)].z);
-            }
-            if (v)
-            {
-                v[3 * i]     = double(hv[static_cast<size_t>(i)].x);
-                v[3 * i + 1] = double(hv[static_cast<size_t>(i)].y);
-                v[3 * i + 2] = double(hv[static_cast<size_t>(i)].z);
-            }
-        }
     }
 
     void set_mass(sbsb200_ctx& c, int64_t gv, double m) override

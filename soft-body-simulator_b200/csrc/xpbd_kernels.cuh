@@ -394,4 +394,48 @@ __global__ void __launch_bounds__(256) k_surface_gather(DeviceScene<R> s)
     st4(&s.surf_pos[i], ld4(&s.prev[s.surf_v[i]]));
 }
 
+// Host-format (3 doubles per vertex) <-> device layout.  Upload sets x = xi = xn and keeps the
+// inverse mass (tetrahedral_body_t::transform semantics, tetrahedral_body.cpp:121-132).
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_unpack_state(DeviceScene<R> s, int64_t first, int64_t n, double const* __restrict__ x, double const* __restrict__ v)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    Real4<R> p = ld4(&s.pos[first + i]);
+    p.x        = R(x[3 * i]);
+    p.y        = R(x[3 * i + 1]);
+    p.z        = R(x[3 * i + 2]);
+    st4(&s.pos[first + i], p);
+    st4(&s.prev[first + i], Real4<R>{p.x, p.y, p.z, R(0)});
+    Real4<R> vel = {R(0), R(0), R(0), R(0)};
+    if (v)
+        vel = {R(v[3 * i]), R(v[3 * i + 1]), R(v[3 * i + 2]), R(0)};
+    st4(&s.vel[first + i], vel);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_pack_state(DeviceScene<R> s, int64_t first, int64_t n, double* __restrict__ x, double* __restrict__ v)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    if (x)
+    {
+        Real4<R> const p = ld4(&s.prev[first + i]);
+        x[3 * i]         = double(p.x);
+        x[3 * i + 1]     = double(p.y);
+        x[3 * i + 2]     = double(p.z);
+    }
+    if (v)
+    {
+        Real4<R> const q = ld4(&s.vel[first + i]);
+        v[3 * i]         = double(q.x);
+        v[3 * i + 1]     = double(q.y);
+        v[3 * i + 2]     = double(q.z);
+    }
+}
+
 } // namespace sbsb200

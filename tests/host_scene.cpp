@@ -1,0 +1,60 @@
+// TEST-ONLY harness: C entry points over the product's host-side scene compiler
+// (soft-body-simulator_b200/csrc/scene_build.cpp) so that boundary extraction, colouring and
+// the region plan can be tested on a CPU-only box.
+#include "../soft-body-simulator_b200/csrc/scene_build.h"
+
+#include <cstring>
+
+using namespace sbsb200;
+
+extern "C" int hs_boundary(int64_t nV, int64_t nT, const uint32_t* tets, uint32_t* surf_to_tet, uint32_t* tris,
+                           int64_t* n_tris)
+{
+    std::vector<uint32_t> s2t, tr;
+    extract_boundary(nV, nT, tets, s2t, &tr);
+    std::memcpy(surf_to_tet, s2t.data(), sizeof(uint32_t) * s2t.size());
+    if (tris)
+        std::memcpy(tris, tr.data(), sizeof(uint32_t) * tr.size());
+    *n_tris = static_cast<int64_t>(tr.size() / 3);
+    return static_cast<int>(s2t.size());
+}
+
+// colours k-vertex constraints; writes order[n], offsets[n_colours+1]; returns n_colours (<0 on failure)
+extern "C" int hs_colour(int64_t nV, int64_t n, int k, const uint32_t* verts, const double* x0, uint32_t* order,
+                         int64_t* offsets, int max_colours, int* valid)
+{
+    std::vector<uint64_t> keys;
+    morton_keys(n, k, verts, x0, nV, keys);
+    ColourClass cc;
+    if (!colour_constraints(nV, n, k, verts, keys.data(), nullptr, max_colours, cc))
+        return -1;
+    std::memcpy(order, cc.order.data(), sizeof(uint32_t) * cc.order.size());
+    std::memcpy(offsets, cc.offsets.data(), sizeof(int64_t) * cc.offsets.size());
+    *valid = colouring_is_valid(nV, k, verts, cc) ? 1 : 0;
+    return cc.n_colours;
+}
+
+// region plan of a single tet body; outputs tet_region[T], vertex_region[V]; returns n_interface
+extern "C" int64_t hs_regions(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_regions,
+                              int32_t* tet_region, int32_t* vertex_region, int32_t* n_neighbours)
+{
+    HostScene h;
+    h.x0.assign(x0, x0 + 3 * nV);
+    h.mass.assign(static_cast<size_t>(nV), 1.0);
+    h.tets.assign(tets, tets + 4 * nT);
+    h.tet_insertion.resize(static_cast<size_t>(nT));
+    h.tet_material.assign(static_cast<size_t>(nT), 0);
+    HostBody b;
+    b.n_vertices = nV;
+    b.n_tets     = nT;
+    h.bodies.push_back(b);
+    std::vector<uint64_t> keys;
+    morton_keys(nT, 4, tets, x0, nV, keys);
+    RegionPlan plan;
+    plan_regions(h, keys, n_regions, plan);
+    std::memcpy(tet_region, plan.tet_region.data(), sizeof(int32_t) * plan.tet_region.size());
+    std::memcpy(vertex_region, plan.vertex_region.data(), sizeof(int32_t) * plan.vertex_region.size());
+    for (int r = 0; r < plan.n_regions; ++r)
+        n_neighbours[r] = plan.nbr_offsets[r + 1] - plan.nbr_offsets[r];
+    return plan.n_interface;
+}

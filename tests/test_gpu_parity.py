@@ -83,3 +83,147 @@ def test_config2_cantilever_small(sbs, scenes, oracle, precision):
     assert dev <= TOL[precision], dev
     pinned = np.arange(7 * 7 * 15) % 15 == 0
     assert np.array_equal(xg[pinned], scene.items[0].x[pinned].astype(np.float32 if precision == 32 else np.float64))
+
+
+import golden_cases as G  # noqa: E402
+
+
+def _checkers(oracle):
+    """The C restatement and, when it travelled with the repo, the reference's own sources."""
+    out = [("oracle", oracle.World)]
+    from oracle import ref as R
+    if R.available():
+        out.append(("reference", R.World))
+    return out
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("name", G.case_names())
+def test_golden_scenes_against_reference_in_gpu_colour_order(sbs, oracle, name, precision):
+    """Every scene behind tests/golden (floor, box and sphere contacts, two bodies joined by
+    damped springs, damped Green constraints, pinned vertices): the GPU result vs the reference
+    algorithm run with constraints permuted into the GPU's exported colour order."""
+    scene, frames, _ = G.load(name)
+    sim = sbs.Simulation(0, precision)
+    ids = scene.instantiate(sim)
+    order = sim.constraint_order()
+    assert np.array_equal(np.sort(order), np.arange(len(order)))
+    for _ in range(frames):
+        sim.step(scene.dt, scene.substeps, scene.iterations, scene.detect_every_substep)
+    diag = scene.bbox_diagonal()
+    for label, World in _checkers(oracle):
+        ref = World()
+        scene.instantiate(ref)
+        ref.set_constraint_order(order)
+        for _ in range(frames):
+            ref.step(scene.dt, scene.substeps, scene.iterations, scene.detect_every_substep)
+        for b in scene.tet_bodies():
+            xg, vg = sim.download(ids[b])
+            xr, vr = ref.download(b)
+            dev = np.abs(xg - xr).max() / diag
+            assert dev <= TOL[precision], "%s: %s body %d deviates %.3e" % (label, name, b, dev)
+
+
+def test_surface_map_matches_reference_numbering(sbs, scenes, oracle):
+    scene = scenes.config1(W=6, H=5, D=4)
+    sim = sbs.Simulation(0, 32)
+    ids = scene.instantiate(sim)
+    s2t, _ = oracle.boundary_surface(scene.items[0].x0.shape[0], scene.items[0].tets)
+    assert np.array_equal(sim.surface_map(ids[0]), s2t)
+
+
+def test_set_mass_pins_a_vertex_between_frames(sbs, scenes, oracle):
+    """main.cpp:158-165 toggles mass 1 <-> 0 between frames."""
+    scene = scenes.config1(W=4, H=4, D=6)
+    sim = sbs.Simulation(0, 64)
+    ids = scene.instantiate(sim)
+    ref = oracle.World()
+    scene.instantiate(ref)
+    ref.set_constraint_order(sim.constraint_order())
+    for w in (sim, ref):
+        w.step(scene.dt, 10, 10)
+    x1, _ = sim.download(ids[0])
+    for w, b in ((sim, ids[0]), (ref, 0)):
+        w.set_mass(b, 17, 0.0)
+        w.step(scene.dt, 10, 10)
+    xg, _ = sim.download(ids[0])
+    xr, _ = ref.download(0)
+    assert np.abs(xg - xr).max() <= 1e-9 * scene.bbox_diagonal()
+
+
+def test_step_host_round_trip_equals_resident_stepping(sbs, scenes):
+    scene = scenes.config1(W=5, H=5, D=7)
+    a = sbs.Simulation(0, 32)
+    b = sbs.Simulation(0, 32)
+    ia = scene.instantiate(a)
+    ib = scene.instantiate(b)
+    nV = scene.items[0].x0.shape[0]
+    xin = scene.items[0].x.copy()
+    vin = np.zeros((nV, 3))
+    xo = np.empty((nV, 3))
+    vo = np.empty((nV, 3))
+    for _ in range(2):
+        a.step(scene.dt, 10, 10)
+        b.step_host(ib[0], xin, vin, scene.dt, 10, 10, False, xo, vo)
+        xin[:] = xo
+        vin[:] = vo
+    xa, va = a.download(ia[0])
+    # the host round trip goes through fp64 host arrays of fp32 device values: exact
+    assert np.array_equal(xa, xo) and np.array_equal(va, vo)
+
+
+def test_error_behaviour(sbs, scenes):
+    sim = sbs.Simulation(0, 32)
+    with pytest.raises(sbs.SbsError):
+        sim.step(0.016, 10, 10)                      # step before finalize
+    with pytest.raises(sbs.SbsError):
+        sim.add_tet_body(np.zeros((4, 3)), np.array([[0, 1, 2, 7]]))   # vertex index out of range
+    b = sim.add_tet_body(np.eye(4, 3), np.array([[0, 1, 2, 3]]))
+    with pytest.raises(sbs.SbsError):
+        sim.add_distance_constraints(b, 5, np.array([[0, 1]]))          # no such body
+    sim.finalize()
+    with pytest.raises(sbs.SbsError):
+        sim.finalize()                               # twice
+    with pytest.raises(sbs.SbsError):
+        sim.step(0.016, 0, 10)                       # substeps must be positive
+    with pytest.raises(sbs.SbsError):
+        sim.add_sdf_plane((0, 1, 0), (0, 0, 0), (-1, -1, -1, 1, 1, 1))  # after finalize
+    sim.step(0.016, 2, 2)
+    x, v = sim.download(b)
+    assert np.isfinite(x).all()
+
+
+def test_empty_scene_and_body_without_tets(sbs):
+    sim = sbs.Simulation(0, 32)
+    sim.finalize()
+    sim.step(0.016, 2, 2)
+    sim.synchronize()
+    sim2 = sbs.Simulation(0, 32)
+    b = sim2.add_tet_body(np.array([[0.0, 1.0, 0.0]]), np.zeros((0, 4), np.uint32))
+    sim2.finalize()
+    sim2.step(0.016, 1, 1)
+    x, v = sim2.download(b)
+    np.testing.assert_allclose(x[0], [0.0, 1.0 - 9.81 * 0.016 ** 2, 0.0], rtol=1e-6)
+
+
+@pytest.mark.parametrize("precision", [32])
+def test_full_size_properties_config3(sbs, scenes, precision):
+    """BASELINE size (1M tets): properties that need no oracle run — finite state, exported
+    order is a permutation, determinism (two contexts give identical bits), momentum sanity."""
+    scene = scenes.config3()
+    out = []
+    for _ in range(2):
+        sim = sbs.Simulation(0, precision)
+        ids = scene.instantiate(sim)
+        order = sim.constraint_order()
+        sim.step(scene.dt, scene.substeps, scene.iterations, True)
+        x, v = sim.download(ids[0])
+        out.append((x, v))
+        st = sim.stats()
+        sim.close()
+    assert np.array_equal(np.sort(order), np.arange(scene.n_tets))
+    assert np.isfinite(out[0][0]).all() and np.isfinite(out[0][1]).all()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert st["n_tets"] == 1_000_000 and st["n_surface_vertices"] == 22_002
+    # the block may only have moved a little in one frame
+    assert np.abs(out[0][0] - scene.items[0].x).max() < 1.0

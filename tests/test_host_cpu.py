@@ -1,0 +1,247 @@
+"""CPU tests of the product's host side: C-ABI surface, host scene compiler, and the device
+math compiled for the host (tests/host_math.cu) against the oracle."""
+import ctypes as C
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BUILD = os.path.join(HERE, "_build")
+dp = C.POINTER(C.c_double)
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+
+
+def _newer(target, sources):
+    return os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in sources)
+
+
+@pytest.fixture(scope="session")
+def hostscene():
+    os.makedirs(BUILD, exist_ok=True)
+    lib = os.path.join(BUILD, "libhostscene.so")
+    src = [os.path.join(HERE, "host_scene.cpp"), os.path.join(ROOT, "soft-body-simulator_b200/csrc/scene_build.cpp"),
+           os.path.join(ROOT, "soft-body-simulator_b200/csrc/scene_build.h")]
+    if not _newer(lib, src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", lib, src[0], src[1]])
+    L = C.CDLL(lib)
+    L.hs_boundary.argtypes = [C.c_int64, C.c_int64, u32p, u32p, u32p, i64p]
+    L.hs_colour.argtypes = [C.c_int64, C.c_int64, C.c_int, u32p, dp, u32p, i64p, C.c_int, i32p]
+    L.hs_regions.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, i32p, i32p, i32p]
+    L.hs_regions.restype = C.c_int64
+    return L
+
+
+@pytest.fixture(scope="session")
+def hostmath():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    os.makedirs(BUILD, exist_ok=True)
+    lib = os.path.join(BUILD, "libhostmath.so")
+    src = [os.path.join(HERE, "host_math.cu"), os.path.join(ROOT, "soft-body-simulator_b200/csrc/xpbd_math.cuh"),
+           os.path.join(ROOT, "soft-body-simulator_b200/csrc/xpbd_kernels.cuh")]
+    if not _newer(lib, src):
+        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC",
+                               "-shared", "-o", lib, src[0]])
+    L = C.CDLL(lib)
+    for f in (L.hostmath_green_project_f64, L.hostmath_green_project_f32):
+        f.argtypes = [dp, dp, dp, dp] + [C.c_double] * 6 + [dp]
+    return L
+
+
+def test_c_abi_exports_every_declared_symbol(sbs):
+    header = open(os.path.join(ROOT, "include", "sbs_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(sbsb200_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 20
+    assert sorted(sbs.EXPORTS) == declared
+    L = C.CDLL(sbs.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_no_cpu_fallback_create_fails_loudly_without_gpu(sbs):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sbs.SbsError) as e:
+        sbs.Simulation(0, sbs.FP32)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product path must never import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "soft-body-simulator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("test oracle", "").replace("the oracle", "").lower() \
+                    or f == "scenes.py", os.path.join(dirpath, f)
+    out = subprocess.run(["ldd", os.path.join(pkg, "lib", "libsbsb200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "sbsref" not in out
+
+
+@pytest.mark.parametrize("dims", [(2, 2, 2), (4, 3, 5), (9, 8, 7)])
+def test_boundary_matches_oracle_numbering(hostscene, oracle, dims):
+    pos, tets = oracle.bar_model(*dims)
+    tets = np.ascontiguousarray(tets, np.uint32)
+    nV, nT = len(pos), len(tets)
+    s2t = np.empty(nV, np.uint32)
+    tris = np.empty((4 * nT, 3), np.uint32)
+    ntri = C.c_int64(0)
+    nvs = hostscene.hs_boundary(nV, nT, tets.ctypes.data_as(u32p), s2t.ctypes.data_as(u32p),
+                                tris.ctypes.data_as(u32p), C.byref(ntri))
+    exp_s2t, exp_tris = oracle.boundary_surface(nV, tets)
+    assert np.array_equal(s2t[:nvs], exp_s2t)
+    assert np.array_equal(tris[:ntri.value], exp_tris)
+    W, H, D = dims
+    assert nvs == W * H * D - max(W - 2, 0) * max(H - 2, 0) * max(D - 2, 0)
+
+
+def test_boundary_of_irregular_mesh_with_dangling_face(hostscene, oracle):
+    # two tets sharing a face + one tet sharing only an edge: non-manifold input
+    tets = np.array([[0, 1, 2, 3], [1, 2, 3, 4], [0, 1, 5, 6]], np.uint32)
+    s2t = np.empty(7, np.uint32)
+    ntri = C.c_int64(0)
+    nvs = hostscene.hs_boundary(7, 3, tets.ctypes.data_as(u32p), s2t.ctypes.data_as(u32p), None, C.byref(ntri))
+    exp, _ = oracle.boundary_surface(7, tets)
+    assert np.array_equal(s2t[:nvs], exp) and ntri.value == 10
+
+
+@pytest.mark.parametrize("dims", [(3, 3, 3), (8, 8, 16), (21, 21, 51)])
+def test_colouring_is_conflict_free_and_a_permutation(hostscene, oracle, dims):
+    pos, tets = oracle.bar_model(*dims)
+    tets = np.ascontiguousarray(tets, np.uint32)
+    x0 = pos.astype(np.float64)
+    n = len(tets)
+    order = np.empty(n, np.uint32)
+    offsets = np.zeros(300, np.int64)
+    valid = C.c_int32(0)
+    nc = hostscene.hs_colour(len(pos), n, 4, tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp),
+                             order.ctypes.data_as(u32p), offsets.ctypes.data_as(i64p), 256, C.byref(valid))
+    assert 0 < nc <= 48 and valid.value == 1
+    assert np.array_equal(np.sort(order), np.arange(n))
+    assert offsets[0] == 0 and offsets[nc] == n and np.all(np.diff(offsets[:nc + 1]) > 0)
+    # independent check of vertex-disjointness per colour
+    for c in range(nc):
+        vs = tets[order[offsets[c]:offsets[c + 1]]].reshape(-1)
+        assert len(np.unique(vs)) == len(vs)
+
+
+def test_colouring_reports_capacity_overflow(hostscene):
+    # a fan of 40 tets around one edge needs 40 colours
+    n = 40
+    tets = np.array([[0, 1, 2 + i, 3 + i] for i in range(n)], np.uint32)
+    x0 = np.random.default_rng(0).normal(size=(n + 3, 3))
+    order = np.empty(n, np.uint32)
+    offsets = np.zeros(300, np.int64)
+    valid = C.c_int32(0)
+    assert hostscene.hs_colour(n + 3, n, 4, tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp),
+                               order.ctypes.data_as(u32p), offsets.ctypes.data_as(i64p), 16, C.byref(valid)) < 0
+    assert hostscene.hs_colour(n + 3, n, 4, tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp),
+                               order.ctypes.data_as(u32p), offsets.ctypes.data_as(i64p), 64, C.byref(valid)) == n
+
+
+def test_empty_inputs(hostscene):
+    order = np.empty(1, np.uint32)
+    offsets = np.zeros(4, np.int64)
+    valid = C.c_int32(0)
+    x0 = np.zeros((1, 3))
+    tets = np.zeros((1, 4), np.uint32)
+    assert hostscene.hs_colour(0, 0, 4, tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp),
+                               order.ctypes.data_as(u32p), offsets.ctypes.data_as(i64p), 256, C.byref(valid)) == 0
+    s2t = np.empty(1, np.uint32)
+    ntri = C.c_int64(0)
+    assert hostscene.hs_boundary(0, 0, tets.ctypes.data_as(u32p), s2t.ctypes.data_as(u32p), None, C.byref(ntri)) == 0
+
+
+@pytest.mark.parametrize("regions", [1, 8, 37])
+def test_region_plan_partitions_tets_and_classifies_vertices(hostscene, oracle, regions):
+    pos, tets = oracle.bar_model(9, 9, 17)
+    tets = np.ascontiguousarray(tets, np.uint32)
+    x0 = pos.astype(np.float64)
+    treg = np.empty(len(tets), np.int32)
+    vreg = np.empty(len(pos), np.int32)
+    nnb = np.zeros(regions, np.int32)
+    n_if = hostscene.hs_regions(len(pos), len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), regions,
+                                treg.ctypes.data_as(i32p), vreg.ctypes.data_as(i32p), nnb.ctypes.data_as(i32p))
+    counts = np.bincount(treg, minlength=regions)
+    assert counts.min() >= len(tets) // regions - 1 and counts.max() <= len(tets) // regions + 1
+    # a vertex is interior to r iff all its tets are in r
+    owner = np.full(len(pos), -2, np.int64)
+    for t, r in zip(tets, treg):
+        for v in t:
+            owner[v] = r if owner[v] in (-2, r) else -1
+    assert np.array_equal(np.where(owner >= 0, owner, -1), vreg)
+    assert n_if == int((vreg < 0).sum())
+    if regions == 1:
+        assert n_if == 0 and nnb[0] == 0
+    else:
+        assert (nnb > 0).all()
+
+
+def _host_project(fn, xi, xn, w, DmInv, V0, E, nu, alpha, beta, dt, lam):
+    xi = np.ascontiguousarray(xi, float).reshape(12).copy()
+    xn = np.ascontiguousarray(xn, float).reshape(12)
+    w = np.ascontiguousarray(w, float)
+    D = np.ascontiguousarray(DmInv, float).reshape(9)
+    l = np.array([lam], float)
+    mu = E / (2 * (1 + nu))
+    la = E * nu / ((1 + nu) * (1 - 2 * nu))
+    fn(xi.ctypes.data_as(dp), xn.ctypes.data_as(dp), w.ctypes.data_as(dp), D.ctypes.data_as(dp), V0, mu, la, alpha,
+       beta, dt, l.ctypes.data_as(dp))
+    return xi.reshape(4, 3), l[0]
+
+
+def test_device_math_on_host_matches_oracle(hostmath, oracle):
+    """The product replaces the general SVD by an eigen-decomposition of F^T F; check that
+    algebra (same source the kernels compile) against the oracle's SVD-based projection over
+    stretched, compressed-below-clamp, inverted, pinned and damped cases."""
+    rng = np.random.default_rng(1)
+    worst64 = worst32 = 0.0
+    n_inv = n_clamp = 0
+    for it in range(4000):
+        x0 = rng.normal(size=(4, 3))
+        DmInv, V0 = oracle.green_rest_state(x0)
+        if abs(V0) < 0.02:
+            continue
+        mode = it % 4
+        A = (np.eye(3) + 0.05 * rng.normal(size=(3, 3)), np.eye(3) + 0.3 * rng.normal(size=(3, 3)),
+             np.diag([1.1, 0.95, 1.0]) + 0.02 * rng.normal(size=(3, 3)), rng.normal(size=(3, 3)))[mode]
+        Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(Q) < 0:
+            Q[:, 0] *= -1
+        xi = (x0 @ A.T) @ Q.T + rng.normal(size=3)
+        xn = xi + 0.01 * rng.normal(size=(4, 3))
+        w = rng.uniform(0.5, 2, size=4)
+        if it % 9 == 0:
+            w[it % 4] = 0
+        beta = 0.0 if it % 3 else 1e-3
+        lam = -1e-7 * rng.uniform()
+        ref_xi, ref_lam, ran, diag = oracle.green_project(xi, xn, w, DmInv, V0, 1e6, 0.3, 1e-4, beta, 0.0016, lam)
+        n_inv += diag[6] > 0
+        n_clamp += diag[2] < 0.577
+        a, al = _host_project(hostmath.hostmath_green_project_f64, xi, xn, w, DmInv, V0, 1e6, 0.3, 1e-4, beta, 0.0016, lam)
+        b, bl = _host_project(hostmath.hostmath_green_project_f32, xi, xn, w, DmInv, V0, 1e6, 0.3, 1e-4, beta, 0.0016, lam)
+        scale = max(1.0, np.abs(ref_xi - xi).max())
+        worst64 = max(worst64, np.abs(a - ref_xi).max() / scale)
+        worst32 = max(worst32, np.abs(b - ref_xi).max() / scale)
+        assert al == pytest.approx(ref_lam, rel=1e-9, abs=1e-18)
+    assert n_inv > 100 and n_clamp > 100
+    assert worst64 < 1e-11, worst64
+    assert worst32 < 5e-5, worst32
+
+
+def test_device_math_rest_state_early_out(hostmath, oracle):
+    x0 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float)
+    DmInv, V0 = oracle.green_rest_state(x0)
+    for fn in (hostmath.hostmath_green_project_f64, hostmath.hostmath_green_project_f32):
+        out, lam = _host_project(fn, x0, x0, np.ones(4), DmInv, V0, 1e6, 0.3, 1e-4, 0.0, 0.0016, 0.0)
+        assert np.array_equal(out, x0) and lam == 0.0
