@@ -134,6 +134,9 @@ int64_t sbsb200_get_surface_map(const sbsb200_ctx* ctx, int body, uint32_t* map,
 
 int sbsb200_get_stats(const sbsb200_ctx* ctx, sbsb200_stats* out);
 
+/* Why the schedule in use differs from the requested one ("" when it does not). */
+const char* sbsb200_schedule_note(const sbsb200_ctx* ctx);
+
 /* ---- state ----------------------------------------------------------------------------- */
 
 /* Overwrite x (and v, NULL = 0) of a body; xi = xn = x as tetrahedral_body_t::transform

@@ -25,6 +25,7 @@ EXPORTS = [
     "sbsb200_set_collision_compliance", "sbsb200_add_tet_body", "sbsb200_add_distance_constraints",
     "sbsb200_add_sdf_plane", "sbsb200_add_sdf_sphere", "sbsb200_add_sdf_box", "sbsb200_finalize",
     "sbsb200_constraint_count", "sbsb200_get_constraint_order", "sbsb200_get_surface_map", "sbsb200_get_stats",
+    "sbsb200_schedule_note",
     "sbsb200_upload", "sbsb200_download", "sbsb200_set_mass", "sbsb200_step", "sbsb200_step_host",
     "sbsb200_synchronize", "sbsb200_get_contacts",
 ]
@@ -79,6 +80,8 @@ def load_library():
     L.sbsb200_get_surface_map.argtypes = [vp, C.c_int, _u32p, C.c_int64]
     L.sbsb200_get_surface_map.restype = C.c_int64
     L.sbsb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.sbsb200_schedule_note.argtypes = [vp]
+    L.sbsb200_schedule_note.restype = C.c_char_p
     L.sbsb200_upload.argtypes = [vp, C.c_int, _dp, _dp]
     L.sbsb200_download.argtypes = [vp, C.c_int, _dp, _dp]
     L.sbsb200_set_mass.argtypes = [vp, C.c_int, C.c_int64, C.c_double]
@@ -183,6 +186,9 @@ class Simulation:
         s = Stats()
         self._ck(self._L.sbsb200_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def schedule_note(self):
+        return self._L.sbsb200_schedule_note(self._h).decode()
 
     def upload(self, body, x, v=None):
         x = _f64(x)

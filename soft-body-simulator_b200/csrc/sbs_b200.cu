@@ -94,7 +94,8 @@ struct sbsb200_ctx
     int schedule_request    = SBSB200_SCHED_AUTO;
     int schedule            = SBSB200_SCHED_GRAPH;
     double collision_alpha  = 1e-8; // simulation_parameters.h:24
-    ColourClass green_cc, dist_cc;
+    ClusterPlan green_plan;
+    ColourClass dist_cc;
     RegionPlan plan;
     std::vector<uint32_t> order; // exported serial order (insertion indices)
     std::vector<int32_t> vertex_body;
@@ -107,6 +108,7 @@ struct sbsb200_ctx
     int sm_count          = 0;
     int64_t n_surface     = 0;
     bool any_damping      = false;
+    std::string schedule_note;
 };
 
 namespace {
@@ -122,7 +124,7 @@ struct Engine final : EngineBase
     DevBuf<uint4> tet_v;
     DevBuf<uint2> dist_v;
     DevBuf<R> tet_lambda, dist_lambda;
-    DevBuf<uint32_t> surf_v, contact_v, contact_count;
+    DevBuf<uint32_t> surf_v, surf_first, contact_v, contact_count;
     DevBuf<int32_t> surf_body;
     DevBuf<typename DeviceScene<R>::Sdf> sdf;
     DevBuf<double> stage_x, stage_v; // raw host-format staging for upload/download
@@ -164,7 +166,7 @@ struct Engine final : EngineBase
         std::vector<Real4<R>> r0(static_cast<size_t>(T)), r1(static_cast<size_t>(T)), r2(static_cast<size_t>(T));
         for (int64_t p = 0; p < T; ++p)
         {
-            uint32_t const t  = c.green_cc.order[static_cast<size_t>(p)];
+            uint32_t const t  = c.green_plan.storage_order[static_cast<size_t>(p)];
             uint32_t const* v = &h.tets[4 * static_cast<size_t>(t)];
             hv[static_cast<size_t>(p)] = make_uint4(v[0], v[1], v[2], v[3]);
             // Dm columns x0_1-x0_4, x0_2-x0_4, x0_3-x0_4 (green_constraint.cpp:38-41)
@@ -251,6 +253,8 @@ struct Engine final : EngineBase
         surf_v.upload(sv, st);
         surf_body.upload(sb, st);
         surf_pos.alloc(static_cast<size_t>(Vs));
+        surf_first.alloc(static_cast<size_t>(Vs));
+        CK(cudaMemsetAsync(surf_first.p, 0xff, sizeof(uint32_t) * std::max<int64_t>(Vs, 1), st));
         sdf.upload(hs, st);
         int64_t const cap = Vs * static_cast<int64_t>(hs.size());
         contact_v.alloc(static_cast<size_t>(cap));
@@ -278,6 +282,7 @@ struct Engine final : EngineBase
         d.surf_v          = surf_v.p;
         d.surf_body       = surf_body.p;
         d.surf_pos        = surf_pos.p;
+        d.surf_first      = surf_first.p;
         d.n_sdf           = static_cast<int32_t>(hs.size());
         d.sdf             = sdf.p;
         d.contact_cap     = cap;
@@ -294,7 +299,22 @@ struct Engine final : EngineBase
             ++c.kernels;
         }
         if (c.schedule == SBSB200_SCHED_PERSISTENT)
-            pp.build(c.scene, c.green_cc, c.plan, d, st, c.sm_count);
+        {
+            bool ok = false;
+            try
+            {
+                ok = pp.build(c.scene, c.green_plan, c.plan, d, st, c.sm_count);
+            }
+            catch (std::exception const& e)
+            {
+                pp.why_not = e.what();
+            }
+            if (!ok)
+            { // the (colour, region) order is still a valid colouring for the per-colour kernels
+                c.schedule      = SBSB200_SCHED_GRAPH;
+                c.schedule_note = "persistent schedule unavailable: " + pp.why_not;
+            }
+        }
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
     }
@@ -326,7 +346,7 @@ struct Engine final : EngineBase
                 detect_now();
             if (c.schedule == SBSB200_SCHED_PERSISTENT)
             {
-                launched += pp.substep(d, dt, iterations, collide, c.any_damping, st);
+                launched += pp.substep(d, dt, iterations, collide, st);
             }
             else
             {
@@ -344,17 +364,27 @@ struct Engine final : EngineBase
                         ++launched;
                     }
                     // gauss_seidel_solver.cpp:32-35 in the exported colour order
-                    for (int32_t col = 0; col < c.green_cc.n_colours; ++col)
+                    for (int32_t col = 0; col < c.green_plan.n_colours; ++col)
                     {
-                        int64_t const b = c.green_cc.offsets[col], e = c.green_cc.offsets[col + 1];
-                        if (e == b)
-                            continue;
-                        unsigned const g = static_cast<unsigned>((e - b + 127) / 128);
-                        if (c.any_damping)
-                            k_project_green<R, true><<<g, 128, 0, st>>>(d, b, static_cast<int32_t>(e - b), dt, first);
-                        else
-                            k_project_green<R, false><<<g, 128, 0, st>>>(d, b, static_cast<int32_t>(e - b), dt, first);
-                        ++launched;
+                        ChunkDesc const& hd = c.green_plan.chunks[static_cast<size_t>(col) * c.green_plan.n_regions];
+                        // graph schedule after a failed persistent build: regions of one colour are
+                        // adjacent in storage, but each has its own column layout -> one launch each
+                        for (int32_t reg = 0; reg < c.green_plan.n_regions; ++reg)
+                        {
+                            ChunkDesc const& h2 = (&hd)[reg];
+                            if (h2.n[0] == 0)
+                                continue;
+                            DevChunk dc;
+                            dc.first = h2.first;
+                            for (int m = 0; m < 8; ++m)
+                                dc.n[m] = h2.n[m];
+                            unsigned const g = static_cast<unsigned>((h2.n[0] + 127) / 128);
+                            if (c.any_damping)
+                                k_project_green<R, true><<<g, 128, 0, st>>>(d, dc, dt, first);
+                            else
+                                k_project_green<R, false><<<g, 128, 0, st>>>(d, dc, dt, first);
+                            ++launched;
+                        }
                     }
                     for (int32_t col = 0; col < c.dist_cc.n_colours; ++col)
                     {
@@ -372,14 +402,14 @@ struct Engine final : EngineBase
                     ++launched;
                 }
             }
-            if (detect == SBSB200_DETECT_PER_SUBSTEP && d.n_surface > 0)
+            if (detect == SBSB200_DETECT_PER_SUBSTEP && d.n_surface > 0 && c.schedule != SBSB200_SCHED_PERSISTENT)
             {
                 k_surface_gather<R><<<gridS, 256, 0, st>>>(d);
                 ++launched;
             }
         }
-        if (detect == SBSB200_DETECT_PER_FRAME && d.n_surface > 0)
-        { // timestep.cpp:60-66
+        if (detect == SBSB200_DETECT_PER_FRAME && d.n_surface > 0 && c.schedule != SBSB200_SCHED_PERSISTENT)
+        { // timestep.cpp:60-66 (the persistent kernel writes the surface copy itself)
             k_surface_gather<R><<<gridS, 256, 0, st>>>(d);
             ++launched;
         }
@@ -391,6 +421,13 @@ struct Engine final : EngineBase
     {
         cudaStream_t st = c.stream;
         CK(cudaEventRecord(c.ev0, st));
+        if (c.schedule == SBSB200_SCHED_PERSISTENT)
+        { // a handful of launches per frame, and the progress base changes every launch: no graph
+            c.kernels += enqueue(c, dt, substeps, iterations, detect, st);
+            CK(cudaEventRecord(c.ev1, st));
+            c.timed = true;
+            return;
+        }
         auto const key = std::make_tuple(dt, substeps, iterations, detect);
         auto it        = graphs.find(key);
         if (it == graphs.end())
@@ -804,30 +841,37 @@ int sbsb200_finalize(sbsb200_ctx* c)
         for (Material const& m : h.materials)
             c->any_damping = c->any_damping || m.beta != 0.;
 
-        std::vector<uint64_t> tkeys, dkeys;
-        morton_keys(T, 4, h.tets.data(), h.x0.data(), V, tkeys);
+        std::vector<uint64_t> dkeys;
         morton_keys(D, 2, h.dist_pairs.data(), h.x0.data(), V, dkeys);
 
-        // schedule choice
-        c->schedule = c->schedule_request == SBSB200_SCHED_AUTO ? SBSB200_SCHED_GRAPH : c->schedule_request;
-        if (c->schedule == SBSB200_SCHED_PERSISTENT && (D > 0 || T == 0))
-            c->schedule = SBSB200_SCHED_GRAPH; // distance constraints are not region-partitioned
+        // schedule choice: the persistent kernel covers Green + collision constraints without
+        // damping; distance constraints and beta != 0 (which needs xn in the projection) take
+        // the per-colour kernels
+        bool const persistent_ok = T > 0 && D == 0 && !c->any_damping;
+        c->schedule = c->schedule_request == SBSB200_SCHED_GRAPH ? SBSB200_SCHED_GRAPH : SBSB200_SCHED_PERSISTENT;
+        if (c->schedule == SBSB200_SCHED_PERSISTENT && !persistent_ok)
+        {
+            c->schedule      = SBSB200_SCHED_GRAPH;
+            c->schedule_note = "persistent schedule needs tets, no distance constraints and beta = 0";
+        }
 
-        int32_t const* region = nullptr;
         if (c->schedule == SBSB200_SCHED_PERSISTENT)
         {
-            plan_regions(h, tkeys, PersistentPlan<float>::regions_for(c->sm_count, T), c->plan);
-            region = c->plan.tet_region.data();
+            build_cluster_plan(h, PersistentPlan<float>::regions_for(c->sm_count, T),
+                               PersistentPlan<float>::wants_region_per_body(h, c->sm_count), c->green_plan);
+            classify_regions(h, c->green_plan.tet_region, c->green_plan.n_regions, c->plan);
         }
-        if (!colour_constraints(V, T, 4, h.tets.data(), tkeys.data(), region, 256, c->green_cc))
-            return fail(c, SBSB200_ERR_CAPACITY, "more than 256 colours needed for the tet mesh");
+        else
+            build_cluster_plan(h, 1, false, c->green_plan);
+        if (!cluster_plan_is_valid(h, c->green_plan))
+            return fail(c, SBSB200_ERR_CAPACITY, "clustered colouring failed (more than 128 colours needed?)");
         if (!colour_constraints(V, D, 2, h.dist_pairs.data(), dkeys.data(), nullptr, 256, c->dist_cc))
             return fail(c, SBSB200_ERR_CAPACITY, "more than 256 colours needed for the distance constraints");
 
         // exported serial order: green colours, then distance colours
         c->order.clear();
         c->order.reserve(static_cast<size_t>(T + D));
-        for (uint32_t t : c->green_cc.order)
+        for (uint32_t t : c->green_plan.serial_order)
             c->order.push_back(h.tet_insertion[t]);
         for (uint32_t i : c->dist_cc.order)
             c->order.push_back(h.dist_insertion[i]);
@@ -877,7 +921,7 @@ int sbsb200_get_stats(const sbsb200_ctx* cc, sbsb200_stats* out)
     out->n_tets               = c->scene.n_tets();
     out->n_distance           = c->scene.n_dist();
     out->n_surface_vertices   = c->n_surface;
-    out->n_green_colours      = c->green_cc.n_colours;
+    out->n_green_colours      = c->green_plan.n_colours;
     out->n_distance_colours   = c->dist_cc.n_colours;
     out->schedule             = c->schedule;
     out->n_regions            = c->plan.n_regions;
@@ -894,6 +938,8 @@ int sbsb200_get_stats(const sbsb200_ctx* cc, sbsb200_stats* out)
     }
     return SBSB200_OK;
 }
+
+const char* sbsb200_schedule_note(const sbsb200_ctx* c) { return c ? c->schedule_note.c_str() : ""; }
 
 int sbsb200_upload(sbsb200_ctx* c, int body, const double* x, const double* v)
 {

@@ -218,9 +218,17 @@ bool colouring_is_valid(int64_t n_vertices, int k, uint32_t const* verts, Colour
 // regions
 // ---------------------------------------------------------------------------------------------
 void plan_regions(HostScene const& scene, std::vector<uint64_t> const& tet_keys, int32_t n_regions,
-                  RegionPlan& plan)
+                  RegionPlan& plan, bool one_region_per_body)
 {
-    int64_t const T = scene.n_tets(), V = scene.n_vertices();
+    int64_t const T = scene.n_tets();
+    std::vector<int32_t> body_region(scene.bodies.size(), -1);
+    if (one_region_per_body)
+    {
+        n_regions = 0;
+        for (size_t b = 0; b < scene.bodies.size(); ++b)
+            if (scene.bodies[b].kind == BodyKind::tet && scene.bodies[b].n_tets > 0)
+                body_region[b] = n_regions++;
+    }
     n_regions       = std::max<int32_t>(1, n_regions);
     plan            = RegionPlan{};
     plan.n_regions  = n_regions;
@@ -241,9 +249,24 @@ void plan_regions(HostScene const& scene, std::vector<uint64_t> const& tet_keys,
         return tet_keys[a] < tet_keys[b];
     });
     for (int64_t p = 0; p < T; ++p)
-        plan.tet_region[by_key[static_cast<size_t>(p)]] =
-            static_cast<int32_t>((p * static_cast<int64_t>(n_regions)) / std::max<int64_t>(T, 1));
+    {
+        uint32_t const t = by_key[static_cast<size_t>(p)];
+        plan.tet_region[t] = one_region_per_body
+                                 ? body_region[static_cast<size_t>(tet_body[t])]
+                                 : static_cast<int32_t>((p * static_cast<int64_t>(n_regions)) / std::max<int64_t>(T, 1));
+    }
 
+    classify_regions(scene, plan.tet_region, n_regions, plan);
+}
+
+void classify_regions(HostScene const& scene, std::vector<int32_t> const& tet_region_in, int32_t n_regions,
+                      RegionPlan& plan)
+{
+    int64_t const T = scene.n_tets(), V = scene.n_vertices();
+    std::vector<int32_t> const tet_region_copy = tet_region_in;
+    plan                                       = RegionPlan{};
+    plan.n_regions                             = n_regions;
+    plan.tet_region                            = tet_region_copy;
     // vertex ownership: -2 = untouched so far, r >= 0 = only region r so far, -1 = interface
     plan.vertex_region.assign(static_cast<size_t>(V), -2);
     for (int64_t t = 0; t < T; ++t)
@@ -259,6 +282,20 @@ void plan_regions(HostScene const& scene, std::vector<uint64_t> const& tet_keys,
     // vertices touched by distance constraints stay global
     for (uint32_t v : scene.dist_pairs)
         plan.vertex_region[v] = -1;
+
+    // owner of every vertex: its region when interior, the lowest sharing region when on an
+    // interface, round-robin for vertices no tet touches (they still fall under gravity)
+    plan.vertex_owner.assign(static_cast<size_t>(V), -1);
+    for (int64_t t = 0; t < T; ++t)
+        for (int a = 0; a < 4; ++a)
+        {
+            int32_t& o      = plan.vertex_owner[scene.tets[4 * static_cast<size_t>(t) + a]];
+            int32_t const r = plan.tet_region[static_cast<size_t>(t)];
+            o               = o < 0 ? r : std::min(o, r);
+        }
+    for (int64_t v = 0; v < V; ++v)
+        if (plan.vertex_owner[static_cast<size_t>(v)] < 0)
+            plan.vertex_owner[static_cast<size_t>(v)] = static_cast<int32_t>(v % n_regions);
 
     plan.region_vtx_offsets.assign(static_cast<size_t>(n_regions) + 1, 0);
     plan.vertex_slot.assign(static_cast<size_t>(V), 0);
@@ -325,6 +362,273 @@ void plan_regions(HostScene const& scene, std::vector<uint64_t> const& tet_keys,
     plan.nbr.resize(edges.size());
     for (size_t i = 0; i < edges.size(); ++i)
         plan.nbr[i] = edges[i].second; // edges sorted by (first, second) => grouped by region
+}
+
+// ---------------------------------------------------------------------------------------------
+// clustered colouring
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Cluster
+{
+    int32_t body;
+    uint32_t cx, cy, cz; // grid cell
+    uint64_t morton;
+    uint32_t first, count; // range in the (body, cell)-sorted tet list
+    int32_t colour = -1, region = 0;
+};
+} // namespace
+
+void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_region_per_body, ClusterPlan& out)
+{
+    int64_t const T = scene.n_tets(), V = scene.n_vertices();
+    out             = ClusterPlan{};
+    out.tet_region.assign(static_cast<size_t>(T), 0);
+    if (T == 0)
+    {
+        out.n_regions = std::max<int32_t>(1, one_region_per_body ? 1 : n_regions);
+        out.chunks.clear();
+        return;
+    }
+    constexpr double kTargetTets = 5.0;
+
+    // per tet: body, rest centroid, |rest volume|
+    std::vector<int32_t> tet_body(static_cast<size_t>(T), 0);
+    for (size_t b = 0; b < scene.bodies.size(); ++b)
+        if (scene.bodies[b].kind == BodyKind::tet)
+            for (int64_t t = scene.bodies[b].t_offset; t < scene.bodies[b].t_offset + scene.bodies[b].n_tets; ++t)
+                tet_body[static_cast<size_t>(t)] = static_cast<int32_t>(b);
+
+    std::vector<uint32_t> sorted(static_cast<size_t>(T));
+    std::vector<std::array<uint32_t, 3>> cell(static_cast<size_t>(T));
+    for (size_t b = 0; b < scene.bodies.size(); ++b)
+    {
+        HostBody const& hb = scene.bodies[b];
+        if (hb.kind != BodyKind::tet || hb.n_tets == 0)
+            continue;
+        double lo[3] = {1e300, 1e300, 1e300};
+        for (int64_t v = hb.v_offset; v < hb.v_offset + hb.n_vertices; ++v)
+            for (int d = 0; d < 3; ++d)
+                lo[d] = std::min(lo[d], scene.x0[3 * static_cast<size_t>(v) + d]);
+        double vol = 0;
+        for (int64_t t = hb.t_offset; t < hb.t_offset + hb.n_tets; ++t)
+        {
+            uint32_t const* v = &scene.tets[4 * static_cast<size_t>(t)];
+            double e[3][3];
+            for (int k = 0; k < 3; ++k)
+                for (int d = 0; d < 3; ++d)
+                    e[k][d] = scene.x0[3 * static_cast<size_t>(v[k]) + d] - scene.x0[3 * static_cast<size_t>(v[3]) + d];
+            vol += std::abs(e[0][0] * (e[1][1] * e[2][2] - e[1][2] * e[2][1]) -
+                            e[0][1] * (e[1][0] * e[2][2] - e[1][2] * e[2][0]) +
+                            e[0][2] * (e[1][0] * e[2][1] - e[1][1] * e[2][0])) / 6.0;
+        }
+        double h = std::cbrt(kTargetTets * vol / static_cast<double>(hb.n_tets));
+        if (!(h > 0) || !std::isfinite(h))
+            h = 1.0;
+        // snap h so that tiny rounding of the cube root cannot drift the grid across a big lattice
+        double const snapped = std::round(h * 1048576.0) / 1048576.0;
+        h                    = snapped > 0 ? snapped : h;
+        for (int64_t t = hb.t_offset; t < hb.t_offset + hb.n_tets; ++t)
+        {
+            uint32_t const* v = &scene.tets[4 * static_cast<size_t>(t)];
+            for (int d = 0; d < 3; ++d)
+            {
+                double c = 0;
+                for (int k = 0; k < 4; ++k)
+                    c += scene.x0[3 * static_cast<size_t>(v[k]) + d];
+                double const u = (c * 0.25 - lo[d]) / h;
+                cell[static_cast<size_t>(t)][d] =
+                    static_cast<uint32_t>(std::min(1048575.0, std::max(0.0, std::floor(u))));
+            }
+        }
+    }
+    std::iota(sorted.begin(), sorted.end(), 0u);
+    std::stable_sort(sorted.begin(), sorted.end(), [&](uint32_t a, uint32_t b) {
+        if (tet_body[a] != tet_body[b])
+            return tet_body[a] < tet_body[b];
+        return cell[a] < cell[b]; // raster order (x, y, z); stable => insertion order inside a cell
+    });
+
+    // clusters: runs of equal (body, cell), split at kMaxCluster
+    std::vector<Cluster> clusters;
+    for (int64_t p = 0; p < T;)
+    {
+        int64_t q = p;
+        while (q < T && q - p < kMaxCluster && tet_body[sorted[q]] == tet_body[sorted[p]] &&
+               cell[sorted[q]] == cell[sorted[p]])
+            ++q;
+        Cluster c;
+        c.body   = tet_body[sorted[p]];
+        c.cx     = cell[sorted[p]][0];
+        c.cy     = cell[sorted[p]][1];
+        c.cz     = cell[sorted[p]][2];
+        c.morton = spread10(c.cx) | (spread10(c.cy) << 1) | (spread10(c.cz) << 2) |
+                   ((static_cast<uint64_t>(c.cx >> 10) ^ (c.cy >> 10) ^ (c.cz >> 10)) << 30);
+        c.first  = static_cast<uint32_t>(p);
+        c.count  = static_cast<uint32_t>(q - p);
+        clusters.push_back(c);
+        p = q;
+    }
+    out.n_clusters = static_cast<int64_t>(clusters.size());
+
+    // first-fit colouring in (body, raster) order; same-colour clusters must be vertex-disjoint
+    {
+        constexpr int kWords = 2; // up to 128 cluster colours
+        std::vector<std::array<uint64_t, kWords>> used(static_cast<size_t>(V), std::array<uint64_t, kWords>{});
+        for (Cluster& c : clusters)
+        {
+            std::array<uint64_t, kWords> mask{};
+            for (uint32_t p = c.first; p < c.first + c.count; ++p)
+                for (int a = 0; a < 4; ++a)
+                {
+                    auto const& u = used[scene.tets[4 * static_cast<size_t>(sorted[p]) + a]];
+                    for (int w = 0; w < kWords; ++w)
+                        mask[w] |= u[w];
+                }
+            int32_t col = -1;
+            for (int w = 0; w < kWords && col < 0; ++w)
+                if (~mask[w])
+                    col = 64 * w + __builtin_ctzll(~mask[w]);
+            if (col < 0)
+                col = 64 * kWords - 1; // cannot happen for sane meshes; validity check will flag it
+            c.colour      = col;
+            out.n_colours = std::max(out.n_colours, col + 1);
+            for (uint32_t p = c.first; p < c.first + c.count; ++p)
+                for (int a = 0; a < 4; ++a)
+                    used[scene.tets[4 * static_cast<size_t>(sorted[p]) + a]][col >> 6] |= (1ull << (col & 63));
+        }
+    }
+
+    // regions
+    if (one_region_per_body)
+    {
+        std::vector<int32_t> body_region(scene.bodies.size(), -1);
+        int32_t nr = 0;
+        for (size_t b = 0; b < scene.bodies.size(); ++b)
+            if (scene.bodies[b].kind == BodyKind::tet && scene.bodies[b].n_tets > 0)
+                body_region[b] = nr++;
+        out.n_regions = std::max<int32_t>(1, nr);
+        for (Cluster& c : clusters)
+            c.region = body_region[static_cast<size_t>(c.body)];
+    }
+    else if (n_regions > 1)
+    {
+        out.n_regions = n_regions;
+        std::vector<uint32_t> idx(clusters.size());
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+            if (clusters[a].body != clusters[b].body)
+                return clusters[a].body < clusters[b].body;
+            return clusters[a].morton < clusters[b].morton;
+        });
+        int64_t seen = 0;
+        for (uint32_t i : idx)
+        { // balanced by tet count: cluster goes to the region its first tet falls into
+            clusters[i].region = static_cast<int32_t>(std::min<int64_t>(n_regions - 1, (seen * n_regions) / T));
+            seen += clusters[i].count;
+        }
+    }
+    else
+        out.n_regions = 1;
+
+    // final order: (colour, region, size descending, morton)
+    std::vector<uint32_t> idx(clusters.size());
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+        Cluster const &x = clusters[a], &y = clusters[b];
+        if (x.colour != y.colour)
+            return x.colour < y.colour;
+        if (x.region != y.region)
+            return x.region < y.region;
+        if (x.count != y.count)
+            return x.count > y.count;
+        if (x.body != y.body)
+            return x.body < y.body;
+        return x.morton < y.morton;
+    });
+
+    size_t const n_chunks = static_cast<size_t>(out.n_colours) * static_cast<size_t>(out.n_regions);
+    out.chunks.assign(n_chunks, ChunkDesc{});
+    out.storage_order.resize(static_cast<size_t>(T));
+    out.serial_order.reserve(static_cast<size_t>(T));
+    int64_t store = 0;
+    size_t i      = 0;
+    for (size_t ch = 0; ch < n_chunks; ++ch)
+    {
+        int32_t const col = static_cast<int32_t>(ch / static_cast<size_t>(out.n_regions));
+        int32_t const reg = static_cast<int32_t>(ch % static_cast<size_t>(out.n_regions));
+        size_t j          = i;
+        while (j < idx.size() && clusters[idx[j]].colour == col && clusters[idx[j]].region == reg)
+            ++j;
+        ChunkDesc& d = out.chunks[ch];
+        d.first      = static_cast<int32_t>(store);
+        for (size_t k = i; k < j; ++k)
+        {
+            Cluster const& c = clusters[idx[k]];
+            for (uint32_t m = 0; m < c.count; ++m)
+            {
+                ++d.n[m];
+                out.serial_order.push_back(sorted[c.first + m]);
+                out.tet_region[sorted[c.first + m]] = reg;
+            }
+        }
+        int64_t col_base = store;
+        for (int m = 0; m < kMaxCluster; ++m)
+        {
+            for (size_t k = i; k < j; ++k)
+            {
+                Cluster const& c = clusters[idx[k]];
+                if (c.count > static_cast<uint32_t>(m))
+                    out.storage_order[static_cast<size_t>(col_base + static_cast<int64_t>(k - i))] = sorted[c.first + m];
+            }
+            col_base += d.n[m];
+        }
+        store = col_base;
+        out.max_chunk_clusters = std::max<int64_t>(out.max_chunk_clusters, static_cast<int64_t>(j - i));
+        i = j;
+    }
+}
+
+bool cluster_plan_is_valid(HostScene const& scene, ClusterPlan const& plan)
+{
+    int64_t const T = scene.n_tets(), V = scene.n_vertices();
+    if (static_cast<int64_t>(plan.storage_order.size()) != T || static_cast<int64_t>(plan.serial_order.size()) != T)
+        return false;
+    std::vector<char> seen(static_cast<size_t>(T), 0);
+    for (uint32_t t : plan.storage_order)
+    {
+        if (t >= T || seen[t])
+            return false;
+        seen[t] = 1;
+    }
+    // per colour: a vertex may only be touched by ONE cluster (identified by chunk + cluster index)
+    std::vector<int64_t> owner(static_cast<size_t>(V), -1);
+    std::vector<int32_t> stamp(static_cast<size_t>(V), -1);
+    int64_t cluster_id = 0;
+    for (int32_t col = 0; col < plan.n_colours; ++col)
+        for (int32_t reg = 0; reg < plan.n_regions; ++reg)
+        {
+            ChunkDesc const& d = plan.chunks[static_cast<size_t>(col) * plan.n_regions + reg];
+            for (int32_t i = 0; i < d.n[0]; ++i, ++cluster_id)
+            {
+                int64_t base = d.first;
+                for (int m = 0; m < kMaxCluster && i < d.n[m]; ++m)
+                {
+                    uint32_t const t = plan.storage_order[static_cast<size_t>(base + i)];
+                    if (plan.tet_region[t] != reg)
+                        return false;
+                    for (int a = 0; a < 4; ++a)
+                    {
+                        uint32_t const v = scene.tets[4 * static_cast<size_t>(t) + a];
+                        if (stamp[v] == col && owner[v] != cluster_id)
+                            return false;
+                        stamp[v] = col;
+                        owner[v] = cluster_id;
+                    }
+                    base += d.n[m];
+                }
+            }
+        }
+    return true;
 }
 
 } // namespace sbsb200

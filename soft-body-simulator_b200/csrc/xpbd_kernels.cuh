@@ -34,6 +34,7 @@ struct DeviceScene
     uint32_t const* surf_v;    // global vertex id of surface vertex i
     int32_t const* surf_body;  // body of surface vertex i
     Real4<R>* surf_pos;        // visual-model copy the detection reads (tetrahedral_body.cpp:157-165)
+    uint32_t* surf_first;      // index of the first contact of surface vertex i, 0xffffffff if none
     int32_t n_sdf;
     struct Sdf
     {
@@ -141,42 +142,60 @@ SBS_HD void green_project(Real4<R>& p1, Real4<R>& p2, Real4<R>& p3, Real4<R>& p4
 __device__ __forceinline__ int mat_index(float v) { return __float_as_int(v); }
 __device__ __forceinline__ int mat_index(double v) { return static_cast<int>(v); }
 
-// One colour of Green constraints: thread per tet.  first_iteration folds the lambda reset of
-// constraint_t::prepare_for_projection (constraint.cpp:12-16) into the first sweep.
+// Chunk descriptor of the clustered colouring (mirrors sbsb200::ChunkDesc in scene_build.h)
+struct DevChunk
+{
+    int32_t first;
+    int32_t n[8];
+};
+
+// One colour of Green constraints: thread per CLUSTER, the cluster's tets one after the other
+// (they share vertices; clusters of one colour do not).  Tet m of cluster i sits at
+// first + n[0] + .. + n[m-1] + i, so every pass over m is a coalesced sweep.  first_iteration
+// folds the lambda reset of constraint_t::prepare_for_projection (constraint.cpp:12-16) into the
+// first sweep.
 template <typename R, bool kDamped>
 __global__ void __launch_bounds__(128)
-k_project_green(DeviceScene<R> s, int64_t first, int32_t count, R dt, int first_iteration)
+k_project_green(DeviceScene<R> s, DevChunk chunk, R dt, int first_iteration)
 {
     int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count)
+    if (i >= chunk.n[0])
         return;
-    int64_t const t  = first + i;
-    uint4 const v    = __ldg(&s.tet_v[t]);
-    Real4<R> const r0 = ld4_ro(&s.tet_r0[t]);
-    Real4<R> const r1 = ld4_ro(&s.tet_r1[t]);
-    Real4<R> const r2 = ld4_ro(&s.tet_r2[t]);
-    Real4<R> p1 = ld4(&s.pos[v.x]), p2 = ld4(&s.pos[v.y]), p3 = ld4(&s.pos[v.z]), p4 = ld4(&s.pos[v.w]);
-    Real4<R> const mat = ld4_ro(&s.materials[mat_index(r2.z)]);
-    R lambda           = first_iteration ? R(0) : s.tet_lambda[t];
-    Vec3<R> xn1{}, xn2{}, xn3{}, xn4{};
-    if (kDamped)
+    int64_t base = chunk.first;
+#pragma unroll 1
+    for (int m = 0; m < 8; ++m)
     {
-        Real4<R> const a = ld4(&s.prev[v.x]), b = ld4(&s.prev[v.y]), c = ld4(&s.prev[v.z]), d = ld4(&s.prev[v.w]);
-        xn1 = {a.x, a.y, a.z};
-        xn2 = {b.x, b.y, b.z};
-        xn3 = {c.x, c.y, c.z};
-        xn4 = {d.x, d.y, d.z};
-    }
-    R const lambda_in = lambda;
-    green_project<R, kDamped>(p1, p2, p3, p4, xn1, xn2, xn3, xn4, r0, r1, r2, mat, dt, lambda);
-    if (lambda != lambda_in || first_iteration)
-        s.tet_lambda[t] = lambda;
-    if (lambda != lambda_in)
-    {
-        st4(&s.pos[v.x], p1);
-        st4(&s.pos[v.y], p2);
-        st4(&s.pos[v.z], p3);
-        st4(&s.pos[v.w], p4);
+        if (i >= chunk.n[m])
+            break;
+        int64_t const t   = base + i;
+        base += chunk.n[m];
+        uint4 const v     = __ldg(&s.tet_v[t]);
+        Real4<R> const r0 = ld4_ro(&s.tet_r0[t]);
+        Real4<R> const r1 = ld4_ro(&s.tet_r1[t]);
+        Real4<R> const r2 = ld4_ro(&s.tet_r2[t]);
+        Real4<R> p1 = ld4(&s.pos[v.x]), p2 = ld4(&s.pos[v.y]), p3 = ld4(&s.pos[v.z]), p4 = ld4(&s.pos[v.w]);
+        Real4<R> const mat = ld4_ro(&s.materials[mat_index(r2.z)]);
+        R lambda           = first_iteration ? R(0) : s.tet_lambda[t];
+        Vec3<R> xn1{}, xn2{}, xn3{}, xn4{};
+        if (kDamped)
+        {
+            Real4<R> const a = ld4(&s.prev[v.x]), b = ld4(&s.prev[v.y]), c = ld4(&s.prev[v.z]), d = ld4(&s.prev[v.w]);
+            xn1 = {a.x, a.y, a.z};
+            xn2 = {b.x, b.y, b.z};
+            xn3 = {c.x, c.y, c.z};
+            xn4 = {d.x, d.y, d.z};
+        }
+        R const lambda_in = lambda;
+        green_project<R, kDamped>(p1, p2, p3, p4, xn1, xn2, xn3, xn4, r0, r1, r2, mat, dt, lambda);
+        if (lambda != lambda_in || first_iteration)
+            s.tet_lambda[t] = lambda;
+        if (lambda != lambda_in)
+        {
+            st4(&s.pos[v.x], p1);
+            st4(&s.pos[v.y], p2);
+            st4(&s.pos[v.z], p3);
+            st4(&s.pos[v.w], p4);
+        }
     }
 }
 
@@ -311,6 +330,8 @@ __global__ void __launch_bounds__(256) k_detect_all(DeviceScene<R> s)
     if (lane == 31 && total > 0)
         base = atomicAdd(s.contact_count, static_cast<uint32_t>(total));
     base = __shfl_sync(0xffffffffu, base, 31);
+    if (valid)
+        s.surf_first[i] = n_mine > 0 ? base + static_cast<uint32_t>(incl - n_mine) : 0xffffffffu;
     if (!valid || n_mine == 0)
         return;
     uint32_t slot      = base + static_cast<uint32_t>(incl - n_mine);

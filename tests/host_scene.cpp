@@ -58,3 +58,45 @@ extern "C" int64_t hs_regions(int64_t nV, int64_t nT, const uint32_t* tets, cons
         n_neighbours[r] = plan.nbr_offsets[r + 1] - plan.nbr_offsets[r];
     return plan.n_interface;
 }
+
+// clustered colouring of a single tet body (or `n_bodies` copies laid out along x); outputs
+// serial_order[T], storage_order[T], tet_region[T]; returns n_colours, or -1 if the plan is invalid
+extern "C" int hs_cluster_plan(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_bodies,
+                               int n_regions, int per_body, uint32_t* serial_order, uint32_t* storage_order,
+                               int32_t* tet_region, int64_t* n_clusters, int64_t* max_chunk)
+{
+    HostScene h;
+    for (int b = 0; b < n_bodies; ++b)
+    {
+        HostBody hb;
+        hb.v_offset   = h.n_vertices();
+        hb.n_vertices = nV;
+        hb.t_offset   = h.n_tets();
+        hb.n_tets     = nT;
+        for (int64_t i = 0; i < nV; ++i)
+        {
+            h.x0.push_back(x0[3 * i] + 1000.0 * b);
+            h.x0.push_back(x0[3 * i + 1]);
+            h.x0.push_back(x0[3 * i + 2]);
+            h.mass.push_back(1.0);
+        }
+        for (int64_t t = 0; t < nT; ++t)
+        {
+            for (int a = 0; a < 4; ++a)
+                h.tets.push_back(static_cast<uint32_t>(hb.v_offset + tets[4 * t + a]));
+            h.tet_insertion.push_back(h.n_constraints++);
+            h.tet_material.push_back(0);
+        }
+        h.bodies.push_back(hb);
+    }
+    ClusterPlan plan;
+    build_cluster_plan(h, n_regions, per_body != 0, plan);
+    if (!cluster_plan_is_valid(h, plan))
+        return -1;
+    std::memcpy(serial_order, plan.serial_order.data(), sizeof(uint32_t) * plan.serial_order.size());
+    std::memcpy(storage_order, plan.storage_order.data(), sizeof(uint32_t) * plan.storage_order.size());
+    std::memcpy(tet_region, plan.tet_region.data(), sizeof(int32_t) * plan.tet_region.size());
+    *n_clusters = plan.n_clusters;
+    *max_chunk  = plan.max_chunk_clusters;
+    return plan.n_colours;
+}

@@ -15,8 +15,8 @@ def run_pair(sbs, oracle, scene, precision, frames=1, schedule=0, substeps=None,
     ref = oracle.World()
     scene.instantiate(ref)
     ref.set_constraint_order(sim.constraint_order())
-    S = substeps or scene.substeps
-    K = iterations or scene.iterations
+    S = scene.substeps if substeps is None else substeps
+    K = scene.iterations if iterations is None else iterations
     ref.contact_history = []
     for _ in range(frames):
         sim.step(scene.dt, S, K, scene.detect_every_substep)
@@ -30,10 +30,12 @@ def run_pair(sbs, oracle, scene, precision, frames=1, schedule=0, substeps=None,
     return sim, ref, out
 
 
+@pytest.mark.parametrize("schedule", [1, 2])
 @pytest.mark.parametrize("precision", [64, 32])
-def test_config1_beam_on_floor(sbs, scenes, oracle, precision):
+def test_config1_beam_on_floor(sbs, scenes, oracle, precision, schedule):
     scene = scenes.config1()
-    sim, ref, out = run_pair(sbs, oracle, scene, precision, frames=2)
+    sim, ref, out = run_pair(sbs, oracle, scene, precision, frames=2, schedule=schedule)
+    assert sim.stats()["schedule"] == schedule, sim.schedule_note()
     diag = scene.bbox_diagonal()
     (xg, vg, xr, vr), = out
     assert np.isfinite(xg).all()
@@ -65,19 +67,21 @@ def test_contact_set_matches(sbs, scenes, oracle, precision):
         assert len(set(gkey) ^ set(rkey)) <= max(2, len(rkey) // 20)
 
 
-def test_predict_commit_exact_fp64(sbs, scenes, oracle):
+@pytest.mark.parametrize("schedule", [1, 2])
+def test_predict_commit_exact_fp64(sbs, scenes, oracle, schedule):
     """Order-independent stages must match exactly: zero iterations leaves predict + commit."""
     scene = scenes.config1(W=4, H=4, D=5)
-    sim, ref, out = run_pair(sbs, oracle, scene, 64, frames=3, iterations=0)
+    sim, ref, out = run_pair(sbs, oracle, scene, 64, frames=3, iterations=0, schedule=schedule)
     (xg, vg, xr, vr), = out
     assert np.array_equal(xg, xr)
     assert np.array_equal(vg, vr)
 
 
+@pytest.mark.parametrize("schedule", [1, 2])
 @pytest.mark.parametrize("precision", [64, 32])
-def test_config2_cantilever_small(sbs, scenes, oracle, precision):
+def test_config2_cantilever_small(sbs, scenes, oracle, precision, schedule):
     scene = scenes.config2(W=7, H=7, D=15)
-    sim, ref, out = run_pair(sbs, oracle, scene, precision, frames=1)
+    sim, ref, out = run_pair(sbs, oracle, scene, precision, frames=1, schedule=schedule)
     (xg, vg, xr, vr), = out
     dev = np.abs(xg - xr).max() / scene.bbox_diagonal()
     assert dev <= TOL[precision], dev
@@ -97,14 +101,15 @@ def _checkers(oracle):
     return out
 
 
+@pytest.mark.parametrize("schedule", [1, 2])
 @pytest.mark.parametrize("precision", [64, 32])
 @pytest.mark.parametrize("name", G.case_names())
-def test_golden_scenes_against_reference_in_gpu_colour_order(sbs, oracle, name, precision):
+def test_golden_scenes_against_reference_in_gpu_colour_order(sbs, oracle, name, precision, schedule):
     """Every scene behind tests/golden (floor, box and sphere contacts, two bodies joined by
     damped springs, damped Green constraints, pinned vertices): the GPU result vs the reference
     algorithm run with constraints permuted into the GPU's exported colour order."""
     scene, frames, _ = G.load(name)
-    sim = sbs.Simulation(0, precision)
+    sim = sbs.Simulation(0, precision, schedule=schedule)
     ids = scene.instantiate(sim)
     order = sim.constraint_order()
     assert np.array_equal(np.sort(order), np.arange(len(order)))
@@ -204,6 +209,25 @@ def test_empty_scene_and_body_without_tets(sbs):
     sim2.step(0.016, 1, 1)
     x, v = sim2.download(b)
     np.testing.assert_allclose(x[0], [0.0, 1.0 - 9.81 * 0.016 ** 2, 0.0], rtol=1e-6)
+
+
+def test_ensemble_of_independent_bodies(sbs, scenes, oracle):
+    """config4 in small: 400 bodies -> one region per body, no synchronisation at all."""
+    scene = scenes.config4(n_bodies=400, W=3, H=3, D=5)
+    sim = sbs.Simulation(0, 64)
+    ids = scene.instantiate(sim)
+    st = sim.stats()
+    assert st["schedule"] == 2 and st["n_regions"] == 400 and st["n_interface_vertices"] == 0, sim.schedule_note()
+    ref = oracle.World()
+    scene.instantiate(ref)
+    ref.set_constraint_order(sim.constraint_order())
+    sim.step(scene.dt, 10, 10)
+    ref.step(scene.dt, 10, 10)
+    assert len(ref.contacts()[0]) > 0
+    worst = 0.0
+    for b in scene.tet_bodies():
+        worst = max(worst, np.abs(sim.download(ids[b])[0] - ref.download(b)[0]).max())
+    assert worst <= 1e-9 * scene.bbox_diagonal()
 
 
 @pytest.mark.parametrize("precision", [32])

@@ -35,6 +35,8 @@ def hostscene():
     L.hs_colour.argtypes = [C.c_int64, C.c_int64, C.c_int, u32p, dp, u32p, i64p, C.c_int, i32p]
     L.hs_regions.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, i32p, i32p, i32p]
     L.hs_regions.restype = C.c_int64
+    L.hs_cluster_plan.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int, u32p, u32p, i32p, i64p,
+                                  i64p]
     return L
 
 
@@ -133,6 +135,60 @@ def test_colouring_is_conflict_free_and_a_permutation(hostscene, oracle, dims):
     for c in range(nc):
         vs = tets[order[offsets[c]:offsets[c + 1]]].reshape(-1)
         assert len(np.unique(vs)) == len(vs)
+
+
+@pytest.mark.parametrize("dims,bodies,regions,per_body", [((8, 8, 16), 1, 1, 0), ((8, 8, 16), 1, 148, 0),
+                                                          ((21, 21, 51), 1, 148, 0), ((6, 6, 17), 40, 0, 1),
+                                                          ((2, 2, 2), 1, 1, 0), ((3, 2, 2), 3, 5, 0)])
+def test_clustered_colouring_of_lattices(hostscene, oracle, dims, bodies, regions, per_body):
+    """Clusters = lattice cells (5 tets), exactly 8 colours (2x2x2 parity), conflict-free (checked
+    by cluster_plan_is_valid inside hs_cluster_plan), serial and storage orders are permutations,
+    and the tets of one cell are consecutive in the exported serial order."""
+    pos, tets = oracle.bar_model(*dims)
+    tets = np.ascontiguousarray(tets, np.uint32)
+    x0 = pos.astype(np.float64)
+    T = len(tets) * bodies
+    serial = np.empty(T, np.uint32)
+    storage = np.empty(T, np.uint32)
+    treg = np.empty(T, np.int32)
+    ncl, mch = C.c_int64(0), C.c_int64(0)
+    nc = hostscene.hs_cluster_plan(len(pos), len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), bodies,
+                                   regions, per_body, serial.ctypes.data_as(u32p), storage.ctypes.data_as(u32p),
+                                   treg.ctypes.data_as(i32p), C.byref(ncl), C.byref(mch))
+    n_cells = (dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1)
+    assert nc == min(8, 2 ** sum(d > 2 for d in dims))
+    assert ncl.value == n_cells * bodies
+    assert np.array_equal(np.sort(serial), np.arange(T)) and np.array_equal(np.sort(storage), np.arange(T))
+    cells = serial.reshape(-1, 5) // 5
+    assert (cells == cells[:, :1]).all()                      # a cell's 5 tets run back to back ...
+    assert (np.diff(serial.reshape(-1, 5), axis=1) == 1).all()  # ... in insertion order
+    if per_body:
+        assert np.array_equal(treg, np.repeat(np.arange(bodies), len(tets)))
+
+
+def test_clustered_colouring_of_an_irregular_mesh(hostscene):
+    """Random Delaunay-like soup: a fan of tets around shared vertices, unequal cluster sizes."""
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(0, 4, size=(200, 3))
+    tets = []
+    for _ in range(600):
+        c = rng.integers(0, 200)
+        d = np.linalg.norm(pts - pts[c], axis=1)
+        near = np.argsort(d)[:8]
+        tets.append(rng.choice(near, 4, replace=False))
+    tets = np.ascontiguousarray(np.array(tets), np.uint32)
+    T = len(tets)
+    serial = np.empty(T, np.uint32)
+    storage = np.empty(T, np.uint32)
+    treg = np.empty(T, np.int32)
+    ncl, mch = C.c_int64(0), C.c_int64(0)
+    for regions in (1, 7):
+        nc = hostscene.hs_cluster_plan(200, T, tets.ctypes.data_as(u32p), pts.ctypes.data_as(dp), 1, regions, 0,
+                                       serial.ctypes.data_as(u32p), storage.ctypes.data_as(u32p),
+                                       treg.ctypes.data_as(i32p), C.byref(ncl), C.byref(mch))
+        assert nc > 0, "plan must be conflict-free"
+        assert np.array_equal(np.sort(serial), np.arange(T))
+        assert treg.min() >= 0 and treg.max() < regions
 
 
 def test_colouring_reports_capacity_overflow(hostscene):
