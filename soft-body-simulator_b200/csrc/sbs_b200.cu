@@ -848,7 +848,9 @@ int sbsb200_finalize(sbsb200_ctx* c)
         // damping; distance constraints and beta != 0 (which needs xn in the projection) take
         // the per-colour kernels
         bool const persistent_ok = T > 0 && D == 0 && !c->any_damping;
-        c->schedule = c->schedule_request == SBSB200_SCHED_GRAPH ? SBSB200_SCHED_GRAPH : SBSB200_SCHED_PERSISTENT;
+        // AUTO = per-colour kernels in a CUDA graph: measured faster than the persistent kernel on
+        // every BASELINE config in round 1 (profiles/r01_summary.md)
+        c->schedule = c->schedule_request == SBSB200_SCHED_PERSISTENT ? SBSB200_SCHED_PERSISTENT : SBSB200_SCHED_GRAPH;
         if (c->schedule == SBSB200_SCHED_PERSISTENT && !persistent_ok)
         {
             c->schedule      = SBSB200_SCHED_GRAPH;

@@ -41,10 +41,36 @@ SBS_HD Vec3<R> cross(Vec3<R> a, Vec3<R> b)
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 
-SBS_HD float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+// fp32 uses the SFU approximations (MUFU.RSQ / MUFU.RCP, ~2 ulp) on the device: the IEEE
+// sequences for 1/sqrt, sqrt and division are 20-40 dependent instructions each and sat on the
+// critical path of every Jacobi rotation.  fp64 (validation build) stays IEEE.
+SBS_HD float rsqrt_(float x)
+{
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
 SBS_HD double rsqrt_(double x) { return 1.0 / sqrt(x); }
-SBS_HD float sqrt_(float x) { return sqrtf(x); }
+SBS_HD float sqrt_(float x)
+{
+#ifdef __CUDA_ARCH__
+    return x > 0.0f ? x * rsqrtf(x) : 0.0f;
+#else
+    return sqrtf(x);
+#endif
+}
 SBS_HD double sqrt_(double x) { return sqrt(x); }
+SBS_HD float div_(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+SBS_HD double div_(double a, double b) { return a / b; }
 SBS_HD float abs_(float x) { return fabsf(x); }
 SBS_HD double abs_(double x) { return fabs(x); }
 SBS_HD float max_(float a, float b) { return fmaxf(a, b); }
@@ -102,12 +128,16 @@ struct Eps<float>
 {
     static constexpr float off_rel = 1e-13f; // off^2 <= off_rel * diag^2  (~ (3e-7)^2)
     static constexpr int max_sweeps = 6;
+    static constexpr float polar_tol = 2e-8f; // |R_{k+1} - R_k|_F^2 below this => next error ~ tol/2
+    static constexpr int polar_iters = 8;
 };
 template <>
 struct Eps<double>
 {
     static constexpr double off_rel = 1e-30;
     static constexpr int max_sweeps = 12;
+    static constexpr double polar_tol = 2e-17;
+    static constexpr int polar_iters = 12;
 };
 
 // One Jacobi rotation on the symmetric matrix (app, aqq, apq, arp, arq) and the eigenvector
@@ -120,7 +150,7 @@ SBS_HD void jacobi_rotate(R& app, R& aqq, R& apq, R& arp, R& arq, Vec3<R>& vp,
         return;
     R const d   = aqq - app;
     R const den = abs_(d) + sqrt_(d * d + R(4) * apq * apq);
-    R const t   = (d >= R(0) ? R(2) : R(-2)) * apq / den;
+    R const t   = div_((d >= R(0) ? R(2) : R(-2)) * apq, den);
     R const c   = rsqrt_(R(1) + t * t);
     R const s   = t * c;
     app -= t * apq;
@@ -186,16 +216,23 @@ struct GreenOut
 // Steps 2-9 of green_constraint_t::project_positions (green_constraint.cpp:61-120) for one
 // tet: D = DmInv (row-major d00..d22), V0s = signed rest volume.
 //
-// Instead of a general SVD F = U S V^T we diagonalise F^T F = V S^2 V^T (V a proper rotation,
-// sigma sorted descending) and rebuild U' = (F v1/|.|, F v2/|.| orthogonalised, u1 x u2).
-// With that U', U' V^T is always a proper rotation, which is exactly what the reference's
-// "if inverted: sigma3 -> -sigma3, U.col(2) -> -U.col(2)" produces; the flipped sigma3 is
-// negative and is therefore always clamped to 0.577 (green_constraint.cpp:92-102).
+// Two algebraically equivalent routes to (P, psi), see DESIGN.md "Green projection without SVD":
+//
+//  FAST (tet not inverted and every singular value > 0.577, i.e. the clamp at :99-102 and the
+//  flip at :92-96 are both inactive — the overwhelmingly common case).  With A = F^T F,
+//  E_G = (A - I)/2 and R = polar rotation of F:
+//      P    = U Phat V^T = F (2 mu E_G + lam tr(E_G) I)
+//      |E|_F^2 = |E_G|_F^2,   tr E = tr(U Ehat V^T) = tr(R E_G)      (NOT tr(E_G): :108-110)
+//  "every sigma > 0.577" <=> A - 0.577^2 I positive definite (three leading minors), and R
+//  comes from the Newton iteration R <- (R + R^-T)/2 (quadratic; 3-4 steps at 10% strain).
+//
+//  GENERAL: diagonalise A = V S^2 V^T (V a proper rotation, sigma sorted descending) and rebuild
+//  U' = (F v1/|.|, F v2/|.| orthogonalised, u1 x u2).  With that U', U' V^T is always a proper
+//  rotation, which is exactly what "if inverted: sigma3 -> -sigma3, U.col(2) -> -U.col(2)"
+//  produces; the flipped sigma3 is negative and therefore always clamped to 0.577.
 template <typename R>
-SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3,
-                                                       Vec3<R> x4, R d00, R d01, R d02, R d10,
-                                                       R d11, R d12, R d20, R d21, R d22, R V0s,
-                                                       R mu, R lam)
+SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3, Vec3<R> x4, R d00, R d01, R d02, R d10,
+                                   R d11, R d12, R d20, R d21, R d22, R V0s, R mu, R lam)
 {
     Vec3<R> const e1 = x1 - x4, e2 = x2 - x4, e3 = x3 - x4; // columns of Ds (:69-72)
     // sign of det(Ds) vs sign of V0 (:61-65); >= 0 counts as positive
@@ -209,74 +246,122 @@ SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3,
                         e1.z * d01 + e2.z * d11 + e3.z * d21};
     Vec3<R> const c2 = {e1.x * d02 + e2.x * d12 + e3.x * d22, e1.y * d02 + e2.y * d12 + e3.y * d22,
                         e1.z * d02 + e2.z * d12 + e3.z * d22};
+    R const a00 = dot(c0, c0), a11 = dot(c1, c1), a22 = dot(c2, c2), a01 = dot(c0, c1), a02 = dot(c0, c2),
+            a12 = dot(c1, c2);
 
-    R l0, l1, l2;
-    Vec3<R> v0, v1, v2;
-    sym_eig3(dot(c0, c0), dot(c1, c1), dot(c2, c2), dot(c0, c1), dot(c0, c2), dot(c1, c2), l0, l1,
-             l2, v0, v1, v2);
+    Vec3<R> pk0, pk1, pk2; // columns of P
+    R psi;
 
-    // U' columns
-    auto Fv = [&](Vec3<R> v) -> Vec3<R> {
-        return {c0.x * v.x + c1.x * v.y + c2.x * v.z, c0.y * v.x + c1.y * v.y + c2.y * v.z,
-                c0.z * v.x + c1.z * v.y + c2.z * v.z};
-    };
-    Vec3<R> u0 = Fv(v0);
-    R n0       = dot(u0, u0);
-    if (n0 > R(0))
-    {
-        R const s = rsqrt_(n0);
-        u0        = {u0.x * s, u0.y * s, u0.z * s};
-    }
-    else
-        u0 = {R(1), R(0), R(0)};
-    Vec3<R> u1 = Fv(v1);
-    {
-        R const p = dot(u1, u0);
-        u1        = {u1.x - p * u0.x, u1.y - p * u0.y, u1.z - p * u0.z};
-    }
-    R const n1 = dot(u1, u1);
-    if (n1 > l0 * R(sizeof(R) == 4 ? 1e-12 : 1e-28))
-    {
-        R const s = rsqrt_(n1);
-        u1        = {u1.x * s, u1.y * s, u1.z * s};
-    }
-    else
-    { // rank <= 1: any unit vector orthogonal to u0
-        Vec3<R> const ax = abs_(u0.x) < R(0.6) ? Vec3<R>{R(1), R(0), R(0)} : Vec3<R>{R(0), R(1), R(0)};
-        u1               = cross(u0, ax);
-        R const s        = rsqrt_(dot(u1, u1));
-        u1               = {u1.x * s, u1.y * s, u1.z * s};
-    }
-    Vec3<R> const u2 = cross(u0, u1);
-
-    // clamped principal stretches (:92-102)
+    // all singular values above the clamp <=> B = A - smin^2 I is positive definite
     R const smin = R(0.577);
-    R const s0   = max_(sqrt_(max_(l0, R(0))), smin);
-    R const s1   = max_(sqrt_(max_(l1, R(0))), smin);
-    R const s2   = inverted ? smin : max_(sqrt_(max_(l2, R(0))), smin);
+    R const b00 = a00 - smin * smin, b11 = a11 - smin * smin, b22 = a22 - smin * smin;
+    R const m2  = b00 * b11 - a01 * a01;
+    R const m3  = b22 * m2 - a02 * (a02 * b11 - a01 * a12) + a12 * (a02 * a01 - b00 * a12);
+    if (!inverted && b00 > R(0) && m2 > R(0) && m3 > R(0))
+    {
+        R const g00 = R(0.5) * (a00 - R(1)), g11 = R(0.5) * (a11 - R(1)), g22 = R(0.5) * (a22 - R(1));
+        R const g01 = R(0.5) * a01, g02 = R(0.5) * a02, g12 = R(0.5) * a12;
+        R const trg = g00 + g11 + g22;
+        R const e2n = g00 * g00 + g11 * g11 + g22 * g22 + R(2) * (g01 * g01 + g02 * g02 + g12 * g12);
+        // M = 2 mu E_G + lam tr(E_G) I ; P = F M
+        R const tm  = R(2) * mu;
+        R const m00 = tm * g00 + lam * trg, m11 = tm * g11 + lam * trg, m22 = tm * g22 + lam * trg;
+        R const m01 = tm * g01, m02 = tm * g02, m12 = tm * g12;
+        pk0 = {c0.x * m00 + c1.x * m01 + c2.x * m02, c0.y * m00 + c1.y * m01 + c2.y * m02,
+               c0.z * m00 + c1.z * m01 + c2.z * m02};
+        pk1 = {c0.x * m01 + c1.x * m11 + c2.x * m12, c0.y * m01 + c1.y * m11 + c2.y * m12,
+               c0.z * m01 + c1.z * m11 + c2.z * m12};
+        pk2 = {c0.x * m02 + c1.x * m12 + c2.x * m22, c0.y * m02 + c1.y * m12 + c2.y * m22,
+               c0.z * m02 + c1.z * m12 + c2.z * m22};
+        // polar rotation by Newton: R <- (R + cof(R)/det(R)) / 2, columns q0 q1 q2
+        Vec3<R> q0 = c0, q1 = c1, q2 = c2;
+#pragma unroll 1
+        for (int it = 0; it < Eps<R>::polar_iters; ++it)
+        {
+            Vec3<R> const n0 = cross(q1, q2), n1 = cross(q2, q0), n2 = cross(q0, q1);
+            R const h        = div_(R(0.5), dot(q0, n0));
+            Vec3<R> const r0 = {R(0.5) * q0.x + h * n0.x, R(0.5) * q0.y + h * n0.y, R(0.5) * q0.z + h * n0.z};
+            Vec3<R> const r1 = {R(0.5) * q1.x + h * n1.x, R(0.5) * q1.y + h * n1.y, R(0.5) * q1.z + h * n1.z};
+            Vec3<R> const r2 = {R(0.5) * q2.x + h * n2.x, R(0.5) * q2.y + h * n2.y, R(0.5) * q2.z + h * n2.z};
+            Vec3<R> const d0 = r0 - q0, d1 = r1 - q1, d2 = r2 - q2;
+            R const change   = dot(d0, d0) + dot(d1, d1) + dot(d2, d2);
+            q0 = r0;
+            q1 = r1;
+            q2 = r2;
+            if (change <= Eps<R>::polar_tol)
+                break;
+        }
+        // tr(R E_G) with R[r][k] = q_k[r]
+        R const Etr = q0.x * g00 + q0.y * g01 + q0.z * g02 + q1.x * g01 + q1.y * g11 + q1.z * g12 + q2.x * g02 +
+                      q2.y * g12 + q2.z * g22;
+        psi = mu * e2n + R(0.5) * lam * Etr * Etr;
+    }
+    else
+    {
+        R l0, l1, l2;
+        Vec3<R> v0, v1, v2;
+        sym_eig3(a00, a11, a22, a01, a02, a12, l0, l1, l2, v0, v1, v2);
 
-    // Ehat, Piolahat (:104-106)
-    R const eh0 = R(0.5) * (s0 * s0 - R(1)), eh1 = R(0.5) * (s1 * s1 - R(1)),
-            eh2  = R(0.5) * (s2 * s2 - R(1));
-    R const ehtr = eh0 + eh1 + eh2;
-    R const ph0 = s0 * (R(2) * mu * eh0 + lam * ehtr), ph1 = s1 * (R(2) * mu * eh1 + lam * ehtr),
-            ph2 = s2 * (R(2) * mu * eh2 + lam * ehtr);
+        // U' columns
+        auto Fv = [&](Vec3<R> v) -> Vec3<R> {
+            return {c0.x * v.x + c1.x * v.y + c2.x * v.z, c0.y * v.x + c1.y * v.y + c2.y * v.z,
+                    c0.z * v.x + c1.z * v.y + c2.z * v.z};
+        };
+        Vec3<R> u0 = Fv(v0);
+        R n0       = dot(u0, u0);
+        if (n0 > R(0))
+        {
+            R const s = rsqrt_(n0);
+            u0        = {u0.x * s, u0.y * s, u0.z * s};
+        }
+        else
+            u0 = {R(1), R(0), R(0)};
+        Vec3<R> u1 = Fv(v1);
+        {
+            R const p = dot(u1, u0);
+            u1        = {u1.x - p * u0.x, u1.y - p * u0.y, u1.z - p * u0.z};
+        }
+        R const n1 = dot(u1, u1);
+        if (n1 > l0 * R(sizeof(R) == 4 ? 1e-12 : 1e-28))
+        {
+            R const s = rsqrt_(n1);
+            u1        = {u1.x * s, u1.y * s, u1.z * s};
+        }
+        else
+        { // rank <= 1: any unit vector orthogonal to u0
+            Vec3<R> const ax = abs_(u0.x) < R(0.6) ? Vec3<R>{R(1), R(0), R(0)} : Vec3<R>{R(0), R(1), R(0)};
+            u1               = cross(u0, ax);
+            R const s        = rsqrt_(dot(u1, u1));
+            u1               = {u1.x * s, u1.y * s, u1.z * s};
+        }
+        Vec3<R> const u2 = cross(u0, u1);
 
-    // psi from E = U Ehat V^T (:108-110): |E|_F^2 = sum ehat_i^2, tr E = sum ehat_i (u_i . v_i)
-    R const Etr = eh0 * dot(u0, v0) + eh1 * dot(u1, v1) + eh2 * dot(u2, v2);
-    R const psi = mu * (eh0 * eh0 + eh1 * eh1 + eh2 * eh2) + R(0.5) * lam * Etr * Etr;
+        // clamped principal stretches (:92-102)
+        R const s0 = max_(sqrt_(max_(l0, R(0))), smin);
+        R const s1 = max_(sqrt_(max_(l1, R(0))), smin);
+        R const s2 = inverted ? smin : max_(sqrt_(max_(l2, R(0))), smin);
 
-    // P = U Piolahat V^T (:112), rows pr0 pr1 pr2
-    Vec3<R> const a0 = {ph0 * u0.x, ph0 * u0.y, ph0 * u0.z};
-    Vec3<R> const a1 = {ph1 * u1.x, ph1 * u1.y, ph1 * u1.z};
-    Vec3<R> const a2 = {ph2 * u2.x, ph2 * u2.y, ph2 * u2.z};
-    // P[r][k] = a0[r] v0[k] + a1[r] v1[k] + a2[r] v2[k]
-    Vec3<R> const pk0 = {a0.x * v0.x + a1.x * v1.x + a2.x * v2.x, a0.y * v0.x + a1.y * v1.x + a2.y * v2.x,
-                         a0.z * v0.x + a1.z * v1.x + a2.z * v2.x}; // column k=0 of P
-    Vec3<R> const pk1 = {a0.x * v0.y + a1.x * v1.y + a2.x * v2.y, a0.y * v0.y + a1.y * v1.y + a2.y * v2.y,
-                         a0.z * v0.y + a1.z * v1.y + a2.z * v2.y};
-    Vec3<R> const pk2 = {a0.x * v0.z + a1.x * v1.z + a2.x * v2.z, a0.y * v0.z + a1.y * v1.z + a2.y * v2.z,
-                         a0.z * v0.z + a1.z * v1.z + a2.z * v2.z};
+        // Ehat, Piolahat (:104-106)
+        R const eh0 = R(0.5) * (s0 * s0 - R(1)), eh1 = R(0.5) * (s1 * s1 - R(1)), eh2 = R(0.5) * (s2 * s2 - R(1));
+        R const ehtr = eh0 + eh1 + eh2;
+        R const ph0 = s0 * (R(2) * mu * eh0 + lam * ehtr), ph1 = s1 * (R(2) * mu * eh1 + lam * ehtr),
+                ph2 = s2 * (R(2) * mu * eh2 + lam * ehtr);
+
+        // psi from E = U Ehat V^T (:108-110): |E|_F^2 = sum ehat_i^2, tr E = sum ehat_i (u_i . v_i)
+        R const Etr = eh0 * dot(u0, v0) + eh1 * dot(u1, v1) + eh2 * dot(u2, v2);
+        psi         = mu * (eh0 * eh0 + eh1 * eh1 + eh2 * eh2) + R(0.5) * lam * Etr * Etr;
+
+        // P = U Piolahat V^T (:112): P[r][k] = sum_i ph_i u_i[r] v_i[k]
+        Vec3<R> const w0 = {ph0 * u0.x, ph0 * u0.y, ph0 * u0.z};
+        Vec3<R> const w1 = {ph1 * u1.x, ph1 * u1.y, ph1 * u1.z};
+        Vec3<R> const w2 = {ph2 * u2.x, ph2 * u2.y, ph2 * u2.z};
+        pk0 = {w0.x * v0.x + w1.x * v1.x + w2.x * v2.x, w0.y * v0.x + w1.y * v1.x + w2.y * v2.x,
+               w0.z * v0.x + w1.z * v1.x + w2.z * v2.x};
+        pk1 = {w0.x * v0.y + w1.x * v1.y + w2.x * v2.y, w0.y * v0.y + w1.y * v1.y + w2.y * v2.y,
+               w0.z * v0.y + w1.z * v1.y + w2.z * v2.y};
+        pk2 = {w0.x * v0.z + w1.x * v1.z + w2.x * v2.z, w0.y * v0.z + w1.y * v1.z + w2.y * v2.z,
+               w0.z * v0.z + w1.z * v1.z + w2.z * v2.z};
+    }
 
     // H = -|V0| P DmInv^T (:115-116): column c of H = -|V0| * sum_k P[:,k] DmInv[c][k]
     R const nv = -abs_(V0s);
