@@ -205,7 +205,10 @@ def main():
     sc = importlib.import_module("soft-body-simulator_b200.scenes")
 
     scene = make_scene(sc, args.workload, rank, world)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-blocking stream: the library captures the frame into a CUDA graph, which
+    # the legacy default stream does not permit
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sim = sbs.Simulation(local, args.precision, stream=stream.cuda_stream, schedule=args.schedule)
     ids = scene.instantiate(sim)
     stats0 = sim.stats()

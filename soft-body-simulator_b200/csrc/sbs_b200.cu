@@ -421,8 +421,10 @@ struct Engine final : EngineBase
     {
         cudaStream_t st = c.stream;
         CK(cudaEventRecord(c.ev0, st));
-        if (c.schedule == SBSB200_SCHED_PERSISTENT)
-        { // a handful of launches per frame, and the progress base changes every launch: no graph
+        bool const legacy_stream = st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread;
+        if (c.schedule == SBSB200_SCHED_PERSISTENT || legacy_stream)
+        { // persistent: a handful of launches per frame, and the progress base changes every launch.
+          // legacy default stream: capture is not permitted on it, so the same kernels go out eagerly
             c.kernels += enqueue(c, dt, substeps, iterations, detect, st);
             CK(cudaEventRecord(c.ev1, st));
             c.timed = true;
