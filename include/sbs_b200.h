@@ -169,6 +169,11 @@ int sbsb200_synchronize(sbsb200_ctx* ctx);
 int64_t sbsb200_get_contacts(sbsb200_ctx* ctx, int64_t cap, int32_t* body, uint32_t* vertex,
                              int32_t* sdf_body, double* point, double* normal);
 
+/* Development aid (persistent schedule, environment SBSB200_TRACE_STEPS=N at finalize): %clock64
+ * stamps of the first N colour steps of the latest launch, 16 per (region, step).  Returns the
+ * number of values available; copies min(cap, that) of them.  Not part of the reference API. */
+int64_t sbsb200_debug_read_trace(sbsb200_ctx* ctx, int64_t* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ EXPORTS = [
     "sbsb200_constraint_count", "sbsb200_get_constraint_order", "sbsb200_get_surface_map", "sbsb200_get_stats",
     "sbsb200_schedule_note",
     "sbsb200_upload", "sbsb200_download", "sbsb200_set_mass", "sbsb200_step", "sbsb200_step_host",
-    "sbsb200_synchronize", "sbsb200_get_contacts",
+    "sbsb200_synchronize", "sbsb200_get_contacts", "sbsb200_debug_read_trace",
 ]
 
 
@@ -90,6 +90,8 @@ def load_library():
     L.sbsb200_synchronize.argtypes = [vp]
     L.sbsb200_get_contacts.argtypes = [vp, C.c_int64, _i32p, _u32p, _i32p, _dp, _dp]
     L.sbsb200_get_contacts.restype = C.c_int64
+    L.sbsb200_debug_read_trace.argtypes = [vp, C.POINTER(C.c_int64), C.c_int64]
+    L.sbsb200_debug_read_trace.restype = C.c_int64
     _lib = L
     return L
 
@@ -215,6 +217,15 @@ class Simulation:
                                            substeps, iterations,
                                            DETECT_PER_SUBSTEP if detect_every_substep else DETECT_PER_FRAME,
                                            _d(x_out), _d(v_out)))
+
+    def debug_trace(self):
+        """[regions, steps, 8] clock stamps (see sbsb200_debug_read_trace); empty when tracing is off."""
+        n = self._L.sbsb200_debug_read_trace(self._h, None, 0)
+        if n <= 0:
+            return np.zeros((0, 0, 8), np.int64)
+        buf = np.zeros(n, np.int64)
+        self._L.sbsb200_debug_read_trace(self._h, buf.ctypes.data_as(C.POINTER(C.c_int64)), n)
+        return buf
 
     def synchronize(self):
         self._ck(self._L.sbsb200_synchronize(self._h))

@@ -78,6 +78,7 @@ struct EngineBase
     virtual int64_t contacts(sbsb200_ctx& c, int64_t cap, int32_t* body, uint32_t* vertex,
                              int32_t* sdf_body, double* point, double* normal)             = 0;
     virtual void invalidate_graphs()                                                       = 0;
+    virtual int64_t read_trace(sbsb200_ctx& c, int64_t* out, int64_t cap)                   = 0;
 };
 
 } // namespace
@@ -366,16 +367,18 @@ struct Engine final : EngineBase
                     // gauss_seidel_solver.cpp:32-35 in the exported colour order
                     for (int32_t col = 0; col < c.green_plan.n_colours; ++col)
                     {
-                        ChunkDesc const& hd = c.green_plan.chunks[static_cast<size_t>(col) * c.green_plan.n_regions];
-                        // graph schedule after a failed persistent build: regions of one colour are
-                        // adjacent in storage, but each has its own column layout -> one launch each
-                        for (int32_t reg = 0; reg < c.green_plan.n_regions; ++reg)
+                        // regions and parts of one colour are adjacent in storage, but each has its own
+                        // column layout -> one launch each (a single launch when there is no region plan)
+                        ChunkDesc const* hd =
+                            &c.green_plan.chunks[static_cast<size_t>(col) * 2 * c.green_plan.n_regions];
+                        for (int32_t rp = 0; rp < 2 * c.green_plan.n_regions; ++rp)
                         {
-                            ChunkDesc const& h2 = (&hd)[reg];
+                            ChunkDesc const& h2 = hd[rp];
                             if (h2.n[0] == 0)
                                 continue;
                             DevChunk dc;
-                            dc.first = h2.first;
+                            dc.first  = h2.first;
+                            dc.cfirst = h2.cfirst;
                             for (int m = 0; m < 8; ++m)
                                 dc.n[m] = h2.n[m];
                             unsigned const g = static_cast<unsigned>((h2.n[0] + 127) / 128);
@@ -512,6 +515,24 @@ struct Engine final : EngineBase
         if (v)
             CK(cudaMemcpyAsync(v, stage_v.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c.stream));
         CK(cudaStreamSynchronize(c.stream));
+        check_persistent(c);
+    }
+
+    void check_persistent(sbsb200_ctx& c)
+    {
+        if (c.schedule == SBSB200_SCHED_PERSISTENT && pp.timed_out())
+            throw CudaError{"the persistent kernel ran out of its poll budget waiting for a vertex of another region"};
+    }
+
+    int64_t read_trace(sbsb200_ctx& c, int64_t* out, int64_t cap) override
+    {
+        int64_t const n = std::min<int64_t>(cap, pp.trace_len);
+        if (n > 0 && out)
+        {
+            CK(cudaStreamSynchronize(c.stream));
+            CK(cudaMemcpy(out, pp.trace.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+        }
+        return pp.trace_len;
     }
 
     void set_mass(sbsb200_ctx& c, int64_t gv, double m) override
@@ -850,9 +871,15 @@ int sbsb200_finalize(sbsb200_ctx* c)
         // damping; distance constraints and beta != 0 (which needs xn in the projection) take
         // the per-colour kernels
         bool const persistent_ok = T > 0 && D == 0 && !c->any_damping;
-        // AUTO = per-colour kernels in a CUDA graph: measured faster than the persistent kernel on
-        // every BASELINE config in round 1 (profiles/r01_summary.md)
-        c->schedule = c->schedule_request == SBSB200_SCHED_PERSISTENT ? SBSB200_SCHED_PERSISTENT : SBSB200_SCHED_GRAPH;
+        // AUTO: the persistent region-resident kernel for connected meshes up to a few million tets
+        // (latency-bound: few clusters per colour and SM), the per-colour kernels in a CUDA graph for
+        // ensembles of small bodies and for very large meshes (throughput-bound) — measured on B200,
+        // profiles/r01_summary.md
+        bool const auto_persistent =
+            persistent_ok && T <= 4000000 && !PersistentPlan<float>::wants_region_per_body(h, c->sm_count);
+        c->schedule = c->schedule_request == SBSB200_SCHED_PERSISTENT                     ? SBSB200_SCHED_PERSISTENT
+                      : c->schedule_request == SBSB200_SCHED_AUTO && auto_persistent ? SBSB200_SCHED_PERSISTENT
+                                                                                     : SBSB200_SCHED_GRAPH;
         if (c->schedule == SBSB200_SCHED_PERSISTENT && !persistent_ok)
         {
             c->schedule      = SBSB200_SCHED_GRAPH;
@@ -861,9 +888,11 @@ int sbsb200_finalize(sbsb200_ctx* c)
 
         if (c->schedule == SBSB200_SCHED_PERSISTENT)
         {
+            ResidentParams const rp = c->precision == SBSB200_FP32 ? PersistentPlan<float>::resident_params()
+                                                                   : PersistentPlan<double>::resident_params();
             build_cluster_plan(h, PersistentPlan<float>::regions_for(c->sm_count, T),
-                               PersistentPlan<float>::wants_region_per_body(h, c->sm_count), c->green_plan);
-            classify_regions(h, c->green_plan.tet_region, c->green_plan.n_regions, c->plan);
+                               PersistentPlan<float>::wants_region_per_body(h, c->sm_count), c->green_plan, &rp,
+                               &c->plan);
         }
         else
             build_cluster_plan(h, 1, false, c->green_plan);
@@ -1019,6 +1048,19 @@ int sbsb200_step_host(sbsb200_ctx* c, int body, const double* x_in, const double
     if (rc)
         return rc;
     return sbsb200_download(c, body, x_out, v_out);
+}
+
+int64_t sbsb200_debug_read_trace(sbsb200_ctx* c, int64_t* out, int64_t cap)
+{
+    if (!c || !c->finalized)
+        return SBSB200_ERR_STATE;
+    int64_t n    = 0;
+    int const rc = guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        n = c->engine->read_trace(*c, out, cap);
+        return SBSB200_OK;
+    });
+    return rc ? rc : n;
 }
 
 int sbsb200_synchronize(sbsb200_ctx* c)

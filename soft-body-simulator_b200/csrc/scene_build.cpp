@@ -260,7 +260,7 @@ void plan_regions(HostScene const& scene, std::vector<uint64_t> const& tet_keys,
 }
 
 void classify_regions(HostScene const& scene, std::vector<int32_t> const& tet_region_in, int32_t n_regions,
-                      RegionPlan& plan)
+                      RegionPlan& plan, int64_t capacity)
 {
     int64_t const T = scene.n_tets(), V = scene.n_vertices();
     std::vector<int32_t> const tet_region_copy = tet_region_in;
@@ -301,7 +301,9 @@ void classify_regions(HostScene const& scene, std::vector<int32_t> const& tet_re
     plan.vertex_slot.assign(static_cast<size_t>(V), 0);
     for (int64_t v = 0; v < V; ++v)
     {
-        int32_t const r = plan.vertex_region[static_cast<size_t>(v)];
+        int32_t& r = plan.vertex_region[static_cast<size_t>(v)];
+        if (r >= 0 && capacity >= 0 && plan.region_vtx_offsets[static_cast<size_t>(r) + 1] >= capacity)
+            r = -1; // the region's shared memory is full: private to the region, but kept in global memory
         if (r >= 0)
             ++plan.region_vtx_offsets[static_cast<size_t>(r) + 1];
         else
@@ -375,10 +377,14 @@ struct Cluster
     uint64_t morton;
     uint32_t first, count; // range in the (body, cell)-sorted tet list
     int32_t colour = -1, region = 0;
+    int32_t part = 1;      // 0 = fetches vertices from global memory, 1 = all vertices resident
+    uint32_t nv = 0;       // unique vertices
+    uint32_t verts[4 * kMaxCluster];
 };
 } // namespace
 
-void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_region_per_body, ClusterPlan& out)
+void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_region_per_body, ClusterPlan& out,
+                        ResidentParams const* resident, RegionPlan* region_plan)
 {
     int64_t const T = scene.n_tets(), V = scene.n_vertices();
     out             = ClusterPlan{};
@@ -453,9 +459,26 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
     for (int64_t p = 0; p < T;)
     {
         int64_t q = p;
+        uint32_t seen[kMaxClusterVertices];
+        uint32_t n_seen = 0;
         while (q < T && q - p < kMaxCluster && tet_body[sorted[q]] == tet_body[sorted[p]] &&
                cell[sorted[q]] == cell[sorted[p]])
+        { // at most kMaxClusterVertices distinct vertices per cluster (scratch slots of one thread)
+            uint32_t fresh[4];
+            uint32_t n_fresh = 0;
+            for (int a = 0; a < 4; ++a)
+            {
+                uint32_t const v = scene.tets[4 * static_cast<size_t>(sorted[q]) + a];
+                if (std::find(seen, seen + n_seen, v) == seen + n_seen &&
+                    std::find(fresh, fresh + n_fresh, v) == fresh + n_fresh)
+                    fresh[n_fresh++] = v;
+            }
+            if (n_seen + n_fresh > static_cast<uint32_t>(kMaxClusterVertices))
+                break;
+            for (uint32_t k = 0; k < n_fresh; ++k)
+                seen[n_seen++] = fresh[k];
             ++q;
+        }
         Cluster c;
         c.body   = tet_body[sorted[p]];
         c.cx     = cell[sorted[p]][0];
@@ -530,7 +553,89 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
     else
         out.n_regions = 1;
 
-    // final order: (colour, region, size descending, morton)
+    // unique vertices per cluster
+    uint32_t max_cluster_vertices = 0;
+    for (Cluster& c : clusters)
+    {
+        c.nv = 0;
+        for (uint32_t p = c.first; p < c.first + c.count; ++p)
+            for (int a = 0; a < 4; ++a)
+            {
+                uint32_t const v = scene.tets[4 * static_cast<size_t>(sorted[p]) + a];
+                if (std::find(c.verts, c.verts + c.nv, v) == c.verts + c.nv)
+                    c.verts[c.nv++] = v;
+            }
+        max_cluster_vertices = std::max(max_cluster_vertices, c.nv);
+    }
+    for (Cluster const& c : clusters)
+        for (uint32_t m = 0; m < c.count; ++m)
+            out.tet_region[sorted[c.first + m]] = c.region;
+
+    // resident schedule: vertex classification, cluster parts, launch shape
+    if (resident)
+    {
+        out.nvc = static_cast<int32_t>((max_cluster_vertices + 3) / 4 * 4);
+        out.nvc = std::max(out.nvc, 4);
+        // threads per CTA: every cluster of a (colour, region) step gets its own thread when possible
+        // (cluster i of the step, part A first, runs on thread i % nt)
+        auto threads_needed = [&](std::vector<int64_t> const& a_cnt, std::vector<int64_t> const& b_cnt) {
+            int64_t need = 0;
+            for (size_t i = 0; i < a_cnt.size(); ++i)
+                need = std::max(need, a_cnt[i] + b_cnt[i]);
+            return static_cast<int32_t>(
+                std::min<int64_t>(resident->max_threads, std::max<int64_t>(64, (need + 31) / 32 * 32)));
+        };
+        size_t const n_steps = static_cast<size_t>(out.n_colours) * static_cast<size_t>(out.n_regions);
+        std::vector<int64_t> a_cnt(n_steps, 0), b_cnt(n_steps, 0);
+        for (Cluster const& c : clusters)
+            ++b_cnt[static_cast<size_t>(c.colour) * out.n_regions + c.region];
+        // The classification depends on the shared-memory capacity, which depends on the thread count
+        // (scratch slots), which depends on the classification.  Start from a safe upper bound of the
+        // thread count, then try once with the count that classification needs; keep it if it holds.
+        std::vector<int64_t> total(b_cnt), none(n_steps, 0);
+        auto classify_with = [&](int32_t nt) -> int32_t { // returns the thread count this classification needs
+            int64_t const scratch  = static_cast<int64_t>(out.nvc) * nt;
+            int64_t const capacity = std::min<int64_t>(resident->smem_bytes / resident->vertex_bytes - scratch, 65535 - scratch);
+            if (capacity < 0)
+            {
+                out.why_not = "shared memory cannot hold the per-thread scratch vertices";
+                return -1;
+            }
+            classify_regions(scene, out.tet_region, out.n_regions, *region_plan, capacity);
+            std::fill(a_cnt.begin(), a_cnt.end(), 0);
+            std::fill(b_cnt.begin(), b_cnt.end(), 0);
+            for (Cluster& c : clusters)
+            {
+                c.part = 1;
+                for (uint32_t k = 0; k < c.nv; ++k)
+                    if (region_plan->vertex_region[c.verts[k]] != c.region)
+                        c.part = 0;
+                ++(c.part == 0 ? a_cnt : b_cnt)[static_cast<size_t>(c.colour) * out.n_regions + c.region];
+            }
+            return threads_needed(a_cnt, b_cnt);
+        };
+        int32_t const upper = threads_needed(none, total);
+        out.nt              = upper;
+        if (region_plan)
+        {
+            int32_t const need = classify_with(upper);
+            if (need > 0 && need < upper)
+            {
+                out.nt = need;
+                if (classify_with(need) > need)
+                { // more residency shifted clusters from A to B beyond the count: stay with the bound
+                    out.nt = upper;
+                    classify_with(upper);
+                }
+            }
+        }
+        if (out.nvc > kMaxClusterVertices)
+            out.why_not = "a cluster has more than 16 distinct vertices";
+        if (out.n_colours > 120)
+            out.why_not = "more than 120 cluster colours (8-bit step distances)";
+    }
+
+    // final order: (colour, region, part, size descending, morton)
     std::vector<uint32_t> idx(clusters.size());
     std::iota(idx.begin(), idx.end(), 0u);
     std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
@@ -539,6 +644,8 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
             return x.colour < y.colour;
         if (x.region != y.region)
             return x.region < y.region;
+        if (x.part != y.part)
+            return x.part < y.part;
         if (x.count != y.count)
             return x.count > y.count;
         if (x.body != y.body)
@@ -546,21 +653,54 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         return x.morton < y.morton;
     });
 
-    size_t const n_chunks = static_cast<size_t>(out.n_colours) * static_cast<size_t>(out.n_regions);
+    size_t const n_chunks = static_cast<size_t>(out.n_colours) * static_cast<size_t>(out.n_regions) * 2;
     out.chunks.assign(n_chunks, ChunkDesc{});
     out.storage_order.resize(static_cast<size_t>(T));
     out.serial_order.reserve(static_cast<size_t>(T));
+    bool const layout = resident && region_plan && out.why_not.empty();
+    // colours that touch each vertex (the touch schedule the tag protocol of the resident kernel follows)
+    std::vector<std::array<uint64_t, 2>> vcolours;
+    if (layout)
+    {
+        out.tet_slots.assign(4 * static_cast<size_t>(T), 0);
+        out.cl_fetch.assign(static_cast<size_t>(out.nvc) * clusters.size(), 0xffffffffu);
+        out.cl_meta.assign(static_cast<size_t>(out.nvc) * clusters.size(), 0u);
+        vcolours.assign(static_cast<size_t>(V), std::array<uint64_t, 2>{});
+        for (Cluster const& c : clusters)
+            for (uint32_t u = 0; u < c.nv; ++u)
+                vcolours[c.verts[u]][c.colour >> 6] |= 1ull << (c.colour & 63);
+        std::vector<char> is_surface(static_cast<size_t>(V), 0);
+        for (HostBody const& hb : scene.bodies)
+            if (hb.kind == BodyKind::tet)
+                for (uint32_t lv : hb.surf_to_tet)
+                    is_surface[static_cast<size_t>(hb.v_offset + lv)] = 1;
+        out.vertex_meta.assign(static_cast<size_t>(V), 0);
+        for (int64_t v = 0; v < V; ++v)
+        {
+            auto const& m = vcolours[static_cast<size_t>(v)];
+            uint32_t last = 0xffu;
+            if (m[1])
+                last = 127u - static_cast<uint32_t>(__builtin_clzll(m[1]));
+            else if (m[0])
+                last = 63u - static_cast<uint32_t>(__builtin_clzll(m[0]));
+            out.vertex_meta[static_cast<size_t>(v)] = last | (is_surface[static_cast<size_t>(v)] ? 0x100u : 0u);
+        }
+    }
     int64_t store = 0;
     size_t i      = 0;
+    int64_t pair_clusters = 0;
     for (size_t ch = 0; ch < n_chunks; ++ch)
     {
-        int32_t const col = static_cast<int32_t>(ch / static_cast<size_t>(out.n_regions));
-        int32_t const reg = static_cast<int32_t>(ch % static_cast<size_t>(out.n_regions));
-        size_t j          = i;
-        while (j < idx.size() && clusters[idx[j]].colour == col && clusters[idx[j]].region == reg)
+        int32_t const col  = static_cast<int32_t>(ch / (2 * static_cast<size_t>(out.n_regions)));
+        int32_t const reg  = static_cast<int32_t>((ch / 2) % static_cast<size_t>(out.n_regions));
+        int32_t const part = static_cast<int32_t>(ch % 2);
+        size_t j           = i;
+        while (j < idx.size() && clusters[idx[j]].colour == col && clusters[idx[j]].region == reg &&
+               clusters[idx[j]].part == part)
             ++j;
         ChunkDesc& d = out.chunks[ch];
         d.first      = static_cast<int32_t>(store);
+        d.cfirst     = static_cast<int32_t>(i);
         for (size_t k = i; k < j; ++k)
         {
             Cluster const& c = clusters[idx[k]];
@@ -568,7 +708,6 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
             {
                 ++d.n[m];
                 out.serial_order.push_back(sorted[c.first + m]);
-                out.tet_region[sorted[c.first + m]] = reg;
             }
         }
         int64_t col_base = store;
@@ -577,15 +716,142 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
             for (size_t k = i; k < j; ++k)
             {
                 Cluster const& c = clusters[idx[k]];
-                if (c.count > static_cast<uint32_t>(m))
-                    out.storage_order[static_cast<size_t>(col_base + static_cast<int64_t>(k - i))] = sorted[c.first + m];
+                if (c.count <= static_cast<uint32_t>(m))
+                    continue;
+                int64_t const pos = col_base + static_cast<int64_t>(k - i);
+                uint32_t const t  = sorted[c.first + m];
+                out.storage_order[static_cast<size_t>(pos)] = t;
+                if (!layout)
+                    continue;
+                // vertex addresses in the CTA's shared array: [nvc * nt scratch | resident vertices]
+                uint32_t const thread = static_cast<uint32_t>((k - i) % static_cast<size_t>(out.nt));
+                for (int a = 0; a < 4; ++a)
+                {
+                    uint32_t const v = scene.tets[4 * static_cast<size_t>(t) + a];
+                    uint32_t slot;
+                    if (region_plan->vertex_region[v] == reg)
+                        slot = static_cast<uint32_t>(out.nvc) * out.nt + region_plan->vertex_slot[v];
+                    else
+                    { // k-th fetched vertex of this cluster
+                        uint32_t kf = 0;
+                        for (uint32_t u = 0; u < c.nv && c.verts[u] != v; ++u)
+                            kf += region_plan->vertex_region[c.verts[u]] != reg;
+                        slot = kf * static_cast<uint32_t>(out.nt) + thread;
+                    }
+                    out.tet_slots[4 * static_cast<size_t>(pos) + a] = static_cast<uint16_t>(slot);
+                }
             }
             col_base += d.n[m];
         }
+        if (layout)
+            for (size_t k = i; k < j; ++k)
+            {
+                Cluster const& c = clusters[idx[k]];
+                uint32_t kf      = 0;
+                for (uint32_t u = 0; u < c.nv; ++u)
+                    if (region_plan->vertex_region[c.verts[u]] != reg)
+                    {
+                        uint32_t const v = c.verts[u];
+                        // How many steps back the previous touch of v lies, for the four kinds of
+                        // colour step: byte 2*(k>0) + cs, cs = 1 when a collision step precedes every
+                        // sweep; 0xff = the predict step of the launch.  Touches are: predict, the
+                        // collision steps if v is a surface vertex, the colours whose clusters contain v.
+                        auto const& m    = vcolours[v];
+                        int32_t prevc    = -1;
+                        for (int32_t pc = col - 1; pc >= 0 && prevc < 0; --pc)
+                            if (m[pc >> 6] >> (pc & 63) & 1ull)
+                                prevc = pc;
+                        int32_t const lastc = static_cast<int32_t>(out.vertex_meta[v] & 0xffu);
+                        bool const surf     = (out.vertex_meta[v] & 0x100u) != 0u;
+                        uint32_t word       = 0;
+                        for (int later = 0; later < 2; ++later)
+                            for (int cs = 0; cs < 2; ++cs)
+                            {
+                                int32_t d;
+                                if (prevc >= 0)
+                                    d = col - prevc;
+                                else if (cs && surf)
+                                    d = col + 1;
+                                else if (later)
+                                    d = out.n_colours + cs + col - lastc;
+                                else
+                                    d = 0xff;
+                                word |= static_cast<uint32_t>(d) << (8 * (2 * later + cs));
+                            }
+                        out.cl_meta[static_cast<size_t>(kf) * clusters.size() + k] = word;
+                        out.cl_fetch[static_cast<size_t>(kf++) * clusters.size() + k] = v;
+                    }
+            }
         store = col_base;
-        out.max_chunk_clusters = std::max<int64_t>(out.max_chunk_clusters, static_cast<int64_t>(j - i));
+        pair_clusters = (part == 0 ? 0 : pair_clusters) + static_cast<int64_t>(j - i);
+        out.max_chunk_clusters = std::max<int64_t>(out.max_chunk_clusters, pair_clusters);
         i = j;
     }
+}
+
+bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& rp)
+{
+    int64_t const T = scene.n_tets(), Q = cp.n_clusters;
+    if (!cp.why_not.empty() || cp.nt <= 0 || cp.nvc <= 0 || cp.nvc % 4 != 0 || cp.nvc > kMaxClusterVertices)
+        return false;
+    if (static_cast<int64_t>(cp.tet_slots.size()) != 4 * T ||
+        static_cast<int64_t>(cp.cl_fetch.size()) != static_cast<int64_t>(cp.nvc) * Q)
+        return false;
+    uint32_t const scratch = static_cast<uint32_t>(cp.nvc) * static_cast<uint32_t>(cp.nt);
+    int64_t clusters_seen  = 0;
+    for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
+    {
+        ChunkDesc const& d = cp.chunks[ch];
+        int32_t const reg  = static_cast<int32_t>((ch / 2) % static_cast<size_t>(cp.n_regions));
+        int32_t const part = static_cast<int32_t>(ch % 2);
+        if (d.cfirst != clusters_seen)
+            return false;
+        clusters_seen += d.n[0];
+        for (int32_t i = 0; i < d.n[0]; ++i)
+        {
+            int64_t const q      = d.cfirst + i;
+            uint32_t const thread = static_cast<uint32_t>(i % cp.nt); // part A comes first in its step
+            bool any_fetch        = false;
+            for (int k = 0; k < cp.nvc; ++k)
+            {
+                uint32_t const v = cp.cl_fetch[static_cast<size_t>(k) * Q + q];
+                if (v == 0xffffffffu)
+                    continue;
+                any_fetch = true;
+                if (v >= rp.vertex_region.size() || rp.vertex_region[v] == reg)
+                    return false; // resident vertices must not be fetched
+            }
+            if (any_fetch != (part == 0))
+                return false;
+            int64_t base = d.first;
+            for (int m = 0; m < kMaxCluster && i < d.n[m]; ++m)
+            {
+                int64_t const pos = base + i;
+                uint32_t const t  = cp.storage_order[static_cast<size_t>(pos)];
+                for (int a = 0; a < 4; ++a)
+                {
+                    uint32_t const v    = scene.tets[4 * static_cast<size_t>(t) + a];
+                    uint32_t const slot = cp.tet_slots[4 * static_cast<size_t>(pos) + a];
+                    if (slot >= scratch)
+                    { // resident slot of this region
+                        int64_t const at = rp.region_vtx_offsets[static_cast<size_t>(reg)] + (slot - scratch);
+                        if (rp.vertex_region[v] != reg || at >= rp.region_vtx_offsets[static_cast<size_t>(reg) + 1] ||
+                            rp.region_vtx[static_cast<size_t>(at)] != v)
+                            return false;
+                    }
+                    else
+                    { // scratch entry k of the thread that runs this cluster
+                        uint32_t const k = slot / static_cast<uint32_t>(cp.nt);
+                        if (slot % static_cast<uint32_t>(cp.nt) != thread || k >= static_cast<uint32_t>(cp.nvc) ||
+                            cp.cl_fetch[static_cast<size_t>(k) * Q + q] != v)
+                            return false;
+                    }
+                }
+                base += d.n[m];
+            }
+        }
+    }
+    return clusters_seen == Q;
 }
 
 bool cluster_plan_is_valid(HostScene const& scene, ClusterPlan const& plan)
@@ -605,9 +871,10 @@ bool cluster_plan_is_valid(HostScene const& scene, ClusterPlan const& plan)
     std::vector<int32_t> stamp(static_cast<size_t>(V), -1);
     int64_t cluster_id = 0;
     for (int32_t col = 0; col < plan.n_colours; ++col)
-        for (int32_t reg = 0; reg < plan.n_regions; ++reg)
+        for (int32_t rp = 0; rp < 2 * plan.n_regions; ++rp)
         {
-            ChunkDesc const& d = plan.chunks[static_cast<size_t>(col) * plan.n_regions + reg];
+            int32_t const reg  = rp / 2;
+            ChunkDesc const& d = plan.chunks[static_cast<size_t>(col) * 2 * plan.n_regions + rp];
             for (int32_t i = 0; i < d.n[0]; ++i, ++cluster_id)
             {
                 int64_t base = d.first;

@@ -116,13 +116,23 @@ void plan_regions(HostScene const& scene, std::vector<uint64_t> const& tet_keys,
 // The equivalent serial Gauss-Seidel order is: colour, cluster, tet-in-cluster.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxCluster = 8;
+constexpr int kMaxClusterVertices = 16; // scratch entries per thread in the resident schedule
 
 struct ChunkDesc
 {
     int32_t first;          // storage index of the chunk's first tet
+    int32_t cfirst;         // storage index of the chunk's first cluster
     int32_t n[kMaxCluster]; // n[j] = number of clusters in the chunk with more than j tets
 };                          // tet j of cluster i (clusters sorted by size, descending) is stored at
                             // first + n[0] + ... + n[j-1] + i  ("column" layout: coalesced per j)
+
+// Layout parameters of the resident (persistent) schedule; see xpbd_persistent.cuh.
+struct ResidentParams
+{
+    int64_t smem_bytes   = 0; // shared memory available to one CTA
+    int32_t vertex_bytes = 16; // sizeof(Real4<R>)
+    int32_t max_threads  = 512;
+};
 
 struct ClusterPlan
 {
@@ -130,23 +140,45 @@ struct ClusterPlan
     int32_t n_regions = 1;
     int64_t n_clusters = 0;
     std::vector<uint32_t> storage_order; // storage position -> tet (index into HostScene::tets / 4)
-    std::vector<uint32_t> serial_order;  // equivalent serial order of tets (colour, cluster, tet)
-    std::vector<ChunkDesc> chunks;       // [colour * n_regions + region]
+    std::vector<uint32_t> serial_order;  // equivalent serial order of tets (colour, region, part, cluster, tet)
+    // [(colour * n_regions + region) * 2 + part]; part 0 = clusters that fetch vertices from global
+    // memory (shared with other regions, or not resident), part 1 = clusters whose vertices are all
+    // resident in the region's shared memory.  Without a region plan everything is in part 1.
+    std::vector<ChunkDesc> chunks;
     std::vector<int32_t> tet_region;     // T
-    int64_t max_chunk_clusters = 0;
+    int64_t max_chunk_clusters = 0;      // max over (colour, region) of the clusters of both parts
+    // resident schedule only
+    int32_t nt  = 0;                     // threads per CTA the scratch slots were laid out for
+    int32_t nvc = 0;                     // scratch entries per thread (multiple of 4, <= kMaxClusterVertices)
+    std::vector<uint16_t> tet_slots;     // 4*T (storage order): index into the CTA's shared vertex array
+    std::vector<uint32_t> cl_fetch;      // [nvc][n_clusters]: global vertex of scratch entry k, 0xffffffff = none
+    // touch schedule for the tag protocol: per vertex  bits 0-7 = last colour touching it (0xff none),
+    // bit 8 = surface vertex; per fetch entry four bytes "steps back to the previous touch" for
+    // the four kinds of colour step (byte 2*(iteration > 0) + collision steps present), 0xff = the
+    // predict step
+    std::vector<uint32_t> vertex_meta;   // V
+    std::vector<uint32_t> cl_meta;       // [nvc][n_clusters]
+    std::string why_not;                 // non-empty when the resident layout could not be built
 };
 
-// n_regions <= 1: no partition (graph schedule).  Otherwise clusters are dealt to regions in
-// (body, Morton) order with balanced tet counts, or one region per body.
+// n_regions <= 1 and no `resident`: no partition (graph schedule).  Otherwise clusters are dealt to
+// regions in (body, Morton) order with balanced tet counts, or one region per body; with
+// `resident` the vertex classification (RegionPlan) and the shared-memory layout are built too.
 void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_region_per_body,
-                        ClusterPlan& out);
+                        ClusterPlan& out, ResidentParams const* resident = nullptr,
+                        RegionPlan* region_plan = nullptr);
+
+// true when every tet slot of the resident layout resolves to the right vertex (resident slot of
+// its region, or the scratch entry the running thread fetched) and parts are classified correctly
+bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& rp);
 
 // true when no two tets of different clusters of one colour share a vertex
 bool cluster_plan_is_valid(HostScene const& scene, ClusterPlan const& plan);
 
 // vertex classification / neighbour lists for a given tet->region map (see RegionPlan)
+// capacity: at most that many resident vertices per region (the rest stay in global memory)
 void classify_regions(HostScene const& scene, std::vector<int32_t> const& tet_region, int32_t n_regions,
-                      RegionPlan& plan);
+                      RegionPlan& plan, int64_t capacity = -1);
 
 // Validation helper: true when no two constraints of the same colour share a vertex.
 bool colouring_is_valid(int64_t n_vertices, int k, uint32_t const* verts, ColourClass const& cc);

@@ -103,34 +103,31 @@ __global__ void __launch_bounds__(256) k_integrate(DeviceScene<R> s, R dt)
 }
 
 // One Green projection given gathered data; returns updated positions/lambda through refs.
-// Steps 10-13 of green_constraint.cpp (:123-157).
+// Steps 10-13 of green_constraint.cpp (:123-157).  `at` = alpha / dt^2 (:134).
 template <typename R, bool kDamped>
-SBS_HD void green_project(Real4<R>& p1, Real4<R>& p2, Real4<R>& p3, Real4<R>& p4,
-                                              Vec3<R> xn1, Vec3<R> xn2, Vec3<R> xn3, Vec3<R> xn4,
-                                              Real4<R> r0, Real4<R> r1, Real4<R> r2, Real4<R> mat,
-                                              R dt, R& lambda)
+SBS_HD void green_project_at(Real4<R>& p1, Real4<R>& p2, Real4<R>& p3, Real4<R>& p4, Vec3<R> xn1, Vec3<R> xn2,
+                             Vec3<R> xn3, Vec3<R> xn4, Real4<R> r0, Real4<R> r1, Real4<R> r2, R mu, R lam, R at,
+                             R beta, R dt, R& lambda)
 {
     Vec3<R> const x1 = {p1.x, p1.y, p1.z}, x2 = {p2.x, p2.y, p2.z}, x3 = {p3.x, p3.y, p3.z},
                   x4 = {p4.x, p4.y, p4.z};
     GreenOut<R> const g =
-        green_gradients<R>(x1, x2, x3, x4, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, mat.x, mat.y);
+        green_gradients<R>(x1, x2, x3, x4, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, mu, lam);
     Vec3<R> const f4 = {-(g.f1.x + g.f2.x + g.f3.x), -(g.f1.y + g.f2.y + g.f3.y), -(g.f1.z + g.f2.z + g.f3.z)};
     R const S = p1.w * dot(g.f1, g.f1) + p2.w * dot(g.f2, g.f2) + p3.w * dot(g.f3, g.f3) + p4.w * dot(f4, f4);
     if (S < R(1e-20)) // :67, :130-131
         return;
-    R const dt2 = dt * dt;
-    R const at  = mat.z / dt2;
-    R num       = -(g.C + at * lambda);
-    R den       = S + at;
+    R num = -(g.C + at * lambda);
+    R den = S + at;
     if (kDamped)
     {
-        R const bt  = mat.w * dt2;
+        R const bt  = beta * (dt * dt);
         R const gam = at * bt / dt;
         R const gd  = dot(g.f1, x1 - xn1) + dot(g.f2, x2 - xn2) + dot(g.f3, x3 - xn3) + dot(f4, x4 - xn4);
         num += gam * gd;
         den = (R(1) + gam) * S + at;
     }
-    R const dl = num / den;
+    R const dl = div_(num, den);
     lambda += dl;
     R const k1 = -p1.w * dl, k2 = -p2.w * dl, k3 = -p3.w * dl, k4 = -p4.w * dl;
     p1.x += k1 * g.f1.x; p1.y += k1 * g.f1.y; p1.z += k1 * g.f1.z;
@@ -139,13 +136,24 @@ SBS_HD void green_project(Real4<R>& p1, Real4<R>& p2, Real4<R>& p3, Real4<R>& p4
     p4.x += k4 * f4.x;   p4.y += k4 * f4.y;   p4.z += k4 * f4.z;
 }
 
+template <typename R, bool kDamped>
+SBS_HD void green_project(Real4<R>& p1, Real4<R>& p2, Real4<R>& p3, Real4<R>& p4,
+                                              Vec3<R> xn1, Vec3<R> xn2, Vec3<R> xn3, Vec3<R> xn4,
+                                              Real4<R> r0, Real4<R> r1, Real4<R> r2, Real4<R> mat,
+                                              R dt, R& lambda)
+{
+    green_project_at<R, kDamped>(p1, p2, p3, p4, xn1, xn2, xn3, xn4, r0, r1, r2, mat.x, mat.y, mat.z / (dt * dt),
+                                 mat.w, dt, lambda);
+}
+
 __device__ __forceinline__ int mat_index(float v) { return __float_as_int(v); }
 __device__ __forceinline__ int mat_index(double v) { return static_cast<int>(v); }
 
 // Chunk descriptor of the clustered colouring (mirrors sbsb200::ChunkDesc in scene_build.h)
 struct DevChunk
 {
-    int32_t first;
+    int32_t first;  // storage index of the chunk's first tet
+    int32_t cfirst; // storage index of the chunk's first cluster
     int32_t n[8];
 };
 

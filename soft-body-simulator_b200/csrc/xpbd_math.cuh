@@ -128,16 +128,14 @@ struct Eps<float>
 {
     static constexpr float off_rel = 1e-13f; // off^2 <= off_rel * diag^2  (~ (3e-7)^2)
     static constexpr int max_sweeps = 6;
-    static constexpr float polar_tol = 2e-8f; // |R_{k+1} - R_k|_F^2 below this => next error ~ tol/2
-    static constexpr int polar_iters = 8;
+
 };
 template <>
 struct Eps<double>
 {
     static constexpr double off_rel = 1e-30;
     static constexpr int max_sweeps = 12;
-    static constexpr double polar_tol = 2e-17;
-    static constexpr int polar_iters = 12;
+
 };
 
 // One Jacobi rotation on the symmetric matrix (app, aqq, apq, arp, arq) and the eigenvector
@@ -213,6 +211,97 @@ struct GreenOut
     R C;                // |V0| * psi
 };
 
+// Newton steps for the polar rotation, chosen a priori from the strain: with eps = |E_G|_F every
+// singular value of F lies within delta0 = 1 - sqrt(1 - 2 eps) of 1 (eps for stretch), and one step
+// of X <- (X + X^-T)/2 maps an error delta to delta^2 / (2 (1 + delta)).
+template <typename R>
+struct PolarSteps;
+template <>
+struct PolarSteps<float>
+{ // final error <= ~3e-7
+    static SBS_HD int of(float e2n) { return e2n <= 5.9e-7f ? 1 : e2n <= 1.5e-3f ? 2 : e2n <= 6.7e-2f ? 3 : 4; }
+    static constexpr float max_e2n = 2.25f; // beyond: general route
+};
+template <>
+struct PolarSteps<double>
+{ // two more steps square 3e-7 twice
+    static SBS_HD int of(double e2n) { return e2n <= 5.9e-7 ? 3 : e2n <= 1.5e-3 ? 4 : e2n <= 6.7e-2 ? 5 : 6; }
+    static constexpr double max_e2n = 2.25;
+};
+
+// GENERAL route of green_gradients (clamp or inversion active): columns of P and psi from the
+// eigen-decomposition of A = F^T F.  Kept out of line: it is rare, long, and register hungry.
+template <typename R>
+__host__ __device__ __noinline__ void green_general(Vec3<R> c0, Vec3<R> c1, Vec3<R> c2, R a00, R a11, R a22, R a01,
+                                                    R a02, R a12, bool inverted, R mu, R lam, Vec3<R>& pk0,
+                                                    Vec3<R>& pk1, Vec3<R>& pk2, R& psi)
+{
+    R const smin = R(0.577);
+    R l0, l1, l2;
+    Vec3<R> v0, v1, v2;
+    sym_eig3(a00, a11, a22, a01, a02, a12, l0, l1, l2, v0, v1, v2);
+
+    // U' columns
+    auto Fv = [&](Vec3<R> v) -> Vec3<R> {
+        return {c0.x * v.x + c1.x * v.y + c2.x * v.z, c0.y * v.x + c1.y * v.y + c2.y * v.z,
+                c0.z * v.x + c1.z * v.y + c2.z * v.z};
+    };
+    Vec3<R> u0 = Fv(v0);
+    R n0       = dot(u0, u0);
+    if (n0 > R(0))
+    {
+        R const s = rsqrt_(n0);
+        u0        = {u0.x * s, u0.y * s, u0.z * s};
+    }
+    else
+        u0 = {R(1), R(0), R(0)};
+    Vec3<R> u1 = Fv(v1);
+    {
+        R const p = dot(u1, u0);
+        u1        = {u1.x - p * u0.x, u1.y - p * u0.y, u1.z - p * u0.z};
+    }
+    R const n1 = dot(u1, u1);
+    if (n1 > l0 * R(sizeof(R) == 4 ? 1e-12 : 1e-28))
+    {
+        R const s = rsqrt_(n1);
+        u1        = {u1.x * s, u1.y * s, u1.z * s};
+    }
+    else
+    { // rank <= 1: any unit vector orthogonal to u0
+        Vec3<R> const ax = abs_(u0.x) < R(0.6) ? Vec3<R>{R(1), R(0), R(0)} : Vec3<R>{R(0), R(1), R(0)};
+        u1               = cross(u0, ax);
+        R const s        = rsqrt_(dot(u1, u1));
+        u1               = {u1.x * s, u1.y * s, u1.z * s};
+    }
+    Vec3<R> const u2 = cross(u0, u1);
+
+    // clamped principal stretches (:92-102)
+    R const s0 = max_(sqrt_(max_(l0, R(0))), smin);
+    R const s1 = max_(sqrt_(max_(l1, R(0))), smin);
+    R const s2 = inverted ? smin : max_(sqrt_(max_(l2, R(0))), smin);
+
+    // Ehat, Piolahat (:104-106)
+    R const eh0 = R(0.5) * (s0 * s0 - R(1)), eh1 = R(0.5) * (s1 * s1 - R(1)), eh2 = R(0.5) * (s2 * s2 - R(1));
+    R const ehtr = eh0 + eh1 + eh2;
+    R const ph0 = s0 * (R(2) * mu * eh0 + lam * ehtr), ph1 = s1 * (R(2) * mu * eh1 + lam * ehtr),
+            ph2 = s2 * (R(2) * mu * eh2 + lam * ehtr);
+
+    // psi from E = U Ehat V^T (:108-110): |E|_F^2 = sum ehat_i^2, tr E = sum ehat_i (u_i . v_i)
+    R const Etr = eh0 * dot(u0, v0) + eh1 * dot(u1, v1) + eh2 * dot(u2, v2);
+    psi         = mu * (eh0 * eh0 + eh1 * eh1 + eh2 * eh2) + R(0.5) * lam * Etr * Etr;
+
+    // P = U Piolahat V^T (:112): P[r][k] = sum_i ph_i u_i[r] v_i[k]
+    Vec3<R> const w0 = {ph0 * u0.x, ph0 * u0.y, ph0 * u0.z};
+    Vec3<R> const w1 = {ph1 * u1.x, ph1 * u1.y, ph1 * u1.z};
+    Vec3<R> const w2 = {ph2 * u2.x, ph2 * u2.y, ph2 * u2.z};
+    pk0 = {w0.x * v0.x + w1.x * v1.x + w2.x * v2.x, w0.y * v0.x + w1.y * v1.x + w2.y * v2.x,
+           w0.z * v0.x + w1.z * v1.x + w2.z * v2.x};
+    pk1 = {w0.x * v0.y + w1.x * v1.y + w2.x * v2.y, w0.y * v0.y + w1.y * v1.y + w2.y * v2.y,
+           w0.z * v0.y + w1.z * v1.y + w2.z * v2.y};
+    pk2 = {w0.x * v0.z + w1.x * v1.z + w2.x * v2.z, w0.y * v0.z + w1.y * v1.z + w2.y * v2.z,
+           w0.z * v0.z + w1.z * v1.z + w2.z * v2.z};
+}
+
 // Steps 2-9 of green_constraint_t::project_positions (green_constraint.cpp:61-120) for one
 // tet: D = DmInv (row-major d00..d22), V0s = signed rest volume.
 //
@@ -224,20 +313,22 @@ struct GreenOut
 //      P    = U Phat V^T = F (2 mu E_G + lam tr(E_G) I)
 //      |E|_F^2 = |E_G|_F^2,   tr E = tr(U Ehat V^T) = tr(R E_G)      (NOT tr(E_G): :108-110)
 //  "every sigma > 0.577" <=> A - 0.577^2 I positive definite (three leading minors), and R
-//  comes from the Newton iteration R <- (R + R^-T)/2 (quadratic; 3-4 steps at 10% strain).
+//  comes from the Newton iteration R <- (R + R^-T)/2 with the step count fixed a priori from
+//  |E_G|_F (no convergence test in the loop).
 //
-//  GENERAL: diagonalise A = V S^2 V^T (V a proper rotation, sigma sorted descending) and rebuild
-//  U' = (F v1/|.|, F v2/|.| orthogonalised, u1 x u2).  With that U', U' V^T is always a proper
-//  rotation, which is exactly what "if inverted: sigma3 -> -sigma3, U.col(2) -> -U.col(2)"
-//  produces; the flipped sigma3 is negative and therefore always clamped to 0.577.
+//  "Inverted" (:61-65) is sign(det Ds) != sign(V0) with zero counted positive; since
+//  det DmInv has the sign of V0 this is det F < 0, up to the zero cases — and those only matter
+//  when sigma_3 = 0, where the general route clamps sigma_3 to 0.577 whatever the flag says.  det F
+//  is the first cofactor expansion of the Newton iteration, so the test is free.
+//
+//  GENERAL: green_general above.  U' V^T is always a proper rotation there, which is exactly what
+//  "if inverted: sigma3 -> -sigma3, U.col(2) -> -U.col(2)" produces; the flipped sigma3 is
+//  negative and therefore always clamped to 0.577.
 template <typename R>
 SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3, Vec3<R> x4, R d00, R d01, R d02, R d10,
                                    R d11, R d12, R d20, R d21, R d22, R V0s, R mu, R lam)
 {
     Vec3<R> const e1 = x1 - x4, e2 = x2 - x4, e3 = x3 - x4; // columns of Ds (:69-72)
-    // sign of det(Ds) vs sign of V0 (:61-65); >= 0 counts as positive
-    R const detDs       = dot(e1, cross(e2, e3));
-    bool const inverted = (detDs >= R(0)) != (V0s >= R(0));
 
     // F = Ds * DmInv, stored by columns c0 c1 c2 (:74)
     Vec3<R> const c0 = {e1.x * d00 + e2.x * d10 + e3.x * d20, e1.y * d00 + e2.y * d10 + e3.y * d20,
@@ -248,6 +339,10 @@ SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3, Vec3<R> x
                         e1.z * d02 + e2.z * d12 + e3.z * d22};
     R const a00 = dot(c0, c0), a11 = dot(c1, c1), a22 = dot(c2, c2), a01 = dot(c0, c1), a02 = dot(c0, c2),
             a12 = dot(c1, c2);
+    // first cofactors of F: det F, and the first Newton step
+    Vec3<R> n0 = cross(c1, c2), n1 = cross(c2, c0), n2 = cross(c0, c1);
+    R det      = dot(c0, n0);
+    bool const inverted = det < R(0);
 
     Vec3<R> pk0, pk1, pk2; // columns of P
     R psi;
@@ -257,15 +352,16 @@ SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3, Vec3<R> x
     R const b00 = a00 - smin * smin, b11 = a11 - smin * smin, b22 = a22 - smin * smin;
     R const m2  = b00 * b11 - a01 * a01;
     R const m3  = b22 * m2 - a02 * (a02 * b11 - a01 * a12) + a12 * (a02 * a01 - b00 * a12);
-    if (!inverted && b00 > R(0) && m2 > R(0) && m3 > R(0))
+    R const g00 = R(0.5) * a00 - R(0.5), g11 = R(0.5) * a11 - R(0.5), g22 = R(0.5) * a22 - R(0.5);
+    R const g01 = R(0.5) * a01, g02 = R(0.5) * a02, g12 = R(0.5) * a12;
+    R const e2n = g00 * g00 + g11 * g11 + g22 * g22 + R(2) * (g01 * g01 + g02 * g02 + g12 * g12);
+    if (!inverted && b00 > R(0) && m2 > R(0) && m3 > R(0) && e2n <= PolarSteps<R>::max_e2n)
     {
-        R const g00 = R(0.5) * (a00 - R(1)), g11 = R(0.5) * (a11 - R(1)), g22 = R(0.5) * (a22 - R(1));
-        R const g01 = R(0.5) * a01, g02 = R(0.5) * a02, g12 = R(0.5) * a12;
         R const trg = g00 + g11 + g22;
-        R const e2n = g00 * g00 + g11 * g11 + g22 * g22 + R(2) * (g01 * g01 + g02 * g02 + g12 * g12);
         // M = 2 mu E_G + lam tr(E_G) I ; P = F M
         R const tm  = R(2) * mu;
-        R const m00 = tm * g00 + lam * trg, m11 = tm * g11 + lam * trg, m22 = tm * g22 + lam * trg;
+        R const lt  = lam * trg;
+        R const m00 = tm * g00 + lt, m11 = tm * g11 + lt, m22 = tm * g22 + lt;
         R const m01 = tm * g01, m02 = tm * g02, m12 = tm * g12;
         pk0 = {c0.x * m00 + c1.x * m01 + c2.x * m02, c0.y * m00 + c1.y * m01 + c2.y * m02,
                c0.z * m00 + c1.z * m01 + c2.z * m02};
@@ -275,21 +371,20 @@ SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3, Vec3<R> x
                c0.z * m02 + c1.z * m12 + c2.z * m22};
         // polar rotation by Newton: R <- (R + cof(R)/det(R)) / 2, columns q0 q1 q2
         Vec3<R> q0 = c0, q1 = c1, q2 = c2;
+        int const steps = PolarSteps<R>::of(e2n);
 #pragma unroll 1
-        for (int it = 0; it < Eps<R>::polar_iters; ++it)
+        for (int it = 0;;)
         {
-            Vec3<R> const n0 = cross(q1, q2), n1 = cross(q2, q0), n2 = cross(q0, q1);
-            R const h        = div_(R(0.5), dot(q0, n0));
-            Vec3<R> const r0 = {R(0.5) * q0.x + h * n0.x, R(0.5) * q0.y + h * n0.y, R(0.5) * q0.z + h * n0.z};
-            Vec3<R> const r1 = {R(0.5) * q1.x + h * n1.x, R(0.5) * q1.y + h * n1.y, R(0.5) * q1.z + h * n1.z};
-            Vec3<R> const r2 = {R(0.5) * q2.x + h * n2.x, R(0.5) * q2.y + h * n2.y, R(0.5) * q2.z + h * n2.z};
-            Vec3<R> const d0 = r0 - q0, d1 = r1 - q1, d2 = r2 - q2;
-            R const change   = dot(d0, d0) + dot(d1, d1) + dot(d2, d2);
-            q0 = r0;
-            q1 = r1;
-            q2 = r2;
-            if (change <= Eps<R>::polar_tol)
+            R const h = div_(R(0.5), det);
+            q0        = {R(0.5) * q0.x + h * n0.x, R(0.5) * q0.y + h * n0.y, R(0.5) * q0.z + h * n0.z};
+            q1        = {R(0.5) * q1.x + h * n1.x, R(0.5) * q1.y + h * n1.y, R(0.5) * q1.z + h * n1.z};
+            q2        = {R(0.5) * q2.x + h * n2.x, R(0.5) * q2.y + h * n2.y, R(0.5) * q2.z + h * n2.z};
+            if (++it >= steps)
                 break;
+            n0  = cross(q1, q2);
+            n1  = cross(q2, q0);
+            n2  = cross(q0, q1);
+            det = dot(q0, n0);
         }
         // tr(R E_G) with R[r][k] = q_k[r]
         R const Etr = q0.x * g00 + q0.y * g01 + q0.z * g02 + q1.x * g01 + q1.y * g11 + q1.z * g12 + q2.x * g02 +
@@ -297,71 +392,7 @@ SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3, Vec3<R> x
         psi = mu * e2n + R(0.5) * lam * Etr * Etr;
     }
     else
-    {
-        R l0, l1, l2;
-        Vec3<R> v0, v1, v2;
-        sym_eig3(a00, a11, a22, a01, a02, a12, l0, l1, l2, v0, v1, v2);
-
-        // U' columns
-        auto Fv = [&](Vec3<R> v) -> Vec3<R> {
-            return {c0.x * v.x + c1.x * v.y + c2.x * v.z, c0.y * v.x + c1.y * v.y + c2.y * v.z,
-                    c0.z * v.x + c1.z * v.y + c2.z * v.z};
-        };
-        Vec3<R> u0 = Fv(v0);
-        R n0       = dot(u0, u0);
-        if (n0 > R(0))
-        {
-            R const s = rsqrt_(n0);
-            u0        = {u0.x * s, u0.y * s, u0.z * s};
-        }
-        else
-            u0 = {R(1), R(0), R(0)};
-        Vec3<R> u1 = Fv(v1);
-        {
-            R const p = dot(u1, u0);
-            u1        = {u1.x - p * u0.x, u1.y - p * u0.y, u1.z - p * u0.z};
-        }
-        R const n1 = dot(u1, u1);
-        if (n1 > l0 * R(sizeof(R) == 4 ? 1e-12 : 1e-28))
-        {
-            R const s = rsqrt_(n1);
-            u1        = {u1.x * s, u1.y * s, u1.z * s};
-        }
-        else
-        { // rank <= 1: any unit vector orthogonal to u0
-            Vec3<R> const ax = abs_(u0.x) < R(0.6) ? Vec3<R>{R(1), R(0), R(0)} : Vec3<R>{R(0), R(1), R(0)};
-            u1               = cross(u0, ax);
-            R const s        = rsqrt_(dot(u1, u1));
-            u1               = {u1.x * s, u1.y * s, u1.z * s};
-        }
-        Vec3<R> const u2 = cross(u0, u1);
-
-        // clamped principal stretches (:92-102)
-        R const s0 = max_(sqrt_(max_(l0, R(0))), smin);
-        R const s1 = max_(sqrt_(max_(l1, R(0))), smin);
-        R const s2 = inverted ? smin : max_(sqrt_(max_(l2, R(0))), smin);
-
-        // Ehat, Piolahat (:104-106)
-        R const eh0 = R(0.5) * (s0 * s0 - R(1)), eh1 = R(0.5) * (s1 * s1 - R(1)), eh2 = R(0.5) * (s2 * s2 - R(1));
-        R const ehtr = eh0 + eh1 + eh2;
-        R const ph0 = s0 * (R(2) * mu * eh0 + lam * ehtr), ph1 = s1 * (R(2) * mu * eh1 + lam * ehtr),
-                ph2 = s2 * (R(2) * mu * eh2 + lam * ehtr);
-
-        // psi from E = U Ehat V^T (:108-110): |E|_F^2 = sum ehat_i^2, tr E = sum ehat_i (u_i . v_i)
-        R const Etr = eh0 * dot(u0, v0) + eh1 * dot(u1, v1) + eh2 * dot(u2, v2);
-        psi         = mu * (eh0 * eh0 + eh1 * eh1 + eh2 * eh2) + R(0.5) * lam * Etr * Etr;
-
-        // P = U Piolahat V^T (:112): P[r][k] = sum_i ph_i u_i[r] v_i[k]
-        Vec3<R> const w0 = {ph0 * u0.x, ph0 * u0.y, ph0 * u0.z};
-        Vec3<R> const w1 = {ph1 * u1.x, ph1 * u1.y, ph1 * u1.z};
-        Vec3<R> const w2 = {ph2 * u2.x, ph2 * u2.y, ph2 * u2.z};
-        pk0 = {w0.x * v0.x + w1.x * v1.x + w2.x * v2.x, w0.y * v0.x + w1.y * v1.x + w2.y * v2.x,
-               w0.z * v0.x + w1.z * v1.x + w2.z * v2.x};
-        pk1 = {w0.x * v0.y + w1.x * v1.y + w2.x * v2.y, w0.y * v0.y + w1.y * v1.y + w2.y * v2.y,
-               w0.z * v0.y + w1.z * v1.y + w2.z * v2.y};
-        pk2 = {w0.x * v0.z + w1.x * v1.z + w2.x * v2.z, w0.y * v0.z + w1.y * v1.z + w2.y * v2.z,
-               w0.z * v0.z + w1.z * v1.z + w2.z * v2.z};
-    }
+        green_general<R>(c0, c1, c2, a00, a11, a22, a01, a02, a12, inverted, mu, lam, pk0, pk1, pk2, psi);
 
     // H = -|V0| P DmInv^T (:115-116): column c of H = -|V0| * sum_k P[:,k] DmInv[c][k]
     R const nv = -abs_(V0s);

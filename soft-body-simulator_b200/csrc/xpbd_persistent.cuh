@@ -1,111 +1,224 @@
 // Persistent, region-resident schedule: ONE cooperative kernel per substep.
 //
 // The tet set is cut into spatially compact regions, one per CTA (one CTA per SM for a large
-// connected mesh).  A vertex whose tets all lie in one region is INTERIOR to it: its (xi, w)
+// connected mesh).  A vertex whose tets all lie in one region is RESIDENT in it: its (xi, w)
 // record lives in that CTA's shared memory for the whole substep (predict, every iteration and
-// colour, commit) and never touches L2/HBM in between.  Vertices shared by several regions are
-// INTERFACE vertices and stay in global memory.  The Gauss-Seidel order is unchanged — colour
-// major over the whole mesh — but instead of a grid-wide barrier per colour each region only
-// waits for its NEIGHBOUR regions (those it shares an interface vertex with) through a
-// monotone progress counter in global memory (release fence + relaxed store / relaxed poll +
-// acquire fence, gpu scope).
+// colour, commit) and never touches L2/HBM in between.  Vertices shared by several regions
+// (and vertices that do not fit the shared memory) live in a global EXCHANGE array.
+//
+// Work unit = CLUSTER (<= 8 tets sharing vertices, <= 16 distinct vertices), one thread each.
+// Every cluster carries a FETCH LIST: its vertices that are not resident.  A thread copies them
+// from the exchange array into its private scratch slots of the shared vertex array, projects
+// the cluster's tets one after the other entirely out of shared memory (the tet records hold
+// 16-bit slots into that array, resident or scratch alike), and writes the scratch entries back.
+// Per-tet constants are prefetched one tet ahead, a thread's first cluster of a colour step one
+// step ahead.
+//
+// The Gauss-Seidel order is unchanged — colour major over the whole mesh.  There is no barrier
+// between regions at all: synchronisation is per VERTEX and data-driven.  An exchange record is
+// one 16-byte word {x, y, z, tag} (fp32; three {value, tag} words in the fp64 build) that is read
+// and written with single 128-bit accesses, so a reader sees position and tag together.  The tag
+// is the step number of the last touch.  Which steps touch a vertex is static (the colours of the
+// clusters that contain it, the collision steps if it is a surface vertex, predict), so every
+// reader knows the tag it has to wait for: every touch is a read-modify-write that waits for the
+// previous touch, which orders read-after-write and write-after-read hazards alike without a
+// fence (the record carries its own flag).
 //
 //   step 0                      : predict   (timestep.cpp:35-43)
 //   step 1 + k(1+C) + 0         : collision constraints of iteration k (gauss_seidel_solver.cpp:28-31)
 //   step 1 + k(1+C) + 1 + c     : colour c of iteration k               (:32-35)
 //   step 1 + K(1+C)             : commit    (timestep.cpp:48-57) + surface copy
 //
-// Before step j a region waits until every neighbour has published "steps < j done"; this
-// orders both the read-after-write and the write-after-read hazards on interface vertices.
-// Regions without any interface (independent bodies of an ensemble) skip all of it and are
-// handed out round-robin, several per CTA.
+// Regions are co-resident (cooperative launch), so waiting on another region cannot deadlock:
+// every wait is for a strictly earlier step.  A poll budget turns a lost update into an error
+// code instead of a hang.
 #pragma once
 
 #include "scene_build.h"
 #include "xpbd_kernels.cuh"
 
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 namespace sbsb200 {
 
-constexpr uint32_t kGlobalBit = 0x80000000u; // vertex address: global index when set, smem slot otherwise
+constexpr uint32_t kGlobalBit = 0x80000000u; // surface vertex address: global index when set, smem slot otherwise
+constexpr uint32_t kNoVertex  = 0xffffffffu; // empty fetch-list entry
+constexpr uint32_t kNoColour  = 0xffu;
+constexpr int kPollBudget     = 1 << 20;     // polls of one record before the kernel gives up
+
+// true when the wait should be abandoned: budget exhausted (sets the error flag) or another thread
+// already gave up (checked every 1024 polls so that one lost update cannot stall the whole launch)
+__device__ __forceinline__ bool poll_expired(uint32_t* error, int polls)
+{
+    if (polls > kPollBudget)
+    {
+        *reinterpret_cast<volatile uint32_t*>(error) = 1u;
+        return true;
+    }
+    return (polls & 1023) == 0 && *reinterpret_cast<volatile uint32_t*>(error) != 0u;
+}
+
+// ---- 128-bit single-copy-atomic accesses (LDG/STG.E.128.STRONG.GPU) ----------------------------
+struct Word128
+{
+    unsigned long long lo, hi;
+};
+// No "memory" clobber: a record carries its own flag and orders nothing else, and a clobber would
+// make the compiler serialise the polls of a fetch list (each load waiting for the shared-memory
+// store of the previous one) — measured at 8 x 600 cycles per cluster.
+__device__ __forceinline__ Word128 ld_b128(void const* p)
+{
+    Word128 w;
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.gpu.global.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+                 : "=l"(w.lo), "=l"(w.hi)
+                 : "l"(p));
+    return w;
+}
+__device__ __forceinline__ void st_b128(void* p, Word128 w)
+{
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.gpu.global.b128 [%0], q;\n\t}" ::"l"(p),
+                 "l"(w.lo), "l"(w.hi));
+}
+
+// Exchange records.  fp32: one word {x, y, z, tag} per vertex.  fp64: three words {value, tag}.
+template <typename R>
+struct Xchg;
+template <>
+struct Xchg<float>
+{
+    static constexpr int kWords = 1;
+    struct Raw
+    {
+        Word128 w;
+    };
+    static __device__ __forceinline__ Raw fetch(void const* base, uint32_t gv)
+    {
+        return Raw{ld_b128(static_cast<char const*>(base) + 16ull * gv)};
+    }
+    static __device__ __forceinline__ bool decode(Raw const& r, uint32_t expect, float& x, float& y, float& z)
+    {
+        x = __uint_as_float(static_cast<uint32_t>(r.w.lo));
+        y = __uint_as_float(static_cast<uint32_t>(r.w.lo >> 32));
+        z = __uint_as_float(static_cast<uint32_t>(r.w.hi));
+        return static_cast<uint32_t>(r.w.hi >> 32) == expect;
+    }
+    static __device__ __forceinline__ bool load(void const* base, uint32_t gv, uint32_t expect, float& x, float& y,
+                                                float& z)
+    {
+        Word128 const w = ld_b128(static_cast<char const*>(base) + 16ull * gv);
+        x               = __uint_as_float(static_cast<uint32_t>(w.lo));
+        y               = __uint_as_float(static_cast<uint32_t>(w.lo >> 32));
+        z               = __uint_as_float(static_cast<uint32_t>(w.hi));
+        return static_cast<uint32_t>(w.hi >> 32) == expect;
+    }
+    static __device__ __forceinline__ void store(void* base, uint32_t gv, float x, float y, float z, uint32_t tag)
+    {
+        Word128 w;
+        w.lo = static_cast<unsigned long long>(__float_as_uint(x)) |
+               (static_cast<unsigned long long>(__float_as_uint(y)) << 32);
+        w.hi = static_cast<unsigned long long>(__float_as_uint(z)) | (static_cast<unsigned long long>(tag) << 32);
+        st_b128(static_cast<char*>(base) + 16ull * gv, w);
+    }
+};
+template <>
+struct Xchg<double>
+{
+    static constexpr int kWords = 3;
+    struct Raw
+    {
+        Word128 w0, w1, w2;
+    };
+    static __device__ __forceinline__ Raw fetch(void const* base, uint32_t gv)
+    {
+        char const* p = static_cast<char const*>(base) + 48ull * gv;
+        return Raw{ld_b128(p), ld_b128(p + 16), ld_b128(p + 32)};
+    }
+    static __device__ __forceinline__ bool decode(Raw const& r, uint32_t expect, double& x, double& y, double& z)
+    {
+        x = __longlong_as_double(static_cast<long long>(r.w0.lo));
+        y = __longlong_as_double(static_cast<long long>(r.w1.lo));
+        z = __longlong_as_double(static_cast<long long>(r.w2.lo));
+        return static_cast<uint32_t>(r.w0.hi) == expect && static_cast<uint32_t>(r.w1.hi) == expect &&
+               static_cast<uint32_t>(r.w2.hi) == expect;
+    }
+    static __device__ __forceinline__ bool load(void const* base, uint32_t gv, uint32_t expect, double& x, double& y,
+                                                double& z)
+    {
+        char const* p    = static_cast<char const*>(base) + 48ull * gv;
+        Word128 const w0 = ld_b128(p), w1 = ld_b128(p + 16), w2 = ld_b128(p + 32);
+        x                = __longlong_as_double(static_cast<long long>(w0.lo));
+        y                = __longlong_as_double(static_cast<long long>(w1.lo));
+        z                = __longlong_as_double(static_cast<long long>(w2.lo));
+        return static_cast<uint32_t>(w0.hi) == expect && static_cast<uint32_t>(w1.hi) == expect &&
+               static_cast<uint32_t>(w2.hi) == expect;
+    }
+    static __device__ __forceinline__ void store(void* base, uint32_t gv, double x, double y, double z, uint32_t tag)
+    {
+        char* p = static_cast<char*>(base) + 48ull * gv;
+        st_b128(p, Word128{static_cast<unsigned long long>(__double_as_longlong(x)), tag});
+        st_b128(p + 16, Word128{static_cast<unsigned long long>(__double_as_longlong(y)), tag});
+        st_b128(p + 32, Word128{static_cast<unsigned long long>(__double_as_longlong(z)), tag});
+    }
+};
 
 template <typename R>
 struct PersistentArgs
 {
     DeviceScene<R> s;
-    int32_t n_regions, n_colours, n_sync_regions, n_island_regions;
-    int32_t const* sync_regions;   // regions with neighbours: one per CTA, CTA b takes sync_regions[b]
-    int32_t const* island_regions; // regions without neighbours: CTA b takes island_regions[b + i*grid]
-    uint4 const* tet_addr;         // per tet (schedule order): 4 vertex addresses
-    DevChunk const* chunks;        // [n_colours * n_regions] clustered-colouring chunks, colour-major then region
-    int32_t const* vtx_off;        // [n_regions + 1] interior vertex list
-    uint32_t const* vtx;           // global vertex id of slot i
-    int32_t const* ifv_off;        // [n_regions + 1] owned interface vertices
+    int32_t n_regions, n_colours;
+    int32_t nvc;                   // scratch entries per thread (4 * NVC4 of the instantiation)
+    int64_t n_clusters;
+    int32_t const* region_order;   // CTA b runs region_order[b], [b + grid], ...; regions that share
+                                   // vertices come first, one per CTA
+    uint2 const* tet_slots;        // per tet (storage order): 4 x u16 slots into the shared vertex array
+    uint4 const* cl_fetch;         // [nvc/4][n_clusters] global vertex ids of the scratch entries
+    uint4 const* cl_meta;          // [nvc/4][n_clusters] touch schedule of those entries (see ClusterPlan)
+    DevChunk const* chunks;        // [(colour * n_regions + region) * 2 + part]
+    int32_t const* vtx_off;        // [n_regions + 1] resident vertex list
+    uint32_t const* vtx;           // global vertex id of resident slot i
+    int32_t const* ifv_off;        // [n_regions + 1] owned non-resident vertices
     uint32_t const* ifv;
+    uint32_t const* ifv_meta;      // their touch schedule (ClusterPlan::vertex_meta)
     int32_t const* surf_off;       // [n_regions + 1] owned surface vertices
     uint32_t const* surf_index;    // surface vertex index (into s.surf_pos / s.surf_first)
-    uint32_t const* surf_addr;     // its vertex address (slot or global)
-    int32_t const* nbr_off;        // [n_regions + 1]
-    int32_t const* nbr;
-    uint32_t* progress;            // [n_regions] steps completed (monotone, wraps)
-    uint32_t base;                 // progress value of every region when this launch starts
+    uint32_t const* surf_addr;     // its vertex address (shared slot, or global | kGlobalBit)
+    uint32_t const* surf_meta;     // touch schedule (used for the non-resident ones)
+    void* xchg;                    // exchange records of every vertex (only non-resident ones are used)
+    uint32_t* error;               // set to 1 when a poll budget ran out
+    uint32_t base;                 // tag of step 0 of this launch
+    long long* trace;              // development aid: per-step clock stamps of thread 0 (nullptr = off)
+    int32_t trace_steps;           // colour steps recorded per region
     int32_t iterations;
     int32_t collide;
     R dt;
 };
 
-// Progress flags: polled with relaxed loads, ONE acquire fence after the poll succeeds; published
-// with one release fence followed by a relaxed store (a fence per poll iteration, or fence.sc via
-// __threadfence(), costs several hundred cycles each on the per-step critical path).
-__device__ __forceinline__ uint32_t ld_relaxed(uint32_t const* p)
+// Wait for `expect` on the record of vertex gv and return its position.
+template <typename R>
+__device__ __forceinline__ void xchg_wait(PersistentArgs<R> const& a, uint32_t gv, uint32_t expect, R& x, R& y, R& z)
 {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v)
-{
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-// interface vertices are shared between SMs: bypass the (non-coherent) L1
-__device__ __forceinline__ Real4<float> ld4_cg(Real4<float> const* p)
-{
-    float4 const v = __ldcg(reinterpret_cast<float4 const*>(p));
-    return {v.x, v.y, v.z, v.w};
-}
-__device__ __forceinline__ Real4<double> ld4_cg(Real4<double> const* p)
-{
-    double2 const a = __ldcg(reinterpret_cast<double2 const*>(p));
-    double2 const b = __ldcg(reinterpret_cast<double2 const*>(p) + 1);
-    return {a.x, a.y, b.x, b.y};
-}
-__device__ __forceinline__ void st4_cg(Real4<float>* p, Real4<float> v)
-{
-    __stcg(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, v.w));
-}
-__device__ __forceinline__ void st4_cg(Real4<double>* p, Real4<double> v)
-{
-    __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
-    __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(v.z, v.w));
+    int polls = 0;
+    while (!Xchg<R>::load(a.xchg, gv, expect, x, y, z))
+    {
+        if (poll_expired(a.error, ++polls))
+            break;
+        __nanosleep(20);
+    }
 }
 
 template <typename R>
 __device__ __forceinline__ Real4<R> load_vertex(uint32_t addr, Real4<R> const* sx, Real4<R> const* pos)
 {
-    return (addr & kGlobalBit) ? ld4_cg(&pos[addr & ~kGlobalBit]) : sx[addr];
-}
-template <typename R>
-__device__ __forceinline__ void store_vertex(uint32_t addr, Real4<R>* sx, Real4<R>* pos, Real4<R> v)
-{
     if (addr & kGlobalBit)
-        st4_cg(&pos[addr & ~kGlobalBit], v);
-    else
-        sx[addr] = v;
+    { // written by another thread of this CTA just before a barrier: read it from L2
+        uint32_t const gv = addr & ~kGlobalBit;
+        return Real4<R>{__ldcg(&pos[gv].x), __ldcg(&pos[gv].y), __ldcg(&pos[gv].z), R(0)};
+    }
+    return sx[addr];
 }
 
 // collision constraints of one vertex, in list order (collision_constraint.cpp:21-48)
@@ -144,176 +257,450 @@ __device__ __forceinline__ bool project_vertex_contacts(DeviceScene<R> const& s,
     return moved;
 }
 
+// per-tet record as the projection consumes it
 template <typename R>
-__device__ void run_region(PersistentArgs<R> const& a, int32_t region, bool sync, Real4<R>* sx)
+struct TetRecord
+{
+    uint2 slots;
+    Real4<R> r0, r1, r2;
+    R lambda;
+};
+
+template <typename R>
+__device__ __forceinline__ TetRecord<R> load_tet(PersistentArgs<R> const& a, int32_t t, int first_iteration)
+{
+    TetRecord<R> q;
+    q.slots  = __ldg(&a.tet_slots[t]);
+    q.r0     = ld4_ro(&a.s.tet_r0[t]);
+    q.r1     = ld4_ro(&a.s.tet_r1[t]);
+    q.r2     = ld4_ro(&a.s.tet_r2[t]);
+    q.lambda = first_iteration ? R(0) : a.s.tet_lambda[t];
+    return q;
+}
+
+// What a thread keeps of a cluster between the moment it is prepared (head loaded, vertices fetched,
+// normally one step ahead) and the moment it runs.
+template <typename R>
+struct ClusterHead
+{
+    TetRecord<R> tet0;
+    R mu, lam, at; // material of the cluster's body; at = alpha / dt^2
+};
+
+template <typename R>
+__device__ __forceinline__ void load_cluster_head(ClusterHead<R>& h, PersistentArgs<R> const& a, DevChunk const& ch,
+                                                  int32_t i, int first_iteration)
+{
+    h.tet0             = load_tet<R>(a, ch.first + i, first_iteration);
+    Real4<R> const mat = ld4_ro(&a.s.materials[mat_index(h.tet0.r2.z)]);
+    h.mu               = mat.x;
+    h.lam              = mat.y;
+    h.at               = mat.z / (a.dt * a.dt);
+}
+
+// Where a colour step sits in the substep: what the tag arithmetic needs.
+struct StepInfo
+{
+    uint32_t step;  // tag of this step
+    uint32_t base;  // tag of the predict step
+    uint32_t shift; // which byte of a fetch entry's schedule word applies: 8 * (2 * (k > 0) + cs)
+};
+
+// tag of the previous touch of a fetched vertex (ClusterPlan::cl_meta)
+__device__ __forceinline__ uint32_t expected_tag(StepInfo const& si, uint32_t meta)
+{
+    uint32_t const d = (meta >> si.shift) & 0xffu;
+    return d == 0xffu ? si.base : si.step - d;
+}
+
+// Fetch of one cluster: every entry of its fetch list waits for the tag of its previous touch and
+// lands in the thread's scratch slots; all polls of a round are in flight together.
+template <typename R, int NVC4, typename Stamp>
+__device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64_t q, Real4<R>* sx,
+                                               StepInfo const& si, Stamp&& stamp)
+{
+    DeviceScene<R> const& s = a.s;
+    int const tid = threadIdx.x, nt = blockDim.x;
+    uint32_t id[4 * NVC4], meta[4 * NVC4];
+    uint32_t pending = 0;
+#pragma unroll
+    for (int k = 0; k < NVC4; ++k)
+    {
+        uint4 const f   = __ldg(&a.cl_fetch[static_cast<int64_t>(k) * a.n_clusters + q]);
+        uint4 const m   = __ldg(&a.cl_meta[static_cast<int64_t>(k) * a.n_clusters + q]);
+        id[4 * k + 0]   = f.x;
+        id[4 * k + 1]   = f.y;
+        id[4 * k + 2]   = f.z;
+        id[4 * k + 3]   = f.w;
+        meta[4 * k + 0] = m.x;
+        meta[4 * k + 1] = m.y;
+        meta[4 * k + 2] = m.z;
+        meta[4 * k + 3] = m.w;
+    }
+    // inverse masses first (constant during the launch, nothing to wait for): they go straight into
+    // the .w of the scratch slots, the polled positions follow
+#pragma unroll
+    for (int j = 0; j < 4 * NVC4; ++j)
+        if (id[j] != kNoVertex)
+        {
+            sx[j * nt + tid].w = s.pos[id[j]].w;
+            pending |= 1u << j;
+        }
+    int polls = 0;
+    stamp(4);
+    while (pending)
+    {
+        // a round: every outstanding record is requested, then every answer is examined
+        constexpr int kBatch = sizeof(R) == 4 ? 4 * NVC4 : 4;
+#pragma unroll
+        for (int h = 0; h < 4 * NVC4; h += kBatch)
+        {
+            typename Xchg<R>::Raw raw[kBatch];
+#pragma unroll
+            for (int e = 0; e < kBatch; ++e)
+                if (pending >> (h + e) & 1u)
+                    raw[e] = Xchg<R>::fetch(a.xchg, id[h + e]);
+#pragma unroll
+            for (int e = 0; e < kBatch; ++e)
+                if (pending >> (h + e) & 1u)
+                {
+                    R x, y, z;
+                    if (Xchg<R>::decode(raw[e], expected_tag(si, meta[h + e]), x, y, z))
+                    {
+                        Real4<R>* slot = &sx[(h + e) * nt + tid];
+                        slot->x        = x;
+                        slot->y        = y;
+                        slot->z        = z;
+                        pending &= ~(1u << (h + e));
+                    }
+                }
+        }
+        if (polls == 0)
+            stamp(2);
+        if (pending && poll_expired(a.error, ++polls))
+            break;
+    }
+    stamp(-(polls + 1)); // slot 1 <- number of poll rounds
+}
+
+// One cluster, fetched already: project its tets in order out of shared memory -> write back.
+// q = storage index of the cluster when it has a fetch list (part A), -1 otherwise.
+template <typename R, int NVC4, typename Stamp>
+__device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk const& ch, int32_t i, int64_t q,
+                                            ClusterHead<R> const& head, Real4<R>* sx, int first_iteration,
+                                            uint32_t tag, Stamp&& stamp)
+{
+    DeviceScene<R> const& s = a.s;
+    int const tid = threadIdx.x, nt = blockDim.x;
+    // the fetch list again, for the write-back: in flight while the tets run
+    uint4 fetch[NVC4];
+#pragma unroll
+    for (int k = 0; k < NVC4; ++k)
+        fetch[k] = q >= 0 ? __ldg(&a.cl_fetch[static_cast<int64_t>(k) * a.n_clusters + q])
+                          : make_uint4(kNoVertex, kNoVertex, kNoVertex, kNoVertex);
+    // column layout: tet m of cluster i sits at first + n[0] + .. + n[m-1] + i
+    int32_t n0 = ch.n[0], n1 = ch.n[1], n2 = ch.n[2], n3 = ch.n[3], n4 = ch.n[4], n5 = ch.n[5], n6 = ch.n[6],
+            n7 = ch.n[7];
+    int32_t t        = ch.first + i;
+    TetRecord<R> cur = head.tet0;
+    int tslot        = 8;
+    stamp(tslot++);
+#pragma unroll 1
+    for (;;)
+    {
+        bool const more = i < n1;
+        TetRecord<R> nxt;
+        if (more)
+            nxt = load_tet<R>(a, t + n0, first_iteration);
+        uint32_t const a1 = cur.slots.x & 0xffffu, a2 = cur.slots.x >> 16, a3 = cur.slots.y & 0xffffu,
+                       a4 = cur.slots.y >> 16;
+        Real4<R> p1 = sx[a1], p2 = sx[a2], p3 = sx[a3], p4 = sx[a4];
+        R lambda = cur.lambda;
+        Vec3<R> const z{};
+        green_project_at<R, false>(p1, p2, p3, p4, z, z, z, z, cur.r0, cur.r1, cur.r2, head.mu, head.lam, head.at,
+                                   R(0), a.dt, lambda);
+        if (lambda != cur.lambda || first_iteration)
+            s.tet_lambda[t] = lambda;
+        if (lambda != cur.lambda)
+        {
+            sx[a1] = p1;
+            sx[a2] = p2;
+            sx[a3] = p3;
+            sx[a4] = p4;
+        }
+        stamp(tslot++);
+        if (!more)
+            break;
+        t += n0;
+        n0  = n1; n1 = n2; n2 = n3; n3 = n4; n4 = n5; n5 = n6; n6 = n7; n7 = 0;
+        cur = nxt;
+    }
+    // write back, always: the tag is what the next touch of each vertex waits for
+#pragma unroll
+    for (int h = 0; h < NVC4; ++h)
+    {
+        uint32_t const id[4] = {fetch[h].x, fetch[h].y, fetch[h].z, fetch[h].w};
+        Real4<R> p[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (id[e] != kNoVertex)
+                p[e] = sx[(4 * h + e) * nt + tid];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (id[e] != kNoVertex)
+                Xchg<R>::store(a.xchg, id[e], p[e].x, p[e].y, p[e].z, tag);
+    }
+    stamp(15);
+}
+
+__device__ __forceinline__ long long clock_stamp()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+
+template <typename R, int NVC4, bool kTrace>
+__device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>* sx, DevChunk* s_chunks)
 {
     DeviceScene<R> const& s = a.s;
     int const tid = threadIdx.x, nt = blockDim.x;
     R const dt              = a.dt;
+    Real4<R>* const sres    = sx + a.nvc * nt; // resident vertices follow the scratch slots
     int32_t const v0 = a.vtx_off[region], nv = a.vtx_off[region + 1] - v0;
     int32_t const i0 = a.ifv_off[region], ni = a.ifv_off[region + 1] - i0;
-    int32_t const n0 = a.nbr_off[region], nn = a.nbr_off[region + 1] - n0;
-    uint32_t step = a.base;
+    int32_t const s0 = a.surf_off[region], ns = a.surf_off[region + 1] - s0;
+    int32_t const C = a.n_colours, cs = a.collide ? 1 : 0, K = C > 0 ? a.iterations : 0;
+    int32_t const per_iteration = C + cs;
+    int32_t const n_phases      = 2 + K * per_iteration; // predict, K x ([collision] colours), commit
 
-    auto wait_neighbours = [&]() {
-        if (sync)
+    // the region's chunk descriptors: [colour][part], read every step
+    {
+        constexpr int32_t W = static_cast<int32_t>(sizeof(DevChunk) / 4);
+        int32_t const words = C * 2 * W;
+        int32_t const* src  = reinterpret_cast<int32_t const*>(a.chunks);
+        int32_t* dst        = reinterpret_cast<int32_t*>(s_chunks);
+        for (int32_t w = tid; w < words; w += nt)
         {
-            if (tid < 32)
-            {
-                for (int32_t j = tid; j < nn; j += 32)
-                {
-                    uint32_t const* flag = &a.progress[a.nbr[n0 + j]];
-                    while (static_cast<int32_t>(ld_relaxed(flag) - step) < 0)
-                    {
-                    }
-                }
-                fence_acq_rel_gpu();
-            }
+            int32_t const c = w / (2 * W), rem = w % (2 * W);
+            dst[w] = src[(static_cast<int64_t>(c) * a.n_regions + region) * 2 * W + rem];
         }
-        __syncthreads();
-    };
-    auto publish = [&]() {
-        ++step;
-        if (sync)
+    }
+    __syncthreads();
+    int32_t traced = 0;
+    auto stamp = [&](int slot) { // slot < 0: record the value -slot in slot 1 instead of a clock stamp
+        if (kTrace && tid == 0 && a.trace && traced < a.trace_steps)
         {
-            __syncthreads();
-            if (tid == 0)
-            {
-                fence_acq_rel_gpu();
-                st_relaxed(&a.progress[region], step);
-            }
+            long long* row = &a.trace[(static_cast<int64_t>(region) * a.trace_steps + traced) * 16];
+            if (slot < 0)
+                row[1] = -slot;
+            else
+                row[slot] = clock_stamp();
         }
     };
-
-    // ---- step 0: predict --------------------------------------------------------------------
-    for (int32_t i = tid; i < nv; i += nt)
-    {
-        uint32_t const gv = a.vtx[v0 + i];
-        Real4<R> p        = ld4(&s.pos[gv]);
-        Real4<R> const x  = ld4(&s.prev[gv]);
-        Real4<R> v        = ld4(&s.vel[gv]);
-        predict_vertex(p, x, v, dt);
-        sx[i] = p;
-    }
-    for (int32_t i = tid; i < ni; i += nt)
-    {
-        uint32_t const gv = a.ifv[i0 + i];
-        Real4<R> p        = ld4_cg(&s.pos[gv]);
-        Real4<R> const x  = ld4(&s.prev[gv]);
-        Real4<R> v        = ld4(&s.vel[gv]);
-        predict_vertex(p, x, v, dt);
-        st4_cg(&s.pos[gv], p);
-    }
-    publish();
-
-    // ---- iterations ---------------------------------------------------------------------------
+    // tag of the last colour step of iteration k that touches a vertex with this schedule
+    auto last_colour_tag = [&](int32_t k, uint32_t lastc) -> uint32_t {
+        return a.base + 1u + static_cast<uint32_t>(k * per_iteration + cs) + lastc;
+    };
     uint32_t const n_contacts =
         a.collide ? min(*s.contact_count, static_cast<uint32_t>(s.contact_cap)) : 0u;
     R const at_c = s.collision_alpha / (dt * dt);
-    int32_t const s0 = a.surf_off[region], ns = a.surf_off[region + 1] - s0;
-    for (int32_t k = 0; k < a.iterations; ++k)
+
+    // Phase p has tag base + p.  p = 0: predict; p = n_phases - 1: commit; in between iteration
+    // k = (p - 1) / per_iteration, and q = (p - 1) % per_iteration is the collision step (q == 0 when
+    // cs) or colour q - cs.  A colour phase with more clusters than threads takes several rounds.
+    //
+    // Every pass of the loop below ends at ONE place that prepares the cluster this thread runs
+    // next (head loaded, vertices fetched) — before the barrier when that cluster belongs to the
+    // next phase: the scratch slots are free once the thread's own cluster is written back, and
+    // the records it waits for come from clusters of phases that do not wait for this thread.
+    ClusterHead<R> head;
+    int32_t item_i = -1; // cluster index within its phase (part A first), -1: nothing prepared
+    int32_t round  = 0;
+    for (int32_t p = 0; p < n_phases;)
     {
-        int const first_iteration = k == 0;
-        if (a.collide)
-        {
-            wait_neighbours();
-            if (n_contacts > 0)
-                for (int32_t i = tid; i < ns; i += nt)
-                {
-                    uint32_t const first = s.surf_first[a.surf_index[s0 + i]];
-                    if (first == 0xffffffffu)
-                        continue;
-                    uint32_t const addr = a.surf_addr[s0 + i];
-                    Real4<R> p          = load_vertex(addr, sx, s.pos);
-                    if (project_vertex_contacts(s, first, n_contacts, p, at_c, first_iteration))
-                        store_vertex(addr, sx, s.pos, p);
-                }
-            publish();
-        }
-        for (int32_t c = 0; c < a.n_colours; ++c)
-        {
-            DevChunk const ch = a.chunks[c * a.n_regions + region];
-            wait_neighbours();
-            for (int32_t i = tid; i < ch.n[0]; i += nt)
+        uint32_t const tag = a.base + static_cast<uint32_t>(p);
+        int32_t const k    = p == 0 ? 0 : (p - 1) / per_iteration;
+        int32_t const q    = p == 0 ? 0 : (p - 1) % per_iteration;
+        bool advance       = true;
+        if (p == 0)
+        { // ---- predict (timestep.cpp:35-43)
+            for (int32_t i = tid; i < nv; i += nt)
             {
-                int32_t base = ch.first;
-#pragma unroll 1
-                for (int m = 0; m < 8; ++m)
+                uint32_t const gv = a.vtx[v0 + i];
+                Real4<R> pp       = ld4(&s.pos[gv]);
+                Real4<R> const x  = ld4(&s.prev[gv]);
+                Real4<R> v        = ld4(&s.vel[gv]);
+                predict_vertex(pp, x, v, dt);
+                sres[i] = pp;
+            }
+            for (int32_t i = tid; i < ni; i += nt)
+            {
+                uint32_t const gv = a.ifv[i0 + i];
+                Real4<R> pp       = ld4(&s.pos[gv]);
+                Real4<R> const x  = ld4(&s.prev[gv]);
+                Real4<R> v        = ld4(&s.vel[gv]);
+                predict_vertex(pp, x, v, dt);
+                Xchg<R>::store(a.xchg, gv, pp.x, pp.y, pp.z, tag);
+            }
+        }
+        else if (p == n_phases - 1)
+        { // ---- commit (timestep.cpp:48-57) + surface copy
+            for (int32_t i = tid; i < nv; i += nt)
+            {
+                uint32_t const gv = a.vtx[v0 + i];
+                Real4<R> const pp = sres[i];
+                Real4<R> xn       = ld4(&s.prev[gv]);
+                Real4<R> v        = ld4(&s.vel[gv]);
+                commit_vertex(pp, xn, v, dt);
+                st4(&s.vel[gv], v);
+                st4(&s.prev[gv], xn);
+            }
+            for (int32_t i = tid; i < ni; i += nt)
+            {
+                uint32_t const gv    = a.ifv[i0 + i];
+                uint32_t const meta  = a.ifv_meta[i0 + i];
+                uint32_t const lastc = meta & 0xffu;
+                uint32_t want        = a.base;
+                if (K > 0)
                 {
-                    if (i >= ch.n[m])
-                        break;
-                    int32_t const t = base + i;
-                    base += ch.n[m];
-                    uint4 const ad    = __ldg(&a.tet_addr[t]);
-                    Real4<R> const r0 = ld4_ro(&s.tet_r0[t]);
-                    Real4<R> const r1 = ld4_ro(&s.tet_r1[t]);
-                    Real4<R> const r2 = ld4_ro(&s.tet_r2[t]);
-                    Real4<R> p1 = load_vertex(ad.x, sx, s.pos), p2 = load_vertex(ad.y, sx, s.pos),
-                             p3 = load_vertex(ad.z, sx, s.pos), p4 = load_vertex(ad.w, sx, s.pos);
-                    Real4<R> const mat = ld4_ro(&s.materials[mat_index(r2.z)]);
-                    R lambda           = first_iteration ? R(0) : s.tet_lambda[t];
-                    R const lambda_in  = lambda;
-                    Vec3<R> const z{};
-                    green_project<R, false>(p1, p2, p3, p4, z, z, z, z, r0, r1, r2, mat, dt, lambda);
-                    if (lambda != lambda_in || first_iteration)
-                        s.tet_lambda[t] = lambda;
-                    if (lambda != lambda_in)
+                    if (lastc != kNoColour)
+                        want = last_colour_tag(K - 1, lastc);
+                    else if (cs && (meta & 0x100u))
+                        want = a.base + 1u + static_cast<uint32_t>((K - 1) * per_iteration);
+                }
+                Real4<R> pp;
+                xchg_wait<R>(a, gv, want, pp.x, pp.y, pp.z);
+                Real4<R> xn = ld4(&s.prev[gv]);
+                Real4<R> v  = ld4(&s.vel[gv]);
+                commit_vertex(pp, xn, v, dt);
+                st4(&s.vel[gv], v);
+                st4(&s.prev[gv], xn);
+            }
+            __syncthreads(); // prev[] of the owned vertices is final: the surface copy below reads it
+            // tetrahedral_body_t::update_visual_model (tetrahedral_body.cpp:157-165), owned surface vertices
+            for (int32_t i = tid; i < ns; i += nt)
+            {
+                uint32_t const addr = a.surf_addr[s0 + i];
+                Real4<R> const pp   = load_vertex(addr, sx, s.prev);
+                st4(&s.surf_pos[a.surf_index[s0 + i]], Real4<R>{pp.x, pp.y, pp.z, R(0)});
+            }
+        }
+        else if (cs && q == 0)
+        { // ---- collision constraints of the owned surface vertices (gauss_seidel_solver.cpp:28-31);
+          //      non-resident ones are re-tagged whether or not they have a contact
+            for (int32_t i = tid; i < ns; i += nt)
+            {
+                uint32_t const addr  = a.surf_addr[s0 + i];
+                uint32_t const first = n_contacts > 0 ? s.surf_first[a.surf_index[s0 + i]] : 0xffffffffu;
+                if (addr & kGlobalBit)
+                {
+                    uint32_t const gv    = addr & ~kGlobalBit;
+                    uint32_t const lastc = a.surf_meta[s0 + i] & 0xffu;
+                    uint32_t const want  = (k > 0 && lastc != kNoColour) ? last_colour_tag(k - 1, lastc)
+                                           : k > 0                       ? tag - static_cast<uint32_t>(per_iteration)
+                                                                         : a.base;
+                    Real4<R> pp;
+                    xchg_wait<R>(a, gv, want, pp.x, pp.y, pp.z);
+                    if (first != 0xffffffffu)
                     {
-                        store_vertex(ad.x, sx, s.pos, p1);
-                        store_vertex(ad.y, sx, s.pos, p2);
-                        store_vertex(ad.z, sx, s.pos, p3);
-                        store_vertex(ad.w, sx, s.pos, p4);
+                        pp.w = s.pos[gv].w;
+                        project_vertex_contacts(s, first, n_contacts, pp, at_c, k == 0);
                     }
+                    Xchg<R>::store(a.xchg, gv, pp.x, pp.y, pp.z, tag);
+                }
+                else if (first != 0xffffffffu)
+                {
+                    Real4<R> pp = sx[addr];
+                    if (project_vertex_contacts(s, first, n_contacts, pp, at_c, k == 0))
+                        sx[addr] = pp;
                 }
             }
-            if (!sync)
-                __syncthreads(); // publish() carries the barrier when syncing
-            publish();
+        }
+        else
+        { // ---- colour q - cs of iteration k (gauss_seidel_solver.cpp:32-35)
+            int32_t const c  = q - cs;
+            int32_t const nA = s_chunks[2 * c].n[0], nB = s_chunks[2 * c + 1].n[0];
+            if (round == 0)
+                stamp(0);
+            if (item_i >= 0)
+            { // cluster item_i of the phase runs on thread item_i % nt; part A (clusters that fetch) first
+                bool const in_a    = item_i < nA;
+                DevChunk const& ch = s_chunks[2 * c + (in_a ? 0 : 1)];
+                int32_t const ci   = in_a ? item_i : item_i - nA;
+                run_cluster<R, NVC4>(a, ch, ci, in_a ? static_cast<int64_t>(ch.cfirst) + ci : int64_t{-1}, head, sx,
+                                     k == 0, tag, stamp);
+            }
+            advance = (round + 1) * nt >= nA + nB;
+            stamp(6);
+        }
+
+        // ---- the one place where the next cluster of this thread is prepared
+        int32_t np = p, ni_next = -1;
+        if (!advance)
+        {
+            ++round;
+            ni_next = round * nt + tid;
+        }
+        else
+        {
+            round = 0;
+            np    = p + 1;
+            ni_next = tid;
+        }
+        item_i = -1;
+        if (np > 0 && np < n_phases - 1)
+        {
+            int32_t const nk = (np - 1) / per_iteration, nq = (np - 1) % per_iteration;
+            if (!(cs && nq == 0))
+            {
+                int32_t const c  = nq - cs;
+                int32_t const nA = s_chunks[2 * c].n[0], nB = s_chunks[2 * c + 1].n[0];
+                if (ni_next < nA + nB)
+                {
+                    item_i             = ni_next;
+                    bool const in_a    = item_i < nA;
+                    DevChunk const& ch = s_chunks[2 * c + (in_a ? 0 : 1)];
+                    int32_t const ci   = in_a ? item_i : item_i - nA;
+                    load_cluster_head<R>(head, a, ch, ci, nk == 0);
+                    if (in_a)
+                        gather_cluster<R, NVC4>(a, static_cast<int64_t>(ch.cfirst) + ci, sx,
+                                                StepInfo{a.base + static_cast<uint32_t>(np), a.base,
+                                                         static_cast<uint32_t>(8 * (2 * (nk > 0 ? 1 : 0) + cs))},
+                                                stamp);
+                }
+            }
+        }
+        if (advance)
+        {
+            __syncthreads();
+            if (p > 0 && p < n_phases - 1 && !(cs && q == 0))
+            {
+                stamp(7);
+                ++traced;
+            }
+            p = np;
         }
     }
-
-    // ---- last step: commit + surface copy -----------------------------------------------------
-    wait_neighbours();
-    for (int32_t i = tid; i < nv; i += nt)
-    {
-        uint32_t const gv = a.vtx[v0 + i];
-        Real4<R> const p  = sx[i];
-        Real4<R> xn       = ld4(&s.prev[gv]);
-        Real4<R> v        = ld4(&s.vel[gv]);
-        commit_vertex(p, xn, v, dt);
-        st4(&s.vel[gv], v);
-        st4(&s.prev[gv], xn);
-    }
-    for (int32_t i = tid; i < ni; i += nt)
-    {
-        uint32_t const gv = a.ifv[i0 + i];
-        Real4<R> const p  = ld4_cg(&s.pos[gv]);
-        Real4<R> xn       = ld4(&s.prev[gv]);
-        Real4<R> v        = ld4(&s.vel[gv]);
-        commit_vertex(p, xn, v, dt);
-        st4(&s.vel[gv], v);
-        st4(&s.prev[gv], xn);
-    }
-    // tetrahedral_body_t::update_visual_model (tetrahedral_body.cpp:157-165) for owned surface vertices
-    for (int32_t i = tid; i < ns; i += nt)
-    {
-        uint32_t const addr = a.surf_addr[s0 + i];
-        Real4<R> const p    = load_vertex(addr, sx, s.pos);
-        st4(&s.surf_pos[a.surf_index[s0 + i]], Real4<R>{p.x, p.y, p.z, R(0)});
-    }
-    publish();
     __syncthreads(); // shared memory is reused by the next region of this CTA
 }
 
-template <typename R>
-__global__ void __launch_bounds__(512) k_substep_persistent(PersistentArgs<R> a)
+// dynamic shared memory: [chunk descriptors of the region | scratch slots | resident vertices]
+__host__ __device__ inline size_t chunk_area_bytes(int n_colours)
+{
+    return (static_cast<size_t>(n_colours) * 2 * sizeof(DevChunk) + 31) / 32 * 32;
+}
+
+template <typename R, int NVC4, bool kTrace, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads) k_substep_persistent(PersistentArgs<R> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Real4<R>* sx = reinterpret_cast<Real4<R>*>(smem_raw);
-    if (static_cast<int32_t>(blockIdx.x) < a.n_sync_regions)
-        run_region<R>(a, a.sync_regions[blockIdx.x], true, sx);
-    for (int32_t i = blockIdx.x; i < a.n_island_regions; i += gridDim.x)
-        run_region<R>(a, a.island_regions[i], false, sx);
+    DevChunk* s_chunks = reinterpret_cast<DevChunk*>(smem_raw);
+    Real4<R>* sx       = reinterpret_cast<Real4<R>*>(smem_raw + chunk_area_bytes(a.n_colours));
+    // regions that share vertices come first in region_order (at most one per CTA: they must be
+    // co-resident), the others follow and are handed out round-robin
+    for (int32_t i = blockIdx.x; i < a.n_regions; i += gridDim.x)
+        run_region<R, NVC4, kTrace>(a, a.region_order[i], sx, s_chunks);
 }
 
 template <typename T>
@@ -342,18 +729,29 @@ template <typename R>
 struct PersistentPlan
 {
     PersistentArgs<R> args{};
-    PBuf<int32_t> sync_regions, island_regions, vtx_off, ifv_off, surf_off, nbr_off, nbr;
+    PBuf<int32_t> region_order, vtx_off, ifv_off, surf_off;
     PBuf<DevChunk> chunks;
-    PBuf<uint32_t> vtx, ifv, surf_index, surf_addr, progress;
-    PBuf<uint4> tet_addr;
+    PBuf<uint32_t> vtx, ifv, ifv_meta, surf_index, surf_addr, surf_meta, error;
+    PBuf<uint2> tet_slots;
+    PBuf<uint4> cl_fetch, cl_meta, xchg;
+    PBuf<long long> trace;
+    int64_t trace_len = 0;
     int grid = 0, block = 0;
     size_t smem = 0;
-    uint32_t base = 0;
+    uint32_t base = 1; // tags start at 1: the zero-initialised exchange array never matches an expected tag
     bool ready = false;
+    void const* kernel = nullptr;
     std::string why_not;
 
-    // how many regions to cut the scene into
-    static int32_t regions_for(int sm_count, int64_t /*n_tets*/) { return sm_count; }
+    static constexpr int64_t kSmemBudget   = 224 * 1024;
+    static constexpr int64_t kVertexBudget = 200 * 1024; // scratch + resident vertices (rest: chunk descriptors)
+
+    // how many regions to cut the scene into: one per SM, but at least ~64 clusters per colour step
+    // and region (small scenes use fewer SMs rather than synchronise regions of a few tets)
+    static int32_t regions_for(int sm_count, int64_t n_tets)
+    {
+        return static_cast<int32_t>(std::max<int64_t>(1, std::min<int64_t>(sm_count, n_tets / 2560)));
+    }
     // ensembles: many independent bodies -> one region per body
     static bool wants_region_per_body(HostScene const& h, int sm_count)
     {
@@ -362,6 +760,21 @@ struct PersistentPlan
             bodies += (b.kind == BodyKind::tet && b.n_tets > 0);
         return bodies >= 2 * static_cast<int64_t>(sm_count);
     }
+    static ResidentParams resident_params()
+    {
+        ResidentParams rp;
+        rp.smem_bytes   = kVertexBudget;
+        rp.vertex_bytes = static_cast<int32_t>(sizeof(Real4<R>));
+        rp.max_threads  = 512;
+        return rp;
+    }
+
+    template <int NVC4, bool kTrace>
+    static void const* pick(bool small)
+    {
+        return small ? reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 256>)
+                     : reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 512>);
+    }
 
     // returns false (with why_not) when the scene does not fit this schedule
     bool build(HostScene const& h, ClusterPlan const& cp, RegionPlan const& plan, DeviceScene<R> const& d,
@@ -369,51 +782,72 @@ struct PersistentPlan
     {
         int32_t const Rn = plan.n_regions;
         int64_t const T = h.n_tets(), V = h.n_vertices();
+        if (!cp.why_not.empty())
+        {
+            why_not = cp.why_not;
+            return false;
+        }
         if (T >= (int64_t{1} << 31) / 2)
         {
             why_not = "too many tets for 32-bit chunk offsets";
             return false;
         }
-        // tets in storage order -> vertex addresses; chunk descriptors
-        std::vector<uint4> addr(static_cast<size_t>(T));
-        for (int64_t p = 0; p < T; ++p)
-        {
-            uint32_t const t = cp.storage_order[static_cast<size_t>(p)];
-            int32_t const r  = plan.tet_region[t];
-            uint32_t ad[4];
-            for (int k = 0; k < 4; ++k)
-            {
-                uint32_t const gv = h.tets[4 * static_cast<size_t>(t) + k];
-                ad[k] = plan.vertex_region[gv] == r ? plan.vertex_slot[gv] : (gv | kGlobalBit);
-            }
-            addr[static_cast<size_t>(p)] = make_uint4(ad[0], ad[1], ad[2], ad[3]);
-        }
-        std::vector<DevChunk> hchunks(cp.chunks.size());
-        for (size_t i = 0; i < cp.chunks.size(); ++i)
-        {
-            hchunks[i].first = cp.chunks[i].first;
-            for (int m = 0; m < 8; ++m)
-                hchunks[i].n[m] = cp.chunks[i].n[m];
-        }
-        if (cp.n_regions != Rn)
+        if (cp.n_regions != Rn || cp.nt <= 0 || static_cast<int64_t>(cp.tet_slots.size()) != 4 * T)
         {
             why_not = "cluster plan and region plan disagree";
             return false;
         }
-        // owned interface vertices, owned surface vertices
+        int const nvc = cp.nvc <= 8 ? 8 : 16; // instantiations: 8 or 16 scratch entries per thread
+        int64_t const scratch = static_cast<int64_t>(cp.nvc) * cp.nt;
+        std::vector<uint2> slots(static_cast<size_t>(T));
+        for (int64_t p = 0; p < T; ++p)
+        {
+            uint32_t q[4];
+            for (int k = 0; k < 4; ++k)
+            { // the plan laid the slots out for cp.nvc scratch entries; the kernel has `nvc`
+                uint32_t const sl = cp.tet_slots[4 * static_cast<size_t>(p) + k];
+                q[k]              = sl >= scratch ? sl + static_cast<uint32_t>((nvc - cp.nvc) * cp.nt) : sl;
+            }
+            slots[static_cast<size_t>(p)] = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
+        }
+        int64_t const Q = cp.n_clusters;
+        std::vector<uint4> fetch(static_cast<size_t>(nvc / 4) * static_cast<size_t>(Q),
+                                 make_uint4(kNoVertex, kNoVertex, kNoVertex, kNoVertex));
+        std::vector<uint4> meta(fetch.size(), make_uint4(0u, 0u, 0u, 0u));
+        for (int k4 = 0; k4 < cp.nvc / 4; ++k4)
+            for (int64_t q = 0; q < Q; ++q)
+            {
+                size_t const at = static_cast<size_t>(k4) * Q + q;
+                auto const f    = [&](int e) { return cp.cl_fetch[static_cast<size_t>(4 * k4 + e) * Q + q]; };
+                auto const m    = [&](int e) { return cp.cl_meta[static_cast<size_t>(4 * k4 + e) * Q + q]; };
+                fetch[at]       = make_uint4(f(0), f(1), f(2), f(3));
+                meta[at]        = make_uint4(m(0), m(1), m(2), m(3));
+            }
+        std::vector<DevChunk> hchunks(cp.chunks.size());
+        for (size_t i = 0; i < cp.chunks.size(); ++i)
+        {
+            hchunks[i].first  = cp.chunks[i].first;
+            hchunks[i].cfirst = cp.chunks[i].cfirst;
+            for (int m = 0; m < 8; ++m)
+                hchunks[i].n[m] = cp.chunks[i].n[m];
+        }
+        // owned non-resident vertices, owned surface vertices
         std::vector<int32_t> ioff(static_cast<size_t>(Rn) + 1, 0), soff(static_cast<size_t>(Rn) + 1, 0);
         for (int64_t v = 0; v < V; ++v)
             if (plan.vertex_region[static_cast<size_t>(v)] < 0)
                 ++ioff[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)]) + 1];
         for (int32_t r = 0; r < Rn; ++r)
             ioff[static_cast<size_t>(r) + 1] += ioff[static_cast<size_t>(r)];
-        std::vector<uint32_t> ifv(static_cast<size_t>(ioff.back()));
+        std::vector<uint32_t> ifv(static_cast<size_t>(ioff.back())), ifm(ifv.size());
         {
             std::vector<int32_t> cur(ioff.begin(), ioff.end() - 1);
             for (int64_t v = 0; v < V; ++v)
                 if (plan.vertex_region[static_cast<size_t>(v)] < 0)
-                    ifv[static_cast<size_t>(cur[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)])]++)] =
-                        static_cast<uint32_t>(v);
+                {
+                    int32_t const at = cur[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)])]++;
+                    ifv[static_cast<size_t>(at)] = static_cast<uint32_t>(v);
+                    ifm[static_cast<size_t>(at)] = cp.vertex_meta[static_cast<size_t>(v)];
+                }
         }
         std::vector<uint32_t> sgv; // global vertex of surface vertex i (same order as DeviceScene::surf_v)
         for (auto const& b : h.bodies)
@@ -424,7 +858,7 @@ struct PersistentPlan
             ++soff[static_cast<size_t>(plan.vertex_owner[gv]) + 1];
         for (int32_t r = 0; r < Rn; ++r)
             soff[static_cast<size_t>(r) + 1] += soff[static_cast<size_t>(r)];
-        std::vector<uint32_t> sidx(sgv.size()), sadr(sgv.size());
+        std::vector<uint32_t> sidx(sgv.size()), sadr(sgv.size()), smeta(sgv.size());
         {
             std::vector<int32_t> cur(soff.begin(), soff.end() - 1);
             for (size_t i = 0; i < sgv.size(); ++i)
@@ -432,12 +866,14 @@ struct PersistentPlan
                 uint32_t const gv = sgv[i];
                 int32_t const r   = plan.vertex_owner[gv];
                 int32_t const pos = cur[static_cast<size_t>(r)]++;
-                sidx[static_cast<size_t>(pos)] = static_cast<uint32_t>(i);
-                sadr[static_cast<size_t>(pos)] =
-                    plan.vertex_region[gv] == r ? plan.vertex_slot[gv] : (gv | kGlobalBit);
+                sidx[static_cast<size_t>(pos)]  = static_cast<uint32_t>(i);
+                sadr[static_cast<size_t>(pos)]  = plan.vertex_region[gv] == r
+                                                      ? static_cast<uint32_t>(nvc * cp.nt) + plan.vertex_slot[gv]
+                                                      : (gv | kGlobalBit);
+                smeta[static_cast<size_t>(pos)] = cp.vertex_meta[gv];
             }
         }
-        // sync regions (have neighbours) vs islands
+        // regions that share vertices must be co-resident; the others are handed out round-robin
         std::vector<int32_t> sync_r, island_r;
         for (int32_t r = 0; r < Rn; ++r)
             (plan.nbr_offsets[static_cast<size_t>(r) + 1] > plan.nbr_offsets[static_cast<size_t>(r)] ? sync_r : island_r)
@@ -445,23 +881,39 @@ struct PersistentPlan
         std::vector<int32_t> voff(plan.region_vtx_offsets.begin(), plan.region_vtx_offsets.end());
 
         // launch shape
-        int64_t const max_chunk = cp.max_chunk_clusters;
-        smem  = static_cast<size_t>(std::max<int64_t>(plan.max_region_vertices, 1)) * sizeof(Real4<R>);
-        block = static_cast<int>(std::min<int64_t>(512, std::max<int64_t>(64, (max_chunk + 31) / 32 * 32)));
-        if (smem > 220 * 1024)
+        smem  = chunk_area_bytes(cp.n_colours) +
+               static_cast<size_t>(static_cast<int64_t>(nvc) * cp.nt + std::max<int64_t>(plan.max_region_vertices, 1)) *
+                   sizeof(Real4<R>);
+        block = cp.nt;
+        if (static_cast<int64_t>(smem) > kSmemBudget)
         {
-            why_not = "a region's interior vertices do not fit shared memory";
+            why_not = "resident vertices and scratch slots do not fit shared memory";
             return false;
         }
-        if (cudaFuncSetAttribute(k_substep_persistent<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)) != cudaSuccess)
+        // SBSB200_TRACE_STEPS=N (development aid): record clock stamps of the first N colour steps of
+        // every launch, readable through sbsb200_debug_read_trace
+        int trace_n = 0;
+        if (char const* e = std::getenv("SBSB200_TRACE_STEPS"))
+            trace_n = std::atoi(e);
+        bool const small = block <= 256; // up to 255 registers per thread
+        if (trace_n > 0 && nvc == 8)
+        {
+            kernel = pick<2, true>(small);
+            trace.upload(std::vector<long long>(static_cast<size_t>(Rn) * trace_n * 16, 0), st);
+            args.trace       = trace.p;
+            args.trace_steps = trace_n;
+            trace_len        = static_cast<int64_t>(Rn) * trace_n * 16;
+        }
+        else
+            kernel = nvc == 8 ? pick<2, false>(small) : pick<4, false>(small);
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
+            cudaSuccess)
         {
             why_not = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
             return false;
         }
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_substep_persistent<R>, block, smem) != cudaSuccess ||
-            per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1)
         {
             why_not = "kernel does not fit an SM with this block/shared-memory size";
             return false;
@@ -476,46 +928,55 @@ struct PersistentPlan
             1, std::max<int64_t>(static_cast<int64_t>(sync_r.size()),
                                  std::min<int64_t>(capacity, static_cast<int64_t>(island_r.size())))));
 
-        sync_regions.upload(sync_r, st);
-        island_regions.upload(island_r, st);
-        tet_addr.upload(addr, st);
+        std::vector<int32_t> order(sync_r);
+        order.insert(order.end(), island_r.begin(), island_r.end());
+        region_order.upload(order, st);
+        tet_slots.upload(slots, st);
+        cl_fetch.upload(fetch, st);
+        cl_meta.upload(meta, st);
         chunks.upload(hchunks, st);
         vtx_off.upload(voff, st);
         vtx.upload(plan.region_vtx, st);
         ifv_off.upload(ioff, st);
         this->ifv.upload(ifv, st);
+        ifv_meta.upload(ifm, st);
         surf_off.upload(soff, st);
         surf_index.upload(sidx, st);
         surf_addr.upload(sadr, st);
-        nbr_off.upload(plan.nbr_offsets, st);
-        nbr.upload(plan.nbr, st);
-        progress.upload(std::vector<uint32_t>(static_cast<size_t>(Rn), 0u), st);
-        base = 0;
+        surf_meta.upload(smeta, st);
+        xchg.upload(std::vector<uint4>(static_cast<size_t>(std::max<int64_t>(V, 1)) * Xchg<R>::kWords,
+                                       make_uint4(0u, 0u, 0u, 0u)),
+                    st);
+        error.upload(std::vector<uint32_t>(1, 0u), st);
+        base = 1;
 
         args.s                = d;
         args.n_regions        = Rn;
         args.n_colours        = cp.n_colours;
-        args.n_sync_regions   = static_cast<int32_t>(sync_r.size());
-        args.n_island_regions = static_cast<int32_t>(island_r.size());
-        args.sync_regions     = sync_regions.p;
-        args.island_regions   = island_regions.p;
-        args.tet_addr         = tet_addr.p;
+
+        args.nvc              = nvc;
+        args.n_clusters       = Q;
+        args.region_order     = region_order.p;
+        args.tet_slots        = tet_slots.p;
+        args.cl_fetch         = cl_fetch.p;
+        args.cl_meta          = cl_meta.p;
         args.chunks           = chunks.p;
         args.vtx_off          = vtx_off.p;
         args.vtx              = vtx.p;
         args.ifv_off          = ifv_off.p;
         args.ifv              = this->ifv.p;
+        args.ifv_meta         = ifv_meta.p;
         args.surf_off         = surf_off.p;
         args.surf_index       = surf_index.p;
         args.surf_addr        = surf_addr.p;
-        args.nbr_off          = nbr_off.p;
-        args.nbr              = nbr.p;
-        args.progress         = progress.p;
+        args.surf_meta        = surf_meta.p;
+        args.xchg             = xchg.p;
+        args.error            = error.p;
         ready                 = true;
         return true;
     }
 
-    // steps published per substep launch
+    // tags consumed per substep launch
     uint32_t steps_per_substep(int iterations, bool collide) const
     {
         return 2u + static_cast<uint32_t>(iterations) * (static_cast<uint32_t>(args.n_colours) + (collide ? 1u : 0u));
@@ -530,13 +991,21 @@ struct PersistentPlan
         args.collide    = collide ? 1 : 0;
         args.base       = base;
         void* params[]  = {&args};
-        cudaError_t const e = cudaLaunchCooperativeKernel(reinterpret_cast<void const*>(k_substep_persistent<R>),
-                                                          dim3(static_cast<unsigned>(grid)), dim3(static_cast<unsigned>(block)),
-                                                          params, smem, st);
+        cudaError_t const e = cudaLaunchCooperativeKernel(kernel, dim3(static_cast<unsigned>(grid)),
+                                                          dim3(static_cast<unsigned>(block)), params, smem, st);
         if (e != cudaSuccess)
             throw std::runtime_error(std::string("cudaLaunchCooperativeKernel: ") + cudaGetErrorString(e));
         base += steps_per_substep(iterations, collide);
         return 1;
+    }
+
+    // true when a launch ran out of its poll budget (call after synchronising the stream)
+    bool timed_out() const
+    {
+        uint32_t e = 0;
+        if (ready && error.p)
+            cudaMemcpy(&e, error.p, sizeof e, cudaMemcpyDeviceToHost);
+        return e != 0;
     }
 };
 

@@ -62,7 +62,8 @@ extern "C" int64_t hs_regions(int64_t nV, int64_t nT, const uint32_t* tets, cons
 // clustered colouring of a single tet body (or `n_bodies` copies laid out along x); outputs
 // serial_order[T], storage_order[T], tet_region[T]; returns n_colours, or -1 if the plan is invalid
 extern "C" int hs_cluster_plan(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_bodies,
-                               int n_regions, int per_body, uint32_t* serial_order, uint32_t* storage_order,
+                               int n_regions, int per_body, int64_t smem_bytes, uint32_t* serial_order,
+                               uint32_t* storage_order,
                                int32_t* tet_region, int64_t* n_clusters, int64_t* max_chunk)
 {
     HostScene h;
@@ -90,7 +91,22 @@ extern "C" int hs_cluster_plan(int64_t nV, int64_t nT, const uint32_t* tets, con
         h.bodies.push_back(hb);
     }
     ClusterPlan plan;
-    build_cluster_plan(h, n_regions, per_body != 0, plan);
+    if (smem_bytes > 0)
+    { // resident (persistent) layout: also check the shared-memory slots and fetch lists
+        ResidentParams rp;
+        rp.smem_bytes   = smem_bytes;
+        rp.vertex_bytes = 16;
+        rp.max_threads  = 512;
+        RegionPlan regions;
+        build_cluster_plan(h, n_regions, per_body != 0, plan, &rp, &regions);
+        if (!plan.why_not.empty() || !resident_layout_is_valid(h, plan, regions))
+            return -2;
+        int64_t scratch = static_cast<int64_t>(plan.nvc) * plan.nt;
+        if ((scratch + regions.max_region_vertices) * rp.vertex_bytes > smem_bytes)
+            return -3;
+    }
+    else
+        build_cluster_plan(h, n_regions, per_body != 0, plan);
     if (!cluster_plan_is_valid(h, plan))
         return -1;
     std::memcpy(serial_order, plan.serial_order.data(), sizeof(uint32_t) * plan.serial_order.size());

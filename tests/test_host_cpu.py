@@ -35,7 +35,7 @@ def hostscene():
     L.hs_colour.argtypes = [C.c_int64, C.c_int64, C.c_int, u32p, dp, u32p, i64p, C.c_int, i32p]
     L.hs_regions.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, i32p, i32p, i32p]
     L.hs_regions.restype = C.c_int64
-    L.hs_cluster_plan.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int, u32p, u32p, i32p, i64p,
+    L.hs_cluster_plan.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int, C.c_int64, u32p, u32p, i32p, i64p,
                                   i64p]
     return L
 
@@ -137,10 +137,11 @@ def test_colouring_is_conflict_free_and_a_permutation(hostscene, oracle, dims):
         assert len(np.unique(vs)) == len(vs)
 
 
+@pytest.mark.parametrize("smem", [0, 220 * 1024, 24 * 1024])
 @pytest.mark.parametrize("dims,bodies,regions,per_body", [((8, 8, 16), 1, 1, 0), ((8, 8, 16), 1, 148, 0),
                                                           ((21, 21, 51), 1, 148, 0), ((6, 6, 17), 40, 0, 1),
                                                           ((2, 2, 2), 1, 1, 0), ((3, 2, 2), 3, 5, 0)])
-def test_clustered_colouring_of_lattices(hostscene, oracle, dims, bodies, regions, per_body):
+def test_clustered_colouring_of_lattices(hostscene, oracle, dims, bodies, regions, per_body, smem):
     """Clusters = lattice cells (5 tets), exactly 8 colours (2x2x2 parity), conflict-free (checked
     by cluster_plan_is_valid inside hs_cluster_plan), serial and storage orders are permutations,
     and the tets of one cell are consecutive in the exported serial order."""
@@ -153,7 +154,7 @@ def test_clustered_colouring_of_lattices(hostscene, oracle, dims, bodies, region
     treg = np.empty(T, np.int32)
     ncl, mch = C.c_int64(0), C.c_int64(0)
     nc = hostscene.hs_cluster_plan(len(pos), len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), bodies,
-                                   regions, per_body, serial.ctypes.data_as(u32p), storage.ctypes.data_as(u32p),
+                                   regions, per_body, smem, serial.ctypes.data_as(u32p), storage.ctypes.data_as(u32p),
                                    treg.ctypes.data_as(i32p), C.byref(ncl), C.byref(mch))
     n_cells = (dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1)
     assert nc == min(8, 2 ** sum(d > 2 for d in dims))
@@ -182,9 +183,9 @@ def test_clustered_colouring_of_an_irregular_mesh(hostscene):
     storage = np.empty(T, np.uint32)
     treg = np.empty(T, np.int32)
     ncl, mch = C.c_int64(0), C.c_int64(0)
-    for regions in (1, 7):
+    for regions, smem in ((1, 0), (7, 0), (7, 220 * 1024), (3, 20 * 1024)):
         nc = hostscene.hs_cluster_plan(200, T, tets.ctypes.data_as(u32p), pts.ctypes.data_as(dp), 1, regions, 0,
-                                       serial.ctypes.data_as(u32p), storage.ctypes.data_as(u32p),
+                                       smem, serial.ctypes.data_as(u32p), storage.ctypes.data_as(u32p),
                                        treg.ctypes.data_as(i32p), C.byref(ncl), C.byref(mch))
         assert nc > 0, "plan must be conflict-free"
         assert np.array_equal(np.sort(serial), np.arange(T))

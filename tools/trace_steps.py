@@ -1,0 +1,39 @@
+"""Development aid: per-phase cycle breakdown of the persistent kernel's colour steps.
+SBSB200_TRACE_STEPS=N python tools/trace_steps.py <config>"""
+import importlib, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+N = int(os.environ.setdefault("SBSB200_TRACE_STEPS", "80"))
+sbs = importlib.import_module("soft-body-simulator_b200")
+sc = importlib.import_module("soft-body-simulator_b200.scenes")
+cfg = sys.argv[1] if len(sys.argv) > 1 else "config3"
+scene = getattr(sc, cfg)()
+sim = sbs.Simulation(0, 32, schedule=2)
+scene.instantiate(sim)
+for _ in range(3):
+    sim.step(scene.dt, scene.substeps, scene.iterations, scene.detect_every_substep)
+sim.synchronize()
+print(sim.stats())
+full = sim.debug_trace().reshape(-1, N, 16)
+t = full[:, :, :8]
+t = t[:, 8:, :]                      # skip the first sweep (cold)
+valid = full[:, 8:, 0] > 0
+def show(name, x):
+    x = x[np.isfinite(x)]
+    if x.size:
+        print("  %-14s mean %8.0f  p50 %8.0f  p95 %8.0f  max %8.0f" % (name, x.mean(), np.percentile(x, 50), np.percentile(x, 95), x.max()))
+f = full[:, 8:, :].astype(np.float64)
+f[f == 0] = np.nan
+print("regions %d, steps %d; cycles per colour step of thread 0 (over regions and steps)" % f.shape[:2])
+show("to run_cluster", f[:, :, 3] - f[:, :, 0])
+show("expect+w issue", f[:, :, 4] - f[:, :, 3])
+show("first poll", f[:, :, 2] - f[:, :, 4])
+show("poll rounds", f[:, :, 1])
+show("wait+gather", f[:, :, 8] - f[:, :, 0])
+for j in range(1, 6):
+    show("tet%d" % j, f[:, :, 8 + j] - f[:, :, 7 + j])
+last = np.nanmax(f[:, :, 8:14], axis=2)
+show("scatter", f[:, :, 15] - last)
+show("to loop end", f[:, :, 6] - f[:, :, 15])
+show("prefetch+sync", f[:, :, 7] - f[:, :, 6])
+show("whole step", f[:, :, 7] - f[:, :, 0])
