@@ -228,7 +228,8 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = sim.stats()["kernels_launched"]
+    st_before = sim.stats()
+    launches0 = st_before["kernels_launched"]
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     contacts = 0
     for a, b in ev:
@@ -237,7 +238,10 @@ def main():
         sim.step(scene.dt, S, K, scene.detect_every_substep)
         b.record(stream)
     barrier()
-    launches = sim.stats()["kernels_launched"] - launches0
+    st_after = sim.stats()
+    launches = st_after["kernels_launched"] - launches0
+    kernel_ms = st_after["kernel_ms"] - st_before["kernel_ms"]
+    kernel_launches = st_after["kernel_launches"] - st_before["kernel_launches"]
     ms = sum(a.elapsed_time(b) for a, b in ev)
     contacts = len(sim.contacts()[0])
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -295,7 +299,32 @@ def main():
         if args.precision == 64:
             bytes_step = bytes_step * 336 // 176
         ms_step = ms_max / args.steps
-        achieved = bytes_step / (ms_step * 1e-3) / 1e9
+        frame_gbs = bytes_step / (ms_step * 1e-3) / 1e9
+        sched = {1: "graph", 2: "persistent"}.get(stats0["schedule"], "?")
+        if kernel_launches > 0:
+            # dominant kernel = the substep kernel of the persistent schedule: one launch runs predict,
+            # K sweeps over every tet and contact, and commit for one substep.  Timed live with CUDA
+            # events around every launch of the timed region (sbsb200_stats.kernel_ms).
+            bytes_launch = K * (BYTES_PER_PROJECTION * scene.n_tets + BYTES_PER_COLLISION * contacts) \
+                + BYTES_PER_VERTEX_SUBSTEP * nVtot
+            if args.precision == 64:
+                bytes_launch = bytes_launch * 336 // 176
+            k_ms = kernel_ms / kernel_launches
+            achieved = bytes_launch / (k_ms * 1e-3) / 1e9
+            kernel = {"name": "k_substep_persistent", "launches_timed": int(kernel_launches),
+                      "avg_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": int(bytes_launch),
+                      "share_of_step": kernel_ms / ms}
+        else:
+            # graph schedule: ~800 k_project_green launches per frame inside one CUDA graph; CUDA events
+            # cannot bracket a node of a graph launch, so the frame as a whole is the timed unit
+            achieved, kernel = frame_gbs, {"name": "whole frame (CUDA graph of per-colour kernels)"}
+        traffic = None
+        try:   # dram__bytes_read + dram__bytes_write per launch of the same kernel on the same workload (ncu)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+            if tr["workload"] == scene.name and kernel["name"] in tr["kernel"]:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -304,19 +333,24 @@ def main():
             "config": {"workload": scene.name, "tets_per_gpu": scene.n_tets, "vertices_per_gpu": nVtot,
                        "substeps": S, "iterations": K, "dt": scene.dt,
                        "detection": "every substep" if scene.detect_every_substep else "once per frame",
-                       "colours": stats0["n_green_colours"],
-                       "schedule": {1: "graph", 2: "persistent"}.get(stats0["schedule"], "?"),
+                       "colours": stats0["n_green_colours"], "schedule": sched,
+                       "regions": stats0["n_regions"], "shared_vertices": stats0["n_interface_vertices"],
                        "parallelism": "scenes sharded over %d GPU(s), no collective" % world,
                        "l2": "256 MiB write between timed steps (flush)"},
             "ms_per_frame": ms_step,
             "contacts_last_detection": contacts,
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 (of fallback)",
-                         "algorithmic_bytes_per_step": int(bytes_step),
+                         "kernel": kernel,
+                         "frame": {"algorithmic_bytes_per_step": int(bytes_step), "achieved": frame_gbs,
+                                   "frac": frame_gbs / peak},
                          "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "note": "whole frame (all kernels of the step); see profiles/ for the per-kernel split"},
+                         "note": "algorithmic bytes (SURVEY 8d: 176 B per projection, 64 B per contact "
+                                 "projection, 112 B per vertex and substep) / CUDA-event time; the working set "
+                                 "fits the 126 MB L2, so DRAM traffic is far below the algorithmic bytes "
+                                 "(profiles/)"},
         }
         if e2e:
             line["e2e"] = e2e

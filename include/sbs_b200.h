@@ -67,6 +67,8 @@ typedef struct sbsb200_stats
     int64_t frames;             /* sbsb200_step calls since create */
     int64_t last_contact_count; /* contacts found by the most recent detection */
     double last_step_ms;        /* device time of the most recent sbsb200_step (CUDA events) */
+    double kernel_ms;           /* persistent schedule: summed device time of the substep-kernel launches */
+    int64_t kernel_launches;    /* ... and how many launches that sum covers (CUDA events around each) */
 } sbsb200_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------- */

@@ -36,7 +36,8 @@ class Stats(C.Structure):
                 ("n_distance", C.c_int64), ("n_surface_vertices", C.c_int64), ("n_green_colours", C.c_int32),
                 ("n_distance_colours", C.c_int32), ("schedule", C.c_int32), ("n_regions", C.c_int32),
                 ("n_interface_vertices", C.c_int64), ("kernels_launched", C.c_int64), ("frames", C.c_int64),
-                ("last_contact_count", C.c_int64), ("last_step_ms", C.c_double)]
+                ("last_contact_count", C.c_int64), ("last_step_ms", C.c_double), ("kernel_ms", C.c_double),
+                ("kernel_launches", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -79,6 +79,7 @@ struct EngineBase
                              int32_t* sdf_body, double* point, double* normal)             = 0;
     virtual void invalidate_graphs()                                                       = 0;
     virtual int64_t read_trace(sbsb200_ctx& c, int64_t* out, int64_t cap)                   = 0;
+    virtual void kernel_times(double& ms, int64_t& launches)                                = 0;
 };
 
 } // namespace
@@ -130,10 +131,41 @@ struct Engine final : EngineBase
     DevBuf<typename DeviceScene<R>::Sdf> sdf;
     DevBuf<double> stage_x, stage_v; // raw host-format staging for upload/download
     PersistentPlan<R> pp; // persistent schedule resources (may be inactive)
+    // CUDA-event pairs around the launches of the dominant kernel (persistent schedule: the substep
+    // kernel), folded into a running sum when the statistics are read
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
+    size_t kev_used        = 0;
+    double kernel_ms_sum   = 0;
+    int64_t kernel_ms_count = 0;
     std::map<std::tuple<double, int, int, int>, cudaGraphExec_t> graphs;
     std::map<std::tuple<double, int, int, int>, int64_t> graph_kernels;
 
-    ~Engine() override { invalidate_graphs(); }
+    ~Engine() override
+    {
+        invalidate_graphs();
+        for (auto& e : kev)
+        {
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+    }
+
+    void kernel_times(double& ms, int64_t& launches) override
+    {
+        for (size_t i = 0; i < kev_used; ++i)
+        {
+            float t = 0.f;
+            if (cudaEventSynchronize(kev[i].second) == cudaSuccess &&
+                cudaEventElapsedTime(&t, kev[i].first, kev[i].second) == cudaSuccess)
+            {
+                kernel_ms_sum += t;
+                ++kernel_ms_count;
+            }
+        }
+        kev_used = 0;
+        ms       = kernel_ms_sum;
+        launches = kernel_ms_count;
+    }
 
     void invalidate_graphs() override
     {
@@ -347,7 +379,20 @@ struct Engine final : EngineBase
                 detect_now();
             if (c.schedule == SBSB200_SCHED_PERSISTENT)
             {
+                constexpr size_t kMaxTimedLaunches = 4096;
+                bool const timed = kev_used < kMaxTimedLaunches;
+                if (timed && kev_used == kev.size())
+                {
+                    cudaEvent_t e0 = nullptr, e1 = nullptr;
+                    CK(cudaEventCreate(&e0));
+                    CK(cudaEventCreate(&e1));
+                    kev.emplace_back(e0, e1);
+                }
+                if (timed)
+                    CK(cudaEventRecord(kev[kev_used].first, st));
                 launched += pp.substep(d, dt, iterations, collide, st);
+                if (timed)
+                    CK(cudaEventRecord(kev[kev_used++].second, st));
             }
             else
             {
@@ -962,6 +1007,11 @@ int sbsb200_get_stats(const sbsb200_ctx* cc, sbsb200_stats* out)
     out->kernels_launched     = c->kernels;
     out->frames               = c->frames;
     out->last_contact_count   = c->last_contacts;
+    if (c->engine)
+    {
+        cudaSetDevice(c->device);
+        c->engine->kernel_times(out->kernel_ms, out->kernel_launches);
+    }
     if (c->timed)
     {
         cudaSetDevice(c->device);

@@ -1,0 +1,105 @@
+// The reference's demo set-up (main.cpp:17-130) written against the B200 facade headers: a
+// tetrahedralised bar, transformed, one green constraint per tet, a plane-SDF floor, brute-force
+// collision detection, timestep_t::step.  Writes x0, x, v of the bar (9 doubles per particle) to argv[7].
+//   facade_demo W H D frames substeps iterations out.bin [precision]
+#include <cstdio>
+#include <cstdlib>
+#include <iterator>
+
+#include <sbs/geometry/get_simple_bar_model.h>
+#include <sbs/physics/collision/brute_force_cd_system.h>
+#include <sbs/physics/environment_body.h>
+#include <sbs/physics/gauss_seidel_solver.h>
+#include <sbs/physics/simulation.h>
+#include <sbs/physics/tetrahedral_body.h>
+#include <sbs/physics/timestep.h>
+#include <sbs/physics/xpbd/contact_handler.h>
+#include <sbs/physics/xpbd/green_constraint.h>
+
+int main(int argc, char** argv)
+{
+    if (argc < 8)
+    {
+        std::fprintf(stderr, "usage: %s W H D frames substeps iterations out.bin [32|64]\n", argv[0]);
+        return 2;
+    }
+    std::size_t const W = std::atoi(argv[1]), H = std::atoi(argv[2]), D = std::atoi(argv[3]);
+    int const frames = std::atoi(argv[4]);
+    try
+    {
+        sbs::physics::simulation_t simulation{};
+        if (argc > 8)
+            simulation.precision = std::atoi(argv[8]);
+
+        sbs::common::geometry_t beam_geometry = sbs::geometry::get_simple_bar_model(W, H, D);
+        beam_geometry.set_color(255, 255, 0);
+        auto const beam_idx = static_cast<sbs::index_type>(simulation.bodies().size());
+        simulation.add_body();
+        simulation.bodies()[beam_idx] =
+            std::make_unique<sbs::physics::tetrahedral_body_t>(simulation, beam_idx, beam_geometry);
+        sbs::physics::tetrahedral_body_t& beam =
+            *dynamic_cast<sbs::physics::tetrahedral_body_t*>(simulation.bodies()[beam_idx].get());
+        sbs::affine3 beam_transform = sbs::affine3::translation(-1., 0.4, -1.);
+        beam_transform.rotate(0.3, sbs::vec3{0., 1., 0.2}.normalized());
+        beam_transform.scale(sbs::vec3{1.0, 0.8, 2.});
+        beam.transform(beam_transform);
+        for (auto const& tetrahedron : beam.physical_model().tetrahedra())
+        {
+            auto const alpha = simulation.simulation_parameters().compliance;
+            auto const beta  = simulation.simulation_parameters().damping;
+            auto const nu    = simulation.simulation_parameters().poisson_ratio;
+            auto const E     = simulation.simulation_parameters().young_modulus;
+            simulation.add_constraint(std::make_unique<sbs::physics::xpbd::green_constraint_t>(
+                alpha, beta, simulation, beam_idx, tetrahedron.v1(), tetrahedron.v2(), tetrahedron.v3(),
+                tetrahedron.v4(), E, nu));
+        }
+
+        sbs::common::geometry_t floor_geometry; // visual only
+        auto const floor_idx = static_cast<sbs::index_type>(simulation.bodies().size());
+        sbs::aligned_box3 const floor_volume{sbs::vec3{-200., -5., -200.}, sbs::vec3{200., 5., 200.}};
+        auto const floor_collision_model = sbs::physics::collision::sdf_model_t::from_plane(
+            sbs::hyperplane3(sbs::vec3{0., 1., 0.}, sbs::vec3{0., 0., 0.}), floor_volume);
+        simulation.add_body(std::make_unique<sbs::physics::environment_body_t>(simulation, floor_idx, floor_geometry,
+                                                                               floor_collision_model));
+
+        std::vector<sbs::physics::collision::collision_model_t*> collision_objects{};
+        std::transform(simulation.bodies().begin(), simulation.bodies().end(), std::back_inserter(collision_objects),
+                       [](std::unique_ptr<sbs::physics::body_t>& b) { return &(b->collision_model()); });
+        simulation.use_collision_detection_system(
+            std::make_unique<sbs::physics::collision::brute_force_cd_system_t>(collision_objects));
+        simulation.collision_detection_system()->use_contact_handler(
+            std::make_unique<sbs::physics::xpbd::contact_handler_t>(simulation));
+
+        sbs::physics::timestep_t timestep{};
+        timestep.dt()         = 0.016;
+        timestep.iterations() = std::atoi(argv[6]);
+        timestep.substeps()   = std::atoi(argv[5]);
+        timestep.solver()     = std::make_unique<sbs::physics::gauss_seidel_solver_t>();
+
+        for (int f = 0; f < frames; ++f)
+        {
+            timestep.step(simulation);
+            if (f == 0) // main.cpp:158-165: pin a picked vertex by setting its mass to 0 between frames
+                simulation.particles()[beam_idx][0].mass() = 0.;
+        }
+
+        auto const& ps = static_cast<sbs::physics::simulation_t const&>(simulation).particles()[beam_idx];
+        std::FILE* out = std::fopen(argv[7], "wb");
+        if (!out)
+            return 3;
+        for (auto const& p : ps)
+        {
+            double const row[9] = {p.x0().x(), p.x0().y(), p.x0().z(), p.x().x(), p.x().y(),
+                                   p.x().z(),  p.v().x(),  p.v().y(),  p.v().z()};
+            std::fwrite(row, sizeof(double), 9, out);
+        }
+        std::fclose(out);
+        std::printf("%zu particles, %zu constraints, %d frames\n", ps.size(), simulation.constraints().size(), frames);
+    }
+    catch (sbs::b200::error const& e)
+    {
+        std::fprintf(stderr, "sbs-b200 error %d: %s\n", e.code, e.what());
+        return 10;
+    }
+    return 0;
+}

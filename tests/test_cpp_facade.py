@@ -1,0 +1,71 @@
+"""The C++ facade (soft-body-simulator_b200/cpp/sbs): the reference's class names over the C ABI.
+tests/cpp/facade_demo.cpp is main.cpp:17-130 of the reference written against it."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BUILD = os.path.join(HERE, "_build")
+DEMO = os.path.join(BUILD, "facade_demo")
+LIBDIR = os.path.join(ROOT, "soft-body-simulator_b200", "lib")
+
+
+def build_demo():
+    src = os.path.join(HERE, "cpp", "facade_demo.cpp")
+    hdr = os.path.join(ROOT, "soft-body-simulator_b200", "cpp", "sbs", "b200", "facade.hpp")
+    if os.path.exists(DEMO) and all(os.path.getmtime(DEMO) >= os.path.getmtime(f) for f in (src, hdr)):
+        return DEMO
+    os.makedirs(BUILD, exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I",
+                           os.path.join(ROOT, "soft-body-simulator_b200", "cpp"), src, "-o", DEMO,
+                           "-L", LIBDIR, "-lsbsb200", "-Wl,-rpath," + LIBDIR])
+    return DEMO
+
+
+def test_facade_compiles_against_the_reference_include_paths_and_fails_loudly_without_a_gpu(sbs):
+    sbs.load_library()
+    demo = build_demo()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run itself is covered by the gpu test")
+    r = subprocess.run([demo, "4", "4", "12", "1", "1", "5", os.path.join(BUILD, "never.bin")],
+                       capture_output=True, text=True)
+    assert r.returncode == 10
+    assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+    assert not os.path.exists(os.path.join(BUILD, "never.bin"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [64, 32])
+def test_facade_demo_matches_the_c_abi_path_and_the_oracle(sbs, scenes, oracle, precision):
+    demo = build_demo()
+    out = os.path.join(BUILD, "facade_%d.bin" % precision)
+    W, H, D, frames, S, K = 4, 4, 12, 3, 2, 5
+    subprocess.check_call([demo, str(W), str(H), str(D), str(frames), str(S), str(K), out, str(precision)])
+    rows = np.fromfile(out, np.float64).reshape(-1, 9)
+    x0, xd, vd = rows[:, 0:3], rows[:, 3:6], rows[:, 6:9]
+    pos, tets = scenes.bar_model(W, H, D)
+    assert len(x0) == len(pos)
+    # the same scene through the ctypes binding and through the oracle (reference algorithm)
+    body = scenes.TetBody(x0=x0.copy(), tets=tets.astype(np.uint32), x=x0.copy())
+    floor = scenes.Sdf("plane", (0.0, 1.0, 0.0), (0.0, 0.0, 0.0), (-200.0, -5.0, -200.0, 200.0, 5.0, 200.0))
+    scene = scenes.Scene("facade_demo", [body, floor], substeps=S, iterations=K)
+    sim = sbs.Simulation(0, precision)
+    ids = scene.instantiate(sim)
+    ref = oracle.World()
+    scene.instantiate(ref)
+    ref.set_constraint_order(sim.constraint_order())
+    for f in range(frames):
+        for w, b in ((sim, ids[0]), (ref, 0)):
+            w.step(scene.dt, S, K, False)
+            if f == 0:
+                w.set_mass(b, 0, 0.0)
+    xs, vs = sim.download(ids[0])
+    assert np.array_equal(xs, xd) and np.array_equal(vs, vd)
+    xr, _ = ref.download(0)
+    tol = 1e-9 if precision == 64 else 1e-4
+    assert np.abs(xd - xr).max() <= tol * scene.bbox_diagonal()
+    assert np.abs(xd - x0).max() > 1e-3   # it moved
