@@ -585,6 +585,8 @@ struct Engine final : EngineBase
         R const iw = R(m > 0. ? 1. / m : 0.);
         CK(cudaMemcpyAsync(&pos.p[gv].w, &iw, sizeof(R), cudaMemcpyHostToDevice, c.stream));
         CK(cudaStreamSynchronize(c.stream));
+        if (c.schedule == SBSB200_SCHED_PERSISTENT)
+            pp.set_inverse_mass(static_cast<uint32_t>(gv), iw, c.stream);
     }
 
     int64_t contacts(sbsb200_ctx& c, int64_t cap, int32_t* body, uint32_t* vertex, int32_t* sdf_body,

@@ -177,6 +177,7 @@ struct PersistentArgs
     uint2 const* tet_slots;        // per tet (storage order): 4 x u16 slots into the shared vertex array
     uint4 const* cl_fetch;         // [nvc/4][n_clusters] global vertex ids of the scratch entries
     uint4 const* cl_meta;          // [nvc/4][n_clusters] touch schedule of those entries (see ClusterPlan)
+    Real4<R> const* cl_w;          // [nvc/4][n_clusters] inverse masses of those entries (patched by set_mass)
     DevChunk const* chunks;        // [(colour * n_regions + region) * 2 + part]
     int32_t const* vtx_off;        // [n_regions + 1] resident vertex list
     uint32_t const* vtx;           // global vertex id of resident slot i
@@ -316,36 +317,34 @@ __device__ __forceinline__ uint32_t expected_tag(StepInfo const& si, uint32_t me
 // Fetch of one cluster: every entry of its fetch list waits for the tag of its previous touch and
 // lands in the thread's scratch slots; all polls of a round are in flight together.
 template <typename R, int NVC4, typename Stamp>
-__device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64_t q, Real4<R>* sx,
+__device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, uint4 const (&fetch)[NVC4],
+                                               uint4 const (&fmeta)[NVC4], Real4<R> const (&fw)[NVC4], Real4<R>* sx,
                                                StepInfo const& si, Stamp&& stamp)
 {
-    DeviceScene<R> const& s = a.s;
     int const tid = threadIdx.x, nt = blockDim.x;
     uint32_t id[4 * NVC4], meta[4 * NVC4];
+    R w[4 * NVC4];
     uint32_t pending = 0;
 #pragma unroll
     for (int k = 0; k < NVC4; ++k)
     {
-        uint4 const f   = __ldg(&a.cl_fetch[static_cast<int64_t>(k) * a.n_clusters + q]);
-        uint4 const m   = __ldg(&a.cl_meta[static_cast<int64_t>(k) * a.n_clusters + q]);
-        id[4 * k + 0]   = f.x;
-        id[4 * k + 1]   = f.y;
-        id[4 * k + 2]   = f.z;
-        id[4 * k + 3]   = f.w;
-        meta[4 * k + 0] = m.x;
-        meta[4 * k + 1] = m.y;
-        meta[4 * k + 2] = m.z;
-        meta[4 * k + 3] = m.w;
+        id[4 * k + 0]   = fetch[k].x;
+        id[4 * k + 1]   = fetch[k].y;
+        id[4 * k + 2]   = fetch[k].z;
+        id[4 * k + 3]   = fetch[k].w;
+        meta[4 * k + 0] = fmeta[k].x;
+        meta[4 * k + 1] = fmeta[k].y;
+        meta[4 * k + 2] = fmeta[k].z;
+        meta[4 * k + 3] = fmeta[k].w;
+        w[4 * k + 0]    = fw[k].x;
+        w[4 * k + 1]    = fw[k].y;
+        w[4 * k + 2]    = fw[k].z;
+        w[4 * k + 3]    = fw[k].w;
     }
-    // inverse masses first (constant during the launch, nothing to wait for): they go straight into
-    // the .w of the scratch slots, the polled positions follow
 #pragma unroll
     for (int j = 0; j < 4 * NVC4; ++j)
         if (id[j] != kNoVertex)
-        {
-            sx[j * nt + tid].w = s.pos[id[j]].w;
             pending |= 1u << j;
-        }
     int polls = 0;
     stamp(4);
     while (pending)
@@ -367,10 +366,7 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64
                     R x, y, z;
                     if (Xchg<R>::decode(raw[e], expected_tag(si, meta[h + e]), x, y, z))
                     {
-                        Real4<R>* slot = &sx[(h + e) * nt + tid];
-                        slot->x        = x;
-                        slot->y        = y;
-                        slot->z        = z;
+                        sx[(h + e) * nt + tid] = Real4<R>{x, y, z, w[h + e]};
                         pending &= ~(1u << (h + e));
                     }
                 }
@@ -384,20 +380,14 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64
 }
 
 // One cluster, fetched already: project its tets in order out of shared memory -> write back.
-// q = storage index of the cluster when it has a fetch list (part A), -1 otherwise.
+// fetch = the cluster's fetch list (all kNoVertex for part B): what has to be written back.
 template <typename R, int NVC4, typename Stamp>
-__device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk const& ch, int32_t i, int64_t q,
-                                            ClusterHead<R> const& head, Real4<R>* sx, int first_iteration,
-                                            uint32_t tag, Stamp&& stamp)
+__device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk const& ch, int32_t i,
+                                            uint4 const (&fetch)[NVC4], ClusterHead<R> const& head, Real4<R>* sx,
+                                            int first_iteration, uint32_t tag, Stamp&& stamp)
 {
     DeviceScene<R> const& s = a.s;
     int const tid = threadIdx.x, nt = blockDim.x;
-    // the fetch list again, for the write-back: in flight while the tets run
-    uint4 fetch[NVC4];
-#pragma unroll
-    for (int k = 0; k < NVC4; ++k)
-        fetch[k] = q >= 0 ? __ldg(&a.cl_fetch[static_cast<int64_t>(k) * a.n_clusters + q])
-                          : make_uint4(kNoVertex, kNoVertex, kNoVertex, kNoVertex);
     // column layout: tet m of cluster i sits at first + n[0] + .. + n[m-1] + i
     int32_t n0 = ch.n[0], n1 = ch.n[1], n2 = ch.n[2], n3 = ch.n[3], n4 = ch.n[4], n5 = ch.n[5], n6 = ch.n[6],
             n7 = ch.n[7];
@@ -514,7 +504,11 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
     // next (head loaded, vertices fetched) — before the barrier when that cluster belongs to the
     // next phase: the scratch slots are free once the thread's own cluster is written back, and
     // the records it waits for come from clusters of phases that do not wait for this thread.
-    ClusterHead<R> head;
+    ClusterHead<R> head;       // the prepared cluster of this thread ...
+    uint4 cur_fetch[NVC4];     // ... and its fetch list (what it has to write back)
+#pragma unroll
+    for (int j = 0; j < NVC4; ++j)
+        cur_fetch[j] = make_uint4(kNoVertex, kNoVertex, kNoVertex, kNoVertex);
     int32_t item_i = -1; // cluster index within its phase (part A first), -1: nothing prepared
     int32_t round  = 0;
     for (int32_t p = 0; p < n_phases;)
@@ -522,7 +516,59 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
         uint32_t const tag = a.base + static_cast<uint32_t>(p);
         int32_t const k    = p == 0 ? 0 : (p - 1) / per_iteration;
         int32_t const q    = p == 0 ? 0 : (p - 1) % per_iteration;
-        bool advance       = true;
+        bool const colour  = p > 0 && p < n_phases - 1 && !(cs && q == 0);
+        int32_t const c    = q - cs;
+
+        // ---- (1) what this thread runs after this pass: its loads (static data) go out first, so
+        //          that they are in flight while the work of this pass runs
+        bool advance = true;
+        if (colour)
+            advance = (round + 1) * nt >= s_chunks[2 * c].n[0] + s_chunks[2 * c + 1].n[0];
+        int32_t const np      = advance ? p + 1 : p;
+        int32_t const ni_next = advance ? tid : (round + 1) * nt + tid;
+        bool has_next = false, next_in_a = false;
+        int32_t nk = 0;
+        ClusterHead<R> nhead;
+        uint4 nfetch[NVC4], nmeta[NVC4];
+        Real4<R> nw[NVC4];
+#pragma unroll
+        for (int j = 0; j < NVC4; ++j)
+        {
+            nfetch[j] = make_uint4(kNoVertex, kNoVertex, kNoVertex, kNoVertex);
+            nmeta[j]  = make_uint4(0u, 0u, 0u, 0u);
+            nw[j]     = Real4<R>{R(0), R(0), R(0), R(0)};
+        }
+        if (np > 0 && np < n_phases - 1)
+        {
+            nk               = (np - 1) / per_iteration;
+            int32_t const nq = (np - 1) % per_iteration;
+            if (!(cs && nq == 0))
+            {
+                int32_t const nc = nq - cs;
+                int32_t const nA = s_chunks[2 * nc].n[0], nB = s_chunks[2 * nc + 1].n[0];
+                if (ni_next < nA + nB)
+                {
+                    has_next           = true;
+                    next_in_a          = ni_next < nA;
+                    DevChunk const& ch = s_chunks[2 * nc + (next_in_a ? 0 : 1)];
+                    int32_t const ci   = next_in_a ? ni_next : ni_next - nA;
+                    load_cluster_head<R>(nhead, a, ch, ci, nk == 0);
+                    if (next_in_a)
+                    {
+                        int64_t const cq = static_cast<int64_t>(ch.cfirst) + ci;
+#pragma unroll
+                        for (int j = 0; j < NVC4; ++j)
+                        {
+                            nfetch[j] = __ldg(&a.cl_fetch[static_cast<int64_t>(j) * a.n_clusters + cq]);
+                            nmeta[j]  = __ldg(&a.cl_meta[static_cast<int64_t>(j) * a.n_clusters + cq]);
+                            nw[j]     = ld4_ro(&a.cl_w[static_cast<int64_t>(j) * a.n_clusters + cq]);
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- (2) the work of this pass
         if (p == 0)
         { // ---- predict (timestep.cpp:35-43)
             for (int32_t i = tid; i < nv; i += nt)
@@ -619,68 +665,46 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
         }
         else
         { // ---- colour q - cs of iteration k (gauss_seidel_solver.cpp:32-35)
-            int32_t const c  = q - cs;
-            int32_t const nA = s_chunks[2 * c].n[0], nB = s_chunks[2 * c + 1].n[0];
+            int32_t const nA = s_chunks[2 * c].n[0];
             if (round == 0)
                 stamp(0);
             if (item_i >= 0)
             { // cluster item_i of the phase runs on thread item_i % nt; part A (clusters that fetch) first
                 bool const in_a    = item_i < nA;
                 DevChunk const& ch = s_chunks[2 * c + (in_a ? 0 : 1)];
-                int32_t const ci   = in_a ? item_i : item_i - nA;
-                run_cluster<R, NVC4>(a, ch, ci, in_a ? static_cast<int64_t>(ch.cfirst) + ci : int64_t{-1}, head, sx,
-                                     k == 0, tag, stamp);
+                run_cluster<R, NVC4>(a, ch, in_a ? item_i : item_i - nA, cur_fetch, head, sx, k == 0, tag, stamp);
             }
-            advance = (round + 1) * nt >= nA + nB;
             stamp(6);
         }
 
-        // ---- the one place where the next cluster of this thread is prepared
-        int32_t np = p, ni_next = -1;
-        if (!advance)
+        // ---- (3) the next cluster becomes the prepared one: its shared vertices are fetched now,
+        //          before the barrier when it belongs to the next phase
+        item_i = has_next ? ni_next : -1;
+        if (has_next)
         {
-            ++round;
-            ni_next = round * nt + tid;
-        }
-        else
-        {
-            round = 0;
-            np    = p + 1;
-            ni_next = tid;
-        }
-        item_i = -1;
-        if (np > 0 && np < n_phases - 1)
-        {
-            int32_t const nk = (np - 1) / per_iteration, nq = (np - 1) % per_iteration;
-            if (!(cs && nq == 0))
-            {
-                int32_t const c  = nq - cs;
-                int32_t const nA = s_chunks[2 * c].n[0], nB = s_chunks[2 * c + 1].n[0];
-                if (ni_next < nA + nB)
-                {
-                    item_i             = ni_next;
-                    bool const in_a    = item_i < nA;
-                    DevChunk const& ch = s_chunks[2 * c + (in_a ? 0 : 1)];
-                    int32_t const ci   = in_a ? item_i : item_i - nA;
-                    load_cluster_head<R>(head, a, ch, ci, nk == 0);
-                    if (in_a)
-                        gather_cluster<R, NVC4>(a, static_cast<int64_t>(ch.cfirst) + ci, sx,
-                                                StepInfo{a.base + static_cast<uint32_t>(np), a.base,
-                                                         static_cast<uint32_t>(8 * (2 * (nk > 0 ? 1 : 0) + cs))},
-                                                stamp);
-                }
-            }
+            head = nhead;
+#pragma unroll
+            for (int j = 0; j < NVC4; ++j)
+                cur_fetch[j] = nfetch[j];
+            if (next_in_a)
+                gather_cluster<R, NVC4>(a, nfetch, nmeta, nw, sx,
+                                        StepInfo{a.base + static_cast<uint32_t>(np), a.base,
+                                                 static_cast<uint32_t>(8 * (2 * (nk > 0 ? 1 : 0) + cs))},
+                                        stamp);
         }
         if (advance)
         {
             __syncthreads();
-            if (p > 0 && p < n_phases - 1 && !(cs && q == 0))
+            if (colour)
             {
                 stamp(7);
                 ++traced;
             }
-            p = np;
+            round = 0;
+            p     = np;
         }
+        else
+            ++round;
     }
     __syncthreads(); // shared memory is reused by the next region of this CTA
 }
@@ -734,6 +758,8 @@ struct PersistentPlan
     PBuf<uint32_t> vtx, ifv, ifv_meta, surf_index, surf_addr, surf_meta, error;
     PBuf<uint2> tet_slots;
     PBuf<uint4> cl_fetch, cl_meta, xchg;
+    PBuf<Real4<R>> cl_w;
+    std::vector<uint4> h_fetch; // host copy of cl_fetch, to patch cl_w when a mass changes
     PBuf<long long> trace;
     int64_t trace_len = 0;
     int grid = 0, block = 0;
@@ -823,6 +849,16 @@ struct PersistentPlan
                 fetch[at]       = make_uint4(f(0), f(1), f(2), f(3));
                 meta[at]        = make_uint4(m(0), m(1), m(2), m(3));
             }
+        auto const inv_mass = [&](uint32_t v) -> R {
+            if (v == kNoVertex)
+                return R(0);
+            double const m = h.mass[v];
+            return R(m > 0. ? 1. / m : 0.); // particle.cpp:39-44
+        };
+        std::vector<Real4<R>> fw(fetch.size());
+        for (size_t i = 0; i < fetch.size(); ++i)
+            fw[i] = Real4<R>{inv_mass(fetch[i].x), inv_mass(fetch[i].y), inv_mass(fetch[i].z), inv_mass(fetch[i].w)};
+        h_fetch = fetch;
         std::vector<DevChunk> hchunks(cp.chunks.size());
         for (size_t i = 0; i < cp.chunks.size(); ++i)
         {
@@ -934,6 +970,7 @@ struct PersistentPlan
         tet_slots.upload(slots, st);
         cl_fetch.upload(fetch, st);
         cl_meta.upload(meta, st);
+        cl_w.upload(fw, st);
         chunks.upload(hchunks, st);
         vtx_off.upload(voff, st);
         vtx.upload(plan.region_vtx, st);
@@ -960,6 +997,7 @@ struct PersistentPlan
         args.tet_slots        = tet_slots.p;
         args.cl_fetch         = cl_fetch.p;
         args.cl_meta          = cl_meta.p;
+        args.cl_w             = cl_w.p;
         args.chunks           = chunks.p;
         args.vtx_off          = vtx_off.p;
         args.vtx              = vtx.p;
@@ -997,6 +1035,21 @@ struct PersistentPlan
             throw std::runtime_error(std::string("cudaLaunchCooperativeKernel: ") + cudaGetErrorString(e));
         base += steps_per_substep(iterations, collide);
         return 1;
+    }
+
+    // particle_t::mass() of a vertex changed: patch its inverse mass in every fetch list naming it
+    void set_inverse_mass(uint32_t gv, R w, cudaStream_t st)
+    {
+        if (!ready)
+            return;
+        for (size_t i = 0; i < h_fetch.size(); ++i)
+        {
+            uint32_t const id[4] = {h_fetch[i].x, h_fetch[i].y, h_fetch[i].z, h_fetch[i].w};
+            for (int e = 0; e < 4; ++e)
+                if (id[e] == gv)
+                    cudaMemcpyAsync(reinterpret_cast<R*>(cl_w.p + i) + e, &w, sizeof(R), cudaMemcpyHostToDevice, st);
+        }
+        cudaStreamSynchronize(st);
     }
 
     // true when a launch ran out of its poll budget (call after synchronising the stream)

@@ -25,15 +25,13 @@ def show(name, x):
 f = full[:, 8:, :].astype(np.float64)
 f[f == 0] = np.nan
 print("regions %d, steps %d; cycles per colour step of thread 0 (over regions and steps)" % f.shape[:2])
-show("to run_cluster", f[:, :, 3] - f[:, :, 0])
-show("expect+w issue", f[:, :, 4] - f[:, :, 3])
-show("first poll", f[:, :, 2] - f[:, :, 4])
-show("poll rounds", f[:, :, 1])
-show("wait+gather", f[:, :, 8] - f[:, :, 0])
+show("start->tets", f[:, :, 8] - f[:, :, 0])
 for j in range(1, 6):
     show("tet%d" % j, f[:, :, 8 + j] - f[:, :, 7 + j])
 last = np.nanmax(f[:, :, 8:14], axis=2)
-show("scatter", f[:, :, 15] - last)
-show("to loop end", f[:, :, 6] - f[:, :, 15])
-show("prefetch+sync", f[:, :, 7] - f[:, :, 6])
+show("write back", f[:, :, 15] - last)
+show("->gather next", f[:, :, 4] - f[:, :, 15])
+show("first poll", f[:, :, 2] - f[:, :, 4])
+show("poll rounds", f[:, :, 1])
+show("polls+barrier", f[:, :, 7] - f[:, :, 2])
 show("whole step", f[:, :, 7] - f[:, :, 0])
