@@ -15,14 +15,20 @@
 // step ahead.
 //
 // The Gauss-Seidel order is unchanged — colour major over the whole mesh.  There is no barrier
-// between regions at all: synchronisation is per VERTEX and data-driven.  An exchange record is
-// one 16-byte word {x, y, z, tag} (fp32; three {value, tag} words in the fp64 build) that is read
-// and written with single 128-bit accesses, so a reader sees position and tag together.  The tag
-// is the step number of the last touch.  Which steps touch a vertex is static (the colours of the
-// clusters that contain it, the collision steps if it is a surface vertex, predict), so every
-// reader knows the tag it has to wait for: every touch is a read-modify-write that waits for the
+// between regions at all: synchronisation is per VERTEX and data-driven, through MAILBOXES.
+// Every fetch-list entry (cluster, scratch slot) owns a mailbox; so does every non-resident
+// vertex on behalf of its owner region (predict, collision constraints, commit).  A mailbox is one
+// 16-byte word {x, y, z, tag} (fp32; three {value, tag} words in the fp64 build) read and written
+// with single 128-bit accesses, so a reader sees position and tag together.  Which steps touch a
+// vertex is static (the colours of the clusters that contain it, the collision steps if it is a
+// surface vertex, predict, commit), so (a) whoever touches a vertex knows whose turn is next and
+// PUSHES the new position into that mailbox, tagged with the current step, and (b) every reader
+// knows the tag it has to wait for.  Every touch is a read-modify-write that waits for the
 // previous touch, which orders read-after-write and write-after-read hazards alike without a
-// fence (the record carries its own flag).
+// fence (the record carries its own flag).  Mailboxes of the clusters of a step are laid out
+// [slot][cluster]: the 32 lanes of a warp poll 32 adjacent records (4 cache lines per load
+// instead of 32 — the scattered variant was bound by L1 wavefronts), and the pushes, which are
+// fire-and-forget, carry the scatter.  A mailbox may just as well sit in another GPU's memory.
 //
 //   step 0                      : predict   (timestep.cpp:35-43)
 //   step 1 + k(1+C) + 0         : collision constraints of iteration k (gauss_seidel_solver.cpp:28-31)
@@ -37,6 +43,7 @@
 #include "scene_build.h"
 #include "xpbd_kernels.cuh"
 
+#include <algorithm>
 #include <cooperative_groups.h>
 #include <cstdlib>
 #include <stdexcept>
@@ -48,6 +55,9 @@ namespace sbsb200 {
 constexpr uint32_t kGlobalBit = 0x80000000u; // surface vertex address: global index when set, smem slot otherwise
 constexpr uint32_t kNoVertex  = 0xffffffffu; // empty fetch-list entry
 constexpr uint32_t kNoColour  = 0xffu;
+constexpr uint32_t kNoBox     = 0xffffffffu; // "no such mailbox"
+constexpr uint32_t kNoEntry   = 0xffffffffu; // cl_meta of an unused scratch slot
+constexpr uint32_t kSurfaceBit = 0x80000000u; // cl_to_owner: the vertex is a surface vertex
 constexpr int kPollBudget     = 1 << 20;     // polls of one record before the kernel gives up
 
 // true when the wait should be abandoned: budget exhausted (sets the error flag) or another thread
@@ -175,20 +185,28 @@ struct PersistentArgs
     int32_t const* region_order;   // CTA b runs region_order[b], [b + grid], ...; regions that share
                                    // vertices come first, one per CTA
     uint2 const* tet_slots;        // per tet (storage order): 4 x u16 slots into the shared vertex array
-    uint4 const* cl_fetch;         // [nvc/4][n_clusters] global vertex ids of the scratch entries
-    uint4 const* cl_meta;          // [nvc/4][n_clusters] touch schedule of those entries (see ClusterPlan)
-    Real4<R> const* cl_w;          // [nvc/4][n_clusters] inverse masses of those entries (patched by set_mass)
+    // per fetch-list entry, [nvc/4][n_clusters] each (entry j of cluster q: component j%4 of [j/4][q]);
+    // the mailbox of that entry is box[j * n_clusters + q]
+    uint4 const* cl_meta;          // touch schedule (ClusterPlan::cl_meta), 0xffffffff = no entry
+    Real4<R> const* cl_w;          // inverse mass (patched by set_mass)
+    uint4 const* cl_to;            // where the vertex goes next: the mailbox of the next entry touching it in
+                                   // the sweep, or of the first one (next sweep) when this is the last
+    uint4 const* cl_to_owner;      // the same, but the owner mailbox instead of "the first one": used when
+                                   // the owner is next (commit; collision step if kSurfaceBit is set).
+                                   // kNoBox = unused scratch slot
     DevChunk const* chunks;        // [(colour * n_regions + region) * 2 + part]
     int32_t const* vtx_off;        // [n_regions + 1] resident vertex list
     uint32_t const* vtx;           // global vertex id of resident slot i
     int32_t const* ifv_off;        // [n_regions + 1] owned non-resident vertices
     uint32_t const* ifv;
     uint32_t const* ifv_meta;      // their touch schedule (ClusterPlan::vertex_meta)
+    uint32_t const* ifv_first;     // mailbox of the first entry touching them in a sweep (kNoBox: none);
+                                   // the owner mailbox of owned vertex i is box[n_entries + i]
     int32_t const* surf_off;       // [n_regions + 1] owned surface vertices
     uint32_t const* surf_index;    // surface vertex index (into s.surf_pos / s.surf_first)
-    uint32_t const* surf_addr;     // its vertex address (shared slot, or global | kGlobalBit)
-    uint32_t const* surf_meta;     // touch schedule (used for the non-resident ones)
-    void* xchg;                    // exchange records of every vertex (only non-resident ones are used)
+    uint32_t const* surf_addr;     // shared-memory slot, or (index into ifv) | kGlobalBit when not resident
+    void* box;                     // mailboxes: n_entries of the fetch lists, then one per owned vertex
+    uint32_t n_entries;            // nvc * n_clusters
     uint32_t* error;               // set to 1 when a poll budget ran out
     uint32_t base;                 // tag of step 0 of this launch
     long long* trace;              // development aid: per-step clock stamps of thread 0 (nullptr = off)
@@ -198,12 +216,12 @@ struct PersistentArgs
     R dt;
 };
 
-// Wait for `expect` on the record of vertex gv and return its position.
+// Wait for `expect` on mailbox `b` and return the position in it.
 template <typename R>
-__device__ __forceinline__ void xchg_wait(PersistentArgs<R> const& a, uint32_t gv, uint32_t expect, R& x, R& y, R& z)
+__device__ __forceinline__ void xchg_wait(PersistentArgs<R> const& a, uint32_t b, uint32_t expect, R& x, R& y, R& z)
 {
     int polls = 0;
-    while (!Xchg<R>::load(a.xchg, gv, expect, x, y, z))
+    while (!Xchg<R>::load(a.box, b, expect, x, y, z))
     {
         if (poll_expired(a.error, ++polls))
             break;
@@ -305,6 +323,8 @@ struct StepInfo
     uint32_t step;  // tag of this step
     uint32_t base;  // tag of the predict step
     uint32_t shift; // which byte of a fetch entry's schedule word applies: 8 * (2 * (k > 0) + cs)
+    bool to_owner;  // after the last entry of a sweep the owner is next (collision step or commit) ...
+    bool surface_to_owner; // ... for surface vertices only (a collision step follows, not the commit)
 };
 
 // tag of the previous touch of a fetched vertex (ClusterPlan::cl_meta)
@@ -317,21 +337,17 @@ __device__ __forceinline__ uint32_t expected_tag(StepInfo const& si, uint32_t me
 // Fetch of one cluster: every entry of its fetch list waits for the tag of its previous touch and
 // lands in the thread's scratch slots; all polls of a round are in flight together.
 template <typename R, int NVC4, typename Stamp>
-__device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, uint4 const (&fetch)[NVC4],
-                                               uint4 const (&fmeta)[NVC4], Real4<R> const (&fw)[NVC4], Real4<R>* sx,
-                                               StepInfo const& si, Stamp&& stamp)
+__device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64_t q, uint4 const (&fmeta)[NVC4],
+                                               Real4<R> const (&fw)[NVC4], Real4<R>* sx, StepInfo const& si,
+                                               Stamp&& stamp)
 {
     int const tid = threadIdx.x, nt = blockDim.x;
-    uint32_t id[4 * NVC4], meta[4 * NVC4];
+    uint32_t meta[4 * NVC4];
     R w[4 * NVC4];
     uint32_t pending = 0;
 #pragma unroll
     for (int k = 0; k < NVC4; ++k)
     {
-        id[4 * k + 0]   = fetch[k].x;
-        id[4 * k + 1]   = fetch[k].y;
-        id[4 * k + 2]   = fetch[k].z;
-        id[4 * k + 3]   = fetch[k].w;
         meta[4 * k + 0] = fmeta[k].x;
         meta[4 * k + 1] = fmeta[k].y;
         meta[4 * k + 2] = fmeta[k].z;
@@ -343,8 +359,9 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, uint4
     }
 #pragma unroll
     for (int j = 0; j < 4 * NVC4; ++j)
-        if (id[j] != kNoVertex)
+        if (meta[j] != kNoEntry)
             pending |= 1u << j;
+    uint32_t const mine = static_cast<uint32_t>(q); // mailbox of entry j: j * n_clusters + q
     int polls = 0;
     stamp(4);
     while (pending)
@@ -358,7 +375,7 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, uint4
 #pragma unroll
             for (int e = 0; e < kBatch; ++e)
                 if (pending >> (h + e) & 1u)
-                    raw[e] = Xchg<R>::fetch(a.xchg, id[h + e]);
+                    raw[e] = Xchg<R>::fetch(a.box, static_cast<uint32_t>(h + e) * static_cast<uint32_t>(a.n_clusters) + mine);
 #pragma unroll
             for (int e = 0; e < kBatch; ++e)
                 if (pending >> (h + e) & 1u)
@@ -380,14 +397,23 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, uint4
 }
 
 // One cluster, fetched already: project its tets in order out of shared memory -> write back.
-// fetch = the cluster's fetch list (all kNoVertex for part B): what has to be written back.
+// q = storage index of the cluster when it has a fetch list (part A), -1 otherwise.
 template <typename R, int NVC4, typename Stamp>
-__device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk const& ch, int32_t i,
-                                            uint4 const (&fetch)[NVC4], ClusterHead<R> const& head, Real4<R>* sx,
-                                            int first_iteration, uint32_t tag, Stamp&& stamp)
+__device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk const& ch, int32_t i, int64_t q,
+                                            ClusterHead<R> const& head, Real4<R>* sx, int first_iteration,
+                                            StepInfo const& si, Stamp&& stamp)
 {
     DeviceScene<R> const& s = a.s;
     int const tid = threadIdx.x, nt = blockDim.x;
+    // where the fetched vertices go afterwards (static routing data): in flight while the tets run
+    uint4 to[NVC4], to_owner[NVC4];
+#pragma unroll
+    for (int k = 0; k < NVC4; ++k)
+    {
+        int64_t const at = static_cast<int64_t>(k) * a.n_clusters + (q >= 0 ? q : 0);
+        to[k]            = q >= 0 ? __ldg(&a.cl_to[at]) : make_uint4(kNoBox, kNoBox, kNoBox, kNoBox);
+        to_owner[k]      = q >= 0 ? __ldg(&a.cl_to_owner[at]) : make_uint4(kNoBox, kNoBox, kNoBox, kNoBox);
+    }
     // column layout: tet m of cluster i sits at first + n[0] + .. + n[m-1] + i
     int32_t n0 = ch.n[0], n1 = ch.n[1], n2 = ch.n[2], n3 = ch.n[3], n4 = ch.n[4], n5 = ch.n[5], n6 = ch.n[6],
             n7 = ch.n[7];
@@ -425,20 +451,24 @@ __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk
         n0  = n1; n1 = n2; n2 = n3; n3 = n4; n4 = n5; n5 = n6; n6 = n7; n7 = 0;
         cur = nxt;
     }
-    // write back, always: the tag is what the next touch of each vertex waits for
+    // push every fetched vertex to whoever touches it next, always: the tag is what that touch waits for
 #pragma unroll
     for (int h = 0; h < NVC4; ++h)
     {
-        uint32_t const id[4] = {fetch[h].x, fetch[h].y, fetch[h].z, fetch[h].w};
+        uint32_t const ta[4] = {to[h].x, to[h].y, to[h].z, to[h].w};
+        uint32_t const tb[4] = {to_owner[h].x, to_owner[h].y, to_owner[h].z, to_owner[h].w};
         Real4<R> p[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-            if (id[e] != kNoVertex)
+            if (tb[e] != kNoBox)
                 p[e] = sx[(4 * h + e) * nt + tid];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-            if (id[e] != kNoVertex)
-                Xchg<R>::store(a.xchg, id[e], p[e].x, p[e].y, p[e].z, tag);
+            if (tb[e] != kNoBox)
+            {
+                bool const owner_next = si.to_owner || (si.surface_to_owner && (tb[e] & kSurfaceBit));
+                Xchg<R>::store(a.box, owner_next ? (tb[e] & ~kSurfaceBit) : ta[e], p[e].x, p[e].y, p[e].z, si.step);
+            }
     }
     stamp(15);
 }
@@ -504,11 +534,8 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
     // next (head loaded, vertices fetched) — before the barrier when that cluster belongs to the
     // next phase: the scratch slots are free once the thread's own cluster is written back, and
     // the records it waits for come from clusters of phases that do not wait for this thread.
-    ClusterHead<R> head;       // the prepared cluster of this thread ...
-    uint4 cur_fetch[NVC4];     // ... and its fetch list (what it has to write back)
-#pragma unroll
-    for (int j = 0; j < NVC4; ++j)
-        cur_fetch[j] = make_uint4(kNoVertex, kNoVertex, kNoVertex, kNoVertex);
+    ClusterHead<R> head;  // the prepared cluster of this thread ...
+    int64_t cur_q = -1;   // ... and its storage index when it has a fetch list (part A), else -1
     int32_t item_i = -1; // cluster index within its phase (part A first), -1: nothing prepared
     int32_t round  = 0;
     for (int32_t p = 0; p < n_phases;)
@@ -529,14 +556,14 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
         bool has_next = false, next_in_a = false;
         int32_t nk = 0;
         ClusterHead<R> nhead;
-        uint4 nfetch[NVC4], nmeta[NVC4];
+        uint4 nmeta[NVC4];
         Real4<R> nw[NVC4];
+        int64_t next_q = -1;
 #pragma unroll
         for (int j = 0; j < NVC4; ++j)
         {
-            nfetch[j] = make_uint4(kNoVertex, kNoVertex, kNoVertex, kNoVertex);
-            nmeta[j]  = make_uint4(0u, 0u, 0u, 0u);
-            nw[j]     = Real4<R>{R(0), R(0), R(0), R(0)};
+            nmeta[j] = make_uint4(kNoEntry, kNoEntry, kNoEntry, kNoEntry);
+            nw[j]    = Real4<R>{R(0), R(0), R(0), R(0)};
         }
         if (np > 0 && np < n_phases - 1)
         {
@@ -555,13 +582,12 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                     load_cluster_head<R>(nhead, a, ch, ci, nk == 0);
                     if (next_in_a)
                     {
-                        int64_t const cq = static_cast<int64_t>(ch.cfirst) + ci;
+                        next_q = static_cast<int64_t>(ch.cfirst) + ci;
 #pragma unroll
                         for (int j = 0; j < NVC4; ++j)
                         {
-                            nfetch[j] = __ldg(&a.cl_fetch[static_cast<int64_t>(j) * a.n_clusters + cq]);
-                            nmeta[j]  = __ldg(&a.cl_meta[static_cast<int64_t>(j) * a.n_clusters + cq]);
-                            nw[j]     = ld4_ro(&a.cl_w[static_cast<int64_t>(j) * a.n_clusters + cq]);
+                            nmeta[j] = __ldg(&a.cl_meta[static_cast<int64_t>(j) * a.n_clusters + next_q]);
+                            nw[j]    = ld4_ro(&a.cl_w[static_cast<int64_t>(j) * a.n_clusters + next_q]);
                         }
                     }
                 }
@@ -587,7 +613,11 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                 Real4<R> const x  = ld4(&s.prev[gv]);
                 Real4<R> v        = ld4(&s.vel[gv]);
                 predict_vertex(pp, x, v, dt);
-                Xchg<R>::store(a.xchg, gv, pp.x, pp.y, pp.z, tag);
+                // next touch: the owner's collision step (surface vertex), else the first cluster of the
+                // sweep that contains the vertex, else (no sweep touches it) the owner's commit
+                uint32_t const first = a.ifv_first[i0 + i];
+                bool const to_me     = K == 0 || first == kNoBox || (cs && (a.ifv_meta[i0 + i] & 0x100u));
+                Xchg<R>::store(a.box, to_me ? a.n_entries + static_cast<uint32_t>(i0 + i) : first, pp.x, pp.y, pp.z, tag);
             }
         }
         else if (p == n_phases - 1)
@@ -616,7 +646,7 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                         want = a.base + 1u + static_cast<uint32_t>((K - 1) * per_iteration);
                 }
                 Real4<R> pp;
-                xchg_wait<R>(a, gv, want, pp.x, pp.y, pp.z);
+                xchg_wait<R>(a, a.n_entries + static_cast<uint32_t>(i0 + i), want, pp.x, pp.y, pp.z);
                 Real4<R> xn = ld4(&s.prev[gv]);
                 Real4<R> v  = ld4(&s.vel[gv]);
                 commit_vertex(pp, xn, v, dt);
@@ -627,8 +657,10 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
             // tetrahedral_body_t::update_visual_model (tetrahedral_body.cpp:157-165), owned surface vertices
             for (int32_t i = tid; i < ns; i += nt)
             {
-                uint32_t const addr = a.surf_addr[s0 + i];
-                Real4<R> const pp   = load_vertex(addr, sx, s.prev);
+                uint32_t addr = a.surf_addr[s0 + i];
+                if (addr & kGlobalBit)
+                    addr = a.ifv[addr & ~kGlobalBit] | kGlobalBit;
+                Real4<R> const pp = load_vertex(addr, sx, s.prev);
                 st4(&s.surf_pos[a.surf_index[s0 + i]], Real4<R>{pp.x, pp.y, pp.z, R(0)});
             }
         }
@@ -640,20 +672,22 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                 uint32_t const addr  = a.surf_addr[s0 + i];
                 uint32_t const first = n_contacts > 0 ? s.surf_first[a.surf_index[s0 + i]] : 0xffffffffu;
                 if (addr & kGlobalBit)
-                {
-                    uint32_t const gv    = addr & ~kGlobalBit;
-                    uint32_t const lastc = a.surf_meta[s0 + i] & 0xffu;
+                { // owned, not resident: out of the owner mailbox, on to the first cluster of the sweep
+                    uint32_t const iv    = addr & ~kGlobalBit;
+                    uint32_t const gv    = a.ifv[iv];
+                    uint32_t const lastc = a.ifv_meta[iv] & 0xffu;
                     uint32_t const want  = (k > 0 && lastc != kNoColour) ? last_colour_tag(k - 1, lastc)
                                            : k > 0                       ? tag - static_cast<uint32_t>(per_iteration)
                                                                          : a.base;
                     Real4<R> pp;
-                    xchg_wait<R>(a, gv, want, pp.x, pp.y, pp.z);
+                    xchg_wait<R>(a, a.n_entries + iv, want, pp.x, pp.y, pp.z);
                     if (first != 0xffffffffu)
                     {
                         pp.w = s.pos[gv].w;
                         project_vertex_contacts(s, first, n_contacts, pp, at_c, k == 0);
                     }
-                    Xchg<R>::store(a.xchg, gv, pp.x, pp.y, pp.z, tag);
+                    uint32_t const to = a.ifv_first[iv];
+                    Xchg<R>::store(a.box, to != kNoBox ? to : a.n_entries + iv, pp.x, pp.y, pp.z, tag);
                 }
                 else if (first != 0xffffffffu)
                 {
@@ -672,7 +706,8 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
             { // cluster item_i of the phase runs on thread item_i % nt; part A (clusters that fetch) first
                 bool const in_a    = item_i < nA;
                 DevChunk const& ch = s_chunks[2 * c + (in_a ? 0 : 1)];
-                run_cluster<R, NVC4>(a, ch, in_a ? item_i : item_i - nA, cur_fetch, head, sx, k == 0, tag, stamp);
+                StepInfo const si{tag, a.base, static_cast<uint32_t>(8 * (2 * (k > 0 ? 1 : 0) + cs)), k == K - 1, cs != 0};
+                run_cluster<R, NVC4>(a, ch, in_a ? item_i : item_i - nA, cur_q, head, sx, k == 0, si, stamp);
             }
             stamp(6);
         }
@@ -682,14 +717,12 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
         item_i = has_next ? ni_next : -1;
         if (has_next)
         {
-            head = nhead;
-#pragma unroll
-            for (int j = 0; j < NVC4; ++j)
-                cur_fetch[j] = nfetch[j];
+            head  = nhead;
+            cur_q = next_q;
             if (next_in_a)
-                gather_cluster<R, NVC4>(a, nfetch, nmeta, nw, sx,
+                gather_cluster<R, NVC4>(a, next_q, nmeta, nw, sx,
                                         StepInfo{a.base + static_cast<uint32_t>(np), a.base,
-                                                 static_cast<uint32_t>(8 * (2 * (nk > 0 ? 1 : 0) + cs))},
+                                                 static_cast<uint32_t>(8 * (2 * (nk > 0 ? 1 : 0) + cs)), false, false},
                                         stamp);
         }
         if (advance)
@@ -755,9 +788,9 @@ struct PersistentPlan
     PersistentArgs<R> args{};
     PBuf<int32_t> region_order, vtx_off, ifv_off, surf_off;
     PBuf<DevChunk> chunks;
-    PBuf<uint32_t> vtx, ifv, ifv_meta, surf_index, surf_addr, surf_meta, error;
+    PBuf<uint32_t> vtx, ifv, ifv_meta, ifv_first, surf_index, surf_addr, error;
     PBuf<uint2> tet_slots;
-    PBuf<uint4> cl_fetch, cl_meta, xchg;
+    PBuf<uint4> cl_meta, cl_to, cl_to_owner, box;
     PBuf<Real4<R>> cl_w;
     std::vector<uint4> h_fetch; // host copy of cl_fetch, to patch cl_w when a mass changes
     PBuf<long long> trace;
@@ -839,13 +872,15 @@ struct PersistentPlan
         int64_t const Q = cp.n_clusters;
         std::vector<uint4> fetch(static_cast<size_t>(nvc / 4) * static_cast<size_t>(Q),
                                  make_uint4(kNoVertex, kNoVertex, kNoVertex, kNoVertex));
-        std::vector<uint4> meta(fetch.size(), make_uint4(0u, 0u, 0u, 0u));
+        std::vector<uint4> meta(fetch.size(), make_uint4(kNoEntry, kNoEntry, kNoEntry, kNoEntry));
         for (int k4 = 0; k4 < cp.nvc / 4; ++k4)
             for (int64_t q = 0; q < Q; ++q)
             {
                 size_t const at = static_cast<size_t>(k4) * Q + q;
                 auto const f    = [&](int e) { return cp.cl_fetch[static_cast<size_t>(4 * k4 + e) * Q + q]; };
-                auto const m    = [&](int e) { return cp.cl_meta[static_cast<size_t>(4 * k4 + e) * Q + q]; };
+                auto const m    = [&](int e) {
+                    return f(e) == kNoVertex ? kNoEntry : cp.cl_meta[static_cast<size_t>(4 * k4 + e) * Q + q];
+                };
                 fetch[at]       = make_uint4(f(0), f(1), f(2), f(3));
                 meta[at]        = make_uint4(m(0), m(1), m(2), m(3));
             }
@@ -885,6 +920,76 @@ struct PersistentPlan
                     ifm[static_cast<size_t>(at)] = cp.vertex_meta[static_cast<size_t>(v)];
                 }
         }
+        // ---- routing of the mailboxes -------------------------------------------------------------
+        // entry (j, q) = scratch slot j of cluster q has mailbox j * Q + q; owned vertex i (position in
+        // ifv) has mailbox n_entries + i.  Per vertex the entries are ordered by the colour of their
+        // cluster: each pushes to the next one, the last one to the owner or back to the first.
+        uint32_t const n_entries = static_cast<uint32_t>(static_cast<int64_t>(nvc) * Q);
+        std::vector<uint32_t> ifv_pos(static_cast<size_t>(V), kNoBox);
+        for (size_t i = 0; i < ifv.size(); ++i)
+            ifv_pos[ifv[i]] = static_cast<uint32_t>(i);
+        std::vector<int32_t> cluster_colour(static_cast<size_t>(Q), 0);
+        for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
+            for (int32_t i = 0; i < cp.chunks[ch].n[0]; ++i)
+                cluster_colour[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
+                    static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
+        struct Touch
+        {
+            uint32_t vertex;
+            int32_t colour;
+            uint32_t box;
+        };
+        std::vector<Touch> touches;
+        for (int j = 0; j < cp.nvc; ++j)
+            for (int64_t q = 0; q < Q; ++q)
+            {
+                uint32_t const v = cp.cl_fetch[static_cast<size_t>(j) * Q + q];
+                if (v != kNoVertex)
+                    touches.push_back({v, cluster_colour[static_cast<size_t>(q)],
+                                       static_cast<uint32_t>(static_cast<int64_t>(j) * Q + q)});
+            }
+        std::sort(touches.begin(), touches.end(), [](Touch const& x, Touch const& y) {
+            return x.vertex != y.vertex ? x.vertex < y.vertex : x.colour < y.colour;
+        });
+        std::vector<uint32_t> r_to(n_entries, kNoBox), r_to_owner(n_entries, kNoBox);
+        std::vector<uint32_t> ifirst(ifv.size(), kNoBox);
+        for (size_t i = 0; i < touches.size();)
+        {
+            size_t j = i;
+            while (j < touches.size() && touches[j].vertex == touches[i].vertex)
+                ++j;
+            uint32_t const v   = touches[i].vertex;
+            uint32_t const pos = ifv_pos[v];
+            if (pos == kNoBox)
+            {
+                why_not = "a fetched vertex has no owner mailbox";
+                return false;
+            }
+            ifirst[pos] = touches[i].box;
+            for (size_t t = i; t < j; ++t)
+            {
+                if (t + 1 < j && touches[t + 1].colour == touches[t].colour)
+                {
+                    why_not = "two clusters of one colour touch the same vertex";
+                    return false;
+                }
+                uint32_t const surface      = (cp.vertex_meta[v] & 0x100u) ? kSurfaceBit : 0u;
+                r_to[touches[t].box]        = t + 1 < j ? touches[t + 1].box : touches[i].box;
+                r_to_owner[touches[t].box]  = (t + 1 < j ? touches[t + 1].box : n_entries + pos) | surface;
+            }
+            i = j;
+        }
+        auto const pack = [&](std::vector<uint32_t> const& r) {
+            std::vector<uint4> out(fetch.size(), make_uint4(kNoBox, kNoBox, kNoBox, kNoBox));
+            for (int k4 = 0; k4 < nvc / 4; ++k4)
+                for (int64_t q = 0; q < Q; ++q)
+                    out[static_cast<size_t>(k4) * Q + q] =
+                        make_uint4(r[static_cast<size_t>(4 * k4 + 0) * Q + q], r[static_cast<size_t>(4 * k4 + 1) * Q + q],
+                                   r[static_cast<size_t>(4 * k4 + 2) * Q + q], r[static_cast<size_t>(4 * k4 + 3) * Q + q]);
+            return out;
+        };
+        std::vector<uint4> const h_to = pack(r_to), h_to_owner = pack(r_to_owner);
+
         std::vector<uint32_t> sgv; // global vertex of surface vertex i (same order as DeviceScene::surf_v)
         for (auto const& b : h.bodies)
             if (b.kind == BodyKind::tet)
@@ -894,7 +999,7 @@ struct PersistentPlan
             ++soff[static_cast<size_t>(plan.vertex_owner[gv]) + 1];
         for (int32_t r = 0; r < Rn; ++r)
             soff[static_cast<size_t>(r) + 1] += soff[static_cast<size_t>(r)];
-        std::vector<uint32_t> sidx(sgv.size()), sadr(sgv.size()), smeta(sgv.size());
+        std::vector<uint32_t> sidx(sgv.size()), sadr(sgv.size());
         {
             std::vector<int32_t> cur(soff.begin(), soff.end() - 1);
             for (size_t i = 0; i < sgv.size(); ++i)
@@ -905,8 +1010,7 @@ struct PersistentPlan
                 sidx[static_cast<size_t>(pos)]  = static_cast<uint32_t>(i);
                 sadr[static_cast<size_t>(pos)]  = plan.vertex_region[gv] == r
                                                       ? static_cast<uint32_t>(nvc * cp.nt) + plan.vertex_slot[gv]
-                                                      : (gv | kGlobalBit);
-                smeta[static_cast<size_t>(pos)] = cp.vertex_meta[gv];
+                                                      : (ifv_pos[gv] | kGlobalBit);
             }
         }
         // regions that share vertices must be co-resident; the others are handed out round-robin
@@ -968,7 +1072,9 @@ struct PersistentPlan
         order.insert(order.end(), island_r.begin(), island_r.end());
         region_order.upload(order, st);
         tet_slots.upload(slots, st);
-        cl_fetch.upload(fetch, st);
+        cl_to.upload(h_to, st);
+        cl_to_owner.upload(h_to_owner, st);
+        ifv_first.upload(ifirst, st);
         cl_meta.upload(meta, st);
         cl_w.upload(fw, st);
         chunks.upload(hchunks, st);
@@ -980,10 +1086,9 @@ struct PersistentPlan
         surf_off.upload(soff, st);
         surf_index.upload(sidx, st);
         surf_addr.upload(sadr, st);
-        surf_meta.upload(smeta, st);
-        xchg.upload(std::vector<uint4>(static_cast<size_t>(std::max<int64_t>(V, 1)) * Xchg<R>::kWords,
-                                       make_uint4(0u, 0u, 0u, 0u)),
-                    st);
+        box.upload(std::vector<uint4>((static_cast<size_t>(n_entries) + ifv.size() + 1) * Xchg<R>::kWords,
+                                      make_uint4(0u, 0u, 0u, 0u)),
+                   st);
         error.upload(std::vector<uint32_t>(1, 0u), st);
         base = 1;
 
@@ -995,7 +1100,10 @@ struct PersistentPlan
         args.n_clusters       = Q;
         args.region_order     = region_order.p;
         args.tet_slots        = tet_slots.p;
-        args.cl_fetch         = cl_fetch.p;
+        args.cl_to            = cl_to.p;
+        args.cl_to_owner      = cl_to_owner.p;
+        args.ifv_first        = ifv_first.p;
+        args.n_entries        = n_entries;
         args.cl_meta          = cl_meta.p;
         args.cl_w             = cl_w.p;
         args.chunks           = chunks.p;
@@ -1007,8 +1115,7 @@ struct PersistentPlan
         args.surf_off         = surf_off.p;
         args.surf_index       = surf_index.p;
         args.surf_addr        = surf_addr.p;
-        args.surf_meta        = surf_meta.p;
-        args.xchg             = xchg.p;
+        args.box              = box.p;
         args.error            = error.p;
         ready                 = true;
         return true;
