@@ -50,16 +50,18 @@ def parse():
     ap.add_argument("--schedule", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--decompose", action="store_true",
+                    help="N > 1: cut the ONE body of the workload over the N GPUs (default for config5)")
     return ap.parse_args()
 
 
-def make_scene(sc, workload, rank, world):
+def make_scene(sc, workload, rank, world, decompose=False):
     if workload == "config1":
         return sc.config1()
     if workload == "config2":
         return sc.config2()
     if workload == "config3":
-        return sc.config3(seed=3 + 100 * rank)
+        return sc.config3(seed=3 + (0 if decompose else 100 * rank))
     if workload == "config5":
         return sc.config5()
     per = 4096 // world
@@ -204,13 +206,24 @@ def main():
     sbs = importlib.import_module("soft-body-simulator_b200")
     sc = importlib.import_module("soft-body-simulator_b200.scenes")
 
-    scene = make_scene(sc, args.workload, rank, world)
+    decomposed = world > 1 and (args.workload == "config5" or (args.decompose and args.workload in ("config2", "config3")))
+    scene = make_scene(sc, args.workload, rank, world, decomposed)
     # a dedicated non-blocking stream: the library captures the frame into a CUDA graph, which
     # the legacy default stream does not permit
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    sim = sbs.Simulation(local, args.precision, stream=stream.cuda_stream, schedule=args.schedule)
-    ids = scene.instantiate(sim)
+    sim = sbs.Simulation(local, args.precision, stream=stream.cuda_stream,
+                         schedule=sbs.SCHED_PERSISTENT if decomposed else args.schedule)
+    if decomposed:
+        # ONE body cut into world x regions; every rank runs its block, shared vertices travel through
+        # mailboxes in peer memory (NVLink stores issued by the substep kernel; no collective)
+        ids = scene.instantiate(sim, partition=(rank, world))
+        handles = [None] * world
+        dist.all_gather_object(handles, sim.mailbox_handle())
+        sim.connect_peers(handles)
+        dist.barrier()
+    else:
+        ids = scene.instantiate(sim)
     stats0 = sim.stats()
     S, K = scene.substeps, scene.iterations
     proj_per_step = scene.n_tets * S * K
@@ -248,7 +261,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    total_proj = proj_per_step * args.steps * (world if args.workload in ("config3", "config4") else 1)
+    total_proj = proj_per_step * args.steps * (world if args.workload in ("config3", "config4") and not decomposed else 1)
     value = total_proj / (ms_max * 1e-3)
 
     # ---- end-to-end through the C ABI with host buffers -----------------------------------
@@ -278,7 +291,7 @@ def main():
         t = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        scale = world if args.workload in ("config3", "config4") else 1
+        scale = world if args.workload in ("config3", "config4") and not decomposed else 1
         e2e = {"value": proj_per_step * n_e2e * scale / float(t.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(2 * nV * 24), "d2h_bytes_per_step": int(2 * nV * 24),
                "steps": n_e2e, "timing": "wall clock around sbsb200_step_host (max over ranks)",
@@ -305,8 +318,9 @@ def main():
             # dominant kernel = the substep kernel of the persistent schedule: one launch runs predict,
             # K sweeps over every tet and contact, and commit for one substep.  Timed live with CUDA
             # events around every launch of the timed region (sbsb200_stats.kernel_ms).
-            bytes_launch = K * (BYTES_PER_PROJECTION * scene.n_tets + BYTES_PER_COLLISION * contacts) \
-                + BYTES_PER_VERTEX_SUBSTEP * nVtot
+            share = world if decomposed else 1        # a rank of a decomposed body runs 1/world of it
+            bytes_launch = (K * (BYTES_PER_PROJECTION * scene.n_tets + BYTES_PER_COLLISION * contacts)
+                            + BYTES_PER_VERTEX_SUBSTEP * nVtot) // share
             if args.precision == 64:
                 bytes_launch = bytes_launch * 336 // 176
             k_ms = kernel_ms / kernel_launches
@@ -328,14 +342,17 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if args.workload == "config4" else "weak", "vs_baseline": None,
+            "scaling": "strong" if args.workload in ("config4", "config5") or decomposed else "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
-            "config": {"workload": scene.name, "tets_per_gpu": scene.n_tets, "vertices_per_gpu": nVtot,
+            "config": {"workload": scene.name, "tets_per_gpu": scene.n_tets // (world if decomposed else 1),
+                       "vertices_per_gpu": nVtot // (world if decomposed else 1),
                        "substeps": S, "iterations": K, "dt": scene.dt,
                        "detection": "every substep" if scene.detect_every_substep else "once per frame",
                        "colours": stats0["n_green_colours"], "schedule": sched,
                        "regions": stats0["n_regions"], "shared_vertices": stats0["n_interface_vertices"],
-                       "parallelism": "scenes sharded over %d GPU(s), no collective" % world,
+                       "parallelism": ("one body decomposed over %d GPUs, shared vertices pushed to peer memory by "
+                                       "the substep kernel" % world) if decomposed else
+                                      "scenes sharded over %d GPU(s), no collective" % world,
                        "l2": "256 MiB write between timed steps (flush)"},
             "ms_per_frame": ms_step,
             "contacts_last_detection": contacts,
@@ -354,7 +371,7 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"], _ = cpu_baseline(sc, args.workload)
             except Exception as exc:  # the checker failing must not hide the GPU number

@@ -139,6 +139,21 @@ int sbsb200_get_stats(const sbsb200_ctx* ctx, sbsb200_stats* out);
 /* Why the schedule in use differs from the requested one ("" when it does not). */
 const char* sbsb200_schedule_note(const sbsb200_ctx* ctx);
 
+/* ---- one scene decomposed over several GPUs (one context per GPU, any mix of processes) ---------
+ * Every rank describes the SAME scene, calls set_partition(rank, world) before finalize, and then
+ * runs its own block of regions; vertices shared between regions travel through mailboxes that
+ * live on the reading rank, so a push to another rank is a peer store over NVLink issued by the
+ * substep kernel itself (no host-side exchange, no collective).  After finalize every rank maps
+ * the other ranks' mailbox arrays: across processes through CUDA IPC handles (64 bytes each,
+ * exchanged by any means — bench.py uses torch.distributed.all_gather), inside one process
+ * through connect_peer_context.  The reference has no counterpart (it is single-threaded). */
+int sbsb200_set_partition(sbsb200_ctx* ctx, int rank, int world);
+int sbsb200_get_mailbox_handle(sbsb200_ctx* ctx, void* handle64);
+int sbsb200_connect_peers(sbsb200_ctx* ctx, const void* handles /* world x 64 bytes */, int world);
+int sbsb200_connect_peer_context(sbsb200_ctx* ctx, int peer_rank, sbsb200_ctx* peer);
+/* rank that owns (predicts, commits, holds the valid x and v of) every vertex of a body */
+int sbsb200_get_vertex_ranks(const sbsb200_ctx* ctx, int body, int32_t* out, int64_t n);
+
 /* ---- state ----------------------------------------------------------------------------- */
 
 /* Overwrite x (and v, NULL = 0) of a body; xi = xn = x as tetrahedral_body_t::transform

@@ -28,6 +28,8 @@ EXPORTS = [
     "sbsb200_schedule_note",
     "sbsb200_upload", "sbsb200_download", "sbsb200_set_mass", "sbsb200_step", "sbsb200_step_host",
     "sbsb200_synchronize", "sbsb200_get_contacts", "sbsb200_debug_read_trace",
+    "sbsb200_set_partition", "sbsb200_get_mailbox_handle", "sbsb200_connect_peers", "sbsb200_connect_peer_context",
+    "sbsb200_get_vertex_ranks",
 ]
 
 
@@ -91,6 +93,11 @@ def load_library():
     L.sbsb200_synchronize.argtypes = [vp]
     L.sbsb200_get_contacts.argtypes = [vp, C.c_int64, _i32p, _u32p, _i32p, _dp, _dp]
     L.sbsb200_get_contacts.restype = C.c_int64
+    L.sbsb200_set_partition.argtypes = [vp, C.c_int, C.c_int]
+    L.sbsb200_get_mailbox_handle.argtypes = [vp, C.c_char_p]
+    L.sbsb200_connect_peers.argtypes = [vp, C.c_char_p, C.c_int]
+    L.sbsb200_connect_peer_context.argtypes = [vp, C.c_int, vp]
+    L.sbsb200_get_vertex_ranks.argtypes = [vp, C.c_int, _i32p, C.c_int64]
     L.sbsb200_debug_read_trace.argtypes = [vp, C.POINTER(C.c_int64), C.c_int64]
     L.sbsb200_debug_read_trace.restype = C.c_int64
     _lib = L
@@ -218,6 +225,28 @@ class Simulation:
                                            substeps, iterations,
                                            DETECT_PER_SUBSTEP if detect_every_substep else DETECT_PER_FRAME,
                                            _d(x_out), _d(v_out)))
+
+    # ---- one scene decomposed over several GPUs ----------------------------------------------
+    def set_partition(self, rank, world):
+        self._ck(self._L.sbsb200_set_partition(self._h, rank, world))
+
+    def mailbox_handle(self):
+        buf = C.create_string_buffer(64)
+        self._ck(self._L.sbsb200_get_mailbox_handle(self._h, buf))
+        return buf.raw
+
+    def connect_peers(self, handles):
+        """handles: list of `world` 64-byte CUDA IPC handles (own entry ignored)."""
+        blob = b"".join(handles)
+        self._ck(self._L.sbsb200_connect_peers(self._h, blob, len(handles)))
+
+    def connect_peer_context(self, peer_rank, peer):
+        self._ck(self._L.sbsb200_connect_peer_context(self._h, peer_rank, peer._h))
+
+    def vertex_ranks(self, body):
+        out = np.empty(self._nv[body], np.int32)
+        self._ck(self._L.sbsb200_get_vertex_ranks(self._h, body, out.ctypes.data_as(_i32p), len(out)))
+        return out
 
     def debug_trace(self):
         """[regions, steps, 8] clock stamps (see sbsb200_debug_read_trace); empty when tracing is off."""

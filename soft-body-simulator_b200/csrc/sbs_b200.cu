@@ -80,6 +80,9 @@ struct EngineBase
     virtual void invalidate_graphs()                                                       = 0;
     virtual int64_t read_trace(sbsb200_ctx& c, int64_t* out, int64_t cap)                   = 0;
     virtual void kernel_times(double& ms, int64_t& launches)                                = 0;
+    virtual void* mailbox_pointer(size_t& bytes)                                            = 0;
+    virtual void set_peer_mailboxes(int rank, void* p)                                      = 0;
+    virtual bool peers_connected()                                                          = 0;
 };
 
 } // namespace
@@ -108,6 +111,8 @@ struct sbsb200_ctx
     int64_t frames        = 0;
     int64_t last_contacts = 0;
     int sm_count          = 0;
+    int rank = 0, world = 1; // decomposition of one scene over several GPUs (sbsb200_set_partition)
+    std::vector<void*> ipc_opened;
     int64_t n_surface     = 0;
     bool any_damping      = false;
     std::string schedule_note;
@@ -149,6 +154,14 @@ struct Engine final : EngineBase
             cudaEventDestroy(e.second);
         }
     }
+
+    void* mailbox_pointer(size_t& bytes) override
+    {
+        bytes = pp.box_bytes;
+        return pp.ready ? static_cast<void*>(pp.box.p) : nullptr;
+    }
+    void set_peer_mailboxes(int rank, void* p) override { pp.args.box_of_rank[rank] = p; }
+    bool peers_connected() override { return !pp.ready || pp.peers_connected(); }
 
     void kernel_times(double& ms, int64_t& launches) override
     {
@@ -336,7 +349,7 @@ struct Engine final : EngineBase
             bool ok = false;
             try
             {
-                ok = pp.build(c.scene, c.green_plan, c.plan, d, st, c.sm_count);
+                ok = pp.build(c.scene, c.green_plan, c.plan, d, st, c.sm_count, c.rank, c.world);
             }
             catch (std::exception const& e)
             {
@@ -741,6 +754,8 @@ void sbsb200_destroy(sbsb200_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream)
         cudaStreamSynchronize(c->stream);
+    for (void* p : c->ipc_opened)
+        cudaIpcCloseMemHandle(p);
     c->engine.reset();
     if (c->ev0)
         cudaEventDestroy(c->ev0);
@@ -927,6 +942,13 @@ int sbsb200_finalize(sbsb200_ctx* c)
         c->schedule = c->schedule_request == SBSB200_SCHED_PERSISTENT                     ? SBSB200_SCHED_PERSISTENT
                       : c->schedule_request == SBSB200_SCHED_AUTO && auto_persistent ? SBSB200_SCHED_PERSISTENT
                                                                                      : SBSB200_SCHED_GRAPH;
+        if (c->world > 1)
+        { // a decomposed scene exists only in the resident schedule (mailboxes in peer memory)
+            if (!persistent_ok || c->schedule_request == SBSB200_SCHED_GRAPH)
+                return fail(c, SBSB200_ERR_INVALID,
+                            "a partitioned scene needs the persistent schedule (tets, no distance constraints, beta = 0)");
+            c->schedule = SBSB200_SCHED_PERSISTENT;
+        }
         if (c->schedule == SBSB200_SCHED_PERSISTENT && !persistent_ok)
         {
             c->schedule      = SBSB200_SCHED_GRAPH;
@@ -937,7 +959,7 @@ int sbsb200_finalize(sbsb200_ctx* c)
         {
             ResidentParams const rp = c->precision == SBSB200_FP32 ? PersistentPlan<float>::resident_params()
                                                                    : PersistentPlan<double>::resident_params();
-            build_cluster_plan(h, PersistentPlan<float>::regions_for(c->sm_count, T),
+            build_cluster_plan(h, PersistentPlan<float>::regions_for(c->sm_count, T, c->world),
                                PersistentPlan<float>::wants_region_per_body(h, c->sm_count), c->green_plan, &rp,
                                &c->plan);
         }
@@ -961,6 +983,8 @@ int sbsb200_finalize(sbsb200_ctx* c)
         else
             c->engine.reset(new Engine<double>());
         c->engine->build(*c);
+        if (c->world > 1 && c->schedule != SBSB200_SCHED_PERSISTENT)
+            return fail(c, SBSB200_ERR_CAPACITY, "partitioned scene: " + c->schedule_note);
         c->finalized = true;
         return SBSB200_OK;
     });
@@ -1073,12 +1097,111 @@ int sbsb200_set_mass(sbsb200_ctx* c, int body, int64_t vertex, double mass)
     });
 }
 
+int sbsb200_set_partition(sbsb200_ctx* c, int rank, int world)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "set_partition must precede finalize");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world)
+        return fail(c, SBSB200_ERR_INVALID, "bad rank/world (at most 8 ranks)");
+    c->rank  = rank;
+    c->world = world;
+    return SBSB200_OK;
+}
+
+int sbsb200_get_mailbox_handle(sbsb200_ctx* c, void* handle64)
+{
+    if (!c || !handle64)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "get_mailbox_handle before finalize");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        size_t bytes = 0;
+        void* p      = c->engine->mailbox_pointer(bytes);
+        if (!p)
+            return fail(c, SBSB200_ERR_STATE, "this scene has no mailboxes (not the persistent schedule)");
+        cudaIpcMemHandle_t hnd;
+        CK(cudaIpcGetMemHandle(&hnd, p));
+        std::memcpy(handle64, &hnd, 64);
+        return SBSB200_OK;
+    });
+}
+
+int sbsb200_connect_peers(sbsb200_ctx* c, const void* handles, int world)
+{
+    if (!c || !handles)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized || world != c->world)
+        return fail(c, SBSB200_ERR_STATE, "connect_peers: finalize first, with the same world size");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        for (int r = 0; r < world; ++r)
+        {
+            if (r == c->rank)
+                continue;
+            cudaIpcMemHandle_t hnd;
+            std::memcpy(&hnd, static_cast<char const*>(handles) + 64 * r, 64);
+            void* p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(p);
+            c->engine->set_peer_mailboxes(r, p);
+        }
+        return SBSB200_OK;
+    });
+}
+
+int sbsb200_connect_peer_context(sbsb200_ctx* c, int peer_rank, sbsb200_ctx* peer)
+{
+    if (!c || !peer || !c->finalized || !peer->finalized || peer_rank < 0 || peer_rank >= c->world || peer_rank == c->rank)
+        return fail(c, SBSB200_ERR_INVALID, "connect_peer_context: both contexts finalized, peer_rank another rank");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        if (peer->device != c->device)
+        {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, c->device, peer->device));
+            if (!can)
+                return fail(c, SBSB200_ERR_CUDA, "no peer access between the two devices");
+            cudaError_t const e = cudaDeviceEnablePeerAccess(peer->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                throw CudaError{std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)};
+            cudaGetLastError();
+        }
+        size_t bytes = 0;
+        void* p      = peer->engine->mailbox_pointer(bytes);
+        if (!p)
+            return fail(c, SBSB200_ERR_STATE, "the peer has no mailboxes");
+        c->engine->set_peer_mailboxes(peer_rank, p);
+        return SBSB200_OK;
+    });
+}
+
+int sbsb200_get_vertex_ranks(const sbsb200_ctx* c, int body, int32_t* out, int64_t n)
+{
+    if (!c || !out || !c->finalized || !is_tet_body(c, body))
+        return SBSB200_ERR_INVALID;
+    HostBody const& hb = c->scene.bodies[static_cast<size_t>(body)];
+    if (n != hb.n_vertices)
+        return SBSB200_ERR_INVALID;
+    int32_t const per_rank = std::max<int32_t>(1, c->plan.n_regions / std::max(1, c->world));
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = c->world > 1 && !c->plan.vertex_owner.empty()
+                     ? c->plan.vertex_owner[static_cast<size_t>(hb.v_offset + i)] / per_rank
+                     : 0;
+    return SBSB200_OK;
+}
+
 int sbsb200_step(sbsb200_ctx* c, double dt, int substeps, int iterations, int detect_mode)
 {
     if (!c)
         return SBSB200_ERR_INVALID;
     if (!c->finalized)
         return fail(c, SBSB200_ERR_STATE, "step before finalize");
+    if (c->world > 1 && !c->engine->peers_connected())
+        return fail(c, SBSB200_ERR_STATE, "partitioned scene: connect the peers' mailboxes before stepping");
     if (!(dt > 0.) || substeps <= 0 || iterations < 0 ||
         (detect_mode != SBSB200_DETECT_PER_FRAME && detect_mode != SBSB200_DETECT_PER_SUBSTEP))
         return fail(c, SBSB200_ERR_INVALID, "bad step arguments");

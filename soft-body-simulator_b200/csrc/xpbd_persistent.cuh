@@ -58,7 +58,11 @@ constexpr uint32_t kNoColour  = 0xffu;
 constexpr uint32_t kNoBox     = 0xffffffffu; // "no such mailbox"
 constexpr uint32_t kNoEntry   = 0xffffffffu; // cl_meta of an unused scratch slot
 constexpr uint32_t kSurfaceBit = 0x80000000u; // cl_to_owner: the vertex is a surface vertex
-constexpr int kPollBudget     = 1 << 20;     // polls of one record before the kernel gives up
+// routing words: bits 0-27 mailbox index, bits 28-30 the rank (GPU) whose memory holds that mailbox
+constexpr uint32_t kBoxIndexMask = 0x0fffffffu;
+constexpr int kRankShift         = 28;
+constexpr int kMaxWorld          = 8;
+constexpr int kPollBudget     = 1 << 24;     // polls of one record before the kernel gives up
 
 // true when the wait should be abandoned: budget exhausted (sets the error flag) or another thread
 // already gave up (checked every 1024 polls so that one lost update cannot stall the whole launch)
@@ -94,6 +98,30 @@ __device__ __forceinline__ void st_b128(void* p, Word128 w)
                  "l"(w.lo), "l"(w.hi));
 }
 
+// system-scope variants: mailboxes in another GPU's memory (stores over NVLink), and polls of
+// mailboxes a peer GPU writes
+__device__ __forceinline__ Word128 ld_b128_sys(void const* p)
+{
+    Word128 w;
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.sys.global.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+                 : "=l"(w.lo), "=l"(w.hi)
+                 : "l"(p));
+    return w;
+}
+__device__ __forceinline__ void st_b128_sys(void* p, Word128 w)
+{
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.sys.global.b128 [%0], q;\n\t}" ::"l"(p),
+                 "l"(w.lo), "l"(w.hi));
+}
+__device__ __forceinline__ Word128 ld_b128_scoped(void const* p, bool sys) { return sys ? ld_b128_sys(p) : ld_b128(p); }
+__device__ __forceinline__ void st_b128_scoped(void* p, Word128 w, bool sys)
+{
+    if (sys)
+        st_b128_sys(p, w);
+    else
+        st_b128(p, w);
+}
+
 // Exchange records.  fp32: one word {x, y, z, tag} per vertex.  fp64: three words {value, tag}.
 template <typename R>
 struct Xchg;
@@ -105,9 +133,9 @@ struct Xchg<float>
     {
         Word128 w;
     };
-    static __device__ __forceinline__ Raw fetch(void const* base, uint32_t gv)
+    static __device__ __forceinline__ Raw fetch(void const* base, uint32_t gv, bool sys = false)
     {
-        return Raw{ld_b128(static_cast<char const*>(base) + 16ull * gv)};
+        return Raw{ld_b128_scoped(static_cast<char const*>(base) + 16ull * gv, sys)};
     }
     static __device__ __forceinline__ bool decode(Raw const& r, uint32_t expect, float& x, float& y, float& z)
     {
@@ -117,21 +145,22 @@ struct Xchg<float>
         return static_cast<uint32_t>(r.w.hi >> 32) == expect;
     }
     static __device__ __forceinline__ bool load(void const* base, uint32_t gv, uint32_t expect, float& x, float& y,
-                                                float& z)
+                                                float& z, bool sys = false)
     {
-        Word128 const w = ld_b128(static_cast<char const*>(base) + 16ull * gv);
+        Word128 const w = ld_b128_scoped(static_cast<char const*>(base) + 16ull * gv, sys);
         x               = __uint_as_float(static_cast<uint32_t>(w.lo));
         y               = __uint_as_float(static_cast<uint32_t>(w.lo >> 32));
         z               = __uint_as_float(static_cast<uint32_t>(w.hi));
         return static_cast<uint32_t>(w.hi >> 32) == expect;
     }
-    static __device__ __forceinline__ void store(void* base, uint32_t gv, float x, float y, float z, uint32_t tag)
+    static __device__ __forceinline__ void store(void* base, uint32_t gv, float x, float y, float z, uint32_t tag,
+                                                 bool sys = false)
     {
         Word128 w;
         w.lo = static_cast<unsigned long long>(__float_as_uint(x)) |
                (static_cast<unsigned long long>(__float_as_uint(y)) << 32);
         w.hi = static_cast<unsigned long long>(__float_as_uint(z)) | (static_cast<unsigned long long>(tag) << 32);
-        st_b128(static_cast<char*>(base) + 16ull * gv, w);
+        st_b128_scoped(static_cast<char*>(base) + 16ull * gv, w, sys);
     }
 };
 template <>
@@ -142,10 +171,10 @@ struct Xchg<double>
     {
         Word128 w0, w1, w2;
     };
-    static __device__ __forceinline__ Raw fetch(void const* base, uint32_t gv)
+    static __device__ __forceinline__ Raw fetch(void const* base, uint32_t gv, bool sys = false)
     {
         char const* p = static_cast<char const*>(base) + 48ull * gv;
-        return Raw{ld_b128(p), ld_b128(p + 16), ld_b128(p + 32)};
+        return Raw{ld_b128_scoped(p, sys), ld_b128_scoped(p + 16, sys), ld_b128_scoped(p + 32, sys)};
     }
     static __device__ __forceinline__ bool decode(Raw const& r, uint32_t expect, double& x, double& y, double& z)
     {
@@ -156,22 +185,23 @@ struct Xchg<double>
                static_cast<uint32_t>(r.w2.hi) == expect;
     }
     static __device__ __forceinline__ bool load(void const* base, uint32_t gv, uint32_t expect, double& x, double& y,
-                                                double& z)
+                                                double& z, bool sys = false)
     {
         char const* p    = static_cast<char const*>(base) + 48ull * gv;
-        Word128 const w0 = ld_b128(p), w1 = ld_b128(p + 16), w2 = ld_b128(p + 32);
+        Word128 const w0 = ld_b128_scoped(p, sys), w1 = ld_b128_scoped(p + 16, sys), w2 = ld_b128_scoped(p + 32, sys);
         x                = __longlong_as_double(static_cast<long long>(w0.lo));
         y                = __longlong_as_double(static_cast<long long>(w1.lo));
         z                = __longlong_as_double(static_cast<long long>(w2.lo));
         return static_cast<uint32_t>(w0.hi) == expect && static_cast<uint32_t>(w1.hi) == expect &&
                static_cast<uint32_t>(w2.hi) == expect;
     }
-    static __device__ __forceinline__ void store(void* base, uint32_t gv, double x, double y, double z, uint32_t tag)
+    static __device__ __forceinline__ void store(void* base, uint32_t gv, double x, double y, double z, uint32_t tag,
+                                                 bool sys = false)
     {
         char* p = static_cast<char*>(base) + 48ull * gv;
-        st_b128(p, Word128{static_cast<unsigned long long>(__double_as_longlong(x)), tag});
-        st_b128(p + 16, Word128{static_cast<unsigned long long>(__double_as_longlong(y)), tag});
-        st_b128(p + 32, Word128{static_cast<unsigned long long>(__double_as_longlong(z)), tag});
+        st_b128_scoped(p, Word128{static_cast<unsigned long long>(__double_as_longlong(x)), tag}, sys);
+        st_b128_scoped(p + 16, Word128{static_cast<unsigned long long>(__double_as_longlong(y)), tag}, sys);
+        st_b128_scoped(p + 32, Word128{static_cast<unsigned long long>(__double_as_longlong(z)), tag}, sys);
     }
 };
 
@@ -180,6 +210,7 @@ struct PersistentArgs
 {
     DeviceScene<R> s;
     int32_t n_regions, n_colours;
+    int32_t n_run;                 // regions this launch runs (entries of region_order)
     int32_t nvc;                   // scratch entries per thread (4 * NVC4 of the instantiation)
     int64_t n_clusters;
     int32_t const* region_order;   // CTA b runs region_order[b], [b + grid], ...; regions that share
@@ -207,6 +238,10 @@ struct PersistentArgs
     uint32_t const* surf_addr;     // shared-memory slot, or (index into ifv) | kGlobalBit when not resident
     void* box;                     // mailboxes: n_entries of the fetch lists, then one per owned vertex
     uint32_t n_entries;            // nvc * n_clusters
+    // decomposition over GPUs: every rank plans the same regions and runs its own block of them; the
+    // mailbox of an entry lives on the rank that reads it, pushes to other ranks are peer stores
+    int32_t rank, world;
+    void* box_of_rank[kMaxWorld];  // mailbox arrays of all ranks (peer-mapped); [rank] == box
     uint32_t* error;               // set to 1 when a poll budget ran out
     uint32_t base;                 // tag of step 0 of this launch
     long long* trace;              // development aid: per-step clock stamps of thread 0 (nullptr = off)
@@ -216,12 +251,26 @@ struct PersistentArgs
     R dt;
 };
 
-// Wait for `expect` on mailbox `b` and return the position in it.
+// Push a position into the mailbox a routing word names (index + rank), tagged with the step.
+template <typename R>
+__device__ __forceinline__ void push(PersistentArgs<R> const& a, uint32_t route, R x, R y, R z, uint32_t tag)
+{
+    uint32_t const index = route & kBoxIndexMask;
+    if (a.world > 1)
+    {
+        uint32_t const r = (route >> kRankShift) & 7u;
+        Xchg<R>::store(a.box_of_rank[r], index, x, y, z, tag, true);
+    }
+    else
+        Xchg<R>::store(a.box, index, x, y, z, tag);
+}
+
+// Wait for `expect` on (local) mailbox `b` and return the position in it.
 template <typename R>
 __device__ __forceinline__ void xchg_wait(PersistentArgs<R> const& a, uint32_t b, uint32_t expect, R& x, R& y, R& z)
 {
     int polls = 0;
-    while (!Xchg<R>::load(a.box, b, expect, x, y, z))
+    while (!Xchg<R>::load(a.box, b, expect, x, y, z, a.world > 1))
     {
         if (poll_expired(a.error, ++polls))
             break;
@@ -375,7 +424,8 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64
 #pragma unroll
             for (int e = 0; e < kBatch; ++e)
                 if (pending >> (h + e) & 1u)
-                    raw[e] = Xchg<R>::fetch(a.box, static_cast<uint32_t>(h + e) * static_cast<uint32_t>(a.n_clusters) + mine);
+                    raw[e] = Xchg<R>::fetch(a.box, static_cast<uint32_t>(h + e) * static_cast<uint32_t>(a.n_clusters) + mine,
+                                            a.world > 1);
 #pragma unroll
             for (int e = 0; e < kBatch; ++e)
                 if (pending >> (h + e) & 1u)
@@ -467,7 +517,7 @@ __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk
             if (tb[e] != kNoBox)
             {
                 bool const owner_next = si.to_owner || (si.surface_to_owner && (tb[e] & kSurfaceBit));
-                Xchg<R>::store(a.box, owner_next ? (tb[e] & ~kSurfaceBit) : ta[e], p[e].x, p[e].y, p[e].z, si.step);
+                push<R>(a, owner_next ? tb[e] : ta[e], p[e].x, p[e].y, p[e].z, si.step);
             }
     }
     stamp(15);
@@ -617,7 +667,10 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                 // sweep that contains the vertex, else (no sweep touches it) the owner's commit
                 uint32_t const first = a.ifv_first[i0 + i];
                 bool const to_me     = K == 0 || first == kNoBox || (cs && (a.ifv_meta[i0 + i] & 0x100u));
-                Xchg<R>::store(a.box, to_me ? a.n_entries + static_cast<uint32_t>(i0 + i) : first, pp.x, pp.y, pp.z, tag);
+                if (to_me)
+                    Xchg<R>::store(a.box, a.n_entries + static_cast<uint32_t>(i0 + i), pp.x, pp.y, pp.z, tag, a.world > 1);
+                else
+                    push<R>(a, first, pp.x, pp.y, pp.z, tag);
             }
         }
         else if (p == n_phases - 1)
@@ -687,7 +740,10 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                         project_vertex_contacts(s, first, n_contacts, pp, at_c, k == 0);
                     }
                     uint32_t const to = a.ifv_first[iv];
-                    Xchg<R>::store(a.box, to != kNoBox ? to : a.n_entries + iv, pp.x, pp.y, pp.z, tag);
+                    if (to != kNoBox)
+                        push<R>(a, to, pp.x, pp.y, pp.z, tag);
+                    else
+                        Xchg<R>::store(a.box, a.n_entries + iv, pp.x, pp.y, pp.z, tag, a.world > 1);
                 }
                 else if (first != 0xffffffffu)
                 {
@@ -756,7 +812,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_substep_persistent(PersistentAr
     Real4<R>* sx       = reinterpret_cast<Real4<R>*>(smem_raw + chunk_area_bytes(a.n_colours));
     // regions that share vertices come first in region_order (at most one per CTA: they must be
     // co-resident), the others follow and are handed out round-robin
-    for (int32_t i = blockIdx.x; i < a.n_regions; i += gridDim.x)
+    for (int32_t i = blockIdx.x; i < a.n_run; i += gridDim.x)
         run_region<R, NVC4, kTrace>(a, a.region_order[i], sx, s_chunks);
 }
 
@@ -807,9 +863,11 @@ struct PersistentPlan
 
     // how many regions to cut the scene into: one per SM, but at least ~64 clusters per colour step
     // and region (small scenes use fewer SMs rather than synchronise regions of a few tets)
-    static int32_t regions_for(int sm_count, int64_t n_tets)
+    // With a decomposition over `world` GPUs every rank runs an equal block of consecutive regions.
+    static int32_t regions_for(int sm_count, int64_t n_tets, int world = 1)
     {
-        return static_cast<int32_t>(std::max<int64_t>(1, std::min<int64_t>(sm_count, n_tets / 2560)));
+        int64_t const per_rank = std::max<int64_t>(1, std::min<int64_t>(sm_count, n_tets / world / 2560));
+        return static_cast<int32_t>(per_rank * world);
     }
     // ensembles: many independent bodies -> one region per body
     static bool wants_region_per_body(HostScene const& h, int sm_count)
@@ -837,9 +895,16 @@ struct PersistentPlan
 
     // returns false (with why_not) when the scene does not fit this schedule
     bool build(HostScene const& h, ClusterPlan const& cp, RegionPlan const& plan, DeviceScene<R> const& d,
-               cudaStream_t st, int sm_count)
+               cudaStream_t st, int sm_count, int rank = 0, int world = 1)
     {
         int32_t const Rn = plan.n_regions;
+        if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || Rn % world != 0)
+        {
+            why_not = "bad partition (world must divide the region count, at most 8 ranks)";
+            return false;
+        }
+        int32_t const per_rank = Rn / world;
+        auto const rank_of_region = [&](int32_t r) { return static_cast<uint32_t>(r / per_rank); };
         int64_t const T = h.n_tets(), V = h.n_vertices();
         if (!cp.why_not.empty())
         {
@@ -928,11 +993,27 @@ struct PersistentPlan
         std::vector<uint32_t> ifv_pos(static_cast<size_t>(V), kNoBox);
         for (size_t i = 0; i < ifv.size(); ++i)
             ifv_pos[ifv[i]] = static_cast<uint32_t>(i);
-        std::vector<int32_t> cluster_colour(static_cast<size_t>(Q), 0);
+        if (static_cast<uint64_t>(n_entries) + ifv.size() >= kBoxIndexMask)
+        {
+            why_not = "too many mailboxes for 28-bit routing words";
+            return false;
+        }
+        std::vector<int32_t> cluster_colour(static_cast<size_t>(Q), 0), cluster_region(static_cast<size_t>(Q), 0);
         for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
             for (int32_t i = 0; i < cp.chunks[ch].n[0]; ++i)
+            {
                 cluster_colour[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
                     static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
+                cluster_region[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
+                    static_cast<int32_t>((ch / 2) % static_cast<size_t>(Rn));
+            }
+        // routing word of a mailbox: its index and the rank whose memory holds it (the rank that reads it)
+        auto const entry_route = [&](uint32_t box) {
+            return box | (rank_of_region(cluster_region[box % static_cast<uint32_t>(Q)]) << kRankShift);
+        };
+        auto const owner_route = [&](uint32_t pos) {
+            return (n_entries + pos) | (rank_of_region(plan.vertex_owner[ifv[pos]]) << kRankShift);
+        };
         struct Touch
         {
             uint32_t vertex;
@@ -965,7 +1046,7 @@ struct PersistentPlan
                 why_not = "a fetched vertex has no owner mailbox";
                 return false;
             }
-            ifirst[pos] = touches[i].box;
+            ifirst[pos] = entry_route(touches[i].box);
             for (size_t t = i; t < j; ++t)
             {
                 if (t + 1 < j && touches[t + 1].colour == touches[t].colour)
@@ -974,8 +1055,8 @@ struct PersistentPlan
                     return false;
                 }
                 uint32_t const surface      = (cp.vertex_meta[v] & 0x100u) ? kSurfaceBit : 0u;
-                r_to[touches[t].box]        = t + 1 < j ? touches[t + 1].box : touches[i].box;
-                r_to_owner[touches[t].box]  = (t + 1 < j ? touches[t + 1].box : n_entries + pos) | surface;
+                r_to[touches[t].box]       = entry_route(t + 1 < j ? touches[t + 1].box : touches[i].box);
+                r_to_owner[touches[t].box] = (t + 1 < j ? entry_route(touches[t + 1].box) : owner_route(pos)) | surface;
             }
             i = j;
         }
@@ -1015,7 +1096,7 @@ struct PersistentPlan
         }
         // regions that share vertices must be co-resident; the others are handed out round-robin
         std::vector<int32_t> sync_r, island_r;
-        for (int32_t r = 0; r < Rn; ++r)
+        for (int32_t r = rank * per_rank; r < (rank + 1) * per_rank; ++r)
             (plan.nbr_offsets[static_cast<size_t>(r) + 1] > plan.nbr_offsets[static_cast<size_t>(r)] ? sync_r : island_r)
                 .push_back(r);
         std::vector<int32_t> voff(plan.region_vtx_offsets.begin(), plan.region_vtx_offsets.end());
@@ -1089,11 +1170,17 @@ struct PersistentPlan
         box.upload(std::vector<uint4>((static_cast<size_t>(n_entries) + ifv.size() + 1) * Xchg<R>::kWords,
                                       make_uint4(0u, 0u, 0u, 0u)),
                    st);
+        box_bytes = (static_cast<size_t>(n_entries) + ifv.size() + 1) * Xchg<R>::kWords * sizeof(uint4);
         error.upload(std::vector<uint32_t>(1, 0u), st);
         base = 1;
 
         args.s                = d;
         args.n_regions        = Rn;
+        args.n_run            = static_cast<int32_t>(order.size());
+        args.rank             = rank;
+        args.world            = world;
+        for (int r = 0; r < kMaxWorld; ++r)
+            args.box_of_rank[r] = r == rank ? static_cast<void*>(box.p) : nullptr;
         args.n_colours        = cp.n_colours;
 
         args.nvc              = nvc;
@@ -1143,6 +1230,16 @@ struct PersistentPlan
         base += steps_per_substep(iterations, collide);
         return 1;
     }
+
+    // every rank's mailbox array must be mapped before the first step of a decomposed scene
+    bool peers_connected() const
+    {
+        for (int r = 0; r < args.world; ++r)
+            if (!args.box_of_rank[r])
+                return false;
+        return true;
+    }
+    size_t box_bytes = 0;
 
     // particle_t::mass() of a vertex changed: patch its inverse mass in every fetch list naming it
     void set_inverse_mass(uint32_t gv, R w, cudaStream_t st)

@@ -92,9 +92,12 @@ class Scene:
     def tet_bodies(self):
         return [i for i, it in enumerate(self.items) if isinstance(it, TetBody)]
 
-    def instantiate(self, backend, finalize=True):
-        """Create the scene on a backend (GPU Simulation or oracle World)."""
+    def instantiate(self, backend, finalize=True, partition=None):
+        """Create the scene on a backend (GPU Simulation or oracle World).  partition = (rank, world):
+        this backend runs its share of the scene decomposed over `world` GPUs."""
         backend.set_collision_compliance(self.collision_compliance)
+        if partition is not None:
+            backend.set_partition(*partition)
         ids = []
         for it in self.items:
             if isinstance(it, TetBody):
