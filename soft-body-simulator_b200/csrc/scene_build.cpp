@@ -582,8 +582,11 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
             int64_t need = 0;
             for (size_t i = 0; i < a_cnt.size(); ++i)
                 need = std::max(need, a_cnt[i] + b_cnt[i]);
+            // more clusters than threads: as many rounds as the largest block needs, of equal width
+            int64_t const rounds = std::max<int64_t>(1, (need + resident->max_threads - 1) / resident->max_threads);
+            int64_t const width  = (need + rounds - 1) / rounds;
             return static_cast<int32_t>(
-                std::min<int64_t>(resident->max_threads, std::max<int64_t>(64, (need + 31) / 32 * 32)));
+                std::min<int64_t>(resident->max_threads, std::max<int64_t>(64, (width + 31) / 32 * 32)));
         };
         size_t const n_steps = static_cast<size_t>(out.n_colours) * static_cast<size_t>(out.n_regions);
         std::vector<int64_t> a_cnt(n_steps, 0), b_cnt(n_steps, 0);

@@ -168,6 +168,22 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
                         ClusterPlan& out, ResidentParams const* resident = nullptr,
                         RegionPlan* region_plan = nullptr);
 
+// ---- decomposition of one scene over several GPUs ---------------------------------------------
+// How many regions to cut a scene into: one per SM of every rank, but at least ~64 clusters per
+// colour step and region (small scenes use fewer SMs rather than synchronise regions of a few tets).
+// Always a multiple of `world`: rank r runs the block of consecutive regions [r, r + 1) * n / world,
+// which is spatially compact because regions follow the Morton order of the clusters.
+inline int32_t regions_for(int sm_count, int64_t n_tets, int world = 1)
+{
+    int64_t per_rank = n_tets / (world > 0 ? world : 1) / 2560;
+    per_rank         = per_rank < 1 ? 1 : per_rank > sm_count ? sm_count : per_rank;
+    return static_cast<int32_t>(per_rank * (world > 0 ? world : 1));
+}
+inline int32_t region_rank(int32_t region, int32_t n_regions, int32_t world)
+{
+    return region / (n_regions / world);
+}
+
 // true when every tet slot of the resident layout resolves to the right vertex (resident slot of
 // its region, or the scratch entry the running thread fetched) and parts are classified correctly
 bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& rp);

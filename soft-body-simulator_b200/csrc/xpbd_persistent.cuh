@@ -861,13 +861,9 @@ struct PersistentPlan
     static constexpr int64_t kSmemBudget   = 224 * 1024;
     static constexpr int64_t kVertexBudget = 200 * 1024; // scratch + resident vertices (rest: chunk descriptors)
 
-    // how many regions to cut the scene into: one per SM, but at least ~64 clusters per colour step
-    // and region (small scenes use fewer SMs rather than synchronise regions of a few tets)
-    // With a decomposition over `world` GPUs every rank runs an equal block of consecutive regions.
     static int32_t regions_for(int sm_count, int64_t n_tets, int world = 1)
     {
-        int64_t const per_rank = std::max<int64_t>(1, std::min<int64_t>(sm_count, n_tets / world / 2560));
-        return static_cast<int32_t>(per_rank * world);
+        return sbsb200::regions_for(sm_count, n_tets, world);
     }
     // ensembles: many independent bodies -> one region per body
     static bool wants_region_per_body(HostScene const& h, int sm_count)
@@ -882,15 +878,16 @@ struct PersistentPlan
         ResidentParams rp;
         rp.smem_bytes   = kVertexBudget;
         rp.vertex_bytes = static_cast<int32_t>(sizeof(Real4<R>));
-        rp.max_threads  = 512;
+        rp.max_threads  = 384; // 168 registers per thread; 512 threads (128 registers) spills in the tet loop
         return rp;
     }
 
+    // the fewer threads a CTA has, the more registers each may use (255 / 168)
     template <int NVC4, bool kTrace>
-    static void const* pick(bool small)
+    static void const* pick(int threads)
     {
-        return small ? reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 256>)
-                     : reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 512>);
+        return threads <= 256 ? reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 256>)
+                              : reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 384>);
     }
 
     // returns false (with why_not) when the scene does not fit this schedule
@@ -904,7 +901,7 @@ struct PersistentPlan
             return false;
         }
         int32_t const per_rank = Rn / world;
-        auto const rank_of_region = [&](int32_t r) { return static_cast<uint32_t>(r / per_rank); };
+        auto const rank_of_region = [&](int32_t r) { return static_cast<uint32_t>(region_rank(r, Rn, world)); };
         int64_t const T = h.n_tets(), V = h.n_vertices();
         if (!cp.why_not.empty())
         {
@@ -1116,17 +1113,16 @@ struct PersistentPlan
         int trace_n = 0;
         if (char const* e = std::getenv("SBSB200_TRACE_STEPS"))
             trace_n = std::atoi(e);
-        bool const small = block <= 256; // up to 255 registers per thread
         if (trace_n > 0 && nvc == 8)
         {
-            kernel = pick<2, true>(small);
+            kernel = pick<2, true>(block);
             trace.upload(std::vector<long long>(static_cast<size_t>(Rn) * trace_n * 16, 0), st);
             args.trace       = trace.p;
             args.trace_steps = trace_n;
             trace_len        = static_cast<int64_t>(Rn) * trace_n * 16;
         }
         else
-            kernel = nvc == 8 ? pick<2, false>(small) : pick<4, false>(small);
+            kernel = nvc == 8 ? pick<2, false>(block) : pick<4, false>(block);
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
             cudaSuccess)
         {

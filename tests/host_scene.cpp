@@ -116,3 +116,37 @@ extern "C" int hs_cluster_plan(int64_t nV, int64_t nT, const uint32_t* tets, con
     *max_chunk  = plan.max_chunk_clusters;
     return plan.n_colours;
 }
+
+// decomposition over `world` ranks of a single lattice body: per-tet region and per-region rank, as
+// the library plans it (regions_for / build_cluster_plan / region_rank); returns the region count
+extern "C" int hs_partition(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int sm_count, int world,
+                            int32_t* tet_region, int32_t* region_rank_out, int cap_regions)
+{
+    HostScene h;
+    h.x0.assign(x0, x0 + 3 * nV);
+    h.mass.assign(static_cast<size_t>(nV), 1.0);
+    h.tets.assign(tets, tets + 4 * nT);
+    for (int64_t t = 0; t < nT; ++t)
+    {
+        h.tet_insertion.push_back(h.n_constraints++);
+        h.tet_material.push_back(0);
+    }
+    HostBody b;
+    b.n_vertices = nV;
+    b.n_tets     = nT;
+    h.bodies.push_back(b);
+    int32_t const n_regions = regions_for(sm_count, nT, world);
+    if (n_regions > cap_regions || n_regions % world != 0)
+        return -1;
+    ResidentParams rp;
+    rp.smem_bytes = 200 * 1024;
+    ClusterPlan plan;
+    RegionPlan regions;
+    build_cluster_plan(h, n_regions, false, plan, &rp, &regions);
+    if (!plan.why_not.empty() || !cluster_plan_is_valid(h, plan) || !resident_layout_is_valid(h, plan, regions))
+        return -2;
+    std::memcpy(tet_region, plan.tet_region.data(), sizeof(int32_t) * plan.tet_region.size());
+    for (int32_t r = 0; r < n_regions; ++r)
+        region_rank_out[r] = region_rank(r, n_regions, world);
+    return n_regions;
+}
