@@ -43,6 +43,11 @@ extern "C" {
 #define SBSB200_DETECT_PER_FRAME 0   /* reference semantics: timestep.cpp:29-30 */
 #define SBSB200_DETECT_PER_SUBSTEP 1 /* == `substeps` calls of step() with substeps=1 */
 
+/* broadphase of the collision detection (sbsb200_set_broadphase) */
+#define SBSB200_BROADPHASE_NONE 0 /* every surface vertex against every SDF (default: cheapest for analytic SDFs) */
+#define SBSB200_BROADPHASE_BVH 1  /* linear BVH of bounding spheres per body, rebuilt on the device at every
+                                   * detection, culled like point_bvh_model_t::collide (bvh_model.cpp:30-100) */
+
 /* schedule selection (sbsb200_set_schedule) */
 #define SBSB200_SCHED_AUTO 0
 #define SBSB200_SCHED_GRAPH 1      /* one kernel per colour, whole frame in a CUDA graph */
@@ -82,6 +87,9 @@ const char* sbsb200_last_error(const sbsb200_ctx* ctx);
  * stream owned by the context.  Must be called before finalize. */
 int sbsb200_set_stream(sbsb200_ctx* ctx, void* cuda_stream);
 int sbsb200_set_schedule(sbsb200_ctx* ctx, int schedule);
+
+/* point_bvh_model_t (include/sbs/physics/collision/bvh_model.h:23-49): the broadphase.  Before finalize. */
+int sbsb200_set_broadphase(sbsb200_ctx* ctx, int mode);
 
 /* simulation_parameters_t::collision_compliance (include/sbs/physics/xpbd/simulation_parameters.h:24) */
 int sbsb200_set_collision_compliance(sbsb200_ctx* ctx, double alpha);

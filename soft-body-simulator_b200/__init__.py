@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsbsb200.so")
 FP32, FP64 = 32, 64
 DETECT_PER_FRAME, DETECT_PER_SUBSTEP = 0, 1
 SCHED_AUTO, SCHED_GRAPH, SCHED_PERSISTENT = 0, 1, 2
+BROADPHASE_NONE, BROADPHASE_BVH = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _u32p = C.POINTER(C.c_uint32)
@@ -29,7 +30,7 @@ EXPORTS = [
     "sbsb200_upload", "sbsb200_download", "sbsb200_set_mass", "sbsb200_step", "sbsb200_step_host",
     "sbsb200_synchronize", "sbsb200_get_contacts", "sbsb200_debug_read_trace",
     "sbsb200_set_partition", "sbsb200_get_mailbox_handle", "sbsb200_connect_peers", "sbsb200_connect_peer_context",
-    "sbsb200_get_vertex_ranks",
+    "sbsb200_get_vertex_ranks", "sbsb200_set_broadphase",
 ]
 
 
@@ -93,6 +94,7 @@ def load_library():
     L.sbsb200_synchronize.argtypes = [vp]
     L.sbsb200_get_contacts.argtypes = [vp, C.c_int64, _i32p, _u32p, _i32p, _dp, _dp]
     L.sbsb200_get_contacts.restype = C.c_int64
+    L.sbsb200_set_broadphase.argtypes = [vp, C.c_int]
     L.sbsb200_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.sbsb200_get_mailbox_handle.argtypes = [vp, C.c_char_p]
     L.sbsb200_connect_peers.argtypes = [vp, C.c_char_p, C.c_int]
@@ -143,6 +145,10 @@ class Simulation:
             self.close()
         except Exception:
             pass
+
+    def set_broadphase(self, mode):
+        """0 = none (every surface vertex against every SDF), 1 = BVH (bvh_model.cpp:30-100)."""
+        self._ck(self._L.sbsb200_set_broadphase(self._h, mode))
 
     def set_collision_compliance(self, alpha):
         self._ck(self._L.sbsb200_set_collision_compliance(self._h, alpha))

@@ -6,6 +6,7 @@
 
 #include "scene_build.h"
 #include "xpbd_kernels.cuh"
+#include "bvh.cuh"
 #include "xpbd_persistent.cuh"
 
 #include <algorithm>
@@ -111,6 +112,7 @@ struct sbsb200_ctx
     int64_t frames        = 0;
     int64_t last_contacts = 0;
     int sm_count          = 0;
+    int broadphase = SBSB200_BROADPHASE_NONE;
     int rank = 0, world = 1; // decomposition of one scene over several GPUs (sbsb200_set_partition)
     std::vector<void*> ipc_opened;
     int64_t n_surface     = 0;
@@ -135,6 +137,14 @@ struct Engine final : EngineBase
     DevBuf<int32_t> surf_body;
     DevBuf<typename DeviceScene<R>::Sdf> sdf;
     DevBuf<double> stage_x, stage_v; // raw host-format staging for upload/download
+    // BVH broadphase (bvh.cuh)
+    BvhView<R> bvh{};
+    DevBuf<uint64_t> bvh_keys, bvh_keys_sorted;
+    DevBuf<uint32_t> bvh_leaf_in, bvh_leaf_surface, bvh_range_first, bvh_range_last, bvh_visits, surf_cull;
+    DevBuf<int32_t> bvh_parent, bvh_child;
+    DevBuf<Real4<R>> bvh_sphere;
+    DevBuf<unsigned char> bvh_temp;
+    size_t bvh_temp_bytes = 0;
     PersistentPlan<R> pp; // persistent schedule resources (may be inactive)
     // CUDA-event pairs around the launches of the dominant kernel (persistent schedule: the substep
     // kernel), folded into a running sum when the statistics are read
@@ -292,6 +302,11 @@ struct Engine final : EngineBase
                     f.b[k] = R(hb.b[k]);
                 }
                 f.r = R(hb.r);
+                for (int k = 0; k < 3; ++k)
+                {
+                    f.vmin[k] = R(hb.volume[k]);
+                    f.vmax[k] = R(hb.volume[3 + k]);
+                }
                 hs.push_back(f);
             }
         }
@@ -337,7 +352,53 @@ struct Engine final : EngineBase
         d.contact_n       = contact_n.p;
         d.contact_count   = contact_count.p;
         d.collision_alpha = R(c.collision_alpha);
+        d.surf_cull       = nullptr;
         c.n_surface       = Vs;
+        if (c.broadphase == SBSB200_BROADPHASE_BVH && Vs > 0 && !hs.empty())
+        { // linear BVH over the surface vertices, rebuilt at every detection
+            size_t const n = static_cast<size_t>(Vs);
+            bvh_keys.alloc(n);
+            bvh_keys_sorted.alloc(n);
+            bvh_leaf_in.alloc(n);
+            bvh_leaf_surface.alloc(n);
+            bvh_parent.alloc(2 * n);
+            bvh_child.alloc(2 * n);
+            bvh_range_first.alloc(n);
+            bvh_range_last.alloc(n);
+            bvh_visits.alloc(n);
+            bvh_sphere.alloc(2 * n);
+            surf_cull.alloc(n);
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, bvh_temp_bytes, bvh_keys.p, bvh_keys_sorted.p, bvh_leaf_in.p,
+                                               bvh_leaf_surface.p, static_cast<int>(Vs), 0, 64, st));
+            bvh_temp.alloc(bvh_temp_bytes);
+            bvh.n            = Vs;
+            bvh.keys         = bvh_keys.p;
+            bvh.keys_sorted  = bvh_keys_sorted.p;
+            bvh.leaf_in      = bvh_leaf_in.p;
+            bvh.leaf_surface = bvh_leaf_surface.p;
+            bvh.parent       = bvh_parent.p;
+            bvh.child        = bvh_child.p;
+            bvh.range_first  = bvh_range_first.p;
+            bvh.range_last   = bvh_range_last.p;
+            bvh.sphere       = bvh_sphere.p;
+            bvh.visits       = bvh_visits.p;
+            bvh.sdf          = sdf.p;
+            // quantisation box of the Morton codes: the rest shape, generously enlarged (tree quality only)
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int64_t i = 0; i < V; ++i)
+                for (int k = 0; k < 3; ++k)
+                {
+                    lo[k] = std::min(lo[k], h.x0[3 * i + k]);
+                    hi[k] = std::max(hi[k], h.x0[3 * i + k]);
+                }
+            for (int k = 0; k < 3; ++k)
+            {
+                double const ext  = std::max(hi[k] - lo[k], 1e-6);
+                bvh.lo[k]         = R(lo[k] - ext);
+                bvh.inv_extent[k] = R(1.0 / (3.0 * ext));
+            }
+            d.surf_cull = surf_cull.p;
+        }
 
         if (Vs > 0)
         {
@@ -381,6 +442,18 @@ struct Engine final : EngineBase
             if (!collide)
                 return;
             CK(cudaMemsetAsync(d.contact_count, 0, sizeof(uint32_t), st));
+            if (d.surf_cull)
+            { // broadphase: keys -> sort -> radix tree -> bounding spheres -> per-leaf ancestor walk
+                int const n = static_cast<int>(bvh.n);
+                k_bvh_keys<R><<<gridS, 256, 0, st>>>(d, bvh);
+                CK(cub::DeviceRadixSort::SortPairs(bvh_temp.p, bvh_temp_bytes, bvh.keys, bvh.keys_sorted, bvh.leaf_in,
+                                                   bvh.leaf_surface, n, 0, 64, st));
+                if (n > 1)
+                    k_bvh_tree<R><<<static_cast<unsigned>((n - 1 + 255) / 256), 256, 0, st>>>(bvh);
+                k_bvh_fit<R><<<gridS, 256, 0, st>>>(d, bvh);
+                k_bvh_cull<R><<<gridS, 256, 0, st>>>(d, bvh, surf_cull.p);
+                launched += n > 1 ? 4 : 3;
+            }
             k_detect_all<R><<<gridS, 256, 0, st>>>(d);
             ++launched;
         };
@@ -788,6 +861,16 @@ int sbsb200_set_schedule(sbsb200_ctx* c, int schedule)
     if (c->finalized)
         return fail(c, SBSB200_ERR_STATE, "set_schedule must precede finalize");
     c->schedule_request = schedule;
+    return SBSB200_OK;
+}
+
+int sbsb200_set_broadphase(sbsb200_ctx* c, int mode)
+{
+    if (!c || (mode != SBSB200_BROADPHASE_NONE && mode != SBSB200_BROADPHASE_BVH))
+        return fail(c, SBSB200_ERR_INVALID, "bad broadphase mode");
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "set_broadphase must precede finalize");
+    c->broadphase = mode;
     return SBSB200_OK;
 }
 

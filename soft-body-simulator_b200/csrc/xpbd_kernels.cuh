@@ -40,6 +40,7 @@ struct DeviceScene
     {
         int32_t kind, body;
         R a[3], b[3], r;
+        R vmin[3], vmax[3]; // englobing volume() box (collision_model.h:39-40), used by the BVH broadphase
     };
     Sdf const* sdf;
     int64_t contact_cap;
@@ -47,6 +48,7 @@ struct DeviceScene
     Real4<R>* contact_q;   // (qs.x, qs.y, qs.z, lambda)
     Real4<R>* contact_n;   // (n.x, n.y, n.z, sdf body as value)
     uint32_t* contact_count;
+    uint32_t const* surf_cull; // BVH broadphase: bit k set = SDF k never reaches this surface vertex (null: off)
     R collision_alpha;
 };
 
@@ -311,15 +313,17 @@ __global__ void __launch_bounds__(256) k_detect_all(DeviceScene<R> s)
     int32_t n_mine    = 0;
     Vec3<R> p         = {R(0), R(0), R(0)};
     int32_t body      = -1;
+    uint32_t culled   = 0u;
     if (valid)
     {
         Real4<R> const q = ld4(&s.surf_pos[i]);
         p                = {q.x, q.y, q.z};
         body             = s.surf_body[i];
+        culled = s.surf_cull ? s.surf_cull[i] : 0u;
         for (int32_t k = 0; k < s.n_sdf; ++k)
         {
             Vec3<R> g;
-            if (sdf_eval<R>(s.sdf[k], p, g) < R(0))
+            if (!(k < 32 && (culled >> k & 1u)) && sdf_eval<R>(s.sdf[k], p, g) < R(0))
                 ++n_mine;
         }
     }
@@ -348,6 +352,8 @@ __global__ void __launch_bounds__(256) k_detect_all(DeviceScene<R> s)
     for (int32_t k = 0; k < s.n_sdf; ++k)
     {
         Vec3<R> g;
+        if (k < 32 && (culled >> k & 1u))
+            continue;
         R const sd = sdf_eval<R>(s.sdf[k], p, g);
         if (!(sd < R(0)))
             continue;
