@@ -347,7 +347,8 @@ def main():
             "config": {"workload": scene.name, "tets_per_gpu": scene.n_tets // (world if decomposed else 1),
                        "vertices_per_gpu": nVtot // (world if decomposed else 1),
                        "substeps": S, "iterations": K, "dt": scene.dt,
-                       "detection": "every substep" if scene.detect_every_substep else "once per frame",
+                       "detection": ("every substep" if scene.detect_every_substep else "once per frame")
+                       + (", BVH broadphase" if scene.broadphase else ""),
                        "colours": stats0["n_green_colours"], "schedule": sched,
                        "regions": stats0["n_regions"], "shared_vertices": stats0["n_interface_vertices"],
                        "parallelism": ("one body decomposed over %d GPUs, shared vertices pushed to peer memory by "

@@ -6,15 +6,17 @@
 // volume() box (bvh_model.cpp:47-64) — and every vertex of a visited leaf goes to the narrowphase
 // (:66-96).  So a vertex is examined iff EVERY proper ancestor of its leaf passes that test.
 //
-// Here: a linear BVH (Karras 2012) rebuilt on the device at every detection.  Keys are
-// (body, 30-bit Morton code of the surface copy); one radix sort; the radix tree over the sorted
-// keys contains one subtree per body (the body id is the key's prefix), nodes spanning several
-// bodies always pass; bounding spheres are fitted bottom-up (sphere of two spheres); and the
-// traversal is turned inside out: one thread per surface vertex walks from its leaf to the root
-// and gives up at the first ancestor that fails the test — no queue, no stack, fully parallel.
-// Tree shape and spheres differ from Discregrid's (which is not pinned), so the visited set can
-// only be compared where it does not depend on them: bodies inside the volume box (everything
-// penetrating is found) and bodies whose root sphere misses it (nothing is found).
+// Here: a linear BVH in its implicit form.  Once per frame the surface vertices are sorted by
+// (body, 30-bit Morton code of the surface copy) with one radix sort; the hierarchy is the
+// complete binary tree over that order (node j of level l covers the sorted leaves
+// [j 2^l, (j+1) 2^l) — spatially compact because of the Morton order), so it needs no pointers.
+// At every detection the bounding spheres are refitted bottom-up (sphere of two spheres; 256 leaves
+// per CTA in shared memory, then the few upper levels), nodes that span several bodies are marked
+// and always pass (the reference has one tree per body), and the traversal is turned inside out:
+// one thread per surface vertex tests the ancestors of its leaf — all loads independent, no
+// queue, no stack.  Tree shape and spheres differ from Discregrid's (which is not pinned), so
+// the visited set can only be compared where it does not depend on them: bodies inside the
+// volume box (everything penetrating is found) and bodies whose top sphere misses it (nothing).
 #pragma once
 
 #include "xpbd_kernels.cuh"
@@ -22,6 +24,9 @@
 #include <cub/device/device_radix_sort.cuh>
 
 namespace sbsb200 {
+
+constexpr int kBvhMaxLevels = 32;
+constexpr int kBvhLeafBlock = 256; // leaves fitted per CTA (levels 1..8 in shared memory)
 
 template <typename R>
 struct BvhView
@@ -31,12 +36,13 @@ struct BvhView
     uint64_t* keys_sorted;
     uint32_t* leaf_in;        // 0..n-1
     uint32_t* leaf_surface;   // sorted position -> surface vertex index
-    int32_t* parent;          // [2n-1]: internal nodes 0..n-2, leaves n-1..2n-2
-    int32_t* child;           // [2(n-1)] left, right of internal node i (node ids as in parent[])
-    uint32_t* range_first;    // [n-1] first / last sorted position covered by internal node i
-    uint32_t* range_last;
-    Real4<R>* sphere;         // [2n-1] (centre, radius)
-    uint32_t* visits;         // [n-1] arrival counter of the bottom-up pass
+    uint32_t* leaf_of_surface; // and back
+    uint32_t* done_counter;   // CTAs of the fit kernel that finished the lower levels
+    Real4<R>* sphere;         // nodes of level l >= 1 at sphere[level_offset[l] + j]: (centre, radius);
+                              // radius < 0: the node spans several bodies and always passes
+    int32_t n_levels;         // levels 1 .. n_levels - 1 exist (level 0 = the leaves themselves)
+    int64_t level_offset[kBvhMaxLevels];
+    int64_t level_count[kBvhMaxLevels];
     R lo[3], inv_extent[3];   // quantisation box of the Morton codes (tree quality only)
     typename DeviceScene<R>::Sdf const* sdf;
 };
@@ -82,60 +88,6 @@ __global__ void __launch_bounds__(256) k_bvh_keys(DeviceScene<R> s, BvhView<R> b
     b.leaf_in[i] = static_cast<uint32_t>(i);
 }
 
-// length of the common prefix of the keys at sorted positions i and j (ties broken by position)
-__device__ __forceinline__ int bvh_delta(uint64_t const* keys, int64_t n, int64_t i, int64_t j)
-{
-    if (j < 0 || j >= n)
-        return -1;
-    uint64_t const a = keys[i], c = keys[j];
-    if (a == c)
-        return 64 + __clzll(static_cast<long long>(static_cast<uint64_t>(i) ^ static_cast<uint64_t>(j)));
-    return __clzll(static_cast<long long>(a ^ c));
-}
-
-// Karras, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees" (2012): internal node i
-template <typename R>
-__global__ void __launch_bounds__(256) k_bvh_tree(BvhView<R> b)
-{
-    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    int64_t const n = b.n;
-    if (i >= n - 1)
-        return;
-    uint64_t const* k = b.keys_sorted;
-    int const d       = bvh_delta(k, n, i, i + 1) - bvh_delta(k, n, i, i - 1) >= 0 ? 1 : -1;
-    int const dmin    = bvh_delta(k, n, i, i - d);
-    int64_t lmax      = 2;
-    while (bvh_delta(k, n, i, i + lmax * d) > dmin)
-        lmax *= 2;
-    int64_t l = 0;
-    for (int64_t t = lmax / 2; t >= 1; t /= 2)
-        if (bvh_delta(k, n, i, i + (l + t) * d) > dmin)
-            l += t;
-    int64_t const j   = i + l * d;
-    int const dnode   = bvh_delta(k, n, i, j);
-    int64_t split     = 0;
-    for (int64_t t = (l + 1) / 2;; t = (t + 1) / 2)
-    {
-        if (bvh_delta(k, n, i, i + (split + t) * d) > dnode)
-            split += t;
-        if (t <= 1)
-            break;
-    }
-    int64_t const gamma = i + split * d + (d < 0 ? -1 : 0);
-    int64_t const first = i < j ? i : j, last = i < j ? j : i;
-    int32_t const left  = static_cast<int32_t>(first == gamma ? (n - 1) + gamma : gamma);
-    int32_t const right = static_cast<int32_t>(last == gamma + 1 ? (n - 1) + gamma + 1 : gamma + 1);
-    b.child[2 * i]      = left;
-    b.child[2 * i + 1]  = right;
-    b.parent[left]      = static_cast<int32_t>(i);
-    b.parent[right]     = static_cast<int32_t>(i);
-    b.range_first[i]    = static_cast<uint32_t>(first);
-    b.range_last[i]     = static_cast<uint32_t>(last);
-    b.visits[i]         = 0u;
-    if (i == 0)
-        b.parent[0] = -1;
-}
-
 template <typename R>
 __device__ __forceinline__ Real4<R> sphere_of_two(Real4<R> a, Real4<R> c)
 {
@@ -150,31 +102,96 @@ __device__ __forceinline__ Real4<R> sphere_of_two(Real4<R> a, Real4<R> c)
     return Real4<R>{a.x + dx * t, a.y + dy * t, a.z + dz * t, r};
 }
 
-// bottom-up fit: the second thread to arrive at a node fits it from its two children
+// sphere of a node from its two children; a child that does not exist (odd count) is skipped, a
+// child or a pair that spans several bodies makes the node "always pass" (radius -1)
 template <typename R>
-__global__ void __launch_bounds__(256) k_bvh_fit(DeviceScene<R> s, BvhView<R> b)
+__device__ __forceinline__ Real4<R> fit_pair(Real4<R> a, uint32_t body_a, bool has_b, Real4<R> c, uint32_t body_c,
+                                             uint32_t& body_out)
 {
-    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    int64_t const n = b.n;
-    if (i >= n)
-        return;
-    Real4<R> const p = ld4(&s.surf_pos[b.leaf_surface[i]]);
-    int32_t node     = static_cast<int32_t>(n - 1 + i);
-    b.sphere[node]   = Real4<R>{p.x, p.y, p.z, R(0)};
-    if (n == 1)
-        return;
-    for (;;)
+    body_out = body_a;
+    if (!has_b)
+        return a;
+    if (a.w < R(0) || c.w < R(0) || body_a != body_c)
     {
-        __threadfence();
-        node = b.parent[node];
-        if (node < 0 || atomicAdd(&b.visits[node], 1u) == 0u)
-            return; // the sibling subtree is not done yet: its thread continues upwards
-        __threadfence();
-        // written by another SM a moment ago: read from L2
-        Real4<R> const a = ld4_l2(&b.sphere[b.child[2 * node]]);
-        Real4<R> const c = ld4_l2(&b.sphere[b.child[2 * node + 1]]);
-        st4(&b.sphere[node], sphere_of_two<R>(a, c));
+        body_out = 0xffffffffu;
+        return Real4<R>{a.x, a.y, a.z, R(-1)};
     }
+    return sphere_of_two<R>(a, c);
+}
+
+// Refit of every bounding sphere.  Levels 1 .. 8: every CTA fits the subtree over its 256 consecutive
+// leaves in shared memory.  Levels 9 ..: the LAST CTA to finish does them, level by level (at most
+// n / 256 nodes at level 8), so the refit is one launch.
+template <typename R>
+__global__ void __launch_bounds__(kBvhLeafBlock) k_bvh_fit(DeviceScene<R> s, BvhView<R> b)
+{
+    __shared__ Real4<R> sph[kBvhLeafBlock];
+    __shared__ uint32_t body[kBvhLeafBlock];
+    __shared__ uint32_t ticket;
+    int64_t const base = blockIdx.x * static_cast<int64_t>(kBvhLeafBlock);
+    int64_t const i    = base + threadIdx.x;
+    if (i < b.n)
+    {
+        uint32_t const surface        = b.leaf_surface[i];
+        Real4<R> const p              = ld4(&s.surf_pos[surface]);
+        sph[threadIdx.x]              = Real4<R>{p.x, p.y, p.z, R(0)};
+        body[threadIdx.x]             = static_cast<uint32_t>(b.keys_sorted[i] >> 32);
+        b.leaf_of_surface[surface]    = static_cast<uint32_t>(i);
+    }
+    __syncthreads();
+    int64_t count = b.n - base < kBvhLeafBlock ? b.n - base : kBvhLeafBlock; // nodes of the level below, in this CTA
+    for (int l = 1; l <= 8 && l < b.n_levels; ++l)
+    {
+        int64_t const here = (count + 1) / 2;
+        Real4<R> node;
+        uint32_t nb     = 0;
+        bool const mine = threadIdx.x < here;
+        if (mine)
+        {
+            int const right = 2 * threadIdx.x + 1 < kBvhLeafBlock ? 2 * threadIdx.x + 1 : 0;
+            node = fit_pair<R>(sph[2 * threadIdx.x], body[2 * threadIdx.x], 2 * threadIdx.x + 1 < count, sph[right],
+                               body[right], nb);
+        }
+        __syncthreads();
+        if (mine)
+        {
+            sph[threadIdx.x]  = node;
+            body[threadIdx.x] = nb;
+            st4(&b.sphere[b.level_offset[l] + (base >> l) + threadIdx.x], node);
+        }
+        __syncthreads();
+        count = here;
+    }
+    if (b.n_levels <= 9)
+        return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        ticket = atomicAdd(b.done_counter, 1u);
+    __syncthreads();
+    if (ticket != gridDim.x - 1)
+        return;
+    __threadfence();
+    for (int l = 9; l < b.n_levels; ++l)
+    {
+        int64_t const below = b.level_count[l - 1];
+        for (int64_t j = threadIdx.x; j < b.level_count[l]; j += blockDim.x)
+        {
+            Real4<R> const a = ld4_l2(&b.sphere[b.level_offset[l - 1] + 2 * j]);
+            bool const has_c = 2 * j + 1 < below;
+            Real4<R> const c = has_c ? ld4_l2(&b.sphere[b.level_offset[l - 1] + 2 * j + 1]) : a;
+            // the body of a subtree: of its first leaf; several bodies are already marked by radius < 0,
+            // two single-body children of different bodies are told apart by their first leaves
+            uint32_t const body_a = static_cast<uint32_t>(b.keys_sorted[(2 * j) << (l - 1)] >> 32);
+            uint32_t const body_c = has_c ? static_cast<uint32_t>(b.keys_sorted[(2 * j + 1) << (l - 1)] >> 32) : body_a;
+            uint32_t nb;
+            st4(&b.sphere[b.level_offset[l] + j], fit_pair<R>(a, body_a, has_c, c, body_c, nb));
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        *b.done_counter = 0u;
 }
 
 // is_sphere_colliding_with_sdf (bvh_model.cpp:47-64)
@@ -196,33 +213,111 @@ __device__ __forceinline__ bool sphere_reaches_sdf(typename DeviceScene<R>::Sdf 
     return dist2 < sph.w * sph.w;
 }
 
-// Broadphase: bit k of cull[i] is set when the traversal against SDF k never reaches the leaf of
-// surface vertex i.  One thread per surface vertex (leaf), walking its ancestors.
+// Broadphase: bit k of the result is set when the traversal against SDF k never reaches the leaf.
+// The ancestors of the leaf are tested from kBvhFirstLevel upwards: the reference's KD-tree stops
+// splitting at about ten points per leaf, so its smallest spheres correspond to our level 3
+// (8 leaves); the levels below only feed the fit.
+constexpr int kBvhFirstLevel = 3;
+
 template <typename R>
-__global__ void __launch_bounds__(256) k_bvh_cull(DeviceScene<R> s, BvhView<R> b, uint32_t* cull)
+__device__ __forceinline__ uint32_t bvh_cull_mask(DeviceScene<R> const& s, BvhView<R> const& b, int64_t leaf)
 {
-    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    int64_t const n = b.n;
-    if (i >= n)
-        return;
-    uint32_t const surface = b.leaf_surface[i];
-    uint32_t const body    = static_cast<uint32_t>(b.keys_sorted[i] >> 32);
-    uint32_t mask          = 0u;
-    for (int32_t k = 0; k < s.n_sdf && k < 32; ++k)
+    uint32_t mask = 0u;
+    bool above    = false; // reached a node that spans several bodies: above the reference's per-body trees
+    for (int l0 = kBvhFirstLevel; l0 < b.n_levels && !above; l0 += 8)
     {
-        bool visited = true;
-        for (int32_t node = n > 1 ? b.parent[n - 1 + i] : -1; node >= 0 && visited; node = b.parent[node])
-        {
-            // a node that spans several bodies is above every per-body tree of the reference
-            if (static_cast<uint32_t>(b.keys_sorted[b.range_first[node]] >> 32) != body ||
-                static_cast<uint32_t>(b.keys_sorted[b.range_last[node]] >> 32) != body)
-                break;
-            visited = sphere_reaches_sdf<R>(s.sdf[k], ld4(&b.sphere[node]));
-        }
-        if (!visited)
-            mask |= 1u << k;
+        Real4<R> sph[8]; // eight ancestors at a time: their loads are independent
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (l0 + j < b.n_levels)
+                sph[j] = ld4(&b.sphere[b.level_offset[l0 + j] + (leaf >> (l0 + j))]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (l0 + j < b.n_levels && !above)
+            {
+                if (sph[j].w < R(0))
+                    above = true;
+                else
+                    for (int32_t k = 0; k < s.n_sdf && k < 32; ++k)
+                        if (!(mask >> k & 1u) && !sphere_reaches_sdf<R>(s.sdf[k], sph[j]))
+                            mask |= 1u << k;
+            }
     }
-    cull[surface] = mask;
+    return mask;
 }
+
+__device__ __forceinline__ float as_real(float, int v) { return __int_as_float(v); }
+__device__ __forceinline__ double as_real(double, int v) { return static_cast<double>(v); }
+
+// Narrowphase + contact handling (bvh_model.cpp:66-96, xpbd/contact_handler.cpp:14-54):
+// thread per surface vertex, every SDF in body order, warp-aggregated append so that the
+// contacts of one vertex are contiguous and ordered by SDF body.
+template <typename R>
+__global__ void __launch_bounds__(256) k_detect_all(DeviceScene<R> s, BvhView<R> b)
+{
+    int64_t const i   = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    bool const valid  = i < s.n_surface;
+    int32_t n_mine    = 0;
+    Vec3<R> p         = {R(0), R(0), R(0)};
+    int32_t body      = -1;
+    uint32_t culled   = 0u;
+    if (valid)
+    {
+        Real4<R> const q = ld4(&s.surf_pos[i]);
+        p                = {q.x, q.y, q.z};
+        body             = s.surf_body[i];
+        culled = b.n > 0 ? bvh_cull_mask<R>(s, b, b.leaf_of_surface[i]) : 0u; // b.n == 0: no broadphase
+        for (int32_t k = 0; k < s.n_sdf; ++k)
+        {
+            Vec3<R> g;
+            if (!(k < 32 && (culled >> k & 1u)) && sdf_eval<R>(s.sdf[k], p, g) < R(0))
+                ++n_mine;
+        }
+    }
+    // warp-aggregated reservation
+    unsigned const lane = threadIdx.x & 31u;
+    int32_t incl        = n_mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        int32_t const o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= static_cast<unsigned>(d))
+            incl += o;
+    }
+    int32_t const total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base       = 0;
+    if (lane == 31 && total > 0)
+        base = atomicAdd(s.contact_count, static_cast<uint32_t>(total));
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (valid)
+        s.surf_first[i] = n_mine > 0 ? base + static_cast<uint32_t>(incl - n_mine) : 0xffffffffu;
+    if (!valid || n_mine == 0)
+        return;
+    uint32_t slot      = base + static_cast<uint32_t>(incl - n_mine);
+    uint32_t const gv  = s.surf_v[i];
+    bool first         = true;
+    for (int32_t k = 0; k < s.n_sdf; ++k)
+    {
+        Vec3<R> g;
+        if (k < 32 && (culled >> k & 1u))
+            continue;
+        R const sd = sdf_eval<R>(s.sdf[k], p, g);
+        if (!(sd < R(0)))
+            continue;
+        R const inv       = R(1) / sqrt_(dot(g, g)); // grad.normalized() (bvh_model.cpp:82)
+        Vec3<R> const n   = {g.x * inv, g.y * inv, g.z * inv};
+        R const a         = abs_(sd);
+        if (slot < s.contact_cap)
+        {
+            s.contact_v[slot] = gv | (first ? 0x80000000u : 0u);
+            st4(&s.contact_q[slot], Real4<R>{p.x + a * n.x, p.y + a * n.y, p.z + a * n.z, R(0)}); // :83-84
+            st4(&s.contact_n[slot], Real4<R>{n.x, n.y, n.z, as_real(R(0), s.sdf[k].body)});
+        }
+        first = false;
+        ++slot;
+    }
+    (void)body;
+}
+
 
 } // namespace sbsb200

@@ -140,8 +140,7 @@ struct Engine final : EngineBase
     // BVH broadphase (bvh.cuh)
     BvhView<R> bvh{};
     DevBuf<uint64_t> bvh_keys, bvh_keys_sorted;
-    DevBuf<uint32_t> bvh_leaf_in, bvh_leaf_surface, bvh_range_first, bvh_range_last, bvh_visits, surf_cull;
-    DevBuf<int32_t> bvh_parent, bvh_child;
+    DevBuf<uint32_t> bvh_leaf_in, bvh_leaf_surface, bvh_leaf_of_surface, bvh_counter;
     DevBuf<Real4<R>> bvh_sphere;
     DevBuf<unsigned char> bvh_temp;
     size_t bvh_temp_bytes = 0;
@@ -352,7 +351,6 @@ struct Engine final : EngineBase
         d.contact_n       = contact_n.p;
         d.contact_count   = contact_count.p;
         d.collision_alpha = R(c.collision_alpha);
-        d.surf_cull       = nullptr;
         c.n_surface       = Vs;
         if (c.broadphase == SBSB200_BROADPHASE_BVH && Vs > 0 && !hs.empty())
         { // linear BVH over the surface vertices, rebuilt at every detection
@@ -361,13 +359,23 @@ struct Engine final : EngineBase
             bvh_keys_sorted.alloc(n);
             bvh_leaf_in.alloc(n);
             bvh_leaf_surface.alloc(n);
-            bvh_parent.alloc(2 * n);
-            bvh_child.alloc(2 * n);
-            bvh_range_first.alloc(n);
-            bvh_range_last.alloc(n);
-            bvh_visits.alloc(n);
-            bvh_sphere.alloc(2 * n);
-            surf_cull.alloc(n);
+            bvh_leaf_of_surface.alloc(n);
+            bvh_counter.alloc(1);
+            CK(cudaMemsetAsync(bvh_counter.p, 0, sizeof(uint32_t), st));
+            // implicit complete binary tree over the sorted leaves: level l has ceil(n / 2^l) nodes
+            int64_t offset = 0, count = Vs;
+            bvh.n_levels   = 1;
+            for (int l = 1; l < kBvhMaxLevels && count > 1; ++l)
+            {
+                count               = (count + 1) / 2;
+                bvh.level_offset[l] = offset;
+                bvh.level_count[l]  = count;
+                offset += count;
+                bvh.n_levels = l + 1;
+            }
+            bvh.level_offset[0] = 0;
+            bvh.level_count[0]  = Vs;
+            bvh_sphere.alloc(static_cast<size_t>(std::max<int64_t>(offset, 1)));
             CK(cub::DeviceRadixSort::SortPairs(nullptr, bvh_temp_bytes, bvh_keys.p, bvh_keys_sorted.p, bvh_leaf_in.p,
                                                bvh_leaf_surface.p, static_cast<int>(Vs), 0, 64, st));
             bvh_temp.alloc(bvh_temp_bytes);
@@ -376,12 +384,9 @@ struct Engine final : EngineBase
             bvh.keys_sorted  = bvh_keys_sorted.p;
             bvh.leaf_in      = bvh_leaf_in.p;
             bvh.leaf_surface = bvh_leaf_surface.p;
-            bvh.parent       = bvh_parent.p;
-            bvh.child        = bvh_child.p;
-            bvh.range_first  = bvh_range_first.p;
-            bvh.range_last   = bvh_range_last.p;
+            bvh.leaf_of_surface = bvh_leaf_of_surface.p;
+            bvh.done_counter = bvh_counter.p;
             bvh.sphere       = bvh_sphere.p;
-            bvh.visits       = bvh_visits.p;
             bvh.sdf          = sdf.p;
             // quantisation box of the Morton codes: the rest shape, generously enlarged (tree quality only)
             double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -397,7 +402,6 @@ struct Engine final : EngineBase
                 bvh.lo[k]         = R(lo[k] - ext);
                 bvh.inv_extent[k] = R(1.0 / (3.0 * ext));
             }
-            d.surf_cull = surf_cull.p;
         }
 
         if (Vs > 0)
@@ -438,23 +442,28 @@ struct Engine final : EngineBase
         unsigned const gridC = static_cast<unsigned>((d.contact_cap + 255) / 256);
         d.collision_alpha    = R(c.collision_alpha);
 
+        bool bvh_topology_built = false; // rebuilt once per frame, refitted at every detection
         auto detect_now = [&] {
             if (!collide)
                 return;
             CK(cudaMemsetAsync(d.contact_count, 0, sizeof(uint32_t), st));
-            if (d.surf_cull)
-            { // broadphase: keys -> sort -> radix tree -> bounding spheres -> per-leaf ancestor walk
+            if (bvh.n > 0)
+            { // broadphase: (once per frame: keys -> sort) -> refit of the bounding spheres; the cull itself
+              // is the ancestor walk inside k_detect_all
+              // (the reference builds its KD-tree once and refits every sphere per frame, bvh_model.cpp:102-126)
                 int const n = static_cast<int>(bvh.n);
-                k_bvh_keys<R><<<gridS, 256, 0, st>>>(d, bvh);
-                CK(cub::DeviceRadixSort::SortPairs(bvh_temp.p, bvh_temp_bytes, bvh.keys, bvh.keys_sorted, bvh.leaf_in,
-                                                   bvh.leaf_surface, n, 0, 64, st));
-                if (n > 1)
-                    k_bvh_tree<R><<<static_cast<unsigned>((n - 1 + 255) / 256), 256, 0, st>>>(bvh);
-                k_bvh_fit<R><<<gridS, 256, 0, st>>>(d, bvh);
-                k_bvh_cull<R><<<gridS, 256, 0, st>>>(d, bvh, surf_cull.p);
-                launched += n > 1 ? 4 : 3;
+                if (!bvh_topology_built)
+                {
+                    k_bvh_keys<R><<<gridS, 256, 0, st>>>(d, bvh);
+                    CK(cub::DeviceRadixSort::SortPairs(bvh_temp.p, bvh_temp_bytes, bvh.keys, bvh.keys_sorted,
+                                                       bvh.leaf_in, bvh.leaf_surface, n, 0, 64, st));
+                    ++launched;
+                    bvh_topology_built = true;
+                }
+                k_bvh_fit<R><<<static_cast<unsigned>((n + kBvhLeafBlock - 1) / kBvhLeafBlock), kBvhLeafBlock, 0, st>>>(d, bvh);
+                ++launched;
             }
-            k_detect_all<R><<<gridS, 256, 0, st>>>(d);
+            k_detect_all<R><<<gridS, 256, 0, st>>>(d, bvh);
             ++launched;
         };
         if (detect == SBSB200_DETECT_PER_FRAME)

@@ -48,7 +48,6 @@ struct DeviceScene
     Real4<R>* contact_q;   // (qs.x, qs.y, qs.z, lambda)
     Real4<R>* contact_n;   // (n.x, n.y, n.z, sdf body as value)
     uint32_t* contact_count;
-    uint32_t const* surf_cull; // BVH broadphase: bit k set = SDF k never reaches this surface vertex (null: off)
     R collision_alpha;
 };
 
@@ -297,79 +296,6 @@ __device__ __forceinline__ R sdf_eval(typename DeviceScene<R>::Sdf const& f, Vec
     }
     g = {gg[0], gg[1], gg[2]};
     return sd;
-}
-
-__device__ __forceinline__ float as_real(float, int v) { return __int_as_float(v); }
-__device__ __forceinline__ double as_real(double, int v) { return static_cast<double>(v); }
-
-// Narrowphase + contact handling (bvh_model.cpp:66-96, xpbd/contact_handler.cpp:14-54):
-// thread per surface vertex, every SDF in body order, warp-aggregated append so that the
-// contacts of one vertex are contiguous and ordered by SDF body.
-template <typename R>
-__global__ void __launch_bounds__(256) k_detect_all(DeviceScene<R> s)
-{
-    int64_t const i   = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    bool const valid  = i < s.n_surface;
-    int32_t n_mine    = 0;
-    Vec3<R> p         = {R(0), R(0), R(0)};
-    int32_t body      = -1;
-    uint32_t culled   = 0u;
-    if (valid)
-    {
-        Real4<R> const q = ld4(&s.surf_pos[i]);
-        p                = {q.x, q.y, q.z};
-        body             = s.surf_body[i];
-        culled = s.surf_cull ? s.surf_cull[i] : 0u;
-        for (int32_t k = 0; k < s.n_sdf; ++k)
-        {
-            Vec3<R> g;
-            if (!(k < 32 && (culled >> k & 1u)) && sdf_eval<R>(s.sdf[k], p, g) < R(0))
-                ++n_mine;
-        }
-    }
-    // warp-aggregated reservation
-    unsigned const lane = threadIdx.x & 31u;
-    int32_t incl        = n_mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
-    {
-        int32_t const o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= static_cast<unsigned>(d))
-            incl += o;
-    }
-    int32_t const total = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t base       = 0;
-    if (lane == 31 && total > 0)
-        base = atomicAdd(s.contact_count, static_cast<uint32_t>(total));
-    base = __shfl_sync(0xffffffffu, base, 31);
-    if (valid)
-        s.surf_first[i] = n_mine > 0 ? base + static_cast<uint32_t>(incl - n_mine) : 0xffffffffu;
-    if (!valid || n_mine == 0)
-        return;
-    uint32_t slot      = base + static_cast<uint32_t>(incl - n_mine);
-    uint32_t const gv  = s.surf_v[i];
-    bool first         = true;
-    for (int32_t k = 0; k < s.n_sdf; ++k)
-    {
-        Vec3<R> g;
-        if (k < 32 && (culled >> k & 1u))
-            continue;
-        R const sd = sdf_eval<R>(s.sdf[k], p, g);
-        if (!(sd < R(0)))
-            continue;
-        R const inv       = R(1) / sqrt_(dot(g, g)); // grad.normalized() (bvh_model.cpp:82)
-        Vec3<R> const n   = {g.x * inv, g.y * inv, g.z * inv};
-        R const a         = abs_(sd);
-        if (slot < s.contact_cap)
-        {
-            s.contact_v[slot] = gv | (first ? 0x80000000u : 0u);
-            st4(&s.contact_q[slot], Real4<R>{p.x + a * n.x, p.y + a * n.y, p.z + a * n.z, R(0)}); // :83-84
-            st4(&s.contact_n[slot], Real4<R>{n.x, n.y, n.z, as_real(R(0), s.sdf[k].body)});
-        }
-        first = false;
-        ++slot;
-    }
-    (void)body;
 }
 
 // collision_constraint.cpp:21-48.  The thread owning the first contact of a vertex walks the

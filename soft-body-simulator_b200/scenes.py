@@ -76,6 +76,7 @@ class Scene:
     iterations: int = 10
     detect_every_substep: bool = False
     collision_compliance: float = 1e-8
+    broadphase: int = 0                  # 1 = GPU-built BVH (sbsb200_set_broadphase)
 
     @property
     def n_tets(self):
@@ -96,6 +97,8 @@ class Scene:
         """Create the scene on a backend (GPU Simulation or oracle World).  partition = (rank, world):
         this backend runs its share of the scene decomposed over `world` GPUs."""
         backend.set_collision_compliance(self.collision_compliance)
+        if self.broadphase and hasattr(backend, "set_broadphase"):
+            backend.set_broadphase(self.broadphase)
         if partition is not None:
             backend.set_partition(*partition)
         ids = []
@@ -162,13 +165,14 @@ def config2(W=21, H=21, D=51, seed=2):
 
 
 def config3(W=41, H=51, D=101, seed=3, radius=30.0, gap=-0.3):
-    """Block dropped on an analytic sphere + floor, detection every substep."""
+    """Block dropped on an analytic sphere + floor; BVH broadphase and detection every substep."""
     ext = (np.array([W, H, D]) - 1) * _PRESTRAIN
     centre = np.array([ext[0] / 2, -radius, ext[2] / 2])
     body = prestrained_bar(W, H, D, seed, translate=(0.0, gap, 0.0))
     sphere = Sdf("sphere", tuple(centre), (radius, 0.0, 0.0), _BIG)
     floor = Sdf("plane", (0.0, 1.0, 0.0), (0.0, -2.0 * radius, 0.0), _BIG)
-    return Scene("config3_block_%dx%dx%d" % (W, H, D), [body, sphere, floor], detect_every_substep=True)
+    return Scene("config3_block_%dx%dx%d" % (W, H, D), [body, sphere, floor], detect_every_substep=True,
+                 broadphase=1)
 
 
 def _random_rotation(seed):
