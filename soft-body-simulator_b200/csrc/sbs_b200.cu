@@ -10,6 +10,7 @@
 #include "xpbd_persistent.cuh"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -133,6 +134,8 @@ struct Engine final : EngineBase
     DevBuf<uint4> tet_v;
     DevBuf<uint2> dist_v;
     DevBuf<R> tet_lambda, dist_lambda;
+    DevBuf<uint8_t> tet_shape;       // rest-shape dictionary (persistent schedule): index per tet ...
+    DevBuf<Real4<R>> shape_records;  // ... into the distinct (r0, r1, r2) records
     DevBuf<uint32_t> surf_v, surf_first, contact_v, contact_count;
     DevBuf<int32_t> surf_body;
     DevBuf<typename DeviceScene<R>::Sdf> sdf;
@@ -251,6 +254,44 @@ struct Engine final : EngineBase
             else
                 matv = R(mi);
             r2[static_cast<size_t>(p)] = {R(inv[8]), R(V0), matv, R(0)};
+        }
+        { // rest-shape dictionary: distinct (DmInv, V0, material) records, bit for bit
+            std::map<std::array<R, 12>, uint32_t> index;
+            std::vector<uint8_t> shape(static_cast<size_t>(T), 0);
+            std::vector<Real4<R>> records;
+            bool small = true;
+            for (int64_t p = 0; p < T && small; ++p)
+            {
+                auto const& a0 = r0[static_cast<size_t>(p)];
+                auto const& a1 = r1[static_cast<size_t>(p)];
+                auto const& a2 = r2[static_cast<size_t>(p)];
+                std::array<R, 12> const key = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+                auto it = index.find(key);
+                if (it == index.end())
+                {
+                    if (index.size() >= static_cast<size_t>(kMaxShapes))
+                    {
+                        small = false;
+                        break;
+                    }
+                    it = index.emplace(key, static_cast<uint32_t>(index.size())).first;
+                    records.push_back(a0);
+                    records.push_back(a1);
+                    records.push_back(a2);
+                }
+                shape[static_cast<size_t>(p)] = static_cast<uint8_t>(it->second);
+            }
+            if (small && T > 0)
+            {
+                tet_shape.upload(shape, st);
+                shape_records.upload(records, st);
+                pp.d_tet_shape = tet_shape.p;
+                pp.d_shapes    = shape_records.p;
+                pp.n_shapes    = static_cast<int32_t>(index.size());
+                d.tet_shape    = tet_shape.p;
+                d.shapes       = shape_records.p;
+                d.n_shapes     = static_cast<int32_t>(index.size());
+            }
         }
         tet_v.upload(hv, st);
         tet_r0.upload(r0, st);
@@ -522,10 +563,15 @@ struct Engine final : EngineBase
                             for (int m = 0; m < 8; ++m)
                                 dc.n[m] = h2.n[m];
                             unsigned const g = static_cast<unsigned>((h2.n[0] + 127) / 128);
-                            if (c.any_damping)
-                                k_project_green<R, true><<<g, 128, 0, st>>>(d, dc, dt, first);
+                            size_t const dict_bytes = static_cast<size_t>(3 * d.n_shapes) * sizeof(Real4<R>);
+                            if (c.any_damping && d.n_shapes > 0)
+                                k_project_green<R, true, true><<<g, 128, dict_bytes, st>>>(d, dc, dt, first);
+                            else if (c.any_damping)
+                                k_project_green<R, true, false><<<g, 128, 0, st>>>(d, dc, dt, first);
+                            else if (d.n_shapes > 0)
+                                k_project_green<R, false, true><<<g, 128, dict_bytes, st>>>(d, dc, dt, first);
                             else
-                                k_project_green<R, false><<<g, 128, 0, st>>>(d, dc, dt, first);
+                                k_project_green<R, false, false><<<g, 128, 0, st>>>(d, dc, dt, first);
                             ++launched;
                         }
                     }
@@ -1025,12 +1071,10 @@ int sbsb200_finalize(sbsb200_ctx* c)
         // damping; distance constraints and beta != 0 (which needs xn in the projection) take
         // the per-colour kernels
         bool const persistent_ok = T > 0 && D == 0 && !c->any_damping;
-        // AUTO: the persistent region-resident kernel for connected meshes up to a few million tets
-        // (latency-bound: few clusters per colour and SM), the per-colour kernels in a CUDA graph for
-        // ensembles of small bodies and for very large meshes (throughput-bound) — measured on B200,
-        // profiles/r01_summary.md
+        // AUTO: the persistent region-resident kernel for connected meshes, the per-colour kernels in a
+        // CUDA graph for ensembles of small bodies — measured on B200, profiles/r01_summary.md
         bool const auto_persistent =
-            persistent_ok && T <= 4000000 && !PersistentPlan<float>::wants_region_per_body(h, c->sm_count);
+            persistent_ok && T <= 16000000 && !PersistentPlan<float>::wants_region_per_body(h, c->sm_count);
         c->schedule = c->schedule_request == SBSB200_SCHED_PERSISTENT                     ? SBSB200_SCHED_PERSISTENT
                       : c->schedule_request == SBSB200_SCHED_AUTO && auto_persistent ? SBSB200_SCHED_PERSISTENT
                                                                                      : SBSB200_SCHED_GRAPH;

@@ -23,6 +23,11 @@ struct DeviceScene
     Real4<R> const* tet_r1; // d11 d12 d20 d21
     Real4<R> const* tet_r2; // d22, signed V0, material id (as value), unused
     R* tet_lambda;
+    // rest-shape dictionary: meshes with few distinct (DmInv, V0, material) records — every lattice has
+    // ten — stream one byte per tet instead of 48 (n_shapes == 0: no dictionary)
+    uint8_t const* tet_shape;
+    Real4<R> const* shapes;    // [3 * n_shapes]: r0, r1, r2 of every distinct record
+    int32_t n_shapes;
     Real4<R> const* materials; // (mu, lambda, alpha, beta)
     // distance constraints, colour-major
     int64_t n_dist;
@@ -163,10 +168,18 @@ struct DevChunk
 // first + n[0] + .. + n[m-1] + i, so every pass over m is a coalesced sweep.  first_iteration
 // folds the lambda reset of constraint_t::prepare_for_projection (constraint.cpp:12-16) into the
 // first sweep.
-template <typename R, bool kDamped>
+template <typename R, bool kDamped, bool kDict>
 __global__ void __launch_bounds__(128)
 k_project_green(DeviceScene<R> s, DevChunk chunk, R dt, int first_iteration)
 {
+    extern __shared__ __align__(16) unsigned char dict_raw[];
+    Real4<R>* s_dict = reinterpret_cast<Real4<R>*>(dict_raw);
+    if (kDict)
+    {
+        for (int w = threadIdx.x; w < 3 * s.n_shapes; w += blockDim.x)
+            s_dict[w] = s.shapes[w];
+        __syncthreads();
+    }
     int32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= chunk.n[0])
         return;
@@ -179,9 +192,20 @@ k_project_green(DeviceScene<R> s, DevChunk chunk, R dt, int first_iteration)
         int64_t const t   = base + i;
         base += chunk.n[m];
         uint4 const v     = __ldg(&s.tet_v[t]);
-        Real4<R> const r0 = ld4_ro(&s.tet_r0[t]);
-        Real4<R> const r1 = ld4_ro(&s.tet_r1[t]);
-        Real4<R> const r2 = ld4_ro(&s.tet_r2[t]);
+        Real4<R> r0, r1, r2;
+        if (kDict)
+        {
+            int const sh = __ldg(&s.tet_shape[t]);
+            r0           = s_dict[3 * sh];
+            r1           = s_dict[3 * sh + 1];
+            r2           = s_dict[3 * sh + 2];
+        }
+        else
+        {
+            r0 = ld4_ro(&s.tet_r0[t]);
+            r1 = ld4_ro(&s.tet_r1[t]);
+            r2 = ld4_ro(&s.tet_r2[t]);
+        }
         Real4<R> p1 = ld4(&s.pos[v.x]), p2 = ld4(&s.pos[v.y]), p3 = ld4(&s.pos[v.z]), p4 = ld4(&s.pos[v.w]);
         Real4<R> const mat = ld4_ro(&s.materials[mat_index(r2.z)]);
         R lambda           = first_iteration ? R(0) : s.tet_lambda[t];

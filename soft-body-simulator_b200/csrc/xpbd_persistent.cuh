@@ -216,6 +216,11 @@ struct PersistentArgs
     int32_t const* region_order;   // CTA b runs region_order[b], [b + grid], ...; regions that share
                                    // vertices come first, one per CTA
     uint2 const* tet_slots;        // per tet (storage order): 4 x u16 slots into the shared vertex array
+    // rest-shape dictionary (kDict kernels): meshes with few distinct rest shapes — every lattice has ten —
+    // keep the (DmInv, V0, material) records in shared memory and stream one byte per tet instead of 48
+    uint8_t const* tet_shape;      // per tet: index into shapes
+    Real4<R> const* shapes;        // [3 * n_shapes]: r0, r1, r2 of every distinct record
+    int32_t n_shapes;
     // per fetch-list entry, [nvc/4][n_clusters] each (entry j of cluster q: component j%4 of [j/4][q]);
     // the mailbox of that entry is box[j * n_clusters + q]
     uint4 const* cl_meta;          // touch schedule (ClusterPlan::cl_meta), 0xffffffff = no entry
@@ -325,42 +330,62 @@ __device__ __forceinline__ bool project_vertex_contacts(DeviceScene<R> const& s,
     return moved;
 }
 
+constexpr int kMaxShapes = 256;
+
 // per-tet record as the projection consumes it
-template <typename R>
+template <typename R, bool kDict>
 struct TetRecord
 {
     uint2 slots;
     Real4<R> r0, r1, r2;
     R lambda;
 };
-
 template <typename R>
-__device__ __forceinline__ TetRecord<R> load_tet(PersistentArgs<R> const& a, int32_t t, int first_iteration)
+struct TetRecord<R, true>
 {
-    TetRecord<R> q;
-    q.slots  = __ldg(&a.tet_slots[t]);
-    q.r0     = ld4_ro(&a.s.tet_r0[t]);
-    q.r1     = ld4_ro(&a.s.tet_r1[t]);
-    q.r2     = ld4_ro(&a.s.tet_r2[t]);
+    uint2 slots;
+    uint32_t shape; // r0, r1, r2 come out of the shared-memory dictionary when the tet runs
+    R lambda;
+};
+
+template <typename R, bool kDict>
+__device__ __forceinline__ TetRecord<R, kDict> load_tet(PersistentArgs<R> const& a, int32_t t, int first_iteration)
+{
+    TetRecord<R, kDict> q;
+    q.slots = __ldg(&a.tet_slots[t]);
+    if constexpr (kDict)
+        q.shape = __ldg(&a.tet_shape[t]);
+    else
+    {
+        q.r0 = ld4_ro(&a.s.tet_r0[t]);
+        q.r1 = ld4_ro(&a.s.tet_r1[t]);
+        q.r2 = ld4_ro(&a.s.tet_r2[t]);
+    }
     q.lambda = first_iteration ? R(0) : a.s.tet_lambda[t];
     return q;
 }
 
 // What a thread keeps of a cluster between the moment it is prepared (head loaded, vertices fetched,
 // normally one step ahead) and the moment it runs.
-template <typename R>
+template <typename R, bool kDict>
 struct ClusterHead
 {
-    TetRecord<R> tet0;
+    TetRecord<R, kDict> tet0;
     R mu, lam, at; // material of the cluster's body; at = alpha / dt^2
 };
 
-template <typename R>
-__device__ __forceinline__ void load_cluster_head(ClusterHead<R>& h, PersistentArgs<R> const& a, DevChunk const& ch,
-                                                  int32_t i, int first_iteration)
+template <typename R, bool kDict>
+__device__ __forceinline__ void load_cluster_head(ClusterHead<R, kDict>& h, PersistentArgs<R> const& a,
+                                                  DevChunk const& ch, int32_t i, int first_iteration,
+                                                  Real4<R> const* s_dict)
 {
-    h.tet0             = load_tet<R>(a, ch.first + i, first_iteration);
-    Real4<R> const mat = ld4_ro(&a.s.materials[mat_index(h.tet0.r2.z)]);
+    h.tet0 = load_tet<R, kDict>(a, ch.first + i, first_iteration);
+    R mat_id;
+    if constexpr (kDict)
+        mat_id = s_dict[3 * h.tet0.shape + 2].z; // waits for the shape id: one L2 round trip, a step ahead
+    else
+        mat_id = h.tet0.r2.z;
+    Real4<R> const mat = ld4_ro(&a.s.materials[mat_index(mat_id)]);
     h.mu               = mat.x;
     h.lam              = mat.y;
     h.at               = mat.z / (a.dt * a.dt);
@@ -448,10 +473,11 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64
 
 // One cluster, fetched already: project its tets in order out of shared memory -> write back.
 // q = storage index of the cluster when it has a fetch list (part A), -1 otherwise.
-template <typename R, int NVC4, typename Stamp>
+template <typename R, int NVC4, bool kDict, typename Stamp>
 __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk const& ch, int32_t i, int64_t q,
-                                            ClusterHead<R> const& head, Real4<R>* sx, int first_iteration,
-                                            StepInfo const& si, Stamp&& stamp)
+                                            ClusterHead<R, kDict> const& head, Real4<R>* sx,
+                                            Real4<R> const* s_dict, int first_iteration, StepInfo const& si,
+                                            Stamp&& stamp)
 {
     DeviceScene<R> const& s = a.s;
     int const tid = threadIdx.x, nt = blockDim.x;
@@ -468,23 +494,36 @@ __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk
     int32_t n0 = ch.n[0], n1 = ch.n[1], n2 = ch.n[2], n3 = ch.n[3], n4 = ch.n[4], n5 = ch.n[5], n6 = ch.n[6],
             n7 = ch.n[7];
     int32_t t        = ch.first + i;
-    TetRecord<R> cur = head.tet0;
+    TetRecord<R, kDict> cur = head.tet0;
     int tslot        = 8;
     stamp(tslot++);
 #pragma unroll 1
     for (;;)
     {
         bool const more = i < n1;
-        TetRecord<R> nxt;
+        TetRecord<R, kDict> nxt;
         if (more)
-            nxt = load_tet<R>(a, t + n0, first_iteration);
+            nxt = load_tet<R, kDict>(a, t + n0, first_iteration);
         uint32_t const a1 = cur.slots.x & 0xffffu, a2 = cur.slots.x >> 16, a3 = cur.slots.y & 0xffffu,
                        a4 = cur.slots.y >> 16;
         Real4<R> p1 = sx[a1], p2 = sx[a2], p3 = sx[a3], p4 = sx[a4];
         R lambda = cur.lambda;
         Vec3<R> const z{};
-        green_project_at<R, false>(p1, p2, p3, p4, z, z, z, z, cur.r0, cur.r1, cur.r2, head.mu, head.lam, head.at,
-                                   R(0), a.dt, lambda);
+        Real4<R> r0, r1, r2;
+        if constexpr (kDict)
+        {
+            r0 = s_dict[3 * cur.shape];
+            r1 = s_dict[3 * cur.shape + 1];
+            r2 = s_dict[3 * cur.shape + 2];
+        }
+        else
+        {
+            r0 = cur.r0;
+            r1 = cur.r1;
+            r2 = cur.r2;
+        }
+        green_project_at<R, false>(p1, p2, p3, p4, z, z, z, z, r0, r1, r2, head.mu, head.lam, head.at, R(0), a.dt,
+                                   lambda);
         if (lambda != cur.lambda || first_iteration)
             s.tet_lambda[t] = lambda;
         if (lambda != cur.lambda)
@@ -530,8 +569,9 @@ __device__ __forceinline__ long long clock_stamp()
     return t;
 }
 
-template <typename R, int NVC4, bool kTrace>
-__device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>* sx, DevChunk* s_chunks)
+template <typename R, int NVC4, bool kTrace, bool kDict>
+__device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>* sx, DevChunk* s_chunks,
+                           Real4<R>* s_dict)
 {
     DeviceScene<R> const& s = a.s;
     int const tid = threadIdx.x, nt = blockDim.x;
@@ -555,6 +595,9 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
             int32_t const c = w / (2 * W), rem = w % (2 * W);
             dst[w] = src[(static_cast<int64_t>(c) * a.n_regions + region) * 2 * W + rem];
         }
+        if constexpr (kDict)
+            for (int32_t w = tid; w < 3 * a.n_shapes; w += nt)
+                s_dict[w] = a.shapes[w];
     }
     __syncthreads();
     int32_t traced = 0;
@@ -584,7 +627,7 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
     // next (head loaded, vertices fetched) — before the barrier when that cluster belongs to the
     // next phase: the scratch slots are free once the thread's own cluster is written back, and
     // the records it waits for come from clusters of phases that do not wait for this thread.
-    ClusterHead<R> head;  // the prepared cluster of this thread ...
+    ClusterHead<R, kDict> head; // the prepared cluster of this thread ...
     int64_t cur_q = -1;   // ... and its storage index when it has a fetch list (part A), else -1
     int32_t item_i = -1; // cluster index within its phase (part A first), -1: nothing prepared
     int32_t round  = 0;
@@ -605,7 +648,7 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
         int32_t const ni_next = advance ? tid : (round + 1) * nt + tid;
         bool has_next = false, next_in_a = false;
         int32_t nk = 0;
-        ClusterHead<R> nhead;
+        ClusterHead<R, kDict> nhead;
         uint4 nmeta[NVC4];
         Real4<R> nw[NVC4];
         int64_t next_q = -1;
@@ -629,7 +672,7 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                     next_in_a          = ni_next < nA;
                     DevChunk const& ch = s_chunks[2 * nc + (next_in_a ? 0 : 1)];
                     int32_t const ci   = next_in_a ? ni_next : ni_next - nA;
-                    load_cluster_head<R>(nhead, a, ch, ci, nk == 0);
+                    load_cluster_head<R, kDict>(nhead, a, ch, ci, nk == 0, s_dict);
                     if (next_in_a)
                     {
                         next_q = static_cast<int64_t>(ch.cfirst) + ci;
@@ -763,7 +806,8 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                 bool const in_a    = item_i < nA;
                 DevChunk const& ch = s_chunks[2 * c + (in_a ? 0 : 1)];
                 StepInfo const si{tag, a.base, static_cast<uint32_t>(8 * (2 * (k > 0 ? 1 : 0) + cs)), k == K - 1, cs != 0};
-                run_cluster<R, NVC4>(a, ch, in_a ? item_i : item_i - nA, cur_q, head, sx, k == 0, si, stamp);
+                run_cluster<R, NVC4, kDict>(a, ch, in_a ? item_i : item_i - nA, cur_q, head, sx, s_dict, k == 0, si,
+                                            stamp);
             }
             stamp(6);
         }
@@ -798,22 +842,28 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
     __syncthreads(); // shared memory is reused by the next region of this CTA
 }
 
-// dynamic shared memory: [chunk descriptors of the region | scratch slots | resident vertices]
+// dynamic shared memory: [chunk descriptors of the region | rest-shape dictionary | scratch slots | resident vertices]
 __host__ __device__ inline size_t chunk_area_bytes(int n_colours)
 {
     return (static_cast<size_t>(n_colours) * 2 * sizeof(DevChunk) + 31) / 32 * 32;
 }
+template <typename R>
+__host__ __device__ inline size_t dict_area_bytes(int n_shapes)
+{
+    return static_cast<size_t>(3 * n_shapes) * sizeof(Real4<R>);
+}
 
-template <typename R, int NVC4, bool kTrace, int kMaxThreads>
+template <typename R, int NVC4, bool kTrace, int kMaxThreads, bool kDict>
 __global__ void __launch_bounds__(kMaxThreads) k_substep_persistent(PersistentArgs<R> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevChunk* s_chunks = reinterpret_cast<DevChunk*>(smem_raw);
-    Real4<R>* sx       = reinterpret_cast<Real4<R>*>(smem_raw + chunk_area_bytes(a.n_colours));
+    Real4<R>* s_dict   = reinterpret_cast<Real4<R>*>(smem_raw + chunk_area_bytes(a.n_colours));
+    Real4<R>* sx       = s_dict + (kDict ? 3 * a.n_shapes : 0);
     // regions that share vertices come first in region_order (at most one per CTA: they must be
     // co-resident), the others follow and are handed out round-robin
     for (int32_t i = blockIdx.x; i < a.n_run; i += gridDim.x)
-        run_region<R, NVC4, kTrace>(a, a.region_order[i], sx, s_chunks);
+        run_region<R, NVC4, kTrace, kDict>(a, a.region_order[i], sx, s_chunks, s_dict);
 }
 
 template <typename T>
@@ -859,7 +909,7 @@ struct PersistentPlan
     std::string why_not;
 
     static constexpr int64_t kSmemBudget   = 224 * 1024;
-    static constexpr int64_t kVertexBudget = 200 * 1024; // scratch + resident vertices (rest: chunk descriptors)
+    static constexpr int64_t kVertexBudget = 190 * 1024; // scratch + resident vertices (rest: chunk descriptors)
 
     static int32_t regions_for(int sm_count, int64_t n_tets, int world = 1)
     {
@@ -884,13 +934,21 @@ struct PersistentPlan
 
     // the fewer threads a CTA has, the more registers each may use (255 / 168)
     template <int NVC4, bool kTrace>
-    static void const* pick(int threads)
+    static void const* pick(int threads, bool dict)
     {
-        return threads <= 256 ? reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 256>)
-                              : reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 384>);
+        if (dict)
+            return threads <= 256 ? reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 256, true>)
+                                  : reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 384, true>);
+        return threads <= 256 ? reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 256, false>)
+                              : reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 384, false>);
     }
 
     // returns false (with why_not) when the scene does not fit this schedule
+    // rest-shape dictionary built by the engine (null / 0: none)
+    uint8_t const* d_tet_shape  = nullptr;
+    Real4<R> const* d_shapes    = nullptr;
+    int32_t n_shapes            = 0;
+
     bool build(HostScene const& h, ClusterPlan const& cp, RegionPlan const& plan, DeviceScene<R> const& d,
                cudaStream_t st, int sm_count, int rank = 0, int world = 1)
     {
@@ -1099,7 +1157,8 @@ struct PersistentPlan
         std::vector<int32_t> voff(plan.region_vtx_offsets.begin(), plan.region_vtx_offsets.end());
 
         // launch shape
-        smem  = chunk_area_bytes(cp.n_colours) +
+        bool const dict = d_shapes != nullptr && n_shapes > 0 && n_shapes <= kMaxShapes;
+        smem  = chunk_area_bytes(cp.n_colours) + (dict ? dict_area_bytes<R>(n_shapes) : 0) +
                static_cast<size_t>(static_cast<int64_t>(nvc) * cp.nt + std::max<int64_t>(plan.max_region_vertices, 1)) *
                    sizeof(Real4<R>);
         block = cp.nt;
@@ -1115,14 +1174,14 @@ struct PersistentPlan
             trace_n = std::atoi(e);
         if (trace_n > 0 && nvc == 8)
         {
-            kernel = pick<2, true>(block);
+            kernel = pick<2, true>(block, dict);
             trace.upload(std::vector<long long>(static_cast<size_t>(Rn) * trace_n * 16, 0), st);
             args.trace       = trace.p;
             args.trace_steps = trace_n;
             trace_len        = static_cast<int64_t>(Rn) * trace_n * 16;
         }
         else
-            kernel = nvc == 8 ? pick<2, false>(block) : pick<4, false>(block);
+            kernel = nvc == 8 ? pick<2, false>(block, dict) : pick<4, false>(block, dict);
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
             cudaSuccess)
         {
@@ -1183,6 +1242,9 @@ struct PersistentPlan
         args.n_clusters       = Q;
         args.region_order     = region_order.p;
         args.tet_slots        = tet_slots.p;
+        args.tet_shape        = dict ? d_tet_shape : nullptr;
+        args.shapes           = dict ? d_shapes : nullptr;
+        args.n_shapes         = dict ? n_shapes : 0;
         args.cl_to            = cl_to.p;
         args.cl_to_owner      = cl_to_owner.p;
         args.ifv_first        = ifv_first.p;
