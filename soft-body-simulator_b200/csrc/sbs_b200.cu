@@ -85,6 +85,7 @@ struct EngineBase
     virtual void* mailbox_pointer(size_t& bytes)                                            = 0;
     virtual void set_peer_mailboxes(int rank, void* p)                                      = 0;
     virtual bool peers_connected()                                                          = 0;
+    virtual void check_after_sync(sbsb200_ctx& c)                                           = 0;
 };
 
 } // namespace
@@ -703,6 +704,8 @@ struct Engine final : EngineBase
         CK(cudaStreamSynchronize(c.stream));
         check_persistent(c);
     }
+
+    void check_after_sync(sbsb200_ctx& c) override { check_persistent(c); }
 
     void check_persistent(sbsb200_ctx& c)
     {
@@ -1381,6 +1384,8 @@ int sbsb200_synchronize(sbsb200_ctx* c)
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
         CK(cudaStreamSynchronize(c->stream));
+        if (c->engine)
+            c->engine->check_after_sync(*c);
         return SBSB200_OK;
     });
 }
