@@ -541,23 +541,35 @@ __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk
         cur = nxt;
     }
     // push every fetched vertex to whoever touches it next, always: the tag is what that touch waits for
-#pragma unroll
-    for (int h = 0; h < NVC4; ++h)
+    // (select instead of branch per entry; the single-GPU and the peer-memory variants are unswitched)
+    if (q >= 0)
     {
-        uint32_t const ta[4] = {to[h].x, to[h].y, to[h].z, to[h].w};
-        uint32_t const tb[4] = {to_owner[h].x, to_owner[h].y, to_owner[h].z, to_owner[h].w};
-        Real4<R> p[4];
+        bool const multi = a.world > 1;
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (tb[e] != kNoBox)
+        for (int h = 0; h < NVC4; ++h)
+        {
+            uint32_t const ta[4] = {to[h].x, to[h].y, to[h].z, to[h].w};
+            uint32_t const tb[4] = {to_owner[h].x, to_owner[h].y, to_owner[h].z, to_owner[h].w};
+            Real4<R> p[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
                 p[e] = sx[(4 * h + e) * nt + tid];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (tb[e] != kNoBox)
+            for (int e = 0; e < 4; ++e)
             {
-                bool const owner_next = si.to_owner || (si.surface_to_owner && (tb[e] & kSurfaceBit));
-                push<R>(a, owner_next ? tb[e] : ta[e], p[e].x, p[e].y, p[e].z, si.step);
+                bool const owner_next = si.to_owner | (si.surface_to_owner & ((tb[e] & kSurfaceBit) != 0u));
+                uint32_t const route  = owner_next ? tb[e] : ta[e];
+                uint32_t const index  = route & kBoxIndexMask;
+                if (tb[e] != kNoBox)
+                {
+                    if (!multi)
+                        Xchg<R>::store(a.box, index, p[e].x, p[e].y, p[e].z, si.step);
+                    else
+                        Xchg<R>::store(a.box_of_rank[(route >> kRankShift) & 7u], index, p[e].x, p[e].y, p[e].z,
+                                       si.step, true);
+                }
             }
+        }
     }
     stamp(15);
 }
