@@ -283,8 +283,8 @@ def main():
         e0.record(stream)
         for _ in range(n_e2e):
             sim.step_host(ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
-            xin[:] = xo                    # next frame continues from the host copy
-            vin[:] = vo
+            xin, xo = xo, xin              # next frame continues from the host copy: the two pinned
+            vin, vo = vo, vin              # buffer pairs swap roles, nothing is copied on the host
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0

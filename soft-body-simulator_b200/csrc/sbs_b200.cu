@@ -74,7 +74,7 @@ struct EngineBase
     virtual ~EngineBase() = default;
     virtual void build(sbsb200_ctx& c)                                                     = 0;
     virtual void step(sbsb200_ctx& c, double dt, int substeps, int iterations, int detect) = 0;
-    virtual void upload(sbsb200_ctx& c, int body, double const* x, double const* v)        = 0;
+    virtual void upload(sbsb200_ctx& c, int body, double const* x, double const* v, bool sync = true) = 0;
     virtual void download(sbsb200_ctx& c, int body, double* x, double* v)                  = 0;
     virtual void set_mass(sbsb200_ctx& c, int64_t gv, double m)                             = 0;
     virtual int64_t contacts(sbsb200_ctx& c, int64_t cap, int32_t* body, uint32_t* vertex,
@@ -664,7 +664,7 @@ struct Engine final : EngineBase
         }
     }
 
-    void upload(sbsb200_ctx& c, int body, double const* x, double const* v) override
+    void upload(sbsb200_ctx& c, int body, double const* x, double const* v, bool sync) override
     {
         HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
         int64_t const n    = hb.n_vertices;
@@ -683,7 +683,8 @@ struct Engine final : EngineBase
             ++c.kernels;
         }
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(c.stream)); // the caller may reuse x / v as soon as we return
+        if (sync) // the caller may reuse x / v as soon as we return (step_host: they stay valid until its download)
+            CK(cudaStreamSynchronize(c.stream));
     }
 
     void download(sbsb200_ctx& c, int body, double* x, double* v) override
@@ -1355,7 +1356,18 @@ int sbsb200_step(sbsb200_ctx* c, double dt, int substeps, int iterations, int de
 int sbsb200_step_host(sbsb200_ctx* c, int body, const double* x_in, const double* v_in, double dt, int substeps,
                       int iterations, int detect_mode, double* x_out, double* v_out)
 {
-    int rc = sbsb200_upload(c, body, x_in, v_in);
+    if (!c || !x_in)
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "step_host before finalize");
+    if (!is_tet_body(c, body))
+        return fail(c, SBSB200_ERR_INVALID, "not a tetrahedral body");
+    // upload and step are only enqueued; the one synchronisation is the download's
+    int rc = guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->upload(*c, body, x_in, v_in, false);
+        return SBSB200_OK;
+    });
     if (rc)
         return rc;
     rc = sbsb200_step(c, dt, substeps, iterations, detect_mode);

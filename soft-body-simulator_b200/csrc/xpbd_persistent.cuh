@@ -592,7 +592,13 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
     int32_t const v0 = a.vtx_off[region], nv = a.vtx_off[region + 1] - v0;
     int32_t const i0 = a.ifv_off[region], ni = a.ifv_off[region + 1] - i0;
     int32_t const s0 = a.surf_off[region], ns = a.surf_off[region + 1] - s0;
-    int32_t const C = a.n_colours, cs = a.collide ? 1 : 0, K = C > 0 ? a.iterations : 0;
+    // collision steps exist when detection is on — and, on a single GPU, only when it found something:
+    // every CTA reads the same contact count, so they agree on the schedule (ranks of a decomposed
+    // scene detect separately and could disagree: they always keep the steps)
+    uint32_t const n_contacts =
+        a.collide ? min(*s.contact_count, static_cast<uint32_t>(s.contact_cap)) : 0u;
+    int32_t const C = a.n_colours, cs = (a.collide && (n_contacts > 0u || a.world > 1)) ? 1 : 0,
+                  K = C > 0 ? a.iterations : 0;
     int32_t const per_iteration = C + cs;
     int32_t const n_phases      = 2 + K * per_iteration; // predict, K x ([collision] colours), commit
 
@@ -627,8 +633,6 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
     auto last_colour_tag = [&](int32_t k, uint32_t lastc) -> uint32_t {
         return a.base + 1u + static_cast<uint32_t>(k * per_iteration + cs) + lastc;
     };
-    uint32_t const n_contacts =
-        a.collide ? min(*s.contact_count, static_cast<uint32_t>(s.contact_cap)) : 0u;
     R const at_c = s.collision_alpha / (dt * dt);
 
     // Phase p has tag base + p.  p = 0: predict; p = n_phases - 1: commit; in between iteration
