@@ -142,6 +142,10 @@ int sbsb200_get_constraint_order(const sbsb200_ctx* ctx, uint32_t* order, int64_
  * (tetrahedral_mesh_boundary.cpp:49-58).  Pass map=NULL to query the count. */
 int64_t sbsb200_get_surface_map(const sbsb200_ctx* ctx, int body, uint32_t* map, int64_t cap);
 
+/* tetrahedral_mesh_boundary_t::triangles() (tetrahedral_mesh_boundary.cpp:65-120): boundary triangles as
+ * surface-vertex indices, 3 per triangle, in the reference's order.  Pass NULL to query the index count. */
+int64_t sbsb200_get_surface_triangles(const sbsb200_ctx* ctx, int body, uint32_t* triangles, int64_t cap);
+
 int sbsb200_get_stats(const sbsb200_ctx* ctx, sbsb200_stats* out);
 
 /* Why the schedule in use differs from the requested one ("" when it does not). */
@@ -169,6 +173,11 @@ int sbsb200_get_vertex_ranks(const sbsb200_ctx* ctx, int body, int32_t* out, int
 int sbsb200_upload(sbsb200_ctx* ctx, int body, const double* x, const double* v);
 /* particle_t::x(), v() of every vertex of a body (either may be NULL). */
 int sbsb200_download(sbsb200_ctx* ctx, int body, double* x, double* v);
+/* The boundary surface as a renderer consumes it, without downloading the whole state: 6 floats
+ * (x, y, z, nx, ny, nz) per surface vertex from the surface copy of the last step
+ * (tetrahedral_body_t::update_visual_model, tetrahedral_body.cpp:157-165; normals as
+ * tetrahedral_mesh_boundary.cpp:122-145, but summed from zero at every call). */
+int sbsb200_download_surface(sbsb200_ctx* ctx, int body, float* xyz_normal);
 /* particle_t::mass() = m (main.cpp:158-165 toggles 1 <-> 0 between frames). */
 int sbsb200_set_mass(sbsb200_ctx* ctx, int body, int64_t vertex, double mass);
 

@@ -30,7 +30,7 @@ EXPORTS = [
     "sbsb200_upload", "sbsb200_download", "sbsb200_set_mass", "sbsb200_step", "sbsb200_step_host",
     "sbsb200_synchronize", "sbsb200_get_contacts", "sbsb200_debug_read_trace",
     "sbsb200_set_partition", "sbsb200_get_mailbox_handle", "sbsb200_connect_peers", "sbsb200_connect_peer_context",
-    "sbsb200_get_vertex_ranks", "sbsb200_set_broadphase",
+    "sbsb200_get_vertex_ranks", "sbsb200_set_broadphase", "sbsb200_get_surface_triangles", "sbsb200_download_surface",
 ]
 
 
@@ -95,6 +95,9 @@ def load_library():
     L.sbsb200_get_contacts.argtypes = [vp, C.c_int64, _i32p, _u32p, _i32p, _dp, _dp]
     L.sbsb200_get_contacts.restype = C.c_int64
     L.sbsb200_set_broadphase.argtypes = [vp, C.c_int]
+    L.sbsb200_get_surface_triangles.argtypes = [vp, C.c_int, _u32p, C.c_int64]
+    L.sbsb200_get_surface_triangles.restype = C.c_int64
+    L.sbsb200_download_surface.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.sbsb200_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.sbsb200_get_mailbox_handle.argtypes = [vp, C.c_char_p]
     L.sbsb200_connect_peers.argtypes = [vp, C.c_char_p, C.c_int]
@@ -197,6 +200,19 @@ class Simulation:
         m = np.empty(max(n, 1), np.uint32)
         self._ck(self._L.sbsb200_get_surface_map(self._h, body, m.ctypes.data_as(_u32p), n))
         return m[:n]
+
+    def surface_triangles(self, body):
+        n = self._ck(self._L.sbsb200_get_surface_triangles(self._h, body, None, 0))
+        t = np.empty(max(n, 1), np.uint32)
+        self._ck(self._L.sbsb200_get_surface_triangles(self._h, body, t.ctypes.data_as(_u32p), n))
+        return t[:n].reshape(-1, 3)
+
+    def download_surface(self, body):
+        """[n_surface_vertices, 6] float32: position and unit normal of every boundary vertex."""
+        n = len(self.surface_map(body))
+        out = np.empty((max(n, 1), 6), np.float32)
+        self._ck(self._L.sbsb200_download_surface(self._h, body, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out[:n]
 
     def stats(self):
         s = Stats()

@@ -86,6 +86,7 @@ struct EngineBase
     virtual void set_peer_mailboxes(int rank, void* p)                                      = 0;
     virtual bool peers_connected()                                                          = 0;
     virtual void check_after_sync(sbsb200_ctx& c)                                           = 0;
+    virtual void download_surface(sbsb200_ctx& c, int body, float* out)                     = 0;
 };
 
 } // namespace
@@ -135,6 +136,10 @@ struct Engine final : EngineBase
     DevBuf<uint4> tet_v;
     DevBuf<uint2> dist_v;
     DevBuf<R> tet_lambda, dist_lambda;
+    DevBuf<uint32_t> surf_tri;       // boundary triangles of all bodies (surface-vertex indices local to the body)
+    DevBuf<Real4<R>> surf_normal;
+    DevBuf<float> surf_out;
+    std::vector<int64_t> tri_offset; // per body: first triangle in surf_tri
     DevBuf<uint8_t> tet_shape;       // rest-shape dictionary (persistent schedule): index per tet ...
     DevBuf<Real4<R>> shape_records;  // ... into the distinct (r0, r1, r2) records
     DevBuf<uint32_t> surf_v, surf_first, contact_v, contact_count;
@@ -352,6 +357,18 @@ struct Engine final : EngineBase
             }
         }
         int64_t const Vs = static_cast<int64_t>(sv.size());
+        {
+            std::vector<uint32_t> tri;
+            tri_offset.assign(h.bodies.size() + 1, 0);
+            for (size_t b = 0; b < h.bodies.size(); ++b)
+            {
+                tri_offset[b] = static_cast<int64_t>(tri.size() / 3);
+                tri.insert(tri.end(), h.bodies[b].surf_triangles.begin(), h.bodies[b].surf_triangles.end());
+            }
+            tri_offset[h.bodies.size()] = static_cast<int64_t>(tri.size() / 3);
+            surf_tri.upload(tri, st);
+            surf_normal.alloc(static_cast<size_t>(Vs));
+        }
         surf_v.upload(sv, st);
         surf_body.upload(sb, st);
         surf_pos.alloc(static_cast<size_t>(Vs));
@@ -708,6 +725,27 @@ struct Engine final : EngineBase
 
     void check_after_sync(sbsb200_ctx& c) override { check_persistent(c); }
 
+    void download_surface(sbsb200_ctx& c, int body, float* out) override
+    {
+        HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
+        int64_t const n    = static_cast<int64_t>(hb.surf_to_tet.size());
+        int64_t const nt   = tri_offset[static_cast<size_t>(body) + 1] - tri_offset[static_cast<size_t>(body)];
+        if (n == 0)
+            return;
+        if (surf_out.n < static_cast<size_t>(6 * n))
+            surf_out.alloc(static_cast<size_t>(6 * n));
+        CK(cudaMemsetAsync(surf_normal.p + hb.s_offset, 0, sizeof(Real4<R>) * static_cast<size_t>(n), c.stream));
+        if (nt > 0)
+            k_surface_normals<R><<<static_cast<unsigned>((nt + 255) / 256), 256, 0, c.stream>>>(
+                d, tri_offset[static_cast<size_t>(body)], nt, surf_tri.p, hb.s_offset, surf_normal.p);
+        k_surface_pack<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(d, hb.s_offset, n, surf_normal.p,
+                                                                                     surf_out.p);
+        c.kernels += 2;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, surf_out.p, sizeof(float) * 6 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+    }
+
     void check_persistent(sbsb200_ctx& c)
     {
         if (c.schedule == SBSB200_SCHED_PERSISTENT && pp.timed_out())
@@ -964,7 +1002,7 @@ int sbsb200_add_tet_body(sbsb200_ctx* c, int64_t nV, const double* x0, const dou
     hb.n_vertices = nV;
     hb.t_offset   = h.n_tets();
     hb.n_tets     = nT;
-    extract_boundary(nV, nT, tets, hb.surf_to_tet, nullptr);
+    extract_boundary(nV, nT, tets, hb.surf_to_tet, &hb.surf_triangles);
     h.x0.insert(h.x0.end(), x0, x0 + 3 * nV);
     if (mass)
         h.mass.insert(h.mass.end(), mass, mass + nV);
@@ -1150,6 +1188,32 @@ int64_t sbsb200_get_surface_map(const sbsb200_ctx* c, int body, uint32_t* map, i
     if (map)
         std::memcpy(map, m.data(), sizeof(uint32_t) * static_cast<size_t>(std::min<int64_t>(cap, static_cast<int64_t>(m.size()))));
     return static_cast<int64_t>(m.size());
+}
+
+int64_t sbsb200_get_surface_triangles(const sbsb200_ctx* c, int body, uint32_t* triangles, int64_t cap)
+{
+    if (!c || !is_tet_body(c, body))
+        return SBSB200_ERR_INVALID;
+    auto const& t = c->scene.bodies[static_cast<size_t>(body)].surf_triangles;
+    if (triangles)
+        std::memcpy(triangles, t.data(),
+                    sizeof(uint32_t) * static_cast<size_t>(std::min<int64_t>(cap, static_cast<int64_t>(t.size()))));
+    return static_cast<int64_t>(t.size());
+}
+
+int sbsb200_download_surface(sbsb200_ctx* c, int body, float* out)
+{
+    if (!c || !out)
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "download_surface before finalize");
+    if (!is_tet_body(c, body))
+        return fail(c, SBSB200_ERR_INVALID, "not a tetrahedral body");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->download_surface(*c, body, out);
+        return SBSB200_OK;
+    });
 }
 
 int sbsb200_get_stats(const sbsb200_ctx* cc, sbsb200_stats* out)

@@ -28,6 +28,7 @@ struct HostBody
     int64_t t_offset = 0, n_tets = 0;       // range in HostScene::tets (insertion order)
     int64_t s_offset = 0;                   // range in the global surface-vertex list
     std::vector<uint32_t> surf_to_tet;      // body-local tet-mesh vertex of surface vertex i
+    std::vector<uint32_t> surf_triangles;   // boundary triangles as surface-vertex indices (3 per triangle)
     // sdf body
     SdfKind sdf_kind = SdfKind::plane;
     double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, r = 0; // plane: a=n, r=offset; sphere: a=c, r; box: a=min, b=max

@@ -379,6 +379,60 @@ __global__ void __launch_bounds__(256) k_surface_gather(DeviceScene<R> s)
     st4(&s.surf_pos[i], ld4(&s.prev[s.surf_v[i]]));
 }
 
+// Boundary surface for a renderer: per-vertex normals as the reference computes them
+// (tetrahedral_mesh_boundary.cpp:122-145: sum of (p2 - p1) x (p3 - p1) over the incident boundary
+// triangles, normalised) — except that the sum starts from zero at every call (the reference never
+// resets it).  Positions come from the surface copy.
+__device__ __forceinline__ void atomic_add3(Real4<float>* p, float x, float y, float z)
+{
+    atomicAdd(&p->x, x);
+    atomicAdd(&p->y, y);
+    atomicAdd(&p->z, z);
+}
+__device__ __forceinline__ void atomic_add3(Real4<double>* p, double x, double y, double z)
+{
+    atomicAdd(&p->x, x);
+    atomicAdd(&p->y, y);
+    atomicAdd(&p->z, z);
+}
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_surface_normals(DeviceScene<R> s, int64_t first_triangle, int64_t n_triangles, uint32_t const* __restrict__ tri,
+                  int64_t first_surface, Real4<R>* __restrict__ normal)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n_triangles)
+        return;
+    uint32_t const a = tri[3 * (first_triangle + i)], b = tri[3 * (first_triangle + i) + 1],
+                   c = tri[3 * (first_triangle + i) + 2];
+    Real4<R> const p1 = ld4(&s.surf_pos[first_surface + a]), p2 = ld4(&s.surf_pos[first_surface + b]),
+                   p3 = ld4(&s.surf_pos[first_surface + c]);
+    Vec3<R> const n = cross(Vec3<R>{p2.x - p1.x, p2.y - p1.y, p2.z - p1.z}, Vec3<R>{p3.x - p1.x, p3.y - p1.y, p3.z - p1.z});
+    atomic_add3(&normal[first_surface + a], n.x, n.y, n.z);
+    atomic_add3(&normal[first_surface + b], n.x, n.y, n.z);
+    atomic_add3(&normal[first_surface + c], n.x, n.y, n.z);
+}
+// (x, y, z, nx, ny, nz) as floats, the vertex layout of the reference's renderer (renderer.cpp:484-542)
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_surface_pack(DeviceScene<R> s, int64_t first_surface, int64_t n, Real4<R> const* __restrict__ normal,
+               float* __restrict__ out)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    Real4<R> const p = ld4(&s.surf_pos[first_surface + i]);
+    Real4<R> const m = ld4(&normal[first_surface + i]);
+    R const len2     = m.x * m.x + m.y * m.y + m.z * m.z;
+    R const inv      = len2 > R(0) ? R(1) / sqrt_(len2) : R(0);
+    out[6 * i]       = float(p.x);
+    out[6 * i + 1]   = float(p.y);
+    out[6 * i + 2]   = float(p.z);
+    out[6 * i + 3]   = float(m.x * inv);
+    out[6 * i + 4]   = float(m.y * inv);
+    out[6 * i + 5]   = float(m.z * inv);
+}
+
 // Host-format (3 doubles per vertex) <-> device layout.  Upload sets x = xi = xn and keeps the
 // inverse mass (tetrahedral_body_t::transform semantics, tetrahedral_body.cpp:121-132).
 template <typename R>

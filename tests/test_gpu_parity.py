@@ -251,3 +251,25 @@ def test_full_size_properties_config3(sbs, scenes, precision):
     assert st["n_tets"] == 1_000_000 and st["n_surface_vertices"] == 22_002
     # the 10% pre-strain of a 40-wide block relaxes by a few units in one frame, not more
     assert np.abs(out[0][0] - scene.items[0].x).max() < 6.0
+
+
+def test_surface_output_for_rendering(sbs, scenes, oracle):
+    """Boundary positions + normals straight from the device: triangles equal the
+    reference's boundary extraction, normals equal the reference's formula on the downloaded positions."""
+    scene = scenes.config1(W=5, H=4, D=6)
+    sim = sbs.Simulation(0, 32)
+    ids = scene.instantiate(sim)
+    sim.step(scene.dt, 4, 4)
+    s2t, tris = oracle.boundary_surface(scene.items[0].x0.shape[0], scene.items[0].tets)
+    assert np.array_equal(sim.surface_triangles(ids[0]), tris)
+    out = sim.download_surface(ids[0])
+    x, _ = sim.download(ids[0])
+    assert np.array_equal(out[:, :3], x[s2t].astype(np.float32))
+    p = x[s2t]
+    n = np.zeros_like(p)
+    fn = np.cross(p[tris[:, 1]] - p[tris[:, 0]], p[tris[:, 2]] - p[tris[:, 0]])
+    for k in range(3):
+        np.add.at(n, tris[:, k], fn)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    assert np.abs(out[:, 3:] - n).max() < 1e-4
+    assert np.abs(np.linalg.norm(out[:, 3:], axis=1) - 1).max() < 1e-5
