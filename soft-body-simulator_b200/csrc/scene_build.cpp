@@ -792,6 +792,112 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
     }
 }
 
+bool build_mailbox_routes(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& plan, int nvc, int world,
+                          MailboxRoutes& out)
+{
+    out = MailboxRoutes{};
+    int64_t const V = scene.n_vertices(), Q = cp.n_clusters;
+    int32_t const Rn = plan.n_regions;
+    if (world < 1 || Rn % world != 0 || nvc < cp.nvc)
+    {
+        out.why_not = "bad partition (world must divide the region count)";
+        return false;
+    }
+    // owned non-resident vertices, grouped by owner region
+    out.ifv_offsets.assign(static_cast<size_t>(Rn) + 1, 0);
+    for (int64_t v = 0; v < V; ++v)
+        if (plan.vertex_region[static_cast<size_t>(v)] < 0)
+            ++out.ifv_offsets[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)]) + 1];
+    for (int32_t r = 0; r < Rn; ++r)
+        out.ifv_offsets[static_cast<size_t>(r) + 1] += out.ifv_offsets[static_cast<size_t>(r)];
+    out.ifv.assign(static_cast<size_t>(out.ifv_offsets.back()), 0);
+    out.ifv_meta.assign(out.ifv.size(), 0);
+    out.ifv_pos.assign(static_cast<size_t>(V), kRouteNone);
+    {
+        std::vector<int32_t> cur(out.ifv_offsets.begin(), out.ifv_offsets.end() - 1);
+        for (int64_t v = 0; v < V; ++v)
+            if (plan.vertex_region[static_cast<size_t>(v)] < 0)
+            {
+                int32_t const at = cur[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)])]++;
+                out.ifv[static_cast<size_t>(at)]      = static_cast<uint32_t>(v);
+                out.ifv_meta[static_cast<size_t>(at)] = cp.vertex_meta.empty() ? 0u : cp.vertex_meta[static_cast<size_t>(v)];
+                out.ifv_pos[static_cast<size_t>(v)]   = static_cast<uint32_t>(at);
+            }
+    }
+    out.n_entries = static_cast<uint32_t>(static_cast<int64_t>(nvc) * Q);
+    if (static_cast<uint64_t>(out.n_entries) + out.ifv.size() >= kRouteIndexMask)
+    {
+        out.why_not = "too many mailboxes for 28-bit routing words";
+        return false;
+    }
+    std::vector<int32_t> cluster_colour(static_cast<size_t>(Q), 0), cluster_region(static_cast<size_t>(Q), 0);
+    for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
+        for (int32_t i = 0; i < cp.chunks[ch].n[0]; ++i)
+        {
+            cluster_colour[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
+                static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
+            cluster_region[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
+                static_cast<int32_t>((ch / 2) % static_cast<size_t>(Rn));
+        }
+    // routing word of a mailbox: its index and the rank whose memory holds it (the rank that reads it)
+    auto const entry_route = [&](uint32_t box) {
+        return box | (static_cast<uint32_t>(region_rank(cluster_region[box % static_cast<uint32_t>(Q)], Rn, world))
+                      << kRouteRankShift);
+    };
+    auto const owner_route = [&](uint32_t pos) {
+        return (out.n_entries + pos) |
+               (static_cast<uint32_t>(region_rank(plan.vertex_owner[out.ifv[pos]], Rn, world)) << kRouteRankShift);
+    };
+    struct Touch
+    {
+        uint32_t vertex;
+        int32_t colour;
+        uint32_t box;
+    };
+    std::vector<Touch> touches;
+    for (int j = 0; j < cp.nvc; ++j)
+        for (int64_t q = 0; q < Q; ++q)
+        {
+            uint32_t const v = cp.cl_fetch[static_cast<size_t>(j) * Q + q];
+            if (v != kRouteNone)
+                touches.push_back({v, cluster_colour[static_cast<size_t>(q)],
+                                   static_cast<uint32_t>(static_cast<int64_t>(j) * Q + q)});
+        }
+    std::sort(touches.begin(), touches.end(), [](Touch const& x, Touch const& y) {
+        return x.vertex != y.vertex ? x.vertex < y.vertex : x.colour < y.colour;
+    });
+    out.to.assign(out.n_entries, kRouteNone);
+    out.to_owner.assign(out.n_entries, kRouteNone);
+    out.ifv_first.assign(out.ifv.size(), kRouteNone);
+    for (size_t i = 0; i < touches.size();)
+    {
+        size_t j = i;
+        while (j < touches.size() && touches[j].vertex == touches[i].vertex)
+            ++j;
+        uint32_t const v   = touches[i].vertex;
+        uint32_t const pos = out.ifv_pos[v];
+        if (pos == kRouteNone)
+        {
+            out.why_not = "a fetched vertex has no owner mailbox";
+            return false;
+        }
+        out.ifv_first[pos] = entry_route(touches[i].box);
+        for (size_t t = i; t < j; ++t)
+        {
+            if (t + 1 < j && touches[t + 1].colour == touches[t].colour)
+            {
+                out.why_not = "two clusters of one colour touch the same vertex";
+                return false;
+            }
+            uint32_t const surface       = (cp.vertex_meta[v] & 0x100u) ? kRouteSurfaceBit : 0u;
+            out.to[touches[t].box]       = entry_route(t + 1 < j ? touches[t + 1].box : touches[i].box);
+            out.to_owner[touches[t].box] = (t + 1 < j ? entry_route(touches[t + 1].box) : owner_route(pos)) | surface;
+        }
+        i = j;
+    }
+    return true;
+}
+
 bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& rp)
 {
     int64_t const T = scene.n_tets(), Q = cp.n_clusters;

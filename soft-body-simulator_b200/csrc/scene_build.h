@@ -185,6 +185,34 @@ inline int32_t region_rank(int32_t region, int32_t n_regions, int32_t world)
     return region / (n_regions / world);
 }
 
+// ---- mailboxes of the resident schedule (xpbd_persistent.cuh) -----------------------------------
+// Entry (j, q) = scratch slot j of cluster q has mailbox j * Q + q (Q = number of clusters); owned
+// non-resident vertex i (position in `ifv`) has mailbox n_entries + i.  Per vertex the entries are
+// ordered by the colour of their cluster: each pushes to the next one; the last one pushes to the
+// first one (next sweep) or to the owner (collision step, commit).  Routing words carry the mailbox
+// index (bits 0-27) and the rank whose memory holds it (bits 28-30); bit 31 of `to_owner` marks
+// surface vertices.
+constexpr uint32_t kRouteNone       = 0xffffffffu;
+constexpr uint32_t kRouteIndexMask  = 0x0fffffffu;
+constexpr uint32_t kRouteSurfaceBit = 0x80000000u;
+constexpr int kRouteRankShift       = 28;
+
+struct MailboxRoutes
+{
+    uint32_t n_entries = 0;             // nvc * Q
+    std::vector<int32_t> ifv_offsets;   // [n_regions + 1] into ifv: vertices a region owns that are not resident
+    std::vector<uint32_t> ifv;          // global vertex ids
+    std::vector<uint32_t> ifv_meta;     // ClusterPlan::vertex_meta of those
+    std::vector<uint32_t> ifv_first;    // routing word of the first entry touching the vertex in a sweep
+    std::vector<uint32_t> ifv_pos;      // V: position in ifv, kRouteNone for resident vertices
+    std::vector<uint32_t> to, to_owner; // [nvc][Q] routing words, kRouteNone for unused slots
+    std::string why_not;
+};
+
+// nvc: scratch entries per thread of the kernel instantiation (>= cp.nvc); world: ranks the scene is cut over
+bool build_mailbox_routes(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& plan, int nvc, int world,
+                          MailboxRoutes& out);
+
 // true when every tet slot of the resident layout resolves to the right vertex (resident slot of
 // its region, or the scratch entry the running thread fetched) and parts are classified correctly
 bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& rp);

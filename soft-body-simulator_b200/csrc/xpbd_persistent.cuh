@@ -59,8 +59,9 @@ constexpr uint32_t kNoBox     = 0xffffffffu; // "no such mailbox"
 constexpr uint32_t kNoEntry   = 0xffffffffu; // cl_meta of an unused scratch slot
 constexpr uint32_t kSurfaceBit = 0x80000000u; // cl_to_owner: the vertex is a surface vertex
 // routing words: bits 0-27 mailbox index, bits 28-30 the rank (GPU) whose memory holds that mailbox
-constexpr uint32_t kBoxIndexMask = 0x0fffffffu;
-constexpr int kRankShift         = 28;
+constexpr uint32_t kBoxIndexMask = kRouteIndexMask;
+constexpr int kRankShift         = kRouteRankShift;
+static_assert(kNoBox == kRouteNone && kSurfaceBit == kRouteSurfaceBit, "routing words: host and device agree");
 constexpr int kMaxWorld          = 8;
 constexpr int kPollBudget     = 1 << 24;     // polls of one record before the kernel gives up
 
@@ -975,7 +976,6 @@ struct PersistentPlan
             return false;
         }
         int32_t const per_rank = Rn / world;
-        auto const rank_of_region = [&](int32_t r) { return static_cast<uint32_t>(region_rank(r, Rn, world)); };
         int64_t const T = h.n_tets(), V = h.n_vertices();
         if (!cp.why_not.empty())
         {
@@ -1038,99 +1038,20 @@ struct PersistentPlan
             for (int m = 0; m < 8; ++m)
                 hchunks[i].n[m] = cp.chunks[i].n[m];
         }
-        // owned non-resident vertices, owned surface vertices
-        std::vector<int32_t> ioff(static_cast<size_t>(Rn) + 1, 0), soff(static_cast<size_t>(Rn) + 1, 0);
-        for (int64_t v = 0; v < V; ++v)
-            if (plan.vertex_region[static_cast<size_t>(v)] < 0)
-                ++ioff[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)]) + 1];
-        for (int32_t r = 0; r < Rn; ++r)
-            ioff[static_cast<size_t>(r) + 1] += ioff[static_cast<size_t>(r)];
-        std::vector<uint32_t> ifv(static_cast<size_t>(ioff.back())), ifm(ifv.size());
+        // owned non-resident vertices and the routing of the mailboxes (scene_build.cpp, CPU-testable)
+        MailboxRoutes routes;
+        if (!build_mailbox_routes(h, cp, plan, nvc, world, routes))
         {
-            std::vector<int32_t> cur(ioff.begin(), ioff.end() - 1);
-            for (int64_t v = 0; v < V; ++v)
-                if (plan.vertex_region[static_cast<size_t>(v)] < 0)
-                {
-                    int32_t const at = cur[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)])]++;
-                    ifv[static_cast<size_t>(at)] = static_cast<uint32_t>(v);
-                    ifm[static_cast<size_t>(at)] = cp.vertex_meta[static_cast<size_t>(v)];
-                }
-        }
-        // ---- routing of the mailboxes -------------------------------------------------------------
-        // entry (j, q) = scratch slot j of cluster q has mailbox j * Q + q; owned vertex i (position in
-        // ifv) has mailbox n_entries + i.  Per vertex the entries are ordered by the colour of their
-        // cluster: each pushes to the next one, the last one to the owner or back to the first.
-        uint32_t const n_entries = static_cast<uint32_t>(static_cast<int64_t>(nvc) * Q);
-        std::vector<uint32_t> ifv_pos(static_cast<size_t>(V), kNoBox);
-        for (size_t i = 0; i < ifv.size(); ++i)
-            ifv_pos[ifv[i]] = static_cast<uint32_t>(i);
-        if (static_cast<uint64_t>(n_entries) + ifv.size() >= kBoxIndexMask)
-        {
-            why_not = "too many mailboxes for 28-bit routing words";
+            why_not = routes.why_not;
             return false;
         }
-        std::vector<int32_t> cluster_colour(static_cast<size_t>(Q), 0), cluster_region(static_cast<size_t>(Q), 0);
-        for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
-            for (int32_t i = 0; i < cp.chunks[ch].n[0]; ++i)
-            {
-                cluster_colour[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
-                    static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
-                cluster_region[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
-                    static_cast<int32_t>((ch / 2) % static_cast<size_t>(Rn));
-            }
-        // routing word of a mailbox: its index and the rank whose memory holds it (the rank that reads it)
-        auto const entry_route = [&](uint32_t box) {
-            return box | (rank_of_region(cluster_region[box % static_cast<uint32_t>(Q)]) << kRankShift);
-        };
-        auto const owner_route = [&](uint32_t pos) {
-            return (n_entries + pos) | (rank_of_region(plan.vertex_owner[ifv[pos]]) << kRankShift);
-        };
-        struct Touch
-        {
-            uint32_t vertex;
-            int32_t colour;
-            uint32_t box;
-        };
-        std::vector<Touch> touches;
-        for (int j = 0; j < cp.nvc; ++j)
-            for (int64_t q = 0; q < Q; ++q)
-            {
-                uint32_t const v = cp.cl_fetch[static_cast<size_t>(j) * Q + q];
-                if (v != kNoVertex)
-                    touches.push_back({v, cluster_colour[static_cast<size_t>(q)],
-                                       static_cast<uint32_t>(static_cast<int64_t>(j) * Q + q)});
-            }
-        std::sort(touches.begin(), touches.end(), [](Touch const& x, Touch const& y) {
-            return x.vertex != y.vertex ? x.vertex < y.vertex : x.colour < y.colour;
-        });
-        std::vector<uint32_t> r_to(n_entries, kNoBox), r_to_owner(n_entries, kNoBox);
-        std::vector<uint32_t> ifirst(ifv.size(), kNoBox);
-        for (size_t i = 0; i < touches.size();)
-        {
-            size_t j = i;
-            while (j < touches.size() && touches[j].vertex == touches[i].vertex)
-                ++j;
-            uint32_t const v   = touches[i].vertex;
-            uint32_t const pos = ifv_pos[v];
-            if (pos == kNoBox)
-            {
-                why_not = "a fetched vertex has no owner mailbox";
-                return false;
-            }
-            ifirst[pos] = entry_route(touches[i].box);
-            for (size_t t = i; t < j; ++t)
-            {
-                if (t + 1 < j && touches[t + 1].colour == touches[t].colour)
-                {
-                    why_not = "two clusters of one colour touch the same vertex";
-                    return false;
-                }
-                uint32_t const surface      = (cp.vertex_meta[v] & 0x100u) ? kSurfaceBit : 0u;
-                r_to[touches[t].box]       = entry_route(t + 1 < j ? touches[t + 1].box : touches[i].box);
-                r_to_owner[touches[t].box] = (t + 1 < j ? entry_route(touches[t + 1].box) : owner_route(pos)) | surface;
-            }
-            i = j;
-        }
+        std::vector<int32_t> const& ioff  = routes.ifv_offsets;
+        std::vector<uint32_t> const& ifv  = routes.ifv;
+        std::vector<uint32_t> const& ifm  = routes.ifv_meta;
+        std::vector<uint32_t> const& ifirst = routes.ifv_first;
+        std::vector<uint32_t> const& ifv_pos = routes.ifv_pos;
+        uint32_t const n_entries = routes.n_entries;
+        std::vector<int32_t> soff(static_cast<size_t>(Rn) + 1, 0);
         auto const pack = [&](std::vector<uint32_t> const& r) {
             std::vector<uint4> out(fetch.size(), make_uint4(kNoBox, kNoBox, kNoBox, kNoBox));
             for (int k4 = 0; k4 < nvc / 4; ++k4)
@@ -1140,7 +1061,7 @@ struct PersistentPlan
                                    r[static_cast<size_t>(4 * k4 + 2) * Q + q], r[static_cast<size_t>(4 * k4 + 3) * Q + q]);
             return out;
         };
-        std::vector<uint4> const h_to = pack(r_to), h_to_owner = pack(r_to_owner);
+        std::vector<uint4> const h_to = pack(routes.to), h_to_owner = pack(routes.to_owner);
 
         std::vector<uint32_t> sgv; // global vertex of surface vertex i (same order as DeviceScene::surf_v)
         for (auto const& b : h.bodies)

@@ -150,3 +150,58 @@ extern "C" int hs_partition(int64_t nV, int64_t nT, const uint32_t* tets, const 
         region_rank_out[r] = region_rank(r, n_regions, world);
     return n_regions;
 }
+
+// mailbox routing of the resident schedule for a single body cut into `n_regions` regions run by
+// `world` ranks.  Outputs (caller-sized with the capacities given): cl_fetch / to / to_owner
+// [nvc * Q], cluster_region[Q], cluster_colour[Q], ifv / ifv_first [n_ifv], vertex_owner[V];
+// dims = {nvc, Q, n_ifv, n_entries}.  Returns 0, -1 (no plan), -2 (no routes), -3 (capacity).
+extern "C" int hs_mailbox_routes(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_regions,
+                                 int world, int64_t cap_entries, int64_t cap_clusters, uint32_t* cl_fetch,
+                                 uint32_t* to, uint32_t* to_owner, int32_t* cluster_region, int32_t* cluster_colour,
+                                 uint32_t* ifv, uint32_t* ifv_first, int32_t* vertex_owner, int64_t* dims)
+{
+    HostScene h;
+    h.x0.assign(x0, x0 + 3 * nV);
+    h.mass.assign(static_cast<size_t>(nV), 1.0);
+    h.tets.assign(tets, tets + 4 * nT);
+    for (int64_t t = 0; t < nT; ++t)
+    {
+        h.tet_insertion.push_back(h.n_constraints++);
+        h.tet_material.push_back(0);
+    }
+    HostBody b;
+    b.n_vertices = nV;
+    b.n_tets     = nT;
+    extract_boundary(nV, nT, tets, b.surf_to_tet, &b.surf_triangles);
+    h.bodies.push_back(b);
+    ResidentParams rp;
+    rp.smem_bytes = 200 * 1024;
+    ClusterPlan plan;
+    RegionPlan regions;
+    build_cluster_plan(h, n_regions, false, plan, &rp, &regions);
+    if (!plan.why_not.empty())
+        return -1;
+    MailboxRoutes routes;
+    if (!build_mailbox_routes(h, plan, regions, plan.nvc, world, routes))
+        return -2;
+    int64_t const Q = plan.n_clusters;
+    if (routes.n_entries > cap_entries || Q > cap_clusters || static_cast<int64_t>(routes.ifv.size()) > nV)
+        return -3;
+    std::memcpy(cl_fetch, plan.cl_fetch.data(), sizeof(uint32_t) * routes.n_entries);
+    std::memcpy(to, routes.to.data(), sizeof(uint32_t) * routes.n_entries);
+    std::memcpy(to_owner, routes.to_owner.data(), sizeof(uint32_t) * routes.n_entries);
+    for (size_t ch = 0; ch < plan.chunks.size(); ++ch)
+        for (int32_t i = 0; i < plan.chunks[ch].n[0]; ++i)
+        {
+            cluster_colour[plan.chunks[ch].cfirst + i] = static_cast<int32_t>(ch / (2 * static_cast<size_t>(n_regions)));
+            cluster_region[plan.chunks[ch].cfirst + i] = static_cast<int32_t>((ch / 2) % static_cast<size_t>(n_regions));
+        }
+    std::memcpy(ifv, routes.ifv.data(), sizeof(uint32_t) * routes.ifv.size());
+    std::memcpy(ifv_first, routes.ifv_first.data(), sizeof(uint32_t) * routes.ifv.size());
+    std::memcpy(vertex_owner, regions.vertex_owner.data(), sizeof(int32_t) * static_cast<size_t>(nV));
+    dims[0] = plan.nvc;
+    dims[1] = Q;
+    dims[2] = static_cast<int64_t>(routes.ifv.size());
+    dims[3] = routes.n_entries;
+    return 0;
+}

@@ -37,6 +37,8 @@ def hostscene():
     L.hs_regions.restype = C.c_int64
     L.hs_cluster_plan.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int, C.c_int64, u32p, u32p, i32p, i64p,
                                   i64p]
+    L.hs_mailbox_routes.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int64, C.c_int64, u32p, u32p,
+                                    u32p, i32p, i32p, u32p, u32p, i32p, i64p]
     return L
 
 
@@ -50,7 +52,7 @@ def hostmath():
     src = [os.path.join(HERE, "host_math.cu"), os.path.join(ROOT, "soft-body-simulator_b200/csrc/xpbd_math.cuh"),
            os.path.join(ROOT, "soft-body-simulator_b200/csrc/xpbd_kernels.cuh")]
     if not _newer(lib, src):
-        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC",
+        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
                                "-shared", "-o", lib, src[0]])
     L = C.CDLL(lib)
     for f in (L.hostmath_green_project_f64, L.hostmath_green_project_f32):
@@ -242,6 +244,72 @@ def test_region_plan_partitions_tets_and_classifies_vertices(hostscene, oracle, 
         assert n_if == 0 and nnb[0] == 0
     else:
         assert (nnb > 0).all()
+
+
+@pytest.mark.parametrize("regions,world", [(8, 1), (8, 2), (12, 4), (16, 8)])
+def test_mailbox_routes_chain_every_shared_vertex_through_its_colours(hostscene, oracle, regions, world):
+    """Routing of the resident schedule's mailboxes (scene_build.cpp build_mailbox_routes): per shared
+    vertex the scratch entries that fetch it form one cycle in colour order, the last entry of a sweep
+    hands the vertex to its owner, and every routing word names the rank that reads the mailbox."""
+    pos, tets = oracle.bar_model(9, 9, 25)
+    tets = np.ascontiguousarray(tets, np.uint32)
+    x0 = pos.astype(np.float64)
+    V = len(pos)
+    cap_e, cap_q = 1 << 20, 1 << 16
+    fetch = np.empty(cap_e, np.uint32)
+    to = np.empty(cap_e, np.uint32)
+    to_owner = np.empty(cap_e, np.uint32)
+    creg = np.zeros(cap_q, np.int32)
+    ccol = np.zeros(cap_q, np.int32)
+    ifv = np.empty(V, np.uint32)
+    ifirst = np.empty(V, np.uint32)
+    vowner = np.empty(V, np.int32)
+    dims = np.zeros(4, np.int64)
+    rc = hostscene.hs_mailbox_routes(V, len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), regions, world,
+                                     cap_e, cap_q, fetch.ctypes.data_as(u32p), to.ctypes.data_as(u32p),
+                                     to_owner.ctypes.data_as(u32p), creg.ctypes.data_as(i32p),
+                                     ccol.ctypes.data_as(i32p), ifv.ctypes.data_as(u32p), ifirst.ctypes.data_as(u32p),
+                                     vowner.ctypes.data_as(i32p), dims.ctypes.data_as(i64p))
+    assert rc == 0
+    nvc, Q, n_ifv, n_entries = (int(d) for d in dims)
+    assert n_entries == nvc * Q and n_ifv > 0
+    fetch, to, to_owner = fetch[:n_entries], to[:n_entries], to_owner[:n_entries]
+    NONE, IDX, SURF = 0xffffffff, 0x0fffffff, 0x80000000
+    rank_of_region = lambda r: r // (regions // world)
+    used = np.nonzero(fetch != NONE)[0]
+    assert (to[fetch == NONE] == NONE).all() and (to_owner[fetch == NONE] == NONE).all()
+    # every routing word to a scratch mailbox names the rank running the cluster that owns the slot
+    for words in (to[used], to_owner[used]):
+        idx = words & IDX
+        rank = (words >> 28) & 7
+        entry = idx < n_entries
+        assert (rank[entry] == [rank_of_region(creg[b % Q]) for b in idx[entry]]).all()
+    boxes_of = {}
+    for b in used:
+        boxes_of.setdefault(int(fetch[b]), []).append(int(b))
+    pos_of = {int(v): i for i, v in enumerate(ifv[:n_ifv])}
+    assert set(boxes_of) <= set(pos_of)          # only owned non-resident vertices are fetched
+    on_boundary = set(int(v) for v in oracle.boundary_surface(V, tets)[0])
+    for v, boxes in boxes_of.items():
+        first = int(ifirst[pos_of[v]])
+        assert (first >> 28) & 7 == rank_of_region(creg[(first & IDX) % Q])
+        chain, b = [], first & IDX
+        while b not in chain:
+            assert fetch[b] == v
+            chain.append(b)
+            b = int(to[b]) & IDX
+        assert b == chain[0] and sorted(chain) == sorted(boxes)
+        colours = [ccol[c % Q] for c in chain]
+        assert colours == sorted(colours) and len(set(colours)) == len(colours)
+        # to_owner follows the same chain except for the last entry of the sweep
+        for c in chain[:-1]:
+            assert (int(to_owner[c]) & ~SURF) == int(to[c])
+        last = int(to_owner[chain[-1]])
+        assert (last & IDX) == n_entries + pos_of[v]
+        assert (last >> 28) & 7 == rank_of_region(vowner[v])
+        surf = {bool(int(to_owner[c]) & SURF) for c in chain}
+        assert len(surf) == 1
+        assert surf == {v in on_boundary}
 
 
 def _host_project(fn, xi, xn, w, DmInv, V0, E, nu, alpha, beta, dt, lam):
