@@ -121,6 +121,43 @@ int sbsb200_add_sdf_sphere(sbsb200_ctx* ctx, const double centre[3], double radi
 int sbsb200_add_sdf_box(sbsb200_ctx* ctx, const double box_min[3], const double box_max[3],
                         const double volume[6]);
 
+/* environment_body_t holding a discrete-grid sdf_model_t (sdf_model.cpp:18, evaluated by
+ * Discregrid::CubicLagrangeDiscreteGrid::interpolate, sdf_model.cpp:71-74): 32-node cubic cells over
+ * [domain_min, domain_max] with resolution[3] cells per axis.  node_values: one double per node in
+ * Discregrid's node order (corners x-fastest, then two nodes per x-, y-, z-edge; see
+ * csrc/grid_sdf.cuh); n_nodes must equal sbsb200_grid_node_count(resolution).  volume may be NULL:
+ * the englobing volume is then the domain (environment_body.cpp:76). */
+int64_t sbsb200_grid_node_count(const uint32_t resolution[3]);
+int sbsb200_grid_node_position(const double domain_min[3], const double domain_max[3],
+                               const uint32_t resolution[3], int64_t node, double position[3]);
+int sbsb200_add_sdf_grid(sbsb200_ctx* ctx, const double domain_min[3], const double domain_max[3],
+                         const uint32_t resolution[3], const double* node_values, int64_t n_nodes,
+                         const double volume[6]);
+
+/* environment_body_t(sim, id, geometry, domain, resolution) (environment_body.cpp:12-78): the domain
+ * is extended to the triangle mesh and inflated as the reference does (:52-65), the signed distance
+ * to the mesh (Discregrid::MeshDistance: closest triangle, sign from the angle-weighted pseudo-normal
+ * of the closest feature) is sampled at every grid node ON THE DEVICE, and the body collides through
+ * the resulting grid.  positions: 3*nV doubles; triangles: 3*nF vertex indices of a closed,
+ * consistently oriented mesh; domain = {min xyz, max xyz}; resolution NULL = {10, 10, 10}
+ * (environment_body.h:24). */
+int sbsb200_add_sdf_mesh(sbsb200_ctx* ctx, int64_t nV, const double* positions, int64_t nF,
+                         const uint32_t* triangles, const double domain[6], const uint32_t resolution[3]);
+/* The extended domain alone (environment_body.cpp:52-65; host arithmetic, no context needed). */
+int sbsb200_mesh_sdf_domain(int64_t nV, const double* positions, const double domain[6],
+                            double extended[6]);
+
+/* The grid of an sdf body added by sbsb200_add_sdf_grid / _mesh: domain {min xyz, max xyz},
+ * resolution, node values (capacity cap; pass NULL to query).  Returns the node count, < 0 on error. */
+int64_t sbsb200_get_sdf_grid(sbsb200_ctx* ctx, int body, double domain[6], uint32_t resolution[3],
+                             double* node_values, int64_t cap);
+
+/* sdf_model_t::evaluate (sdf_model.cpp:66-75) of an sdf body at n points, on the device, in the
+ * context's precision: signed distance (DBL_MAX outside a grid's domain) and gradient (3*n).
+ * Requires sbsb200_finalize. */
+int sbsb200_eval_sdf(sbsb200_ctx* ctx, int body, int64_t n, const double* points, double* distance,
+                     double* gradient);
+
 /* Boundary extraction, graph colouring, region partition, SoA upload, BVH build.  Replaces
  * the incremental topology build (src/physics/topology.cpp:904-956) and
  * tetrahedral_mesh_boundary_t::extract_boundary_surface

@@ -65,6 +65,17 @@ def lib():
                                         C.c_double, C.c_double, C.c_double, _dp, _dp]
         L.orc_green_project.restype = C.c_int
         L.orc_boundary_surface.argtypes = [C.c_int, C.c_int, _u32p, _u32p, _u32p, _i32p]
+        L.orc_grid_node_count.argtypes = [_u32p]
+        L.orc_grid_node_count.restype = C.c_int64
+        L.orc_grid_node_position.argtypes = [_dp, _dp, _u32p, C.c_int64, _dp]
+        L.orc_grid_shape.argtypes = [_dp, _dp, _dp]
+        L.orc_grid_interpolate.argtypes = [_dp, _dp, _u32p, _dp, _dp, _dp]
+        L.orc_grid_interpolate.restype = C.c_double
+        L.orc_mesh_signed_distance.argtypes = [C.c_int, _dp, C.c_int, _u32p, C.c_int, _dp, _dp]
+        L.orc_mesh_sdf_domain.argtypes = [C.c_int, _dp, _dp, _dp]
+        L.orc_bake_mesh_sdf.argtypes = [C.c_int, _dp, C.c_int, _u32p, _dp, _u32p, _dp, _dp, C.c_int64]
+        L.orc_bake_mesh_sdf.restype = C.c_int64
+        L.orc_add_sdf_grid.argtypes = [C.c_void_p, _dp, _dp, _u32p, _dp, _dp]
         _lib = L
     return _lib
 
@@ -129,6 +140,69 @@ def boundary_surface(nV, tets):
     return s2t[:nvs].copy(), tris[:ntri.value].copy()
 
 
+def grid_node_count(res):
+    return int(lib().orc_grid_node_count(_u32(res).ctypes.data_as(_u32p)))
+
+
+def grid_node_positions(dmin, dmax, res):
+    """Positions of all nodes of a CubicLagrangeDiscreteGrid, in node order."""
+    dmin, dmax, res = _f64(dmin), _f64(dmax), _u32(res)
+    n = grid_node_count(res)
+    out = np.empty((n, 3))
+    x = np.empty(3)
+    f = lib().orc_grid_node_position
+    for l in range(n):
+        f(_d(dmin), _d(dmax), res.ctypes.data_as(_u32p), l, _d(x))
+        out[l] = x
+    return out
+
+
+def grid_shape(xi):
+    N = np.empty(32)
+    dN = np.empty((32, 3))
+    lib().orc_grid_shape(_d(_f64(xi)), _d(N), _d(dN))
+    return N, dN
+
+
+def grid_interpolate(dmin, dmax, res, nodes, points):
+    """CubicLagrangeDiscreteGrid::interpolate at every point: (values, gradients)."""
+    dmin, dmax, res, nodes = _f64(dmin), _f64(dmax), _u32(res), _f64(nodes)
+    pts = _f64(points).reshape(-1, 3)
+    val = np.empty(len(pts))
+    grad = np.empty((len(pts), 3))
+    g = np.empty(3)
+    f = lib().orc_grid_interpolate
+    for i, p in enumerate(pts):
+        val[i] = f(_d(dmin), _d(dmax), res.ctypes.data_as(_u32p), _d(nodes), _d(np.ascontiguousarray(p)), _d(g))
+        grad[i] = g
+    return val, grad
+
+
+def mesh_signed_distance(x, faces, points):
+    x, faces, pts = _f64(x).reshape(-1, 3), _u32(faces).reshape(-1, 3), _f64(points).reshape(-1, 3)
+    out = np.empty(len(pts))
+    lib().orc_mesh_signed_distance(len(x), _d(x), len(faces), faces.ctypes.data_as(_u32p), len(pts), _d(pts), _d(out))
+    return out
+
+
+def mesh_sdf_domain(x, domain):
+    x = _f64(x).reshape(-1, 3)
+    out = np.empty(6)
+    lib().orc_mesh_sdf_domain(len(x), _d(x), _d(_f64(domain).reshape(6)), _d(out))
+    return out
+
+
+def bake_mesh_sdf(x, faces, domain, res):
+    """environment_body_t(sim, id, geometry, domain, resolution): (extended domain[6], node values)."""
+    x, faces, res = _f64(x).reshape(-1, 3), _u32(faces).reshape(-1, 3), _u32(res)
+    n = grid_node_count(res)
+    nodes = np.empty(n)
+    dom = np.empty(6)
+    lib().orc_bake_mesh_sdf(len(x), _d(x), len(faces), faces.ctypes.data_as(_u32p), _d(_f64(domain).reshape(6)),
+                            res.ctypes.data_as(_u32p), _d(dom), _d(nodes), n)
+    return dom, nodes
+
+
 class World:
     """The reference's simulation_t + timestep_t restated (see xpbd_oracle.h)."""
 
@@ -174,6 +248,17 @@ class World:
 
     def add_sdf_box(self, bmin, bmax, volume):
         return lib().orc_add_sdf_box(self._h, _d(_f64(bmin)), _d(_f64(bmax)), _d(_f64(volume).reshape(6)))
+
+    def add_sdf_grid(self, dmin, dmax, res, nodes, volume=None):
+        vol = _d(_f64(volume).reshape(6)) if volume is not None else None
+        return lib().orc_add_sdf_grid(self._h, _d(_f64(dmin)), _d(_f64(dmax)), _u32(res).ctypes.data_as(_u32p),
+                                      _d(_f64(nodes)), vol)
+
+    def add_sdf_mesh(self, x, faces, domain, res=None):
+        """environment_body_t(sim, id, geometry, domain, resolution) (environment_body.cpp:12-78)."""
+        res = (10, 10, 10) if res is None else res
+        dom, nodes = bake_mesh_sdf(x, faces, domain, res)
+        return self.add_sdf_grid(dom[:3], dom[3:], res, nodes, dom)
 
     def constraint_count(self):
         return lib().orc_constraint_count(self._h)

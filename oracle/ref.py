@@ -49,6 +49,10 @@ def lib():
         L.ref_add_sdf_plane.argtypes = [vp, _dp, _dp, _dp]
         L.ref_add_sdf_sphere.argtypes = [vp, _dp, C.c_double, _dp]
         L.ref_add_sdf_box.argtypes = [vp, _dp, _dp, _dp]
+        L.ref_add_sdf_mesh.argtypes = [vp, C.c_int, _dp, C.c_int, _u32p, _dp, _u32p]
+        L.ref_add_sdf_grid.argtypes = [vp, _dp, _dp, _u32p, _dp, _dp]
+        L.ref_sdf_evaluate.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, _dp]
+        L.ref_get_volume.argtypes = [vp, C.c_int, _dp]
         L.ref_constraint_count.argtypes = [vp]
         L.ref_set_constraint_order.argtypes = [vp, _u32p, C.c_int]
         L.ref_upload.argtypes = [vp, C.c_int, _dp, _dp]
@@ -109,6 +113,34 @@ class World:
 
     def add_sdf_box(self, bmin, bmax, volume):
         return lib().ref_add_sdf_box(self._h, _d(_f64(bmin)), _d(_f64(bmax)), _d(_f64(volume).reshape(6)))
+
+    def add_sdf_mesh(self, x, faces, domain, res=None):
+        """environment_body_t(sim, id, geometry, domain, resolution): the reference's own bake."""
+        res = (10, 10, 10) if res is None else res
+        x = _f64(x).reshape(-1, 3)
+        faces = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+        res = np.ascontiguousarray(res, dtype=np.uint32)
+        return lib().ref_add_sdf_mesh(self._h, len(x), _d(x), len(faces), faces.ctypes.data_as(_u32p),
+                                      _d(_f64(domain).reshape(6)), res.ctypes.data_as(_u32p))
+
+    def add_sdf_grid(self, dmin, dmax, res, nodes, volume=None):
+        res = np.ascontiguousarray(res, dtype=np.uint32)
+        vol = _d(_f64(volume).reshape(6)) if volume is not None else None
+        return lib().ref_add_sdf_grid(self._h, _d(_f64(dmin)), _d(_f64(dmax)), res.ctypes.data_as(_u32p),
+                                      _d(_f64(nodes)), vol)
+
+    def sdf_evaluate(self, body, points):
+        pts = _f64(points).reshape(-1, 3)
+        sd = np.empty(len(pts))
+        g = np.empty((len(pts), 3))
+        if lib().ref_sdf_evaluate(self._h, body, len(pts), _d(pts), _d(sd), _d(g)):
+            raise RuntimeError("not an environment body")
+        return sd, g
+
+    def volume(self, body):
+        out = np.empty(6)
+        lib().ref_get_volume(self._h, body, _d(out))
+        return out
 
     def constraint_count(self):
         return lib().ref_constraint_count(self._h)

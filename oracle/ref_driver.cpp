@@ -192,6 +192,72 @@ int ref_add_sdf_box(void* h, const double bmin[3], const double bmax[3], const d
     return add_env(static_cast<world*>(h), collision::sdf_model_t{f, volume});
 }
 
+// environment_body_t(simulation, id, geometry, domain, resolution) — the reference's own bake
+// (environment_body.cpp:12-78) over the shim's Discregrid stand-ins.  geometry_t holds float positions.
+int ref_add_sdf_mesh(void* h, int nV, const double* x, int nF, const uint32_t* faces, const double dom[6],
+                     const uint32_t res[3])
+{
+    world* w = static_cast<world*>(h);
+    common::geometry_t g;
+    for (int i = 0; i < 3 * nV; ++i)
+        g.positions.push_back(static_cast<float>(x[i]));
+    for (int i = 0; i < 3 * nF; ++i)
+        g.indices.push_back(static_cast<int>(faces[i]));
+    g.geometry_type = common::geometry_t::geometry_type_t::triangle;
+    g.set_color(100, 100, 100);
+    Eigen::AlignedBox3d const domain{Eigen::Vector3d{dom[0], dom[1], dom[2]}, Eigen::Vector3d{dom[3], dom[4], dom[5]}};
+    auto const idx = static_cast<index_type>(w->sim.bodies().size());
+    w->sim.add_body(std::make_unique<environment_body_t>(w->sim, idx, g, domain,
+                                                         std::array<unsigned int, 3u>{res[0], res[1], res[2]}));
+    w->is_tet.push_back(0);
+    w->cd_ready = false;
+    return static_cast<int>(idx);
+}
+
+// sdf_model_t(Discregrid::CubicLagrangeDiscreteGrid const&) (sdf_model.cpp:18) with given node values:
+// addFunction samples its argument at the nodes in node order, so a counting functor installs them.
+int ref_add_sdf_grid(void* h, const double dmin[3], const double dmax[3], const uint32_t res[3], const double* nodes,
+                     const double vol[6])
+{
+    Eigen::AlignedBox3d const domain{Eigen::Vector3d{dmin[0], dmin[1], dmin[2]}, Eigen::Vector3d{dmax[0], dmax[1], dmax[2]}};
+    Discregrid::CubicLagrangeDiscreteGrid grid(domain, {res[0], res[1], res[2]});
+    std::size_t next = 0;
+    grid.addFunction([&](Eigen::Vector3d const&) { return nodes[next++]; });
+    collision::sdf_model_t model(grid);
+    model.volume() = vol ? Eigen::AlignedBox3d{Eigen::Vector3d{vol[0], vol[1], vol[2]}, Eigen::Vector3d{vol[3], vol[4], vol[5]}}
+                         : domain;
+    return add_env(static_cast<world*>(h), model);
+}
+
+// sdf_model_t::evaluate (sdf_model.cpp:66-75) of an environment body at n points
+int ref_sdf_evaluate(void* h, int body, int n, const double* pts, double* sd, double* grad)
+{
+    world* w = static_cast<world*>(h);
+    auto const* env = dynamic_cast<environment_body_t const*>(w->sim.bodies()[static_cast<std::size_t>(body)].get());
+    if (!env)
+        return -1;
+    for (int i = 0; i < n; ++i)
+    {
+        auto const [d, g] = env->sdf().evaluate(Eigen::Vector3d{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]});
+        sd[i]             = d;
+        for (int k = 0; k < 3; ++k)
+            grad[3 * i + k] = g(k);
+    }
+    return 0;
+}
+
+int ref_get_volume(void* h, int body, double out[6])
+{
+    world* w       = static_cast<world*>(h);
+    auto const& vb = w->sim.bodies()[static_cast<std::size_t>(body)]->collision_model().volume();
+    for (int k = 0; k < 3; ++k)
+    {
+        out[k]     = vb.min()(k);
+        out[3 + k] = vb.max()(k);
+    }
+    return 0;
+}
+
 int ref_constraint_count(void* h) { return static_cast<int>(static_cast<world*>(h)->sim.constraints().size()); }
 
 // the reference run "with constraints permuted": reorder simulation_t::constraints_

@@ -494,7 +494,7 @@ typedef struct
 } coll_constraint;
 
 enum { B_TET = 0, B_SDF = 1 };
-enum { SDF_PLANE = 0, SDF_SPHERE = 1, SDF_BOX = 2 };
+enum { SDF_PLANE = 0, SDF_SPHERE = 1, SDF_BOX = 2, SDF_GRID = 3 };
 typedef struct
 {
     int kind;
@@ -506,8 +506,10 @@ typedef struct
     double* surf_pos;      /* visual-model vertex positions: what detection sees */
     /* sdf body */
     int sdf_kind;
-    double a[3], b[3], r; /* plane: a=normal, r=offset; sphere: a=centre, r; box: a=min,b=max */
+    double a[3], b[3], r; /* plane: a=normal, r=offset; sphere: a=centre, r; box: a=min,b=max; grid: domain a..b */
     double volume[6];
+    uint32_t grid_n[3];   /* grid: cells per axis */
+    double* grid_nodes;   /* grid: node values, orc_grid_node_count(grid_n) of them */
 } body;
 
 struct orc_world
@@ -540,6 +542,7 @@ void orc_destroy(orc_world* w)
         free(w->bodies[i].p);
         free(w->bodies[i].surf_to_tet);
         free(w->bodies[i].surf_pos);
+        free(w->bodies[i].grid_nodes);
     }
     free(w->bodies);
     free(w->cons);
@@ -671,11 +674,406 @@ int orc_add_sdf_box(orc_world* w, const double bmin[3], const double bmax[3], co
     return add_sdf(w, SDF_BOX, bmin, bmax, 0., vol);
 }
 
-/* sdf_model_t::evaluate (sdf_model.cpp:66-75) for analytic SDFs: (signed distance, gradient) */
+
+/* ---- grid SDF: Discregrid::CubicLagrangeDiscreteGrid restated ---------------------------------
+ * Discregrid (github.com/Q-Minh/Discregrid @ master, CMakeLists.txt:95-100 — a moving branch, not
+ * vendored, absent from this image) is restated from its published algorithm: PARITY UNPINNED at
+ * this boundary.  What pins the restatement is mathematics, checked in
+ * tests/test_oracle_cpu.py: the 32 shape functions are a nodal basis (N_i(x_j) = delta_ij, partition
+ * of unity) and reproduce every polynomial of degree <= 3 exactly, values and gradients.
+ *
+ * Nodes of an (nx, ny, nz)-cell grid: first the (nx+1)(ny+1)(nz+1) cell corners, x fastest; then two
+ * nodes at 1/3 and 2/3 of every x-edge (edge index x fastest, then y, then z), of every y-edge (y
+ * fastest, then z, then x) and of every z-edge (z fastest, then x, then y). */
+static void grid_counts(const uint32_t n[3], uint64_t* nv, uint64_t* nex, uint64_t* ney, uint64_t* nez)
+{
+    *nv  = (uint64_t)(n[0] + 1) * (n[1] + 1) * (n[2] + 1);
+    *nex = (uint64_t)n[0] * (n[1] + 1) * (n[2] + 1);
+    *ney = (uint64_t)(n[0] + 1) * n[1] * (n[2] + 1);
+    *nez = (uint64_t)(n[0] + 1) * (n[1] + 1) * n[2];
+}
+int64_t orc_grid_node_count(const uint32_t n[3])
+{
+    uint64_t nv, nex, ney, nez;
+    grid_counts(n, &nv, &nex, &ney, &nez);
+    return (int64_t)(nv + 2 * (nex + ney + nez));
+}
+/* CubicLagrangeDiscreteGrid::indexToNodePosition */
+void orc_grid_node_position(const double dmin[3], const double dmax[3], const uint32_t n[3], int64_t l,
+                            double x[3])
+{
+    uint64_t nv, nex, ney, nez;
+    grid_counts(n, &nv, &nex, &ney, &nez);
+    double cell[3];
+    for (int d = 0; d < 3; ++d)
+        cell[d] = (dmax[d] - dmin[d]) / (double)n[d];
+    uint64_t u = (uint64_t)l, ijk[3];
+    int axis = -1;
+    if (u < nv)
+    {
+        uint64_t const nxy = (uint64_t)(n[0] + 1) * (n[1] + 1), t = u % nxy;
+        ijk[2] = u / nxy;
+        ijk[1] = t / (n[0] + 1);
+        ijk[0] = t % (n[0] + 1);
+    }
+    else if (u < nv + 2 * nex)
+    {
+        u -= nv;
+        uint64_t const e = u / 2, t = e % ((uint64_t)(n[1] + 1) * n[0]);
+        ijk[2] = e / ((uint64_t)(n[1] + 1) * n[0]);
+        ijk[1] = t / n[0];
+        ijk[0] = t % n[0];
+        axis   = 0;
+    }
+    else if (u < nv + 2 * (nex + ney))
+    {
+        u -= nv + 2 * nex;
+        uint64_t const e = u / 2, t = e % ((uint64_t)(n[2] + 1) * n[1]);
+        ijk[0] = e / ((uint64_t)(n[2] + 1) * n[1]);
+        ijk[2] = t / n[1];
+        ijk[1] = t % n[1];
+        axis   = 1;
+    }
+    else
+    {
+        u -= nv + 2 * (nex + ney);
+        uint64_t const e = u / 2, t = e % ((uint64_t)(n[0] + 1) * n[2]);
+        ijk[1] = e / ((uint64_t)(n[0] + 1) * n[2]);
+        ijk[0] = t / n[2];
+        ijk[2] = t % n[2];
+        axis   = 2;
+    }
+    for (int d = 0; d < 3; ++d)
+        x[d] = dmin[d] + cell[d] * (double)ijk[d];
+    if (axis >= 0)
+        x[axis] += (1.0 + (double)(u % 2)) / 3.0 * cell[axis];
+}
+/* node indices of cell (i, j, k) in the order of the shape functions */
+static void grid_cell_nodes(const uint32_t n[3], uint64_t i, uint64_t j, uint64_t k, uint64_t c[32])
+{
+    uint64_t nv, nex, ney, nez;
+    grid_counts(n, &nv, &nex, &ney, &nez);
+    uint64_t const nx = n[0], ny = n[1], nz = n[2];
+    for (int q = 0; q < 8; ++q)
+        c[q] = (nx + 1) * (ny + 1) * (k + (uint64_t)(q >> 2 & 1)) + (nx + 1) * (j + (uint64_t)(q >> 1 & 1)) + i +
+               (uint64_t)(q & 1);
+    uint64_t off = nv;
+    for (int q = 0; q < 4; ++q) /* x-edges: (j, k), (j, k+1), (j+1, k), (j+1, k+1) */
+    {
+        c[8 + 2 * q]     = off + 2 * (nx * (ny + 1) * (k + (uint64_t)(q & 1)) + nx * (j + (uint64_t)(q >> 1)) + i);
+        c[8 + 2 * q + 1] = c[8 + 2 * q] + 1;
+    }
+    off += 2 * nex;
+    for (int q = 0; q < 4; ++q) /* y-edges: (i, k), (i+1, k), (i, k+1), (i+1, k+1) */
+    {
+        c[16 + 2 * q]     = off + 2 * (ny * (nz + 1) * (i + (uint64_t)(q & 1)) + ny * (k + (uint64_t)(q >> 1)) + j);
+        c[16 + 2 * q + 1] = c[16 + 2 * q] + 1;
+    }
+    off += 2 * ney;
+    for (int q = 0; q < 4; ++q) /* z-edges: (i, j), (i, j+1), (i+1, j), (i+1, j+1) */
+    {
+        c[24 + 2 * q]     = off + 2 * (nz * (nx + 1) * (j + (uint64_t)(q & 1)) + nz * (i + (uint64_t)(q >> 1)) + k);
+        c[24 + 2 * q + 1] = c[24 + 2 * q] + 1;
+    }
+}
+/* 32-node serendipity cubic shape functions on [-1, 1]^3 and their derivatives
+ * (CubicLagrangeDiscreteGrid's shape_function_): corners N = (1/64)(1 +- x)(1 +- y)(1 +- z)
+ * (9(x^2+y^2+z^2) - 19); edge nodes at -+1/3 along x: (9/64)(1 - x^2)(1 -+ 3x)(1 +- y)(1 +- z). */
+void orc_grid_shape(const double xi[3], double N[32], double dN[32][3])
+{
+    double const x = xi[0], y = xi[1], z = xi[2];
+    double const r2 = x * x + y * y + z * z;
+    double const s[3][2] = {{1 - x, 1 + x}, {1 - y, 1 + y}, {1 - z, 1 + z}};
+    for (int q = 0; q < 8; ++q)
+    {
+        double const a = s[0][q & 1], b = s[1][q >> 1 & 1], c = s[2][q >> 2 & 1];
+        double const sa = (q & 1) ? 1. : -1., sb = (q >> 1 & 1) ? 1. : -1., sc = (q >> 2 & 1) ? 1. : -1.;
+        double const f = 9. * r2 - 19.;
+        N[q]     = a * b * c * f / 64.;
+        dN[q][0] = (sa * b * c * f + a * b * c * 18. * x) / 64.;
+        dN[q][1] = (a * sb * c * f + a * b * c * 18. * y) / 64.;
+        dN[q][2] = (a * b * sc * f + a * b * c * 18. * z) / 64.;
+    }
+    /* edge nodes: axis t carries the cubic, (u, v) select the edge */
+    static const int uv[3][2]  = {{1, 2}, {0, 2}, {0, 1}};
+    /* sign selectors of the 4 edges of each family, in the order of grid_cell_nodes */
+    static const int sel[3][4][2] = {
+        {{0, 0}, {0, 1}, {1, 0}, {1, 1}}, /* x-edges: (y, z) = (-,-), (-,+), (+,-), (+,+) */
+        {{0, 0}, {1, 0}, {0, 1}, {1, 1}}, /* y-edges: (x, z) = (-,-), (+,-), (-,+), (+,+) */
+        {{0, 0}, {0, 1}, {1, 0}, {1, 1}}, /* z-edges: (x, y) = (-,-), (-,+), (+,-), (+,+) */
+    };
+    for (int t = 0; t < 3; ++t)
+    {
+        double const w = xi[t];
+        int const u = uv[t][0], v = uv[t][1];
+        for (int q = 0; q < 4; ++q)
+        {
+            double const fu = s[u][sel[t][q][0]], fv = s[v][sel[t][q][1]];
+            double const du = sel[t][q][0] ? 1. : -1., dv = sel[t][q][1] ? 1. : -1.;
+            for (int h = 0; h < 2; ++h)
+            {
+                double const sg = h ? 3. : -3.;               /* node at w = -1/3 (h = 0) or +1/3 */
+                double const g  = (1. - w * w) * (1. + sg * w); /* cubic along the edge */
+                double const dg = -2. * w * (1. + sg * w) + (1. - w * w) * sg;
+                int const id    = 8 + 8 * t + 2 * q + h;
+                N[id]           = 9. / 64. * g * fu * fv;
+                dN[id][t]       = 9. / 64. * dg * fu * fv;
+                dN[id][u]       = 9. / 64. * g * du * fv;
+                dN[id][v]       = 9. / 64. * g * fu * dv;
+            }
+        }
+    }
+}
+/* CubicLagrangeDiscreteGrid::interpolate(field, x, &gradient) as sdf_model_t::evaluate calls it
+ * (sdf_model.cpp:71-74): DBL_MAX outside the domain. */
+double orc_grid_interpolate(const double dmin[3], const double dmax[3], const uint32_t n[3],
+                            const double* nodes, const double p[3], double grad[3])
+{
+    uint64_t ijk[3];
+    double xi[3], c0[3];
+    for (int d = 0; d < 3; ++d)
+    {
+        if (!(dmin[d] <= p[d] && p[d] <= dmax[d]))
+        {
+            if (grad)
+                grad[0] = grad[1] = grad[2] = 0.;
+            return 1.7976931348623157e308;
+        }
+        double const cell = (dmax[d] - dmin[d]) / (double)n[d];
+        uint64_t m        = (uint64_t)((p[d] - dmin[d]) * (1. / cell));
+        if (m >= n[d])
+            m = n[d] - 1;
+        ijk[d]          = m;
+        double const lo = dmin[d] + cell * (double)m, hi = lo + cell;
+        c0[d]           = 2. / (hi - lo);
+        xi[d]           = c0[d] * p[d] - (hi + lo) / (hi - lo);
+    }
+    uint64_t c[32];
+    double N[32], dN[32][3];
+    grid_cell_nodes(n, ijk[0], ijk[1], ijk[2], c);
+    orc_grid_shape(xi, N, dN);
+    double phi = 0., g[3] = {0., 0., 0.};
+    for (int q = 0; q < 32; ++q)
+    {
+        double const v = nodes[c[q]];
+        phi += N[q] * v;
+        for (int d = 0; d < 3; ++d)
+            g[d] += dN[q][d] * v;
+    }
+    if (grad)
+        for (int d = 0; d < 3; ++d)
+            grad[d] = g[d] * c0[d];
+    return phi;
+}
+
+/* ---- Discregrid::MeshDistance restated (brute force over the triangles; Discregrid's BVH and cache
+ * only accelerate the same query): unsigned distance to the closest triangle, sign from the
+ * angle-weighted pseudo-normal of the closest feature (face, edge or vertex).  PARITY UNPINNED, as
+ * above; pinned by analytic shapes in the tests (cube, octahedron). ---------------------------------- */
+typedef struct
+{
+    int nV, nF;
+    const double* x;
+    const uint32_t* f;
+    double* fn; /* 3*nF unit face normals */
+    double* vn; /* 3*nV angle-weighted vertex normals */
+    double* en; /* 9*nF: pseudo-normal of edge (i -> i+1) of face: own normal + the opposite face's */
+} mesh_dist;
+static void v3sub(const double* a, const double* b, double* r) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+static double v3dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static void v3cross(const double* a, const double* b, double* r)
+{
+    r[0] = a[1] * b[2] - a[2] * b[1];
+    r[1] = a[2] * b[0] - a[0] * b[2];
+    r[2] = a[0] * b[1] - a[1] * b[0];
+}
+static void mesh_dist_init(mesh_dist* m, int nV, const double* x, int nF, const uint32_t* f)
+{
+    m->nV = nV; m->nF = nF; m->x = x; m->f = f;
+    m->fn = (double*)calloc((size_t)(3 * nF + 3), sizeof(double));
+    m->vn = (double*)calloc((size_t)(3 * nV + 3), sizeof(double));
+    m->en = (double*)calloc((size_t)(9 * nF + 9), sizeof(double));
+    for (int t = 0; t < nF; ++t)
+    {
+        const double *p0 = &x[3 * f[3 * t]], *p1 = &x[3 * f[3 * t + 1]], *p2 = &x[3 * f[3 * t + 2]];
+        double e[3][3], n[3];
+        v3sub(p1, p0, e[0]); v3sub(p2, p1, e[1]); v3sub(p0, p2, e[2]);
+        double a[3];
+        v3sub(p2, p0, a);
+        v3cross(e[0], a, n);
+        double const ln = sqrt(v3dot(n, n));
+        for (int d = 0; d < 3; ++d)
+            m->fn[3 * t + d] = n[d] / ln;
+        double len[3];
+        for (int k = 0; k < 3; ++k)
+            len[k] = sqrt(v3dot(e[k], e[k]));
+        for (int k = 0; k < 3; ++k)
+        { /* interior angle at corner k: between edge k and the reversed previous edge */
+            int const pk = (k + 2) % 3;
+            double cs    = -v3dot(e[k], e[pk]) / (len[k] * len[pk]);
+            cs           = cs > 1. ? 1. : cs < -1. ? -1. : cs;
+            double const al = acos(cs);
+            for (int d = 0; d < 3; ++d)
+                m->vn[3 * f[3 * t + k] + d] += al * m->fn[3 * t + d];
+        }
+    }
+    for (int t = 0; t < nF; ++t)
+        for (int k = 0; k < 3; ++k)
+        {
+            uint32_t const a = f[3 * t + k], b = f[3 * t + (k + 1) % 3];
+            for (int d = 0; d < 3; ++d)
+                m->en[9 * t + 3 * k + d] = m->fn[3 * t + d];
+            for (int o = 0; o < nF; ++o) /* the face holding the opposite half-edge b -> a */
+            {
+                if (o == t)
+                    continue;
+                int hit = 0;
+                for (int q = 0; q < 3; ++q)
+                    hit |= f[3 * o + q] == b && f[3 * o + (q + 1) % 3] == a;
+                if (hit)
+                {
+                    for (int d = 0; d < 3; ++d)
+                        m->en[9 * t + 3 * k + d] += m->fn[3 * o + d];
+                    break;
+                }
+            }
+        }
+}
+static void mesh_dist_free(mesh_dist* m) { free(m->fn); free(m->vn); free(m->en); }
+/* closest point of triangle (a, b, c) to p; feature: 0-2 vertex, 3-5 edge (k -> k+1), 6 face */
+static double closest_on_triangle(const double* p, const double* a, const double* b, const double* c, double* q,
+                                  int* feature)
+{
+    double ab[3], ac[3], ap[3], bp[3], cp[3];
+    v3sub(b, a, ab); v3sub(c, a, ac); v3sub(p, a, ap);
+    double const d1 = v3dot(ab, ap), d2 = v3dot(ac, ap);
+    double s = 0., t = 0.;
+    if (d1 <= 0. && d2 <= 0.) { *feature = 0; s = 0.; t = 0.; goto done; }
+    v3sub(p, b, bp);
+    double const d3 = v3dot(ab, bp), d4 = v3dot(ac, bp);
+    if (d3 >= 0. && d4 <= d3) { *feature = 1; s = 1.; t = 0.; goto done; }
+    double const vc = d1 * d4 - d3 * d2;
+    if (vc <= 0. && d1 >= 0. && d3 <= 0.) { *feature = 3; s = d1 / (d1 - d3); t = 0.; goto done; }
+    v3sub(p, c, cp);
+    double const d5 = v3dot(ab, cp), d6 = v3dot(ac, cp);
+    if (d6 >= 0. && d5 <= d6) { *feature = 2; s = 0.; t = 1.; goto done; }
+    double const vb = d5 * d2 - d1 * d6;
+    if (vb <= 0. && d2 >= 0. && d6 <= 0.) { *feature = 5; s = 0.; t = d2 / (d2 - d6); goto done; }
+    double const va = d3 * d6 - d5 * d4;
+    if (va <= 0. && (d4 - d3) >= 0. && (d5 - d6) >= 0.)
+    {
+        double const w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        *feature = 4; s = 1. - w; t = w; goto done;
+    }
+    {
+        double const den = 1. / (va + vb + vc);
+        *feature = 6; s = vb * den; t = vc * den;
+    }
+done:
+    for (int d = 0; d < 3; ++d)
+        q[d] = a[d] + s * ab[d] + t * ac[d];
+    double r[3];
+    v3sub(p, q, r);
+    return v3dot(r, r);
+}
+static double mesh_signed_distance(const mesh_dist* m, const double p[3])
+{
+    double best = 1.7976931348623157e308, bq[3] = {0, 0, 0};
+    int bf = -1, bfeat = 6;
+    for (int t = 0; t < m->nF; ++t)
+    {
+        double q[3];
+        int feat;
+        double const d2 = closest_on_triangle(p, &m->x[3 * m->f[3 * t]], &m->x[3 * m->f[3 * t + 1]],
+                                              &m->x[3 * m->f[3 * t + 2]], q, &feat);
+        if (d2 < best)
+        {
+            best = d2; bf = t; bfeat = feat;
+            memcpy(bq, q, sizeof bq);
+        }
+    }
+    if (bf < 0)
+        return best;
+    const double* n = bfeat < 3 ? &m->vn[3 * m->f[3 * bf + bfeat]] : bfeat < 6 ? &m->en[9 * bf + 3 * (bfeat - 3)]
+                                                                              : &m->fn[3 * bf];
+    double r[3];
+    v3sub(p, bq, r);
+    double const dist = sqrt(best);
+    return v3dot(r, n) < 0. ? -dist : dist;
+}
+void orc_mesh_signed_distance(int nV, const double* x, int nF, const uint32_t* faces, int n, const double* points,
+                              double* out)
+{
+    mesh_dist m;
+    mesh_dist_init(&m, nV, x, nF, faces);
+    for (int i = 0; i < n; ++i)
+        out[i] = mesh_signed_distance(&m, &points[3 * i]);
+    mesh_dist_free(&m);
+}
+/* environment_body_t(simulation, id, geometry, domain, resolution) (environment_body.cpp:12-78): the
+ * domain is extended to the mesh and inflated ONCE PER MESH VERTEX (the growth statements sit inside
+ * the outer vertex loop, :55-65), the mesh distance is sampled at every grid node (:67-74). */
+void orc_mesh_sdf_domain(int nV, const double* x, const double domain[6], double out[6])
+{
+    memcpy(out, domain, 6 * sizeof(double));
+    for (int v = 0; v < nV; ++v)
+    {
+        if (v == 0) /* the inner loop's extension is idempotent after the first pass */
+            for (int u = 0; u < nV; ++u)
+                for (int d = 0; d < 3; ++d)
+                {
+                    if (x[3 * u + d] < out[d]) out[d] = x[3 * u + d];
+                    if (x[3 * u + d] > out[3 + d]) out[3 + d] = x[3 * u + d];
+                }
+        for (int side = 1; side >= 0; --side)
+        {
+            double const dx = out[3] - out[0], dy = out[4] - out[1], dz = out[5] - out[2];
+            double const g  = 1.0e-3 * sqrt(dx * dx + dy * dy + dz * dz);
+            for (int d = 0; d < 3; ++d)
+                out[3 * side + d] += side ? g : -g;
+        }
+    }
+}
+int64_t orc_bake_mesh_sdf(int nV, const double* x, int nF, const uint32_t* faces, const double domain[6],
+                          const uint32_t res[3], double out_domain[6], double* nodes, int64_t cap)
+{
+    orc_mesh_sdf_domain(nV, x, domain, out_domain);
+    int64_t const nn = orc_grid_node_count(res);
+    if (!nodes || cap < nn)
+        return nn;
+    mesh_dist m;
+    mesh_dist_init(&m, nV, x, nF, faces);
+    for (int64_t l = 0; l < nn; ++l)
+    {
+        double p[3];
+        orc_grid_node_position(out_domain, out_domain + 3, res, l, p);
+        nodes[l] = mesh_signed_distance(&m, p);
+    }
+    mesh_dist_free(&m);
+    return nn;
+}
+/* environment_body_t holding a grid sdf_model_t (sdf_model.cpp:18, environment_body.cpp:75-77):
+ * volume() is the grid's domain unless given. */
+int orc_add_sdf_grid(orc_world* w, const double dmin[3], const double dmax[3], const uint32_t res[3],
+                     const double* nodes, const double vol[6])
+{
+    double v6[6] = {dmin[0], dmin[1], dmin[2], dmax[0], dmax[1], dmax[2]};
+    int const id = add_sdf(w, SDF_GRID, dmin, dmax, 0., vol ? vol : v6);
+    body* bd     = &w->bodies[id];
+    memcpy(bd->grid_n, res, sizeof bd->grid_n);
+    int64_t const nn = orc_grid_node_count(res);
+    bd->grid_nodes   = (double*)malloc(sizeof(double) * (size_t)nn);
+    memcpy(bd->grid_nodes, nodes, sizeof(double) * (size_t)nn);
+    return id;
+}
+
+/* sdf_model_t::evaluate (sdf_model.cpp:66-75): (signed distance, gradient) */
 static double sdf_eval(const body* s, const double p[3], double g[3])
 {
     switch (s->sdf_kind)
     {
+    case SDF_GRID:
+        return orc_grid_interpolate(s->a, s->b, s->grid_n, s->grid_nodes, p, g);
     case SDF_PLANE:
         g[0] = s->a[0];
         g[1] = s->a[1];

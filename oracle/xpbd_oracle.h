@@ -84,6 +84,27 @@ int orc_add_sdf_sphere(orc_world* w, const double centre[3], double radius,
 int orc_add_sdf_box(orc_world* w, const double bmin[3], const double bmax[3],
                     const double volume[6]);
 
+/* ---- grid SDFs (Discregrid restated; PARITY UNPINNED, see xpbd_oracle.c) ---------------------- */
+/* node count / node position / shape functions / interpolation of a CubicLagrangeDiscreteGrid with
+ * res cells per axis over [dmin, dmax] */
+int64_t orc_grid_node_count(const uint32_t res[3]);
+void orc_grid_node_position(const double dmin[3], const double dmax[3], const uint32_t res[3], int64_t l,
+                            double x[3]);
+void orc_grid_shape(const double xi[3], double N[32], double dN[32][3]);
+double orc_grid_interpolate(const double dmin[3], const double dmax[3], const uint32_t res[3],
+                            const double* nodes, const double p[3], double grad[3]);
+/* Discregrid::MeshDistance::signedDistanceCached at n points (closed, consistently oriented mesh) */
+void orc_mesh_signed_distance(int nV, const double* x, int nF, const uint32_t* faces, int n, const double* points,
+                              double* out);
+/* environment_body.cpp:52-66 (domain extension) and :12-78 (bake); returns the node count */
+void orc_mesh_sdf_domain(int nV, const double* x, const double domain[6], double out[6]);
+int64_t orc_bake_mesh_sdf(int nV, const double* x, int nF, const uint32_t* faces, const double domain[6],
+                          const uint32_t res[3], double out_domain[6], double* nodes, int64_t cap);
+/* environment_body_t with a grid sdf_model_t; vol = NULL: volume() is the grid's domain
+ * (environment_body.cpp:76) */
+int orc_add_sdf_grid(orc_world* w, const double dmin[3], const double dmax[3], const uint32_t res[3],
+                     const double* nodes, const double vol[6]);
+
 /* Number of elastic constraints (green + distance) in insertion order. */
 int orc_constraint_count(const orc_world* w);
 

@@ -25,6 +25,8 @@ EXPORTS = [
     "sbsb200_create", "sbsb200_destroy", "sbsb200_last_error", "sbsb200_set_stream", "sbsb200_set_schedule",
     "sbsb200_set_collision_compliance", "sbsb200_add_tet_body", "sbsb200_add_distance_constraints",
     "sbsb200_add_sdf_plane", "sbsb200_add_sdf_sphere", "sbsb200_add_sdf_box", "sbsb200_finalize",
+    "sbsb200_grid_node_count", "sbsb200_grid_node_position", "sbsb200_add_sdf_grid", "sbsb200_add_sdf_mesh", "sbsb200_mesh_sdf_domain",
+    "sbsb200_get_sdf_grid", "sbsb200_eval_sdf",
     "sbsb200_constraint_count", "sbsb200_get_constraint_order", "sbsb200_get_surface_map", "sbsb200_get_stats",
     "sbsb200_schedule_note",
     "sbsb200_upload", "sbsb200_download", "sbsb200_set_mass", "sbsb200_step", "sbsb200_step_host",
@@ -77,6 +79,15 @@ def load_library():
     L.sbsb200_add_sdf_plane.argtypes = [vp, _dp, _dp, _dp]
     L.sbsb200_add_sdf_sphere.argtypes = [vp, _dp, C.c_double, _dp]
     L.sbsb200_add_sdf_box.argtypes = [vp, _dp, _dp, _dp]
+    L.sbsb200_grid_node_count.argtypes = [_u32p]
+    L.sbsb200_grid_node_count.restype = C.c_int64
+    L.sbsb200_grid_node_position.argtypes = [_dp, _dp, _u32p, C.c_int64, _dp]
+    L.sbsb200_add_sdf_grid.argtypes = [vp, _dp, _dp, _u32p, _dp, C.c_int64, _dp]
+    L.sbsb200_add_sdf_mesh.argtypes = [vp, C.c_int64, _dp, C.c_int64, _u32p, _dp, _u32p]
+    L.sbsb200_mesh_sdf_domain.argtypes = [C.c_int64, _dp, _dp, _dp]
+    L.sbsb200_get_sdf_grid.argtypes = [vp, C.c_int, _dp, _u32p, _dp, C.c_int64]
+    L.sbsb200_get_sdf_grid.restype = C.c_int64
+    L.sbsb200_eval_sdf.argtypes = [vp, C.c_int, C.c_int64, _dp, _dp, _dp]
     L.sbsb200_finalize.argtypes = [vp]
     L.sbsb200_constraint_count.argtypes = [vp]
     L.sbsb200_constraint_count.restype = C.c_int64
@@ -107,6 +118,36 @@ def load_library():
     L.sbsb200_debug_read_trace.restype = C.c_int64
     _lib = L
     return L
+
+
+def grid_node_count(res):
+    """Nodes of a CubicLagrangeDiscreteGrid with res cells per axis (host arithmetic only)."""
+    r = np.ascontiguousarray(res, np.uint32)
+    return int(load_library().sbsb200_grid_node_count(r.ctypes.data_as(_u32p)))
+
+
+def grid_node_positions(dmin, dmax, res):
+    """Positions of all grid nodes in node order (host arithmetic only) — where to sample an SDF for add_sdf_grid."""
+    L = load_library()
+    r = np.ascontiguousarray(res, np.uint32)
+    lo, hi = _f64(dmin), _f64(dmax)
+    n = grid_node_count(r)
+    out = np.empty((n, 3))
+    x = np.empty(3)
+    for l in range(n):
+        if L.sbsb200_grid_node_position(_d(lo), _d(hi), r.ctypes.data_as(_u32p), l, _d(x)) != 0:
+            raise SbsError("bad grid")
+        out[l] = x
+    return out
+
+
+def mesh_sdf_domain(positions, domain):
+    """Grid domain environment_body_t's mesh constructor ends up with (environment_body.cpp:52-65)."""
+    x = _f64(positions).reshape(-1, 3)
+    out = np.empty(6)
+    if load_library().sbsb200_mesh_sdf_domain(x.shape[0], _d(x), _d(_f64(domain).reshape(6)), _d(out)) != 0:
+        raise SbsError("bad arguments")
+    return out
 
 
 def _f64(a):
@@ -182,6 +223,40 @@ class Simulation:
     def add_sdf_box(self, bmin, bmax, volume):
         return self._ck(self._L.sbsb200_add_sdf_box(self._h, _d(_f64(bmin)), _d(_f64(bmax)),
                                                     _d(_f64(volume).reshape(6))))
+
+    def add_sdf_grid(self, dmin, dmax, res, nodes, volume=None):
+        """environment_body_t with a discrete-grid sdf_model_t (sdf_model.cpp:18)."""
+        res = np.ascontiguousarray(res, np.uint32)
+        nodes = _f64(nodes)
+        vol = _d(_f64(volume).reshape(6)) if volume is not None else None
+        return self._ck(self._L.sbsb200_add_sdf_grid(self._h, _d(_f64(dmin)), _d(_f64(dmax)), res.ctypes.data_as(_u32p),
+                                                     _d(nodes), nodes.shape[0], vol))
+
+    def add_sdf_mesh(self, positions, triangles, domain, res=None):
+        """environment_body_t(sim, id, geometry, domain, resolution) (environment_body.cpp:12-78), baked on the device."""
+        x = _f64(positions).reshape(-1, 3)
+        tri = np.ascontiguousarray(triangles, np.uint32).reshape(-1, 3)
+        r = None if res is None else np.ascontiguousarray(res, np.uint32)
+        return self._ck(self._L.sbsb200_add_sdf_mesh(self._h, x.shape[0], _d(x), tri.shape[0], tri.ctypes.data_as(_u32p),
+                                                     _d(_f64(domain).reshape(6)),
+                                                     None if r is None else r.ctypes.data_as(_u32p)))
+
+    def sdf_grid(self, body):
+        """(domain[6], resolution[3], node values) of a grid sdf body."""
+        dom = np.empty(6)
+        res = np.empty(3, np.uint32)
+        n = self._ck(self._L.sbsb200_get_sdf_grid(self._h, body, _d(dom), res.ctypes.data_as(_u32p), None, 0))
+        nodes = np.empty(n)
+        self._ck(self._L.sbsb200_get_sdf_grid(self._h, body, _d(dom), res.ctypes.data_as(_u32p), _d(nodes), n))
+        return dom, res, nodes
+
+    def eval_sdf(self, body, points):
+        """sdf_model_t::evaluate on the device: (distances, gradients)."""
+        pts = _f64(points).reshape(-1, 3)
+        sd = np.empty(pts.shape[0])
+        g = np.empty((pts.shape[0], 3))
+        self._ck(self._L.sbsb200_eval_sdf(self._h, body, pts.shape[0], _d(pts), _d(sd), _d(g)))
+        return sd, g
 
     def finalize(self):
         self._ck(self._L.sbsb200_finalize(self._h))

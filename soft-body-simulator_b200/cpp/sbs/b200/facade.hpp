@@ -12,6 +12,8 @@
 //     solver_t::solve exist for source compatibility and throw: there is no CPU path.
 //   * sdf_model_t takes analytic shapes (plane, sphere, box) instead of a std::function
 //     (include/sbs/physics/collision/sdf_model.h:18-23): a host callback cannot run on the device.
+//     Discrete grids are there: from_grid (node values) and environment_body_t's triangle-mesh
+//     constructor (src/physics/environment_body.cpp:12-78), whose mesh distance is baked on the device.
 //   * particles() is a host mirror: it is refreshed from the device when read after a step, and
 //     written back (x, v, mass) before the next step when it was handed out mutable — the way
 //     main.cpp:158-165 pins a picked vertex by setting its mass to 0 between frames.
@@ -304,11 +306,11 @@ class collision_model_t
     index_type id_ = 0;
 };
 
-// include/sbs/physics/collision/sdf_model.h:15-44 (analytic shapes only, see the file comment)
+// include/sbs/physics/collision/sdf_model.h:15-44 (analytic shapes and discrete grids, see the file comment)
 class sdf_model_t : public collision_model_t
 {
   public:
-    enum class shape_t { plane, sphere, box };
+    enum class shape_t { plane, sphere, box, grid, mesh };
     model_type_t model_type() const override { return model_type_t::sdf; }
     // sdf_model.cpp:52-64
     static sdf_model_t from_plane(hyperplane3 const& plane, aligned_box3 const& volume)
@@ -338,15 +340,58 @@ class sdf_model_t : public collision_model_t
         m.volume() = volume;
         return m;
     }
+    // sdf_model_t(Discregrid::CubicLagrangeDiscreteGrid const&) (sdf_model.cpp:18): node values in Discregrid's
+    // node order over `domain` (positions: sbsb200_grid_node_position); volume() = the domain
+    static sdf_model_t from_grid(aligned_box3 const& domain, std::array<unsigned int, 3u> const& resolution,
+                                 std::vector<scalar_type> node_values)
+    {
+        sdf_model_t m;
+        m.shape_      = shape_t::grid;
+        m.a_          = domain.min();
+        m.b_          = domain.max();
+        m.resolution_ = resolution;
+        m.values_     = std::move(node_values);
+        m.volume()    = domain;
+        return m;
+    }
+    // the model environment_body_t's mesh constructor builds (environment_body.cpp:12-78): the grid is
+    // sampled on the device when the scene is built; a..b is the extended domain
+    static sdf_model_t from_mesh(std::vector<scalar_type> positions, std::vector<std::uint32_t> triangles,
+                                 aligned_box3 const& domain, std::array<unsigned int, 3u> const& resolution)
+    {
+        sdf_model_t m;
+        m.shape_            = shape_t::mesh;
+        m.resolution_       = resolution;
+        double const in[6]  = {domain.min()[0], domain.min()[1], domain.min()[2],
+                               domain.max()[0], domain.max()[1], domain.max()[2]};
+        double out[6];
+        if (sbsb200_mesh_sdf_domain(static_cast<std::int64_t>(positions.size() / 3), positions.data(), in, out) != 0)
+            throw std::invalid_argument("sbs-b200: bad obstacle mesh");
+        m.given_domain_ = domain;
+        m.a_            = vec3(out[0], out[1], out[2]);
+        m.b_            = vec3(out[3], out[4], out[5]);
+        m.volume()      = aligned_box3{m.a_, m.b_}; // environment_body.cpp:76
+        m.values_       = std::move(positions);
+        m.triangles_    = std::move(triangles);
+        return m;
+    }
     shape_t shape() const { return shape_; }
     vec3 const& a() const { return a_; }
     vec3 const& b() const { return b_; }
     scalar_type d() const { return d_; }
+    std::array<unsigned int, 3u> const& resolution() const { return resolution_; }
+    std::vector<scalar_type> const& values() const { return values_; }        // grid: nodes; mesh: positions
+    std::vector<std::uint32_t> const& triangles() const { return triangles_; }
+    aligned_box3 const& given_domain() const { return given_domain_; }
 
   private:
     shape_t shape_ = shape_t::plane;
     vec3 a_, b_;
     scalar_type d_ = 0.;
+    std::array<unsigned int, 3u> resolution_{{10u, 10u, 10u}};
+    std::vector<scalar_type> values_;
+    std::vector<std::uint32_t> triangles_;
+    aligned_box3 given_domain_;
 };
 
 // include/sbs/physics/collision/bvh_model.h:23-49: the surface vertices of a tetrahedral body.
@@ -577,10 +622,23 @@ class tetrahedral_body_t : public body_t
     collision::point_bvh_model_t collision_model_;
 };
 
-// include/sbs/physics/environment_body.h, src/physics/environment_body.cpp:80-88
+// include/sbs/physics/environment_body.h, src/physics/environment_body.cpp:12-88
 class environment_body_t : public body_t
 {
   public:
+    // environment_body.cpp:12-78: triangle mesh -> grid SDF over the extended domain
+    environment_body_t(simulation_t& simulation, index_type id, common::geometry_t const& geometry,
+                       aligned_box3 const& domain, std::array<unsigned int, 3u> const& resolution = {10u, 10u, 10u})
+        : body_t(simulation, id),
+          collision_model_(collision::sdf_model_t::from_mesh(
+              std::vector<scalar_type>(geometry.positions.begin(), geometry.positions.end()),
+              std::vector<std::uint32_t>(geometry.indices.begin(), geometry.indices.end()), domain, resolution))
+    {
+        if (geometry.geometry_type != common::geometry_t::geometry_type_t::triangle || !geometry.has_positions() ||
+            !geometry.has_indices())
+            throw std::invalid_argument("sbs-b200: environment_body_t needs an indexed triangle mesh"); // :27-29
+        collision_model_.id() = id;
+    }
     environment_body_t(simulation_t& simulation, index_type id, common::geometry_t const& /*visual*/,
                        collision::sdf_model_t const& sdf_model)
         : body_t(simulation, id), collision_model_(sdf_model)
@@ -754,6 +812,22 @@ inline void simulation_t::build_device()
             {
                 double const c[3] = {m.a()[0], m.a()[1], m.a()[2]};
                 db                = sbsb200_add_sdf_sphere(ctx_, c, m.d(), vol);
+            }
+            else if (m.shape() == collision::sdf_model_t::shape_t::grid)
+            {
+                double const lo[3] = {m.a()[0], m.a()[1], m.a()[2]}, hi[3] = {m.b()[0], m.b()[1], m.b()[2]};
+                std::uint32_t const res[3] = {m.resolution()[0], m.resolution()[1], m.resolution()[2]};
+                db = sbsb200_add_sdf_grid(ctx_, lo, hi, res, m.values().data(),
+                                          static_cast<std::int64_t>(m.values().size()), vol);
+            }
+            else if (m.shape() == collision::sdf_model_t::shape_t::mesh)
+            {
+                aligned_box3 const& g = m.given_domain();
+                double const dom[6]   = {g.min()[0], g.min()[1], g.min()[2], g.max()[0], g.max()[1], g.max()[2]};
+                std::uint32_t const res[3] = {m.resolution()[0], m.resolution()[1], m.resolution()[2]};
+                db = sbsb200_add_sdf_mesh(ctx_, static_cast<std::int64_t>(m.values().size() / 3), m.values().data(),
+                                          static_cast<std::int64_t>(m.triangles().size() / 3), m.triangles().data(),
+                                          dom, res);
             }
             else
             {

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -87,6 +88,7 @@ struct EngineBase
     virtual bool peers_connected()                                                          = 0;
     virtual void check_after_sync(sbsb200_ctx& c)                                           = 0;
     virtual void download_surface(sbsb200_ctx& c, int body, float* out)                     = 0;
+    virtual void eval_sdf(sbsb200_ctx& c, int body, int64_t n, double const* pts, double* sd, double* grad) = 0;
 };
 
 } // namespace
@@ -145,6 +147,7 @@ struct Engine final : EngineBase
     DevBuf<uint32_t> surf_v, surf_first, contact_v, contact_count;
     DevBuf<int32_t> surf_body;
     DevBuf<typename DeviceScene<R>::Sdf> sdf;
+    DevBuf<R> grid_nodes;            // node values of all grid SDFs, one after the other
     DevBuf<double> stage_x, stage_v; // raw host-format staging for upload/download
     // BVH broadphase (bvh.cuh)
     BvhView<R> bvh{};
@@ -328,6 +331,15 @@ struct Engine final : EngineBase
         std::vector<uint32_t> sv;
         std::vector<int32_t> sb;
         std::vector<typename DeviceScene<R>::Sdf> hs;
+        {
+            std::vector<R> pool;
+            for (HostBody const& hb : h.bodies)
+                if (hb.kind == BodyKind::sdf && hb.sdf_kind == SdfKind::grid)
+                    for (double v : hb.grid_nodes)
+                        pool.push_back(R(v));
+            grid_nodes.upload(pool, st);
+        }
+        size_t grid_at = 0;
         for (size_t b = 0; b < h.bodies.size(); ++b)
         {
             HostBody const& hb = h.bodies[b];
@@ -352,7 +364,10 @@ struct Engine final : EngineBase
                 {
                     f.vmin[k] = R(hb.volume[k]);
                     f.vmax[k] = R(hb.volume[3 + k]);
+                    f.grid_n[k] = hb.grid_n[k];
                 }
+                f.grid_nodes = grid_nodes.p + grid_at;
+                grid_at += hb.grid_nodes.size();
                 hs.push_back(f);
             }
         }
@@ -746,6 +761,29 @@ struct Engine final : EngineBase
         CK(cudaStreamSynchronize(c.stream));
     }
 
+    void eval_sdf(sbsb200_ctx& c, int body, int64_t n, double const* pts, double* sd, double* grad) override
+    {
+        int k = 0; // index among the SDF records = number of sdf bodies before `body`
+        for (int b = 0; b < body; ++b)
+            k += c.scene.bodies[static_cast<size_t>(b)].kind == BodyKind::sdf;
+        DevBuf<double> in, out;
+        in.alloc(static_cast<size_t>(3 * n));
+        out.alloc(static_cast<size_t>(4 * n));
+        CK(cudaMemcpyAsync(in.p, pts, sizeof(double) * 3 * static_cast<size_t>(n), cudaMemcpyHostToDevice, c.stream));
+        k_eval_sdf<R><<<static_cast<unsigned>((n + 127) / 128), 128, 0, c.stream>>>(d, k, n, in.p, out.p);
+        ++c.kernels;
+        CK(cudaGetLastError());
+        std::vector<double> h(static_cast<size_t>(4 * n));
+        CK(cudaMemcpyAsync(h.data(), out.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        for (int64_t i = 0; i < n; ++i)
+        {
+            sd[i] = h[static_cast<size_t>(4 * i)];
+            for (int a = 0; a < 3; ++a)
+                grad[3 * i + a] = h[static_cast<size_t>(4 * i + 1 + a)];
+        }
+    }
+
     void check_persistent(sbsb200_ctx& c)
     {
         if (c.schedule == SBSB200_SCHED_PERSISTENT && pp.timed_out())
@@ -1080,6 +1118,203 @@ int sbsb200_add_sdf_box(sbsb200_ctx* c, const double bmin[3], const double bmax[
     if (!bmax)
         return fail(c, SBSB200_ERR_INVALID, "null argument");
     return add_sdf(c, SdfKind::box, bmin, bmax, 0., volume);
+}
+
+int64_t sbsb200_grid_node_count(const uint32_t res[3])
+{
+    if (!res || !res[0] || !res[1] || !res[2])
+        return SBSB200_ERR_INVALID;
+    return static_cast<int64_t>(GridDims{{res[0], res[1], res[2]}}.nodes());
+}
+
+int sbsb200_grid_node_position(const double dmin[3], const double dmax[3], const uint32_t res[3], int64_t node,
+                               double position[3])
+{
+    if (!dmin || !dmax || !position || node < 0 || node >= sbsb200_grid_node_count(res))
+        return SBSB200_ERR_INVALID;
+    grid_node_position(GridDims{{res[0], res[1], res[2]}}, dmin, dmax, static_cast<uint64_t>(node), position);
+    return SBSB200_OK;
+}
+
+int sbsb200_add_sdf_grid(sbsb200_ctx* c, const double dmin[3], const double dmax[3], const uint32_t res[3],
+                         const double* nodes, int64_t n_nodes, const double volume[6])
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (!dmin || !dmax || !res || !nodes)
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    if (!res[0] || !res[1] || !res[2] || !(dmin[0] < dmax[0] && dmin[1] < dmax[1] && dmin[2] < dmax[2]))
+        return fail(c, SBSB200_ERR_INVALID, "empty grid");
+    if (n_nodes != sbsb200_grid_node_count(res))
+        return fail(c, SBSB200_ERR_INVALID, "node count does not match the resolution (sbsb200_grid_node_count)");
+    double const dom[6] = {dmin[0], dmin[1], dmin[2], dmax[0], dmax[1], dmax[2]};
+    int const id        = add_sdf(c, SdfKind::grid, dmin, dmax, 0., volume ? volume : dom);
+    if (id < 0)
+        return id;
+    HostBody& hb = c->scene.bodies[static_cast<size_t>(id)];
+    std::memcpy(hb.grid_n, res, sizeof hb.grid_n);
+    hb.grid_nodes.assign(nodes, nodes + n_nodes);
+    return id;
+}
+
+int sbsb200_mesh_sdf_domain(int64_t nV, const double* x, const double domain[6], double dom[6])
+{
+    if (!x || !domain || !dom || nV < 0)
+        return SBSB200_ERR_INVALID;
+    // environment_body.cpp:52-65: the box is extended to the mesh and then inflated by 1e-3 of its
+    // diagonal, max first, then min with the diagonal of the already grown box — once per mesh
+    // vertex, because the growth statements sit inside the outer vertex loop
+    std::memcpy(dom, domain, 6 * sizeof(double));
+    for (int64_t v = 0; v < nV; ++v)
+        for (int k = 0; k < 3; ++k)
+        {
+            dom[k]     = std::min(dom[k], x[3 * v + k]);
+            dom[3 + k] = std::max(dom[3 + k], x[3 * v + k]);
+        }
+    for (int64_t v = 0; v < nV; ++v)
+        for (int side = 1; side >= 0; --side)
+        {
+            double const dx = dom[3] - dom[0], dy = dom[4] - dom[1], dz = dom[5] - dom[2];
+            double const g  = 1.0e-3 * std::sqrt(dx * dx + dy * dy + dz * dz);
+            for (int k = 0; k < 3; ++k)
+                dom[3 * side + k] += side ? g : -g;
+        }
+    return SBSB200_OK;
+}
+
+int sbsb200_add_sdf_mesh(sbsb200_ctx* c, int64_t nV, const double* x, int64_t nF, const uint32_t* tri,
+                         const double domain[6], const uint32_t resolution[3])
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "scene already finalized");
+    if (!x || !tri || !domain || nV <= 0 || nF <= 0)
+        return fail(c, SBSB200_ERR_INVALID, "null or empty mesh");
+    uint32_t const dflt[3] = {10u, 10u, 10u}; // environment_body.h:24
+    uint32_t const* res    = resolution ? resolution : dflt;
+    if (!res[0] || !res[1] || !res[2])
+        return fail(c, SBSB200_ERR_INVALID, "empty grid");
+    for (int64_t i = 0; i < 3 * nF; ++i)
+        if (tri[i] >= nV)
+            return fail(c, SBSB200_ERR_INVALID, "triangle index out of range");
+    return guarded(c, [&]() -> int {
+        double dom[6];
+        sbsb200_mesh_sdf_domain(nV, x, domain, dom);
+        // per-triangle records with the pseudo-normals of faces, edges and corners (MeshDistance ctor)
+        std::vector<BakeTriangle> recs(static_cast<size_t>(nF));
+        std::vector<std::array<double, 3>> vn(static_cast<size_t>(nV), {0., 0., 0.});
+        std::map<std::pair<uint32_t, uint32_t>, int64_t> half_edge; // (from, to) -> face
+        for (int64_t f = 0; f < nF; ++f)
+        {
+            BakeTriangle& t = recs[static_cast<size_t>(f)];
+            for (int k = 0; k < 3; ++k)
+            {
+                for (int a = 0; a < 3; ++a)
+                    t.p[k][a] = x[3 * tri[3 * f + k] + a];
+                half_edge[{tri[3 * f + k], tri[3 * f + (k + 1) % 3]}] = f;
+            }
+            double e[3][3], len[3];
+            for (int k = 0; k < 3; ++k)
+            {
+                for (int a = 0; a < 3; ++a)
+                    e[k][a] = t.p[(k + 1) % 3][a] - t.p[k][a];
+                len[k] = std::sqrt(e[k][0] * e[k][0] + e[k][1] * e[k][1] + e[k][2] * e[k][2]);
+            }
+            double const ac[3] = {-e[2][0], -e[2][1], -e[2][2]};
+            double n[3] = {e[0][1] * ac[2] - e[0][2] * ac[1], e[0][2] * ac[0] - e[0][0] * ac[2],
+                           e[0][0] * ac[1] - e[0][1] * ac[0]};
+            double const ln = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            if (!(ln > 0.) || !(len[0] > 0.) || !(len[1] > 0.) || !(len[2] > 0.))
+                throw std::invalid_argument("degenerate triangle in the obstacle mesh");
+            for (int a = 0; a < 3; ++a)
+                t.fn[a] = n[a] / ln;
+            for (int k = 0; k < 3; ++k)
+            { // interior angle at corner k
+                int const pk = (k + 2) % 3;
+                double cs = -(e[k][0] * e[pk][0] + e[k][1] * e[pk][1] + e[k][2] * e[pk][2]) / (len[k] * len[pk]);
+                cs        = std::min(1., std::max(-1., cs));
+                double const al = std::acos(cs);
+                for (int a = 0; a < 3; ++a)
+                    vn[tri[3 * f + k]][static_cast<size_t>(a)] += al * t.fn[a];
+            }
+        }
+        for (int64_t f = 0; f < nF; ++f)
+        {
+            BakeTriangle& t = recs[static_cast<size_t>(f)];
+            for (int k = 0; k < 3; ++k)
+            {
+                auto const opp = half_edge.find({tri[3 * f + (k + 1) % 3], tri[3 * f + k]});
+                for (int a = 0; a < 3; ++a)
+                {
+                    t.en[k][a] = t.fn[a] + (opp != half_edge.end() && opp->second != f
+                                                ? recs[static_cast<size_t>(opp->second)].fn[a]
+                                                : 0.);
+                    t.vn[k][a] = vn[tri[3 * f + k]][static_cast<size_t>(a)];
+                }
+            }
+        }
+        GridDims const g{{res[0], res[1], res[2]}};
+        int64_t const nn = static_cast<int64_t>(g.nodes());
+        CK(cudaSetDevice(c->device));
+        DevBuf<BakeTriangle> d_tris;
+        DevBuf<double> d_nodes;
+        d_tris.upload(recs, c->stream);
+        d_nodes.alloc(static_cast<size_t>(nn));
+        k_bake_mesh_sdf<<<static_cast<unsigned>((nn + 127) / 128), 128, 0, c->stream>>>(
+            g, dom[0], dom[1], dom[2], dom[3], dom[4], dom[5], d_tris.p, nF, d_nodes.p);
+        ++c->kernels;
+        CK(cudaGetLastError());
+        std::vector<double> nodes(static_cast<size_t>(nn));
+        CK(cudaMemcpyAsync(nodes.data(), d_nodes.p, sizeof(double) * nodes.size(), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        // environment_body.cpp:75-77: the model's volume() is the extended domain
+        return sbsb200_add_sdf_grid(c, dom, dom + 3, res, nodes.data(), nn, dom);
+    });
+}
+
+int64_t sbsb200_get_sdf_grid(sbsb200_ctx* c, int body, double domain[6], uint32_t resolution[3], double* nodes,
+                             int64_t cap)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (body < 0 || body >= static_cast<int>(c->scene.bodies.size()) ||
+        c->scene.bodies[static_cast<size_t>(body)].kind != BodyKind::sdf ||
+        c->scene.bodies[static_cast<size_t>(body)].sdf_kind != SdfKind::grid)
+        return fail(c, SBSB200_ERR_INVALID, "not a grid sdf body");
+    HostBody const& hb = c->scene.bodies[static_cast<size_t>(body)];
+    if (domain)
+        for (int k = 0; k < 3; ++k)
+        {
+            domain[k]     = hb.a[k];
+            domain[3 + k] = hb.b[k];
+        }
+    if (resolution)
+        std::memcpy(resolution, hb.grid_n, sizeof hb.grid_n);
+    if (nodes)
+        std::memcpy(nodes, hb.grid_nodes.data(),
+                    sizeof(double) * static_cast<size_t>(std::min<int64_t>(cap, static_cast<int64_t>(hb.grid_nodes.size()))));
+    return static_cast<int64_t>(hb.grid_nodes.size());
+}
+
+int sbsb200_eval_sdf(sbsb200_ctx* c, int body, int64_t n, const double* points, double* distance, double* gradient)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "eval_sdf before finalize");
+    if (body < 0 || body >= static_cast<int>(c->scene.bodies.size()) ||
+        c->scene.bodies[static_cast<size_t>(body)].kind != BodyKind::sdf)
+        return fail(c, SBSB200_ERR_INVALID, "not an sdf body");
+    if (n < 0 || (n > 0 && (!points || !distance || !gradient)))
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    if (n == 0)
+        return SBSB200_OK;
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->eval_sdf(*c, body, n, points, distance, gradient);
+        return SBSB200_OK;
+    });
 }
 
 int sbsb200_finalize(sbsb200_ctx* c)

@@ -18,7 +18,7 @@ struct Material
 };
 
 enum class BodyKind : int { tet = 0, sdf = 1 };
-enum class SdfKind : int { plane = 0, sphere = 1, box = 2 };
+enum class SdfKind : int { plane = 0, sphere = 1, box = 2, grid = 3 };
 
 struct HostBody
 {
@@ -33,6 +33,9 @@ struct HostBody
     SdfKind sdf_kind = SdfKind::plane;
     double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, r = 0; // plane: a=n, r=offset; sphere: a=c, r; box: a=min, b=max
     double volume[6] = {0, 0, 0, 0, 0, 0};
+    // grid sdf (a..b = domain): cells per axis and node values in the order of grid_sdf.cuh
+    uint32_t grid_n[3] = {0, 0, 0};
+    std::vector<double> grid_nodes;
 };
 
 struct HostScene

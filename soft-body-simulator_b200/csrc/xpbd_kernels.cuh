@@ -2,6 +2,7 @@
 // (The persistent, region-resident schedule lives in xpbd_persistent.cuh.)
 #pragma once
 
+#include "grid_sdf.cuh"
 #include "xpbd_math.cuh"
 
 namespace sbsb200 {
@@ -44,8 +45,10 @@ struct DeviceScene
     struct Sdf
     {
         int32_t kind, body;
-        R a[3], b[3], r;
+        R a[3], b[3], r;    // plane: a = n, r = offset; sphere: a = centre, r; box / grid domain: a = min, b = max
         R vmin[3], vmax[3]; // englobing volume() box (collision_model.h:39-40), used by the BVH broadphase
+        uint32_t grid_n[3]; // grid (kind 3): cells per axis and node values (grid_sdf.cuh)
+        R const* grid_nodes;
     };
     Sdf const* sdf;
     int64_t contact_cap;
@@ -266,10 +269,23 @@ k_project_distance(DeviceScene<R> s, int64_t first, int32_t count, R dt, int fir
     st4(&s.pos[v.y], p2);
 }
 
-// sdf_model_t::evaluate (sdf_model.cpp:66-75) for the analytic kinds: signed distance + gradient
+// sdf_model_t::evaluate (sdf_model.cpp:66-75): signed distance + gradient; analytic kinds and the
+// discrete grid (Discregrid's interpolate, grid_sdf.cuh)
 template <typename R>
 __device__ __forceinline__ R sdf_eval(typename DeviceScene<R>::Sdf const& f, Vec3<R> p, Vec3<R>& g)
 {
+    if (f.kind == 3)
+    {
+        R const q[3] = {p.x, p.y, p.z};
+        R phi, gr[3];
+        if (!grid_interpolate<R>(f.grid_n, f.a, f.b, f.grid_nodes, q, phi, gr))
+        {
+            g = {R(0), R(1), R(0)};
+            return R(3.0e38); // outside the domain the reference sees numeric_limits<double>::max()
+        }
+        g = {gr[0], gr[1], gr[2]};
+        return phi;
+    }
     if (f.kind == 0)
     { // plane: Eigen::Hyperplane::signedDistance = n.p + offset (sdf_model.cpp:56-61)
         g = {f.a[0], f.a[1], f.a[2]};
@@ -475,6 +491,23 @@ k_pack_state(DeviceScene<R> s, int64_t first, int64_t n, double* __restrict__ x,
         v[3 * i + 1]     = double(q.y);
         v[3 * i + 2]     = double(q.z);
     }
+}
+
+// sdf_model_t::evaluate at arbitrary points (sbsb200_eval_sdf): out = (distance, gradient) per point
+template <typename R>
+__global__ void __launch_bounds__(128)
+k_eval_sdf(DeviceScene<R> s, int32_t k, int64_t n, double const* __restrict__ pts, double* __restrict__ out)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    Vec3<R> g;
+    R const sd     = sdf_eval<R>(s.sdf[k], Vec3<R>{R(pts[3 * i]), R(pts[3 * i + 1]), R(pts[3 * i + 2])}, g);
+    bool const out_of_domain = s.sdf[k].kind == 3 && sd >= R(3.0e38);
+    out[4 * i]     = out_of_domain ? 1.7976931348623157e308 : static_cast<double>(sd);
+    out[4 * i + 1] = out_of_domain ? 0. : static_cast<double>(g.x);
+    out[4 * i + 2] = out_of_domain ? 0. : static_cast<double>(g.y);
+    out[4 * i + 3] = out_of_domain ? 0. : static_cast<double>(g.z);
 }
 
 } // namespace sbsb200

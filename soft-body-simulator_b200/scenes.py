@@ -60,10 +60,11 @@ class TetBody:
 
 @dataclass
 class Sdf:
-    kind: str                 # "plane" | "sphere" | "box"
+    kind: str                 # "plane" | "sphere" | "box" | "mesh" (a = positions, b = triangles, volume = grid domain)
     a: tuple
     b: tuple
     volume: tuple             # (min xyz, max xyz)
+    res: tuple = None         # "mesh": grid resolution (None = the reference's default 10x10x10)
 
 
 @dataclass
@@ -109,6 +110,8 @@ class Scene:
                 ids.append(backend.add_sdf_plane(it.a, it.b, it.volume))
             elif it.kind == "sphere":
                 ids.append(backend.add_sdf_sphere(it.a, it.b[0], it.volume))
+            elif it.kind == "mesh":
+                ids.append(backend.add_sdf_mesh(it.a, it.b, it.volume, it.res))
             else:
                 ids.append(backend.add_sdf_box(it.a, it.b, it.volume))
         for (b1, b2, pairs, alpha, beta) in self.distance:
@@ -122,6 +125,35 @@ class Scene:
 
 
 _BIG = (-1e4, -1e4, -1e4, 1e4, 1e4, 1e4)
+
+
+def octahedron(centre, radii):
+    """Closed, outward-oriented triangle mesh (6 vertices, 8 faces); float32-representable positions."""
+    c = np.asarray(centre, np.float64)
+    r = np.asarray(radii, np.float64)
+    x = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float64) * r + c
+    f = np.array([[0, 2, 4], [2, 1, 4], [1, 3, 4], [3, 0, 4], [2, 0, 5], [1, 2, 5], [3, 1, 5], [0, 3, 5]], np.uint32)
+    return x.astype(np.float32).astype(np.float64), f
+
+
+def box_mesh(bmin, bmax):
+    """Closed, outward-oriented triangle mesh of an axis-aligned box (8 vertices, 12 faces)."""
+    lo, hi = np.asarray(bmin, np.float64), np.asarray(bmax, np.float64)
+    u = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], np.float64)
+    f = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [1, 2, 6], [1, 6, 5], [2, 3, 7],
+                  [2, 7, 6], [3, 0, 4], [3, 4, 7]], np.uint32)
+    return (lo + u * (hi - lo)).astype(np.float32).astype(np.float64), f
+
+
+def config1_on_mesh(W=4, H=4, D=6, seed=7, res=(8, 8, 8)):
+    """Config 1 with a triangle-mesh obstacle baked into a grid SDF (environment_body.cpp:12-78) poking into
+    the beam from below, next to the floor plane."""
+    sc = config1(W=W, H=H, D=D, seed=seed)
+    x, f = octahedron((0.55 * (W - 1), 0.0, 0.5 * (D - 1)), (0.5 * (W - 1), 0.9, 0.4 * (D - 1)))
+    dom = (-2.0, -3.0, -2.0, 1.1 * (W - 1) + 2.0, 0.95 * (H - 1) + 3.0, float(D - 1) + 2.0)
+    sc.items.append(Sdf("mesh", x, f, dom, res))
+    sc.name = "config1_on_mesh_%dx%dx%d" % (W, H, D)
+    return sc
 
 
 def prestrained_bar(W, H, D, seed, translate=(0.0, 0.0, 0.0), jitter=0.02, rotation=None, mass=None,

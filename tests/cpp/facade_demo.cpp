@@ -11,6 +11,8 @@
 #include <sbs/physics/environment_body.h>
 #include <sbs/physics/gauss_seidel_solver.h>
 #include <sbs/physics/simulation.h>
+#include <string>
+
 #include <sbs/physics/tetrahedral_body.h>
 #include <sbs/physics/timestep.h>
 #include <sbs/physics/xpbd/contact_handler.h>
@@ -20,7 +22,7 @@ int main(int argc, char** argv)
 {
     if (argc < 8)
     {
-        std::fprintf(stderr, "usage: %s W H D frames substeps iterations out.bin [32|64]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s W H D frames substeps iterations out.bin [32|64] [mesh]\n", argv[0]);
         return 2;
     }
     std::size_t const W = std::atoi(argv[1]), H = std::atoi(argv[2]), D = std::atoi(argv[3]);
@@ -61,6 +63,18 @@ int main(int argc, char** argv)
             sbs::hyperplane3(sbs::vec3{0., 1., 0.}, sbs::vec3{0., 0., 0.}), floor_volume);
         simulation.add_body(std::make_unique<sbs::physics::environment_body_t>(simulation, floor_idx, floor_geometry,
                                                                                floor_collision_model));
+
+        if (argc > 9 && std::string(argv[9]) == "mesh")
+        { // a triangle-mesh obstacle: environment_body_t(simulation, id, geometry, domain, resolution)
+            sbs::common::geometry_t rock; // octahedron poking up through the floor under the beam
+            rock.geometry_type = sbs::common::geometry_t::geometry_type_t::triangle;
+            rock.positions     = {1.5f, 0.f, 3.f, -1.5f, 0.f, 3.f, 0.f, 0.75f, 3.f, 0.f, -0.75f, 3.f, 0.f, 0.f, 6.f, 0.f, 0.f, 0.f};
+            rock.indices       = {0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5};
+            auto const rock_idx = static_cast<sbs::index_type>(simulation.bodies().size());
+            sbs::aligned_box3 const rock_domain{sbs::vec3{-6., -3., -6.}, sbs::vec3{8., 8., 30.}};
+            simulation.add_body(std::make_unique<sbs::physics::environment_body_t>(
+                simulation, rock_idx, rock, rock_domain, std::array<unsigned int, 3u>{8u, 6u, 12u}));
+        }
 
         std::vector<sbs::physics::collision::collision_model_t*> collision_objects{};
         std::transform(simulation.bodies().begin(), simulation.bodies().end(), std::back_inserter(collision_objects),

@@ -78,6 +78,9 @@ def cases(sc):
         "ref_two_bodies_springs": (two, 2, 3),
         "ref_config1_damped": (damped, 2, 21),
         "ref_config1_plus_box": (box, 2, 8),
+        # triangle-mesh obstacle baked into a grid SDF by the reference's own environment_body_t constructor
+        # (environment_body.cpp:12-78) over the shim's Discregrid stand-ins
+        "ref_config1_on_mesh": (sc.config1_on_mesh(), 2, 31),
     }
 
 
@@ -110,8 +113,12 @@ def main():
     sc = importlib.import_module("soft-body-simulator_b200.scenes")
     from oracle import ref as R
     R.build()
-    mesh_kats()
+    only = sys.argv[1:]
+    if not only:
+        mesh_kats()
     for name, (scene, frames, seed) in cases(sc).items():
+        if only and name not in only:
+            continue
         out = run_case(R.World, scene, frames, seed)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, {k: getattr(v, "shape", v) for k, v in out.items() if k.startswith(("x_", "contacts"))})

@@ -3,6 +3,8 @@
 // checked against the oracle without a GPU.  Not part of libsbsb200.so; never shipped.
 #include "../soft-body-simulator_b200/csrc/xpbd_kernels.cuh"
 
+#include <vector>
+
 using namespace sbsb200;
 
 template <typename R>
@@ -47,4 +49,36 @@ extern "C" int hostmath_green_project_f32(double* xi, const double* xn, const do
                                           double* lagrange)
 {
     return project<float>(xi, xn, w, DmInv, V0, mu, lam, alpha, beta, dt, lagrange);
+}
+
+// grid SDF sampling (csrc/grid_sdf.cuh) compiled for the host: value and gradient at n points;
+// returns the number of points inside the domain
+template <typename R>
+static int grid_sample(const uint32_t* res, const double* lo, const double* hi, const double* nodes, int64_t n_nodes,
+                       int n, const double* pts, double* val, double* grad)
+{
+    std::vector<R> nd(nodes, nodes + n_nodes);
+    R const l[3] = {R(lo[0]), R(lo[1]), R(lo[2])}, h[3] = {R(hi[0]), R(hi[1]), R(hi[2])};
+    int inside = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        R const p[3] = {R(pts[3 * i]), R(pts[3 * i + 1]), R(pts[3 * i + 2])};
+        R phi = R(0), g[3] = {R(0), R(0), R(0)};
+        bool const in = grid_interpolate<R>(res, l, h, nd.data(), p, phi, g);
+        inside += in;
+        val[i] = in ? double(phi) : 1.7976931348623157e308;
+        for (int k = 0; k < 3; ++k)
+            grad[3 * i + k] = in ? double(g[k]) : 0.;
+    }
+    return inside;
+}
+extern "C" int hostmath_grid_sample_f64(const uint32_t* res, const double* lo, const double* hi, const double* nodes,
+                                        int64_t n_nodes, int n, const double* pts, double* val, double* grad)
+{
+    return grid_sample<double>(res, lo, hi, nodes, n_nodes, n, pts, val, grad);
+}
+extern "C" int hostmath_grid_sample_f32(const uint32_t* res, const double* lo, const double* hi, const double* nodes,
+                                        int64_t n_nodes, int n, const double* pts, double* val, double* grad)
+{
+    return grid_sample<float>(res, lo, hi, nodes, n_nodes, n, pts, val, grad);
 }

@@ -39,12 +39,14 @@ def test_facade_compiles_against_the_reference_include_paths_and_fails_loudly_wi
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("obstacle", ["floor", "mesh"])
 @pytest.mark.parametrize("precision", [64, 32])
-def test_facade_demo_matches_the_c_abi_path_and_the_oracle(sbs, scenes, oracle, precision):
+def test_facade_demo_matches_the_c_abi_path_and_the_oracle(sbs, scenes, oracle, precision, obstacle):
     demo = build_demo()
-    out = os.path.join(BUILD, "facade_%d.bin" % precision)
+    out = os.path.join(BUILD, "facade_%d_%s.bin" % (precision, obstacle))
     W, H, D, frames, S, K = 4, 4, 12, 3, 2, 5
-    subprocess.check_call([demo, str(W), str(H), str(D), str(frames), str(S), str(K), out, str(precision)])
+    subprocess.check_call([demo, str(W), str(H), str(D), str(frames), str(S), str(K), out, str(precision)] +
+                          (["mesh"] if obstacle == "mesh" else []))
     rows = np.fromfile(out, np.float64).reshape(-1, 9)
     x0, xd, vd = rows[:, 0:3], rows[:, 3:6], rows[:, 6:9]
     pos, tets = scenes.bar_model(W, H, D)
@@ -53,6 +55,9 @@ def test_facade_demo_matches_the_c_abi_path_and_the_oracle(sbs, scenes, oracle, 
     body = scenes.TetBody(x0=x0.copy(), tets=tets.astype(np.uint32), x=x0.copy())
     floor = scenes.Sdf("plane", (0.0, 1.0, 0.0), (0.0, 0.0, 0.0), (-200.0, -5.0, -200.0, 200.0, 5.0, 200.0))
     scene = scenes.Scene("facade_demo", [body, floor], substeps=S, iterations=K)
+    if obstacle == "mesh":  # the octahedron of tests/cpp/facade_demo.cpp, baked by environment_body_t's mesh constructor
+        rock_x, rock_f = scenes.octahedron((0.0, 0.0, 3.0), (1.5, 0.75, 3.0))
+        scene.items.append(scenes.Sdf("mesh", rock_x, rock_f, (-6.0, -3.0, -6.0, 8.0, 8.0, 30.0), (8, 6, 12)))
     sim = sbs.Simulation(0, precision)
     ids = scene.instantiate(sim)
     ref = oracle.World()

@@ -42,24 +42,6 @@ def hostscene():
     return L
 
 
-@pytest.fixture(scope="session")
-def hostmath():
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not available")
-    os.makedirs(BUILD, exist_ok=True)
-    lib = os.path.join(BUILD, "libhostmath.so")
-    src = [os.path.join(HERE, "host_math.cu"), os.path.join(ROOT, "soft-body-simulator_b200/csrc/xpbd_math.cuh"),
-           os.path.join(ROOT, "soft-body-simulator_b200/csrc/xpbd_kernels.cuh")]
-    if not _newer(lib, src):
-        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-                               "-shared", "-o", lib, src[0]])
-    L = C.CDLL(lib)
-    for f in (L.hostmath_green_project_f64, L.hostmath_green_project_f32):
-        f.argtypes = [dp, dp, dp, dp] + [C.c_double] * 6 + [dp]
-    return L
-
-
 def test_c_abi_exports_every_declared_symbol(sbs):
     header = open(os.path.join(ROOT, "include", "sbs_b200.h")).read()
     declared = sorted(set(re.findall(r"\b(sbsb200_[a-z_0-9]+)\s*\(", header)))
