@@ -121,6 +121,12 @@ int sbsb200_add_sdf_sphere(sbsb200_ctx* ctx, const double centre[3], double radi
 int sbsb200_add_sdf_box(sbsb200_ctx* ctx, const double box_min[3], const double box_max[3],
                         const double volume[6]);
 
+/* brute_force_cd_system_t(objects) (src/physics/collision/brute_force_cd_system.cpp:8-12; main.cpp:77-86
+ * builds the list): only the collision models handed to the cd system take part in detection.  Every
+ * body does by default; flag = 0 takes a tet body's surface vertices, or an sdf body, out of detection
+ * (a scene file's `"collideable": false`, src/io/load_scene.cpp:248-257).  Before sbsb200_finalize. */
+int sbsb200_set_body_collideable(sbsb200_ctx* ctx, int body, int flag);
+
 /* environment_body_t holding a discrete-grid sdf_model_t (sdf_model.cpp:18, evaluated by
  * Discregrid::CubicLagrangeDiscreteGrid::interpolate, sdf_model.cpp:71-74): 32-node cubic cells over
  * [domain_min, domain_max] with resolution[3] cells per axis.  node_values: one double per node in

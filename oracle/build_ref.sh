@@ -39,3 +39,13 @@ g++ $CXXFLAGS $INC -c "$HERE/ref_driver.cpp" -o "$OUT/obj/ref_driver.o" &
 wait
 g++ -shared -o "$OUT/libsbsref.so" $OBJS "$OUT/obj/ref_driver.o"
 echo "$OUT/libsbsref.so"
+# The reference's own scene loader (src/io/load_scene.cpp, ply.cpp) under tests/cpp/scene_dump.cpp, against
+# the nlohmann/json.hpp that happens to be bundled with this image's python packages (the reference fetches it
+# from the network, CMakeLists.txt:19-25).  Skipped when that header is not found.
+NL="$(python3 -c 'import sysconfig,os;print(os.path.join(sysconfig.get_paths()["purelib"],"include","cudnn_frontend","thirdparty"))' 2>/dev/null || true)"
+if [ -f "$NL/nlohmann/json.hpp" ]; then
+  g++ -std=c++17 -O1 -w -include cstdint -include cassert -include optional -I"$REF/include" -I"$NL" \
+    "$HERE/../tests/cpp/scene_dump.cpp" "$REF/src/io/load_scene.cpp" "$REF/src/io/ply.cpp" \
+    "$REF/src/common/node.cpp" "$REF/src/common/geometry.cpp" -o "$OUT/ref_scene_dump"
+  echo "$OUT/ref_scene_dump"
+fi

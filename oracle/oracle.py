@@ -50,6 +50,7 @@ def lib():
         L.orc_add_sdf_plane.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.orc_add_sdf_sphere.argtypes = [C.c_void_p, _dp, C.c_double, _dp]
         L.orc_add_sdf_box.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.orc_set_body_collideable.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_constraint_count.argtypes = [C.c_void_p]
         L.orc_set_constraint_order.argtypes = [C.c_void_p, _u32p, C.c_int]
         L.orc_upload.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
@@ -259,6 +260,10 @@ class World:
         res = (10, 10, 10) if res is None else res
         dom, nodes = bake_mesh_sdf(x, faces, domain, res)
         return self.add_sdf_grid(dom[:3], dom[3:], res, nodes, dom)
+
+    def set_body_collideable(self, body, flag):
+        if lib().orc_set_body_collideable(self._h, body, 1 if flag else 0):
+            raise RuntimeError("bad body")
 
     def constraint_count(self):
         return lib().orc_constraint_count(self._h)

@@ -53,6 +53,7 @@ def lib():
         L.ref_add_sdf_grid.argtypes = [vp, _dp, _dp, _u32p, _dp, _dp]
         L.ref_sdf_evaluate.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, _dp]
         L.ref_get_volume.argtypes = [vp, C.c_int, _dp]
+        L.ref_set_body_collideable.argtypes = [vp, C.c_int, C.c_int]
         L.ref_constraint_count.argtypes = [vp]
         L.ref_set_constraint_order.argtypes = [vp, _u32p, C.c_int]
         L.ref_upload.argtypes = [vp, C.c_int, _dp, _dp]
@@ -141,6 +142,10 @@ class World:
         out = np.empty(6)
         lib().ref_get_volume(self._h, body, _d(out))
         return out
+
+    def set_body_collideable(self, body, flag):
+        if lib().ref_set_body_collideable(self._h, body, 1 if flag else 0):
+            raise RuntimeError("bad body")
 
     def constraint_count(self):
         return lib().ref_constraint_count(self._h)

@@ -53,6 +53,7 @@ struct world
 {
     simulation_t sim;
     std::vector<int> is_tet; // per body
+    std::vector<int> excluded; // bodies whose collision model is not handed to the cd system
     std::vector<recorded_contact> log;
     bool cd_ready = false;
 };
@@ -81,8 +82,9 @@ void ensure_cd(world* w)
     if (w->cd_ready)
         return;
     std::vector<collision::collision_model_t*> objects; // main.cpp:77-86
-    for (auto& b : w->sim.bodies())
-        objects.push_back(&(b->collision_model()));
+    for (std::size_t i = 0; i < w->sim.bodies().size(); ++i)
+        if (i >= w->excluded.size() || !w->excluded[i])
+            objects.push_back(&(w->sim.bodies()[i]->collision_model()));
     w->sim.use_collision_detection_system(std::make_unique<collision::brute_force_cd_system_t>(objects));
     w->sim.collision_detection_system()->use_contact_handler(
         std::make_unique<recording_handler_t>(w->sim, w->log));
@@ -255,6 +257,17 @@ int ref_get_volume(void* h, int body, double out[6])
         out[k]     = vb.min()(k);
         out[3 + k] = vb.max()(k);
     }
+    return 0;
+}
+
+int ref_set_body_collideable(void* h, int body, int flag)
+{
+    world* w = static_cast<world*>(h);
+    if (body < 0 || static_cast<std::size_t>(body) >= w->sim.bodies().size())
+        return -1;
+    w->excluded.resize(w->sim.bodies().size(), 0);
+    w->excluded[static_cast<std::size_t>(body)] = !flag;
+    w->cd_ready = false;
     return 0;
 }
 

@@ -508,6 +508,7 @@ typedef struct
     int sdf_kind;
     double a[3], b[3], r; /* plane: a=normal, r=offset; sphere: a=centre, r; box: a=min,b=max; grid: domain a..b */
     double volume[6];
+    int excluded;         /* not handed to the cd system (main.cpp:77-86 lists the models that take part) */
     uint32_t grid_n[3];   /* grid: cells per axis */
     double* grid_nodes;   /* grid: node values, orc_grid_node_count(grid_n) of them */
 } body;
@@ -660,6 +661,13 @@ static int add_sdf(orc_world* w, int kind, const double a[3], const double b[3],
     bd->r = r;
     memcpy(bd->volume, volume, sizeof bd->volume);
     return id;
+}
+int orc_set_body_collideable(orc_world* w, int b, int flag)
+{
+    if (b < 0 || b >= w->nb)
+        return -1;
+    w->bodies[b].excluded = !flag;
+    return 0;
 }
 int orc_add_sdf_plane(orc_world* w, const double n[3], const double pt[3], const double vol[6])
 { /* Eigen::Hyperplane(n, e): offset = -n.e ; signedDistance(p) = n.p + offset (sdf_model.cpp:56-61) */
@@ -1166,6 +1174,8 @@ static void detect(orc_world* w)
         for (int j = i + 1; j < w->nb; ++j)
         {
             int const ki = w->bodies[i].kind, kj = w->bodies[j].kind;
+            if (w->bodies[i].excluded || w->bodies[j].excluded)
+                continue;
             if (ki == B_TET && kj == B_SDF)
                 collide_pair(w, i, j);
             else if (ki == B_SDF && kj == B_TET)

@@ -105,6 +105,10 @@ int64_t orc_bake_mesh_sdf(int nV, const double* x, int nF, const uint32_t* faces
 int orc_add_sdf_grid(orc_world* w, const double dmin[3], const double dmax[3], const uint32_t res[3],
                      const double* nodes, const double vol[6]);
 
+/* brute_force_cd_system_t(objects) (collision/brute_force_cd_system.cpp:8-12, main.cpp:77-86): only the
+ * collision models handed to the cd system take part in detection.  Default: every body does. */
+int orc_set_body_collideable(orc_world* w, int body, int flag);
+
 /* Number of elastic constraints (green + distance) in insertion order. */
 int orc_constraint_count(const orc_world* w);
 

@@ -25,7 +25,7 @@ EXPORTS = [
     "sbsb200_create", "sbsb200_destroy", "sbsb200_last_error", "sbsb200_set_stream", "sbsb200_set_schedule",
     "sbsb200_set_collision_compliance", "sbsb200_add_tet_body", "sbsb200_add_distance_constraints",
     "sbsb200_add_sdf_plane", "sbsb200_add_sdf_sphere", "sbsb200_add_sdf_box", "sbsb200_finalize",
-    "sbsb200_grid_node_count", "sbsb200_grid_node_position", "sbsb200_add_sdf_grid", "sbsb200_add_sdf_mesh", "sbsb200_mesh_sdf_domain",
+    "sbsb200_grid_node_count", "sbsb200_grid_node_position", "sbsb200_add_sdf_grid", "sbsb200_add_sdf_mesh", "sbsb200_mesh_sdf_domain", "sbsb200_set_body_collideable",
     "sbsb200_get_sdf_grid", "sbsb200_eval_sdf",
     "sbsb200_constraint_count", "sbsb200_get_constraint_order", "sbsb200_get_surface_map", "sbsb200_get_stats",
     "sbsb200_schedule_note",
@@ -84,6 +84,7 @@ def load_library():
     L.sbsb200_grid_node_position.argtypes = [_dp, _dp, _u32p, C.c_int64, _dp]
     L.sbsb200_add_sdf_grid.argtypes = [vp, _dp, _dp, _u32p, _dp, C.c_int64, _dp]
     L.sbsb200_add_sdf_mesh.argtypes = [vp, C.c_int64, _dp, C.c_int64, _u32p, _dp, _u32p]
+    L.sbsb200_set_body_collideable.argtypes = [vp, C.c_int, C.c_int]
     L.sbsb200_mesh_sdf_domain.argtypes = [C.c_int64, _dp, _dp, _dp]
     L.sbsb200_get_sdf_grid.argtypes = [vp, C.c_int, _dp, _u32p, _dp, C.c_int64]
     L.sbsb200_get_sdf_grid.restype = C.c_int64
@@ -223,6 +224,10 @@ class Simulation:
     def add_sdf_box(self, bmin, bmax, volume):
         return self._ck(self._L.sbsb200_add_sdf_box(self._h, _d(_f64(bmin)), _d(_f64(bmax)),
                                                     _d(_f64(volume).reshape(6))))
+
+    def set_body_collideable(self, body, flag):
+        """Only models handed to the cd system collide (brute_force_cd_system_t(objects), main.cpp:77-86)."""
+        self._ck(self._L.sbsb200_set_body_collideable(self._h, body, 1 if flag else 0))
 
     def add_sdf_grid(self, dmin, dmax, res, nodes, volume=None):
         """environment_body_t with a discrete-grid sdf_model_t (sdf_model.cpp:18)."""

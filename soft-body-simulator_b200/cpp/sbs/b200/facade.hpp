@@ -838,6 +838,18 @@ inline void simulation_t::build_device()
             device_body_[b] = db;
         }
     }
+    // only the collision models handed to the cd system take part in detection (brute_force_cd_system.cpp:8-12)
+    if (collide)
+        for (std::size_t b = 0; b < bodies_.size(); ++b)
+        {
+            if (device_body_[b] < 0)
+                continue;
+            auto const& listed = cd_system_->collision_objects();
+            bool const takes_part =
+                std::find(listed.begin(), listed.end(), &bodies_[b]->collision_model()) != listed.end();
+            if (!takes_part)
+                check(sbsb200_set_body_collideable(ctx_, device_body_[b], 0), "sbsb200_set_body_collideable");
+        }
     // Note: the C ABI numbers constraints per call (all tets of a body, then each batch of distance
     // constraints); device_constraint_order() maps back to positions in constraints().
     for (auto const& c : constraints_)

@@ -265,9 +265,9 @@ __global__ void __launch_bounds__(256) k_detect_all(DeviceScene<R> s, BvhView<R>
     {
         Real4<R> const q = ld4(&s.surf_pos[i]);
         p                = {q.x, q.y, q.z};
-        body             = s.surf_body[i];
-        culled = b.n > 0 ? bvh_cull_mask<R>(s, b, b.leaf_of_surface[i]) : 0u; // b.n == 0: no broadphase
-        for (int32_t k = 0; k < s.n_sdf; ++k)
+        body             = s.surf_body[i]; // negative: the body was not handed to the cd system
+        culled = b.n > 0 && body >= 0 ? bvh_cull_mask<R>(s, b, b.leaf_of_surface[i]) : 0u; // b.n == 0: no broadphase
+        for (int32_t k = 0; body >= 0 && k < s.n_sdf; ++k)
         {
             Vec3<R> g;
             if (!(k < 32 && (culled >> k & 1u)) && sdf_eval<R>(s.sdf[k], p, g) < R(0))

@@ -148,6 +148,8 @@ struct Engine final : EngineBase
     DevBuf<int32_t> surf_body;
     DevBuf<typename DeviceScene<R>::Sdf> sdf;
     DevBuf<R> grid_nodes;            // node values of all grid SDFs, one after the other
+    std::vector<int32_t> sdf_index;  // per body: its SDF record (detection uses the first n_active_sdf), -1 for tet bodies
+    int32_t n_active_sdf = 0;
     DevBuf<double> stage_x, stage_v; // raw host-format staging for upload/download
     // BVH broadphase (bvh.cuh)
     BvhView<R> bvh{};
@@ -339,7 +341,44 @@ struct Engine final : EngineBase
                         pool.push_back(R(v));
             grid_nodes.upload(pool, st);
         }
-        size_t grid_at = 0;
+        // SDF records: the bodies that take part in detection first (DeviceScene::n_sdf of them), the
+        // others behind them so that sbsb200_eval_sdf can still evaluate them
+        sdf_index.assign(h.bodies.size(), -1);
+        std::vector<size_t> grid_at(h.bodies.size(), 0);
+        {
+            size_t at = 0;
+            for (size_t b = 0; b < h.bodies.size(); ++b)
+            {
+                grid_at[b] = at;
+                at += h.bodies[b].grid_nodes.size();
+            }
+        }
+        n_active_sdf = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t b = 0; b < h.bodies.size(); ++b)
+            {
+                HostBody const& hb = h.bodies[b];
+                if (hb.kind != BodyKind::sdf || hb.collideable != (pass == 0))
+                    continue;
+                typename DeviceScene<R>::Sdf f{};
+                f.kind = static_cast<int32_t>(hb.sdf_kind);
+                f.body = static_cast<int32_t>(b);
+                for (int k = 0; k < 3; ++k)
+                {
+                    f.a[k]      = R(hb.a[k]);
+                    f.b[k]      = R(hb.b[k]);
+                    f.vmin[k]   = R(hb.volume[k]);
+                    f.vmax[k]   = R(hb.volume[3 + k]);
+                    f.grid_n[k] = hb.grid_n[k];
+                }
+                f.r          = R(hb.r);
+                f.grid_nodes = grid_nodes.p + grid_at[b];
+                sdf_index[b] = static_cast<int32_t>(hs.size());
+                hs.push_back(f);
+                n_active_sdf += pass == 0;
+            }
+        // surface vertices of every tet body; a body that is not handed to the cd system keeps its
+        // surface (the renderer reads it) but is marked with a negative body id, which detection skips
         for (size_t b = 0; b < h.bodies.size(); ++b)
         {
             HostBody const& hb = h.bodies[b];
@@ -347,29 +386,8 @@ struct Engine final : EngineBase
                 for (uint32_t lv : hb.surf_to_tet)
                 {
                     sv.push_back(static_cast<uint32_t>(hb.v_offset + lv));
-                    sb.push_back(static_cast<int32_t>(b));
+                    sb.push_back(hb.collideable ? static_cast<int32_t>(b) : ~static_cast<int32_t>(b));
                 }
-            else
-            {
-                typename DeviceScene<R>::Sdf f{};
-                f.kind = static_cast<int32_t>(hb.sdf_kind);
-                f.body = static_cast<int32_t>(b);
-                for (int k = 0; k < 3; ++k)
-                {
-                    f.a[k] = R(hb.a[k]);
-                    f.b[k] = R(hb.b[k]);
-                }
-                f.r = R(hb.r);
-                for (int k = 0; k < 3; ++k)
-                {
-                    f.vmin[k] = R(hb.volume[k]);
-                    f.vmax[k] = R(hb.volume[3 + k]);
-                    f.grid_n[k] = hb.grid_n[k];
-                }
-                f.grid_nodes = grid_nodes.p + grid_at;
-                grid_at += hb.grid_nodes.size();
-                hs.push_back(f);
-            }
         }
         int64_t const Vs = static_cast<int64_t>(sv.size());
         {
@@ -417,7 +435,7 @@ struct Engine final : EngineBase
         d.surf_body       = surf_body.p;
         d.surf_pos        = surf_pos.p;
         d.surf_first      = surf_first.p;
-        d.n_sdf           = static_cast<int32_t>(hs.size());
+        d.n_sdf           = n_active_sdf;
         d.sdf             = sdf.p;
         d.contact_cap     = cap;
         d.contact_v       = contact_v.p;
@@ -763,9 +781,7 @@ struct Engine final : EngineBase
 
     void eval_sdf(sbsb200_ctx& c, int body, int64_t n, double const* pts, double* sd, double* grad) override
     {
-        int k = 0; // index among the SDF records = number of sdf bodies before `body`
-        for (int b = 0; b < body; ++b)
-            k += c.scene.bodies[static_cast<size_t>(b)].kind == BodyKind::sdf;
+        int const k = sdf_index[static_cast<size_t>(body)];
         DevBuf<double> in, out;
         in.alloc(static_cast<size_t>(3 * n));
         out.alloc(static_cast<size_t>(4 * n));
@@ -1099,6 +1115,18 @@ int sbsb200_add_distance_constraints(sbsb200_ctx* c, int b1, int b2, int64_t n, 
         h.dist_beta.push_back(beta);
         h.dist_insertion.push_back(h.n_constraints++);
     }
+    return SBSB200_OK;
+}
+
+int sbsb200_set_body_collideable(sbsb200_ctx* c, int body, int flag)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "scene already finalized");
+    if (body < 0 || body >= static_cast<int>(c->scene.bodies.size()))
+        return fail(c, SBSB200_ERR_INVALID, "no such body");
+    c->scene.bodies[static_cast<size_t>(body)].collideable = flag != 0;
     return SBSB200_OK;
 }
 

@@ -23,6 +23,7 @@ enum class SdfKind : int { plane = 0, sphere = 1, box = 2, grid = 3 };
 struct HostBody
 {
     BodyKind kind = BodyKind::tet;
+    bool collideable = true;                // handed to the cd system (sbsb200_set_body_collideable)
     // tet body
     int64_t v_offset = 0, n_vertices = 0;
     int64_t t_offset = 0, n_tets = 0;       // range in HostScene::tets (insertion order)

@@ -114,6 +114,9 @@ class Scene:
                 ids.append(backend.add_sdf_mesh(it.a, it.b, it.volume, it.res))
             else:
                 ids.append(backend.add_sdf_box(it.a, it.b, it.volume))
+        for i, it in zip(ids, self.items):
+            if not getattr(it, "collideable", True):   # not handed to the cd system (main.cpp:77-86)
+                backend.set_body_collideable(i, False)
         for (b1, b2, pairs, alpha, beta) in self.distance:
             backend.add_distance_constraints(b1, b2, pairs, alpha, beta)
         if finalize and hasattr(backend, "finalize"):
