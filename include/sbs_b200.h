@@ -214,6 +214,12 @@ int sbsb200_get_vertex_ranks(const sbsb200_ctx* ctx, int body, int32_t* out, int
 /* Overwrite x (and v, NULL = 0) of a body; xi = xn = x as tetrahedral_body_t::transform
  * leaves them (tetrahedral_body.cpp:121-132); refreshes the surface copy. 3*nV doubles. */
 int sbsb200_upload(sbsb200_ctx* ctx, int body, const double* x, const double* v);
+
+/* The same for n listed vertices of a body (body-local indices): what a UI does to a picked particle
+ * between frames (main.cpp:158-165 writes simulation.particles()[b][v] directly; src/rendering/pick.cpp
+ * finds the vertex).  x: 3*n doubles; v: 3*n doubles or NULL = leave the velocities alone. */
+int sbsb200_set_vertices(sbsb200_ctx* ctx, int body, int64_t n, const uint32_t* vertices,
+                         const double* x, const double* v);
 /* particle_t::x(), v() of every vertex of a body (either may be NULL). */
 int sbsb200_download(sbsb200_ctx* ctx, int body, double* x, double* v);
 /* The boundary surface as a renderer consumes it, without downloading the whole state: 6 floats

@@ -29,7 +29,7 @@ EXPORTS = [
     "sbsb200_get_sdf_grid", "sbsb200_eval_sdf",
     "sbsb200_constraint_count", "sbsb200_get_constraint_order", "sbsb200_get_surface_map", "sbsb200_get_stats",
     "sbsb200_schedule_note",
-    "sbsb200_upload", "sbsb200_download", "sbsb200_set_mass", "sbsb200_step", "sbsb200_step_host",
+    "sbsb200_upload", "sbsb200_set_vertices", "sbsb200_download", "sbsb200_set_mass", "sbsb200_step", "sbsb200_step_host",
     "sbsb200_synchronize", "sbsb200_get_contacts", "sbsb200_debug_read_trace",
     "sbsb200_set_partition", "sbsb200_get_mailbox_handle", "sbsb200_connect_peers", "sbsb200_connect_peer_context",
     "sbsb200_get_vertex_ranks", "sbsb200_set_broadphase", "sbsb200_get_surface_triangles", "sbsb200_download_surface",
@@ -99,6 +99,7 @@ def load_library():
     L.sbsb200_schedule_note.argtypes = [vp]
     L.sbsb200_schedule_note.restype = C.c_char_p
     L.sbsb200_upload.argtypes = [vp, C.c_int, _dp, _dp]
+    L.sbsb200_set_vertices.argtypes = [vp, C.c_int, C.c_int64, _u32p, _dp, _dp]
     L.sbsb200_download.argtypes = [vp, C.c_int, _dp, _dp]
     L.sbsb200_set_mass.argtypes = [vp, C.c_int, C.c_int64, C.c_double]
     L.sbsb200_step.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_int]
@@ -306,6 +307,14 @@ class Simulation:
         x = _f64(x)
         vv = None if v is None else _f64(v)
         self._ck(self._L.sbsb200_upload(self._h, body, _d(x), None if vv is None else _d(vv)))
+
+    def set_vertices(self, body, vertices, x, v=None):
+        """Override x (= xi = xn) and optionally v of a few vertices between frames (dragging a picked vertex)."""
+        ids = np.ascontiguousarray(vertices, np.uint32).reshape(-1)
+        x = _f64(x).reshape(-1, 3)
+        vv = None if v is None else _f64(v).reshape(-1, 3)
+        self._ck(self._L.sbsb200_set_vertices(self._h, body, ids.shape[0], ids.ctypes.data_as(_u32p), _d(x),
+                                              None if vv is None else _d(vv)))
 
     def download(self, body):
         n = self._nv[body]

@@ -77,6 +77,8 @@ struct EngineBase
     virtual void step(sbsb200_ctx& c, double dt, int substeps, int iterations, int detect) = 0;
     virtual void upload(sbsb200_ctx& c, int body, double const* x, double const* v, bool sync = true) = 0;
     virtual void download(sbsb200_ctx& c, int body, double* x, double* v)                  = 0;
+    virtual void set_vertices(sbsb200_ctx& c, int body, int64_t n, uint32_t const* which, double const* x,
+                              double const* v)                                             = 0;
     virtual void set_mass(sbsb200_ctx& c, int64_t gv, double m)                             = 0;
     virtual int64_t contacts(sbsb200_ctx& c, int64_t cap, int32_t* body, uint32_t* vertex,
                              int32_t* sdf_body, double* point, double* normal)             = 0;
@@ -735,6 +737,29 @@ struct Engine final : EngineBase
         CK(cudaGetLastError());
         if (sync) // the caller may reuse x / v as soon as we return (step_host: they stay valid until its download)
             CK(cudaStreamSynchronize(c.stream));
+    }
+
+    void set_vertices(sbsb200_ctx& c, int body, int64_t n, uint32_t const* which, double const* x,
+                      double const* v) override
+    {
+        HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
+        ensure_staging(n);
+        DevBuf<uint32_t> ids;
+        ids.alloc(static_cast<size_t>(n));
+        CK(cudaMemcpyAsync(ids.p, which, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c.stream));
+        CK(cudaMemcpyAsync(stage_x.p, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+        if (v)
+            CK(cudaMemcpyAsync(stage_v.p, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+        k_scatter_state<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(d, hb.v_offset, n, ids.p, stage_x.p,
+                                                                                     v ? stage_v.p : nullptr);
+        ++c.kernels;
+        if (d.n_surface > 0)
+        {
+            k_surface_gather<R><<<static_cast<unsigned>((d.n_surface + 255) / 256), 256, 0, c.stream>>>(d);
+            ++c.kernels;
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c.stream));
     }
 
     void download(sbsb200_ctx& c, int body, double* x, double* v) override
@@ -1528,6 +1553,29 @@ int sbsb200_upload(sbsb200_ctx* c, int body, const double* x, const double* v)
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
         c->engine->upload(*c, body, x, v);
+        return SBSB200_OK;
+    });
+}
+
+int sbsb200_set_vertices(sbsb200_ctx* c, int body, int64_t n, const uint32_t* vertices, const double* x,
+                         const double* v)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "set_vertices before finalize");
+    if (!is_tet_body(c, body))
+        return fail(c, SBSB200_ERR_INVALID, "not a tetrahedral body");
+    if (n < 0 || (n > 0 && (!vertices || !x)))
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    for (int64_t i = 0; i < n; ++i)
+        if (vertices[i] >= c->scene.bodies[static_cast<size_t>(body)].n_vertices)
+            return fail(c, SBSB200_ERR_INVALID, "vertex index out of range");
+    if (n == 0)
+        return SBSB200_OK;
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->set_vertices(*c, body, n, vertices, x, v);
         return SBSB200_OK;
     });
 }

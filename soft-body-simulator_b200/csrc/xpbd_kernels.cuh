@@ -470,6 +470,27 @@ k_unpack_state(DeviceScene<R> s, int64_t first, int64_t n, double const* __restr
     st4(&s.vel[first + i], vel);
 }
 
+// the same for a handful of vertices (dragging a picked vertex between frames): x = xi = xn <- x[i] and,
+// when given, v <- v[i] for the listed vertices of one body; a null v leaves the velocity alone
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_scatter_state(DeviceScene<R> s, int64_t first, int64_t n, uint32_t const* __restrict__ which,
+                double const* __restrict__ x, double const* __restrict__ v)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    int64_t const at = first + which[i];
+    Real4<R> p       = ld4(&s.pos[at]);
+    p.x              = R(x[3 * i]);
+    p.y              = R(x[3 * i + 1]);
+    p.z              = R(x[3 * i + 2]);
+    st4(&s.pos[at], p);
+    st4(&s.prev[at], Real4<R>{p.x, p.y, p.z, R(0)});
+    if (v)
+        st4(&s.vel[at], Real4<R>{R(v[3 * i]), R(v[3 * i + 1]), R(v[3 * i + 2]), R(0)});
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256)
 k_pack_state(DeviceScene<R> s, int64_t first, int64_t n, double* __restrict__ x, double* __restrict__ v)

@@ -16,13 +16,14 @@
 #include <sbs/physics/tetrahedral_body.h>
 #include <sbs/physics/timestep.h>
 #include <sbs/physics/xpbd/contact_handler.h>
+#include <sbs/physics/xpbd/distance_constraint.h>
 #include <sbs/physics/xpbd/green_constraint.h>
 
 int main(int argc, char** argv)
 {
     if (argc < 8)
     {
-        std::fprintf(stderr, "usage: %s W H D frames substeps iterations out.bin [32|64] [mesh]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s W H D frames substeps iterations out.bin [32|64] [mesh|dynamic]\n", argv[0]);
         return 2;
     }
     std::size_t const W = std::atoi(argv[1]), H = std::atoi(argv[2]), D = std::atoi(argv[3]);
@@ -95,6 +96,13 @@ int main(int argc, char** argv)
             timestep.step(simulation);
             if (f == 0) // main.cpp:158-165: pin a picked vertex by setting its mass to 0 between frames
                 simulation.particles()[beam_idx][0].mass() = 0.;
+            if (f == 0 && argc > 9 && std::string(argv[9]) == "dynamic")
+            { // constraints come and go between frames: simulation.cpp:29-39 (remove = swap with the last)
+                simulation.remove_constraint(5);
+                auto const last = static_cast<sbs::index_type>(simulation.particles()[beam_idx].size() - 1);
+                simulation.add_constraint(std::make_unique<sbs::physics::xpbd::distance_constraint_t>(
+                    1e-4, 0., simulation, beam_idx, beam_idx, 1, last));
+            }
         }
 
         auto const& ps = static_cast<sbs::physics::simulation_t const&>(simulation).particles()[beam_idx];

@@ -74,3 +74,60 @@ def test_facade_demo_matches_the_c_abi_path_and_the_oracle(sbs, scenes, oracle, 
     tol = 1e-9 if precision == 64 else 1e-4
     assert np.abs(xd - xr).max() <= tol * scene.bbox_diagonal()
     assert np.abs(xd - x0).max() > 1e-3   # it moved
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [64, 32])
+def test_facade_constraints_added_and_removed_between_frames(sbs, scenes, oracle, precision):
+    """simulation_t::remove_constraint (swap with the last, simulation.cpp:34-39) and add_constraint after the first
+    frame: the facade rebuilds the device scene (colouring included) and carries the state over."""
+    demo = build_demo()
+    out = os.path.join(BUILD, "facade_%d_dynamic.bin" % precision)
+    W, H, D, frames, S, K = 4, 4, 12, 3, 2, 5
+    subprocess.check_call([demo, str(W), str(H), str(D), str(frames), str(S), str(K), out, str(precision), "dynamic"])
+    rows = np.fromfile(out, np.float64).reshape(-1, 9)
+    x0, xd, vd = rows[:, 0:3], rows[:, 3:6], rows[:, 6:9]
+    _, tets = scenes.bar_model(W, H, D)
+    tets = tets.astype(np.uint32)
+    floor = scenes.Sdf("plane", (0.0, 1.0, 0.0), (0.0, 0.0, 0.0), (-200.0, -5.0, -200.0, 200.0, 5.0, 200.0))
+
+    def first_frame(world):
+        scene = scenes.Scene("facade_demo", [scenes.TetBody(x0=x0.copy(), tets=tets, x=x0.copy()), floor],
+                             substeps=S, iterations=K)
+        ids = scene.instantiate(world)
+        return scene, ids
+
+    def later_frames(world, x, v):
+        t2 = tets.copy()
+        t2[5] = t2[-1]
+        mass = np.ones(len(x0))
+        mass[0] = 0.0
+        scene = scenes.Scene("facade_demo", [scenes.TetBody(x0=x0.copy(), tets=t2[:-1], x=x.copy(), mass=mass), floor],
+                             substeps=S, iterations=K)
+        scene.distance.append((0, 0, np.array([[1, len(x0) - 1]], np.uint32), 1e-4, 0.0))
+        ids = scene.instantiate(world)
+        world.upload(ids[0], x, v)
+        return scene, ids
+
+    sim = sbs.Simulation(0, precision)
+    scene, ids = first_frame(sim)
+    ref = oracle.World()
+    first_frame(ref)
+    ref.set_constraint_order(sim.constraint_order())
+    for w in (sim, ref):
+        w.step(scene.dt, S, K, False)
+    xs, vs = sim.download(ids[0])
+    xr, vr = ref.download(0)
+    sim2 = sbs.Simulation(0, precision)
+    scene2, ids2 = later_frames(sim2, xs, vs)
+    ref2 = oracle.World()
+    later_frames(ref2, xr, vr)
+    ref2.set_constraint_order(sim2.constraint_order())
+    for _ in range(frames - 1):
+        for w in (sim2, ref2):
+            w.step(scene.dt, S, K, False)
+    xs2, vs2 = sim2.download(ids2[0])
+    xr2, _ = ref2.download(0)
+    assert np.array_equal(xs2, xd) and np.array_equal(vs2, vd)       # facade == C ABI path, bit for bit
+    tol = 1e-9 if precision == 64 else 1e-4
+    assert np.abs(xd - xr2).max() <= tol * scene.bbox_diagonal()

@@ -156,6 +156,46 @@ def test_set_mass_pins_a_vertex_between_frames(sbs, scenes, oracle):
     assert np.abs(xg - xr).max() <= 1e-9 * scene.bbox_diagonal()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("precision", [64, 32])
+def test_dragging_a_pinned_vertex_between_frames(sbs, scenes, oracle, precision, schedule):
+    """What a picker does (main.cpp:158-165, src/rendering/pick.cpp): pin a vertex (mass 0) and move it a little
+    every frame (sbsb200_set_vertices), with and without a velocity override, in both schedules."""
+    scene = scenes.config1(W=4, H=5, D=7, seed=4)
+    sim = sbs.Simulation(0, precision, schedule=schedule)
+    ids = scene.instantiate(sim)
+    ref = oracle.World()
+    scene.instantiate(ref)
+    ref.set_constraint_order(sim.constraint_order())
+    picked = [3, 88]      # a corner vertex and an interior-face vertex
+    for w, b in ((sim, ids[0]), (ref, 0)):
+        for v in picked:
+            w.set_mass(b, v, 0.0)
+    for f in range(4):
+        xs, _ = sim.download(ids[0])
+        target = xs[picked] + np.array([[0.05, 0.1, 0.0], [0.0, 0.08, -0.04]])
+        vel = None if f % 2 == 0 else np.array([[0.5, 0.0, 0.0], [0.0, 0.0, 0.25]])
+        sim.set_vertices(ids[0], picked, target, vel)
+        xr, vr = ref.download(0)
+        xr[picked] = target
+        if vel is not None:
+            vr[picked] = vel
+        ref.upload(0, xr, vr)
+        for w in (sim, ref):
+            w.step(scene.dt, 5, 6)
+    xg, vg = sim.download(ids[0])
+    xr, vr = ref.download(0)
+    tol = TOL[precision]
+    assert np.abs(xg - xr).max() <= tol * scene.bbox_diagonal()
+    # a pinned vertex is not moved by constraints or gravity, only by its own velocity (timestep.cpp:35-43)
+    assert np.abs(xg[picked] - (target + vel * scene.dt)).max() <= 1e-6
+    with pytest.raises(sbs.SbsError):
+        sim.set_vertices(ids[0], [10 ** 6], [[0, 0, 0]])
+    with pytest.raises(sbs.SbsError):
+        sim.set_vertices(ids[1], [0], [[0, 0, 0]])     # the floor is not a tetrahedral body
+
+
 def test_step_host_round_trip_equals_resident_stepping(sbs, scenes):
     scene = scenes.config1(W=5, H=5, D=7)
     a = sbs.Simulation(0, 32)
