@@ -312,7 +312,8 @@ def main():
         if args.precision == 64:
             bytes_step = bytes_step * 336 // 176
         ms_step = ms_max / args.steps
-        frame_gbs = bytes_step / (ms_step * 1e-3) / 1e9
+        # per-GPU figure: a rank of a decomposed body moves 1/world of the frame's bytes
+        frame_gbs = bytes_step / (world if decomposed else 1) / (ms_step * 1e-3) / 1e9
         sched = {1: "graph", 2: "persistent"}.get(stats0["schedule"], "?")
         if kernel_launches > 0:
             # dominant kernel = the substep kernel of the persistent schedule: one launch runs predict,
@@ -363,7 +364,7 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 (of fallback)",
                          "kernel": kernel,
                          "frame": {"algorithmic_bytes_per_step": int(bytes_step), "achieved": frame_gbs,
-                                   "frac": frame_gbs / peak},
+                                   "frac": frame_gbs / peak, "per": "GPU"},
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "note": "algorithmic bytes (SURVEY 8d: 176 B per projection, 64 B per contact "
                                  "projection, 112 B per vertex and substep) / CUDA-event time; the working set "
