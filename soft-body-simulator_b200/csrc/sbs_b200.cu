@@ -1423,8 +1423,11 @@ int sbsb200_finalize(sbsb200_ctx* c)
 
         if (c->schedule == SBSB200_SCHED_PERSISTENT)
         {
-            ResidentParams const rp = c->precision == SBSB200_FP32 ? PersistentPlan<float>::resident_params()
-                                                                   : PersistentPlan<double>::resident_params();
+            ResidentParams rp = c->precision == SBSB200_FP32 ? PersistentPlan<float>::resident_params()
+                                                             : PersistentPlan<double>::resident_params();
+            // development knob for A/B timing: SBSB200_ROTATE_ITEMS=0 keeps cluster i of a step on thread i
+            if (char const* e = std::getenv("SBSB200_ROTATE_ITEMS"))
+                rp.rotate_items = std::atoi(e) != 0;
             build_cluster_plan(h, PersistentPlan<float>::regions_for(c->sm_count, T, c->world),
                                PersistentPlan<float>::wants_region_per_body(h, c->sm_count), c->green_plan, &rp,
                                &c->plan);

@@ -632,6 +632,7 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
                 }
             }
         }
+        out.rot = resident->rotate_items ? item_rotation(out.nt) : 0;
         if (out.nvc > kMaxClusterVertices)
             out.why_not = "a cluster has more than 16 distinct vertices";
         if (out.n_colours > 120)
@@ -727,7 +728,8 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
                 if (!layout)
                     continue;
                 // vertex addresses in the CTA's shared array: [nvc * nt scratch | resident vertices]
-                uint32_t const thread = static_cast<uint32_t>((k - i) % static_cast<size_t>(out.nt));
+                uint32_t const thread =
+                    static_cast<uint32_t>((k - i + static_cast<size_t>(out.rot)) % static_cast<size_t>(out.nt));
                 for (int a = 0; a < 4; ++a)
                 {
                     uint32_t const v = scene.tets[4 * static_cast<size_t>(t) + a];
@@ -901,7 +903,8 @@ bool build_mailbox_routes(HostScene const& scene, ClusterPlan const& cp, RegionP
 bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& rp)
 {
     int64_t const T = scene.n_tets(), Q = cp.n_clusters;
-    if (!cp.why_not.empty() || cp.nt <= 0 || cp.nvc <= 0 || cp.nvc % 4 != 0 || cp.nvc > kMaxClusterVertices)
+    if (!cp.why_not.empty() || cp.nt <= 0 || cp.nvc <= 0 || cp.nvc % 4 != 0 || cp.nvc > kMaxClusterVertices ||
+        cp.rot < 0 || cp.rot >= cp.nt)
         return false;
     if (static_cast<int64_t>(cp.tet_slots.size()) != 4 * T ||
         static_cast<int64_t>(cp.cl_fetch.size()) != static_cast<int64_t>(cp.nvc) * Q)
@@ -919,7 +922,7 @@ bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, Reg
         for (int32_t i = 0; i < d.n[0]; ++i)
         {
             int64_t const q      = d.cfirst + i;
-            uint32_t const thread = static_cast<uint32_t>(i % cp.nt); // part A comes first in its step
+            uint32_t const thread = static_cast<uint32_t>((i + cp.rot) % cp.nt); // part A comes first in its step
             bool any_fetch        = false;
             for (int k = 0; k < cp.nvc; ++k)
             {

@@ -137,7 +137,19 @@ struct ResidentParams
     int64_t smem_bytes   = 0; // shared memory available to one CTA
     int32_t vertex_bytes = 16; // sizeof(Real4<R>)
     int32_t max_threads  = 512;
+    bool rotate_items    = false; // part A clusters on the warps with a sub-partition to themselves (item_rotation)
 };
+
+// Which thread runs cluster i of a (colour, region) step.  Warp w of a CTA issues on sub-partition w % 4,
+// so with W = nt / 32 warps the sub-partitions W % 4 .. 3 hold one warp less than the others.  The
+// clusters that exchange vertices with other regions (part A, first in a step) carry the polls and
+// pushes on top of the projections: they go to the warps that have a sub-partition to themselves,
+// i.e. the numbering of a step's clusters starts at warp W % 4 (measured: profiles/r01_summary.md).
+inline int32_t item_rotation(int32_t nt)
+{
+    int32_t const warps = nt / 32;
+    return nt > 0 && nt % 32 == 0 ? (32 * (warps % 4)) % nt : 0;
+}
 
 struct ClusterPlan
 {
@@ -154,6 +166,7 @@ struct ClusterPlan
     int64_t max_chunk_clusters = 0;      // max over (colour, region) of the clusters of both parts
     // resident schedule only
     int32_t nt  = 0;                     // threads per CTA the scratch slots were laid out for
+    int32_t rot = 0;                     // cluster i of a step (part A first) runs on thread (i + rot) % nt, see item_rotation
     int32_t nvc = 0;                     // scratch entries per thread (multiple of 4, <= kMaxClusterVertices)
     std::vector<uint16_t> tet_slots;     // 4*T (storage order): index into the CTA's shared vertex array
     std::vector<uint32_t> cl_fetch;      // [nvc][n_clusters]: global vertex of scratch entry k, 0xffffffff = none

@@ -213,6 +213,8 @@ struct PersistentArgs
     int32_t n_regions, n_colours;
     int32_t n_run;                 // regions this launch runs (entries of region_order)
     int32_t nvc;                   // scratch entries per thread (4 * NVC4 of the instantiation)
+    int32_t rot;                   // cluster i of a step runs on thread (i + rot) % nt (ClusterPlan::rot)
+    int32_t poll_first;            // issue the polls of the next cluster before the pushes of this one
     int64_t n_clusters;
     int32_t const* region_order;   // CTA b runs region_order[b], [b + grid], ...; regions that share
                                    // vertices come first, one per CTA
@@ -411,10 +413,13 @@ __device__ __forceinline__ uint32_t expected_tag(StepInfo const& si, uint32_t me
 
 // Fetch of one cluster: every entry of its fetch list waits for the tag of its previous touch and
 // lands in the thread's scratch slots; all polls of a round are in flight together.
-template <typename R, int NVC4, typename Stamp>
+// `between` runs once, after the first records are requested and before any answer is examined (hence
+// before any scratch slot is overwritten): the pushes of the cluster that just ran go there, so that the
+// polls do not queue behind those scattered stores in the load/store pipe.
+template <typename R, int NVC4, typename Stamp, typename Between>
 __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64_t q, uint4 const (&fmeta)[NVC4],
                                                Real4<R> const (&fw)[NVC4], Real4<R>* sx, StepInfo const& si,
-                                               Stamp&& stamp)
+                                               Stamp&& stamp, Between&& between)
 {
     int const tid = threadIdx.x, nt = blockDim.x;
     uint32_t meta[4 * NVC4];
@@ -452,6 +457,8 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64
                 if (pending >> (h + e) & 1u)
                     raw[e] = Xchg<R>::fetch(a.box, static_cast<uint32_t>(h + e) * static_cast<uint32_t>(a.n_clusters) + mine,
                                             a.world > 1);
+            if (h == 0 && polls == 0)
+                between();
 #pragma unroll
             for (int e = 0; e < kBatch; ++e)
                 if (pending >> (h + e) & 1u)
@@ -474,16 +481,16 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64
 
 // One cluster, fetched already: project its tets in order out of shared memory -> write back.
 // q = storage index of the cluster when it has a fetch list (part A), -1 otherwise.
+// The fetched vertices are NOT written back here: push_cluster does that with the routing words
+// loaded here (`to`, `to_owner`).
 template <typename R, int NVC4, bool kDict, typename Stamp>
 __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk const& ch, int32_t i, int64_t q,
                                             ClusterHead<R, kDict> const& head, Real4<R>* sx,
-                                            Real4<R> const* s_dict, int first_iteration, StepInfo const& si,
-                                            Stamp&& stamp)
+                                            Real4<R> const* s_dict, int first_iteration, uint4 (&to)[NVC4],
+                                            uint4 (&to_owner)[NVC4], Stamp&& stamp)
 {
     DeviceScene<R> const& s = a.s;
-    int const tid = threadIdx.x, nt = blockDim.x;
     // where the fetched vertices go afterwards (static routing data): in flight while the tets run
-    uint4 to[NVC4], to_owner[NVC4];
 #pragma unroll
     for (int k = 0; k < NVC4; ++k)
     {
@@ -541,9 +548,17 @@ __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk
         n0  = n1; n1 = n2; n2 = n3; n3 = n4; n4 = n5; n5 = n6; n6 = n7; n7 = 0;
         cur = nxt;
     }
-    // push every fetched vertex to whoever touches it next, always: the tag is what that touch waits for
-    // (select instead of branch per entry; the single-GPU and the peer-memory variants are unswitched)
-    if (q >= 0)
+}
+
+// Push every fetched vertex of the cluster that just ran to whoever touches it next, always: the tag is
+// what that touch waits for (select instead of branch per entry; the single-GPU and the peer-memory
+// variants are unswitched).  Reads the thread's scratch slots: call it before they are refilled.
+template <typename R, int NVC4, typename Stamp>
+__device__ __forceinline__ void push_cluster(PersistentArgs<R> const& a, uint4 const (&to)[NVC4],
+                                             uint4 const (&to_owner)[NVC4], Real4<R> const* sx, StepInfo const& si,
+                                             Stamp&& stamp)
+{
+    int const tid = threadIdx.x, nt = blockDim.x;
     {
         bool const multi = a.world > 1;
 #pragma unroll
@@ -620,8 +635,10 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
     }
     __syncthreads();
     int32_t traced = 0;
+    // cluster i of a step runs on thread (i + rot) % nt (scene_build.h, item_rotation)
+    int32_t const my_item = tid >= a.rot ? tid - a.rot : tid + nt - a.rot;
     auto stamp = [&](int slot) { // slot < 0: record the value -slot in slot 1 instead of a clock stamp
-        if (kTrace && tid == 0 && a.trace && traced < a.trace_steps)
+        if (kTrace && my_item == 0 && a.trace && traced < a.trace_steps)
         {
             long long* row = &a.trace[(static_cast<int64_t>(region) * a.trace_steps + traced) * 16];
             if (slot < 0)
@@ -662,7 +679,7 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
         if (colour)
             advance = (round + 1) * nt >= s_chunks[2 * c].n[0] + s_chunks[2 * c + 1].n[0];
         int32_t const np      = advance ? p + 1 : p;
-        int32_t const ni_next = advance ? tid : (round + 1) * nt + tid;
+        int32_t const ni_next = advance ? my_item : (round + 1) * nt + my_item;
         bool has_next = false, next_in_a = false;
         int32_t nk = 0;
         ClusterHead<R, kDict> nhead;
@@ -705,6 +722,9 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
         }
 
         // ---- (2) the work of this pass
+        uint4 to[NVC4], to_owner[NVC4]; // routing words of the cluster this pass runs (push_cluster)
+        bool pushing = false;
+        StepInfo const si{tag, a.base, static_cast<uint32_t>(8 * (2 * (k > 0 ? 1 : 0) + cs)), k == K - 1, cs != 0};
         if (p == 0)
         { // ---- predict (timestep.cpp:35-43)
             for (int32_t i = tid; i < nv; i += nt)
@@ -819,18 +839,24 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
             if (round == 0)
                 stamp(0);
             if (item_i >= 0)
-            { // cluster item_i of the phase runs on thread item_i % nt; part A (clusters that fetch) first
+            { // cluster item_i of the phase runs on thread (item_i + rot) % nt; part A (clusters that fetch) first
                 bool const in_a    = item_i < nA;
                 DevChunk const& ch = s_chunks[2 * c + (in_a ? 0 : 1)];
-                StepInfo const si{tag, a.base, static_cast<uint32_t>(8 * (2 * (k > 0 ? 1 : 0) + cs)), k == K - 1, cs != 0};
-                run_cluster<R, NVC4, kDict>(a, ch, in_a ? item_i : item_i - nA, cur_q, head, sx, s_dict, k == 0, si,
-                                            stamp);
+                run_cluster<R, NVC4, kDict>(a, ch, in_a ? item_i : item_i - nA, cur_q, head, sx, s_dict, k == 0, to,
+                                            to_owner, stamp);
+                pushing = cur_q >= 0;
             }
             stamp(6);
         }
 
-        // ---- (3) the next cluster becomes the prepared one: its shared vertices are fetched now,
-        //          before the barrier when it belongs to the next phase
+        // ---- (3) the fetched vertices of the cluster that ran go to whoever touches them next, and the
+        //          next cluster becomes the prepared one: its shared vertices are fetched now, before the
+        //          barrier when it belongs to the next phase.  The first polls are issued BEFORE the
+        //          pushes (poll_first): the pushes are scattered 16-byte stores that keep the load/store
+        //          pipe busy for ~1000 cycles, and a poll queued behind them took 1600 cycles to answer.
+        bool const gather_next = has_next && next_in_a;
+        if (pushing && !(a.poll_first && gather_next))
+            push_cluster<R, NVC4>(a, to, to_owner, sx, si, stamp);
         item_i = has_next ? ni_next : -1;
         if (has_next)
         {
@@ -840,7 +866,10 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                 gather_cluster<R, NVC4>(a, next_q, nmeta, nw, sx,
                                         StepInfo{a.base + static_cast<uint32_t>(np), a.base,
                                                  static_cast<uint32_t>(8 * (2 * (nk > 0 ? 1 : 0) + cs)), false, false},
-                                        stamp);
+                                        stamp, [&] {
+                                            if (pushing && a.poll_first)
+                                                push_cluster<R, NVC4>(a, to, to_owner, sx, si, stamp);
+                                        });
         }
         if (advance)
         {
@@ -1176,6 +1205,11 @@ struct PersistentPlan
         args.n_colours        = cp.n_colours;
 
         args.nvc              = nvc;
+        args.rot              = cp.rot;
+        // development knob for A/B timing: SBSB200_POLL_FIRST=1 issues the polls before the pushes
+        args.poll_first       = 0;
+        if (char const* e = std::getenv("SBSB200_POLL_FIRST"))
+            args.poll_first = std::atoi(e) != 0 ? 1 : 0;
         args.n_clusters       = Q;
         args.region_order     = region_order.p;
         args.tet_slots        = tet_slots.p;

@@ -59,6 +59,9 @@ extern "C" int64_t hs_regions(int64_t nV, int64_t nT, const uint32_t* tets, cons
     return plan.n_interface;
 }
 
+// thread (i + rotation) % nt runs cluster i of a step of the resident schedule (scene_build.h)
+extern "C" int hs_item_rotation(int nt) { return item_rotation(nt); }
+
 // clustered colouring of a single tet body (or `n_bodies` copies laid out along x); outputs
 // serial_order[T], storage_order[T], tet_region[T]; returns n_colours, or -1 if the plan is invalid
 extern "C" int hs_cluster_plan(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_bodies,

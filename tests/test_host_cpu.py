@@ -176,6 +176,17 @@ def test_clustered_colouring_of_an_irregular_mesh(hostscene):
         assert treg.min() >= 0 and treg.max() < regions
 
 
+def test_clusters_that_exchange_vertices_start_on_the_least_loaded_sub_partitions(hostscene):
+    """Warp w issues on sub-partition w % 4; with W warps the sub-partitions W % 4 .. 3 hold one warp less.
+    Part A clusters are numbered first in a step, so the numbering starts at warp W % 4."""
+    for nt, rot in ((192, 64), (160, 32), (224, 96), (256, 0), (384, 0), (128, 0), (64, 0), (96, 0), (320, 64)):
+        assert hostscene.hs_item_rotation(nt) == rot
+        warps = nt // 32
+        per_smsp = [len(range(s, warps, 4)) for s in range(4)]
+        first_warp = rot // 32
+        assert per_smsp[first_warp % 4] == min(p for p in per_smsp if p > 0) or warps < 4
+
+
 def test_colouring_reports_capacity_overflow(hostscene):
     # a fan of 40 tets around one edge needs 40 colours
     n = 40
