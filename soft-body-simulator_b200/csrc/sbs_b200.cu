@@ -160,6 +160,12 @@ struct Engine final : EngineBase
     DevBuf<Real4<R>> bvh_sphere;
     DevBuf<unsigned char> bvh_temp;
     size_t bvh_temp_bytes = 0;
+    // The order of the leaves (keys -> radix sort) is kept for kBvhTopologyFrames frames; the bounding
+    // spheres are refitted at every detection, so an older order only costs culling quality, never a
+    // contact.  (The reference builds its KD-tree once and only ever refits it, bvh_model.cpp:24-28, :102-126.)
+    static constexpr int kBvhTopologyFrames = 8;
+    int bvh_topology_valid_frames = 0; // 0: sort at the next detection
+    int bvh_sort_end_bit          = 64; // key bits in use: 32 Morton bits + the bits of the body index
     PersistentPlan<R> pp; // persistent schedule resources (may be inactive)
     // CUDA-event pairs around the launches of the dominant kernel (persistent schedule: the substep
     // kernel), folded into a running sum when the statistics are read
@@ -470,6 +476,9 @@ struct Engine final : EngineBase
             bvh.level_offset[0] = 0;
             bvh.level_count[0]  = Vs;
             bvh_sphere.alloc(static_cast<size_t>(std::max<int64_t>(offset, 1)));
+            bvh_sort_end_bit = 33;
+            while (bvh_sort_end_bit < 64 && (uint64_t{1} << (bvh_sort_end_bit - 32)) < c.scene.bodies.size())
+                ++bvh_sort_end_bit;
             CK(cub::DeviceRadixSort::SortPairs(nullptr, bvh_temp_bytes, bvh_keys.p, bvh_keys_sorted.p, bvh_leaf_in.p,
                                                bvh_leaf_surface.p, static_cast<int>(Vs), 0, 64, st));
             bvh_temp.alloc(bvh_temp_bytes);
@@ -536,7 +545,17 @@ struct Engine final : EngineBase
         unsigned const gridC = static_cast<unsigned>((d.contact_cap + 255) / 256);
         d.collision_alpha    = R(c.collision_alpha);
 
-        bool bvh_topology_built = false; // rebuilt once per frame, refitted at every detection
+        // leaves re-sorted once per frame at most (every kBvhTopologyFrames frames when the frame is enqueued
+        // eagerly; a captured frame is replayed as it is, so it always sorts), refitted at every detection
+        cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+        CK(cudaStreamIsCapturing(st, &capture));
+        bool const eager        = capture == cudaStreamCaptureStatusNone;
+        bool bvh_topology_built = false;
+        if (eager && bvh_topology_valid_frames > 0)
+        {
+            bvh_topology_built = true;
+            --bvh_topology_valid_frames;
+        }
         auto detect_now = [&] {
             if (!collide)
                 return;
@@ -550,9 +569,11 @@ struct Engine final : EngineBase
                 {
                     k_bvh_keys<R><<<gridS, 256, 0, st>>>(d, bvh);
                     CK(cub::DeviceRadixSort::SortPairs(bvh_temp.p, bvh_temp_bytes, bvh.keys, bvh.keys_sorted,
-                                                       bvh.leaf_in, bvh.leaf_surface, n, 0, 64, st));
+                                                       bvh.leaf_in, bvh.leaf_surface, n, 0, bvh_sort_end_bit, st));
                     ++launched;
                     bvh_topology_built = true;
+                    if (eager)
+                        bvh_topology_valid_frames = kBvhTopologyFrames - 1;
                 }
                 k_bvh_fit<R><<<static_cast<unsigned>((n + kBvhLeafBlock - 1) / kBvhLeafBlock), kBvhLeafBlock, 0, st>>>(d, bvh);
                 ++launched;

@@ -137,7 +137,7 @@ struct ResidentParams
     int64_t smem_bytes   = 0; // shared memory available to one CTA
     int32_t vertex_bytes = 16; // sizeof(Real4<R>)
     int32_t max_threads  = 512;
-    bool rotate_items    = false; // part A clusters on the warps with a sub-partition to themselves (item_rotation)
+    bool rotate_items    = true;  // part A clusters on the warps with a sub-partition to themselves (item_rotation)
 };
 
 // Which thread runs cluster i of a (colour, region) step.  Warp w of a CTA issues on sub-partition w % 4,

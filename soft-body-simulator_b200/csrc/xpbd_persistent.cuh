@@ -214,7 +214,6 @@ struct PersistentArgs
     int32_t n_run;                 // regions this launch runs (entries of region_order)
     int32_t nvc;                   // scratch entries per thread (4 * NVC4 of the instantiation)
     int32_t rot;                   // cluster i of a step runs on thread (i + rot) % nt (ClusterPlan::rot)
-    int32_t poll_first;            // issue the polls of the next cluster before the pushes of this one
     int64_t n_clusters;
     int32_t const* region_order;   // CTA b runs region_order[b], [b + grid], ...; regions that share
                                    // vertices come first, one per CTA
@@ -413,13 +412,10 @@ __device__ __forceinline__ uint32_t expected_tag(StepInfo const& si, uint32_t me
 
 // Fetch of one cluster: every entry of its fetch list waits for the tag of its previous touch and
 // lands in the thread's scratch slots; all polls of a round are in flight together.
-// `between` runs once, after the first records are requested and before any answer is examined (hence
-// before any scratch slot is overwritten): the pushes of the cluster that just ran go there, so that the
-// polls do not queue behind those scattered stores in the load/store pipe.
-template <typename R, int NVC4, typename Stamp, typename Between>
+template <typename R, int NVC4, typename Stamp>
 __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64_t q, uint4 const (&fmeta)[NVC4],
                                                Real4<R> const (&fw)[NVC4], Real4<R>* sx, StepInfo const& si,
-                                               Stamp&& stamp, Between&& between)
+                                               Stamp&& stamp)
 {
     int const tid = threadIdx.x, nt = blockDim.x;
     uint32_t meta[4 * NVC4];
@@ -457,8 +453,6 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64
                 if (pending >> (h + e) & 1u)
                     raw[e] = Xchg<R>::fetch(a.box, static_cast<uint32_t>(h + e) * static_cast<uint32_t>(a.n_clusters) + mine,
                                             a.world > 1);
-            if (h == 0 && polls == 0)
-                between();
 #pragma unroll
             for (int e = 0; e < kBatch; ++e)
                 if (pending >> (h + e) & 1u)
@@ -849,13 +843,12 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
             stamp(6);
         }
 
-        // ---- (3) the fetched vertices of the cluster that ran go to whoever touches them next, and the
-        //          next cluster becomes the prepared one: its shared vertices are fetched now, before the
-        //          barrier when it belongs to the next phase.  The first polls are issued BEFORE the
-        //          pushes (poll_first): the pushes are scattered 16-byte stores that keep the load/store
-        //          pipe busy for ~1000 cycles, and a poll queued behind them took 1600 cycles to answer.
-        bool const gather_next = has_next && next_in_a;
-        if (pushing && !(a.poll_first && gather_next))
+        // ---- (3) the fetched vertices of the cluster that ran go to whoever touches them next — first,
+        //          because a neighbour's next step waits for them (issuing this thread's own polls ahead
+        //          of the pushes hid their latency but cost 8 % of the frame: profiles/r01_summary.md) —
+        //          and the next cluster becomes the prepared one: its shared vertices are fetched now,
+        //          before the barrier when it belongs to the next phase
+        if (pushing)
             push_cluster<R, NVC4>(a, to, to_owner, sx, si, stamp);
         item_i = has_next ? ni_next : -1;
         if (has_next)
@@ -866,10 +859,7 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                 gather_cluster<R, NVC4>(a, next_q, nmeta, nw, sx,
                                         StepInfo{a.base + static_cast<uint32_t>(np), a.base,
                                                  static_cast<uint32_t>(8 * (2 * (nk > 0 ? 1 : 0) + cs)), false, false},
-                                        stamp, [&] {
-                                            if (pushing && a.poll_first)
-                                                push_cluster<R, NVC4>(a, to, to_owner, sx, si, stamp);
-                                        });
+                                        stamp);
         }
         if (advance)
         {
@@ -1206,10 +1196,6 @@ struct PersistentPlan
 
         args.nvc              = nvc;
         args.rot              = cp.rot;
-        // development knob for A/B timing: SBSB200_POLL_FIRST=1 issues the polls before the pushes
-        args.poll_first       = 0;
-        if (char const* e = std::getenv("SBSB200_POLL_FIRST"))
-            args.poll_first = std::atoi(e) != 0 ? 1 : 0;
         args.n_clusters       = Q;
         args.region_order     = region_order.p;
         args.tet_slots        = tet_slots.p;

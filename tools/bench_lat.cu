@@ -43,6 +43,88 @@ __global__ void pingpong(uint4* flags, long long* out, int partner, int iters)
     long long t1 = clock64();
     if (me0) out[0] = (t1 - t0) / iters;
 }
+
+// The exchange pattern of the resident kernel: every thread of a few warps per SM pushes 8 records to
+// scattered mailboxes (16-byte stores), then polls 8 records laid out [slot][thread] (coalesced 16-byte
+// loads).  Cycles until the stores are issued, and until the loads that follow have answered.
+// STORE: 0 st.relaxed.gpu.b128, 1 plain st.global.v4.u32, 2 st.global.cg.v4.u32
+// LOAD : 0 ld.relaxed.gpu.b128, 1 ld.global.cg.v4.u32, 2 ld.volatile.global.v4.u32
+template <int STORE, int LOAD, bool LOADS_FIRST>
+__global__ void exchange(uint4* box, unsigned n_box, long long* out, unsigned* sink, int iters)
+{
+    unsigned const tid = threadIdx.x, nt = blockDim.x, gid = blockIdx.x * nt + tid;
+    unsigned acc = 0;
+    long long t_store = 0, t_load = 0;
+    for (int it = 0; it < iters; ++it)
+    {
+        unsigned seed = (gid * 2654435761u) ^ (unsigned(it) * 40503u);
+        uint4* dst[8];
+        for (int e = 0; e < 8; ++e)
+        {
+            seed   = seed * 1664525u + 1013904223u;
+            dst[e] = box + (seed >> 8) % n_box;                       // scattered
+        }
+        uint4 const* src = box + ((blockIdx.x * 8u) * nt + tid) % n_box; // [slot][thread]: + e * nt
+        __syncthreads();
+        long long t0 = clock64();
+        uint4 got[8];
+        auto loads = [&] {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+            {
+                uint4 const* p = src + e * nt;
+                if (LOAD == 0) { W w = ldb(p); got[e] = make_uint4((unsigned)w.lo, (unsigned)(w.lo >> 32), (unsigned)w.hi, (unsigned)(w.hi >> 32)); }
+                if (LOAD == 1) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(got[e].x), "=r"(got[e].y), "=r"(got[e].z), "=r"(got[e].w) : "l"(p));
+                if (LOAD == 2) asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(got[e].x), "=r"(got[e].y), "=r"(got[e].z), "=r"(got[e].w) : "l"(p));
+            }
+        };
+        auto stores = [&] {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+            {
+                if (STORE == 0) stb(dst[e], W{gid, (unsigned long long)it});
+                if (STORE == 1) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst[e]), "r"(gid), "r"(0u), "r"(unsigned(it)), "r"(0u));
+                if (STORE == 2) asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst[e]), "r"(gid), "r"(0u), "r"(unsigned(it)), "r"(0u));
+            }
+        };
+        if (LOADS_FIRST) loads();
+        stores();
+        long long t1;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1));
+        if (!LOADS_FIRST) loads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            acc += got[e].x ^ got[e].w;
+        long long t2;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t2) : "r"(acc));
+        t_store += t1 - t0;
+        t_load += t2 - t1;
+    }
+    if (tid == 0)
+    {
+        out[2 * blockIdx.x]     = t_store / iters;
+        out[2 * blockIdx.x + 1] = t_load / iters;
+    }
+    sink[gid] = acc;
+}
+
+template <int STORE, int LOAD, bool LOADS_FIRST>
+static void run_exchange(char const* name, uint4* box, unsigned n_box, long long* out, unsigned* sink)
+{
+    for (int threads : {96, 192})
+    {
+        for (int rep = 0; rep < 2; ++rep)
+        {
+            exchange<STORE, LOAD, LOADS_FIRST><<<148, threads>>>(box, n_box, out, sink, 200);
+            cudaDeviceSynchronize();
+        }
+        long long hc[296]; cudaMemcpy(hc, out, sizeof hc, cudaMemcpyDeviceToHost);
+        double a = 0, b = 0; for (int i = 0; i < 148; ++i) { a += hc[2 * i]; b += hc[2 * i + 1]; }
+        printf("exchange %-44s %3d threads/SM: %5.0f cycles to issue%s 8 scattered stores, %5.0f more until 8 coalesced loads answered\n",
+               name, threads, a / 148, LOADS_FIRST ? " 8 loads +" : "", b / 148);
+    }
+}
+
 int main()
 {
     int n = 1 << 20;
@@ -66,6 +148,19 @@ int main()
         cudaDeviceSynchronize();
         long long c; cudaMemcpy(&c, out, 8, cudaMemcpyDeviceToHost);
         printf("ping-pong block 0 <-> block %d: %lld cycles per round trip (2 store->visible hops)\n", partner, c);
+    }
+    {
+        unsigned const n_box = 1u << 20; // 16 MB of mailboxes, as config 3
+        unsigned* sink; cudaMalloc(&sink, 4 * 148 * 256);
+        long long* out2; cudaMalloc(&out2, 8 * 2 * 148);
+        run_exchange<0, 0, false>("st.relaxed.gpu.b128 / ld.relaxed.gpu.b128", tab, n_box, out2, sink);
+        run_exchange<1, 0, false>("st.global.v4 (weak) / ld.relaxed.gpu.b128", tab, n_box, out2, sink);
+        run_exchange<2, 0, false>("st.global.cg.v4 / ld.relaxed.gpu.b128", tab, n_box, out2, sink);
+        run_exchange<0, 1, false>("st.relaxed.gpu.b128 / ld.global.cg.v4", tab, n_box, out2, sink);
+        run_exchange<1, 1, false>("st.global.v4 (weak) / ld.global.cg.v4", tab, n_box, out2, sink);
+        run_exchange<0, 2, false>("st.relaxed.gpu.b128 / ld.volatile.v4", tab, n_box, out2, sink);
+        run_exchange<0, 0, true>("loads first: st.relaxed.gpu / ld.relaxed.gpu", tab, n_box, out2, sink);
+        run_exchange<1, 1, true>("loads first: st.global.v4 / ld.global.cg.v4", tab, n_box, out2, sink);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
 }
