@@ -91,3 +91,23 @@ def test_config2_at_full_size_fp32(sbs, scenes, oracle):
     xr, _ = ref.download(0)
     dev = np.abs(xg - xr).max() / scene.bbox_diagonal()
     assert dev <= 1e-4, dev
+
+
+def test_config3_at_full_size_one_substep_fp32(sbs, scenes, oracle):
+    """BASELINE configs[2], the bench workload (1M tets on sphere + floor, BVH broadphase, 148 regions, six
+    warps per region with the clusters that exchange vertices on the warps that have a sub-partition to
+    themselves): ONE substep (detection + 10 iterations = 1e7 projections on the CPU) against the reference
+    algorithm run in the exported colour order, fp32 build."""
+    scene = scenes.config3()
+    scene.dt = scene.dt / scene.substeps
+    scene.substeps = 1
+    sim, ids, ref = run_pair(sbs, oracle, scene, 32, 0)
+    st = sim.stats()
+    assert st["n_tets"] == 1_000_000 and st["schedule"] == sbs.SCHED_PERSISTENT and st["n_regions"] > 100
+    xg, vg = sim.download(ids[0])
+    xr, vr = ref.download(0)
+    dev = np.abs(xg - xr).max() / scene.bbox_diagonal()
+    assert dev <= 1e-4, dev
+    assert len(sim.contacts()[0]) == len(ref.contacts()[0]) > 0
+    assert np.abs(xg - scene.items[0].x).max() > 1e-3        # something moved
+
