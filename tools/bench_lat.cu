@@ -125,6 +125,149 @@ static void run_exchange(char const* name, uint4* box, unsigned n_box, long long
     }
 }
 
+
+// Round trip of a poll: LOADS strong 128-bit loads per thread, issued together, until all have answered.
+// Three warps per SM poll; with `writers` three more warps of every SM keep storing (strong, scattered) into the
+// mailboxes another SM polls, as the neighbours of a region do.  layout 0: mailboxes [slot][thread] (a warp's
+// load covers four 128-byte lines, eight mailboxes of eight different writers per line ... as in the kernel);
+// layout 1: one mailbox per 128-byte line.
+template <int LOADS>
+__global__ void poll_probe(uint4* box, long long* out, unsigned* sink, int iters, int writers, int layout)
+{
+    unsigned const tid = threadIdx.x, warp = tid / 32;
+    unsigned const stride = layout ? 8u : 1u;                 // in 16-byte units
+    unsigned const per_cta = 8u * 96u * stride;                // mailboxes of one CTA's pollers
+    unsigned acc = 0;
+    long long total = 0;
+    if (warp < 3)
+    {
+        uint4 const* mine = box + blockIdx.x * per_cta + tid * stride;
+        for (int it = 0; it < iters; ++it)
+        {
+            long long t0 = clock64();
+            W got[LOADS];
+#pragma unroll
+            for (int e = 0; e < LOADS; ++e)
+                got[e] = ldb(mine + e * 96u * stride);
+#pragma unroll
+            for (int e = 0; e < LOADS; ++e)
+                acc += (unsigned)got[e].lo ^ (unsigned)(got[e].hi >> 32);
+            long long t1;
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1) : "r"(acc));
+            total += t1 - t0;
+        }
+        if (tid == 0)
+            out[blockIdx.x] = total / iters;
+    }
+    else if (writers)
+    {
+        unsigned const victim = (blockIdx.x + 1 + warp) % gridDim.x;
+        unsigned seed = blockIdx.x * 7919u + tid;
+        for (int it = 0; it < iters * 2; ++it)
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+            {
+                seed = seed * 1664525u + 1013904223u;
+                stb(box + victim * per_cta + ((seed >> 10) % (8u * 96u)) * stride, W{seed, (unsigned long long)it});
+            }
+    }
+    sink[blockIdx.x * blockDim.x + tid] = acc;
+}
+
+template <int LOADS>
+static void run_poll(uint4* box, long long* out, unsigned* sink)
+{
+    for (int layout = 0; layout < 2; ++layout)
+        for (int writers = 0; writers < 2; ++writers)
+        {
+            for (int rep = 0; rep < 2; ++rep)
+            {
+                poll_probe<LOADS><<<148, 192>>>(box, out, sink, 300, writers, layout);
+                cudaDeviceSynchronize();
+            }
+            long long hc[148]; cudaMemcpy(hc, out, sizeof hc, cudaMemcpyDeviceToHost);
+            double m = 0; for (auto c : hc) m += double(c);
+            printf("poll round trip, %d strong 128-bit loads per thread, %s, %s: %5.0f cycles\n", LOADS,
+                   layout ? "one mailbox per 128-byte line" : "mailboxes [slot][thread]         ",
+                   writers ? "neighbours writing" : "nobody writing    ", m / 148);
+        }
+}
+
+
+// The same poll probe with other access flavours: SF 0 st.relaxed.gpu.b128, 1 st.global.v4.u32 (weak), 2 st.global.cg.v4.u32;
+// LF 0 ld.relaxed.gpu.b128, 1 ld.global.cg.v4.u32, 2 ld.volatile.global.v4.u32.  `gap`: the writers pause that many
+// nanoseconds between batches of 8 stores (0 = hammer), to see how the polls degrade with the write rate.
+template <int LOADS, int SF, int LF>
+__global__ void poll_flavours(uint4* box, long long* out, unsigned* sink, int iters, unsigned gap)
+{
+    unsigned const tid = threadIdx.x, warp = tid / 32;
+    unsigned const per_cta = 8u * 96u;
+    unsigned acc = 0;
+    long long total = 0;
+    if (warp < 3)
+    {
+        uint4 const* mine = box + blockIdx.x * per_cta + tid;
+        for (int it = 0; it < iters; ++it)
+        {
+            long long t0 = clock64();
+            uint4 got[LOADS];
+#pragma unroll
+            for (int e = 0; e < LOADS; ++e)
+            {
+                uint4 const* p = mine + e * 96u;
+                if (LF == 0) { W w = ldb(p); got[e] = make_uint4((unsigned)w.lo, (unsigned)(w.lo >> 32), (unsigned)w.hi, (unsigned)(w.hi >> 32)); }
+                if (LF == 1) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(got[e].x), "=r"(got[e].y), "=r"(got[e].z), "=r"(got[e].w) : "l"(p));
+                if (LF == 2) asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(got[e].x), "=r"(got[e].y), "=r"(got[e].z), "=r"(got[e].w) : "l"(p));
+            }
+#pragma unroll
+            for (int e = 0; e < LOADS; ++e)
+                acc += got[e].x ^ got[e].w;
+            long long t1;
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1) : "r"(acc));
+            total += t1 - t0;
+        }
+        if (tid == 0)
+            out[blockIdx.x] = total / iters;
+    }
+    else
+    {
+        unsigned const victim = (blockIdx.x + 1 + warp) % gridDim.x;
+        unsigned seed = blockIdx.x * 7919u + tid;
+        int const rounds = gap ? iters / 2 : iters * 2;
+        for (int it = 0; it < rounds; ++it)
+        {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+            {
+                seed = seed * 1664525u + 1013904223u;
+                uint4* d = box + victim * per_cta + (seed >> 10) % per_cta;
+                if (SF == 0) stb(d, W{seed, (unsigned long long)it});
+                if (SF == 1) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(d), "r"(seed), "r"(0u), "r"(unsigned(it)), "r"(0u));
+                if (SF == 2) asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(d), "r"(seed), "r"(0u), "r"(unsigned(it)), "r"(0u));
+            }
+            if (gap)
+                __nanosleep(gap);
+        }
+    }
+    sink[blockIdx.x * blockDim.x + tid] = acc;
+}
+
+template <int LOADS, int SF, int LF>
+static void run_flavours(char const* name, uint4* box, long long* out, unsigned* sink)
+{
+    for (unsigned gap : {0u, 2000u, 5000u})
+    {
+        for (int rep = 0; rep < 2; ++rep)
+        {
+            poll_flavours<LOADS, SF, LF><<<148, 192>>>(box, out, sink, 300, gap);
+            cudaDeviceSynchronize();
+        }
+        long long hc[148]; cudaMemcpy(hc, out, sizeof hc, cudaMemcpyDeviceToHost);
+        double m = 0; for (auto c : hc) m += double(c);
+        printf("poll flavours, %d loads, %-40s writers pause %4u ns: %5.0f cycles\n", LOADS, name, gap, m / 148);
+    }
+}
+
 int main()
 {
     int n = 1 << 20;
@@ -161,6 +304,29 @@ int main()
         run_exchange<0, 2, false>("st.relaxed.gpu.b128 / ld.volatile.v4", tab, n_box, out2, sink);
         run_exchange<0, 0, true>("loads first: st.relaxed.gpu / ld.relaxed.gpu", tab, n_box, out2, sink);
         run_exchange<1, 1, true>("loads first: st.global.v4 / ld.global.cg.v4", tab, n_box, out2, sink);
+    }
+    {
+        uint4* big; cudaMalloc(&big, sizeof(uint4) * 148u * 8u * 96u * 8u); cudaMemset(big, 0, sizeof(uint4) * 148u * 8u * 96u * 8u);
+        unsigned* sink; cudaMalloc(&sink, 4 * 148 * 256);
+        long long* out3; cudaMalloc(&out3, 8 * 148);
+        run_poll<1>(big, out3, sink);
+        run_poll<2>(big, out3, sink);
+        run_poll<4>(big, out3, sink);
+        run_poll<8>(big, out3, sink);
+    }
+    {
+        uint4* big; cudaMalloc(&big, sizeof(uint4) * 148u * 8u * 96u); cudaMemset(big, 0, sizeof(uint4) * 148u * 8u * 96u);
+        unsigned* sink; cudaMalloc(&sink, 4 * 148 * 256);
+        long long* out4; cudaMalloc(&out4, 8 * 148);
+        run_flavours<4, 0, 0>("st.relaxed.gpu / ld.relaxed.gpu", big, out4, sink);
+        run_flavours<4, 1, 0>("st.global.v4 (weak) / ld.relaxed.gpu", big, out4, sink);
+        run_flavours<4, 2, 0>("st.global.cg.v4 / ld.relaxed.gpu", big, out4, sink);
+        run_flavours<4, 0, 1>("st.relaxed.gpu / ld.global.cg.v4", big, out4, sink);
+        run_flavours<4, 0, 2>("st.relaxed.gpu / ld.volatile.v4", big, out4, sink);
+        run_flavours<4, 1, 1>("st.global.v4 (weak) / ld.global.cg.v4", big, out4, sink);
+        run_flavours<8, 0, 0>("st.relaxed.gpu / ld.relaxed.gpu", big, out4, sink);
+        run_flavours<8, 1, 1>("st.global.v4 (weak) / ld.global.cg.v4", big, out4, sink);
+        run_flavours<8, 0, 2>("st.relaxed.gpu / ld.volatile.v4", big, out4, sink);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
 }
