@@ -3,6 +3,8 @@ import importlib, sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sbs = importlib.import_module("soft-body-simulator_b200")
 sc = importlib.import_module("soft-body-simulator_b200.scenes")
+if os.environ.get("SBSB200_LIB"):          # a variant build of the library (development A/B)
+    sbs.LIB_PATH = os.environ["SBSB200_LIB"]
 cfg = sys.argv[1] if len(sys.argv) > 1 else "config1"
 prec = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 sched = int(sys.argv[3]) if len(sys.argv) > 3 else 0
