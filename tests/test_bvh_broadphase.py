@@ -29,6 +29,30 @@ def test_bvh_finds_exactly_the_contacts_of_the_plain_narrowphase_inside_the_volu
     assert np.array_equal(out[0][1][0], out[1][1][0]) and np.array_equal(out[0][1][1], out[1][1][1])
 
 
+@pytest.mark.parametrize("schedule", [1, 2])
+def test_bvh_leaf_order_kept_over_several_frames_loses_no_contact(sbs, scenes, schedule):
+    """The leaves are re-sorted every 8 frames only (eager frames of the resident schedule); the spheres are
+    refitted at every detection, so frames that reuse an older order still find exactly the contacts of the plain
+    narrowphase while the body moves and deforms."""
+    scene = scenes.config3(W=9, H=9, D=13, radius=6.0, gap=-0.4)
+    sims = []
+    for mode in (sbs.BROADPHASE_NONE, sbs.BROADPHASE_BVH):
+        sim = sbs.Simulation(0, 32, schedule=schedule)
+        sim.set_broadphase(mode)
+        sims.append((sim, scene.instantiate(sim)))
+    seen = 0
+    for frame in range(5):
+        keys, states = [], []
+        for sim, ids in sims:
+            sim.step(scene.dt, 3, 4, True)
+            keys.append(contacts_key(sim))
+            states.append(sim.download(ids[0]))
+        assert keys[0] == keys[1], "frame %d" % frame
+        assert np.array_equal(states[0][0], states[1][0]) and np.array_equal(states[0][1], states[1][1])
+        seen += len(keys[0])
+    assert seen > 0
+
+
 def test_bvh_culls_like_the_reference_when_the_body_is_outside_the_sdf_volume(sbs, scenes, oracle):
     """A beam dips below the floor plane, but the plane's englobing volume() box is far away: the root
     sphere neither has its centre inside the SDF nor reaches the box, so the reference's traversal stops at
