@@ -1449,6 +1449,11 @@ int sbsb200_finalize(sbsb200_ctx* c)
             // development knob for A/B timing: SBSB200_ROTATE_ITEMS=0 keeps cluster i of a step on thread i
             if (char const* e = std::getenv("SBSB200_ROTATE_ITEMS"))
                 rp.rotate_items = std::atoi(e) != 0;
+            // experimental, off by default: hand-off inside a region, slab-shaped regions
+            if (char const* e = std::getenv("SBSB200_HANDOFF"))
+                rp.handoff = std::atoi(e) != 0 && c->precision == SBSB200_FP32 && c->world == 1;
+            if (char const* e = std::getenv("SBSB200_SLABS"))
+                rp.slabs = std::atoi(e) != 0 && c->world == 1;
             build_cluster_plan(h, PersistentPlan<float>::regions_for(c->sm_count, T, c->world),
                                PersistentPlan<float>::wants_region_per_body(h, c->sm_count), c->green_plan, &rp,
                                &c->plan);

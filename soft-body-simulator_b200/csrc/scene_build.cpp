@@ -533,6 +533,30 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         for (Cluster& c : clusters)
             c.region = body_region[static_cast<size_t>(c.body)];
     }
+    else if (n_regions > 1 && resident && resident->slabs && !clusters.empty())
+    { // layers of the cluster grid along its longest axis, consecutive layers per region, at most one region per layer
+        uint32_t lo[3] = {~0u, ~0u, ~0u}, hi[3] = {0u, 0u, 0u};
+        for (Cluster const& c : clusters)
+        {
+            uint32_t const g[3] = {c.cx, c.cy, c.cz};
+            for (int d = 0; d < 3; ++d)
+            {
+                lo[d] = std::min(lo[d], g[d]);
+                hi[d] = std::max(hi[d], g[d]);
+            }
+        }
+        int axis = 0;
+        for (int d = 1; d < 3; ++d)
+            if (hi[d] - lo[d] > hi[axis] - lo[axis])
+                axis = d;
+        int64_t const layers = static_cast<int64_t>(hi[axis] - lo[axis]) + 1;
+        out.n_regions        = static_cast<int32_t>(std::min<int64_t>(n_regions, layers));
+        for (Cluster& c : clusters)
+        {
+            uint32_t const g[3] = {c.cx, c.cy, c.cz};
+            c.region = static_cast<int32_t>((static_cast<int64_t>(g[axis] - lo[axis]) * out.n_regions) / layers);
+        }
+    }
     else if (n_regions > 1)
     {
         out.n_regions = n_regions;
@@ -571,6 +595,102 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         for (uint32_t m = 0; m < c.count; ++m)
             out.tet_region[sorted[c.first + m]] = c.region;
 
+    // Hand-off: renumber the colours so that consecutive colours hand a shared vertex over INSIDE a region as
+    // often as possible.  D[a][b] = shared vertices whose clusters of colours a and b lie in different regions;
+    // the order is the path of least total D (exhaustive up to 9 colours, nearest neighbour + 2-opt beyond).
+    // On a lattice this is a Gray code of the cell parities: every step then depends on other regions across
+    // one face orientation only.  Any order of the colours is a valid Gauss-Seidel order.
+    if (resident && resident->handoff && out.n_regions > 1 && out.n_colours > 2)
+    {
+        int32_t const C = out.n_colours;
+        struct Touch3
+        {
+            uint32_t v;
+            int32_t colour, region;
+        };
+        std::vector<Touch3> touches;
+        touches.reserve(clusters.size() * 8);
+        for (Cluster const& c : clusters)
+            for (uint32_t u = 0; u < c.nv; ++u)
+                touches.push_back({c.verts[u], c.colour, c.region});
+        std::sort(touches.begin(), touches.end(), [](Touch3 const& a, Touch3 const& b) { return a.v < b.v; });
+        std::vector<int64_t> D(static_cast<size_t>(C) * C, 0);
+        for (size_t i = 0; i < touches.size();)
+        {
+            size_t j = i;
+            while (j < touches.size() && touches[j].v == touches[i].v)
+                ++j;
+            for (size_t a = i; a < j; ++a)
+                for (size_t b = a + 1; b < j; ++b)
+                    if (touches[a].region != touches[b].region)
+                    {
+                        ++D[static_cast<size_t>(touches[a].colour) * C + touches[b].colour];
+                        ++D[static_cast<size_t>(touches[b].colour) * C + touches[a].colour];
+                    }
+            i = j;
+        }
+        auto const cost = [&](std::vector<int32_t> const& o) {
+            int64_t s = 0;
+            for (int32_t i = 0; i + 1 < C; ++i) // open path: the sweep's last colour never hands over to its first
+                s += D[static_cast<size_t>(o[i]) * C + o[i + 1]];
+            return s;
+        };
+        std::vector<int32_t> best(static_cast<size_t>(C));
+        std::iota(best.begin(), best.end(), 0);
+        int64_t best_cost = cost(best);
+        if (C <= 9)
+        {
+            std::vector<int32_t> o(best);
+            while (std::next_permutation(o.begin(), o.end()))
+            {
+                int64_t const s = cost(o);
+                if (s < best_cost)
+                {
+                    best_cost = s;
+                    best      = o;
+                }
+            }
+        }
+        else
+        {
+            std::vector<int32_t> o{0};
+            std::vector<char> taken(static_cast<size_t>(C), 0);
+            taken[0] = 1;
+            while (static_cast<int32_t>(o.size()) < C)
+            {
+                int32_t pick = -1;
+                for (int32_t c = 0; c < C; ++c)
+                    if (!taken[c] && (pick < 0 || D[static_cast<size_t>(o.back()) * C + c] <
+                                                      D[static_cast<size_t>(o.back()) * C + pick]))
+                        pick = c;
+                taken[pick] = 1;
+                o.push_back(pick);
+            }
+            for (bool improved = true; improved;)
+            {
+                improved = false;
+                for (int32_t i = 1; i + 1 < C; ++i)
+                    for (int32_t j = i + 1; j < C; ++j)
+                    {
+                        std::vector<int32_t> t(o);
+                        std::reverse(t.begin() + i, t.begin() + j + 1);
+                        if (cost(t) < cost(o))
+                        {
+                            o        = t;
+                            improved = true;
+                        }
+                    }
+            }
+            if (cost(o) < best_cost)
+                best = o;
+        }
+        std::vector<int32_t> renumber(static_cast<size_t>(C));
+        for (int32_t i = 0; i < C; ++i)
+            renumber[static_cast<size_t>(best[i])] = i;
+        for (Cluster& c : clusters)
+            c.colour = renumber[static_cast<size_t>(c.colour)];
+    }
+
     // resident schedule: vertex classification, cluster parts, launch shape
     if (resident)
     {
@@ -597,7 +717,7 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         // thread count, then try once with the count that classification needs; keep it if it holds.
         std::vector<int64_t> total(b_cnt), none(n_steps, 0);
         auto classify_with = [&](int32_t nt) -> int32_t { // returns the thread count this classification needs
-            int64_t const scratch  = static_cast<int64_t>(out.nvc) * nt;
+            int64_t const scratch  = static_cast<int64_t>(resident->handoff ? 2 : 1) * out.nvc * nt;
             int64_t const capacity = std::min<int64_t>(resident->smem_bytes / resident->vertex_bytes - scratch, 65535 - scratch);
             if (capacity < 0)
             {
@@ -633,6 +753,12 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
             }
         }
         out.rot = resident->rotate_items ? item_rotation(out.nt) : 0;
+        {   // hand-off needs every step to be a single round (a thread's scratch slots belong to ONE cluster per step)
+            int64_t widest = 0;
+            for (size_t i = 0; i < a_cnt.size(); ++i)
+                widest = std::max(widest, a_cnt[i] + b_cnt[i]);
+            out.banks = resident->handoff && region_plan && widest <= out.nt ? 2 : 1;
+        }
         if (out.nvc > kMaxClusterVertices)
             out.why_not = "a cluster has more than 16 distinct vertices";
         if (out.n_colours > 120)
@@ -735,7 +861,7 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
                     uint32_t const v = scene.tets[4 * static_cast<size_t>(t) + a];
                     uint32_t slot;
                     if (region_plan->vertex_region[v] == reg)
-                        slot = static_cast<uint32_t>(out.nvc) * out.nt + region_plan->vertex_slot[v];
+                        slot = static_cast<uint32_t>(out.banks * out.nvc) * out.nt + region_plan->vertex_slot[v];
                     else
                     { // k-th fetched vertex of this cluster
                         uint32_t kf = 0;
@@ -832,10 +958,12 @@ bool build_mailbox_routes(HostScene const& scene, ClusterPlan const& cp, RegionP
         out.why_not = "too many mailboxes for 28-bit routing words";
         return false;
     }
-    std::vector<int32_t> cluster_colour(static_cast<size_t>(Q), 0), cluster_region(static_cast<size_t>(Q), 0);
+    std::vector<int32_t> cluster_colour(static_cast<size_t>(Q), 0), cluster_region(static_cast<size_t>(Q), 0),
+        cluster_item(static_cast<size_t>(Q), 0); // position in its chunk = in its step for part A (first in a step)
     for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
         for (int32_t i = 0; i < cp.chunks[ch].n[0]; ++i)
         {
+            cluster_item[static_cast<size_t>(cp.chunks[ch].cfirst + i)] = i;
             cluster_colour[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
                 static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
             cluster_region[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
@@ -870,6 +998,20 @@ bool build_mailbox_routes(HostScene const& scene, ClusterPlan const& cp, RegionP
     });
     out.to.assign(out.n_entries, kRouteNone);
     out.to_owner.assign(out.n_entries, kRouteNone);
+    out.local_prev.assign(out.n_entries, 0);
+    out.n_local = 0;
+    if (cp.banks == 2 && static_cast<uint64_t>(out.n_entries) + out.ifv.size() >= kRouteLocalBit)
+    {
+        out.why_not = "too many mailboxes for 27-bit routing words (hand-off)";
+        return false;
+    }
+    // hand-off: the next touch is by a cluster of the same region in the very next step -> the vertex goes
+    // straight into that cluster's scratch slot (entry * nt + thread), no mailbox, no poll
+    auto const local_route = [&](uint32_t box) {
+        uint32_t const q = box % static_cast<uint32_t>(Q), entry = box / static_cast<uint32_t>(Q);
+        uint32_t const thread = static_cast<uint32_t>((cluster_item[q] + cp.rot) % cp.nt);
+        return kRouteLocalBit | (entry * static_cast<uint32_t>(cp.nt) + thread);
+    };
     out.ifv_first.assign(out.ifv.size(), kRouteNone);
     for (size_t i = 0; i < touches.size();)
     {
@@ -892,6 +1034,17 @@ bool build_mailbox_routes(HostScene const& scene, ClusterPlan const& cp, RegionP
                 return false;
             }
             uint32_t const surface       = (cp.vertex_meta[v] & 0x100u) ? kRouteSurfaceBit : 0u;
+            bool const local = cp.banks == 2 && t + 1 < j && touches[t + 1].colour == touches[t].colour + 1 &&
+                               cluster_region[touches[t + 1].box % static_cast<uint32_t>(Q)] ==
+                                   cluster_region[touches[t].box % static_cast<uint32_t>(Q)];
+            if (local)
+            {
+                out.to[touches[t].box]             = local_route(touches[t + 1].box);
+                out.to_owner[touches[t].box]       = local_route(touches[t + 1].box) | surface;
+                out.local_prev[touches[t + 1].box] = 1;
+                ++out.n_local;
+                continue;
+            }
             out.to[touches[t].box]       = entry_route(t + 1 < j ? touches[t + 1].box : touches[i].box);
             out.to_owner[touches[t].box] = (t + 1 < j ? entry_route(touches[t + 1].box) : owner_route(pos)) | surface;
         }
@@ -909,7 +1062,10 @@ bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, Reg
     if (static_cast<int64_t>(cp.tet_slots.size()) != 4 * T ||
         static_cast<int64_t>(cp.cl_fetch.size()) != static_cast<int64_t>(cp.nvc) * Q)
         return false;
-    uint32_t const scratch = static_cast<uint32_t>(cp.nvc) * static_cast<uint32_t>(cp.nt);
+    if (cp.banks < 1 || cp.banks > 2)
+        return false;
+    // tet slots name bank 0 of the scratch slots; resident vertices follow the last bank
+    uint32_t const scratch = static_cast<uint32_t>(cp.banks * cp.nvc) * static_cast<uint32_t>(cp.nt);
     int64_t clusters_seen  = 0;
     for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
     {

@@ -137,6 +137,13 @@ struct ResidentParams
     int64_t smem_bytes   = 0; // shared memory available to one CTA
     int32_t vertex_bytes = 16; // sizeof(Real4<R>)
     int32_t max_threads  = 512;
+    // EXPERIMENTAL, off by default (development knobs SBSB200_HANDOFF / SBSB200_SLABS):
+    bool handoff         = false; // shared vertices go from one cluster to the next through shared memory when both
+                                  // belong to the same region and run in consecutive steps (two banks of scratch
+                                  // slots), and the colours are ordered so that most consecutive touches do
+    bool slabs           = false; // regions = layers of clusters along the longest axis of the cluster grid (at most
+                                  // one region per layer) instead of compact Morton blocks: with the hand-off and the
+                                  // colour order that goes with it, most steps then depend on no other region at all
     bool rotate_items    = true;  // part A clusters on the warps with a sub-partition to themselves (item_rotation)
 };
 
@@ -167,6 +174,10 @@ struct ClusterPlan
     // resident schedule only
     int32_t nt  = 0;                     // threads per CTA the scratch slots were laid out for
     int32_t rot = 0;                     // cluster i of a step (part A first) runs on thread (i + rot) % nt, see item_rotation
+    int32_t banks = 1;                   // banks of scratch slots: 2 = the cluster of step p uses bank p % 2, so that a
+                                         // cluster may WRITE a shared vertex straight into the scratch slot of the
+                                         // cluster of the same region that touches it in the next step (hand-off);
+                                         // tet slots name bank 0, resident vertices start at banks * nvc * nt
     int32_t nvc = 0;                     // scratch entries per thread (multiple of 4, <= kMaxClusterVertices)
     std::vector<uint16_t> tet_slots;     // 4*T (storage order): index into the CTA's shared vertex array
     std::vector<uint32_t> cl_fetch;      // [nvc][n_clusters]: global vertex of scratch entry k, 0xffffffff = none
@@ -213,6 +224,11 @@ constexpr uint32_t kRouteNone       = 0xffffffffu;
 constexpr uint32_t kRouteIndexMask  = 0x0fffffffu;
 constexpr uint32_t kRouteSurfaceBit = 0x80000000u;
 constexpr int kRouteRankShift       = 28;
+// hand-off inside a region (ClusterPlan::banks == 2): bit 27 set, bits 0-26 = scratch slot (entry * nt + thread)
+// of the cluster that touches the vertex in the next step; mailbox indices then stay below 2^27
+constexpr uint32_t kRouteLocalBit       = 0x08000000u;
+constexpr uint32_t kRouteLocalIndexMask = 0x07ffffffu;
+constexpr uint32_t kMetaLocal           = 0xfefefefeu; // cl_meta of an entry that arrives by hand-off: nothing to poll
 
 struct MailboxRoutes
 {
@@ -223,6 +239,8 @@ struct MailboxRoutes
     std::vector<uint32_t> ifv_first;    // routing word of the first entry touching the vertex in a sweep
     std::vector<uint32_t> ifv_pos;      // V: position in ifv, kRouteNone for resident vertices
     std::vector<uint32_t> to, to_owner; // [nvc][Q] routing words, kRouteNone for unused slots
+    std::vector<uint8_t> local_prev;    // [nvc][Q] 1: the entry is handed over in shared memory by the previous touch
+    int64_t n_local = 0;                // how many
     std::string why_not;
 };
 

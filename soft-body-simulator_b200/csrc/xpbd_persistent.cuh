@@ -214,6 +214,9 @@ struct PersistentArgs
     int32_t n_run;                 // regions this launch runs (entries of region_order)
     int32_t nvc;                   // scratch entries per thread (4 * NVC4 of the instantiation)
     int32_t rot;                   // cluster i of a step runs on thread (i + rot) % nt (ClusterPlan::rot)
+    int32_t banks;                 // banks of scratch slots (ClusterPlan::banks); 2 only in the kHandoff kernels:
+                                   // the cluster of phase p keeps its fetched vertices in bank p % 2
+    uint2 const* tet_slots_odd;    // kHandoff: tet_slots with the scratch slots moved to bank 1 (odd phases)
     int64_t n_clusters;
     int32_t const* region_order;   // CTA b runs region_order[b], [b + grid], ...; regions that share
                                    // vertices come first, one per CTA
@@ -351,10 +354,11 @@ struct TetRecord<R, true>
 };
 
 template <typename R, bool kDict>
-__device__ __forceinline__ TetRecord<R, kDict> load_tet(PersistentArgs<R> const& a, int32_t t, int first_iteration)
+__device__ __forceinline__ TetRecord<R, kDict> load_tet(PersistentArgs<R> const& a, uint2 const* slots, int32_t t,
+                                                        int first_iteration)
 {
     TetRecord<R, kDict> q;
-    q.slots = __ldg(&a.tet_slots[t]);
+    q.slots = __ldg(&slots[t]);
     if constexpr (kDict)
         q.shape = __ldg(&a.tet_shape[t]);
     else
@@ -378,10 +382,10 @@ struct ClusterHead
 
 template <typename R, bool kDict>
 __device__ __forceinline__ void load_cluster_head(ClusterHead<R, kDict>& h, PersistentArgs<R> const& a,
-                                                  DevChunk const& ch, int32_t i, int first_iteration,
-                                                  Real4<R> const* s_dict)
+                                                  uint2 const* slots, DevChunk const& ch, int32_t i,
+                                                  int first_iteration, Real4<R> const* s_dict)
 {
-    h.tet0 = load_tet<R, kDict>(a, ch.first + i, first_iteration);
+    h.tet0 = load_tet<R, kDict>(a, slots, ch.first + i, first_iteration);
     R mat_id;
     if constexpr (kDict)
         mat_id = s_dict[3 * h.tet0.shape + 2].z; // waits for the shape id: one L2 round trip, a step ahead
@@ -412,7 +416,9 @@ __device__ __forceinline__ uint32_t expected_tag(StepInfo const& si, uint32_t me
 
 // Fetch of one cluster: every entry of its fetch list waits for the tag of its previous touch and
 // lands in the thread's scratch slots; all polls of a round are in flight together.
-template <typename R, int NVC4, typename Stamp>
+// kHandoff: entries marked kMetaLocal were written into the scratch slot by the previous touch (same region,
+// previous step) and are not polled.
+template <typename R, int NVC4, bool kHandoff, typename Stamp>
 __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64_t q, uint4 const (&fmeta)[NVC4],
                                                Real4<R> const (&fw)[NVC4], Real4<R>* sx, StepInfo const& si,
                                                Stamp&& stamp)
@@ -435,7 +441,7 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64
     }
 #pragma unroll
     for (int j = 0; j < 4 * NVC4; ++j)
-        if (meta[j] != kNoEntry)
+        if (meta[j] != kNoEntry && !(kHandoff && meta[j] == kMetaLocal))
             pending |= 1u << j;
     uint32_t const mine = static_cast<uint32_t>(q); // mailbox of entry j: j * n_clusters + q
     int polls = 0;
@@ -480,8 +486,8 @@ __device__ __forceinline__ void gather_cluster(PersistentArgs<R> const& a, int64
 template <typename R, int NVC4, bool kDict, typename Stamp>
 __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk const& ch, int32_t i, int64_t q,
                                             ClusterHead<R, kDict> const& head, Real4<R>* sx,
-                                            Real4<R> const* s_dict, int first_iteration, uint4 (&to)[NVC4],
-                                            uint4 (&to_owner)[NVC4], Stamp&& stamp)
+                                            Real4<R> const* s_dict, int first_iteration, uint2 const* slots,
+                                            uint4 (&to)[NVC4], uint4 (&to_owner)[NVC4], Stamp&& stamp)
 {
     DeviceScene<R> const& s = a.s;
     // where the fetched vertices go afterwards (static routing data): in flight while the tets run
@@ -505,7 +511,7 @@ __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk
         bool const more = i < n1;
         TetRecord<R, kDict> nxt;
         if (more)
-            nxt = load_tet<R, kDict>(a, t + n0, first_iteration);
+            nxt = load_tet<R, kDict>(a, slots, t + n0, first_iteration);
         uint32_t const a1 = cur.slots.x & 0xffffu, a2 = cur.slots.x >> 16, a3 = cur.slots.y & 0xffffu,
                        a4 = cur.slots.y >> 16;
         Real4<R> p1 = sx[a1], p2 = sx[a2], p3 = sx[a3], p4 = sx[a4];
@@ -547,10 +553,12 @@ __device__ __forceinline__ void run_cluster(PersistentArgs<R> const& a, DevChunk
 // Push every fetched vertex of the cluster that just ran to whoever touches it next, always: the tag is
 // what that touch waits for (select instead of branch per entry; the single-GPU and the peer-memory
 // variants are unswitched).  Reads the thread's scratch slots: call it before they are refilled.
-template <typename R, int NVC4, typename Stamp>
+// kHandoff: sx is this step's bank of scratch slots, sx_next the next step's, where a hand-off inside the region
+// deposits the vertex (routing word with kRouteLocalBit: the scratch slot of the cluster that runs next).
+template <typename R, int NVC4, bool kHandoff, typename Stamp>
 __device__ __forceinline__ void push_cluster(PersistentArgs<R> const& a, uint4 const (&to)[NVC4],
-                                             uint4 const (&to_owner)[NVC4], Real4<R> const* sx, StepInfo const& si,
-                                             Stamp&& stamp)
+                                             uint4 const (&to_owner)[NVC4], Real4<R> const* sx, Real4<R>* sx_next,
+                                             StepInfo const& si, Stamp&& stamp)
 {
     int const tid = threadIdx.x, nt = blockDim.x;
     {
@@ -570,7 +578,10 @@ __device__ __forceinline__ void push_cluster(PersistentArgs<R> const& a, uint4 c
                 bool const owner_next = si.to_owner | (si.surface_to_owner & ((tb[e] & kSurfaceBit) != 0u));
                 uint32_t const route  = owner_next ? tb[e] : ta[e];
                 uint32_t const index  = route & kBoxIndexMask;
-                if (tb[e] != kNoBox)
+                bool const local = kHandoff && tb[e] != kNoBox && (route & kRouteLocalBit) != 0u;
+                if (kHandoff && local)
+                    sx_next[route & kRouteLocalIndexMask] = p[e];
+                if (tb[e] != kNoBox && !local)
                 {
                     if (!multi)
                         Xchg<R>::store(a.box, index, p[e].x, p[e].y, p[e].z, si.step);
@@ -591,14 +602,19 @@ __device__ __forceinline__ long long clock_stamp()
     return t;
 }
 
-template <typename R, int NVC4, bool kTrace, bool kDict>
+template <typename R, int NVC4, bool kTrace, bool kDict, bool kHandoff>
 __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>* sx, DevChunk* s_chunks,
                            Real4<R>* s_dict)
 {
     DeviceScene<R> const& s = a.s;
     int const tid = threadIdx.x, nt = blockDim.x;
     R const dt              = a.dt;
-    Real4<R>* const sres    = sx + a.nvc * nt; // resident vertices follow the scratch slots
+    Real4<R>* const sres    = sx + (kHandoff ? a.banks : 1) * a.nvc * nt; // resident vertices follow the scratch slots
+    // kHandoff with two banks: the cluster of phase p keeps its fetched vertices in bank p % 2
+    auto bank_of  = [&](int32_t phase) -> int32_t { return kHandoff && a.banks > 1 && (phase & 1) ? a.nvc * nt : 0; };
+    auto slots_of = [&](int32_t phase) -> uint2 const* {
+        return kHandoff && (phase & 1) ? a.tet_slots_odd : a.tet_slots;
+    };
     int32_t const v0 = a.vtx_off[region], nv = a.vtx_off[region + 1] - v0;
     int32_t const i0 = a.ifv_off[region], ni = a.ifv_off[region + 1] - i0;
     int32_t const s0 = a.surf_off[region], ns = a.surf_off[region + 1] - s0;
@@ -700,7 +716,7 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
                     next_in_a          = ni_next < nA;
                     DevChunk const& ch = s_chunks[2 * nc + (next_in_a ? 0 : 1)];
                     int32_t const ci   = next_in_a ? ni_next : ni_next - nA;
-                    load_cluster_head<R, kDict>(nhead, a, ch, ci, nk == 0, s_dict);
+                    load_cluster_head<R, kDict>(nhead, a, slots_of(np), ch, ci, nk == 0, s_dict);
                     if (next_in_a)
                     {
                         next_q = static_cast<int64_t>(ch.cfirst) + ci;
@@ -836,8 +852,8 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
             { // cluster item_i of the phase runs on thread (item_i + rot) % nt; part A (clusters that fetch) first
                 bool const in_a    = item_i < nA;
                 DevChunk const& ch = s_chunks[2 * c + (in_a ? 0 : 1)];
-                run_cluster<R, NVC4, kDict>(a, ch, in_a ? item_i : item_i - nA, cur_q, head, sx, s_dict, k == 0, to,
-                                            to_owner, stamp);
+                run_cluster<R, NVC4, kDict>(a, ch, in_a ? item_i : item_i - nA, cur_q, head, sx, s_dict, k == 0,
+                                            slots_of(p), to, to_owner, stamp);
                 pushing = cur_q >= 0;
             }
             stamp(6);
@@ -849,14 +865,14 @@ __device__ void run_region(PersistentArgs<R> const& a, int32_t region, Real4<R>*
         //          and the next cluster becomes the prepared one: its shared vertices are fetched now,
         //          before the barrier when it belongs to the next phase
         if (pushing)
-            push_cluster<R, NVC4>(a, to, to_owner, sx, si, stamp);
+            push_cluster<R, NVC4, kHandoff>(a, to, to_owner, sx + bank_of(p), sx + bank_of(p + 1), si, stamp);
         item_i = has_next ? ni_next : -1;
         if (has_next)
         {
             head  = nhead;
             cur_q = next_q;
             if (next_in_a)
-                gather_cluster<R, NVC4>(a, next_q, nmeta, nw, sx,
+                gather_cluster<R, NVC4, kHandoff>(a, next_q, nmeta, nw, sx + bank_of(np),
                                         StepInfo{a.base + static_cast<uint32_t>(np), a.base,
                                                  static_cast<uint32_t>(8 * (2 * (nk > 0 ? 1 : 0) + cs)), false, false},
                                         stamp);
@@ -889,7 +905,7 @@ __host__ __device__ inline size_t dict_area_bytes(int n_shapes)
     return static_cast<size_t>(3 * n_shapes) * sizeof(Real4<R>);
 }
 
-template <typename R, int NVC4, bool kTrace, int kMaxThreads, bool kDict>
+template <typename R, int NVC4, bool kTrace, int kMaxThreads, bool kDict, bool kHandoff = false>
 __global__ void __launch_bounds__(kMaxThreads) k_substep_persistent(PersistentArgs<R> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -899,7 +915,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_substep_persistent(PersistentAr
     // regions that share vertices come first in region_order (at most one per CTA: they must be
     // co-resident), the others follow and are handed out round-robin
     for (int32_t i = blockIdx.x; i < a.n_run; i += gridDim.x)
-        run_region<R, NVC4, kTrace, kDict>(a, a.region_order[i], sx, s_chunks, s_dict);
+        run_region<R, NVC4, kTrace, kDict, kHandoff>(a, a.region_order[i], sx, s_chunks, s_dict);
 }
 
 template <typename T>
@@ -931,7 +947,7 @@ struct PersistentPlan
     PBuf<int32_t> region_order, vtx_off, ifv_off, surf_off;
     PBuf<DevChunk> chunks;
     PBuf<uint32_t> vtx, ifv, ifv_meta, ifv_first, surf_index, surf_addr, error;
-    PBuf<uint2> tet_slots;
+    PBuf<uint2> tet_slots, tet_slots_odd;
     PBuf<uint4> cl_meta, cl_to, cl_to_owner, box;
     PBuf<Real4<R>> cl_w;
     std::vector<uint4> h_fetch; // host copy of cl_fetch, to patch cl_w when a mass changes
@@ -970,8 +986,19 @@ struct PersistentPlan
 
     // the fewer threads a CTA has, the more registers each may use (255 / 168)
     template <int NVC4, bool kTrace>
-    static void const* pick(int threads, bool dict)
+    static void const* pick(int threads, bool dict, bool handoff = false)
     {
+        if constexpr (sizeof(R) == 4 && !kTrace)
+            if (handoff) // experimental kernels (hand-off inside a region): fp32 only
+            {
+                if (dict)
+                    return threads <= 256
+                               ? reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, false, 256, true, true>)
+                               : reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, false, 384, true, true>);
+                return threads <= 256
+                           ? reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, false, 256, false, true>)
+                           : reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, false, 384, false, true>);
+            }
         if (dict)
             return threads <= 256 ? reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 256, true>)
                                   : reinterpret_cast<void const*>(k_substep_persistent<R, NVC4, kTrace, 384, true>);
@@ -996,6 +1023,11 @@ struct PersistentPlan
         }
         int32_t const per_rank = Rn / world;
         int64_t const T = h.n_tets(), V = h.n_vertices();
+        if (cp.banks > 1 && sizeof(R) != 4)
+        {
+            why_not = "the hand-off kernels exist in the fp32 build only";
+            return false;
+        }
         if (!cp.why_not.empty())
         {
             why_not = cp.why_not;
@@ -1012,17 +1044,26 @@ struct PersistentPlan
             return false;
         }
         int const nvc = cp.nvc <= 8 ? 8 : 16; // instantiations: 8 or 16 scratch entries per thread
-        int64_t const scratch = static_cast<int64_t>(cp.nvc) * cp.nt;
-        std::vector<uint2> slots(static_cast<size_t>(T));
+        int64_t const scratch = static_cast<int64_t>(cp.banks) * cp.nvc * cp.nt; // where the plan's resident slots start
+        std::vector<uint2> slots(static_cast<size_t>(T)), slots_odd(cp.banks > 1 ? static_cast<size_t>(T) : 0);
         for (int64_t p = 0; p < T; ++p)
         {
-            uint32_t q[4];
+            uint32_t q[4], o[4];
             for (int k = 0; k < 4; ++k)
-            { // the plan laid the slots out for cp.nvc scratch entries; the kernel has `nvc`
+            { // the plan laid the slots out for cp.nvc scratch entries per bank; the kernel has `nvc`.  Scratch
+              // slots name bank 0; with two banks the odd phases use the copy that names bank 1
                 uint32_t const sl = cp.tet_slots[4 * static_cast<size_t>(p) + k];
-                q[k]              = sl >= scratch ? sl + static_cast<uint32_t>((nvc - cp.nvc) * cp.nt) : sl;
+                q[k]              = sl >= scratch ? sl + static_cast<uint32_t>(cp.banks * (nvc - cp.nvc) * cp.nt) : sl;
+                o[k]              = sl >= scratch ? q[k] : sl + static_cast<uint32_t>(nvc * cp.nt);
+                if (q[k] > 0xffffu || (cp.banks > 1 && o[k] > 0xffffu))
+                {
+                    why_not = "shared-memory slot does not fit 16 bits";
+                    return false;
+                }
             }
             slots[static_cast<size_t>(p)] = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
+            if (cp.banks > 1)
+                slots_odd[static_cast<size_t>(p)] = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
         }
         int64_t const Q = cp.n_clusters;
         std::vector<uint4> fetch(static_cast<size_t>(nvc / 4) * static_cast<size_t>(Q),
@@ -1064,6 +1105,15 @@ struct PersistentPlan
             why_not = routes.why_not;
             return false;
         }
+        if (cp.banks > 1) // entries that arrive by hand-off are not polled
+            for (int k4 = 0; k4 < cp.nvc / 4; ++k4)
+                for (int64_t q = 0; q < Q; ++q)
+                {
+                    uint32_t* m = &meta[static_cast<size_t>(k4) * Q + q].x;
+                    for (int e = 0; e < 4; ++e)
+                        if (routes.local_prev[static_cast<size_t>(4 * k4 + e) * Q + q])
+                            m[e] = kMetaLocal;
+                }
         std::vector<int32_t> const& ioff  = routes.ifv_offsets;
         std::vector<uint32_t> const& ifv  = routes.ifv;
         std::vector<uint32_t> const& ifm  = routes.ifv_meta;
@@ -1101,7 +1151,7 @@ struct PersistentPlan
                 int32_t const pos = cur[static_cast<size_t>(r)]++;
                 sidx[static_cast<size_t>(pos)]  = static_cast<uint32_t>(i);
                 sadr[static_cast<size_t>(pos)]  = plan.vertex_region[gv] == r
-                                                      ? static_cast<uint32_t>(nvc * cp.nt) + plan.vertex_slot[gv]
+                                                      ? static_cast<uint32_t>(cp.banks * nvc * cp.nt) + plan.vertex_slot[gv]
                                                       : (ifv_pos[gv] | kGlobalBit);
             }
         }
@@ -1115,7 +1165,7 @@ struct PersistentPlan
         // launch shape
         bool const dict = d_shapes != nullptr && n_shapes > 0 && n_shapes <= kMaxShapes;
         smem  = chunk_area_bytes(cp.n_colours) + (dict ? dict_area_bytes<R>(n_shapes) : 0) +
-               static_cast<size_t>(static_cast<int64_t>(nvc) * cp.nt + std::max<int64_t>(plan.max_region_vertices, 1)) *
+               static_cast<size_t>(static_cast<int64_t>(cp.banks) * nvc * cp.nt + std::max<int64_t>(plan.max_region_vertices, 1)) *
                    sizeof(Real4<R>);
         block = cp.nt;
         if (static_cast<int64_t>(smem) > kSmemBudget)
@@ -1137,7 +1187,7 @@ struct PersistentPlan
             trace_len        = static_cast<int64_t>(Rn) * trace_n * 16;
         }
         else
-            kernel = nvc == 8 ? pick<2, false>(block, dict) : pick<4, false>(block, dict);
+            kernel = nvc == 8 ? pick<2, false>(block, dict, cp.banks > 1) : pick<4, false>(block, dict, cp.banks > 1);
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
             cudaSuccess)
         {
@@ -1164,6 +1214,8 @@ struct PersistentPlan
         order.insert(order.end(), island_r.begin(), island_r.end());
         region_order.upload(order, st);
         tet_slots.upload(slots, st);
+        if (cp.banks > 1)
+            tet_slots_odd.upload(slots_odd, st);
         cl_to.upload(h_to, st);
         cl_to_owner.upload(h_to_owner, st);
         ifv_first.upload(ifirst, st);
@@ -1196,9 +1248,12 @@ struct PersistentPlan
 
         args.nvc              = nvc;
         args.rot              = cp.rot;
+        args.banks            = cp.banks;
+        n_local_entries       = routes.n_local;
         args.n_clusters       = Q;
         args.region_order     = region_order.p;
         args.tet_slots        = tet_slots.p;
+        args.tet_slots_odd    = cp.banks > 1 ? tet_slots_odd.p : tet_slots.p;
         args.tet_shape        = dict ? d_tet_shape : nullptr;
         args.shapes           = dict ? d_shapes : nullptr;
         args.n_shapes         = dict ? n_shapes : 0;
@@ -1255,6 +1310,7 @@ struct PersistentPlan
         return true;
     }
     size_t box_bytes = 0;
+    int64_t n_local_entries = 0; // fetch-list entries that arrive by hand-off inside their region
 
     // particle_t::mass() of a vertex changed: patch its inverse mass in every fetch list naming it
     void set_inverse_mass(uint32_t gv, R w, cudaStream_t st)

@@ -208,3 +208,100 @@ extern "C" int hs_mailbox_routes(int64_t nV, int64_t nT, const uint32_t* tets, c
     dims[3] = routes.n_entries;
     return 0;
 }
+
+// EXPERIMENTAL hand-off inside a region (ResidentParams::handoff, optionally with slab-shaped regions): plan a
+// single lattice body, build the routes and check every local routing word: it must name the scratch slot
+// (entry * nt + thread) of the cluster of the SAME region and the NEXT colour that fetches the same vertex, and
+// exactly those entries must be marked "arrives by hand-off".  Returns the number of local hand-offs, or a
+// negative error code; n_remote = touches that still go through a mailbox; steps_without_remote = colour steps
+// (colour, region) none of whose clusters polls a mailbox filled by another region... counted as colours for
+// which NO entry of ANY region has a remote previous touch inside the sweep.
+extern "C" int64_t hs_handoff_check(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_regions,
+                                    int world, int slabs, int64_t* n_remote, int32_t* n_colours, int32_t* n_regions_out,
+                                    int32_t* colours_without_remote)
+{
+    HostScene h;
+    h.x0.assign(x0, x0 + 3 * nV);
+    h.mass.assign(static_cast<size_t>(nV), 1.0);
+    h.tets.assign(tets, tets + 4 * nT);
+    for (int64_t t = 0; t < nT; ++t)
+    {
+        h.tet_insertion.push_back(h.n_constraints++);
+        h.tet_material.push_back(0);
+    }
+    HostBody b;
+    b.n_vertices = nV;
+    b.n_tets     = nT;
+    extract_boundary(nV, nT, tets, b.surf_to_tet, &b.surf_triangles);
+    h.bodies.push_back(b);
+    ResidentParams rp;
+    rp.smem_bytes = 200 * 1024;
+    rp.handoff    = true;
+    rp.slabs      = slabs != 0;
+    ClusterPlan plan;
+    RegionPlan regions;
+    build_cluster_plan(h, n_regions, false, plan, &rp, &regions);
+    if (!plan.why_not.empty() || plan.banks != 2)
+        return -1;
+    if (!cluster_plan_is_valid(h, plan) || !resident_layout_is_valid(h, plan, regions))
+        return -2;
+    MailboxRoutes routes;
+    if (!build_mailbox_routes(h, plan, regions, plan.nvc, world, routes))
+        return -3;
+    *n_colours     = plan.n_colours;
+    *n_regions_out = plan.n_regions;
+    int32_t const Rn = plan.n_regions;
+    int64_t const Q = plan.n_clusters;
+    std::vector<int32_t> colour(static_cast<size_t>(Q)), region(static_cast<size_t>(Q)), item(static_cast<size_t>(Q));
+    for (size_t ch = 0; ch < plan.chunks.size(); ++ch)
+        for (int32_t i = 0; i < plan.chunks[ch].n[0]; ++i)
+        {
+            size_t const q = static_cast<size_t>(plan.chunks[ch].cfirst + i);
+            colour[q]      = static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
+            region[q]      = static_cast<int32_t>((ch / 2) % static_cast<size_t>(Rn));
+            item[q]        = i;
+        }
+    // consumer lookup: (region, colour, entry, vertex) -> cluster
+    int64_t local = 0, marked = 0, remote = 0;
+    std::vector<char> colour_has_remote(static_cast<size_t>(plan.n_colours), 0);
+    for (uint32_t box = 0; box < routes.n_entries; ++box)
+    {
+        marked += routes.local_prev[box];
+        uint32_t const v = plan.cl_fetch[box];
+        if (v == 0xffffffffu)
+            continue;
+        size_t const q = box % static_cast<size_t>(Q);
+        if (!routes.local_prev[box] && colour[q] > 0)
+            colour_has_remote[static_cast<size_t>(colour[q])] = 1; // polls a mailbox in the middle of a sweep
+        uint32_t const word = routes.to[box];
+        if (!(word & kRouteLocalBit))
+        {
+            ++remote;
+            continue;
+        }
+        if ((routes.to_owner[box] & ~kRouteSurfaceBit) != word)
+            return -5;
+        ++local;
+        uint32_t const idx = word & kRouteLocalIndexMask, thread = idx % plan.nt, entry = idx / plan.nt;
+        if (entry >= static_cast<uint32_t>(plan.nvc))
+            return -10;
+        // the consumer runs on `thread` in the next colour step of the same region: its position in the step
+        int32_t const want_item = static_cast<int32_t>((thread + plan.nt - plan.rot) % plan.nt);
+        size_t const chA = (static_cast<size_t>(colour[q] + 1) * Rn + region[q]) * 2; // part A chunk of that step
+        if (colour[q] + 1 >= plan.n_colours || want_item >= plan.chunks[chA].n[0])
+            return -6;
+        size_t const q2 = static_cast<size_t>(plan.chunks[chA].cfirst + want_item);
+        if (plan.cl_fetch[static_cast<size_t>(entry) * Q + q2] != v)
+            return -8;
+        if (!routes.local_prev[static_cast<size_t>(entry) * Q + q2])
+            return -7;
+    }
+    if (marked != local)
+        return -9;
+    *n_remote = remote;
+    int32_t free_colours = 0;
+    for (int32_t c = 1; c < plan.n_colours; ++c)
+        free_colours += !colour_has_remote[static_cast<size_t>(c)];
+    *colours_without_remote = free_colours;
+    return local;
+}

@@ -39,6 +39,8 @@ def hostscene():
                                   i64p]
     L.hs_mailbox_routes.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int64, C.c_int64, u32p, u32p,
                                     u32p, i32p, i32p, u32p, u32p, i32p, i64p]
+    L.hs_handoff_check.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int, i64p, i32p, i32p, i32p]
+    L.hs_handoff_check.restype = C.c_int64
     return L
 
 
@@ -185,6 +187,33 @@ def test_clusters_that_exchange_vertices_start_on_the_least_loaded_sub_partition
         per_smsp = [len(range(s, warps, 4)) for s in range(4)]
         first_warp = rot // 32
         assert per_smsp[first_warp % 4] == min(p for p in per_smsp if p > 0) or warps < 4
+
+
+@pytest.mark.parametrize("dims,regions,world,slabs", [((9, 9, 25), 4, 1, 0), ((9, 9, 25), 8, 2, 0),
+                                                      ((21, 21, 51), 39, 1, 0), ((9, 9, 25), 148, 1, 1),
+                                                      ((21, 21, 51), 148, 1, 1)])
+def test_experimental_hand_off_inside_a_region(hostscene, oracle, dims, regions, world, slabs):
+    """EXPERIMENTAL (off by default).  Shared vertices go from one cluster to the next
+    through shared memory when both belong to the same region and run in consecutive steps: every such
+    routing word names the scratch slot of the consumer and exactly the consumers' entries are marked "not
+    polled" (checked inside hs_handoff_check).  With the colours ordered for it about half of the touches of
+    shared vertices are hand-offs; with slab-shaped regions (one layer of cells each) six of the eight touches
+    of an interior vertex are (vertices on the mesh boundary are touched by fewer colours: a touch whose
+    predecessor is not in the very previous step still goes through its mailbox)."""
+    pos, tets = oracle.bar_model(*dims)
+    tets = np.ascontiguousarray(tets, np.uint32)
+    x0 = pos.astype(np.float64)
+    remote, ncol, nreg, free = C.c_int64(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    local = hostscene.hs_handoff_check(len(pos), len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), regions,
+                                       world, slabs, C.byref(remote), C.byref(ncol), C.byref(nreg), C.byref(free))
+    assert local > 0, "hand-off check failed with code %d" % local
+    assert ncol.value == 8 and remote.value > 0      # region changes still go through the mailboxes
+    print("regions %d: hand-offs %d, mailbox pushes %d, colours 1..7 without a remote dependency: %d"
+          % (nreg.value, local, remote.value, free.value))
+    assert local > 0.45 * (local + remote.value)
+    if slabs:
+        assert nreg.value == dims[2] - 1             # one region per layer of cells along the longest axis
+        assert local > 0.6 * (local + remote.value)  # interior vertices: 6 of 8 touches per sweep are hand-offs
 
 
 def test_colouring_reports_capacity_overflow(hostscene):
