@@ -51,7 +51,12 @@ extern "C" {
 /* schedule selection (sbsb200_set_schedule) */
 #define SBSB200_SCHED_AUTO 0
 #define SBSB200_SCHED_GRAPH 1      /* one kernel per colour, whole frame in a CUDA graph */
-#define SBSB200_SCHED_PERSISTENT 2 /* one cooperative kernel per substep, region-resident state */
+#define SBSB200_SCHED_PERSISTENT 2 /* resident schedule: one kernel per substep, every region's vertices in shared memory */
+
+/* region shape of the resident schedule (sbsb200_set_region_shape) */
+#define SBSB200_REGIONS_PENCILS 0 /* bundles of cell columns along the shortest axis (default): half of the colour
+                                   * steps of a sweep on a lattice then exchange nothing between regions */
+#define SBSB200_REGIONS_COMPACT 1 /* compact blocks in Morton order */
 
 typedef struct sbsb200_ctx sbsb200_ctx;
 
@@ -74,6 +79,13 @@ typedef struct sbsb200_stats
     double last_step_ms;        /* device time of the most recent sbsb200_step (CUDA events) */
     double kernel_ms;           /* persistent schedule: summed device time of the substep-kernel launches */
     int64_t kernel_launches;    /* ... and how many launches that sum covers (CUDA events around each) */
+    int64_t n_shared_vertices;  /* resident schedule: vertices touched by more than one region */
+    int64_t pulls_per_sweep;    /* ... mailbox pulls (= pushes) of one Gauss-Seidel sweep over all regions */
+    int64_t pushes_per_sweep;
+    int32_t quiet_colours;      /* ... colour steps of a sweep that (practically) wait for no other region */
+    int32_t reserved_;
+    int64_t green_general_calls; /* debug counter: projections that took the clamp / inversion route
+                                  * (green_constraint.cpp:61-65, :91-102) on this device since finalize */
 } sbsb200_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -87,6 +99,9 @@ const char* sbsb200_last_error(const sbsb200_ctx* ctx);
  * stream owned by the context.  Must be called before finalize. */
 int sbsb200_set_stream(sbsb200_ctx* ctx, void* cuda_stream);
 int sbsb200_set_schedule(sbsb200_ctx* ctx, int schedule);
+/* How the resident schedule cuts a connected mesh into regions (a tuning knob; any shape gives a valid
+ * Gauss-Seidel order, exported by sbsb200_get_constraint_order).  Before finalize.  No reference counterpart. */
+int sbsb200_set_region_shape(sbsb200_ctx* ctx, int shape);
 
 /* point_bvh_model_t (include/sbs/physics/collision/bvh_model.h:23-49): the broadphase.  Before finalize. */
 int sbsb200_set_broadphase(sbsb200_ctx* ctx, int mode);
@@ -229,6 +244,9 @@ int sbsb200_download(sbsb200_ctx* ctx, int body, double* x, double* v);
 int sbsb200_download_surface(sbsb200_ctx* ctx, int body, float* xyz_normal);
 /* particle_t::mass() = m (main.cpp:158-165 toggles 1 <-> 0 between frames). */
 int sbsb200_set_mass(sbsb200_ctx* ctx, int body, int64_t vertex, double mass);
+/* The same for n vertices of a body in one call (one copy, one synchronisation): what a host-side mirror of
+ * simulation_t::particles() pushes after the caller edited masses (body-local vertex indices). */
+int sbsb200_set_masses(sbsb200_ctx* ctx, int body, int64_t n, const uint32_t* vertices, const double* masses);
 
 /* ---- the hot path ---------------------------------------------------------------------- */
 
@@ -243,6 +261,11 @@ int sbsb200_step_host(sbsb200_ctx* ctx, int body, const double* x_in, const doub
                       double dt, int substeps, int iterations, int detect_mode, double* x_out,
                       double* v_out);
 
+/* The same with float host buffers: half the bytes over PCIe when the caller keeps its particles in single
+ * precision (a renderer-side mirror); the device state has the context's precision either way. */
+int sbsb200_step_host_f32(sbsb200_ctx* ctx, int body, const float* x_in, const float* v_in, double dt,
+                          int substeps, int iterations, int detect_mode, float* x_out, float* v_out);
+
 int sbsb200_synchronize(sbsb200_ctx* ctx);
 
 /* Contacts of the most recent detection, as the arguments handed to
@@ -252,9 +275,11 @@ int sbsb200_synchronize(sbsb200_ctx* ctx);
 int64_t sbsb200_get_contacts(sbsb200_ctx* ctx, int64_t cap, int32_t* body, uint32_t* vertex,
                              int32_t* sdf_body, double* point, double* normal);
 
-/* Development aid (persistent schedule, environment SBSB200_TRACE_STEPS=N at finalize): %clock64
- * stamps of the first N colour steps of the latest launch, 16 per (region, step).  Returns the
- * number of values available; copies min(cap, that) of them.  Not part of the reference API. */
+/* Development aid (resident schedule): sbsb200_debug_trace_steps(ctx, N) before finalize selects a kernel
+ * build that records %clock64 stamps of the first N colour steps of every launch, 16 per (region, step);
+ * sbsb200_debug_read_trace returns the number of values available and copies min(cap, that) of them.
+ * Not part of the reference API; N = 0 (default) runs the production kernels. */
+int sbsb200_debug_trace_steps(sbsb200_ctx* ctx, int steps);
 int64_t sbsb200_debug_read_trace(sbsb200_ctx* ctx, int64_t* out, int64_t cap);
 
 #ifdef __cplusplus

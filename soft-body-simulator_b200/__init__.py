@@ -16,6 +16,7 @@ FP32, FP64 = 32, 64
 DETECT_PER_FRAME, DETECT_PER_SUBSTEP = 0, 1
 SCHED_AUTO, SCHED_GRAPH, SCHED_PERSISTENT = 0, 1, 2
 BROADPHASE_NONE, BROADPHASE_BVH = 0, 1
+REGIONS_PENCILS, REGIONS_COMPACT = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _u32p = C.POINTER(C.c_uint32)
@@ -33,6 +34,7 @@ EXPORTS = [
     "sbsb200_synchronize", "sbsb200_get_contacts", "sbsb200_debug_read_trace",
     "sbsb200_set_partition", "sbsb200_get_mailbox_handle", "sbsb200_connect_peers", "sbsb200_connect_peer_context",
     "sbsb200_get_vertex_ranks", "sbsb200_set_broadphase", "sbsb200_get_surface_triangles", "sbsb200_download_surface",
+    "sbsb200_set_region_shape", "sbsb200_set_masses", "sbsb200_step_host_f32", "sbsb200_debug_trace_steps",
 ]
 
 
@@ -42,7 +44,9 @@ class Stats(C.Structure):
                 ("n_distance_colours", C.c_int32), ("schedule", C.c_int32), ("n_regions", C.c_int32),
                 ("n_interface_vertices", C.c_int64), ("kernels_launched", C.c_int64), ("frames", C.c_int64),
                 ("last_contact_count", C.c_int64), ("last_step_ms", C.c_double), ("kernel_ms", C.c_double),
-                ("kernel_launches", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("n_shared_vertices", C.c_int64), ("pulls_per_sweep", C.c_int64),
+                ("pushes_per_sweep", C.c_int64), ("quiet_colours", C.c_int32), ("reserved_", C.c_int32),
+                ("green_general_calls", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -116,6 +120,11 @@ def load_library():
     L.sbsb200_connect_peers.argtypes = [vp, C.c_char_p, C.c_int]
     L.sbsb200_connect_peer_context.argtypes = [vp, C.c_int, vp]
     L.sbsb200_get_vertex_ranks.argtypes = [vp, C.c_int, _i32p, C.c_int64]
+    L.sbsb200_set_region_shape.argtypes = [vp, C.c_int]
+    L.sbsb200_set_masses.argtypes = [vp, C.c_int, C.c_int64, _u32p, _dp]
+    _fp = C.POINTER(C.c_float)
+    L.sbsb200_step_host_f32.argtypes = [vp, C.c_int, _fp, _fp, C.c_double, C.c_int, C.c_int, C.c_int, _fp, _fp]
+    L.sbsb200_debug_trace_steps.argtypes = [vp, C.c_int]
     L.sbsb200_debug_read_trace.argtypes = [vp, C.POINTER(C.c_int64), C.c_int64]
     L.sbsb200_debug_read_trace.restype = C.c_int64
     _lib = L
@@ -163,7 +172,7 @@ def _d(a):
 class Simulation:
     """One sbsb200 context == the reference's simulation_t + timestep_t on one GPU."""
 
-    def __init__(self, device=0, precision=FP32, stream=None, schedule=SCHED_AUTO):
+    def __init__(self, device=0, precision=FP32, stream=None, schedule=SCHED_AUTO, region_shape=None, trace_steps=0):
         self._L = load_library()
         h = C.c_void_p()
         rc = self._L.sbsb200_create(device, precision, C.byref(h))
@@ -175,6 +184,10 @@ class Simulation:
             self._ck(self._L.sbsb200_set_stream(self._h, C.c_void_p(stream)))
         if schedule != SCHED_AUTO:
             self._ck(self._L.sbsb200_set_schedule(self._h, schedule))
+        if region_shape is not None:
+            self._ck(self._L.sbsb200_set_region_shape(self._h, region_shape))
+        if trace_steps:
+            self._ck(self._L.sbsb200_debug_trace_steps(self._h, trace_steps))
 
     def _ck(self, rc):
         if rc < 0:
@@ -326,6 +339,25 @@ class Simulation:
     def set_mass(self, body, vertex, mass):
         self._ck(self._L.sbsb200_set_mass(self._h, body, vertex, mass))
 
+    def set_masses(self, body, vertices, masses):
+        ids = np.ascontiguousarray(vertices, np.uint32).reshape(-1)
+        m = _f64(masses).reshape(-1)
+        assert ids.shape == m.shape
+        self._ck(self._L.sbsb200_set_masses(self._h, body, ids.shape[0], ids.ctypes.data_as(_u32p), _d(m)))
+
+    def step_host_f32(self, body, x_in, v_in, dt, substeps, iterations, detect_every_substep, x_out, v_out):
+        """The same as step_host with float32 host arrays [nV, 3] (v_in / x_out / v_out may be None)."""
+        fp = C.POINTER(C.c_float)
+        f = lambda a: None if a is None else a.ctypes.data_as(fp)
+        for a in (x_in, v_in, x_out, v_out):
+            assert a is None or (a.dtype == np.float32 and a.flags["C_CONTIGUOUS"])
+        self._ck(self._L.sbsb200_step_host_f32(self._h, body, f(x_in), f(v_in), dt, substeps, iterations,
+                                               DETECT_PER_SUBSTEP if detect_every_substep else DETECT_PER_FRAME,
+                                               f(x_out), f(v_out)))
+
+    def contact_count(self):
+        return self._ck(self._L.sbsb200_get_contacts(self._h, 0, None, None, None, None, None))
+
     def step(self, dt, substeps, iterations, detect_every_substep=False):
         self._ck(self._L.sbsb200_step(self._h, dt, substeps, iterations,
                                       DETECT_PER_SUBSTEP if detect_every_substep else DETECT_PER_FRAME))
@@ -335,7 +367,7 @@ class Simulation:
         self._ck(self._L.sbsb200_step_host(self._h, body, _d(x_in), None if v_in is None else _d(v_in), dt,
                                            substeps, iterations,
                                            DETECT_PER_SUBSTEP if detect_every_substep else DETECT_PER_FRAME,
-                                           _d(x_out), _d(v_out)))
+                                           None if x_out is None else _d(x_out), None if v_out is None else _d(v_out)))
 
     # ---- one scene decomposed over several GPUs ----------------------------------------------
     def set_partition(self, rank, world):

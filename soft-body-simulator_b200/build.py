@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "lib", "libsbsb200.so")
 SOURCES = ["csrc/sbs_b200.cu", "csrc/scene_build.cpp"]
-HEADERS = ["csrc/scene_build.h", "csrc/xpbd_math.cuh", "csrc/xpbd_kernels.cuh", "csrc/xpbd_persistent.cuh", "csrc/bvh.cuh", "csrc/grid_sdf.cuh",
+HEADERS = ["csrc/scene_build.h", "csrc/xpbd_math.cuh", "csrc/xpbd_kernels.cuh", "csrc/xpbd_resident.cuh", "csrc/bvh.cuh", "csrc/grid_sdf.cuh",
            "../include/sbs_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall", "-shared"]

@@ -7,7 +7,7 @@
 #include "scene_build.h"
 #include "xpbd_kernels.cuh"
 #include "bvh.cuh"
-#include "xpbd_persistent.cuh"
+#include "xpbd_resident.cuh"
 
 #include <algorithm>
 #include <array>
@@ -79,7 +79,10 @@ struct EngineBase
     virtual void download(sbsb200_ctx& c, int body, double* x, double* v)                  = 0;
     virtual void set_vertices(sbsb200_ctx& c, int body, int64_t n, uint32_t const* which, double const* x,
                               double const* v)                                             = 0;
-    virtual void set_mass(sbsb200_ctx& c, int64_t gv, double m)                             = 0;
+    virtual void set_masses(sbsb200_ctx& c, int64_t first, int64_t n, uint32_t const* which, double const* m) = 0;
+    virtual uint64_t general_route_calls()                                                  = 0;
+    virtual void step_host_f32(sbsb200_ctx& c, int body, float const* x, float const* v, double dt, int substeps,
+                               int iterations, int detect, float* x_out, float* v_out)      = 0;
     virtual int64_t contacts(sbsb200_ctx& c, int64_t cap, int32_t* body, uint32_t* vertex,
                              int32_t* sdf_body, double* point, double* normal)             = 0;
     virtual void invalidate_graphs()                                                       = 0;
@@ -110,6 +113,10 @@ struct sbsb200_ctx
     ClusterPlan green_plan;
     ColourClass dist_cc;
     RegionPlan plan;
+    ExchangePlan xplan;          // resident schedule: who pulls and pushes which shared vertex when (host side)
+    int region_shape  = SBSB200_REGIONS_PENCILS;
+    int trace_steps   = 0;       // development aid (sbsb200_debug_trace_steps)
+    uint64_t general_calls0 = 0; // device counter of green_general calls when the scene was finalized
     std::vector<uint32_t> order; // exported serial order (insertion indices)
     std::vector<int32_t> vertex_body;
     std::unique_ptr<EngineBase> engine;
@@ -166,7 +173,7 @@ struct Engine final : EngineBase
     static constexpr int kBvhTopologyFrames = 8;
     int bvh_topology_valid_frames = 0; // 0: sort at the next detection
     int bvh_sort_end_bit          = 64; // key bits in use: 32 Morton bits + the bits of the body index
-    PersistentPlan<R> pp; // persistent schedule resources (may be inactive)
+    ResidentPlan<R> pp; // resident schedule resources (may be inactive)
     // CUDA-event pairs around the launches of the dominant kernel (persistent schedule: the substep
     // kernel), folded into a running sum when the statistics are read
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
@@ -517,7 +524,7 @@ struct Engine final : EngineBase
             bool ok = false;
             try
             {
-                ok = pp.build(c.scene, c.green_plan, c.plan, d, st, c.sm_count, c.rank, c.world);
+                ok = pp.build(c.scene, c.green_plan, c.plan, c.xplan, d, st, c.sm_count, c.rank, c.world, c.trace_steps);
             }
             catch (std::exception const& e)
             {
@@ -747,7 +754,7 @@ struct Engine final : EngineBase
         CK(cudaMemcpyAsync(stage_x.p, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
         if (v)
             CK(cudaMemcpyAsync(stage_v.p, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
-        k_unpack_state<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(
+        k_unpack_state<R, double><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(
             d, hb.v_offset, n, stage_x.p, v ? stage_v.p : nullptr);
         ++c.kernels;
         if (d.n_surface > 0)
@@ -790,7 +797,7 @@ struct Engine final : EngineBase
         if (n == 0 || (!x && !v))
             return;
         ensure_staging(n);
-        k_pack_state<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(
+        k_pack_state<R, double><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(
             d, hb.v_offset, n, x ? stage_x.p : nullptr, v ? stage_v.p : nullptr);
         ++c.kernels;
         CK(cudaGetLastError());
@@ -863,13 +870,72 @@ struct Engine final : EngineBase
         return pp.trace_len;
     }
 
-    void set_mass(sbsb200_ctx& c, int64_t gv, double m) override
+    // particle_t::mass() of n vertices (first + which[i]): one staging copy, one kernel, one synchronisation.
+    // The inverse mass rides in pos[].w; the resident kernel reads it at the start of every substep.
+    void set_masses(sbsb200_ctx& c, int64_t first, int64_t n, uint32_t const* which, double const* m) override
     {
-        R const iw = R(m > 0. ? 1. / m : 0.);
-        CK(cudaMemcpyAsync(&pos.p[gv].w, &iw, sizeof(R), cudaMemcpyHostToDevice, c.stream));
+        if (n <= 0)
+            return;
+        std::vector<R> iw(static_cast<size_t>(n));
+        for (int64_t i = 0; i < n; ++i)
+            iw[static_cast<size_t>(i)] = R(m[i] > 0. ? 1. / m[i] : 0.); // particle.cpp:39-44
+        DevBuf<uint32_t> ids;
+        DevBuf<R> w;
+        ids.alloc(static_cast<size_t>(n));
+        w.alloc(static_cast<size_t>(n));
+        CK(cudaMemcpyAsync(ids.p, which, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c.stream));
+        CK(cudaMemcpyAsync(w.p, iw.data(), sizeof(R) * n, cudaMemcpyHostToDevice, c.stream));
+        k_scatter_inverse_mass<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(d, first, n, ids.p, w.p);
+        ++c.kernels;
+        CK(cudaGetLastError());
         CK(cudaStreamSynchronize(c.stream));
-        if (c.schedule == SBSB200_SCHED_PERSISTENT)
-            pp.set_inverse_mass(static_cast<uint32_t>(gv), iw, c.stream);
+    }
+
+    uint64_t general_route_calls() override
+    {
+        unsigned long long n = 0;
+        CK(cudaMemcpyFromSymbol(&n, g_general_route_calls, sizeof n));
+        return n;
+    }
+
+    // sbsb200_step_host_f32: the state crosses PCIe as floats (half the bytes of the double interface)
+    void step_host_f32(sbsb200_ctx& c, int body, float const* x, float const* v, double dt, int substeps, int iterations,
+                       int detect, float* x_out, float* v_out) override
+    {
+        HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
+        int64_t const n    = hb.n_vertices;
+        ensure_staging(n);
+        float* sxf = reinterpret_cast<float*>(stage_x.p);
+        float* svf = reinterpret_cast<float*>(stage_v.p);
+        if (n > 0)
+        {
+            CK(cudaMemcpyAsync(sxf, x, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+            if (v)
+                CK(cudaMemcpyAsync(svf, v, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+            k_unpack_state<R, float><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(d, hb.v_offset, n, sxf,
+                                                                                                 v ? svf : nullptr);
+            ++c.kernels;
+            if (d.n_surface > 0)
+            {
+                k_surface_gather<R><<<static_cast<unsigned>((d.n_surface + 255) / 256), 256, 0, c.stream>>>(d);
+                ++c.kernels;
+            }
+        }
+        step(c, dt, substeps, iterations, detect);
+        ++c.frames;
+        if (n > 0 && (x_out || v_out))
+        {
+            k_pack_state<R, float><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(
+                d, hb.v_offset, n, x_out ? sxf : nullptr, v_out ? svf : nullptr);
+            ++c.kernels;
+            CK(cudaGetLastError());
+            if (x_out)
+                CK(cudaMemcpyAsync(x_out, sxf, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c.stream));
+            if (v_out)
+                CK(cudaMemcpyAsync(v_out, svf, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c.stream));
+        }
+        CK(cudaStreamSynchronize(c.stream));
+        check_persistent(c);
     }
 
     int64_t contacts(sbsb200_ctx& c, int64_t cap, int32_t* body, uint32_t* vertex, int32_t* sdf_body,
@@ -1068,6 +1134,26 @@ int sbsb200_set_broadphase(sbsb200_ctx* c, int mode)
     if (c->finalized)
         return fail(c, SBSB200_ERR_STATE, "set_broadphase must precede finalize");
     c->broadphase = mode;
+    return SBSB200_OK;
+}
+
+int sbsb200_set_region_shape(sbsb200_ctx* c, int shape)
+{
+    if (!c || (shape != SBSB200_REGIONS_PENCILS && shape != SBSB200_REGIONS_COMPACT))
+        return fail(c, SBSB200_ERR_INVALID, "bad region shape");
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "scene already finalized");
+    c->region_shape = shape;
+    return SBSB200_OK;
+}
+
+int sbsb200_debug_trace_steps(sbsb200_ctx* c, int steps)
+{
+    if (!c || steps < 0)
+        return fail(c, SBSB200_ERR_INVALID, "bad argument");
+    if (c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "scene already finalized");
+    c->trace_steps = steps;
     return SBSB200_OK;
 }
 
@@ -1422,10 +1508,10 @@ int sbsb200_finalize(sbsb200_ctx* c)
         // damping; distance constraints and beta != 0 (which needs xn in the projection) take
         // the per-colour kernels
         bool const persistent_ok = T > 0 && D == 0 && !c->any_damping;
-        // AUTO: the persistent region-resident kernel for connected meshes, the per-colour kernels in a
-        // CUDA graph for ensembles of small bodies — measured on B200, profiles/r01_summary.md
+        // AUTO: the resident kernel whenever it applies (connected meshes cut into one region per SM, ensembles
+        // with a few whole bodies per region); the per-colour kernels in a CUDA graph otherwise
         bool const auto_persistent =
-            persistent_ok && T <= 16000000 && !PersistentPlan<float>::wants_region_per_body(h, c->sm_count);
+            persistent_ok;
         c->schedule = c->schedule_request == SBSB200_SCHED_PERSISTENT                     ? SBSB200_SCHED_PERSISTENT
                       : c->schedule_request == SBSB200_SCHED_AUTO && auto_persistent ? SBSB200_SCHED_PERSISTENT
                                                                                      : SBSB200_SCHED_GRAPH;
@@ -1443,20 +1529,44 @@ int sbsb200_finalize(sbsb200_ctx* c)
         }
 
         if (c->schedule == SBSB200_SCHED_PERSISTENT)
-        {
-            ResidentParams rp = c->precision == SBSB200_FP32 ? PersistentPlan<float>::resident_params()
-                                                             : PersistentPlan<double>::resident_params();
-            // development knob for A/B timing: SBSB200_ROTATE_ITEMS=0 keeps cluster i of a step on thread i
-            if (char const* e = std::getenv("SBSB200_ROTATE_ITEMS"))
-                rp.rotate_items = std::atoi(e) != 0;
-            // experimental, off by default: hand-off inside a region, slab-shaped regions
-            if (char const* e = std::getenv("SBSB200_HANDOFF"))
-                rp.handoff = std::atoi(e) != 0 && c->precision == SBSB200_FP32 && c->world == 1;
-            if (char const* e = std::getenv("SBSB200_SLABS"))
-                rp.slabs = std::atoi(e) != 0 && c->world == 1;
-            build_cluster_plan(h, PersistentPlan<float>::regions_for(c->sm_count, T, c->world),
-                               PersistentPlan<float>::wants_region_per_body(h, c->sm_count), c->green_plan, &rp,
-                               &c->plan);
+        { // one region per SM; when the vertices a region touches do not fit its shared memory, two smaller
+          // regions per SM (half the threads each); beyond that the per-colour kernels take over
+            bool const ensemble = ResidentPlan<float>::wants_region_per_body(h, c->sm_count);
+            int64_t const vertex_bytes = c->precision == SBSB200_FP32 ? 16 : 32;
+            bool planned = false;
+            std::string why;
+            for (int per_sm = 1; per_sm <= 2 && !planned; ++per_sm)
+            {
+                ResidentParams rp = c->precision == SBSB200_FP32 ? ResidentPlan<float>::resident_params()
+                                                                 : ResidentPlan<double>::resident_params();
+                rp.pencils     = c->region_shape == SBSB200_REGIONS_PENCILS;
+                rp.smem_bytes  = rp.smem_bytes / per_sm - (per_sm > 1 ? 4096 : 0);
+                rp.max_threads = per_sm == 1 ? 384 : 192;
+                int32_t n_regions = regions_for(c->sm_count, T, c->world);
+                if (per_sm == 2)
+                {
+                    if (ensemble || n_regions != c->sm_count * c->world)
+                        break; // smaller scenes already have the regions they need
+                    n_regions *= 2;
+                }
+                build_cluster_plan(h, n_regions, ensemble, c->green_plan, &rp, &c->plan);
+                if (!build_exchange_plan(h, c->green_plan, c->plan, c->world, c->xplan))
+                    why = c->xplan.why_not;
+                else if (c->xplan.max_local * vertex_bytes > rp.smem_bytes)
+                    why = "the vertices a region touches do not fit shared memory";
+                else
+                    planned = true;
+            }
+            if (!planned)
+            {
+                if (c->world > 1)
+                    return fail(c, SBSB200_ERR_CAPACITY, "partitioned scene: " + why);
+                c->schedule      = SBSB200_SCHED_GRAPH;
+                c->schedule_note = "resident schedule unavailable: " + why;
+                c->plan          = RegionPlan{};
+                c->xplan         = ExchangePlan{};
+                build_cluster_plan(h, 1, false, c->green_plan);
+            }
         }
         else
             build_cluster_plan(h, 1, false, c->green_plan);
@@ -1478,6 +1588,7 @@ int sbsb200_finalize(sbsb200_ctx* c)
         else
             c->engine.reset(new Engine<double>());
         c->engine->build(*c);
+        c->general_calls0 = c->engine->general_route_calls();
         if (c->world > 1 && c->schedule != SBSB200_SCHED_PERSISTENT)
             return fail(c, SBSB200_ERR_CAPACITY, "partitioned scene: " + c->schedule_note);
         c->finalized = true;
@@ -1554,10 +1665,23 @@ int sbsb200_get_stats(const sbsb200_ctx* cc, sbsb200_stats* out)
     out->kernels_launched     = c->kernels;
     out->frames               = c->frames;
     out->last_contact_count   = c->last_contacts;
+    out->n_shared_vertices    = c->xplan.n_shared;
+    out->pulls_per_sweep      = c->xplan.n_pulls[2];
+    out->pushes_per_sweep     = c->xplan.n_pushes[0];
+    for (int64_t n : c->xplan.pulls_by_colour)
+        out->quiet_colours += c->schedule == SBSB200_SCHED_PERSISTENT && 50 * n <= c->xplan.n_pulls[2];
     if (c->engine)
     {
         cudaSetDevice(c->device);
         c->engine->kernel_times(out->kernel_ms, out->kernel_launches);
+        try
+        {
+            out->green_general_calls = static_cast<int64_t>(c->engine->general_route_calls() - c->general_calls0);
+        }
+        catch (...)
+        {
+            out->green_general_calls = -1;
+        }
     }
     if (c->timed)
     {
@@ -1624,21 +1748,33 @@ int sbsb200_download(sbsb200_ctx* c, int body, double* x, double* v)
     });
 }
 
-int sbsb200_set_mass(sbsb200_ctx* c, int body, int64_t vertex, double mass)
+int sbsb200_set_masses(sbsb200_ctx* c, int body, int64_t n, const uint32_t* vertices, const double* masses)
 {
     if (!c)
         return SBSB200_ERR_INVALID;
-    if (!is_tet_body(c, body) || vertex < 0 || vertex >= c->scene.bodies[static_cast<size_t>(body)].n_vertices)
-        return fail(c, SBSB200_ERR_INVALID, "bad body or vertex");
-    int64_t const gv = c->scene.bodies[static_cast<size_t>(body)].v_offset + vertex;
-    c->scene.mass[static_cast<size_t>(gv)] = mass;
-    if (!c->finalized)
+    if (!is_tet_body(c, body) || n < 0 || (n > 0 && (!vertices || !masses)))
+        return fail(c, SBSB200_ERR_INVALID, "bad body or arguments");
+    HostBody const& hb = c->scene.bodies[static_cast<size_t>(body)];
+    for (int64_t i = 0; i < n; ++i)
+        if (vertices[i] >= static_cast<uint64_t>(hb.n_vertices))
+            return fail(c, SBSB200_ERR_INVALID, "vertex index out of range");
+    for (int64_t i = 0; i < n; ++i)
+        c->scene.mass[static_cast<size_t>(hb.v_offset + vertices[i])] = masses[i];
+    if (!c->finalized || n == 0)
         return SBSB200_OK;
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
-        c->engine->set_mass(*c, gv, mass);
+        c->engine->set_masses(*c, hb.v_offset, n, vertices, masses);
         return SBSB200_OK;
     });
+}
+
+int sbsb200_set_mass(sbsb200_ctx* c, int body, int64_t vertex, double mass)
+{
+    if (vertex < 0 || vertex > 0xffffffffll)
+        return c ? fail(c, SBSB200_ERR_INVALID, "bad body or vertex") : SBSB200_ERR_INVALID;
+    uint32_t const v = static_cast<uint32_t>(vertex);
+    return sbsb200_set_masses(c, body, 1, &v, &mass);
 }
 
 int sbsb200_set_partition(sbsb200_ctx* c, int rank, int world)
@@ -1777,8 +1913,32 @@ int sbsb200_step_host(sbsb200_ctx* c, int body, const double* x_in, const double
     rc = sbsb200_step(c, dt, substeps, iterations, detect_mode);
     if (rc)
         return rc;
+    if (!x_out && !v_out) // nothing to download: still return only when x_in / v_in may be reused and the step is done
+        return sbsb200_synchronize(c);
     return sbsb200_download(c, body, x_out, v_out);
 }
+
+int sbsb200_step_host_f32(sbsb200_ctx* c, int body, const float* x_in, const float* v_in, double dt, int substeps,
+                          int iterations, int detect_mode, float* x_out, float* v_out)
+{
+    if (!c || !x_in)
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "step_host before finalize");
+    if (!is_tet_body(c, body))
+        return fail(c, SBSB200_ERR_INVALID, "not a tetrahedral body");
+    if (c->world > 1 && !c->engine->peers_connected())
+        return fail(c, SBSB200_ERR_STATE, "partitioned scene: connect the peers' mailboxes before stepping");
+    if (!(dt > 0.) || substeps <= 0 || iterations < 0 ||
+        (detect_mode != SBSB200_DETECT_PER_FRAME && detect_mode != SBSB200_DETECT_PER_SUBSTEP))
+        return fail(c, SBSB200_ERR_INVALID, "bad step arguments");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->step_host_f32(*c, body, x_in, v_in, dt, substeps, iterations, detect_mode, x_out, v_out);
+        return SBSB200_OK;
+    });
+}
+
 
 int64_t sbsb200_debug_read_trace(sbsb200_ctx* c, int64_t* out, int64_t cap)
 {

@@ -523,54 +523,92 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
 
     // regions
     if (one_region_per_body)
-    {
-        std::vector<int32_t> body_region(scene.bodies.size(), -1);
-        int32_t nr = 0;
+    { // ensembles: consecutive whole bodies per region, enough of them to fill the warps of a colour step
+        std::vector<int32_t> body_index(scene.bodies.size(), -1);
+        int32_t nb = 0;
         for (size_t b = 0; b < scene.bodies.size(); ++b)
             if (scene.bodies[b].kind == BodyKind::tet && scene.bodies[b].n_tets > 0)
-                body_region[b] = nr++;
-        out.n_regions = std::max<int32_t>(1, nr);
-        for (Cluster& c : clusters)
-            c.region = body_region[static_cast<size_t>(c.body)];
-    }
-    else if (n_regions > 1 && resident && resident->slabs && !clusters.empty())
-    { // layers of the cluster grid along its longest axis, consecutive layers per region, at most one region per layer
-        uint32_t lo[3] = {~0u, ~0u, ~0u}, hi[3] = {0u, 0u, 0u};
-        for (Cluster const& c : clusters)
+                body_index[b] = nb++;
+        int32_t group = 1;
+        if (resident)
         {
-            uint32_t const g[3] = {c.cx, c.cy, c.cz};
-            for (int d = 0; d < 3; ++d)
-            {
-                lo[d] = std::min(lo[d], g[d]);
-                hi[d] = std::max(hi[d], g[d]);
+            group = resident->bodies_per_region;
+            if (group <= 0)
+            { // about 160 clusters in the widest colour step of a region, and the vertices must fit shared memory
+                std::vector<int32_t> per(static_cast<size_t>(std::max(nb, 1)) * static_cast<size_t>(out.n_colours), 0);
+                int32_t widest = 1;
+                for (Cluster const& c : clusters)
+                    widest = std::max(widest, ++per[static_cast<size_t>(body_index[static_cast<size_t>(c.body)]) *
+                                                        static_cast<size_t>(out.n_colours) + c.colour]);
+                int64_t most_vertices = 1;
+                for (HostBody const& hb : scene.bodies)
+                    if (hb.kind == BodyKind::tet)
+                        most_vertices = std::max<int64_t>(most_vertices, hb.n_vertices);
+                int64_t const fit = resident->smem_bytes / (most_vertices * resident->vertex_bytes);
+                group = static_cast<int32_t>(std::max<int64_t>(1, std::min<int64_t>((160 + widest / 2) / widest, fit)));
             }
         }
-        int axis = 0;
-        for (int d = 1; d < 3; ++d)
-            if (hi[d] - lo[d] > hi[axis] - lo[axis])
-                axis = d;
-        int64_t const layers = static_cast<int64_t>(hi[axis] - lo[axis]) + 1;
-        out.n_regions        = static_cast<int32_t>(std::min<int64_t>(n_regions, layers));
+        out.n_regions = std::max<int32_t>(1, (nb + group - 1) / group);
         for (Cluster& c : clusters)
-        {
-            uint32_t const g[3] = {c.cx, c.cy, c.cz};
-            c.region = static_cast<int32_t>((static_cast<int64_t>(g[axis] - lo[axis]) * out.n_regions) / layers);
-        }
+            c.region = body_index[static_cast<size_t>(c.body)] / group;
     }
     else if (n_regions > 1)
     {
         out.n_regions = n_regions;
         std::vector<uint32_t> idx(clusters.size());
         std::iota(idx.begin(), idx.end(), 0u);
+        // Pencils: whole columns of clusters along the shortest axis of the cluster grid, bundled in the 2-D
+        // Morton order of the two other coordinates.  No region boundary is then perpendicular to the pencil
+        // axis, and with the colours ordered for it (below) half of the steps of a sweep on a lattice depend on
+        // no other region.  Needs a few columns per region; otherwise compact Morton blocks.
+        bool pencils = resident && resident->pencils;
+        int axis     = 0;
+        if (pencils)
+        {
+            uint32_t lo[3] = {~0u, ~0u, ~0u}, hi[3] = {0u, 0u, 0u};
+            for (Cluster const& c : clusters)
+            {
+                uint32_t const g[3] = {c.cx, c.cy, c.cz};
+                for (int d = 0; d < 3; ++d)
+                {
+                    lo[d] = std::min(lo[d], g[d]);
+                    hi[d] = std::max(hi[d], g[d]);
+                }
+            }
+            for (int d = 1; d < 3; ++d)
+                if (hi[d] - lo[d] < hi[axis] - lo[axis])
+                    axis = d;
+            int const b = (axis + 1) % 3, c = (axis + 2) % 3;
+            int64_t const columns = (static_cast<int64_t>(hi[b] - lo[b]) + 1) * (static_cast<int64_t>(hi[c] - lo[c]) + 1);
+            pencils               = columns >= 4 * static_cast<int64_t>(n_regions);
+        }
+        auto const column_key = [&](Cluster const& c) -> uint64_t {
+            uint32_t const g[3] = {c.cx, c.cy, c.cz};
+            uint32_t const u = g[(axis + 1) % 3], v = g[(axis + 2) % 3];
+            // 2-D Morton code of (u, v): the bits of u on the even positions of a 3-D spread, v on the odd ones
+            uint64_t key = 0;
+            for (int bit = 0; bit < 20; ++bit)
+                key |= (static_cast<uint64_t>(u >> bit & 1u) << (2 * bit)) | (static_cast<uint64_t>(v >> bit & 1u) << (2 * bit + 1));
+            return key;
+        };
+        std::vector<uint64_t> key(clusters.size());
+        for (size_t i = 0; i < clusters.size(); ++i)
+            key[i] = pencils ? column_key(clusters[i]) : clusters[i].morton;
         std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
             if (clusters[a].body != clusters[b].body)
                 return clusters[a].body < clusters[b].body;
-            return clusters[a].morton < clusters[b].morton;
+            return key[a] < key[b];
         });
-        int64_t seen = 0;
-        for (uint32_t i : idx)
-        { // balanced by tet count: cluster goes to the region its first tet falls into
-            clusters[i].region = static_cast<int32_t>(std::min<int64_t>(n_regions - 1, (seen * n_regions) / T));
+        int64_t seen   = 0;
+        int32_t region = 0;
+        for (size_t k = 0; k < idx.size(); ++k)
+        { // balanced by tet count; a pencil column is never split
+            uint32_t const i = idx[k];
+            bool const new_unit =
+                !pencils || k == 0 || clusters[idx[k - 1]].body != clusters[i].body || key[idx[k - 1]] != key[i];
+            if (new_unit)
+                region = static_cast<int32_t>(std::min<int64_t>(n_regions - 1, (seen * n_regions) / T));
+            clusters[i].region = region;
             seen += clusters[i].count;
         }
     }
@@ -578,7 +616,6 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         out.n_regions = 1;
 
     // unique vertices per cluster
-    uint32_t max_cluster_vertices = 0;
     for (Cluster& c : clusters)
     {
         c.nv = 0;
@@ -589,18 +626,18 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
                 if (std::find(c.verts, c.verts + c.nv, v) == c.verts + c.nv)
                     c.verts[c.nv++] = v;
             }
-        max_cluster_vertices = std::max(max_cluster_vertices, c.nv);
     }
     for (Cluster const& c : clusters)
         for (uint32_t m = 0; m < c.count; ++m)
             out.tet_region[sorted[c.first + m]] = c.region;
 
-    // Hand-off: renumber the colours so that consecutive colours hand a shared vertex over INSIDE a region as
-    // often as possible.  D[a][b] = shared vertices whose clusters of colours a and b lie in different regions;
-    // the order is the path of least total D (exhaustive up to 9 colours, nearest neighbour + 2-opt beyond).
-    // On a lattice this is a Gray code of the cell parities: every step then depends on other regions across
-    // one face orientation only.  Any order of the colours is a valid Gauss-Seidel order.
-    if (resident && resident->handoff && out.n_regions > 1 && out.n_colours > 2)
+    // Renumber the colours so that consecutive colours hand a shared vertex over INSIDE a region as often as
+    // possible.  D[a][b] = shared vertices whose clusters of colours a and b lie in different regions; the
+    // order is the cycle of least total D (exhaustive up to 9 colours, nearest neighbour + 2-opt beyond).  On a
+    // lattice this is a Gray code of the cell parities: every step then depends on other regions across one
+    // face orientation only, and with pencil regions the steps that flip the parity along the pencil axis
+    // depend on no other region at all.  Any order of the colours is a valid Gauss-Seidel order.
+    if (resident && out.n_regions > 1 && out.n_colours > 2)
     {
         int32_t const C = out.n_colours;
         struct Touch3
@@ -631,8 +668,8 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         }
         auto const cost = [&](std::vector<int32_t> const& o) {
             int64_t s = 0;
-            for (int32_t i = 0; i + 1 < C; ++i) // open path: the sweep's last colour never hands over to its first
-                s += D[static_cast<size_t>(o[i]) * C + o[i + 1]];
+            for (int32_t i = 0; i < C; ++i) // a cycle: the last colour of a sweep hands over to the first of the next
+                s += D[static_cast<size_t>(o[i]) * C + o[(i + 1) % C]];
             return s;
         };
         std::vector<int32_t> best(static_cast<size_t>(C));
@@ -641,7 +678,7 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         if (C <= 9)
         {
             std::vector<int32_t> o(best);
-            while (std::next_permutation(o.begin(), o.end()))
+            while (std::next_permutation(o.begin() + 1, o.end())) // a cycle: colour 0 stays first
             {
                 int64_t const s = cost(o);
                 if (s < best_cost)
@@ -694,73 +731,28 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
     // resident schedule: vertex classification, cluster parts, launch shape
     if (resident)
     {
-        out.nvc = static_cast<int32_t>((max_cluster_vertices + 3) / 4 * 4);
-        out.nvc = std::max(out.nvc, 4);
-        // threads per CTA: every cluster of a (colour, region) step gets its own thread when possible
-        // (cluster i of the step, part A first, runs on thread i % nt)
-        auto threads_needed = [&](std::vector<int64_t> const& a_cnt, std::vector<int64_t> const& b_cnt) {
-            int64_t need = 0;
-            for (size_t i = 0; i < a_cnt.size(); ++i)
-                need = std::max(need, a_cnt[i] + b_cnt[i]);
-            // more clusters than threads: as many rounds as the largest block needs, of equal width
-            int64_t const rounds = std::max<int64_t>(1, (need + resident->max_threads - 1) / resident->max_threads);
-            int64_t const width  = (need + rounds - 1) / rounds;
-            return static_cast<int32_t>(
-                std::min<int64_t>(resident->max_threads, std::max<int64_t>(64, (width + 31) / 32 * 32)));
-        };
-        size_t const n_steps = static_cast<size_t>(out.n_colours) * static_cast<size_t>(out.n_regions);
-        std::vector<int64_t> a_cnt(n_steps, 0), b_cnt(n_steps, 0);
-        for (Cluster const& c : clusters)
-            ++b_cnt[static_cast<size_t>(c.colour) * out.n_regions + c.region];
-        // The classification depends on the shared-memory capacity, which depends on the thread count
-        // (scratch slots), which depends on the classification.  Start from a safe upper bound of the
-        // thread count, then try once with the count that classification needs; keep it if it holds.
-        std::vector<int64_t> total(b_cnt), none(n_steps, 0);
-        auto classify_with = [&](int32_t nt) -> int32_t { // returns the thread count this classification needs
-            int64_t const scratch  = static_cast<int64_t>(resident->handoff ? 2 : 1) * out.nvc * nt;
-            int64_t const capacity = std::min<int64_t>(resident->smem_bytes / resident->vertex_bytes - scratch, 65535 - scratch);
-            if (capacity < 0)
-            {
-                out.why_not = "shared memory cannot hold the per-thread scratch vertices";
-                return -1;
-            }
-            classify_regions(scene, out.tet_region, out.n_regions, *region_plan, capacity);
-            std::fill(a_cnt.begin(), a_cnt.end(), 0);
-            std::fill(b_cnt.begin(), b_cnt.end(), 0);
+        if (region_plan)
+        {
+            classify_regions(scene, out.tet_region, out.n_regions, *region_plan);
             for (Cluster& c : clusters)
-            {
+            { // part 0: the cluster has a vertex that another region touches too
                 c.part = 1;
                 for (uint32_t k = 0; k < c.nv; ++k)
                     if (region_plan->vertex_region[c.verts[k]] != c.region)
                         c.part = 0;
-                ++(c.part == 0 ? a_cnt : b_cnt)[static_cast<size_t>(c.colour) * out.n_regions + c.region];
-            }
-            return threads_needed(a_cnt, b_cnt);
-        };
-        int32_t const upper = threads_needed(none, total);
-        out.nt              = upper;
-        if (region_plan)
-        {
-            int32_t const need = classify_with(upper);
-            if (need > 0 && need < upper)
-            {
-                out.nt = need;
-                if (classify_with(need) > need)
-                { // more residency shifted clusters from A to B beyond the count: stay with the bound
-                    out.nt = upper;
-                    classify_with(upper);
-                }
             }
         }
+        // threads per CTA: every cluster of a (colour, region) step gets its own thread when possible
+        // (cluster i of the step, part 0 first, runs on thread (i + rot) % nt); more clusters than threads:
+        // as many rounds as the widest step needs, of equal width
+        std::vector<int64_t> cnt(static_cast<size_t>(out.n_colours) * static_cast<size_t>(out.n_regions), 0);
+        int64_t need = 0;
+        for (Cluster const& c : clusters)
+            need = std::max(need, ++cnt[static_cast<size_t>(c.colour) * out.n_regions + c.region]);
+        int64_t const rounds = std::max<int64_t>(1, (need + resident->max_threads - 1) / resident->max_threads);
+        int64_t const width  = (need + rounds - 1) / rounds;
+        out.nt  = static_cast<int32_t>(std::min<int64_t>(resident->max_threads, std::max<int64_t>(64, (width + 31) / 32 * 32)));
         out.rot = resident->rotate_items ? item_rotation(out.nt) : 0;
-        {   // hand-off needs every step to be a single round (a thread's scratch slots belong to ONE cluster per step)
-            int64_t widest = 0;
-            for (size_t i = 0; i < a_cnt.size(); ++i)
-                widest = std::max(widest, a_cnt[i] + b_cnt[i]);
-            out.banks = resident->handoff && region_plan && widest <= out.nt ? 2 : 1;
-        }
-        if (out.nvc > kMaxClusterVertices)
-            out.why_not = "a cluster has more than 16 distinct vertices";
         if (out.n_colours > 120)
             out.why_not = "more than 120 cluster colours (8-bit step distances)";
     }
@@ -787,35 +779,6 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
     out.chunks.assign(n_chunks, ChunkDesc{});
     out.storage_order.resize(static_cast<size_t>(T));
     out.serial_order.reserve(static_cast<size_t>(T));
-    bool const layout = resident && region_plan && out.why_not.empty();
-    // colours that touch each vertex (the touch schedule the tag protocol of the resident kernel follows)
-    std::vector<std::array<uint64_t, 2>> vcolours;
-    if (layout)
-    {
-        out.tet_slots.assign(4 * static_cast<size_t>(T), 0);
-        out.cl_fetch.assign(static_cast<size_t>(out.nvc) * clusters.size(), 0xffffffffu);
-        out.cl_meta.assign(static_cast<size_t>(out.nvc) * clusters.size(), 0u);
-        vcolours.assign(static_cast<size_t>(V), std::array<uint64_t, 2>{});
-        for (Cluster const& c : clusters)
-            for (uint32_t u = 0; u < c.nv; ++u)
-                vcolours[c.verts[u]][c.colour >> 6] |= 1ull << (c.colour & 63);
-        std::vector<char> is_surface(static_cast<size_t>(V), 0);
-        for (HostBody const& hb : scene.bodies)
-            if (hb.kind == BodyKind::tet)
-                for (uint32_t lv : hb.surf_to_tet)
-                    is_surface[static_cast<size_t>(hb.v_offset + lv)] = 1;
-        out.vertex_meta.assign(static_cast<size_t>(V), 0);
-        for (int64_t v = 0; v < V; ++v)
-        {
-            auto const& m = vcolours[static_cast<size_t>(v)];
-            uint32_t last = 0xffu;
-            if (m[1])
-                last = 127u - static_cast<uint32_t>(__builtin_clzll(m[1]));
-            else if (m[0])
-                last = 63u - static_cast<uint32_t>(__builtin_clzll(m[0]));
-            out.vertex_meta[static_cast<size_t>(v)] = last | (is_surface[static_cast<size_t>(v)] ? 0x100u : 0u);
-        }
-    }
     int64_t store = 0;
     size_t i      = 0;
     int64_t pair_clusters = 0;
@@ -848,71 +811,10 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
                 Cluster const& c = clusters[idx[k]];
                 if (c.count <= static_cast<uint32_t>(m))
                     continue;
-                int64_t const pos = col_base + static_cast<int64_t>(k - i);
-                uint32_t const t  = sorted[c.first + m];
-                out.storage_order[static_cast<size_t>(pos)] = t;
-                if (!layout)
-                    continue;
-                // vertex addresses in the CTA's shared array: [nvc * nt scratch | resident vertices]
-                uint32_t const thread =
-                    static_cast<uint32_t>((k - i + static_cast<size_t>(out.rot)) % static_cast<size_t>(out.nt));
-                for (int a = 0; a < 4; ++a)
-                {
-                    uint32_t const v = scene.tets[4 * static_cast<size_t>(t) + a];
-                    uint32_t slot;
-                    if (region_plan->vertex_region[v] == reg)
-                        slot = static_cast<uint32_t>(out.banks * out.nvc) * out.nt + region_plan->vertex_slot[v];
-                    else
-                    { // k-th fetched vertex of this cluster
-                        uint32_t kf = 0;
-                        for (uint32_t u = 0; u < c.nv && c.verts[u] != v; ++u)
-                            kf += region_plan->vertex_region[c.verts[u]] != reg;
-                        slot = kf * static_cast<uint32_t>(out.nt) + thread;
-                    }
-                    out.tet_slots[4 * static_cast<size_t>(pos) + a] = static_cast<uint16_t>(slot);
-                }
+                out.storage_order[static_cast<size_t>(col_base + static_cast<int64_t>(k - i))] = sorted[c.first + m];
             }
             col_base += d.n[m];
         }
-        if (layout)
-            for (size_t k = i; k < j; ++k)
-            {
-                Cluster const& c = clusters[idx[k]];
-                uint32_t kf      = 0;
-                for (uint32_t u = 0; u < c.nv; ++u)
-                    if (region_plan->vertex_region[c.verts[u]] != reg)
-                    {
-                        uint32_t const v = c.verts[u];
-                        // How many steps back the previous touch of v lies, for the four kinds of
-                        // colour step: byte 2*(k>0) + cs, cs = 1 when a collision step precedes every
-                        // sweep; 0xff = the predict step of the launch.  Touches are: predict, the
-                        // collision steps if v is a surface vertex, the colours whose clusters contain v.
-                        auto const& m    = vcolours[v];
-                        int32_t prevc    = -1;
-                        for (int32_t pc = col - 1; pc >= 0 && prevc < 0; --pc)
-                            if (m[pc >> 6] >> (pc & 63) & 1ull)
-                                prevc = pc;
-                        int32_t const lastc = static_cast<int32_t>(out.vertex_meta[v] & 0xffu);
-                        bool const surf     = (out.vertex_meta[v] & 0x100u) != 0u;
-                        uint32_t word       = 0;
-                        for (int later = 0; later < 2; ++later)
-                            for (int cs = 0; cs < 2; ++cs)
-                            {
-                                int32_t d;
-                                if (prevc >= 0)
-                                    d = col - prevc;
-                                else if (cs && surf)
-                                    d = col + 1;
-                                else if (later)
-                                    d = out.n_colours + cs + col - lastc;
-                                else
-                                    d = 0xff;
-                                word |= static_cast<uint32_t>(d) << (8 * (2 * later + cs));
-                            }
-                        out.cl_meta[static_cast<size_t>(kf) * clusters.size() + k] = word;
-                        out.cl_fetch[static_cast<size_t>(kf++) * clusters.size() + k] = v;
-                    }
-            }
         store = col_base;
         pair_clusters = (part == 0 ? 0 : pair_clusters) + static_cast<int64_t>(j - i);
         out.max_chunk_clusters = std::max<int64_t>(out.max_chunk_clusters, pair_clusters);
@@ -920,206 +822,359 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
     }
 }
 
-bool build_mailbox_routes(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& plan, int nvc, int world,
-                          MailboxRoutes& out)
+bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& plan, int world,
+                         ExchangePlan& out)
 {
-    out = MailboxRoutes{};
-    int64_t const V = scene.n_vertices(), Q = cp.n_clusters;
-    int32_t const Rn = plan.n_regions;
-    if (world < 1 || Rn % world != 0 || nvc < cp.nvc)
+    out = ExchangePlan{};
+    int64_t const V = scene.n_vertices(), T = scene.n_tets(), Q = cp.n_clusters;
+    int32_t const Rn = cp.n_regions, C = cp.n_colours;
+    out.n_regions = Rn;
+    out.n_colours = C;
+    out.world     = world;
+    if (world < 1 || Rn % world != 0 || plan.n_regions != Rn || static_cast<int64_t>(plan.vertex_region.size()) != V)
     {
         out.why_not = "bad partition (world must divide the region count)";
         return false;
     }
-    // owned non-resident vertices, grouped by owner region
-    out.ifv_offsets.assign(static_cast<size_t>(Rn) + 1, 0);
-    for (int64_t v = 0; v < V; ++v)
-        if (plan.vertex_region[static_cast<size_t>(v)] < 0)
-            ++out.ifv_offsets[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)]) + 1];
-    for (int32_t r = 0; r < Rn; ++r)
-        out.ifv_offsets[static_cast<size_t>(r) + 1] += out.ifv_offsets[static_cast<size_t>(r)];
-    out.ifv.assign(static_cast<size_t>(out.ifv_offsets.back()), 0);
-    out.ifv_meta.assign(out.ifv.size(), 0);
-    out.ifv_pos.assign(static_cast<size_t>(V), kRouteNone);
+    if (!cp.why_not.empty())
     {
-        std::vector<int32_t> cur(out.ifv_offsets.begin(), out.ifv_offsets.end() - 1);
-        for (int64_t v = 0; v < V; ++v)
-            if (plan.vertex_region[static_cast<size_t>(v)] < 0)
-            {
-                int32_t const at = cur[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)])]++;
-                out.ifv[static_cast<size_t>(at)]      = static_cast<uint32_t>(v);
-                out.ifv_meta[static_cast<size_t>(at)] = cp.vertex_meta.empty() ? 0u : cp.vertex_meta[static_cast<size_t>(v)];
-                out.ifv_pos[static_cast<size_t>(v)]   = static_cast<uint32_t>(at);
-            }
+        out.why_not = cp.why_not;
+        return false;
     }
-    out.n_entries = static_cast<uint32_t>(static_cast<int64_t>(nvc) * Q);
-    if (static_cast<uint64_t>(out.n_entries) + out.ifv.size() >= kRouteIndexMask)
+    // ---- clusters back from the chunks: colour, region, part, tets --------------------------------------
+    struct Cl
+    {
+        int32_t colour, region, part;
+        int64_t xq; // number among the exchange clusters, -1 for part 1
+        uint32_t n_shared;
+        uint32_t shared[kMaxClusterVertices];
+    };
+    std::vector<Cl> cl(static_cast<size_t>(Q));
+    std::vector<char> touched(static_cast<size_t>(V), 0);
+    for (uint32_t v : scene.tets)
+        touched[v] = 1;
+    auto const is_shared = [&](uint32_t v) { return touched[v] && plan.vertex_region[v] < 0; };
+    out.chunk_xfirst.assign(static_cast<size_t>(C) * Rn, 0);
+    int64_t nx = 0;
+    uint32_t most_shared = 0;
+    std::vector<int32_t> pos_cluster(static_cast<size_t>(T), 0); // storage position -> cluster
+    for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
+    {
+        ChunkDesc const& d = cp.chunks[ch];
+        int32_t const col = static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
+        int32_t const reg = static_cast<int32_t>((ch / 2) % static_cast<size_t>(Rn));
+        int32_t const part = static_cast<int32_t>(ch % 2);
+        if (part == 0)
+            out.chunk_xfirst[static_cast<size_t>(col) * Rn + reg] = static_cast<int32_t>(nx);
+        for (int32_t i = 0; i < d.n[0]; ++i)
+        {
+            Cl& c      = cl[static_cast<size_t>(d.cfirst + i)];
+            c.colour   = col;
+            c.region   = reg;
+            c.part     = part;
+            c.xq       = part == 0 ? nx++ : -1;
+            c.n_shared = 0;
+            int64_t base = d.first;
+            for (int m = 0; m < kMaxCluster && i < d.n[m]; ++m)
+            {
+                int64_t const pos = base + i;
+                pos_cluster[static_cast<size_t>(pos)] = d.cfirst + i;
+                uint32_t const t = cp.storage_order[static_cast<size_t>(pos)];
+                for (int a = 0; a < 4; ++a)
+                {
+                    uint32_t const v = scene.tets[4 * static_cast<size_t>(t) + a];
+                    if (is_shared(v) && std::find(c.shared, c.shared + c.n_shared, v) == c.shared + c.n_shared)
+                    {
+                        if (c.n_shared >= static_cast<uint32_t>(kMaxClusterVertices))
+                        {
+                            out.why_not = "a cluster has more than 16 shared vertices";
+                            return false;
+                        }
+                        c.shared[c.n_shared++] = v;
+                    }
+                }
+                base += d.n[m];
+            }
+            if ((c.n_shared > 0) != (part == 0))
+            {
+                out.why_not = "cluster parts and vertex classification disagree";
+                return false;
+            }
+            most_shared = std::max(most_shared, c.n_shared);
+        }
+    }
+    out.n_xclusters = nx;
+    out.entries     = static_cast<int32_t>(std::max<uint32_t>(4u, (most_shared + 3u) / 4u * 4u));
+
+    // ---- local vertex tables: owned vertices first, then guests -------------------------------------------
+    out.vertex_owner = plan.vertex_owner;
+    out.loc_off.assign(static_cast<size_t>(Rn) + 1, 0);
+    out.n_owned.assign(static_cast<size_t>(Rn), 0);
+    for (int64_t v = 0; v < V; ++v)
+        ++out.n_owned[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)])];
+    // guests: (region, shared vertex) pairs with region != owner
+    std::vector<std::pair<int32_t, uint32_t>> guests;
+    for (Cl const& c : cl)
+        for (uint32_t k = 0; k < c.n_shared; ++k)
+            if (plan.vertex_owner[c.shared[k]] != c.region)
+                guests.emplace_back(c.region, c.shared[k]);
+    std::sort(guests.begin(), guests.end());
+    guests.erase(std::unique(guests.begin(), guests.end()), guests.end());
+    {
+        std::vector<int32_t> n_guests(static_cast<size_t>(Rn), 0);
+        for (auto const& g : guests)
+            ++n_guests[static_cast<size_t>(g.first)];
+        for (int32_t r = 0; r < Rn; ++r)
+        {
+            int64_t const n = static_cast<int64_t>(out.n_owned[static_cast<size_t>(r)]) + n_guests[static_cast<size_t>(r)];
+            out.max_local   = std::max(out.max_local, n);
+            out.loc_off[static_cast<size_t>(r) + 1] = out.loc_off[static_cast<size_t>(r)] + static_cast<int32_t>(n);
+        }
+    }
+    if (out.max_local > 65535)
+    {
+        out.why_not = "a region touches more than 65535 vertices (16-bit slots)";
+        return false;
+    }
+    out.loc_vtx.assign(static_cast<size_t>(out.loc_off.back()), 0);
+    std::vector<uint32_t> owner_slot(static_cast<size_t>(V), 0);
+    {
+        std::vector<int32_t> cur(static_cast<size_t>(Rn), 0);
+        for (int64_t v = 0; v < V; ++v)
+        {
+            int32_t const r = plan.vertex_owner[static_cast<size_t>(v)];
+            owner_slot[static_cast<size_t>(v)] = static_cast<uint32_t>(cur[static_cast<size_t>(r)]);
+            out.loc_vtx[static_cast<size_t>(out.loc_off[static_cast<size_t>(r)] + cur[static_cast<size_t>(r)]++)] =
+                static_cast<uint32_t>(v);
+        }
+        for (auto const& g : guests) // sorted by (region, vertex): the guest slots of a region are in vertex order
+            out.loc_vtx[static_cast<size_t>(out.loc_off[static_cast<size_t>(g.first)] + cur[static_cast<size_t>(g.first)]++)] =
+                g.second;
+    }
+    auto const slot_of = [&](int32_t r, uint32_t v) -> uint32_t {
+        if (plan.vertex_owner[v] == r)
+            return owner_slot[v];
+        auto const it = std::lower_bound(guests.begin(), guests.end(), std::make_pair(r, v));
+        int64_t const first_guest =
+            std::lower_bound(guests.begin(), guests.end(), std::make_pair(r, 0u)) - guests.begin();
+        return static_cast<uint32_t>(out.n_owned[static_cast<size_t>(r)] + ((it - guests.begin()) - first_guest));
+    };
+    out.tet_slots.assign(4 * static_cast<size_t>(T), 0);
+    for (int64_t pos = 0; pos < T; ++pos)
+    {
+        uint32_t const t = cp.storage_order[static_cast<size_t>(pos)];
+        int32_t const r  = cl[static_cast<size_t>(pos_cluster[static_cast<size_t>(pos)])].region;
+        for (int a = 0; a < 4; ++a)
+        {
+            uint32_t const v = scene.tets[4 * static_cast<size_t>(t) + a];
+            if (plan.vertex_owner[v] != r && !is_shared(v))
+            {
+                out.why_not = "a private vertex is owned by another region";
+                return false;
+            }
+            out.tet_slots[4 * static_cast<size_t>(pos) + a] = static_cast<uint16_t>(slot_of(r, v));
+        }
+    }
+
+    // ---- shared vertices: owner records and the touch chains ---------------------------------------------
+    out.n_entries = static_cast<uint32_t>(static_cast<int64_t>(out.entries) * nx);
+    std::vector<char> is_surface(static_cast<size_t>(V), 0);
+    for (HostBody const& hb : scene.bodies)
+        if (hb.kind == BodyKind::tet)
+            for (uint32_t lv : hb.surf_to_tet)
+                is_surface[static_cast<size_t>(hb.v_offset + lv)] = 1;
+    out.osv_off.assign(static_cast<size_t>(Rn) + 1, 0);
+    std::vector<uint32_t> osv_pos(static_cast<size_t>(V), kRouteNone);
+    for (int64_t v = 0; v < V; ++v)
+        if (is_shared(static_cast<uint32_t>(v)))
+        {
+            ++out.osv_off[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)]) + 1];
+            ++out.n_shared;
+        }
+    for (int32_t r = 0; r < Rn; ++r)
+        out.osv_off[static_cast<size_t>(r) + 1] += out.osv_off[static_cast<size_t>(r)];
+    if (static_cast<uint64_t>(out.n_entries) + static_cast<uint64_t>(out.n_shared) >= kRouteIndexMask)
     {
         out.why_not = "too many mailboxes for 28-bit routing words";
         return false;
     }
-    std::vector<int32_t> cluster_colour(static_cast<size_t>(Q), 0), cluster_region(static_cast<size_t>(Q), 0),
-        cluster_item(static_cast<size_t>(Q), 0); // position in its chunk = in its step for part A (first in a step)
-    for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
-        for (int32_t i = 0; i < cp.chunks[ch].n[0]; ++i)
-        {
-            cluster_item[static_cast<size_t>(cp.chunks[ch].cfirst + i)] = i;
-            cluster_colour[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
-                static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
-            cluster_region[static_cast<size_t>(cp.chunks[ch].cfirst + i)] =
-                static_cast<int32_t>((ch / 2) % static_cast<size_t>(Rn));
-        }
-    // routing word of a mailbox: its index and the rank whose memory holds it (the rank that reads it)
-    auto const entry_route = [&](uint32_t box) {
-        return box | (static_cast<uint32_t>(region_rank(cluster_region[box % static_cast<uint32_t>(Q)], Rn, world))
-                      << kRouteRankShift);
-    };
-    auto const owner_route = [&](uint32_t pos) {
-        return (out.n_entries + pos) |
-               (static_cast<uint32_t>(region_rank(plan.vertex_owner[out.ifv[pos]], Rn, world)) << kRouteRankShift);
-    };
+    out.osv_slot.assign(static_cast<size_t>(out.n_shared), 0);
+    out.osv_meta.assign(static_cast<size_t>(out.n_shared), 0);
+    out.osv_first.assign(static_cast<size_t>(out.n_shared), kRouteNone);
+    {
+        std::vector<int32_t> cur(out.osv_off.begin(), out.osv_off.end() - 1);
+        for (int64_t v = 0; v < V; ++v)
+            if (is_shared(static_cast<uint32_t>(v)))
+            {
+                int32_t const at = cur[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)])]++;
+                osv_pos[static_cast<size_t>(v)]      = static_cast<uint32_t>(at);
+                out.osv_slot[static_cast<size_t>(at)] = owner_slot[static_cast<size_t>(v)];
+            }
+    }
+    auto const rank_of = [&](int32_t region) { return static_cast<uint32_t>(region_rank(region, Rn, world)); };
     struct Touch
     {
         uint32_t vertex;
-        int32_t colour;
-        uint32_t box;
+        int32_t colour, region;
+        uint32_t entry;
+        int64_t xq;
     };
     std::vector<Touch> touches;
-    for (int j = 0; j < cp.nvc; ++j)
-        for (int64_t q = 0; q < Q; ++q)
-        {
-            uint32_t const v = cp.cl_fetch[static_cast<size_t>(j) * Q + q];
-            if (v != kRouteNone)
-                touches.push_back({v, cluster_colour[static_cast<size_t>(q)],
-                                   static_cast<uint32_t>(static_cast<int64_t>(j) * Q + q)});
-        }
+    for (Cl const& c : cl)
+        for (uint32_t k = 0; k < c.n_shared; ++k)
+            touches.push_back({c.shared[k], c.colour, c.region, k, c.xq});
     std::sort(touches.begin(), touches.end(), [](Touch const& x, Touch const& y) {
         return x.vertex != y.vertex ? x.vertex < y.vertex : x.colour < y.colour;
     });
-    out.to.assign(out.n_entries, kRouteNone);
-    out.to_owner.assign(out.n_entries, kRouteNone);
-    out.local_prev.assign(out.n_entries, 0);
-    out.n_local = 0;
-    if (cp.banks == 2 && static_cast<uint64_t>(out.n_entries) + out.ifv.size() >= kRouteLocalBit)
-    {
-        out.why_not = "too many mailboxes for 27-bit routing words (hand-off)";
-        return false;
-    }
-    // hand-off: the next touch is by a cluster of the same region in the very next step -> the vertex goes
-    // straight into that cluster's scratch slot (entry * nt + thread), no mailbox, no poll
-    auto const local_route = [&](uint32_t box) {
-        uint32_t const q = box % static_cast<uint32_t>(Q), entry = box / static_cast<uint32_t>(Q);
-        uint32_t const thread = static_cast<uint32_t>((cluster_item[q] + cp.rot) % cp.nt);
-        return kRouteLocalBit | (entry * static_cast<uint32_t>(cp.nt) + thread);
+    auto const entry_route = [&](Touch const& t) {
+        return static_cast<uint32_t>(static_cast<int64_t>(t.entry) * nx + t.xq) | (rank_of(t.region) << kRouteRankShift);
     };
-    out.ifv_first.assign(out.ifv.size(), kRouteNone);
+    auto const owner_route = [&](uint32_t v) {
+        return (out.n_entries + osv_pos[v]) | (rank_of(plan.vertex_owner[v]) << kRouteRankShift);
+    };
+    // per (variant, exchange cluster): the words, in the order of the cluster's shared vertices
+    std::vector<std::vector<uint32_t>> pulls(4 * static_cast<size_t>(nx)), pushes(4 * static_cast<size_t>(nx));
+    std::vector<char> colour_pulls(static_cast<size_t>(std::max(C, 1)), 0);
+    out.pulls_by_colour.assign(static_cast<size_t>(std::max(C, 1)), 0);
     for (size_t i = 0; i < touches.size();)
     {
         size_t j = i;
         while (j < touches.size() && touches[j].vertex == touches[i].vertex)
             ++j;
-        uint32_t const v   = touches[i].vertex;
-        uint32_t const pos = out.ifv_pos[v];
-        if (pos == kRouteNone)
-        {
-            out.why_not = "a fetched vertex has no owner mailbox";
-            return false;
-        }
-        out.ifv_first[pos] = entry_route(touches[i].box);
-        for (size_t t = i; t < j; ++t)
-        {
-            if (t + 1 < j && touches[t + 1].colour == touches[t].colour)
+        uint32_t const v    = touches[i].vertex;
+        int32_t const owner = plan.vertex_owner[v];
+        bool const surf     = is_surface[v] != 0;
+        Touch const& first  = touches[i];
+        Touch const& last   = touches[j - 1];
+        for (size_t t = i; t + 1 < j; ++t)
+            if (touches[t + 1].colour == touches[t].colour)
             {
                 out.why_not = "two clusters of one colour touch the same vertex";
                 return false;
             }
-            uint32_t const surface       = (cp.vertex_meta[v] & 0x100u) ? kRouteSurfaceBit : 0u;
-            bool const local = cp.banks == 2 && t + 1 < j && touches[t + 1].colour == touches[t].colour + 1 &&
-                               cluster_region[touches[t + 1].box % static_cast<uint32_t>(Q)] ==
-                                   cluster_region[touches[t].box % static_cast<uint32_t>(Q)];
-            if (local)
-            {
-                out.to[touches[t].box]             = local_route(touches[t + 1].box);
-                out.to_owner[touches[t].box]       = local_route(touches[t + 1].box) | surface;
-                out.local_prev[touches[t + 1].box] = 1;
-                ++out.n_local;
-                continue;
-            }
-            out.to[touches[t].box]       = entry_route(t + 1 < j ? touches[t + 1].box : touches[i].box);
-            out.to_owner[touches[t].box] = (t + 1 < j ? entry_route(touches[t + 1].box) : owner_route(pos)) | surface;
+        out.osv_meta[osv_pos[v]]  = static_cast<uint32_t>(last.colour) | (surf ? kOsvSurface : 0u) |
+                                   (last.region != owner ? kOsvLastRemote : 0u) |
+                                   (first.region != owner ? kOsvFirstRemote : 0u);
+        out.osv_first[osv_pos[v]] = entry_route(first);
+        for (size_t t = i; t < j; ++t)
+        {
+            Touch const& me     = touches[t];
+            uint32_t const slot = slot_of(me.region, v);
+            for (int later = 0; later < 2; ++later)
+                for (int cs = 0; cs < 2; ++cs)
+                { // the previous touch: a colour of the same sweep, the owner's collision step, the last colour of
+                  // the previous sweep, or the owner's predict step
+                    int32_t from, d;
+                    if (t > i)
+                    {
+                        from = touches[t - 1].region;
+                        d    = me.colour - touches[t - 1].colour;
+                    }
+                    else if (cs && surf)
+                    {
+                        from = owner;
+                        d    = me.colour + 1;
+                    }
+                    else if (later)
+                    {
+                        from = last.region;
+                        d    = C + cs + me.colour - last.colour;
+                    }
+                    else
+                    {
+                        from = owner;
+                        d    = static_cast<int32_t>(kPullPredict);
+                    }
+                    if (from != me.region)
+                    {
+                        pulls[static_cast<size_t>(2 * later + cs) * nx + me.xq].push_back(
+                            kPullValid | (me.entry << 24) | (static_cast<uint32_t>(d) << 16) | slot);
+                        ++out.n_pulls[2 * later + cs];
+                        if (later && !cs)
+                        {
+                            colour_pulls[static_cast<size_t>(me.colour)] = 1;
+                            ++out.pulls_by_colour[static_cast<size_t>(me.colour)];
+                        }
+                    }
+                }
+            for (int final_sweep = 0; final_sweep < 2; ++final_sweep)
+                for (int cs = 0; cs < 2; ++cs)
+                { // the next touch: a colour of the same sweep, the owner (collision step of the next sweep, or
+                  // commit), or the first colour of the next sweep
+                    int32_t to;
+                    uint32_t route;
+                    if (t + 1 < j)
+                    {
+                        to    = touches[t + 1].region;
+                        route = entry_route(touches[t + 1]);
+                    }
+                    else if ((cs && surf) || final_sweep)
+                    {
+                        to    = owner;
+                        route = owner_route(v);
+                    }
+                    else
+                    {
+                        to    = first.region;
+                        route = entry_route(first);
+                    }
+                    if (to != me.region)
+                    {
+                        auto& w = pushes[static_cast<size_t>(2 * final_sweep + cs) * nx + me.xq];
+                        w.push_back(kPullValid | slot);
+                        w.push_back(route);
+                        ++out.n_pushes[2 * final_sweep + cs];
+                    }
+                }
         }
         i = j;
     }
-    return true;
-}
-
-bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& rp)
-{
-    int64_t const T = scene.n_tets(), Q = cp.n_clusters;
-    if (!cp.why_not.empty() || cp.nt <= 0 || cp.nvc <= 0 || cp.nvc % 4 != 0 || cp.nvc > kMaxClusterVertices ||
-        cp.rot < 0 || cp.rot >= cp.nt)
-        return false;
-    if (static_cast<int64_t>(cp.tet_slots.size()) != 4 * T ||
-        static_cast<int64_t>(cp.cl_fetch.size()) != static_cast<int64_t>(cp.nvc) * Q)
-        return false;
-    if (cp.banks < 1 || cp.banks > 2)
-        return false;
-    // tet slots name bank 0 of the scratch slots; resident vertices follow the last bank
-    uint32_t const scratch = static_cast<uint32_t>(cp.banks * cp.nvc) * static_cast<uint32_t>(cp.nt);
-    int64_t clusters_seen  = 0;
-    for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
-    {
-        ChunkDesc const& d = cp.chunks[ch];
-        int32_t const reg  = static_cast<int32_t>((ch / 2) % static_cast<size_t>(cp.n_regions));
-        int32_t const part = static_cast<int32_t>(ch % 2);
-        if (d.cfirst != clusters_seen)
-            return false;
-        clusters_seen += d.n[0];
-        for (int32_t i = 0; i < d.n[0]; ++i)
+    for (int32_t c = 0; c < C; ++c)
+        out.quiet_steps += !colour_pulls[static_cast<size_t>(c)];
+    size_t const E = static_cast<size_t>(out.entries);
+    out.pull.assign(4 * E * static_cast<size_t>(nx), 0u);
+    out.push.assign(4 * 2 * E * static_cast<size_t>(nx), 0u);
+    for (size_t var = 0; var < 4; ++var)
+        for (int64_t xq = 0; xq < nx; ++xq)
         {
-            int64_t const q      = d.cfirst + i;
-            uint32_t const thread = static_cast<uint32_t>((i + cp.rot) % cp.nt); // part A comes first in its step
-            bool any_fetch        = false;
-            for (int k = 0; k < cp.nvc; ++k)
+            auto const& pl = pulls[var * static_cast<size_t>(nx) + xq];
+            for (size_t k = 0; k < pl.size(); ++k) // [variant][k / 4][xq][k % 4]
+                out.pull[((var * (E / 4) + k / 4) * static_cast<size_t>(nx) + xq) * 4 + k % 4] = pl[k];
+            auto const& ps = pushes[var * static_cast<size_t>(nx) + xq];
+            for (size_t k = 0; k < ps.size() / 2; ++k) // [variant][k / 2][xq][2 * (k % 2) ..]
             {
-                uint32_t const v = cp.cl_fetch[static_cast<size_t>(k) * Q + q];
-                if (v == 0xffffffffu)
-                    continue;
-                any_fetch = true;
-                if (v >= rp.vertex_region.size() || rp.vertex_region[v] == reg)
-                    return false; // resident vertices must not be fetched
-            }
-            if (any_fetch != (part == 0))
-                return false;
-            int64_t base = d.first;
-            for (int m = 0; m < kMaxCluster && i < d.n[m]; ++m)
-            {
-                int64_t const pos = base + i;
-                uint32_t const t  = cp.storage_order[static_cast<size_t>(pos)];
-                for (int a = 0; a < 4; ++a)
-                {
-                    uint32_t const v    = scene.tets[4 * static_cast<size_t>(t) + a];
-                    uint32_t const slot = cp.tet_slots[4 * static_cast<size_t>(pos) + a];
-                    if (slot >= scratch)
-                    { // resident slot of this region
-                        int64_t const at = rp.region_vtx_offsets[static_cast<size_t>(reg)] + (slot - scratch);
-                        if (rp.vertex_region[v] != reg || at >= rp.region_vtx_offsets[static_cast<size_t>(reg) + 1] ||
-                            rp.region_vtx[static_cast<size_t>(at)] != v)
-                            return false;
-                    }
-                    else
-                    { // scratch entry k of the thread that runs this cluster
-                        uint32_t const k = slot / static_cast<uint32_t>(cp.nt);
-                        if (slot % static_cast<uint32_t>(cp.nt) != thread || k >= static_cast<uint32_t>(cp.nvc) ||
-                            cp.cl_fetch[static_cast<size_t>(k) * Q + q] != v)
-                            return false;
-                    }
-                }
-                base += d.n[m];
+                size_t const at = ((var * (E / 2) + k / 2) * static_cast<size_t>(nx) + xq) * 4 + 2 * (k % 2);
+                out.push[at]     = ps[2 * k];
+                out.push[at + 1] = ps[2 * k + 1];
             }
         }
+
+    // ---- surface vertices by owner -----------------------------------------------------------------------
+    std::vector<uint32_t> sgv; // global vertex of surface vertex i (the order of DeviceScene::surf_v)
+    for (HostBody const& hb : scene.bodies)
+        if (hb.kind == BodyKind::tet)
+            for (uint32_t lv : hb.surf_to_tet)
+                sgv.push_back(static_cast<uint32_t>(hb.v_offset + lv));
+    out.surf_off.assign(static_cast<size_t>(Rn) + 1, 0);
+    for (uint32_t gv : sgv)
+        ++out.surf_off[static_cast<size_t>(plan.vertex_owner[gv]) + 1];
+    for (int32_t r = 0; r < Rn; ++r)
+        out.surf_off[static_cast<size_t>(r) + 1] += out.surf_off[static_cast<size_t>(r)];
+    out.surf_slot.assign(sgv.size(), 0);
+    out.surf_index.assign(sgv.size(), 0);
+    out.surf_osv.assign(sgv.size(), kRouteNone);
+    {
+        std::vector<int32_t> cur(out.surf_off.begin(), out.surf_off.end() - 1);
+        for (size_t s = 0; s < sgv.size(); ++s)
+        {
+            uint32_t const gv = sgv[s];
+            int32_t const at  = cur[static_cast<size_t>(plan.vertex_owner[gv])]++;
+            out.surf_slot[static_cast<size_t>(at)]  = owner_slot[gv];
+            out.surf_index[static_cast<size_t>(at)] = static_cast<uint32_t>(s);
+            out.surf_osv[static_cast<size_t>(at)]   = osv_pos[gv];
+        }
     }
-    return clusters_seen == Q;
+    return true;
 }
 
 bool cluster_plan_is_valid(HostScene const& scene, ClusterPlan const& plan)

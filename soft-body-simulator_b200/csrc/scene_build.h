@@ -131,25 +131,24 @@ struct ChunkDesc
 };                          // tet j of cluster i (clusters sorted by size, descending) is stored at
                             // first + n[0] + ... + n[j-1] + i  ("column" layout: coalesced per j)
 
-// Layout parameters of the resident (persistent) schedule; see xpbd_persistent.cuh.
+// Layout parameters of the resident schedule; see xpbd_resident.cuh.
 struct ResidentParams
 {
-    int64_t smem_bytes   = 0; // shared memory available to one CTA
+    int64_t smem_bytes   = 0;  // shared memory available to one CTA for vertices
     int32_t vertex_bytes = 16; // sizeof(Real4<R>)
     int32_t max_threads  = 512;
-    // EXPERIMENTAL, off by default (development knobs SBSB200_HANDOFF / SBSB200_SLABS):
-    bool handoff         = false; // shared vertices go from one cluster to the next through shared memory when both
-                                  // belong to the same region and run in consecutive steps (two banks of scratch
-                                  // slots), and the colours are ordered so that most consecutive touches do
-    bool slabs           = false; // regions = layers of clusters along the longest axis of the cluster grid (at most
-                                  // one region per layer) instead of compact Morton blocks: with the hand-off and the
-                                  // colour order that goes with it, most steps then depend on no other region at all
-    bool rotate_items    = true;  // part A clusters on the warps with a sub-partition to themselves (item_rotation)
+    bool rotate_items    = true; // clusters that exchange vertices on the warps with a sub-partition to themselves
+    bool pencils         = true; // regions = bundles of whole cluster columns along the shortest axis of the cluster
+                                 // grid (compact in the two other axes) instead of compact Morton blocks: with the
+                                 // colour order that goes with it (a Gray code of the cell parities on a lattice)
+                                 // every step that flips the parity along the pencil axis depends on no other region
+    int32_t bodies_per_region = 0; // ensembles (one_region_per_body): consecutive bodies grouped into one region so
+                                   // that a colour step fills its warps; 0 = choose (about 160 clusters per step)
 };
 
 // Which thread runs cluster i of a (colour, region) step.  Warp w of a CTA issues on sub-partition w % 4,
 // so with W = nt / 32 warps the sub-partitions W % 4 .. 3 hold one warp less than the others.  The
-// clusters that exchange vertices with other regions (part A, first in a step) carry the polls and
+// clusters that exchange vertices with other regions (part 0, first in a step) carry the polls and
 // pushes on top of the projections: they go to the warps that have a sub-partition to themselves,
 // i.e. the numbering of a step's clusters starts at warp W % 4 (measured: profiles/r01_summary.md).
 inline int32_t item_rotation(int32_t nt)
@@ -165,34 +164,23 @@ struct ClusterPlan
     int64_t n_clusters = 0;
     std::vector<uint32_t> storage_order; // storage position -> tet (index into HostScene::tets / 4)
     std::vector<uint32_t> serial_order;  // equivalent serial order of tets (colour, region, part, cluster, tet)
-    // [(colour * n_regions + region) * 2 + part]; part 0 = clusters that fetch vertices from global
-    // memory (shared with other regions, or not resident), part 1 = clusters whose vertices are all
-    // resident in the region's shared memory.  Without a region plan everything is in part 1.
+    // [(colour * n_regions + region) * 2 + part]; part 0 = clusters with a vertex that another region touches
+    // too (they exchange it through mailboxes), part 1 = clusters private to the region.  Without a region
+    // plan everything is in part 1.
     std::vector<ChunkDesc> chunks;
     std::vector<int32_t> tet_region;     // T
     int64_t max_chunk_clusters = 0;      // max over (colour, region) of the clusters of both parts
     // resident schedule only
-    int32_t nt  = 0;                     // threads per CTA the scratch slots were laid out for
-    int32_t rot = 0;                     // cluster i of a step (part A first) runs on thread (i + rot) % nt, see item_rotation
-    int32_t banks = 1;                   // banks of scratch slots: 2 = the cluster of step p uses bank p % 2, so that a
-                                         // cluster may WRITE a shared vertex straight into the scratch slot of the
-                                         // cluster of the same region that touches it in the next step (hand-off);
-                                         // tet slots name bank 0, resident vertices start at banks * nvc * nt
-    int32_t nvc = 0;                     // scratch entries per thread (multiple of 4, <= kMaxClusterVertices)
-    std::vector<uint16_t> tet_slots;     // 4*T (storage order): index into the CTA's shared vertex array
-    std::vector<uint32_t> cl_fetch;      // [nvc][n_clusters]: global vertex of scratch entry k, 0xffffffff = none
-    // touch schedule for the tag protocol: per vertex  bits 0-7 = last colour touching it (0xff none),
-    // bit 8 = surface vertex; per fetch entry four bytes "steps back to the previous touch" for
-    // the four kinds of colour step (byte 2*(iteration > 0) + collision steps present), 0xff = the
-    // predict step
-    std::vector<uint32_t> vertex_meta;   // V
-    std::vector<uint32_t> cl_meta;       // [nvc][n_clusters]
+    int32_t nt  = 0;                     // threads per CTA
+    int32_t rot = 0;                     // cluster i of a step (part 0 first) runs on thread (i + rot) % nt, see item_rotation
     std::string why_not;                 // non-empty when the resident layout could not be built
 };
 
 // n_regions <= 1 and no `resident`: no partition (graph schedule).  Otherwise clusters are dealt to
-// regions in (body, Morton) order with balanced tet counts, or one region per body; with
-// `resident` the vertex classification (RegionPlan) and the shared-memory layout are built too.
+// regions with balanced tet counts — pencils (ResidentParams::pencils) or (body, Morton) order — or, for
+// ensembles, whole bodies per region; with `resident` the vertex classification (RegionPlan), the parts and
+// the launch shape are built too, and the colours are renumbered so that consecutive colours hand a shared
+// vertex over inside a region as often as possible.
 void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_region_per_body,
                         ClusterPlan& out, ResidentParams const* resident = nullptr,
                         RegionPlan* region_plan = nullptr);
@@ -201,7 +189,7 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
 // How many regions to cut a scene into: one per SM of every rank, but at least ~64 clusters per
 // colour step and region (small scenes use fewer SMs rather than synchronise regions of a few tets).
 // Always a multiple of `world`: rank r runs the block of consecutive regions [r, r + 1) * n / world,
-// which is spatially compact because regions follow the Morton order of the clusters.
+// which is spatially compact because regions follow a space-filling order of the clusters.
 inline int32_t regions_for(int sm_count, int64_t n_tets, int world = 1)
 {
     int64_t per_rank = n_tets / (world > 0 ? world : 1) / 2560;
@@ -213,44 +201,69 @@ inline int32_t region_rank(int32_t region, int32_t n_regions, int32_t world)
     return region / (n_regions / world);
 }
 
-// ---- mailboxes of the resident schedule (xpbd_persistent.cuh) -----------------------------------
-// Entry (j, q) = scratch slot j of cluster q has mailbox j * Q + q (Q = number of clusters); owned
-// non-resident vertex i (position in `ifv`) has mailbox n_entries + i.  Per vertex the entries are
-// ordered by the colour of their cluster: each pushes to the next one; the last one pushes to the
-// first one (next sweep) or to the owner (collision step, commit).  Routing words carry the mailbox
-// index (bits 0-27) and the rank whose memory holds it (bits 28-30); bit 31 of `to_owner` marks
-// surface vertices.
+// ---- the resident schedule's exchange plan (xpbd_resident.cuh) ------------------------------------
+// Every region keeps ONE shared-memory slot for every vertex its tets touch: the vertices it owns (it predicts,
+// collides and commits them) first, then its guests (owned by another region).  A vertex that only one region
+// touches never leaves that region's shared memory during a substep.  A SHARED vertex (touched by several
+// regions) travels: whoever touches it knows, statically, who touched it before and who touches it next —
+// touches are: predict (owner), per iteration [the collision step (owner, surface vertices, when collision steps
+// exist)] and the colours of the clusters that contain it, commit (owner).  When the next touch is by another
+// region the position is PUSHED into a mailbox of that region, tagged with the step; when the previous touch was
+// by another region the position is PULLED (polled for the expected tag) out of the own mailbox into the slot;
+// when both touches are by the same region nothing happens at all — the value stays in the slot.
+//
+// Mailboxes: one per (exchange cluster, entry) — entry = position of the shared vertex among the shared vertices
+// of its cluster — at index entry * n_xclusters + xq, and one per shared vertex for its owner at n_entries + i.
+// Routing words carry the mailbox index (bits 0-27) and the rank whose memory holds it (bits 28-30).
 constexpr uint32_t kRouteNone       = 0xffffffffu;
 constexpr uint32_t kRouteIndexMask  = 0x0fffffffu;
-constexpr uint32_t kRouteSurfaceBit = 0x80000000u;
 constexpr int kRouteRankShift       = 28;
-// hand-off inside a region (ClusterPlan::banks == 2): bit 27 set, bits 0-26 = scratch slot (entry * nt + thread)
-// of the cluster that touches the vertex in the next step; mailbox indices then stay below 2^27
-constexpr uint32_t kRouteLocalBit       = 0x08000000u;
-constexpr uint32_t kRouteLocalIndexMask = 0x07ffffffu;
-constexpr uint32_t kMetaLocal           = 0xfefefefeu; // cl_meta of an entry that arrives by hand-off: nothing to poll
+// pull word: bit 31 valid, bits 24-27 entry, bits 16-23 steps back to the previous touch (0xff = the predict
+// step), bits 0-15 slot.  push words: {bit 31 valid | slot, routing word}
+constexpr uint32_t kPullValid      = 0x80000000u;
+constexpr uint32_t kPullPredict    = 0xffu;
+// owned shared vertex (ExchangePlan::osv), meta word
+constexpr uint32_t kOsvSurface     = 0x100u; // takes part in the collision steps
+constexpr uint32_t kOsvLastRemote  = 0x200u; // the last colour touching it in a sweep belongs to another region
+constexpr uint32_t kOsvFirstRemote = 0x400u; // the first one does
 
-struct MailboxRoutes
+struct ExchangePlan
 {
-    uint32_t n_entries = 0;             // nvc * Q
-    std::vector<int32_t> ifv_offsets;   // [n_regions + 1] into ifv: vertices a region owns that are not resident
-    std::vector<uint32_t> ifv;          // global vertex ids
-    std::vector<uint32_t> ifv_meta;     // ClusterPlan::vertex_meta of those
-    std::vector<uint32_t> ifv_first;    // routing word of the first entry touching the vertex in a sweep
-    std::vector<uint32_t> ifv_pos;      // V: position in ifv, kRouteNone for resident vertices
-    std::vector<uint32_t> to, to_owner; // [nvc][Q] routing words, kRouteNone for unused slots
-    std::vector<uint8_t> local_prev;    // [nvc][Q] 1: the entry is handed over in shared memory by the previous touch
-    int64_t n_local = 0;                // how many
+    int32_t n_regions = 0, n_colours = 0, world = 1;
+    // local vertex tables
+    std::vector<int32_t> loc_off;      // [R + 1] into loc_vtx
+    std::vector<int32_t> n_owned;      // [R] the first n_owned slots of a region are the vertices it owns
+    std::vector<uint32_t> loc_vtx;     // global vertex of slot i
+    std::vector<int32_t> vertex_owner; // [V]
+    int64_t max_local = 0;             // largest table
+    int64_t n_shared  = 0;             // vertices touched by more than one region
+    std::vector<uint16_t> tet_slots;   // 4 * T (storage order): slot in the table of the tet's region
+    // exchange clusters (part 0 of every chunk), numbered in storage order
+    int64_t n_xclusters = 0;
+    std::vector<int32_t> chunk_xfirst; // [colour * R + region]: number of the chunk's first exchange cluster
+    int32_t entries = 0;               // shared vertices per cluster at most, rounded up to a multiple of 4
+    // per variant, COMPACTED (valid words first, then zeros):
+    //   pull variant = 2 * (iteration > 0) + (collision steps present)
+    //   push variant = 2 * (last iteration) + (collision steps present)
+    std::vector<uint32_t> pull;        // [variant][entries / 4][n_xclusters][4]: four pull words per 16-byte record
+    std::vector<uint32_t> push;        // [variant][entries / 2][n_xclusters][4]: {slot word, route, slot word, route}
+    uint32_t n_entries = 0;            // entries * n_xclusters: mailboxes of the clusters
+    // owner side
+    std::vector<int32_t> osv_off;      // [R + 1] shared vertices a region owns
+    std::vector<uint32_t> osv_slot, osv_meta, osv_first; // slot; last colour | kOsv*; routing word of the first
+                                                         // cluster entry touching it in a sweep
+    std::vector<int32_t> surf_off;     // [R + 1] surface vertices a region owns
+    std::vector<uint32_t> surf_slot, surf_index, surf_osv; // slot; surface-vertex index; position in osv or kRouteNone
+    // statistics
+    int64_t n_pulls[4] = {0, 0, 0, 0}, n_pushes[4] = {0, 0, 0, 0};
+    std::vector<int64_t> pulls_by_colour; // [colour], variant: later sweep, no collision steps
+    int32_t quiet_steps = 0;           // colours whose clusters pull nothing in any region (variant: later sweep, no
+                                       // collision steps): steps that wait for no other region
     std::string why_not;
 };
 
-// nvc: scratch entries per thread of the kernel instantiation (>= cp.nvc); world: ranks the scene is cut over
-bool build_mailbox_routes(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& plan, int nvc, int world,
-                          MailboxRoutes& out);
-
-// true when every tet slot of the resident layout resolves to the right vertex (resident slot of
-// its region, or the scratch entry the running thread fetched) and parts are classified correctly
-bool resident_layout_is_valid(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& rp);
+bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPlan const& plan, int world,
+                         ExchangePlan& out);
 
 // true when no two tets of different clusters of one colour share a vertex
 bool cluster_plan_is_valid(HostScene const& scene, ClusterPlan const& plan);

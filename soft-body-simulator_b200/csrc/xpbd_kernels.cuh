@@ -451,9 +451,9 @@ k_surface_pack(DeviceScene<R> s, int64_t first_surface, int64_t n, Real4<R> cons
 
 // Host-format (3 doubles per vertex) <-> device layout.  Upload sets x = xi = xn and keeps the
 // inverse mass (tetrahedral_body_t::transform semantics, tetrahedral_body.cpp:121-132).
-template <typename R>
+template <typename R, typename H>
 __global__ void __launch_bounds__(256)
-k_unpack_state(DeviceScene<R> s, int64_t first, int64_t n, double const* __restrict__ x, double const* __restrict__ v)
+k_unpack_state(DeviceScene<R> s, int64_t first, int64_t n, H const* __restrict__ x, H const* __restrict__ v)
 {
     int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i >= n)
@@ -491,9 +491,20 @@ k_scatter_state(DeviceScene<R> s, int64_t first, int64_t n, uint32_t const* __re
         st4(&s.vel[at], Real4<R>{R(v[3 * i]), R(v[3 * i + 1]), R(v[3 * i + 2]), R(0)});
 }
 
+// particle_t::mass() of a handful of vertices (sbsb200_set_masses): the inverse mass rides in pos[].w
 template <typename R>
 __global__ void __launch_bounds__(256)
-k_pack_state(DeviceScene<R> s, int64_t first, int64_t n, double* __restrict__ x, double* __restrict__ v)
+k_scatter_inverse_mass(DeviceScene<R> s, int64_t first, int64_t n, uint32_t const* __restrict__ which,
+                       R const* __restrict__ w)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n)
+        s.pos[first + which[i]].w = w[i];
+}
+
+template <typename R, typename H>
+__global__ void __launch_bounds__(256)
+k_pack_state(DeviceScene<R> s, int64_t first, int64_t n, H* __restrict__ x, H* __restrict__ v)
 {
     int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i >= n)
@@ -501,16 +512,16 @@ k_pack_state(DeviceScene<R> s, int64_t first, int64_t n, double* __restrict__ x,
     if (x)
     {
         Real4<R> const p = ld4(&s.prev[first + i]);
-        x[3 * i]         = double(p.x);
-        x[3 * i + 1]     = double(p.y);
-        x[3 * i + 2]     = double(p.z);
+        x[3 * i]         = H(p.x);
+        x[3 * i + 1]     = H(p.y);
+        x[3 * i + 2]     = H(p.z);
     }
     if (v)
     {
         Real4<R> const q = ld4(&s.vel[first + i]);
-        v[3 * i]         = double(q.x);
-        v[3 * i + 1]     = double(q.y);
-        v[3 * i + 2]     = double(q.z);
+        v[3 * i]         = H(q.x);
+        v[3 * i + 1]     = H(q.y);
+        v[3 * i + 2]     = H(q.z);
     }
 }
 

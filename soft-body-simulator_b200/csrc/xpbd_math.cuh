@@ -229,6 +229,11 @@ struct PolarSteps<double>
     static constexpr double max_e2n = 2.25;
 };
 
+// how often the general route ran on this device (debug counter behind sbsb200_stats.green_general_calls)
+#ifdef __CUDACC__
+__device__ unsigned long long g_general_route_calls = 0;
+#endif
+
 // GENERAL route of green_gradients (clamp or inversion active): columns of P and psi from the
 // eigen-decomposition of A = F^T F.  Kept out of line: it is rare, long, and register hungry.
 template <typename R>
@@ -236,6 +241,9 @@ __host__ __device__ __noinline__ void green_general(Vec3<R> c0, Vec3<R> c1, Vec3
                                                     R a02, R a12, bool inverted, R mu, R lam, Vec3<R>& pk0,
                                                     Vec3<R>& pk1, Vec3<R>& pk2, R& psi)
 {
+#ifdef __CUDA_ARCH__
+    atomicAdd(&g_general_route_calls, 1ull);
+#endif
     R const smin = R(0.577);
     R l0, l1, l2;
     Vec3<R> v0, v1, v2;

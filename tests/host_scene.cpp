@@ -95,17 +95,19 @@ extern "C" int hs_cluster_plan(int64_t nV, int64_t nT, const uint32_t* tets, con
     }
     ClusterPlan plan;
     if (smem_bytes > 0)
-    { // resident (persistent) layout: also check the shared-memory slots and fetch lists
+    { // resident layout: the exchange plan must exist and the local vertex tables must fit shared memory
         ResidentParams rp;
         rp.smem_bytes   = smem_bytes;
         rp.vertex_bytes = 16;
         rp.max_threads  = 512;
         RegionPlan regions;
         build_cluster_plan(h, n_regions, per_body != 0, plan, &rp, &regions);
-        if (!plan.why_not.empty() || !resident_layout_is_valid(h, plan, regions))
+        if (!plan.why_not.empty())
             return -2;
-        int64_t scratch = static_cast<int64_t>(plan.nvc) * plan.nt;
-        if ((scratch + regions.max_region_vertices) * rp.vertex_bytes > smem_bytes)
+        ExchangePlan xp;
+        if (!build_exchange_plan(h, plan, regions, 1, xp))
+            return -2;
+        if (xp.max_local * rp.vertex_bytes > smem_bytes)
             return -3;
     }
     else
@@ -146,7 +148,10 @@ extern "C" int hs_partition(int64_t nV, int64_t nT, const uint32_t* tets, const 
     ClusterPlan plan;
     RegionPlan regions;
     build_cluster_plan(h, n_regions, false, plan, &rp, &regions);
-    if (!plan.why_not.empty() || !cluster_plan_is_valid(h, plan) || !resident_layout_is_valid(h, plan, regions))
+    if (!plan.why_not.empty() || !cluster_plan_is_valid(h, plan))
+        return -2;
+    ExchangePlan xp;
+    if (!build_exchange_plan(h, plan, regions, world, xp))
         return -2;
     std::memcpy(tet_region, plan.tet_region.data(), sizeof(int32_t) * plan.tet_region.size());
     for (int32_t r = 0; r < n_regions; ++r)
@@ -154,154 +159,257 @@ extern "C" int hs_partition(int64_t nV, int64_t nT, const uint32_t* tets, const 
     return n_regions;
 }
 
-// mailbox routing of the resident schedule for a single body cut into `n_regions` regions run by
-// `world` ranks.  Outputs (caller-sized with the capacities given): cl_fetch / to / to_owner
-// [nvc * Q], cluster_region[Q], cluster_colour[Q], ifv / ifv_first [n_ifv], vertex_owner[V];
-// dims = {nvc, Q, n_ifv, n_entries}.  Returns 0, -1 (no plan), -2 (no routes), -3 (capacity).
-extern "C" int hs_mailbox_routes(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_regions,
-                                 int world, int64_t cap_entries, int64_t cap_clusters, uint32_t* cl_fetch,
-                                 uint32_t* to, uint32_t* to_owner, int32_t* cluster_region, int32_t* cluster_colour,
-                                 uint32_t* ifv, uint32_t* ifv_first, int32_t* vertex_owner, int64_t* dims)
+// ---------------------------------------------------------------------------------------------------------
+// Emulation of the resident schedule's exchange protocol (xpbd_resident.cuh) on the CPU, with an order-
+// sensitive integer "projection": every region keeps its local vertex table, pulls and pushes exactly what
+// the exchange plan says, phase by phase, and the result must equal the plain serial sweep in the exported
+// order.  Checks on the way: a pull finds exactly the expected tag, a push never overwrites a record nobody
+// consumed, a routing word names the rank that runs the reading region.
+// `n_bodies` copies of the body (laid out along x); per_body: ensemble mode.  reverse: regions are visited
+// in reverse order inside a phase (the protocol must not depend on it).
+// Returns 0, or a negative code; stats = {regions, colours, exchange clusters, entries, shared vertices,
+// pulls (later sweep, no collision steps), pushes (same), quiet steps, max_local, threads}.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+inline uint64_t mix(uint64_t a, uint64_t b)
 {
-    HostScene h;
-    h.x0.assign(x0, x0 + 3 * nV);
-    h.mass.assign(static_cast<size_t>(nV), 1.0);
-    h.tets.assign(tets, tets + 4 * nT);
-    for (int64_t t = 0; t < nT; ++t)
-    {
-        h.tet_insertion.push_back(h.n_constraints++);
-        h.tet_material.push_back(0);
-    }
-    HostBody b;
-    b.n_vertices = nV;
-    b.n_tets     = nT;
-    extract_boundary(nV, nT, tets, b.surf_to_tet, &b.surf_triangles);
-    h.bodies.push_back(b);
-    ResidentParams rp;
-    rp.smem_bytes = 200 * 1024;
-    ClusterPlan plan;
-    RegionPlan regions;
-    build_cluster_plan(h, n_regions, false, plan, &rp, &regions);
-    if (!plan.why_not.empty())
-        return -1;
-    MailboxRoutes routes;
-    if (!build_mailbox_routes(h, plan, regions, plan.nvc, world, routes))
-        return -2;
-    int64_t const Q = plan.n_clusters;
-    if (routes.n_entries > cap_entries || Q > cap_clusters || static_cast<int64_t>(routes.ifv.size()) > nV)
-        return -3;
-    std::memcpy(cl_fetch, plan.cl_fetch.data(), sizeof(uint32_t) * routes.n_entries);
-    std::memcpy(to, routes.to.data(), sizeof(uint32_t) * routes.n_entries);
-    std::memcpy(to_owner, routes.to_owner.data(), sizeof(uint32_t) * routes.n_entries);
-    for (size_t ch = 0; ch < plan.chunks.size(); ++ch)
-        for (int32_t i = 0; i < plan.chunks[ch].n[0]; ++i)
-        {
-            cluster_colour[plan.chunks[ch].cfirst + i] = static_cast<int32_t>(ch / (2 * static_cast<size_t>(n_regions)));
-            cluster_region[plan.chunks[ch].cfirst + i] = static_cast<int32_t>((ch / 2) % static_cast<size_t>(n_regions));
-        }
-    std::memcpy(ifv, routes.ifv.data(), sizeof(uint32_t) * routes.ifv.size());
-    std::memcpy(ifv_first, routes.ifv_first.data(), sizeof(uint32_t) * routes.ifv.size());
-    std::memcpy(vertex_owner, regions.vertex_owner.data(), sizeof(int32_t) * static_cast<size_t>(nV));
-    dims[0] = plan.nvc;
-    dims[1] = Q;
-    dims[2] = static_cast<int64_t>(routes.ifv.size());
-    dims[3] = routes.n_entries;
-    return 0;
+    uint64_t z = a * 0x9e3779b97f4a7c15ull + (b ^ (b >> 29)) + 0x7f4a7c15ull;
+    z          = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z          = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
 }
+struct Box
+{
+    uint64_t value = 0;
+    uint32_t tag   = 0;
+    bool consumed  = true;
+};
+} // namespace
 
-// EXPERIMENTAL hand-off inside a region (ResidentParams::handoff, optionally with slab-shaped regions): plan a
-// single lattice body, build the routes and check every local routing word: it must name the scratch slot
-// (entry * nt + thread) of the cluster of the SAME region and the NEXT colour that fetches the same vertex, and
-// exactly those entries must be marked "arrives by hand-off".  Returns the number of local hand-offs, or a
-// negative error code; n_remote = touches that still go through a mailbox; steps_without_remote = colour steps
-// (colour, region) none of whose clusters polls a mailbox filled by another region... counted as colours for
-// which NO entry of ANY region has a remote previous touch inside the sweep.
-extern "C" int64_t hs_handoff_check(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_regions,
-                                    int world, int slabs, int64_t* n_remote, int32_t* n_colours, int32_t* n_regions_out,
-                                    int32_t* colours_without_remote)
+extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_bodies,
+                                   int n_regions, int world, int per_body, int iterations, int collide, int reverse,
+                                   int pencils, int64_t* stats)
 {
     HostScene h;
-    h.x0.assign(x0, x0 + 3 * nV);
-    h.mass.assign(static_cast<size_t>(nV), 1.0);
-    h.tets.assign(tets, tets + 4 * nT);
-    for (int64_t t = 0; t < nT; ++t)
+    for (int b = 0; b < n_bodies; ++b)
     {
-        h.tet_insertion.push_back(h.n_constraints++);
-        h.tet_material.push_back(0);
+        HostBody hb;
+        hb.v_offset   = h.n_vertices();
+        hb.n_vertices = nV;
+        hb.t_offset   = h.n_tets();
+        hb.n_tets     = nT;
+        for (int64_t i = 0; i < nV; ++i)
+        {
+            h.x0.push_back(x0[3 * i] + 1000.0 * b);
+            h.x0.push_back(x0[3 * i + 1]);
+            h.x0.push_back(x0[3 * i + 2]);
+            h.mass.push_back(1.0);
+        }
+        for (int64_t t = 0; t < nT; ++t)
+        {
+            for (int a = 0; a < 4; ++a)
+                h.tets.push_back(static_cast<uint32_t>(hb.v_offset + tets[4 * t + a]));
+            h.tet_insertion.push_back(h.n_constraints++);
+            h.tet_material.push_back(0);
+        }
+        extract_boundary(nV, nT, tets, hb.surf_to_tet, &hb.surf_triangles);
+        h.bodies.push_back(hb);
     }
-    HostBody b;
-    b.n_vertices = nV;
-    b.n_tets     = nT;
-    extract_boundary(nV, nT, tets, b.surf_to_tet, &b.surf_triangles);
-    h.bodies.push_back(b);
     ResidentParams rp;
     rp.smem_bytes = 200 * 1024;
-    rp.handoff    = true;
-    rp.slabs      = slabs != 0;
-    ClusterPlan plan;
+    rp.pencils    = pencils != 0;
+    ClusterPlan cp;
     RegionPlan regions;
-    build_cluster_plan(h, n_regions, false, plan, &rp, &regions);
-    if (!plan.why_not.empty() || plan.banks != 2)
+    build_cluster_plan(h, n_regions, per_body != 0, cp, &rp, &regions);
+    if (!cp.why_not.empty() || !cluster_plan_is_valid(h, cp))
         return -1;
-    if (!cluster_plan_is_valid(h, plan) || !resident_layout_is_valid(h, plan, regions))
+    ExchangePlan xp;
+    if (!build_exchange_plan(h, cp, regions, world, xp))
         return -2;
-    MailboxRoutes routes;
-    if (!build_mailbox_routes(h, plan, regions, plan.nvc, world, routes))
+    int32_t const Rn = cp.n_regions, C = cp.n_colours, K = iterations, cs = collide ? 1 : 0;
+    int64_t const V = h.n_vertices(), NX = xp.n_xclusters;
+    if (Rn % world != 0)
         return -3;
-    *n_colours     = plan.n_colours;
-    *n_regions_out = plan.n_regions;
-    int32_t const Rn = plan.n_regions;
-    int64_t const Q = plan.n_clusters;
-    std::vector<int32_t> colour(static_cast<size_t>(Q)), region(static_cast<size_t>(Q)), item(static_cast<size_t>(Q));
-    for (size_t ch = 0; ch < plan.chunks.size(); ++ch)
-        for (int32_t i = 0; i < plan.chunks[ch].n[0]; ++i)
-        {
-            size_t const q = static_cast<size_t>(plan.chunks[ch].cfirst + i);
-            colour[q]      = static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
-            region[q]      = static_cast<int32_t>((ch / 2) % static_cast<size_t>(Rn));
-            item[q]        = i;
-        }
-    // consumer lookup: (region, colour, entry, vertex) -> cluster
-    int64_t local = 0, marked = 0, remote = 0;
-    std::vector<char> colour_has_remote(static_cast<size_t>(plan.n_colours), 0);
-    for (uint32_t box = 0; box < routes.n_entries; ++box)
+    std::vector<char> surface(static_cast<size_t>(V), 0);
+    for (HostBody const& hb : h.bodies)
+        for (uint32_t lv : hb.surf_to_tet)
+            surface[static_cast<size_t>(hb.v_offset + lv)] = 1;
+
+    // ---- serial sweep in the exported order
+    auto project = [](uint64_t* p[4], uint64_t t) {
+        uint64_t const hsh = mix(mix(mix(*p[0], *p[1]), mix(*p[2], *p[3])), t);
+        for (int a = 0; a < 4; ++a)
+            *p[a] = mix(*p[a], hsh + static_cast<uint64_t>(a));
+    };
+    std::vector<uint64_t> ref(static_cast<size_t>(V));
+    for (int64_t v = 0; v < V; ++v)
+        ref[static_cast<size_t>(v)] = mix(static_cast<uint64_t>(v), 1);
+    for (int k = 0; k < K; ++k)
     {
-        marked += routes.local_prev[box];
-        uint32_t const v = plan.cl_fetch[box];
-        if (v == 0xffffffffu)
-            continue;
-        size_t const q = box % static_cast<size_t>(Q);
-        if (!routes.local_prev[box] && colour[q] > 0)
-            colour_has_remote[static_cast<size_t>(colour[q])] = 1; // polls a mailbox in the middle of a sweep
-        uint32_t const word = routes.to[box];
-        if (!(word & kRouteLocalBit))
+        if (cs)
+            for (int64_t v = 0; v < V; ++v)
+                if (surface[static_cast<size_t>(v)])
+                    ref[static_cast<size_t>(v)] = mix(ref[static_cast<size_t>(v)], 77u + static_cast<uint64_t>(k));
+        for (uint32_t t : cp.serial_order)
         {
-            ++remote;
-            continue;
+            uint64_t* p[4];
+            for (int a = 0; a < 4; ++a)
+                p[a] = &ref[h.tets[4 * static_cast<size_t>(t) + a]];
+            project(p, t);
         }
-        if ((routes.to_owner[box] & ~kRouteSurfaceBit) != word)
-            return -5;
-        ++local;
-        uint32_t const idx = word & kRouteLocalIndexMask, thread = idx % plan.nt, entry = idx / plan.nt;
-        if (entry >= static_cast<uint32_t>(plan.nvc))
-            return -10;
-        // the consumer runs on `thread` in the next colour step of the same region: its position in the step
-        int32_t const want_item = static_cast<int32_t>((thread + plan.nt - plan.rot) % plan.nt);
-        size_t const chA = (static_cast<size_t>(colour[q] + 1) * Rn + region[q]) * 2; // part A chunk of that step
-        if (colour[q] + 1 >= plan.n_colours || want_item >= plan.chunks[chA].n[0])
-            return -6;
-        size_t const q2 = static_cast<size_t>(plan.chunks[chA].cfirst + want_item);
-        if (plan.cl_fetch[static_cast<size_t>(entry) * Q + q2] != v)
-            return -8;
-        if (!routes.local_prev[static_cast<size_t>(entry) * Q + q2])
-            return -7;
     }
-    if (marked != local)
-        return -9;
-    *n_remote = remote;
-    int32_t free_colours = 0;
-    for (int32_t c = 1; c < plan.n_colours; ++c)
-        free_colours += !colour_has_remote[static_cast<size_t>(c)];
-    *colours_without_remote = free_colours;
-    return local;
+
+    // ---- the regions, phase by phase
+    uint32_t const base = 1;
+    int32_t const per_iteration = C + cs, n_phases = 2 + K * per_iteration;
+    std::vector<std::vector<Box>> box(static_cast<size_t>(world),
+                                      std::vector<Box>(static_cast<size_t>(xp.n_entries) + static_cast<size_t>(xp.n_shared)));
+    std::vector<std::vector<uint64_t>> sx(static_cast<size_t>(Rn));
+    std::vector<uint64_t> result(static_cast<size_t>(V), 0);
+    int error = 0;
+    auto rank_of = [&](int32_t r) { return static_cast<uint32_t>(region_rank(r, Rn, world)); };
+    auto push    = [&](int32_t /*from*/, uint32_t route, uint64_t value, uint32_t tag) {
+        uint32_t const rank = route >> kRouteRankShift & 7u, index = route & kRouteIndexMask;
+        if (rank >= static_cast<uint32_t>(world) || index >= box[rank].size())
+        {
+            error = -10;
+            return;
+        }
+        Box& b = box[rank][index];
+        if (!b.consumed)
+            error = -11; // overwrites a record nobody read
+        b = Box{value, tag, false};
+    };
+    auto pull = [&](int32_t region, uint32_t index, uint32_t expect) -> uint64_t {
+        Box& b = box[rank_of(region)][index];
+        if (b.tag != expect || b.consumed)
+            error = -12; // the expected record is not there
+        b.consumed = true;
+        return b.value;
+    };
+    auto last_colour_tag = [&](int32_t k, uint32_t lastc) {
+        return base + 1u + static_cast<uint32_t>(k * per_iteration + cs) + lastc;
+    };
+    for (int32_t r = 0; r < Rn; ++r)
+        sx[static_cast<size_t>(r)].assign(static_cast<size_t>(xp.loc_off[r + 1] - xp.loc_off[r]), 0xdeadbeefdeadbeefull);
+    for (int32_t p = 0; p < n_phases && !error; ++p)
+    {
+        uint32_t const tag = base + static_cast<uint32_t>(p);
+        int32_t const k = p == 0 ? 0 : (p - 1) / per_iteration, q = p == 0 ? 0 : (p - 1) % per_iteration;
+        for (int32_t rr = 0; rr < Rn && !error; ++rr)
+        {
+            int32_t const r = reverse ? Rn - 1 - rr : rr;
+            std::vector<uint64_t>& s = sx[static_cast<size_t>(r)];
+            uint32_t const* loc      = &xp.loc_vtx[static_cast<size_t>(xp.loc_off[r])];
+            if (p == 0)
+            { // predict
+                for (int32_t i = 0; i < xp.n_owned[r]; ++i)
+                    s[static_cast<size_t>(i)] = mix(loc[i], 1);
+                for (int32_t i = xp.osv_off[r]; i < xp.osv_off[r + 1]; ++i)
+                {
+                    uint32_t const meta = xp.osv_meta[static_cast<size_t>(i)];
+                    bool const to_me    = K == 0 || (cs && (meta & kOsvSurface));
+                    if (!to_me && (meta & kOsvFirstRemote))
+                        push(r, xp.osv_first[static_cast<size_t>(i)], s[xp.osv_slot[static_cast<size_t>(i)]], tag);
+                }
+            }
+            else if (p == n_phases - 1)
+            { // commit
+                for (int32_t i = xp.osv_off[r]; i < xp.osv_off[r + 1]; ++i)
+                {
+                    uint32_t const meta = xp.osv_meta[static_cast<size_t>(i)];
+                    if (K > 0 && (meta & kOsvLastRemote))
+                        s[xp.osv_slot[static_cast<size_t>(i)]] =
+                            pull(r, xp.n_entries + static_cast<uint32_t>(i), last_colour_tag(K - 1, meta & 0xffu));
+                }
+                for (int32_t i = 0; i < xp.n_owned[r]; ++i)
+                    result[loc[i]] = s[static_cast<size_t>(i)];
+            }
+            else if (cs && q == 0)
+            { // collision step: owned surface vertices
+                for (int32_t i = xp.surf_off[r]; i < xp.surf_off[r + 1]; ++i)
+                {
+                    uint32_t const slot = xp.surf_slot[static_cast<size_t>(i)], o = xp.surf_osv[static_cast<size_t>(i)];
+                    uint32_t const meta = o == kRouteNone ? 0u : xp.osv_meta[o];
+                    if (o != kRouteNone && k > 0 && (meta & kOsvLastRemote))
+                        s[slot] = pull(r, xp.n_entries + o, last_colour_tag(k - 1, meta & 0xffu));
+                    if (loc[slot] >= static_cast<uint32_t>(V) || !surface[loc[slot]])
+                        error = -13;
+                    s[slot] = mix(s[slot], 77u + static_cast<uint64_t>(k));
+                    if (o != kRouteNone && (meta & kOsvFirstRemote))
+                        push(r, xp.osv_first[o], s[slot], tag);
+                }
+            }
+            else
+            { // colour step
+                int32_t const c  = q - cs;
+                int pv           = 2 * (k > 0 ? 1 : 0) + cs, qv = 2 * (k == K - 1 ? 1 : 0) + cs;
+                size_t const E   = static_cast<size_t>(xp.entries);
+                for (int part = 0; part < 2; ++part)
+                {
+                    ChunkDesc const& d = cp.chunks[(static_cast<size_t>(c) * Rn + r) * 2 + part];
+                    for (int32_t i = 0; i < d.n[0] && !error; ++i)
+                    {
+                        int64_t const xq = part == 0 ? xp.chunk_xfirst[static_cast<size_t>(c) * Rn + r] + i : -1;
+                        if (part == 0)
+                            for (size_t e = 0; e < E; ++e)
+                            {
+                                uint32_t const w = xp.pull[((pv * (E / 4) + e / 4) * static_cast<size_t>(NX) + xq) * 4 + e % 4];
+                                if (!(w & kPullValid))
+                                    break;
+                                uint32_t const dd = w >> 16 & 0xffu, entry = w >> 24 & 0xfu, slot = w & 0xffffu;
+                                s[slot] = pull(r, static_cast<uint32_t>(entry * NX + xq), dd == kPullPredict ? base : tag - dd);
+                            }
+                        int64_t bse = d.first;
+                        for (int m = 0; m < kMaxCluster && i < d.n[m]; ++m)
+                        {
+                            int64_t const pos = bse + i;
+                            uint32_t const t  = cp.storage_order[static_cast<size_t>(pos)];
+                            uint64_t* pp[4];
+                            for (int a = 0; a < 4; ++a)
+                            {
+                                uint32_t const slot = xp.tet_slots[4 * static_cast<size_t>(pos) + a];
+                                if (slot >= s.size() || loc[slot] != h.tets[4 * static_cast<size_t>(t) + a])
+                                    error = -14;
+                                pp[a] = &s[slot];
+                            }
+                            if (!error)
+                                project(pp, t);
+                            bse += d.n[m];
+                        }
+                        if (part == 0)
+                            for (size_t e = 0; e < E; ++e)
+                            {
+                                size_t const at = ((qv * (E / 2) + e / 2) * static_cast<size_t>(NX) + xq) * 4 + 2 * (e % 2);
+                                uint32_t const w = xp.push[at];
+                                if (!(w & kPullValid))
+                                    break;
+                                push(r, xp.push[at + 1], s[w & 0xffffu], tag);
+                            }
+                    }
+                }
+            }
+        }
+    }
+    if (error)
+        return error;
+    for (int64_t v = 0; v < V; ++v)
+        if (result[static_cast<size_t>(v)] != ref[static_cast<size_t>(v)])
+            return -20;
+    if (stats)
+    {
+        stats[0] = Rn;
+        stats[1] = C;
+        stats[2] = NX;
+        stats[3] = xp.entries;
+        stats[4] = xp.n_shared;
+        stats[5] = xp.n_pulls[2];
+        stats[6] = xp.n_pushes[0];
+        stats[7] = xp.quiet_steps;
+        stats[8] = xp.max_local;
+        stats[9] = cp.nt;
+        for (int32_t c = 0; c < C && c < 16; ++c)
+            stats[10 + c] = xp.pulls_by_colour[static_cast<size_t>(c)];
+    }
+    return 0;
 }

@@ -37,10 +37,8 @@ def hostscene():
     L.hs_regions.restype = C.c_int64
     L.hs_cluster_plan.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int, C.c_int64, u32p, u32p, i32p, i64p,
                                   i64p]
-    L.hs_mailbox_routes.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int64, C.c_int64, u32p, u32p,
-                                    u32p, i32p, i32p, u32p, u32p, i32p, i64p]
-    L.hs_handoff_check.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int, i64p, i32p, i32p, i32p]
-    L.hs_handoff_check.restype = C.c_int64
+    L.hs_exchange_emulate.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, i64p]
     return L
 
 
@@ -149,8 +147,12 @@ def test_clustered_colouring_of_lattices(hostscene, oracle, dims, bodies, region
     cells = serial.reshape(-1, 5) // 5
     assert (cells == cells[:, :1]).all()                      # a cell's 5 tets run back to back ...
     assert (np.diff(serial.reshape(-1, 5), axis=1) == 1).all()  # ... in insertion order
-    if per_body:
-        assert np.array_equal(treg, np.repeat(np.arange(bodies), len(tets)))
+    if per_body:   # ensembles: whole bodies per region, a few consecutive ones so that a colour step fills its warps
+        body_of_tet = np.repeat(np.arange(bodies), len(tets))
+        group = body_of_tet[treg == 0].max() + 1
+        assert np.array_equal(treg, body_of_tet // group)
+        if smem:
+            assert group == 2            # 6x6x17: 72 clusters in the widest colour step of a body
 
 
 def test_clustered_colouring_of_an_irregular_mesh(hostscene):
@@ -189,31 +191,53 @@ def test_clusters_that_exchange_vertices_start_on_the_least_loaded_sub_partition
         assert per_smsp[first_warp % 4] == min(p for p in per_smsp if p > 0) or warps < 4
 
 
-@pytest.mark.parametrize("dims,regions,world,slabs", [((9, 9, 25), 4, 1, 0), ((9, 9, 25), 8, 2, 0),
-                                                      ((21, 21, 51), 39, 1, 0), ((9, 9, 25), 148, 1, 1),
-                                                      ((21, 21, 51), 148, 1, 1)])
-def test_experimental_hand_off_inside_a_region(hostscene, oracle, dims, regions, world, slabs):
-    """EXPERIMENTAL (off by default).  Shared vertices go from one cluster to the next
-    through shared memory when both belong to the same region and run in consecutive steps: every such
-    routing word names the scratch slot of the consumer and exactly the consumers' entries are marked "not
-    polled" (checked inside hs_handoff_check).  With the colours ordered for it about half of the touches of
-    shared vertices are hand-offs; with slab-shaped regions (one layer of cells each) six of the eight touches
-    of an interior vertex are (vertices on the mesh boundary are touched by fewer colours: a touch whose
-    predecessor is not in the very previous step still goes through its mailbox)."""
+EMU_KEYS = "regions colours xclusters entries shared pulls pushes quiet max_local nt".split()
+
+
+def _emulate(hostscene, oracle, dims, bodies, regions, world, per_body, iterations, collide, reverse, pencils):
     pos, tets = oracle.bar_model(*dims)
     tets = np.ascontiguousarray(tets, np.uint32)
     x0 = pos.astype(np.float64)
-    remote, ncol, nreg, free = C.c_int64(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
-    local = hostscene.hs_handoff_check(len(pos), len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), regions,
-                                       world, slabs, C.byref(remote), C.byref(ncol), C.byref(nreg), C.byref(free))
-    assert local > 0, "hand-off check failed with code %d" % local
-    assert ncol.value == 8 and remote.value > 0      # region changes still go through the mailboxes
-    print("regions %d: hand-offs %d, mailbox pushes %d, colours 1..7 without a remote dependency: %d"
-          % (nreg.value, local, remote.value, free.value))
-    assert local > 0.45 * (local + remote.value)
-    if slabs:
-        assert nreg.value == dims[2] - 1             # one region per layer of cells along the longest axis
-        assert local > 0.6 * (local + remote.value)  # interior vertices: 6 of 8 touches per sweep are hand-offs
+    st = np.zeros(26, np.int64)
+    rc = hostscene.hs_exchange_emulate(len(pos), len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), bodies,
+                                       regions, world, per_body, iterations, collide, reverse, pencils,
+                                       st.ctypes.data_as(i64p))
+    return rc, dict(zip(EMU_KEYS, st[:10].tolist())), st[10:18].tolist()
+
+
+@pytest.mark.parametrize("dims,bodies,regions,world,per_body,collide,pencils", [
+    ((9, 9, 25), 1, 8, 1, 0, 0, 1), ((9, 9, 25), 1, 8, 1, 0, 1, 1), ((9, 9, 25), 1, 8, 2, 0, 1, 1),
+    ((9, 9, 25), 1, 12, 4, 0, 1, 0), ((9, 9, 25), 1, 16, 8, 0, 1, 1), ((21, 21, 51), 1, 39, 1, 0, 1, 1),
+    ((5, 4, 7), 2, 3, 1, 0, 1, 1), ((6, 6, 17), 12, 0, 1, 1, 1, 1), ((4, 4, 6), 1, 1, 1, 0, 1, 1)])
+def test_exchange_plan_reproduces_the_serial_sweep(hostscene, oracle, dims, bodies, regions, world, per_body, collide,
+                                                   pencils):
+    """The resident schedule's exchange protocol (scene_build.cpp build_exchange_plan, xpbd_resident.cuh) emulated
+    on the CPU with an order-sensitive integer projection: every region keeps its own vertex table and pulls /
+    pushes exactly what the plan says; a pull must find exactly the expected tag, a push must never overwrite a
+    record nobody consumed, a routing word must name the rank of the reading region, and the result must equal
+    the serial Gauss-Seidel sweep in the exported order — whatever order the regions run in inside a step."""
+    for reverse in (0, 1):
+        rc, st, by_colour = _emulate(hostscene, oracle, dims, bodies, regions, world, per_body, 3, collide, reverse, pencils)
+        assert rc == 0, "emulation failed with code %d" % rc
+    if per_body or regions <= 1:
+        assert st["shared"] == 0 and st["pulls"] == 0 and st["xclusters"] == 0     # islands exchange nothing
+    else:
+        assert st["shared"] > 0 and st["pulls"] == st["pushes"] > 0
+
+
+def test_pencil_regions_leave_half_of_the_colour_steps_without_exchange(hostscene, oracle):
+    """Regions = bundles of cell columns along the shortest axis, colours ordered as a Gray code of the cell
+    parities: the steps that flip the parity along the pencil axis pull (practically) nothing from other
+    regions — only vertices on the mesh boundary, which fewer colours touch, still do.  Compact regions
+    spread the pulls over all eight steps."""
+    rc, st, by_colour = _emulate(hostscene, oracle, (21, 21, 51), 1, 39, 1, 0, 2, 0, 0, 1)
+    assert rc == 0 and st["colours"] == 8
+    quiet = sorted(by_colour)[:4]
+    busy = sorted(by_colour)[4:]
+    assert max(quiet) * 10 < min(busy), by_colour
+    assert [n * 10 < min(busy) for n in by_colour] in ([True, False] * 4, [False, True] * 4)   # every other step
+    rc, st2, by_colour2 = _emulate(hostscene, oracle, (21, 21, 51), 1, 39, 1, 0, 2, 0, 0, 0)
+    assert rc == 0 and min(by_colour2) * 10 > max(by_colour2)
 
 
 def test_colouring_reports_capacity_overflow(hostscene):
@@ -266,72 +290,6 @@ def test_region_plan_partitions_tets_and_classifies_vertices(hostscene, oracle, 
         assert n_if == 0 and nnb[0] == 0
     else:
         assert (nnb > 0).all()
-
-
-@pytest.mark.parametrize("regions,world", [(8, 1), (8, 2), (12, 4), (16, 8)])
-def test_mailbox_routes_chain_every_shared_vertex_through_its_colours(hostscene, oracle, regions, world):
-    """Routing of the resident schedule's mailboxes (scene_build.cpp build_mailbox_routes): per shared
-    vertex the scratch entries that fetch it form one cycle in colour order, the last entry of a sweep
-    hands the vertex to its owner, and every routing word names the rank that reads the mailbox."""
-    pos, tets = oracle.bar_model(9, 9, 25)
-    tets = np.ascontiguousarray(tets, np.uint32)
-    x0 = pos.astype(np.float64)
-    V = len(pos)
-    cap_e, cap_q = 1 << 20, 1 << 16
-    fetch = np.empty(cap_e, np.uint32)
-    to = np.empty(cap_e, np.uint32)
-    to_owner = np.empty(cap_e, np.uint32)
-    creg = np.zeros(cap_q, np.int32)
-    ccol = np.zeros(cap_q, np.int32)
-    ifv = np.empty(V, np.uint32)
-    ifirst = np.empty(V, np.uint32)
-    vowner = np.empty(V, np.int32)
-    dims = np.zeros(4, np.int64)
-    rc = hostscene.hs_mailbox_routes(V, len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), regions, world,
-                                     cap_e, cap_q, fetch.ctypes.data_as(u32p), to.ctypes.data_as(u32p),
-                                     to_owner.ctypes.data_as(u32p), creg.ctypes.data_as(i32p),
-                                     ccol.ctypes.data_as(i32p), ifv.ctypes.data_as(u32p), ifirst.ctypes.data_as(u32p),
-                                     vowner.ctypes.data_as(i32p), dims.ctypes.data_as(i64p))
-    assert rc == 0
-    nvc, Q, n_ifv, n_entries = (int(d) for d in dims)
-    assert n_entries == nvc * Q and n_ifv > 0
-    fetch, to, to_owner = fetch[:n_entries], to[:n_entries], to_owner[:n_entries]
-    NONE, IDX, SURF = 0xffffffff, 0x0fffffff, 0x80000000
-    rank_of_region = lambda r: r // (regions // world)
-    used = np.nonzero(fetch != NONE)[0]
-    assert (to[fetch == NONE] == NONE).all() and (to_owner[fetch == NONE] == NONE).all()
-    # every routing word to a scratch mailbox names the rank running the cluster that owns the slot
-    for words in (to[used], to_owner[used]):
-        idx = words & IDX
-        rank = (words >> 28) & 7
-        entry = idx < n_entries
-        assert (rank[entry] == [rank_of_region(creg[b % Q]) for b in idx[entry]]).all()
-    boxes_of = {}
-    for b in used:
-        boxes_of.setdefault(int(fetch[b]), []).append(int(b))
-    pos_of = {int(v): i for i, v in enumerate(ifv[:n_ifv])}
-    assert set(boxes_of) <= set(pos_of)          # only owned non-resident vertices are fetched
-    on_boundary = set(int(v) for v in oracle.boundary_surface(V, tets)[0])
-    for v, boxes in boxes_of.items():
-        first = int(ifirst[pos_of[v]])
-        assert (first >> 28) & 7 == rank_of_region(creg[(first & IDX) % Q])
-        chain, b = [], first & IDX
-        while b not in chain:
-            assert fetch[b] == v
-            chain.append(b)
-            b = int(to[b]) & IDX
-        assert b == chain[0] and sorted(chain) == sorted(boxes)
-        colours = [ccol[c % Q] for c in chain]
-        assert colours == sorted(colours) and len(set(colours)) == len(colours)
-        # to_owner follows the same chain except for the last entry of the sweep
-        for c in chain[:-1]:
-            assert (int(to_owner[c]) & ~SURF) == int(to[c])
-        last = int(to_owner[chain[-1]])
-        assert (last & IDX) == n_entries + pos_of[v]
-        assert (last >> 28) & 7 == rank_of_region(vowner[v])
-        surf = {bool(int(to_owner[c]) & SURF) for c in chain}
-        assert len(surf) == 1
-        assert surf == {v in on_boundary}
 
 
 def _host_project(fn, xi, xn, w, DmInv, V0, E, nu, alpha, beta, dt, lam):

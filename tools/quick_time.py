@@ -13,7 +13,8 @@ t0 = time.time()
 scene = {"config1": sc.config1, "config2": sc.config2, "config3": sc.config3, "config5": sc.config5,
          "config4": lambda: sc.config4(int(os.environ.get("NB", "512")))}[cfg]()
 t1 = time.time()
-sim = sbs.Simulation(0, prec, schedule=sched)
+sim = sbs.Simulation(0, prec, schedule=sched,
+                     region_shape=int(os.environ["REGION_SHAPE"]) if "REGION_SHAPE" in os.environ else None)
 scene.instantiate(sim)
 t2 = time.time()
 print("scene %s: build %.2fs finalize+upload %.2fs" % (scene.name, t1 - t0, t2 - t1), sim.stats())

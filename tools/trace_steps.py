@@ -3,12 +3,13 @@ SBSB200_TRACE_STEPS=N python tools/trace_steps.py <config>"""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-N = int(os.environ.setdefault("SBSB200_TRACE_STEPS", "80"))
+N = int(os.environ.get("TRACE_STEPS", "80"))
 sbs = importlib.import_module("soft-body-simulator_b200")
 sc = importlib.import_module("soft-body-simulator_b200.scenes")
 cfg = sys.argv[1] if len(sys.argv) > 1 else "config3"
 scene = getattr(sc, cfg)()
-sim = sbs.Simulation(0, 32, schedule=2)
+sim = sbs.Simulation(0, 32, schedule=2, trace_steps=N,
+                     region_shape=int(os.environ["REGION_SHAPE"]) if "REGION_SHAPE" in os.environ else None)
 scene.instantiate(sim)
 for _ in range(3):
     sim.step(scene.dt, scene.substeps, scene.iterations, scene.detect_every_substep)
