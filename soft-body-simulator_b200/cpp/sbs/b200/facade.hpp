@@ -580,6 +580,8 @@ class simulation_t
     sbsb200_ctx* ctx_ = nullptr;
     std::vector<int> device_body_;  // simulation body index -> device body index (-1: not on the device)
     std::vector<body_t const*> built_bodies_; // the bodies the device scene was built from
+    std::vector<std::vector<double>> device_mass_; // per body: the masses the device scene holds
+    scalar_type device_collision_compliance_ = -1; // the value last pushed to the device
     bool dirty_        = true;      // scene description changed since the device scene was built
     bool host_stale_   = false;     // the device stepped since particles_ was last refreshed
     bool host_written_ = false;     // particles_ was handed out mutable since the last upload
@@ -861,6 +863,13 @@ inline void simulation_t::build_device()
                   "sbsb200_add_distance_constraints");
         }
     check(sbsb200_finalize(ctx_), "sbsb200_finalize");
+    // the device scene was built from the particles' masses: nothing to push until the caller changes one
+    device_mass_.assign(bodies_.size(), {});
+    for (std::size_t b = 0; b < bodies_.size(); ++b)
+        if (device_body_[b] >= 0 && dynamic_cast<tetrahedral_body_t const*>(bodies_[b].get()))
+            for (particle_t const& p : particles_[b])
+                device_mass_[b].push_back(p.mass());
+    device_collision_compliance_ = simulation_parameters_.collision_compliance;
     dirty_        = false;
     host_stale_   = false;
     host_written_ = true; // positions/velocities of the host mirror go to the device before the first step
@@ -882,8 +891,24 @@ inline void simulation_t::push_host()
             }
         if (!ps.empty())
             check(sbsb200_upload(ctx_, device_body_[b], x.data(), v.data()), "sbsb200_upload");
+        // masses: only the ones the caller changed since they last went to the device (main.cpp:158-165 toggles a
+        // picked particle between 1 and 0), in one call
+        std::vector<double>& known = device_mass_[b];
+        std::vector<std::uint32_t> which;
+        std::vector<double> mass;
         for (std::size_t i = 0; i < ps.size(); ++i)
-            check(sbsb200_set_mass(ctx_, device_body_[b], static_cast<std::int64_t>(i), ps[i].mass()), "sbsb200_set_mass");
+            if (i >= known.size() || known[i] != ps[i].mass())
+            {
+                which.push_back(static_cast<std::uint32_t>(i));
+                mass.push_back(ps[i].mass());
+            }
+        if (!which.empty())
+            check(sbsb200_set_masses(ctx_, device_body_[b], static_cast<std::int64_t>(which.size()), which.data(),
+                                     mass.data()),
+                  "sbsb200_set_masses");
+        known.resize(ps.size());
+        for (std::size_t i = 0; i < ps.size(); ++i)
+            known[i] = ps[i].mass();
     }
     host_written_ = false;
 }
@@ -927,6 +952,13 @@ inline void simulation_t::device_step(scalar_type dt, std::size_t substeps, std:
     }
     if (host_written_)
         push_host();
+    // xpbd/contact_handler.cpp:42-52 reads the compliance whenever it creates a collision constraint, i.e. at every
+    // detection: a value changed through simulation_parameters() applies from the next step on
+    if (device_collision_compliance_ != simulation_parameters_.collision_compliance)
+    {
+        check(sbsb200_set_collision_compliance(ctx_, simulation_parameters_.collision_compliance), "collision compliance");
+        device_collision_compliance_ = simulation_parameters_.collision_compliance;
+    }
     check(sbsb200_step(ctx_, dt, static_cast<int>(substeps), static_cast<int>(iterations), detect_mode),
           "sbsb200_step");
     host_stale_ = true;

@@ -632,8 +632,8 @@ struct Engine final : EngineBase
                         // regions and parts of one colour are adjacent in storage, but each has its own
                         // column layout -> one launch each (a single launch when there is no region plan)
                         ChunkDesc const* hd =
-                            &c.green_plan.chunks[static_cast<size_t>(col) * 2 * c.green_plan.n_regions];
-                        for (int32_t rp = 0; rp < 2 * c.green_plan.n_regions; ++rp)
+                            &c.green_plan.chunks[static_cast<size_t>(col) * kParts * c.green_plan.n_regions];
+                        for (int32_t rp = 0; rp < kParts * c.green_plan.n_regions; ++rp)
                         {
                             ChunkDesc const& h2 = hd[rp];
                             if (h2.n[0] == 0)
@@ -1535,11 +1535,26 @@ int sbsb200_finalize(sbsb200_ctx* c)
             int64_t const vertex_bytes = c->precision == SBSB200_FP32 ? 16 : 32;
             bool planned = false;
             std::string why;
-            for (int per_sm = 1; per_sm <= 2 && !planned; ++per_sm)
+            // attempts: pencil-shaped regions (unless compact ones were asked for), compact regions (fewer vertices
+            // per region), two smaller compact regions per SM
+            struct Attempt
             {
+                bool pencils;
+                int per_sm;
+            };
+            std::vector<Attempt> attempts;
+            if (c->region_shape == SBSB200_REGIONS_PENCILS)
+                attempts.push_back({true, 1});
+            attempts.push_back({false, 1});
+            attempts.push_back({false, 2});
+            for (Attempt const& at : attempts)
+            {
+                if (planned)
+                    break;
+                int const per_sm  = at.per_sm;
                 ResidentParams rp = c->precision == SBSB200_FP32 ? ResidentPlan<float>::resident_params()
                                                                  : ResidentPlan<double>::resident_params();
-                rp.pencils     = c->region_shape == SBSB200_REGIONS_PENCILS;
+                rp.pencils     = at.pencils;
                 rp.smem_bytes  = rp.smem_bytes / per_sm - (per_sm > 1 ? 4096 : 0);
                 rp.max_threads = per_sm == 1 ? 384 : 192;
                 int32_t n_regions = regions_for(c->sm_count, T, c->world);
@@ -1666,10 +1681,10 @@ int sbsb200_get_stats(const sbsb200_ctx* cc, sbsb200_stats* out)
     out->frames               = c->frames;
     out->last_contact_count   = c->last_contacts;
     out->n_shared_vertices    = c->xplan.n_shared;
-    out->pulls_per_sweep      = c->xplan.n_pulls[2];
+    out->pulls_per_sweep      = c->xplan.n_pulls[1];
     out->pushes_per_sweep     = c->xplan.n_pushes[0];
     for (int64_t n : c->xplan.pulls_by_colour)
-        out->quiet_colours += c->schedule == SBSB200_SCHED_PERSISTENT && 50 * n <= c->xplan.n_pulls[2];
+        out->quiet_colours += c->schedule == SBSB200_SCHED_PERSISTENT && 50 * n <= c->xplan.n_pulls[1];
     if (c->engine)
     {
         cudaSetDevice(c->device);

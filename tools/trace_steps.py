@@ -36,3 +36,16 @@ show("first poll", f[:, :, 2] - f[:, :, 4])
 show("poll rounds", f[:, :, 1])
 show("polls+barrier", f[:, :, 7] - f[:, :, 2])
 show("whole step", f[:, :, 7] - f[:, :, 0])
+C = sim.stats()["n_green_colours"]
+whole = f[:, :, 7] - f[:, :, 0]
+print("whole step by position in the sweep (mean over regions; max over regions = what the slowest region needs):")
+for c in range(C):
+    w = whole[:, c::C]
+    print("  colour %d: mean %7.0f  max-over-regions mean %7.0f  tets %6.0f  push %5.0f" % (
+        c, np.nanmean(w), np.nanmean(np.nanmax(w, axis=0)),
+        np.nanmean((np.nanmax(f[:, c::C, 8:14], axis=2) - f[:, c::C, 8])), np.nanmean(f[:, c::C, 15] - np.nanmax(f[:, c::C, 8:14], axis=2))))
+# time between the barriers of consecutive steps of one region = the step as the region experiences it
+gap = np.diff(f[:, :, 7], axis=1)
+print("barrier-to-barrier: mean %.0f p50 %.0f p95 %.0f" % (np.nanmean(gap), np.nanpercentile(gap, 50), np.nanpercentile(gap, 95)))
+for c in range(C):
+    print("  into colour %d: %.0f" % ((c + 1) % C, np.nanmean(gap[:, c::C])))
