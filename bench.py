@@ -4,22 +4,28 @@
 One "step" = one frame of the hot path (timestep_t::step: detection, 10 substeps x 10
 Gauss-Seidel iterations, commit, surface update) over one batch of synthetic input.
 
-  N = 1 : BASELINE.json configs[2] — the 1M-tet grid-tetrahedralised block dropped on an SDF
-          sphere + floor, collision detection every substep ("config3").
-  N > 1 : the path shards by independent scenes (north_star (3): "independent bodies or scenes
-          split across GPUs"): every rank runs its own config3 scene, no data-path collective,
-          weak scaling.  `--workload config4` shards the 4096-body ensemble instead
-          (strong scaling, 4096/N bodies per rank); `--workload config5` runs the 8M-tet body
-          on one GPU.
+Headline (`value`, `e2e`, `roofline`): BASELINE.json configs[2] — the 1M-tet grid-tetrahedralised block
+on an SDF sphere + floor, BVH broadphase and collision detection every substep ("config3"), in sustained
+contact (`contacts` reports min / mean / max over the timed frames; the run fails when the mean is 0).
+With N > 1 every rank runs its own config3 scene (independent scenes, no data-path collective, weak scaling),
+so the N = 1 line of a scaling run equals the single-GPU bench.
+
+Sub-records of the same JSON line (BASELINE.json configs[3], [4], the multi-GPU rows of SURVEY 8e):
+  `decomposed` : ONE 8M-tet body (config5) cut over the N ranks; shared vertices travel through mailboxes in
+                 peer memory, pushed over NVLink by the substep kernel itself (no collective); strong scaling.
+                 At N = 1 the same body on one GPU — the reference point for the scaling efficiency.
+  `ensemble`   : 4096 independent 2k-tet bodies (config4), 4096 / N per rank, no cross-GPU traffic; strong scaling.
+  `fp64`       : the headline scene in the fp64 validation build (the reference is fp64 throughout).
 
 `value`  : projections/s with state resident in HBM (CUDA events on the launch stream,
            per-step event pairs, L2 flushed between steps, max over ranks).
-`e2e`    : the same metric through the C ABI with HOST buffers (sbsb200_step_host: pinned
+`e2e`    : the same metric through the C ABI with HOST buffers (sbsb200_step_host_f32: pinned
            host x,v -> device, step, device -> host x,v inside the timed region).
 `--impl reference` times the reference's CPU algorithm (oracle/_ref when built, else the C
 port in oracle/) on a bounded sample of the same workload, rank 0 only.
 """
 import argparse
+import hashlib
 import importlib
 import json
 import os
@@ -48,10 +54,12 @@ def parse():
     ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5"])
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--schedule", type=int, default=0)
+    ap.add_argument("--region-shape", type=int, default=None, help="0 pencils (default), 1 compact")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="headline only: skip the decomposed / ensemble / fp64 sub-records")
     ap.add_argument("--decompose", action="store_true",
-                    help="N > 1: cut the ONE body of the workload over the N GPUs (default for config5)")
+                    help="N > 1: cut the ONE body of the headline workload over the N GPUs (config2, config3, config5)")
     return ap.parse_args()
 
 
@@ -119,56 +127,51 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(sc, workload, rank=0, world=1):
-    """Reference algorithm on the host: ONE substep (10 iterations) of the same scene, serial."""
+def reference_world():
+    """(kind, constructor) of the CPU checker: the reference's own sources when built, else the C port."""
     from oracle import oracle as O
-    kind, W = "port", None
     try:
         from oracle import ref as REF
         if REF.available():
-            kind, W = "reference", REF.World()
+            return "reference", REF.World
     except Exception:
-        W = None
-    if W is None:
-        O.build()
-        W = O.World()
+        pass
+    O.build()
+    return "port", O.World
+
+
+def cpu_baseline(sc, workload, rank=0, world=1):
+    """Reference algorithm on the host: ONE substep (10 iterations) of the same scene, serial."""
+    kind, mk = reference_world()
+    W = mk()
     scene = make_scene(sc, workload, rank, world)
     scene.instantiate(W)
     dt = scene.dt / scene.substeps
     t0 = time.perf_counter()
-    W.step(dt, 1, scene.iterations, False)
+    W.step(dt, 1, scene.iterations, scene.detect_every_substep)
     sec = time.perf_counter() - t0
     proj = scene.n_tets * scene.iterations
     return {"value": proj / sec, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "1 substep (%d iterations, %d projections) of %s in %.2f s, serial Gauss-Seidel "
-                      "as the reference (single-threaded), fp64" % (scene.iterations, proj, scene.name, sec),
-            "seconds": sec, "host_cores_available": os.cpu_count()}, scene
+            "sample": "1 substep (detection + %d iterations, %d projections, %d contacts) of %s in %.2f s, serial "
+                      "Gauss-Seidel as the reference (single-threaded), fp64"
+                      % (scene.iterations, proj, len(W.contacts()[0]), scene.name, sec),
+            "seconds": sec, "host_cores_available": os.cpu_count()}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     sc = importlib.import_module("soft-body-simulator_b200.scenes")
-    from oracle import oracle as O
-    kind, mk = "port", None
-    try:
-        from oracle import ref as REF
-        if REF.available():
-            kind, mk = "reference", REF.World
-    except Exception:
-        mk = None
-    if mk is None:
-        O.build()
-        mk = O.World
+    kind, mk = reference_world()
     scene = make_scene(sc, args.workload, 0, world)
     W = mk()
     scene.instantiate(W)
     dt = scene.dt / scene.substeps
     for _ in range(args.warmup):
-        W.step(dt, 1, 1, False)          # warm caches; 1 iteration each
+        W.step(dt, 1, 1, scene.detect_every_substep)          # warm caches; 1 iteration each
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        W.step(dt, 1, scene.iterations, False)
+        W.step(dt, 1, scene.iterations, scene.detect_every_substep)
     sec = time.perf_counter() - t0
     proj = scene.n_tets * scene.iterations * args.steps
     value = proj / sec
@@ -178,13 +181,170 @@ def run_reference(args, rank, world):
             "data": "synthetic",
             "config": {"workload": scene.name, "tets": scene.n_tets, "substeps": scene.substeps,
                        "iterations": scene.iterations,
-                       "step": "bounded sample: each step is ONE substep (%d iterations) of the frame" % scene.iterations},
+                       "step": "bounded sample: each step is ONE substep (detection + %d iterations) of the frame"
+                               % scene.iterations},
+            "contacts_last_detection": len(W.contacts()[0]),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
                              "sample": "%d x 1 substep of %s, serial (the reference solver is single-threaded)"
                                        % (args.steps, scene.name)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+class Bench:
+    """One scene on this rank's GPU (or its share of a decomposed one), timed as the contract says."""
+
+    def __init__(self, env, scene, precision, schedule=0, decomposed=False, region_shape=None):
+        import torch
+        import torch.distributed as dist
+        self.env, self.scene, self.precision, self.decomposed = env, scene, precision, decomposed
+        sbs = env["sbs"]
+        self.sim = sbs.Simulation(env["local"], precision, stream=env["stream"].cuda_stream,
+                                  schedule=sbs.SCHED_PERSISTENT if decomposed else schedule, region_shape=region_shape)
+        if decomposed:
+            # ONE body cut into world x regions; every rank runs its block, shared vertices travel through mailboxes
+            # in peer memory (NVLink stores issued by the substep kernel; no collective)
+            self.ids = scene.instantiate(self.sim, partition=(env["rank"], env["world"]))
+            handles = [None] * env["world"]
+            dist.all_gather_object(handles, self.sim.mailbox_handle())
+            self.sim.connect_peers(handles)
+            dist.barrier()
+        else:
+            self.ids = scene.instantiate(self.sim)
+        self.stats0 = self.sim.stats()
+        torch.cuda.synchronize()
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.env["world"] > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if self.env["world"] > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def resident(self, steps, warmup):
+        """State resident in HBM: per-step CUDA-event pairs, L2 flushed between steps, max over ranks."""
+        import torch
+        sim, scene, stream = self.sim, self.scene, self.env["stream"]
+        S, K = scene.substeps, scene.iterations
+        for _ in range(warmup):
+            sim.step(scene.dt, S, K, scene.detect_every_substep)
+        self.barrier()
+        st0 = sim.stats()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        contacts = []
+        for a, b in ev:
+            self.env["flush"].zero_()           # L2 flush between timed iterations (not timed)
+            a.record(stream)
+            sim.step(scene.dt, S, K, scene.detect_every_substep)
+            b.record(stream)
+            if not self.decomposed:             # (a rank of a decomposed body must not block between frames)
+                contacts.append(sim.contact_count())
+        self.barrier()
+        if self.decomposed:
+            contacts.append(sim.contact_count())
+        st1 = sim.stats()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        return {"ms_per_step": self.max_over_ranks(ms) / steps, "steps": steps, "warmup": warmup,
+                "launches": st1["kernels_launched"] - st0["kernels_launched"],
+                "kernel_ms": st1["kernel_ms"] - st0["kernel_ms"],
+                "kernel_launches": st1["kernel_launches"] - st0["kernel_launches"], "ms_this_rank": ms,
+                "contacts": {"min": int(min(contacts)), "mean": float(sum(contacts)) / len(contacts),
+                             "max": int(max(contacts)), "samples": len(contacts),
+                             "what": "contacts of the last detection of every timed frame"
+                                     + (" (last frame only)" if self.decomposed else "")},
+                "general_route_projections": st1["green_general_calls"]}
+
+    def end_to_end(self, steps):
+        """Through sbsb200_step_host_f32 with pinned HOST buffers: H2D of x, v, the frame, D2H of x, v per step."""
+        import numpy as np
+        import torch
+        sim, scene, stream = self.sim, self.scene, self.env["stream"]
+        S, K = scene.substeps, scene.iterations
+        b0 = scene.tet_bodies()[0]
+        body = scene.items[b0]
+        nV = body.x0.shape[0]
+        x_in = torch.from_numpy(body.x.astype(np.float32)).pin_memory()
+        v_in = torch.from_numpy((body.v if body.v is not None else np.zeros_like(body.x)).astype(np.float32)).pin_memory()
+        x_out = torch.empty((nV, 3), dtype=torch.float32).pin_memory()
+        v_out = torch.empty((nV, 3), dtype=torch.float32).pin_memory()
+        xin, vin, xo, vo = x_in.numpy(), v_in.numpy(), x_out.numpy(), v_out.numpy()
+        for _ in range(2):
+            sim.step_host_f32(self.ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
+            xin, xo = xo, xin
+            vin, vo = vo, vin
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            sim.step_host_f32(self.ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
+            xin, xo = xo, xin              # next frame continues from the host copy: the two pinned
+            vin, vo = vo, vin              # buffer pairs swap roles, nothing is copied on the host
+        self.barrier()
+        wall = self.max_over_ranks(time.perf_counter() - t0)
+        return {"seconds": wall, "steps": steps, "h2d_bytes_per_step": int(2 * nV * 12),
+                "d2h_bytes_per_step": int(2 * nV * 12), "contacts_last_detection": sim.contact_count(),
+                "timing": "wall clock around sbsb200_step_host_f32 (float host buffers), max over ranks",
+                "bodies_round_tripped": 1}
+
+    def roofline(self, res, peak, peaks_found, share=1):
+        """Algorithmic bytes / CUDA-event time, per GPU.  share: ranks one body is cut over."""
+        scene, st = self.scene, self.stats0
+        S, K = scene.substeps, scene.iterations
+        contacts = res["contacts"]["mean"]
+        scale = 336.0 / 176.0 if self.precision == 64 else 1.0
+        n_det = S if scene.detect_every_substep else 1
+        bytes_step = (S * K * (BYTES_PER_PROJECTION * scene.n_tets + BYTES_PER_COLLISION * contacts)
+                      + S * BYTES_PER_VERTEX_SUBSTEP * st["n_vertices"] + n_det * BYTES_PER_SURFACE_DETECT
+                      * st["n_surface_vertices"]) * scale / share
+        frame_gbs = bytes_step / (res["ms_per_step"] * 1e-3) / 1e9
+        if res["kernel_launches"] > 0:
+            # dominant kernel = the substep kernel of the resident schedule: one launch runs predict, K sweeps over
+            # every tet and contact, and commit for one substep.  Timed live with CUDA events around every launch
+            # of the timed region (sbsb200_stats.kernel_ms).
+            bytes_launch = (K * (BYTES_PER_PROJECTION * scene.n_tets + BYTES_PER_COLLISION * contacts)
+                            + BYTES_PER_VERTEX_SUBSTEP * st["n_vertices"]) * scale / share
+            k_ms = res["kernel_ms"] / res["kernel_launches"]
+            achieved = bytes_launch / (k_ms * 1e-3) / 1e9
+            kernel = {"name": "k_substep_resident", "launches_timed": int(res["kernel_launches"]),
+                      "avg_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": int(bytes_launch),
+                      "share_of_step": res["kernel_ms"] / res["ms_this_rank"]}
+        else:
+            # graph schedule: ~800 k_project_green launches per frame inside one CUDA graph; CUDA events cannot
+            # bracket a node of a graph launch, so the frame as a whole is the timed unit
+            achieved, kernel = frame_gbs, {"name": "whole frame (CUDA graph of per-colour kernels)"}
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks_found else "6650 (of fallback)",
+                "kernel": kernel,
+                "frame": {"algorithmic_bytes_per_step": int(bytes_step), "achieved": frame_gbs,
+                          "frac": frame_gbs / peak, "per": "GPU"},
+                "frac_of_8TBs_nominal": achieved / 8000.0}
+
+    def describe(self):
+        scene, st = self.scene, self.stats0
+        sched = {1: "graph", 2: "resident"}.get(st["schedule"], "?")
+        return {"workload": scene.name, "tets": scene.n_tets, "vertices": st["n_vertices"], "schedule": sched,
+                "regions": st["n_regions"], "colours": st["n_green_colours"], "shared_vertices": st["n_shared_vertices"],
+                "pulls_per_sweep": st["pulls_per_sweep"], "colour_steps_without_exchange": st["quiet_colours"],
+                "schedule_note": self.sim.schedule_note()}
+
+    def close(self):
+        self.sim.close()
+
+
+def lib_sha(sbs):
+    try:
+        return hashlib.sha256(open(sbs.LIB_PATH, "rb").read()).hexdigest()[:16]
+    except OSError:
+        return None
 
 
 def main():
@@ -205,177 +365,144 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sbs = importlib.import_module("soft-body-simulator_b200")
     sc = importlib.import_module("soft-body-simulator_b200.scenes")
-
-    decomposed = world > 1 and (args.workload == "config5" or (args.decompose and args.workload in ("config2", "config3")))
-    scene = make_scene(sc, args.workload, rank, world, decomposed)
     # a dedicated non-blocking stream: the library captures the frame into a CUDA graph, which
     # the legacy default stream does not permit
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    sim = sbs.Simulation(local, args.precision, stream=stream.cuda_stream,
-                         schedule=sbs.SCHED_PERSISTENT if decomposed else args.schedule)
-    if decomposed:
-        # ONE body cut into world x regions; every rank runs its block, shared vertices travel through
-        # mailboxes in peer memory (NVLink stores issued by the substep kernel; no collective)
-        ids = scene.instantiate(sim, partition=(rank, world))
-        handles = [None] * world
-        dist.all_gather_object(handles, sim.mailbox_handle())
-        sim.connect_peers(handles)
-        dist.barrier()
-    else:
-        ids = scene.instantiate(sim)
-    stats0 = sim.stats()
+    env = {"sbs": sbs, "sc": sc, "rank": rank, "world": world, "local": local, "stream": stream,
+           "flush": torch.empty(256 << 20, dtype=torch.uint8, device="cuda")}     # > 126 MB L2
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    # ---- headline ---------------------------------------------------------------------------
+    decomposed = world > 1 and (args.workload == "config5" or (args.decompose and args.workload in ("config2", "config3")))
+    sharded = args.workload in ("config3", "config4") and not decomposed       # every rank has its own scene(s)
+    scene = make_scene(sc, args.workload, rank, world, decomposed)
     S, K = scene.substeps, scene.iterations
-    proj_per_step = scene.n_tets * S * K
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ----------------------------------------------------------
-    for _ in range(args.warmup):
-        sim.step(scene.dt, S, K, scene.detect_every_substep)
-    barrier()
+    head = Bench(env, scene, args.precision, args.schedule, decomposed, args.region_shape)
     sampler = ClockSampler(local)
     sampler.start()
-    st_before = sim.stats()
-    launches0 = st_before["kernels_launched"]
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    contacts = 0
-    for a, b in ev:
-        flush.zero_()                      # L2 flush between timed iterations (not timed)
-        a.record(stream)
-        sim.step(scene.dt, S, K, scene.detect_every_substep)
-        b.record(stream)
-    barrier()
-    st_after = sim.stats()
-    launches = st_after["kernels_launched"] - launches0
-    kernel_ms = st_after["kernel_ms"] - st_before["kernel_ms"]
-    kernel_launches = st_after["kernel_launches"] - st_before["kernel_launches"]
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    contacts = len(sim.contacts()[0])
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    total_proj = proj_per_step * args.steps * (world if args.workload in ("config3", "config4") and not decomposed else 1)
-    value = total_proj / (ms_max * 1e-3)
-
-    # ---- end-to-end through the C ABI with host buffers -----------------------------------
+    res = head.resident(args.steps, args.warmup)
+    clocks = sampler.stop()
+    total_tets = scene.n_tets * (world if sharded else 1)
+    if args.workload == "config4":
+        total_tets = 4096 * (scene.n_tets // max(1, len(scene.tet_bodies())))
+    value = total_tets * S * K / (res["ms_per_step"] * 1e-3)
     e2e = None
     if not args.no_e2e:
-        b0 = scene.tet_bodies()[0]
-        nV = scene.items[b0].x0.shape[0]
-        x_in = torch.from_numpy(scene.items[b0].x.copy()).pin_memory()
-        v_in = torch.zeros((nV, 3), dtype=torch.float64).pin_memory()
-        x_out = torch.empty((nV, 3), dtype=torch.float64).pin_memory()
-        v_out = torch.empty((nV, 3), dtype=torch.float64).pin_memory()
-        xin, vin, xo, vo = x_in.numpy(), v_in.numpy(), x_out.numpy(), v_out.numpy()
-        for _ in range(2):
-            sim.step_host(ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_e2e = max(3, args.steps // 2)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(n_e2e):
-            sim.step_host(ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
-            xin, xo = xo, xin              # next frame continues from the host copy: the two pinned
-            vin, vo = vo, vin              # buffer pairs swap roles, nothing is copied on the host
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        scale = world if args.workload in ("config3", "config4") and not decomposed else 1
-        e2e = {"value": proj_per_step * n_e2e * scale / float(t.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(2 * nV * 24), "d2h_bytes_per_step": int(2 * nV * 24),
-               "steps": n_e2e, "timing": "wall clock around sbsb200_step_host (max over ranks)",
-               "bodies_round_tripped": 1}
-    clocks = sampler.stop()
+        r = head.end_to_end(max(3, args.steps // 2))
+        e2e = {"value": total_tets * S * K * r["steps"] / r["seconds"], "unit": UNIT,
+               "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"],
+               "steps": r["steps"], "timing": r["timing"], "bodies_round_tripped": r["bodies_round_tripped"],
+               "contacts_last_detection": r["contacts_last_detection"]}
+    roof = head.roofline(res, peak, bool(peaks), share=world if decomposed else 1)
+    try:   # dram__bytes_read + dram__bytes_write per launch of the same kernel on the same workload, from an ncu
+        # capture of THIS build of the library (profiles/); a capture of another build is not quoted
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        if tr["workload"] == scene.name and tr.get("lib_sha16") == lib_sha(sbs) and roof["kernel"]["name"] in tr["kernel"]:
+            roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roof["traffic_source"] = "profiles/r02_ncu_traffic.json (ncu --set full of this build)"
+    except Exception:
+        pass
+    roof["note"] = ("algorithmic bytes (SURVEY 8d: 176 B per projection, 64 B per contact projection, 112 B per "
+                    "vertex and substep) / CUDA-event time; the working set fits the 126 MB L2 and the vertices "
+                    "live in shared memory, so DRAM traffic is far below the algorithmic bytes (profiles/)")
+    head_desc = head.describe()
+    if args.workload == "config3" and world == 1 and res["contacts"]["mean"] <= 0:
+        raise SystemExit("bench.py: the timed frames of config3 held no contact — the scene is not the one "
+                         "BASELINE.json names (collision constraints every substep)")
+    head.close()
+
+    # ---- sub-records ----------------------------------------------------------------------------
+    sub = {}
+    if not args.no_sub and args.workload == "config3" and args.precision == 32:
+        sub_steps, sub_warm = max(3, min(args.steps, 5)), max(3, min(args.warmup, 3))
+        # (1) one 8M-tet body, decomposed over the N ranks (N = 1: the same body on one GPU)
+        try:
+            s5 = sc.config5()
+            b = Bench(env, s5, 32, sbs.SCHED_PERSISTENT if world > 1 else 0, world > 1, args.region_shape)
+            r5 = b.resident(sub_steps, sub_warm)
+            rec = {"config": dict(b.describe(), parallelism=(
+                       "one body cut over %d GPUs; shared vertices pushed into peer memory over NVLink by the substep "
+                       "kernel, no collective" % world) if world > 1 else "one GPU (reference point of the strong scaling)",
+                       tets_per_gpu=s5.n_tets // world),
+                   "scaling": "strong", "n_gpus": world, "steps": r5["steps"], "warmup": r5["warmup"],
+                   "ms_per_step": r5["ms_per_step"], "value": s5.n_tets * S * K / (r5["ms_per_step"] * 1e-3), "unit": UNIT,
+                   "gpu_launches": int(r5["launches"]), "contacts": r5["contacts"],
+                   "roofline": b.roofline(r5, peak, bool(peaks), share=world)}
+            if not args.no_e2e:
+                r = b.end_to_end(3)
+                rec["e2e"] = {"value": s5.n_tets * S * K * r["steps"] / r["seconds"], "unit": UNIT,
+                              "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"],
+                              "steps": r["steps"], "timing": r["timing"],
+                              "note": "every rank round-trips the body's x, v (float) through pinned host memory each frame; "
+                                      "a rank holds and returns valid state for the vertices it owns"}
+            sub["decomposed"] = rec
+            b.close()
+        except Exception as exc:                      # a failing sub-record must not hide the headline
+            sub["decomposed"] = {"error": repr(exc)}
+            if world > 1:
+                raise
+        # (2) 4096 independent bodies, 4096 / N per rank
+        try:
+            per = 4096 // world
+            s4 = sc.config4(per, first=rank * per)
+            b = Bench(env, s4, 32, 0, False, args.region_shape)
+            r4 = b.resident(sub_steps, sub_warm)
+            tets4 = 4096 * (s4.n_tets // per)
+            sub["ensemble"] = {"config": dict(b.describe(), bodies_per_gpu=per, parallelism="bodies sharded over %d GPU(s), "
+                                              "no cross-GPU traffic" % world),
+                               "scaling": "strong", "n_gpus": world, "steps": r4["steps"], "warmup": r4["warmup"],
+                               "ms_per_step": r4["ms_per_step"], "value": tets4 * S * K / (r4["ms_per_step"] * 1e-3),
+                               "unit": UNIT, "gpu_launches": int(r4["launches"]), "contacts": r4["contacts"],
+                               "roofline": b.roofline(r4, peak, bool(peaks))}
+            b.close()
+        except Exception as exc:
+            sub["ensemble"] = {"error": repr(exc)}
+        # (3) the headline scene in the fp64 validation build (the reference computes in fp64)
+        if world == 1:
+            try:
+                b = Bench(env, make_scene(sc, "config3", rank, world), 64, args.schedule, False, args.region_shape)
+                r64 = b.resident(sub_steps, sub_warm)
+                sub["fp64"] = {"config": b.describe(), "dtype": "f64", "steps": r64["steps"], "warmup": r64["warmup"],
+                               "ms_per_step": r64["ms_per_step"],
+                               "value": scene.n_tets * S * K / (r64["ms_per_step"] * 1e-3), "unit": UNIT,
+                               "contacts": r64["contacts"], "roofline": b.roofline(r64, peak, bool(peaks)),
+                               "note": "336 B per projection in fp64 (SURVEY 8d)"}
+                b.close()
+            except Exception as exc:
+                sub["fp64"] = {"error": repr(exc)}
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        nVtot, nVs = stats0["n_vertices"], stats0["n_surface_vertices"]
-        n_det = S if scene.detect_every_substep else 1
-        bytes_step = S * K * (BYTES_PER_PROJECTION * scene.n_tets + BYTES_PER_COLLISION * contacts) \
-            + S * BYTES_PER_VERTEX_SUBSTEP * nVtot + n_det * BYTES_PER_SURFACE_DETECT * nVs
-        if args.precision == 64:
-            bytes_step = bytes_step * 336 // 176
-        ms_step = ms_max / args.steps
-        # per-GPU figure: a rank of a decomposed body moves 1/world of the frame's bytes
-        frame_gbs = bytes_step / (world if decomposed else 1) / (ms_step * 1e-3) / 1e9
-        sched = {1: "graph", 2: "persistent"}.get(stats0["schedule"], "?")
-        if kernel_launches > 0:
-            # dominant kernel = the substep kernel of the persistent schedule: one launch runs predict,
-            # K sweeps over every tet and contact, and commit for one substep.  Timed live with CUDA
-            # events around every launch of the timed region (sbsb200_stats.kernel_ms).
-            share = world if decomposed else 1        # a rank of a decomposed body runs 1/world of it
-            bytes_launch = (K * (BYTES_PER_PROJECTION * scene.n_tets + BYTES_PER_COLLISION * contacts)
-                            + BYTES_PER_VERTEX_SUBSTEP * nVtot) // share
-            if args.precision == 64:
-                bytes_launch = bytes_launch * 336 // 176
-            k_ms = kernel_ms / kernel_launches
-            achieved = bytes_launch / (k_ms * 1e-3) / 1e9
-            kernel = {"name": "k_substep_persistent", "launches_timed": int(kernel_launches),
-                      "avg_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": int(bytes_launch),
-                      "share_of_step": kernel_ms / ms}
-        else:
-            # graph schedule: ~800 k_project_green launches per frame inside one CUDA graph; CUDA events
-            # cannot bracket a node of a graph launch, so the frame as a whole is the timed unit
-            achieved, kernel = frame_gbs, {"name": "whole frame (CUDA graph of per-colour kernels)"}
-        traffic = None
-        try:   # dram__bytes_read + dram__bytes_write per launch of the same kernel on the same workload (ncu)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-            if tr["workload"] == scene.name and kernel["name"] in tr["kernel"]:
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-        except Exception:
-            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if args.workload in ("config4", "config5") or decomposed else "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
-            "config": {"workload": scene.name, "tets_per_gpu": scene.n_tets // (world if decomposed else 1),
-                       "vertices_per_gpu": nVtot // (world if decomposed else 1),
-                       "substeps": S, "iterations": K, "dt": scene.dt,
-                       "detection": ("every substep" if scene.detect_every_substep else "once per frame")
-                       + (", BVH broadphase" if scene.broadphase else ""),
-                       "colours": stats0["n_green_colours"], "schedule": sched,
-                       "regions": stats0["n_regions"], "shared_vertices": stats0["n_interface_vertices"],
-                       "parallelism": ("one body decomposed over %d GPUs, shared vertices pushed to peer memory by "
-                                       "the substep kernel" % world) if decomposed else
-                                      "scenes sharded over %d GPU(s), no collective" % world,
-                       "l2": "256 MiB write between timed steps (flush)"},
-            "ms_per_frame": ms_step,
-            "contacts_last_detection": contacts,
-            "clocks": clocks, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 (of fallback)",
-                         "kernel": kernel,
-                         "frame": {"algorithmic_bytes_per_step": int(bytes_step), "achieved": frame_gbs,
-                                   "frac": frame_gbs / peak, "per": "GPU"},
-                         "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "note": "algorithmic bytes (SURVEY 8d: 176 B per projection, 64 B per contact "
-                                 "projection, 112 B per vertex and substep) / CUDA-event time; the working set "
-                                 "fits the 126 MB L2, so DRAM traffic is far below the algorithmic bytes "
-                                 "(profiles/)"},
+            "config": dict(head_desc, tets_per_gpu=scene.n_tets // (world if decomposed else 1),
+                           substeps=S, iterations=K, dt=scene.dt,
+                           detection=("every substep" if scene.detect_every_substep else "once per frame")
+                           + (", BVH broadphase" if scene.broadphase else ""),
+                           parallelism=("one body decomposed over %d GPUs, shared vertices pushed to peer memory by "
+                                        "the substep kernel" % world) if decomposed else
+                           "scenes sharded over %d GPU(s), no collective" % world,
+                           l2="256 MiB write between timed steps (flush)"),
+            "ms_per_frame": res["ms_per_step"],
+            "contacts": res["contacts"], "contacts_last_detection": res["contacts"]["max"],
+            "general_route_projections": res["general_route_projections"],
+            "clocks": clocks, "gpu_launches": int(res["launches"]),
+            "roofline": roof, "lib_sha16": lib_sha(sbs),
         }
         if e2e:
             line["e2e"] = e2e
+        line.update(sub)
         if not args.no_cpu_baseline and world == 1:
             try:
-                line["cpu_baseline"], _ = cpu_baseline(sc, args.workload)
+                line["cpu_baseline"] = cpu_baseline(sc, args.workload)
             except Exception as exc:  # the checker failing must not hide the GPU number
                 line["cpu_baseline"] = {"error": repr(exc)}
         print(json.dumps(line))

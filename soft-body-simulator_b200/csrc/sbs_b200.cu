@@ -304,6 +304,8 @@ struct Engine final : EngineBase
                     records.push_back(a0);
                     records.push_back(a1);
                     records.push_back(a2);
+                    Material const& mt = h.materials[h.tet_material[c.green_plan.storage_order[static_cast<size_t>(p)]]];
+                    records.push_back(Real4<R>{R(mt.mu), R(mt.lambda), R(mt.alpha), R(mt.beta)});
                 }
                 shape[static_cast<size_t>(p)] = static_cast<uint8_t>(it->second);
             }
@@ -644,7 +646,7 @@ struct Engine final : EngineBase
                             for (int m = 0; m < 8; ++m)
                                 dc.n[m] = h2.n[m];
                             unsigned const g = static_cast<unsigned>((h2.n[0] + 127) / 128);
-                            size_t const dict_bytes = static_cast<size_t>(3 * d.n_shapes) * sizeof(Real4<R>);
+                            size_t const dict_bytes = static_cast<size_t>(kShapeWords * d.n_shapes) * sizeof(Real4<R>);
                             if (c.any_damping && d.n_shapes > 0)
                                 k_project_green<R, true, true><<<g, 128, dict_bytes, st>>>(d, dc, dt, first);
                             else if (c.any_damping)
@@ -1139,7 +1141,7 @@ int sbsb200_set_broadphase(sbsb200_ctx* c, int mode)
 
 int sbsb200_set_region_shape(sbsb200_ctx* c, int shape)
 {
-    if (!c || (shape != SBSB200_REGIONS_PENCILS && shape != SBSB200_REGIONS_COMPACT))
+    if (!c || (shape != SBSB200_REGIONS_PENCILS && shape != SBSB200_REGIONS_COMPACT && shape != SBSB200_REGIONS_SLABS))
         return fail(c, SBSB200_ERR_INVALID, "bad region shape");
     if (c->finalized)
         return fail(c, SBSB200_ERR_STATE, "scene already finalized");
@@ -1539,14 +1541,16 @@ int sbsb200_finalize(sbsb200_ctx* c)
             // per region), two smaller compact regions per SM
             struct Attempt
             {
-                bool pencils;
+                bool slabs, pencils;
                 int per_sm;
             };
             std::vector<Attempt> attempts;
-            if (c->region_shape == SBSB200_REGIONS_PENCILS)
-                attempts.push_back({true, 1});
-            attempts.push_back({false, 1});
-            attempts.push_back({false, 2});
+            if (c->region_shape == SBSB200_REGIONS_SLABS && c->world == 1)
+                attempts.push_back({true, false, 1});
+            if (c->region_shape != SBSB200_REGIONS_COMPACT)
+                attempts.push_back({false, true, 1});
+            attempts.push_back({false, false, 1});
+            attempts.push_back({false, false, 2});
             for (Attempt const& at : attempts)
             {
                 if (planned)
@@ -1555,6 +1559,7 @@ int sbsb200_finalize(sbsb200_ctx* c)
                 ResidentParams rp = c->precision == SBSB200_FP32 ? ResidentPlan<float>::resident_params()
                                                                  : ResidentPlan<double>::resident_params();
                 rp.pencils     = at.pencils;
+                rp.slabs       = at.slabs;
                 rp.smem_bytes  = rp.smem_bytes / per_sm - (per_sm > 1 ? 4096 : 0);
                 rp.max_threads = per_sm == 1 ? 384 : 192;
                 int32_t n_regions = regions_for(c->sm_count, T, c->world);

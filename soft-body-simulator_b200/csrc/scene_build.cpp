@@ -552,6 +552,30 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         for (Cluster& c : clusters)
             c.region = body_index[static_cast<size_t>(c.body)] / group;
     }
+    else if (n_regions > 1 && resident && resident->slabs && !clusters.empty())
+    { // layers of the cluster grid along its longest axis, consecutive layers per region, at most one region per layer
+        uint32_t lo[3] = {~0u, ~0u, ~0u}, hi[3] = {0u, 0u, 0u};
+        for (Cluster const& c : clusters)
+        {
+            uint32_t const g[3] = {c.cx, c.cy, c.cz};
+            for (int d = 0; d < 3; ++d)
+            {
+                lo[d] = std::min(lo[d], g[d]);
+                hi[d] = std::max(hi[d], g[d]);
+            }
+        }
+        int axis = 0;
+        for (int d = 1; d < 3; ++d)
+            if (hi[d] - lo[d] > hi[axis] - lo[axis])
+                axis = d;
+        int64_t const layers = static_cast<int64_t>(hi[axis] - lo[axis]) + 1;
+        out.n_regions        = static_cast<int32_t>(std::min<int64_t>(n_regions, layers));
+        for (Cluster& c : clusters)
+        {
+            uint32_t const g[3] = {c.cx, c.cy, c.cz};
+            c.region = static_cast<int32_t>((static_cast<int64_t>(g[axis] - lo[axis]) * out.n_regions) / layers);
+        }
+    }
     else if (n_regions > 1)
     {
         out.n_regions = n_regions;
@@ -735,10 +759,17 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         {
             classify_regions(scene, out.tet_region, out.n_regions, *region_plan);
             // the first colour of a sweep that touches a vertex: that cluster projects the vertex's contacts
+            // A vertex is OWNED (predicted, committed, its surface copy written) by the region of that cluster: its
+            // first touch after the predict step is then local, and the contacts a rank of a decomposed scene
+            // detects for the vertices it owns are the ones its own clusters project.
             std::vector<int32_t> first_colour(static_cast<size_t>(V), 0x7fffffff);
             for (Cluster const& c : clusters)
                 for (uint32_t k = 0; k < c.nv; ++k)
-                    first_colour[c.verts[k]] = std::min(first_colour[c.verts[k]], c.colour);
+                    if (c.colour < first_colour[c.verts[k]])
+                    {
+                        first_colour[c.verts[k]]            = c.colour;
+                        region_plan->vertex_owner[c.verts[k]] = c.region;
+                    }
             std::vector<char> collides(static_cast<size_t>(V), 0);
             for (HostBody const& hb : scene.bodies)
                 if (hb.kind == BodyKind::tet && hb.collideable)

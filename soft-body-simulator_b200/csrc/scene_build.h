@@ -139,6 +139,11 @@ struct ResidentParams
     int32_t vertex_bytes = 16; // sizeof(Real4<R>)
     int32_t max_threads  = 512;
     bool rotate_items    = true; // clusters that exchange vertices on the warps with a sub-partition to themselves
+    bool slabs           = false; // regions = whole layers of the cluster grid along its LONGEST axis (consecutive
+                                  // layers per region, at most one region per layer): region boundaries are
+                                  // perpendicular to one axis only, so with the colour order that goes with it six of
+                                  // the eight steps of a sweep on a lattice depend on no other region.  Pays when the
+                                  // axis has about as many layers as there are SMs.
     bool pencils         = true; // regions = bundles of whole cluster columns along the shortest axis of the cluster
                                  // grid (compact in the two other axes) instead of compact Morton blocks: with the
                                  // colour order that goes with it (a Gray code of the cell parities on a lattice)

@@ -9,6 +9,8 @@ namespace sbsb200 {
 
 // Device view of the scene.  Everything is SoA of 16-byte (fp32) / 32-byte (fp64) records so a
 // thread's gather is one vector transaction per record.
+constexpr int kShapeWords = 4; // Real4 records per entry of the rest-shape dictionary
+
 template <typename R>
 struct DeviceScene
 {
@@ -27,7 +29,7 @@ struct DeviceScene
     // rest-shape dictionary: meshes with few distinct (DmInv, V0, material) records — every lattice has
     // ten — stream one byte per tet instead of 48 (n_shapes == 0: no dictionary)
     uint8_t const* tet_shape;
-    Real4<R> const* shapes;    // [3 * n_shapes]: r0, r1, r2 of every distinct record
+    Real4<R> const* shapes;    // [kShapeWords * n_shapes]: r0, r1, r2 of every distinct record and its material (mu, lambda, alpha, beta)
     int32_t n_shapes;
     Real4<R> const* materials; // (mu, lambda, alpha, beta)
     // distance constraints, colour-major
@@ -179,7 +181,7 @@ k_project_green(DeviceScene<R> s, DevChunk chunk, R dt, int first_iteration)
     Real4<R>* s_dict = reinterpret_cast<Real4<R>*>(dict_raw);
     if (kDict)
     {
-        for (int w = threadIdx.x; w < 3 * s.n_shapes; w += blockDim.x)
+        for (int w = threadIdx.x; w < kShapeWords * s.n_shapes; w += blockDim.x)
             s_dict[w] = s.shapes[w];
         __syncthreads();
     }
@@ -199,9 +201,9 @@ k_project_green(DeviceScene<R> s, DevChunk chunk, R dt, int first_iteration)
         if (kDict)
         {
             int const sh = __ldg(&s.tet_shape[t]);
-            r0           = s_dict[3 * sh];
-            r1           = s_dict[3 * sh + 1];
-            r2           = s_dict[3 * sh + 2];
+            r0           = s_dict[kShapeWords * sh];
+            r1           = s_dict[kShapeWords * sh + 1];
+            r2           = s_dict[kShapeWords * sh + 2];
         }
         else
         {

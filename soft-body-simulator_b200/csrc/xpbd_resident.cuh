@@ -204,7 +204,7 @@ struct ResidentArgs
     // rest-shape dictionary (kDict kernels): meshes with few distinct rest shapes — every lattice has ten —
     // keep the (DmInv, V0, material) records in shared memory and stream one byte per tet instead of 48
     uint8_t const* tet_shape;      // per tet: index into shapes
-    Real4<R> const* shapes;        // [3 * n_shapes]: r0, r1, r2 of every distinct record
+    Real4<R> const* shapes;        // [kShapeWords * n_shapes]: r0, r1, r2 and the material of every distinct record
     int32_t n_shapes;
     DevChunk const* chunks;        // [(colour * n_regions + region) * kParts + part] (ClusterPlan::chunks)
     // local vertex tables (ExchangePlan)
@@ -306,7 +306,29 @@ __device__ __forceinline__ bool project_vertex_contacts(DeviceScene<R> const& s,
     return moved;
 }
 
+template <typename R>
+__device__ __forceinline__ bool project_contact(Real4<R>& p, Real4<R>& q, Real4<R> const& m, R at, int first_iteration,
+                                                bool& dirty);
+// the same, continuing at contact j of a vertex whose first contact was handled by the caller
+template <typename R>
+__device__ __forceinline__ bool project_vertex_contacts_from(DeviceScene<R> const& s, uint32_t j, uint32_t n_contacts,
+                                                             Real4<R>& p, R at, int first_iteration)
+{
+    bool moved = false;
+    for (; j < n_contacts && !(s.contact_v[j] & 0x80000000u); ++j)
+    {
+        Real4<R> q       = ld4(&s.contact_q[j]);
+        Real4<R> const m = ld4(&s.contact_n[j]);
+        bool dirty       = false;
+        moved            = project_contact(p, q, m, at, first_iteration, dirty) || moved;
+        if (dirty)
+            st4(&s.contact_q[j], q);
+    }
+    return moved;
+}
+
 constexpr int kMaxShapes = 256;
+constexpr int kTraceWarps = 12; // warps per CTA the trace buffer has room for
 
 // per-tet record as the projection consumes it
 template <typename R, bool kDict>
@@ -361,7 +383,7 @@ __host__ __device__ inline size_t xfirst_area_bytes(int n_colours)
 template <typename R>
 __host__ __device__ inline size_t dict_area_bytes(int n_shapes)
 {
-    return static_cast<size_t>(3 * n_shapes) * sizeof(Real4<R>);
+    return static_cast<size_t>(kShapeWords * n_shapes) * sizeof(Real4<R>);
 }
 
 // What a thread keeps of a cluster between the moment it is prepared (head loaded, shared vertices pulled,
@@ -372,21 +394,53 @@ struct ClusterHead
     TetRecord<R, kDict> tet0;
     R mu, lam, at; // material of the cluster's body; at = alpha / dt^2
 };
+template <typename R>
+struct ClusterHead<R, true>
+{
+    TetRecord<R, true> tet0; // the material comes out of the dictionary with the rest shape
+};
 
 template <typename R, bool kDict>
 __device__ __forceinline__ void load_cluster_head(ClusterHead<R, kDict>& h, ResidentArgs<R> const& a, DevChunk const& ch,
                                                   int32_t i, int first_iteration, Real4<R> const* s_dict)
 {
     h.tet0 = load_tet<R, kDict>(a, a.tet_slots, ch.first + i, first_iteration);
-    R mat_id;
-    if constexpr (kDict)
-        mat_id = s_dict[3 * h.tet0.shape + 2].z; // waits for the shape id: one L2 round trip, a step ahead
-    else
-        mat_id = h.tet0.r2.z;
-    Real4<R> const mat = ld4_ro(&a.s.materials[mat_index(mat_id)]);
-    h.mu               = mat.x;
-    h.lam              = mat.y;
-    h.at               = mat.z / (a.dt * a.dt);
+    if constexpr (!kDict)
+    {
+        Real4<R> const mat = ld4_ro(&a.s.materials[mat_index(h.tet0.r2.z)]);
+        h.mu               = mat.x;
+        h.lam              = mat.y;
+        h.at               = mat.z / (a.dt * a.dt);
+    }
+}
+
+// Early pulls: the words of a pull record whose previous touch lies two or more steps back (or is the predict
+// step) name records that were pushed before the CURRENT step began — they are requested while the current
+// cluster's tets run (the records of a later touch cannot be: they are pushed during this step).
+template <typename R>
+struct EarlyPull
+{
+    typename Xchg<R>::Raw raw[4];
+    uint32_t mask = 0; // words of the record that were requested
+};
+template <typename R>
+__device__ __forceinline__ void pull_request_early(ResidentArgs<R> const& a, int64_t xq, uint4 w, bool after_predict,
+                                                   EarlyPull<R>& early)
+{
+    uint32_t const word[4] = {w.x, w.y, w.z, w.w};
+    uint32_t const nx      = static_cast<uint32_t>(a.n_xclusters);
+    early.mask             = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+    {
+        uint32_t const d = word[e] >> 16 & 0xffu;
+        // d == kPullPredict: pushed in the predict step — early unless that is the current step
+        if ((word[e] & kPullValid) && d >= 2u && (d != kPullPredict || after_predict))
+        {
+            early.raw[e] = Xchg<R>::fetch(a.box, (word[e] >> 24 & 0xfu) * nx + static_cast<uint32_t>(xq), a.world > 1);
+            early.mask |= 1u << e;
+        }
+    }
 }
 
 // Pull the shared vertices of a cluster whose previous touch was by another region: every pull word names
@@ -394,7 +448,7 @@ __device__ __forceinline__ void load_cluster_head(ClusterHead<R, kDict>& h, Resi
 // are in flight together.  `w` = the first group (loaded a step ahead), further groups are rare.
 template <typename R, typename Stamp>
 __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 const* pull_variant, int64_t xq, uint4 w,
-                                             Real4<R>* sx, uint32_t tag, Stamp&& stamp)
+                                             EarlyPull<R> const& early, Real4<R>* sx, uint32_t tag, Stamp&& stamp)
 {
     uint32_t const mine = static_cast<uint32_t>(xq); // mailbox of entry e: e * n_xclusters + xq
     uint32_t const nx   = static_cast<uint32_t>(a.n_xclusters);
@@ -410,6 +464,25 @@ __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 con
             if (word[e] & kPullValid)
                 pending |= 1u << e;
         bool const full = pending == 0xfu;
+        auto const land = [&](int e, typename Xchg<R>::Raw const& raw) {
+            uint32_t const d = word[e] >> 16 & 0xffu;
+            R x, y, z;
+            if (Xchg<R>::decode(raw, d == kPullPredict ? a.base : tag - d, x, y, z))
+            {
+                Real4<R>* dst = &sx[word[e] & 0xffffu];
+                dst->x        = x;
+                dst->y        = y;
+                dst->z        = z;
+                pending &= ~(1u << e);
+            }
+        };
+        if (g == 0)
+        { // the records requested while the tets ran
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (early.mask >> e & 1u)
+                    land(e, early.raw[e]);
+        }
         while (pending)
         {
             typename Xchg<R>::Raw raw[4];
@@ -420,18 +493,7 @@ __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 con
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (pending >> e & 1u)
-                {
-                    uint32_t const d = word[e] >> 16 & 0xffu;
-                    R x, y, z;
-                    if (Xchg<R>::decode(raw[e], d == kPullPredict ? a.base : tag - d, x, y, z))
-                    {
-                        Real4<R>* dst = &sx[word[e] & 0xffffu];
-                        dst->x        = x;
-                        dst->y        = y;
-                        dst->z        = z;
-                        pending &= ~(1u << e);
-                    }
-                }
+                    land(e, raw[e]);
             if (polls == 0)
                 stamp(2);
             if (pending && poll_expired(a.error, ++polls))
@@ -445,15 +507,32 @@ __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 con
 }
 
 // Push the shared vertices of the cluster that just ran whose next touch is by another region.
-// w0, w1 = the first two groups of two (loaded before the tets ran).
+// w0, w1 = the first two groups of two (loaded before the tets ran).  The positions of a batch are read first
+// and the stores issued back to back.
 template <typename R>
 __device__ __forceinline__ void push_cluster(ResidentArgs<R> const& a, uint4 const* push_variant, int64_t xq, uint4 w0,
                                              uint4 w1, Real4<R> const* sx, uint32_t tag)
 {
-    int const groups = a.entries / 2;
-    uint4 w          = w0;
-    for (int g = 0;;)
+    if (!(w0.x & kPullValid))
+        return;
     {
+        uint32_t const slot[4]  = {w0.x, w0.z, w1.x, w1.z};
+        uint32_t const route[4] = {w0.y, w0.w, w1.y, w1.w};
+        Real4<R> p[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            p[e] = sx[slot[e] & 0xffffu]; // slot 0 when the entry is empty: a harmless read
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (slot[e] & kPullValid)
+                push<R>(a, route[e], p[e].x, p[e].y, p[e].z, tag);
+    }
+    if (!(w1.z & kPullValid))
+        return;
+    int const groups = a.entries / 2;
+    for (int g = 2; g < groups; ++g)
+    {
+        uint4 const w = __ldg(&push_variant[static_cast<int64_t>(g) * a.n_xclusters + xq]);
         if (!(w.x & kPullValid))
             break;
         Real4<R> const p = sx[w.x & 0xffffu];
@@ -462,19 +541,19 @@ __device__ __forceinline__ void push_cluster(ResidentArgs<R> const& a, uint4 con
             break;
         Real4<R> const q = sx[w.z & 0xffffu];
         push<R>(a, w.w, q.x, q.y, q.z, tag);
-        if (++g >= groups)
-            break;
-        w = g == 1 ? w1 : __ldg(&push_variant[static_cast<int64_t>(g) * a.n_xclusters + xq]);
     }
 }
 
 // One cluster: project its tets in order out of shared memory (slots of the region's vertex table).
-template <typename R, bool kDict, typename Stamp>
+// after_first() runs once, after the first tet: loads requested at the start of the pass have arrived by then,
+// and what it requests in turn is in flight while the other tets run.
+template <typename R, bool kDict, typename Stamp, typename AfterFirst>
 __device__ __forceinline__ void run_cluster(ResidentArgs<R> const& a, DevChunk const& ch, int32_t i,
                                             ClusterHead<R, kDict> const& head, Real4<R>* sx, Real4<R> const* s_dict,
-                                            int first_iteration, Stamp&& stamp)
+                                            int first_iteration, Stamp&& stamp, AfterFirst&& after_first)
 {
     DeviceScene<R> const& s = a.s;
+    bool first              = true;
     // column layout: tet m of cluster i sits at first + n[0] + .. + n[m-1] + i
     int32_t n0 = ch.n[0], n1 = ch.n[1], n2 = ch.n[2], n3 = ch.n[3], n4 = ch.n[4], n5 = ch.n[5], n6 = ch.n[6],
             n7 = ch.n[7];
@@ -495,20 +574,32 @@ __device__ __forceinline__ void run_cluster(ResidentArgs<R> const& a, DevChunk c
         R lambda = cur.lambda;
         Vec3<R> const z{};
         Real4<R> r0, r1, r2;
+        R mu, lam, at;
         if constexpr (kDict)
         {
-            r0 = s_dict[3 * cur.shape];
-            r1 = s_dict[3 * cur.shape + 1];
-            r2 = s_dict[3 * cur.shape + 2];
+            r0                 = s_dict[kShapeWords * cur.shape];
+            r1                 = s_dict[kShapeWords * cur.shape + 1];
+            r2                 = s_dict[kShapeWords * cur.shape + 2];
+            Real4<R> const mat = s_dict[kShapeWords * cur.shape + 3];
+            mu                 = mat.x;
+            lam                = mat.y;
+            at                 = mat.z / (a.dt * a.dt);
         }
         else
         {
-            r0 = cur.r0;
-            r1 = cur.r1;
-            r2 = cur.r2;
+            r0  = cur.r0;
+            r1  = cur.r1;
+            r2  = cur.r2;
+            mu  = head.mu;
+            lam = head.lam;
+            at  = head.at;
         }
-        green_project_at<R, false>(p1, p2, p3, p4, z, z, z, z, r0, r1, r2, head.mu, head.lam, head.at, R(0), a.dt,
-                                   lambda);
+        green_project_at<R, false>(p1, p2, p3, p4, z, z, z, z, r0, r1, r2, mu, lam, at, R(0), a.dt, lambda);
+        if (first)
+        {
+            after_first();
+            first = false;
+        }
         if (lambda != cur.lambda || first_iteration)
             s.tet_lambda[t] = lambda;
         if (lambda != cur.lambda)
@@ -545,10 +636,34 @@ __device__ __forceinline__ StepItem locate(DevChunk const* group, int32_t i)
     return {3, i - n0 - n1 - n2, -1, -1};
 }
 
+// one collision constraint (collision_constraint.cpp:21-48) given its record: q = (qs, lambda), m = (n, sdf id)
+template <typename R>
+__device__ __forceinline__ bool project_contact(Real4<R>& p, Real4<R>& q, Real4<R> const& m, R at, int first_iteration,
+                                                bool& dirty)
+{
+    R lambda  = first_iteration ? R(0) : q.w;
+    R const C = (p.x - q.x) * m.x + (p.y - q.y) * m.y + (p.z - q.z) * m.z;
+    if (C >= R(0))
+    {
+        dirty = first_iteration != 0; // the reset of lambda (constraint.cpp:12-16) still has to be stored
+        q.w   = lambda;
+        return false;
+    }
+    R const dl = -(C + at * lambda) / (p.w + at);
+    lambda += dl;
+    p.x += p.w * m.x * dl;
+    p.y += p.w * m.y * dl;
+    p.z += p.w * m.z * dl;
+    q.w   = lambda;
+    dirty = true;
+    return true;
+}
+
 // Collision constraints of the surface vertices a cluster is the first of the sweep to touch
 // (collision_constraint.cpp:21-48; gauss_seidel_solver.cpp:28-31 runs them before the elastic constraints of the
 // iteration, and they touch one vertex each, so "right before the first tet that touches the vertex" is the same
 // order).  w0, w1: the first two records (two vertices each), f: their first-contact indices, loaded a step ahead.
+// The records of all four vertices are requested together: one round trip, not one per vertex and field.
 template <typename R>
 __device__ __forceinline__ void collide_cluster(ResidentArgs<R> const& a, int64_t sq, uint4 w0, uint4 w1,
                                                 uint32_t const (&f)[4], uint32_t n_contacts, Real4<R>* sx, R at_c,
@@ -556,12 +671,28 @@ __device__ __forceinline__ void collide_cluster(ResidentArgs<R> const& a, int64_
 {
     DeviceScene<R> const& s = a.s;
     uint32_t const slot[4]  = {w0.x, w0.z, w1.x, w1.z};
+    Real4<R> q[4], m[4];
+    uint32_t next[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if ((slot[e] & kPullValid) && f[e] != 0xffffffffu)
+        {
+            q[e]    = ld4(&s.contact_q[f[e]]);
+            m[e]    = ld4(&s.contact_n[f[e]]);
+            next[e] = f[e] + 1u < n_contacts ? s.contact_v[f[e] + 1u] : 0x80000000u; // bit 31: another vertex's first
+        }
 #pragma unroll
     for (int e = 0; e < 4; ++e)
         if ((slot[e] & kPullValid) && f[e] != 0xffffffffu)
         {
             Real4<R> pp = sx[slot[e] & 0xffffu];
-            if (project_vertex_contacts(s, f[e], n_contacts, pp, at_c, first_iteration))
+            bool dirty  = false;
+            bool moved  = project_contact(pp, q[e], m[e], at_c, first_iteration, dirty);
+            if (dirty)
+                st4(&s.contact_q[f[e]], q[e]);
+            if (!(next[e] & 0x80000000u)) // several SDFs touch this vertex: the others in list order
+                moved = project_vertex_contacts_from(s, f[e] + 1u, n_contacts, pp, at_c, first_iteration) || moved;
+            if (moved)
                 sx[slot[e] & 0xffffu] = pp;
         }
     if (w1.z & kPullValid) // more than four: rare (corners of the mesh)
@@ -619,21 +750,31 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
             s_first[2 * c + 1] = a.chunk_sfirst[static_cast<int64_t>(c) * a.n_regions + region];
         }
         if constexpr (kDict)
-            for (int32_t w = tid; w < 3 * a.n_shapes; w += nt)
+            for (int32_t w = tid; w < kShapeWords * a.n_shapes; w += nt)
                 s_dict[w] = a.shapes[w];
     }
     __syncthreads();
     int32_t traced = 0;
     // cluster i of a step runs on thread (i + rot) % nt (scene_build.h, item_rotation)
     int32_t const my_item = tid >= a.rot ? tid - a.rot : tid + nt - a.rot;
+    // development aid: lane 0 of every warp records %clock64 stamps of its colour steps, 16 per (region, step, warp);
+    // slot 3 holds %globaltimer at the start of the step (clocks of different SMs are not comparable)
     auto stamp = [&](int slot) { // slot < 0: record the value -slot in slot 1 instead of a clock stamp
-        if (kTrace && my_item == 0 && a.trace && traced < a.trace_steps)
+        if (kTrace && (tid & 31) == 0 && a.trace && traced < a.trace_steps)
         {
-            long long* row = &a.trace[(static_cast<int64_t>(region) * a.trace_steps + traced) * 16];
+            long long* row =
+                &a.trace[((static_cast<int64_t>(region) * a.trace_steps + traced) * kTraceWarps + (tid >> 5)) * 16];
             if (slot < 0)
                 row[1] = -slot;
             else
                 row[slot] = clock_stamp();
+            if (slot == 0)
+            {
+                long long g;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+                row[3]  = g;
+                row[5]  = my_item < (s_chunks[kParts * ((traced) % a.n_colours)].n[0] + s_chunks[kParts * ((traced) % a.n_colours) + 1].n[0]) ? 1 : 0;
+            }
         }
     };
     // tag of the last colour step of iteration k that touches a vertex with this schedule
@@ -679,6 +820,9 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
         ClusterHead<R, kDict> nhead;
         uint4 npull = make_uint4(0u, 0u, 0u, 0u), nw0 = npull, nw1 = npull;
         int64_t next_xq = -1, next_sq = -1;
+        EarlyPull<R> early;
+        uint32_t nfirst[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        bool nfirst_loaded = false;
         if (np > 0 && np < n_phases - 1)
         {
             nk                = (np - 1) / C;
@@ -786,7 +930,20 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
                 if (cur.s >= 0 && n_contacts > 0u)
                     collide_cluster<R>(a, static_cast<int64_t>(s_first[2 * c + 1]) + cur.s, cw0, cw1, cfirst, n_contacts, sx,
                                        at_c, k == 0);
-                run_cluster<R, kDict>(a, ch, cur.ci, head, sx, s_dict, k == 0, stamp);
+                run_cluster<R, kDict>(a, ch, cur.ci, head, sx, s_dict, k == 0, stamp, [&] {
+                    if constexpr (kExchange && sizeof(R) == 4)
+                        if (next_xq >= 0 && (npull.x & kPullValid))
+                            pull_request_early<R>(a, next_xq, npull, true, early);
+                    if (next_sq >= 0)
+                    { // first contacts of the surface vertices the next cluster touches first (written by the
+                      // detection, constant during the launch)
+                        nfirst[0] = (nw0.x & kPullValid) ? s.surf_first[nw0.y] : 0xffffffffu;
+                        nfirst[1] = (nw0.z & kPullValid) ? s.surf_first[nw0.w] : 0xffffffffu;
+                        nfirst[2] = (nw1.x & kPullValid) ? s.surf_first[nw1.y] : 0xffffffffu;
+                        nfirst[3] = (nw1.z & kPullValid) ? s.surf_first[nw1.w] : 0xffffffffu;
+                        nfirst_loaded = true;
+                    }
+                });
                 // ---- (3) shared vertices whose next touch is another region's go there first: a neighbour's
                 //          next step waits for them
                 if (xq >= 0)
@@ -805,14 +962,20 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
             cw0  = nw0;
             cw1  = nw1;
             if (kExchange && next_xq >= 0 && (npull.x & kPullValid))
-                pull_cluster<R>(a, a.pull + static_cast<int64_t>(nk > 0 ? 1 : 0) * pull_stride, next_xq, npull, sx,
+                pull_cluster<R>(a, a.pull + static_cast<int64_t>(nk > 0 ? 1 : 0) * pull_stride, next_xq, npull, early, sx,
                                 a.base + static_cast<uint32_t>(np), stamp);
             if (next_sq >= 0)
-            { // first contacts of the surface vertices it touches first (written by the detection, constant here)
-                cfirst[0] = (nw0.x & kPullValid) ? s.surf_first[nw0.y] : 0xffffffffu;
-                cfirst[1] = (nw0.z & kPullValid) ? s.surf_first[nw0.w] : 0xffffffffu;
-                cfirst[2] = (nw1.x & kPullValid) ? s.surf_first[nw1.y] : 0xffffffffu;
-                cfirst[3] = (nw1.z & kPullValid) ? s.surf_first[nw1.w] : 0xffffffffu;
+            {
+                if (!nfirst_loaded)
+                { // (this thread ran no cluster in this pass)
+                    nfirst[0] = (nw0.x & kPullValid) ? s.surf_first[nw0.y] : 0xffffffffu;
+                    nfirst[1] = (nw0.z & kPullValid) ? s.surf_first[nw0.w] : 0xffffffffu;
+                    nfirst[2] = (nw1.x & kPullValid) ? s.surf_first[nw1.y] : 0xffffffffu;
+                    nfirst[3] = (nw1.z & kPullValid) ? s.surf_first[nw1.w] : 0xffffffffu;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    cfirst[e] = nfirst[e];
             }
         }
         if (advance)
@@ -839,7 +1002,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_substep_resident(Re
     DevChunk* s_chunks = reinterpret_cast<DevChunk*>(smem_raw);
     int32_t* s_first   = reinterpret_cast<int32_t*>(smem_raw + chunk_area_bytes(a.n_colours)); // {xfirst, sfirst} per colour
     Real4<R>* s_dict   = reinterpret_cast<Real4<R>*>(smem_raw + chunk_area_bytes(a.n_colours) + xfirst_area_bytes(a.n_colours));
-    Real4<R>* sx       = s_dict + (kDict ? 3 * a.n_shapes : 0);
+    Real4<R>* sx       = s_dict + (kDict ? kShapeWords * a.n_shapes : 0);
     // regions that exchange vertices come first in region_order (at most one per CTA: they must be
     // co-resident), the others follow and are handed out round-robin
     for (int32_t i = blockIdx.x; i < a.n_run; i += gridDim.x)
@@ -997,10 +1160,10 @@ struct ResidentPlan
         if (trace_n > 0)
         { // development aid: clock stamps of the first trace_n colour steps of every launch (sbsb200_debug_read_trace)
             kernel = pick<true>(block, dict, exchange, two_per_sm);
-            trace.upload(std::vector<long long>(static_cast<size_t>(Rn) * trace_n * 16, 0), st);
+            trace.upload(std::vector<long long>(static_cast<size_t>(Rn) * trace_n * kTraceWarps * 16, 0), st);
             args.trace       = trace.p;
             args.trace_steps = trace_n;
-            trace_len        = static_cast<int64_t>(Rn) * trace_n * 16;
+            trace_len        = static_cast<int64_t>(Rn) * trace_n * kTraceWarps * 16;
         }
         else
             kernel = pick<false>(block, dict, exchange, two_per_sm);

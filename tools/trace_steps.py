@@ -1,9 +1,10 @@
-"""Development aid: per-phase cycle breakdown of the persistent kernel's colour steps.
-SBSB200_TRACE_STEPS=N python tools/trace_steps.py <config>"""
+"""Development aid: per-warp cycle breakdown of the resident kernel's colour steps (sbsb200_debug_trace_steps).
+TRACE_STEPS=N REGION_SHAPE=0|1 python tools/trace_steps.py <config>"""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 N = int(os.environ.get("TRACE_STEPS", "80"))
+W = 12
 sbs = importlib.import_module("soft-body-simulator_b200")
 sc = importlib.import_module("soft-body-simulator_b200.scenes")
 cfg = sys.argv[1] if len(sys.argv) > 1 else "config3"
@@ -14,38 +15,42 @@ scene.instantiate(sim)
 for _ in range(3):
     sim.step(scene.dt, scene.substeps, scene.iterations, scene.detect_every_substep)
 sim.synchronize()
-print(sim.stats())
-full = sim.debug_trace().reshape(-1, N, 16)
-t = full[:, :, :8]
-t = t[:, 8:, :]                      # skip the first sweep (cold)
-valid = full[:, 8:, 0] > 0
-def show(name, x):
-    x = x[np.isfinite(x)]
-    if x.size:
-        print("  %-14s mean %8.0f  p50 %8.0f  p95 %8.0f  max %8.0f" % (name, x.mean(), np.percentile(x, 50), np.percentile(x, 95), x.max()))
-f = full[:, 8:, :].astype(np.float64)
-f[f == 0] = np.nan
-print("regions %d, steps %d; cycles per colour step of thread 0 (over regions and steps)" % f.shape[:2])
-show("start->tets", f[:, :, 8] - f[:, :, 0])
-for j in range(1, 6):
-    show("tet%d" % j, f[:, :, 8 + j] - f[:, :, 7 + j])
-last = np.nanmax(f[:, :, 8:14], axis=2)
-show("write back", f[:, :, 15] - last)
-show("->gather next", f[:, :, 4] - f[:, :, 15])
-show("first poll", f[:, :, 2] - f[:, :, 4])
-show("poll rounds", f[:, :, 1])
-show("polls+barrier", f[:, :, 7] - f[:, :, 2])
-show("whole step", f[:, :, 7] - f[:, :, 0])
-C = sim.stats()["n_green_colours"]
-whole = f[:, :, 7] - f[:, :, 0]
-print("whole step by position in the sweep (mean over regions; max over regions = what the slowest region needs):")
-for c in range(C):
-    w = whole[:, c::C]
-    print("  colour %d: mean %7.0f  max-over-regions mean %7.0f  tets %6.0f  push %5.0f" % (
-        c, np.nanmean(w), np.nanmean(np.nanmax(w, axis=0)),
-        np.nanmean((np.nanmax(f[:, c::C, 8:14], axis=2) - f[:, c::C, 8])), np.nanmean(f[:, c::C, 15] - np.nanmax(f[:, c::C, 8:14], axis=2))))
-# time between the barriers of consecutive steps of one region = the step as the region experiences it
-gap = np.diff(f[:, :, 7], axis=1)
+st = sim.stats()
+print(st)
+C = st["n_green_colours"]
+full = sim.debug_trace().reshape(-1, N, W, 16).astype(np.float64)
+full[full == 0] = np.nan
+f = full[:, C:, :, :]                      # skip the first sweep (cold)
+nw = int(np.isfinite(f[0, 0, :, 0]).sum())
+print("regions %d, steps %d, warps %d" % (f.shape[0], f.shape[1], nw))
+f = f[:, :, :nw, :]
+t0 = np.nanmin(f[:, :, :, 0], axis=2, keepdims=True)          # step start of the region = first warp out of the barrier
+rel = lambda slot: f[:, :, :, slot] - t0[:, :, :]
+last_tet = np.nanmax(f[:, :, :, 8:14], axis=3) - t0[:, :, :]
+def by_colour(x, name):
+    # x: [regions, steps, warps] -> per colour (position in sweep): mean over regions & sweeps, per warp
+    print(name)
+    for c in range(C):
+        v = x[:, c::C, :]
+        print("  colour %d: per warp %s | mean %6.0f  max-over-regions %6.0f" % (
+            c, " ".join("%6.0f" % np.nanmean(v[:, :, w]) for w in range(nw)), np.nanmean(v),
+            np.nanmean(np.nanmax(np.nanmax(v, axis=2), axis=0))))
+by_colour(rel(8), "first tet starts (prepare after the barrier + collision constraints of first touches)")
+by_colour(last_tet, "last tet done")
+by_colour(rel(15), "pushes issued")
+by_colour(rel(2), "first poll round answered (pulls for the NEXT step; empty when the warp's lane 0 pulls nothing)")
+by_colour(f[:, :, :, 1], "poll rounds")
+by_colour(rel(6) , "ready for the barrier... (before the pulls)")
+by_colour(rel(7), "out of the barrier = step done")
+gap = np.diff(np.nanmin(f[:, :, :, 7], axis=2), axis=1)
 print("barrier-to-barrier: mean %.0f p50 %.0f p95 %.0f" % (np.nanmean(gap), np.nanpercentile(gap, 50), np.nanpercentile(gap, 95)))
 for c in range(C):
-    print("  into colour %d: %.0f" % ((c + 1) % C, np.nanmean(gap[:, c::C])))
+    print("  into colour %d: mean %.0f  max-over-regions %.0f" % ((c + 1) % C, np.nanmean(gap[:, c::C]), np.nanmean(np.nanmax(gap[:, c::C], axis=0))))
+g = np.nanmin(f[:, :, :, 3], axis=2)      # globaltimer (ns) at the start of a step, per region
+skew = g - np.nanmin(g, axis=0, keepdims=True)
+print("start skew between regions (ns): per colour mean of max %s" % [int(np.nanmean(np.nanmax(skew[:, c::C], axis=0))) for c in range(C)])
+step_ns = np.diff(np.nanmin(g, axis=0))
+print("global step (first region to first region, ns): by colour %s" % [int(np.nanmean(step_ns[c::C])) for c in range(C)])
+late = np.nanmean(skew, axis=1)
+o = np.argsort(late)
+print("regions that start latest on average (ns): %s ; earliest: %s" % ([(int(r), int(late[r])) for r in o[-8:]], [(int(r), int(late[r])) for r in o[:4]]))
