@@ -57,9 +57,6 @@ extern "C" {
 #define SBSB200_REGIONS_PENCILS 0 /* bundles of cell columns along the shortest axis (default): half of the colour
                                    * steps of a sweep on a lattice then exchange nothing between regions */
 #define SBSB200_REGIONS_COMPACT 1 /* compact blocks in Morton order */
-#define SBSB200_REGIONS_SLABS 2   /* whole layers of cells along the longest axis, at most one region per layer: six of
-                                   * the eight colour steps exchange nothing; fewer regions than SMs when the axis is
-                                   * short (single GPU only; falls back to pencils when a layer does not fit) */
 
 typedef struct sbsb200_ctx sbsb200_ctx;
 

@@ -634,8 +634,8 @@ struct Engine final : EngineBase
                         // regions and parts of one colour are adjacent in storage, but each has its own
                         // column layout -> one launch each (a single launch when there is no region plan)
                         ChunkDesc const* hd =
-                            &c.green_plan.chunks[static_cast<size_t>(col) * kParts * c.green_plan.n_regions];
-                        for (int32_t rp = 0; rp < kParts * c.green_plan.n_regions; ++rp)
+                            &c.green_plan.chunks[static_cast<size_t>(col) * 2 * c.green_plan.n_regions];
+                        for (int32_t rp = 0; rp < 2 * c.green_plan.n_regions; ++rp)
                         {
                             ChunkDesc const& h2 = hd[rp];
                             if (h2.n[0] == 0)
@@ -1141,7 +1141,7 @@ int sbsb200_set_broadphase(sbsb200_ctx* c, int mode)
 
 int sbsb200_set_region_shape(sbsb200_ctx* c, int shape)
 {
-    if (!c || (shape != SBSB200_REGIONS_PENCILS && shape != SBSB200_REGIONS_COMPACT && shape != SBSB200_REGIONS_SLABS))
+    if (!c || (shape != SBSB200_REGIONS_PENCILS && shape != SBSB200_REGIONS_COMPACT))
         return fail(c, SBSB200_ERR_INVALID, "bad region shape");
     if (c->finalized)
         return fail(c, SBSB200_ERR_STATE, "scene already finalized");
@@ -1541,16 +1541,14 @@ int sbsb200_finalize(sbsb200_ctx* c)
             // per region), two smaller compact regions per SM
             struct Attempt
             {
-                bool slabs, pencils;
+                bool pencils;
                 int per_sm;
             };
             std::vector<Attempt> attempts;
-            if (c->region_shape == SBSB200_REGIONS_SLABS && c->world == 1)
-                attempts.push_back({true, false, 1});
             if (c->region_shape != SBSB200_REGIONS_COMPACT)
-                attempts.push_back({false, true, 1});
-            attempts.push_back({false, false, 1});
-            attempts.push_back({false, false, 2});
+                attempts.push_back({true, 1});
+            attempts.push_back({false, 1});
+            attempts.push_back({false, 2});
             for (Attempt const& at : attempts)
             {
                 if (planned)
@@ -1559,7 +1557,6 @@ int sbsb200_finalize(sbsb200_ctx* c)
                 ResidentParams rp = c->precision == SBSB200_FP32 ? ResidentPlan<float>::resident_params()
                                                                  : ResidentPlan<double>::resident_params();
                 rp.pencils     = at.pencils;
-                rp.slabs       = at.slabs;
                 rp.smem_bytes  = rp.smem_bytes / per_sm - (per_sm > 1 ? 4096 : 0);
                 rp.max_threads = per_sm == 1 ? 384 : 192;
                 int32_t n_regions = regions_for(c->sm_count, T, c->world);
@@ -1686,10 +1683,10 @@ int sbsb200_get_stats(const sbsb200_ctx* cc, sbsb200_stats* out)
     out->frames               = c->frames;
     out->last_contact_count   = c->last_contacts;
     out->n_shared_vertices    = c->xplan.n_shared;
-    out->pulls_per_sweep      = c->xplan.n_pulls[1];
+    out->pulls_per_sweep      = c->xplan.n_pulls[2];
     out->pushes_per_sweep     = c->xplan.n_pushes[0];
     for (int64_t n : c->xplan.pulls_by_colour)
-        out->quiet_colours += c->schedule == SBSB200_SCHED_PERSISTENT && 50 * n <= c->xplan.n_pulls[1];
+        out->quiet_colours += c->schedule == SBSB200_SCHED_PERSISTENT && 50 * n <= c->xplan.n_pulls[2];
     if (c->engine)
     {
         cudaSetDevice(c->device);

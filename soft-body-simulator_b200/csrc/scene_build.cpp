@@ -377,7 +377,9 @@ struct Cluster
     uint64_t morton;
     uint32_t first, count; // range in the (body, cell)-sorted tet list
     int32_t colour = -1, region = 0;
-    int32_t part = kParts - 1; // see ClusterPlan::chunks
+    int32_t part = 1;      // 0 = has a vertex that another region touches too, 1 = private to its region
+    int32_t prio = 2;      // position inside its chunk: 0 = pushes a vertex to another region in its step, 1 = pulls
+                           // one that was pushed in the very previous step, 2 = neither
     uint32_t nv = 0;       // unique vertices
     uint32_t verts[4 * kMaxCluster];
 };
@@ -551,30 +553,6 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         out.n_regions = std::max<int32_t>(1, (nb + group - 1) / group);
         for (Cluster& c : clusters)
             c.region = body_index[static_cast<size_t>(c.body)] / group;
-    }
-    else if (n_regions > 1 && resident && resident->slabs && !clusters.empty())
-    { // layers of the cluster grid along its longest axis, consecutive layers per region, at most one region per layer
-        uint32_t lo[3] = {~0u, ~0u, ~0u}, hi[3] = {0u, 0u, 0u};
-        for (Cluster const& c : clusters)
-        {
-            uint32_t const g[3] = {c.cx, c.cy, c.cz};
-            for (int d = 0; d < 3; ++d)
-            {
-                lo[d] = std::min(lo[d], g[d]);
-                hi[d] = std::max(hi[d], g[d]);
-            }
-        }
-        int axis = 0;
-        for (int d = 1; d < 3; ++d)
-            if (hi[d] - lo[d] > hi[axis] - lo[axis])
-                axis = d;
-        int64_t const layers = static_cast<int64_t>(hi[axis] - lo[axis]) + 1;
-        out.n_regions        = static_cast<int32_t>(std::min<int64_t>(n_regions, layers));
-        for (Cluster& c : clusters)
-        {
-            uint32_t const g[3] = {c.cx, c.cy, c.cz};
-            c.region = static_cast<int32_t>((static_cast<int64_t>(g[axis] - lo[axis]) * out.n_regions) / layers);
-        }
     }
     else if (n_regions > 1)
     {
@@ -758,32 +736,67 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         if (region_plan)
         {
             classify_regions(scene, out.tet_region, out.n_regions, *region_plan);
-            // the first colour of a sweep that touches a vertex: that cluster projects the vertex's contacts
-            // A vertex is OWNED (predicted, committed, its surface copy written) by the region of that cluster: its
-            // first touch after the predict step is then local, and the contacts a rank of a decomposed scene
-            // detects for the vertices it owns are the ones its own clusters project.
-            std::vector<int32_t> first_colour(static_cast<size_t>(V), 0x7fffffff);
-            for (Cluster const& c : clusters)
-                for (uint32_t k = 0; k < c.nv; ++k)
-                    if (c.colour < first_colour[c.verts[k]])
-                    {
-                        first_colour[c.verts[k]]            = c.colour;
-                        region_plan->vertex_owner[c.verts[k]] = c.region;
-                    }
-            std::vector<char> collides(static_cast<size_t>(V), 0);
-            for (HostBody const& hb : scene.bodies)
-                if (hb.kind == BodyKind::tet && hb.collideable)
-                    for (uint32_t lv : hb.surf_to_tet)
-                        collides[static_cast<size_t>(hb.v_offset + lv)] = 1;
             for (Cluster& c : clusters)
-            {
-                bool exchanges = false, first_touch = false;
+            { // part 0: the cluster has a vertex that another region touches too
+                c.part = 1;
                 for (uint32_t k = 0; k < c.nv; ++k)
+                    if (region_plan->vertex_region[c.verts[k]] != c.region)
+                        c.part = 0;
+            }
+            // A vertex is OWNED (predicted, collided, committed, its surface copy written) by the region of the
+            // first cluster of a sweep that touches it: after the owner's steps its next touch is then local, and the
+            // contacts a rank of a decomposed scene detects for the vertices it owns are the ones it projects.
+            {
+                std::vector<int32_t> first_colour(static_cast<size_t>(V), 0x7fffffff);
+                for (Cluster const& c : clusters)
+                    for (uint32_t k = 0; k < c.nv; ++k)
+                        if (c.colour < first_colour[c.verts[k]])
+                        {
+                            first_colour[c.verts[k]]              = c.colour;
+                            region_plan->vertex_owner[c.verts[k]] = c.region;
+                        }
+            }
+            // Inside a chunk the clusters that PUSH in their step come first, then those that wait for a record
+            // pushed in the step before: the first clusters of a step run on the warps that have a sub-partition
+            // to themselves (item_rotation) and finish early, so what a neighbour waits for leaves early, and who
+            // waits does so on a warp the others do not wait for.
+            {
+                struct Touch4
                 {
-                    exchanges   = exchanges || region_plan->vertex_region[c.verts[k]] != c.region;
-                    first_touch = first_touch || (collides[c.verts[k]] && first_colour[c.verts[k]] == c.colour);
+                    uint32_t v;
+                    int32_t colour, region;
+                    uint32_t cluster;
+                };
+                std::vector<Touch4> tl;
+                for (size_t ci = 0; ci < clusters.size(); ++ci)
+                    if (clusters[ci].part == 0)
+                        for (uint32_t k = 0; k < clusters[ci].nv; ++k)
+                            if (region_plan->vertex_region[clusters[ci].verts[k]] < 0)
+                                tl.push_back({clusters[ci].verts[k], clusters[ci].colour, clusters[ci].region,
+                                              static_cast<uint32_t>(ci)});
+                std::sort(tl.begin(), tl.end(), [](Touch4 const& a, Touch4 const& b) {
+                    return a.v != b.v ? a.v < b.v : a.colour < b.colour;
+                });
+                int32_t const C = out.n_colours;
+                for (size_t i = 0; i < tl.size();)
+                {
+                    size_t j = i;
+                    while (j < tl.size() && tl[j].v == tl[i].v)
+                        ++j;
+                    size_t const n = j - i;
+                    for (size_t t = 0; t < n; ++t)
+                    {
+                        Touch4 const& me   = tl[i + t];
+                        Touch4 const& next = tl[i + (t + 1) % n];
+                        Touch4 const& prev = tl[i + (t + n - 1) % n];
+                        Cluster& c         = clusters[me.cluster];
+                        if (next.region != me.region)
+                            c.prio = 0;
+                        else if (prev.region != me.region && (me.colour - prev.colour + C) % C == 1)
+                            c.prio = std::min(c.prio, 1);
+                    }
+                    i = j;
                 }
-                c.part = (exchanges ? 0 : 2) + (first_touch ? 0 : 1);
             }
         }
         // threads per CTA: every cluster of a (colour, region) step gets its own thread when possible
@@ -814,12 +827,14 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
             return x.part < y.part;
         if (x.count != y.count)
             return x.count > y.count;
+        if (x.prio != y.prio)
+            return x.prio < y.prio;
         if (x.body != y.body)
             return x.body < y.body;
         return x.morton < y.morton;
     });
 
-    size_t const n_chunks = static_cast<size_t>(out.n_colours) * static_cast<size_t>(out.n_regions) * kParts;
+    size_t const n_chunks = static_cast<size_t>(out.n_colours) * static_cast<size_t>(out.n_regions) * 2;
     out.chunks.assign(n_chunks, ChunkDesc{});
     out.storage_order.resize(static_cast<size_t>(T));
     out.serial_order.reserve(static_cast<size_t>(T));
@@ -828,9 +843,9 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
     int64_t pair_clusters = 0;
     for (size_t ch = 0; ch < n_chunks; ++ch)
     {
-        int32_t const col  = static_cast<int32_t>(ch / (kParts * static_cast<size_t>(out.n_regions)));
-        int32_t const reg  = static_cast<int32_t>((ch / kParts) % static_cast<size_t>(out.n_regions));
-        int32_t const part = static_cast<int32_t>(ch % kParts);
+        int32_t const col  = static_cast<int32_t>(ch / (2 * static_cast<size_t>(out.n_regions)));
+        int32_t const reg  = static_cast<int32_t>((ch / 2) % static_cast<size_t>(out.n_regions));
+        int32_t const part = static_cast<int32_t>(ch % 2);
         size_t j           = i;
         while (j < idx.size() && clusters[idx[j]].colour == col && clusters[idx[j]].region == reg &&
                clusters[idx[j]].part == part)
@@ -902,56 +917,14 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
     int64_t nx = 0;
     uint32_t most_shared = 0;
     std::vector<int32_t> pos_cluster(static_cast<size_t>(T), 0); // storage position -> cluster
-    // collision clusters: the surface vertices a cluster is the first of a sweep to touch
-    std::vector<int32_t> first_colour(static_cast<size_t>(V), 0x7fffffff);
-    std::vector<uint32_t> surface_index(static_cast<size_t>(V), kRouteNone); // index in DeviceScene::surf_v order
-    {
-        uint32_t s = 0;
-        for (HostBody const& hb : scene.bodies)
-            if (hb.kind == BodyKind::tet)
-                for (uint32_t lv : hb.surf_to_tet)
-                {
-                    if (hb.collideable)
-                        surface_index[static_cast<size_t>(hb.v_offset + lv)] = s;
-                    ++s;
-                }
-    }
     for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
     {
         ChunkDesc const& d = cp.chunks[ch];
-        int32_t const col = static_cast<int32_t>(ch / (kParts * static_cast<size_t>(Rn)));
-        for (int32_t i = 0; i < d.n[0]; ++i)
-        {
-            int64_t base = d.first;
-            for (int m = 0; m < kMaxCluster && i < d.n[m]; ++m)
-            {
-                uint32_t const t = cp.storage_order[static_cast<size_t>(base + i)];
-                for (int a = 0; a < 4; ++a)
-                {
-                    int32_t& f = first_colour[scene.tets[4 * static_cast<size_t>(t) + a]];
-                    f          = std::min(f, col);
-                }
-                base += d.n[m];
-            }
-        }
-    }
-    out.chunk_sfirst.assign(static_cast<size_t>(C) * Rn, 0);
-    int64_t ns = 0;
-    std::vector<std::vector<uint32_t>> coll_words; // per collision cluster: {slot word, surface index} pairs (slots filled below)
-    std::vector<std::pair<int64_t, uint32_t>> coll_pending; // (collision cluster, vertex) in the order of coll_words
-    for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
-    {
-        ChunkDesc const& d = cp.chunks[ch];
-        int32_t const col = static_cast<int32_t>(ch / (kParts * static_cast<size_t>(Rn)));
-        int32_t const reg = static_cast<int32_t>((ch / kParts) % static_cast<size_t>(Rn));
-        int32_t const part4 = static_cast<int32_t>(ch % kParts);
-        int32_t const part = part4 < 2 ? 0 : 1; // 0: exchanges
-        bool const collision_part = part4 % 2 == 0;
-        if (part4 == 0)
-        {
+        int32_t const col = static_cast<int32_t>(ch / (2 * static_cast<size_t>(Rn)));
+        int32_t const reg = static_cast<int32_t>((ch / 2) % static_cast<size_t>(Rn));
+        int32_t const part = static_cast<int32_t>(ch % 2);
+        if (part == 0)
             out.chunk_xfirst[static_cast<size_t>(col) * Rn + reg] = static_cast<int32_t>(nx);
-            out.chunk_sfirst[static_cast<size_t>(col) * Rn + reg] = static_cast<int32_t>(ns);
-        }
         for (int32_t i = 0; i < d.n[0]; ++i)
         {
             Cl& c      = cl[static_cast<size_t>(d.cfirst + i)];
@@ -987,47 +960,9 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
                 return false;
             }
             most_shared = std::max(most_shared, c.n_shared);
-            // first touches of surface vertices
-            uint32_t n_first = 0;
-            {
-                uint32_t seen[4 * kMaxCluster];
-                uint32_t n_seen = 0;
-                int64_t b2 = d.first;
-                for (int m = 0; m < kMaxCluster && i < d.n[m]; ++m)
-                {
-                    uint32_t const t = cp.storage_order[static_cast<size_t>(b2 + i)];
-                    for (int a = 0; a < 4; ++a)
-                    {
-                        uint32_t const v = scene.tets[4 * static_cast<size_t>(t) + a];
-                        if (surface_index[v] == kRouteNone || first_colour[v] != col ||
-                            std::find(seen, seen + n_seen, v) != seen + n_seen)
-                            continue;
-                        seen[n_seen++] = v;
-                        if (!collision_part)
-                        {
-                            out.why_not = "cluster parts and first touches of surface vertices disagree";
-                            return false;
-                        }
-                        coll_pending.emplace_back(ns, v);
-                        ++n_first;
-                    }
-                    b2 += d.n[m];
-                }
-            }
-            if (collision_part)
-            {
-                if (n_first == 0)
-                {
-                    out.why_not = "a cluster of a collision part touches no surface vertex first";
-                    return false;
-                }
-                out.coll_groups = std::max<int32_t>(out.coll_groups, static_cast<int32_t>((n_first + 1) / 2));
-                ++ns;
-            }
         }
     }
     out.n_xclusters = nx;
-    out.n_sclusters = ns;
     out.entries     = static_cast<int32_t>(std::max<uint32_t>(4u, (most_shared + 3u) / 4u * 4u));
 
     // ---- local vertex tables: owned vertices first, then guests -------------------------------------------
@@ -1102,6 +1037,11 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
 
     // ---- shared vertices: owner records and the touch chains ---------------------------------------------
     out.n_entries = static_cast<uint32_t>(static_cast<int64_t>(out.entries) * nx);
+    std::vector<char> is_surface(static_cast<size_t>(V), 0);
+    for (HostBody const& hb : scene.bodies)
+        if (hb.kind == BodyKind::tet)
+            for (uint32_t lv : hb.surf_to_tet)
+                is_surface[static_cast<size_t>(hb.v_offset + lv)] = 1;
     out.osv_off.assign(static_cast<size_t>(Rn) + 1, 0);
     std::vector<uint32_t> osv_pos(static_cast<size_t>(V), kRouteNone);
     for (int64_t v = 0; v < V; ++v)
@@ -1152,7 +1092,8 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
         return (out.n_entries + osv_pos[v]) | (rank_of(plan.vertex_owner[v]) << kRouteRankShift);
     };
     // per (variant, exchange cluster): the words, in the order of the cluster's shared vertices
-    std::vector<std::vector<uint32_t>> pulls(2 * static_cast<size_t>(nx)), pushes(2 * static_cast<size_t>(nx));
+    std::vector<std::vector<uint32_t>> pulls(4 * static_cast<size_t>(nx)), pushes(4 * static_cast<size_t>(nx));
+    std::vector<char> colour_pulls(static_cast<size_t>(std::max(C, 1)), 0);
     out.pulls_by_colour.assign(static_cast<size_t>(std::max(C, 1)), 0);
     for (size_t i = 0; i < touches.size();)
     {
@@ -1161,6 +1102,7 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
             ++j;
         uint32_t const v    = touches[i].vertex;
         int32_t const owner = plan.vertex_owner[v];
+        bool const surf     = is_surface[v] != 0;
         Touch const& first  = touches[i];
         Touch const& last   = touches[j - 1];
         for (size_t t = i; t + 1 < j; ++t)
@@ -1169,7 +1111,8 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
                 out.why_not = "two clusters of one colour touch the same vertex";
                 return false;
             }
-        out.osv_meta[osv_pos[v]]  = static_cast<uint32_t>(last.colour) | (last.region != owner ? kOsvLastRemote : 0u) |
+        out.osv_meta[osv_pos[v]]  = static_cast<uint32_t>(last.colour) | (surf ? kOsvSurface : 0u) |
+                                   (last.region != owner ? kOsvLastRemote : 0u) |
                                    (first.region != owner ? kOsvFirstRemote : 0u);
         out.osv_first[osv_pos[v]] = entry_route(first);
         for (size_t t = i; t < j; ++t)
@@ -1177,67 +1120,80 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
             Touch const& me     = touches[t];
             uint32_t const slot = slot_of(me.region, v);
             for (int later = 0; later < 2; ++later)
-            { // the previous touch: a colour of the same sweep, the last colour of the previous sweep, or the
-              // owner's predict step
-                int32_t from, d;
-                if (t > i)
-                {
-                    from = touches[t - 1].region;
-                    d    = me.colour - touches[t - 1].colour;
+                for (int cs = 0; cs < 2; ++cs)
+                { // the previous touch: a colour of the same sweep, the owner's collision step, the last colour of
+                  // the previous sweep, or the owner's predict step
+                    int32_t from, d;
+                    if (t > i)
+                    {
+                        from = touches[t - 1].region;
+                        d    = me.colour - touches[t - 1].colour;
+                    }
+                    else if (cs && surf)
+                    {
+                        from = owner;
+                        d    = me.colour + 1;
+                    }
+                    else if (later)
+                    {
+                        from = last.region;
+                        d    = C + cs + me.colour - last.colour;
+                    }
+                    else
+                    {
+                        from = owner;
+                        d    = static_cast<int32_t>(kPullPredict);
+                    }
+                    if (from != me.region)
+                    {
+                        pulls[static_cast<size_t>(2 * later + cs) * nx + me.xq].push_back(
+                            kPullValid | (me.entry << 24) | (static_cast<uint32_t>(d) << 16) | slot);
+                        ++out.n_pulls[2 * later + cs];
+                        if (later && !cs)
+                        {
+                            colour_pulls[static_cast<size_t>(me.colour)] = 1;
+                            ++out.pulls_by_colour[static_cast<size_t>(me.colour)];
+                        }
+                    }
                 }
-                else if (later)
-                {
-                    from = last.region;
-                    d    = C + me.colour - last.colour;
-                }
-                else
-                {
-                    from = owner;
-                    d    = static_cast<int32_t>(kPullPredict);
-                }
-                if (from != me.region)
-                {
-                    pulls[static_cast<size_t>(later) * nx + me.xq].push_back(kPullValid | (me.entry << 24) |
-                                                                           (static_cast<uint32_t>(d) << 16) | slot);
-                    ++out.n_pulls[later];
-                    if (later)
-                        ++out.pulls_by_colour[static_cast<size_t>(me.colour)];
-                }
-            }
             for (int final_sweep = 0; final_sweep < 2; ++final_sweep)
-            { // the next touch: a colour of the same sweep, the first colour of the next sweep, or the owner's commit
-                int32_t to;
-                uint32_t route;
-                if (t + 1 < j)
-                {
-                    to    = touches[t + 1].region;
-                    route = entry_route(touches[t + 1]);
+                for (int cs = 0; cs < 2; ++cs)
+                { // the next touch: a colour of the same sweep, the owner (collision step of the next sweep, or
+                  // commit), or the first colour of the next sweep
+                    int32_t to;
+                    uint32_t route;
+                    if (t + 1 < j)
+                    {
+                        to    = touches[t + 1].region;
+                        route = entry_route(touches[t + 1]);
+                    }
+                    else if ((cs && surf) || final_sweep)
+                    {
+                        to    = owner;
+                        route = owner_route(v);
+                    }
+                    else
+                    {
+                        to    = first.region;
+                        route = entry_route(first);
+                    }
+                    if (to != me.region)
+                    {
+                        auto& w = pushes[static_cast<size_t>(2 * final_sweep + cs) * nx + me.xq];
+                        w.push_back(kPullValid | slot);
+                        w.push_back(route);
+                        ++out.n_pushes[2 * final_sweep + cs];
+                    }
                 }
-                else if (final_sweep)
-                {
-                    to    = owner;
-                    route = owner_route(v);
-                }
-                else
-                {
-                    to    = first.region;
-                    route = entry_route(first);
-                }
-                if (to != me.region)
-                {
-                    auto& w = pushes[static_cast<size_t>(final_sweep) * nx + me.xq];
-                    w.push_back(kPullValid | slot);
-                    w.push_back(route);
-                    ++out.n_pushes[final_sweep];
-                }
-            }
         }
         i = j;
     }
+    for (int32_t c = 0; c < C; ++c)
+        out.quiet_steps += !colour_pulls[static_cast<size_t>(c)];
     size_t const E = static_cast<size_t>(out.entries);
-    out.pull.assign(2 * E * static_cast<size_t>(nx), 0u);
-    out.push.assign(2 * 2 * E * static_cast<size_t>(nx), 0u);
-    for (size_t var = 0; var < 2; ++var)
+    out.pull.assign(4 * E * static_cast<size_t>(nx), 0u);
+    out.push.assign(4 * 2 * E * static_cast<size_t>(nx), 0u);
+    for (size_t var = 0; var < 4; ++var)
         for (int64_t xq = 0; xq < nx; ++xq)
         {
             auto const& pl = pulls[var * static_cast<size_t>(nx) + xq];
@@ -1251,27 +1207,6 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
                 out.push[at + 1] = ps[2 * k + 1];
             }
         }
-    // collision words: [group][collision cluster][4]
-    out.coll_groups = std::max<int32_t>(out.coll_groups, 1);
-    out.coll.assign(static_cast<size_t>(out.coll_groups) * static_cast<size_t>(ns) * 4, 0u);
-    {
-        std::vector<int32_t> filled(static_cast<size_t>(ns), 0);
-        std::vector<int32_t> scl_region(static_cast<size_t>(ns), 0);
-        { // region of every collision cluster
-            int64_t s2 = 0;
-            for (size_t ch = 0; ch < cp.chunks.size(); ++ch)
-                if (ch % kParts % 2 == 0)
-                    for (int32_t i2 = 0; i2 < cp.chunks[ch].n[0]; ++i2)
-                        scl_region[static_cast<size_t>(s2++)] = static_cast<int32_t>((ch / kParts) % static_cast<size_t>(Rn));
-        }
-        for (auto const& pv : coll_pending)
-        {
-            int32_t const k = filled[static_cast<size_t>(pv.first)]++;
-            size_t const at = ((static_cast<size_t>(k / 2)) * static_cast<size_t>(ns) + static_cast<size_t>(pv.first)) * 4 + 2 * (k % 2);
-            out.coll[at]     = kPullValid | slot_of(scl_region[static_cast<size_t>(pv.first)], pv.second);
-            out.coll[at + 1] = surface_index[pv.second];
-        }
-    }
 
     // ---- surface vertices by owner -----------------------------------------------------------------------
     std::vector<uint32_t> sgv; // global vertex of surface vertex i (the order of DeviceScene::surf_v)
@@ -1286,6 +1221,7 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
         out.surf_off[static_cast<size_t>(r) + 1] += out.surf_off[static_cast<size_t>(r)];
     out.surf_slot.assign(sgv.size(), 0);
     out.surf_index.assign(sgv.size(), 0);
+    out.surf_osv.assign(sgv.size(), kRouteNone);
     {
         std::vector<int32_t> cur(out.surf_off.begin(), out.surf_off.end() - 1);
         for (size_t s = 0; s < sgv.size(); ++s)
@@ -1294,6 +1230,7 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
             int32_t const at  = cur[static_cast<size_t>(plan.vertex_owner[gv])]++;
             out.surf_slot[static_cast<size_t>(at)]  = owner_slot[gv];
             out.surf_index[static_cast<size_t>(at)] = static_cast<uint32_t>(s);
+            out.surf_osv[static_cast<size_t>(at)]   = osv_pos[gv];
         }
     }
     return true;
@@ -1316,10 +1253,10 @@ bool cluster_plan_is_valid(HostScene const& scene, ClusterPlan const& plan)
     std::vector<int32_t> stamp(static_cast<size_t>(V), -1);
     int64_t cluster_id = 0;
     for (int32_t col = 0; col < plan.n_colours; ++col)
-        for (int32_t rp = 0; rp < kParts * plan.n_regions; ++rp)
+        for (int32_t rp = 0; rp < 2 * plan.n_regions; ++rp)
         {
-            int32_t const reg  = rp / kParts;
-            ChunkDesc const& d = plan.chunks[static_cast<size_t>(col) * kParts * plan.n_regions + rp];
+            int32_t const reg  = rp / 2;
+            ChunkDesc const& d = plan.chunks[static_cast<size_t>(col) * 2 * plan.n_regions + rp];
             for (int32_t i = 0; i < d.n[0]; ++i, ++cluster_id)
             {
                 int64_t base = d.first;

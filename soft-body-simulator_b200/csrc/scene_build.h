@@ -121,7 +121,6 @@ void plan_regions(HostScene const& scene, std::vector<uint64_t> const& tet_keys,
 // The equivalent serial Gauss-Seidel order is: colour, cluster, tet-in-cluster.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxCluster = 8;
-constexpr int kParts      = 4; // chunks per (colour, region), see ClusterPlan::chunks
 constexpr int kMaxClusterVertices = 16; // scratch entries per thread in the resident schedule
 
 struct ChunkDesc
@@ -139,11 +138,6 @@ struct ResidentParams
     int32_t vertex_bytes = 16; // sizeof(Real4<R>)
     int32_t max_threads  = 512;
     bool rotate_items    = true; // clusters that exchange vertices on the warps with a sub-partition to themselves
-    bool slabs           = false; // regions = whole layers of the cluster grid along its LONGEST axis (consecutive
-                                  // layers per region, at most one region per layer): region boundaries are
-                                  // perpendicular to one axis only, so with the colour order that goes with it six of
-                                  // the eight steps of a sweep on a lattice depend on no other region.  Pays when the
-                                  // axis has about as many layers as there are SMs.
     bool pencils         = true; // regions = bundles of whole cluster columns along the shortest axis of the cluster
                                  // grid (compact in the two other axes) instead of compact Morton blocks: with the
                                  // colour order that goes with it (a Gray code of the cell parities on a lattice)
@@ -170,17 +164,15 @@ struct ClusterPlan
     int64_t n_clusters = 0;
     std::vector<uint32_t> storage_order; // storage position -> tet (index into HostScene::tets / 4)
     std::vector<uint32_t> serial_order;  // equivalent serial order of tets (colour, region, part, cluster, tet)
-    // [(colour * n_regions + region) * kParts + part].  Resident schedule: parts 0, 1 = clusters with a vertex
-    // that another region touches too (they exchange it through mailboxes), parts 2, 3 = clusters private to
-    // the region; parts 0, 2 = clusters that are the FIRST of a sweep to touch some surface vertex (they project
-    // its collision constraints before their tets), parts 1, 3 = the others.  Without a region plan everything
-    // is in part 3.
+    // [(colour * n_regions + region) * 2 + part]; part 0 = clusters with a vertex that another region touches
+    // too (they exchange it through mailboxes), part 1 = clusters private to the region.  Without a region
+    // plan everything is in part 1.
     std::vector<ChunkDesc> chunks;
     std::vector<int32_t> tet_region;     // T
     int64_t max_chunk_clusters = 0;      // max over (colour, region) of the clusters of both parts
     // resident schedule only
     int32_t nt  = 0;                     // threads per CTA
-    int32_t rot = 0;                     // cluster i of a step (parts in order) runs on thread (i + rot) % nt, see item_rotation
+    int32_t rot = 0;                     // cluster i of a step (part 0 first) runs on thread (i + rot) % nt, see item_rotation
     std::string why_not;                 // non-empty when the resident layout could not be built
 };
 
@@ -210,20 +202,15 @@ inline int32_t region_rank(int32_t region, int32_t n_regions, int32_t world)
 }
 
 // ---- the resident schedule's exchange plan (xpbd_resident.cuh) ------------------------------------
-// Every region keeps ONE shared-memory slot for every vertex its tets touch: the vertices it owns (it predicts
-// and commits them) first, then its guests (owned by another region).  A vertex that only one region touches
-// never leaves that region's shared memory during a substep.  A SHARED vertex (touched by several regions)
-// travels: whoever touches it knows, statically, who touched it before and who touches it next — touches are:
-// predict (owner), per iteration the colours of the clusters that contain it, commit (owner).  When the next
-// touch is by another region the position is PUSHED into a mailbox of that region, tagged with the step; when
-// the previous touch was by another region the position is PULLED (polled for the expected tag) out of the own
-// mailbox into the slot; when both touches are by the same region nothing happens at all — the value stays in
-// the slot.
-//
-// Collision constraints touch one vertex each and come first in an iteration (gauss_seidel_solver.cpp:28-31):
-// projecting the contacts of a vertex right before the first Green constraint of the sweep that touches it is
-// the same serial order.  So the cluster that is the first of a sweep to touch a surface vertex projects that
-// vertex's contacts before its tets (ExchangePlan::coll): there is no separate collision step.
+// Every region keeps ONE shared-memory slot for every vertex its tets touch: the vertices it owns (it predicts,
+// collides and commits them) first, then its guests (owned by another region).  A vertex that only one region
+// touches never leaves that region's shared memory during a substep.  A SHARED vertex (touched by several
+// regions) travels: whoever touches it knows, statically, who touched it before and who touches it next —
+// touches are: predict (owner), per iteration [the collision step (owner, surface vertices, when collision steps
+// exist)] and the colours of the clusters that contain it, commit (owner).  When the next touch is by another
+// region the position is PUSHED into a mailbox of that region, tagged with the step; when the previous touch was
+// by another region the position is PULLED (polled for the expected tag) out of the own mailbox into the slot;
+// when both touches are by the same region nothing happens at all — the value stays in the slot.
 //
 // Mailboxes: one per (exchange cluster, entry) — entry = position of the shared vertex among the shared vertices
 // of its cluster — at index entry * n_xclusters + xq, and one per shared vertex for its owner at n_entries + i.
@@ -232,12 +219,12 @@ constexpr uint32_t kRouteNone       = 0xffffffffu;
 constexpr uint32_t kRouteIndexMask  = 0x0fffffffu;
 constexpr int kRouteRankShift       = 28;
 // pull word: bit 31 valid, bits 24-27 entry, bits 16-23 steps back to the previous touch (0xff = the predict
-// step), bits 0-15 slot.  push words: {bit 31 valid | slot, routing word}.  collision words: {bit 31 valid |
-// slot, surface-vertex index}
+// step), bits 0-15 slot.  push words: {bit 31 valid | slot, routing word}
 constexpr uint32_t kPullValid      = 0x80000000u;
 constexpr uint32_t kPullPredict    = 0xffu;
-// owned shared vertex (ExchangePlan::osv), meta word: bits 0-7 the last colour touching it in a sweep
-constexpr uint32_t kOsvLastRemote  = 0x200u; // that last cluster belongs to another region
+// owned shared vertex (ExchangePlan::osv), meta word
+constexpr uint32_t kOsvSurface     = 0x100u; // takes part in the collision steps
+constexpr uint32_t kOsvLastRemote  = 0x200u; // the last colour touching it in a sweep belongs to another region
 constexpr uint32_t kOsvFirstRemote = 0x400u; // the first one does
 
 struct ExchangePlan
@@ -251,29 +238,27 @@ struct ExchangePlan
     int64_t max_local = 0;             // largest table
     int64_t n_shared  = 0;             // vertices touched by more than one region
     std::vector<uint16_t> tet_slots;   // 4 * T (storage order): slot in the table of the tet's region
-    // exchange clusters (parts 0, 1 of every chunk group), numbered in storage order
+    // exchange clusters (part 0 of every chunk), numbered in storage order
     int64_t n_xclusters = 0;
-    std::vector<int32_t> chunk_xfirst; // [colour * R + region]: number of the group's first exchange cluster
+    std::vector<int32_t> chunk_xfirst; // [colour * R + region]: number of the chunk's first exchange cluster
     int32_t entries = 0;               // shared vertices per cluster at most, rounded up to a multiple of 4
     // per variant, COMPACTED (valid words first, then zeros):
-    //   pull variant = (iteration > 0), push variant = (last iteration)
+    //   pull variant = 2 * (iteration > 0) + (collision steps present)
+    //   push variant = 2 * (last iteration) + (collision steps present)
     std::vector<uint32_t> pull;        // [variant][entries / 4][n_xclusters][4]: four pull words per 16-byte record
     std::vector<uint32_t> push;        // [variant][entries / 2][n_xclusters][4]: {slot word, route, slot word, route}
     uint32_t n_entries = 0;            // entries * n_xclusters: mailboxes of the clusters
-    // collision clusters (parts 0 and 2), numbered in storage order: the surface vertices they touch first in a sweep
-    int64_t n_sclusters = 0;
-    std::vector<int32_t> chunk_sfirst; // [colour * R + region]
-    int32_t coll_groups = 0;           // records of two per cluster at most
-    std::vector<uint32_t> coll;        // [coll_groups][n_sclusters][4]: {slot word, surface index, slot word, surface index}
     // owner side
     std::vector<int32_t> osv_off;      // [R + 1] shared vertices a region owns
     std::vector<uint32_t> osv_slot, osv_meta, osv_first; // slot; last colour | kOsv*; routing word of the first
                                                          // cluster entry touching it in a sweep
-    std::vector<int32_t> surf_off;     // [R + 1] surface vertices a region owns (surface copy at commit)
-    std::vector<uint32_t> surf_slot, surf_index; // slot; surface-vertex index
+    std::vector<int32_t> surf_off;     // [R + 1] surface vertices a region owns
+    std::vector<uint32_t> surf_slot, surf_index, surf_osv; // slot; surface-vertex index; position in osv or kRouteNone
     // statistics
-    int64_t n_pulls[2] = {0, 0}, n_pushes[2] = {0, 0};
-    std::vector<int64_t> pulls_by_colour; // [colour], later sweeps
+    int64_t n_pulls[4] = {0, 0, 0, 0}, n_pushes[4] = {0, 0, 0, 0};
+    std::vector<int64_t> pulls_by_colour; // [colour], variant: later sweep, no collision steps
+    int32_t quiet_steps = 0;           // colours whose clusters pull nothing in any region (variant: later sweep, no
+                                       // collision steps): steps that wait for no other region
     std::string why_not;
 };
 

@@ -9,7 +9,8 @@
 //
 // A vertex that only one region touches never leaves its shared memory during a substep.  A vertex that
 // several regions touch TRAVELS, and only when it has to: which steps touch a vertex is static (predict, per
-// iteration the colours of the clusters that contain it, commit), so every touch knows who touched the vertex before and who
+// iteration the collision step of its owner if it is a surface vertex and collision steps exist, the colours
+// of the clusters that contain it, commit), so every touch knows who touched the vertex before and who
 // touches it next (scene_build.h, ExchangePlan).  Next touch by another region: the position is PUSHED into a
 // mailbox of that region, tagged with the step.  Previous touch by another region: it is PULLED — polled for
 // the expected tag — from the own mailbox into the slot.  Both by the same region: nothing happens, the value
@@ -22,12 +23,10 @@
 // With pencil-shaped regions and the colour order that goes with them (scene_build.cpp) the steps that flip
 // the cell parity along the pencil axis — half of the steps of a sweep on a lattice — pull nothing at all.
 //
-//   step 0             : predict   (timestep.cpp:35-43)
-//   step 1 + k C + c   : colour c of iteration k (gauss_seidel_solver.cpp:32-35); the cluster that is the first of
-//                        the sweep to touch a surface vertex projects that vertex's collision constraints before its
-//                        tets (:28-31 runs them first in the iteration; they touch one vertex each, so this is the
-//                        same serial order) — there is no separate collision step
-//   step 1 + K C       : commit    (timestep.cpp:48-57) + surface copy
+//   step 0                      : predict   (timestep.cpp:35-43)
+//   step 1 + k(1+C) + 0         : collision constraints of iteration k (gauss_seidel_solver.cpp:28-31)
+//   step 1 + k(1+C) + 1 + c     : colour c of iteration k               (:32-35)
+//   step 1 + K(1+C)             : commit    (timestep.cpp:48-57) + surface copy
 //
 // Regions that exchange are co-resident (cooperative launch), so waiting cannot deadlock: every wait is for a
 // strictly earlier step.  A poll budget turns a lost update into an error code instead of a hang.
@@ -206,31 +205,26 @@ struct ResidentArgs
     uint8_t const* tet_shape;      // per tet: index into shapes
     Real4<R> const* shapes;        // [kShapeWords * n_shapes]: r0, r1, r2 and the material of every distinct record
     int32_t n_shapes;
-    DevChunk const* chunks;        // [(colour * n_regions + region) * kParts + part] (ClusterPlan::chunks)
+    DevChunk const* chunks;        // [(colour * n_regions + region) * 2 + part]
     // local vertex tables (ExchangePlan)
     int32_t const* loc_off;        // [n_regions + 1]
     int32_t const* n_owned;        // [n_regions]
     uint32_t const* loc_vtx;       // global vertex of slot i
-    // exchange clusters: parts 0, 1 of every chunk group, numbered chunk_xfirst[colour * n_regions + region] + i
+    // exchange clusters: part 0 of every chunk, numbered chunk_xfirst[colour * n_regions + region] + i
     int32_t const* chunk_xfirst;
     int64_t n_xclusters;
     int32_t entries;               // mailboxes per exchange cluster (multiple of 4)
-    uint4 const* pull;             // [iteration > 0][entries / 4][n_xclusters]: four pull words each, valid ones first
-    uint4 const* push;             // [last iteration][entries / 2][n_xclusters]: {slot, route, slot, route}
-    // collision clusters: parts 0, 2 — the first of a sweep to touch some surface vertices, whose contacts they
-    // project before their tets; numbered chunk_sfirst[colour * n_regions + region] + position
-    int32_t const* chunk_sfirst;
-    int64_t n_sclusters;
-    int32_t coll_groups;
-    uint4 const* coll;             // [coll_groups][n_sclusters]: {slot, surface index, slot, surface index}
+    uint4 const* pull;             // [variant][entries / 4][n_xclusters]: four pull words each, valid ones first
+    uint4 const* push;             // [variant][entries / 2][n_xclusters]: {slot, route, slot, route}
     // owner side: shared vertices and surface vertices a region owns
     int32_t const* osv_off;        // [n_regions + 1]
     uint32_t const* osv_slot;
-    uint32_t const* osv_meta;      // last colour | kOsvLastRemote | kOsvFirstRemote
+    uint32_t const* osv_meta;      // last colour | kOsvSurface | kOsvLastRemote | kOsvFirstRemote
     uint32_t const* osv_first;     // routing word of the first cluster entry touching the vertex in a sweep
     int32_t const* surf_off;       // [n_regions + 1]
     uint32_t const* surf_slot;
-    uint32_t const* surf_index;    // surface vertex index (into s.surf_pos)
+    uint32_t const* surf_index;    // surface vertex index (into s.surf_pos / s.surf_first)
+    uint32_t const* surf_osv;      // position in osv, kRouteNone when only this region touches the vertex
     void* box;                     // mailboxes: n_entries of the clusters, then one per shared vertex for its owner
     uint32_t n_entries;            // entries * n_xclusters
     // decomposition over GPUs: every rank plans the same regions and runs its own block of them; a mailbox
@@ -306,27 +300,6 @@ __device__ __forceinline__ bool project_vertex_contacts(DeviceScene<R> const& s,
     return moved;
 }
 
-template <typename R>
-__device__ __forceinline__ bool project_contact(Real4<R>& p, Real4<R>& q, Real4<R> const& m, R at, int first_iteration,
-                                                bool& dirty);
-// the same, continuing at contact j of a vertex whose first contact was handled by the caller
-template <typename R>
-__device__ __forceinline__ bool project_vertex_contacts_from(DeviceScene<R> const& s, uint32_t j, uint32_t n_contacts,
-                                                             Real4<R>& p, R at, int first_iteration)
-{
-    bool moved = false;
-    for (; j < n_contacts && !(s.contact_v[j] & 0x80000000u); ++j)
-    {
-        Real4<R> q       = ld4(&s.contact_q[j]);
-        Real4<R> const m = ld4(&s.contact_n[j]);
-        bool dirty       = false;
-        moved            = project_contact(p, q, m, at, first_iteration, dirty) || moved;
-        if (dirty)
-            st4(&s.contact_q[j], q);
-    }
-    return moved;
-}
-
 constexpr int kMaxShapes = 256;
 constexpr int kTraceWarps = 12; // warps per CTA the trace buffer has room for
 
@@ -374,11 +347,11 @@ __device__ __forceinline__ long long clock_stamp()
 // dynamic shared memory: [chunk descriptors of the region | first exchange cluster per colour | rest-shape dictionary | vertex table]
 __host__ __device__ inline size_t chunk_area_bytes(int n_colours)
 {
-    return (static_cast<size_t>(n_colours) * kParts * sizeof(DevChunk) + 31) / 32 * 32;
+    return (static_cast<size_t>(n_colours) * 2 * sizeof(DevChunk) + 31) / 32 * 32;
 }
 __host__ __device__ inline size_t xfirst_area_bytes(int n_colours)
 {
-    return (static_cast<size_t>(n_colours) * 2 * sizeof(int32_t) + 31) / 32 * 32; // xfirst, sfirst per colour
+    return (static_cast<size_t>(n_colours) * sizeof(int32_t) + 31) / 32 * 32;
 }
 template <typename R>
 __host__ __device__ inline size_t dict_area_bytes(int n_shapes)
@@ -414,41 +387,12 @@ __device__ __forceinline__ void load_cluster_head(ClusterHead<R, kDict>& h, Resi
     }
 }
 
-// Early pulls: the words of a pull record whose previous touch lies two or more steps back (or is the predict
-// step) name records that were pushed before the CURRENT step began — they are requested while the current
-// cluster's tets run (the records of a later touch cannot be: they are pushed during this step).
-template <typename R>
-struct EarlyPull
-{
-    typename Xchg<R>::Raw raw[4];
-    uint32_t mask = 0; // words of the record that were requested
-};
-template <typename R>
-__device__ __forceinline__ void pull_request_early(ResidentArgs<R> const& a, int64_t xq, uint4 w, bool after_predict,
-                                                   EarlyPull<R>& early)
-{
-    uint32_t const word[4] = {w.x, w.y, w.z, w.w};
-    uint32_t const nx      = static_cast<uint32_t>(a.n_xclusters);
-    early.mask             = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-    {
-        uint32_t const d = word[e] >> 16 & 0xffu;
-        // d == kPullPredict: pushed in the predict step — early unless that is the current step
-        if ((word[e] & kPullValid) && d >= 2u && (d != kPullPredict || after_predict))
-        {
-            early.raw[e] = Xchg<R>::fetch(a.box, (word[e] >> 24 & 0xfu) * nx + static_cast<uint32_t>(xq), a.world > 1);
-            early.mask |= 1u << e;
-        }
-    }
-}
-
 // Pull the shared vertices of a cluster whose previous touch was by another region: every pull word names
 // the slot, the mailbox entry and how many steps back the previous touch lies; all polls of a group of four
 // are in flight together.  `w` = the first group (loaded a step ahead), further groups are rare.
 template <typename R, typename Stamp>
 __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 const* pull_variant, int64_t xq, uint4 w,
-                                             EarlyPull<R> const& early, Real4<R>* sx, uint32_t tag, Stamp&& stamp)
+                                             Real4<R>* sx, uint32_t tag, Stamp&& stamp)
 {
     uint32_t const mine = static_cast<uint32_t>(xq); // mailbox of entry e: e * n_xclusters + xq
     uint32_t const nx   = static_cast<uint32_t>(a.n_xclusters);
@@ -464,25 +408,6 @@ __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 con
             if (word[e] & kPullValid)
                 pending |= 1u << e;
         bool const full = pending == 0xfu;
-        auto const land = [&](int e, typename Xchg<R>::Raw const& raw) {
-            uint32_t const d = word[e] >> 16 & 0xffu;
-            R x, y, z;
-            if (Xchg<R>::decode(raw, d == kPullPredict ? a.base : tag - d, x, y, z))
-            {
-                Real4<R>* dst = &sx[word[e] & 0xffffu];
-                dst->x        = x;
-                dst->y        = y;
-                dst->z        = z;
-                pending &= ~(1u << e);
-            }
-        };
-        if (g == 0)
-        { // the records requested while the tets ran
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (early.mask >> e & 1u)
-                    land(e, early.raw[e]);
-        }
         while (pending)
         {
             typename Xchg<R>::Raw raw[4];
@@ -493,7 +418,18 @@ __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 con
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (pending >> e & 1u)
-                    land(e, raw[e]);
+                {
+                    uint32_t const d = word[e] >> 16 & 0xffu;
+                    R x, y, z;
+                    if (Xchg<R>::decode(raw[e], d == kPullPredict ? a.base : tag - d, x, y, z))
+                    {
+                        Real4<R>* dst = &sx[word[e] & 0xffffu];
+                        dst->x        = x;
+                        dst->y        = y;
+                        dst->z        = z;
+                        pending &= ~(1u << e);
+                    }
+                }
             if (polls == 0)
                 stamp(2);
             if (pending && poll_expired(a.error, ++polls))
@@ -545,15 +481,12 @@ __device__ __forceinline__ void push_cluster(ResidentArgs<R> const& a, uint4 con
 }
 
 // One cluster: project its tets in order out of shared memory (slots of the region's vertex table).
-// after_first() runs once, after the first tet: loads requested at the start of the pass have arrived by then,
-// and what it requests in turn is in flight while the other tets run.
-template <typename R, bool kDict, typename Stamp, typename AfterFirst>
+template <typename R, bool kDict, typename Stamp>
 __device__ __forceinline__ void run_cluster(ResidentArgs<R> const& a, DevChunk const& ch, int32_t i,
                                             ClusterHead<R, kDict> const& head, Real4<R>* sx, Real4<R> const* s_dict,
-                                            int first_iteration, Stamp&& stamp, AfterFirst&& after_first)
+                                            int first_iteration, Stamp&& stamp)
 {
     DeviceScene<R> const& s = a.s;
-    bool first              = true;
     // column layout: tet m of cluster i sits at first + n[0] + .. + n[m-1] + i
     int32_t n0 = ch.n[0], n1 = ch.n[1], n2 = ch.n[2], n3 = ch.n[3], n4 = ch.n[4], n5 = ch.n[5], n6 = ch.n[6],
             n7 = ch.n[7];
@@ -595,11 +528,6 @@ __device__ __forceinline__ void run_cluster(ResidentArgs<R> const& a, DevChunk c
             at  = head.at;
         }
         green_project_at<R, false>(p1, p2, p3, p4, z, z, z, z, r0, r1, r2, mu, lam, at, R(0), a.dt, lambda);
-        if (first)
-        {
-            after_first();
-            first = false;
-        }
         if (lambda != cur.lambda || first_iteration)
             s.tet_lambda[t] = lambda;
         if (lambda != cur.lambda)
@@ -618,108 +546,11 @@ __device__ __forceinline__ void run_cluster(ResidentArgs<R> const& a, DevChunk c
     }
 }
 
-// Where cluster `i` of a colour step sits: its chunk (part), index in the chunk, number among the exchange clusters
-// (parts 0, 1) and among the collision clusters (parts 0, 2) of the (colour, region) group, -1 when not one.
-struct StepItem
-{
-    int32_t part, ci, x, s;
-};
-__device__ __forceinline__ StepItem locate(DevChunk const* group, int32_t i)
-{
-    int32_t const n0 = group[0].n[0], n1 = group[1].n[0], n2 = group[2].n[0];
-    if (i < n0)
-        return {0, i, i, i};
-    if (i < n0 + n1)
-        return {1, i - n0, i, -1};
-    if (i < n0 + n1 + n2)
-        return {2, i - n0 - n1, -1, i - n1};
-    return {3, i - n0 - n1 - n2, -1, -1};
-}
-
-// one collision constraint (collision_constraint.cpp:21-48) given its record: q = (qs, lambda), m = (n, sdf id)
-template <typename R>
-__device__ __forceinline__ bool project_contact(Real4<R>& p, Real4<R>& q, Real4<R> const& m, R at, int first_iteration,
-                                                bool& dirty)
-{
-    R lambda  = first_iteration ? R(0) : q.w;
-    R const C = (p.x - q.x) * m.x + (p.y - q.y) * m.y + (p.z - q.z) * m.z;
-    if (C >= R(0))
-    {
-        dirty = first_iteration != 0; // the reset of lambda (constraint.cpp:12-16) still has to be stored
-        q.w   = lambda;
-        return false;
-    }
-    R const dl = -(C + at * lambda) / (p.w + at);
-    lambda += dl;
-    p.x += p.w * m.x * dl;
-    p.y += p.w * m.y * dl;
-    p.z += p.w * m.z * dl;
-    q.w   = lambda;
-    dirty = true;
-    return true;
-}
-
-// Collision constraints of the surface vertices a cluster is the first of the sweep to touch
-// (collision_constraint.cpp:21-48; gauss_seidel_solver.cpp:28-31 runs them before the elastic constraints of the
-// iteration, and they touch one vertex each, so "right before the first tet that touches the vertex" is the same
-// order).  w0, w1: the first two records (two vertices each), f: their first-contact indices, loaded a step ahead.
-// The records of all four vertices are requested together: one round trip, not one per vertex and field.
-template <typename R>
-__device__ __forceinline__ void collide_cluster(ResidentArgs<R> const& a, int64_t sq, uint4 w0, uint4 w1,
-                                                uint32_t const (&f)[4], uint32_t n_contacts, Real4<R>* sx, R at_c,
-                                                int first_iteration)
-{
-    DeviceScene<R> const& s = a.s;
-    uint32_t const slot[4]  = {w0.x, w0.z, w1.x, w1.z};
-    Real4<R> q[4], m[4];
-    uint32_t next[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-        if ((slot[e] & kPullValid) && f[e] != 0xffffffffu)
-        {
-            q[e]    = ld4(&s.contact_q[f[e]]);
-            m[e]    = ld4(&s.contact_n[f[e]]);
-            next[e] = f[e] + 1u < n_contacts ? s.contact_v[f[e] + 1u] : 0x80000000u; // bit 31: another vertex's first
-        }
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-        if ((slot[e] & kPullValid) && f[e] != 0xffffffffu)
-        {
-            Real4<R> pp = sx[slot[e] & 0xffffu];
-            bool dirty  = false;
-            bool moved  = project_contact(pp, q[e], m[e], at_c, first_iteration, dirty);
-            if (dirty)
-                st4(&s.contact_q[f[e]], q[e]);
-            if (!(next[e] & 0x80000000u)) // several SDFs touch this vertex: the others in list order
-                moved = project_vertex_contacts_from(s, f[e] + 1u, n_contacts, pp, at_c, first_iteration) || moved;
-            if (moved)
-                sx[slot[e] & 0xffffu] = pp;
-        }
-    if (w1.z & kPullValid) // more than four: rare (corners of the mesh)
-        for (int g = 2; g < a.coll_groups; ++g)
-        {
-            uint4 const w = __ldg(&a.coll[static_cast<int64_t>(g) * a.n_sclusters + sq]);
-            uint32_t const sl[2] = {w.x, w.z}, si[2] = {w.y, w.w};
-            for (int e = 0; e < 2; ++e)
-                if (sl[e] & kPullValid)
-                {
-                    uint32_t const first = s.surf_first[si[e]];
-                    if (first == 0xffffffffu)
-                        continue;
-                    Real4<R> pp = sx[sl[e] & 0xffffu];
-                    if (project_vertex_contacts(s, first, n_contacts, pp, at_c, first_iteration))
-                        sx[sl[e] & 0xffffu] = pp;
-                }
-            if (!(w.z & kPullValid))
-                break;
-        }
-}
-
 // kExchange = false: the launch runs regions that share no vertex with any other (ensembles, a body in one
 // region): no mailbox code at all.
 template <typename R, bool kTrace, bool kDict, bool kExchange>
 __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* sx, DevChunk* s_chunks,
-                           int32_t* s_first, Real4<R>* s_dict)
+                           int32_t* s_xfirst, Real4<R>* s_dict)
 {
     DeviceScene<R> const& s = a.s;
     int const tid = threadIdx.x, nt = blockDim.x;
@@ -727,28 +558,30 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
     int32_t const l0 = a.loc_off[region], nl = a.loc_off[region + 1] - l0, no = a.n_owned[region];
     int32_t const o0 = kExchange ? a.osv_off[region] : 0, n_osv = kExchange ? a.osv_off[region + 1] - o0 : 0;
     int32_t const s0 = a.surf_off[region], ns = a.surf_off[region + 1] - s0;
-    // contacts of the last detection (every CTA reads the same count)
+    // collision steps exist when detection is on — and, on a single GPU, only when it found something:
+    // every CTA reads the same contact count, so they agree on the schedule (ranks of a decomposed
+    // scene detect separately and could disagree: they always keep the steps)
     uint32_t const n_contacts =
         a.collide ? min(*s.contact_count, static_cast<uint32_t>(s.contact_cap)) : 0u;
-    int32_t const C = a.n_colours, K = C > 0 ? a.iterations : 0;
-    int32_t const n_phases = 2 + K * C; // predict, K x colours, commit
+    int32_t const C = a.n_colours, cs = (a.collide && (n_contacts > 0u || a.world > 1)) ? 1 : 0,
+                  K = C > 0 ? a.iterations : 0;
+    int32_t const per_iteration = C + cs;
+    int32_t const n_phases      = 2 + K * per_iteration; // predict, K x ([collision] colours), commit
 
     // the region's chunk descriptors: [colour][part], read every step
     {
         constexpr int32_t W = static_cast<int32_t>(sizeof(DevChunk) / 4);
-        int32_t const words = C * kParts * W;
+        int32_t const words = C * 2 * W;
         int32_t const* src  = reinterpret_cast<int32_t const*>(a.chunks);
         int32_t* dst        = reinterpret_cast<int32_t*>(s_chunks);
         for (int32_t w = tid; w < words; w += nt)
         {
-            int32_t const c = w / (kParts * W), rem = w % (kParts * W);
-            dst[w] = src[(static_cast<int64_t>(c) * a.n_regions + region) * kParts * W + rem];
+            int32_t const c = w / (2 * W), rem = w % (2 * W);
+            dst[w] = src[(static_cast<int64_t>(c) * a.n_regions + region) * 2 * W + rem];
         }
-        for (int32_t c = tid; c < C; c += nt)
-        {
-            s_first[2 * c]     = kExchange ? a.chunk_xfirst[static_cast<int64_t>(c) * a.n_regions + region] : 0;
-            s_first[2 * c + 1] = a.chunk_sfirst[static_cast<int64_t>(c) * a.n_regions + region];
-        }
+        if constexpr (kExchange)
+            for (int32_t c = tid; c < C; c += nt)
+                s_xfirst[c] = a.chunk_xfirst[static_cast<int64_t>(c) * a.n_regions + region];
         if constexpr (kDict)
             for (int32_t w = tid; w < kShapeWords * a.n_shapes; w += nt)
                 s_dict[w] = a.shapes[w];
@@ -772,77 +605,70 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
             {
                 long long g;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-                row[3]  = g;
-                row[5]  = my_item < (s_chunks[kParts * ((traced) % a.n_colours)].n[0] + s_chunks[kParts * ((traced) % a.n_colours) + 1].n[0]) ? 1 : 0;
+                row[3] = g;
             }
         }
     };
     // tag of the last colour step of iteration k that touches a vertex with this schedule
     auto last_colour_tag = [&](int32_t k, uint32_t lastc) -> uint32_t {
-        return a.base + 1u + static_cast<uint32_t>(k * C) + lastc;
+        return a.base + 1u + static_cast<uint32_t>(k * per_iteration + cs) + lastc;
     };
     R const at_c = s.collision_alpha / (dt * dt);
     int64_t const pull_stride = static_cast<int64_t>(a.entries / 4) * a.n_xclusters; // records per pull variant
     int64_t const push_stride = static_cast<int64_t>(a.entries / 2) * a.n_xclusters;
 
-    // Phase p has tag base + p.  p = 0: predict; p = n_phases - 1: commit; in between colour
-    // c = (p - 1) % C of iteration k = (p - 1) / C.  A colour phase with more clusters than threads takes
-    // several rounds.
+    // Phase p has tag base + p.  p = 0: predict; p = n_phases - 1: commit; in between iteration
+    // k = (p - 1) / per_iteration, and q = (p - 1) % per_iteration is the collision step (q == 0 when
+    // cs) or colour q - cs.  A colour phase with more clusters than threads takes several rounds.
     //
     // Every pass of the loop below ends at ONE place that prepares the cluster this thread runs
     // next (head loaded, shared vertices pulled) — before the barrier when that cluster belongs to the
     // next phase: a pulled vertex is touched by no cluster of this region in between (its previous touch
     // was by another region), and the records it waits for come from phases that do not wait for this thread.
     ClusterHead<R, kDict> head; // the prepared cluster of this thread ...
-    StepItem cur{3, -1, -1, -1}; // ... where it sits in its step (ci < 0: nothing prepared)
-    uint4 cw0 = make_uint4(0u, 0u, 0u, 0u), cw1 = cw0; // ... the surface vertices it touches first, and their
-    uint32_t cfirst[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}; // first contacts
-    int32_t round = 0;
+    int64_t cur_xq = -1;  // ... and its number among the exchange clusters (part 0), else -1
+    int32_t item_i = -1;  // cluster index within its phase (part 0 first), -1: nothing prepared
+    int32_t round  = 0;
     for (int32_t p = 0; p < n_phases;)
     {
         uint32_t const tag = a.base + static_cast<uint32_t>(p);
-        int32_t const k    = p == 0 ? 0 : (p - 1) / C;
-        int32_t const c    = p == 0 ? 0 : (p - 1) % C;
-        bool const colour  = p > 0 && p < n_phases - 1;
+        int32_t const k    = p == 0 ? 0 : (p - 1) / per_iteration;
+        int32_t const q    = p == 0 ? 0 : (p - 1) % per_iteration;
+        bool const colour  = p > 0 && p < n_phases - 1 && !(cs && q == 0);
+        int32_t const c    = q - cs;
 
         // ---- (1) what this thread runs after this pass: its loads (static data) go out first, so
         //          that they are in flight while the work of this pass runs
         bool advance = true;
         if (colour)
-        {
-            DevChunk const* g = &s_chunks[kParts * c];
-            advance           = (round + 1) * nt >= g[0].n[0] + g[1].n[0] + g[2].n[0] + g[3].n[0];
-        }
+            advance = (round + 1) * nt >= s_chunks[2 * c].n[0] + s_chunks[2 * c + 1].n[0];
         int32_t const np      = advance ? p + 1 : p;
         int32_t const ni_next = advance ? my_item : (round + 1) * nt + my_item;
-        StepItem nxt{3, -1, -1, -1};
-        int32_t nk = 0;
+        bool has_next         = false;
+        int32_t nk            = 0;
         ClusterHead<R, kDict> nhead;
-        uint4 npull = make_uint4(0u, 0u, 0u, 0u), nw0 = npull, nw1 = npull;
-        int64_t next_xq = -1, next_sq = -1;
-        EarlyPull<R> early;
-        uint32_t nfirst[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-        bool nfirst_loaded = false;
+        uint4 npull           = make_uint4(0u, 0u, 0u, 0u);
+        int64_t next_xq       = -1;
         if (np > 0 && np < n_phases - 1)
         {
-            nk                = (np - 1) / C;
-            int32_t const nc  = (np - 1) % C;
-            DevChunk const* g = &s_chunks[kParts * nc];
-            if (ni_next < g[0].n[0] + g[1].n[0] + g[2].n[0] + g[3].n[0])
+            nk               = (np - 1) / per_iteration;
+            int32_t const nq = (np - 1) % per_iteration;
+            if (!(cs && nq == 0))
             {
-                nxt = locate(g, ni_next);
-                load_cluster_head<R, kDict>(nhead, a, g[nxt.part], nxt.ci, nk == 0, s_dict);
-                if (kExchange && nxt.x >= 0)
+                int32_t const nc = nq - cs;
+                int32_t const nA = s_chunks[2 * nc].n[0], nB = s_chunks[2 * nc + 1].n[0];
+                if (ni_next < nA + nB)
                 {
-                    next_xq = static_cast<int64_t>(s_first[2 * nc]) + nxt.x;
-                    npull   = __ldg(&a.pull[static_cast<int64_t>(nk > 0 ? 1 : 0) * pull_stride + next_xq]);
-                }
-                if (nxt.s >= 0 && n_contacts > 0u)
-                {
-                    next_sq = static_cast<int64_t>(s_first[2 * nc + 1]) + nxt.s;
-                    nw0     = __ldg(&a.coll[next_sq]);
-                    if (a.coll_groups > 1)
-                        nw1 = __ldg(&a.coll[a.n_sclusters + next_sq]);
+                    has_next           = true;
+                    bool const in_x    = ni_next < nA;
+                    DevChunk const& ch = s_chunks[2 * nc + (in_x ? 0 : 1)];
+                    int32_t const ci   = in_x ? ni_next : ni_next - nA;
+                    load_cluster_head<R, kDict>(nhead, a, ch, ci, nk == 0, s_dict);
+                    if (kExchange && in_x)
+                    {
+                        next_xq = static_cast<int64_t>(s_xfirst[nc]) + ci;
+                        npull   = __ldg(&a.pull[static_cast<int64_t>(2 * (nk > 0 ? 1 : 0) + cs) * pull_stride + next_xq]);
+                    }
                 }
             }
         }
@@ -865,14 +691,18 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
             if constexpr (kExchange)
             {
                 __syncthreads();
-                // next touch of an owned shared vertex: the first cluster of the sweep that contains it — pushed
-                // when that cluster is another region's
+                // next touch of an owned shared vertex: the owner's collision step (surface vertex), else the
+                // first cluster of the sweep that contains it — pushed when that cluster is another region's
                 for (int32_t i = tid; i < n_osv; i += nt)
-                    if (K > 0 && (a.osv_meta[o0 + i] & kOsvFirstRemote))
+                {
+                    uint32_t const meta = a.osv_meta[o0 + i];
+                    bool const to_me    = K == 0 || (cs && (meta & kOsvSurface));
+                    if (!to_me && (meta & kOsvFirstRemote))
                     {
                         Real4<R> const pp = sx[a.osv_slot[o0 + i]];
                         push<R>(a, a.osv_first[o0 + i], pp.x, pp.y, pp.z, tag);
                     }
+                }
             }
         }
         else if (p == n_phases - 1)
@@ -883,7 +713,7 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
                 {
                     uint32_t const meta = a.osv_meta[o0 + i];
                     if (K > 0 && (meta & kOsvLastRemote))
-                    { // its last touch (last colour of the last sweep) was another region's
+                    {
                         Real4<R>* dst = &sx[a.osv_slot[o0 + i]];
                         R x, y, z;
                         xchg_wait<R>(a, a.n_entries + static_cast<uint32_t>(o0 + i), last_colour_tag(K - 1, meta & 0xffu), x, y, z);
@@ -911,43 +741,66 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
                 st4(&s.surf_pos[a.surf_index[s0 + i]], Real4<R>{pp.x, pp.y, pp.z, R(0)});
             }
         }
+        else if (cs && q == 0)
+        { // ---- collision constraints of the owned surface vertices (gauss_seidel_solver.cpp:28-31)
+            for (int32_t i = tid; i < ns; i += nt)
+            {
+                uint32_t const slot  = a.surf_slot[s0 + i];
+                uint32_t const first = n_contacts > 0 ? s.surf_first[a.surf_index[s0 + i]] : 0xffffffffu;
+                uint32_t meta        = 0;
+                uint32_t osv         = kRouteNone;
+                if constexpr (kExchange)
+                {
+                    osv = a.surf_osv[s0 + i];
+                    if (osv != kRouteNone)
+                    { // shared: its last touch (last colour of the previous sweep) may have been another region's
+                        meta = a.osv_meta[osv];
+                        if (k > 0 && (meta & kOsvLastRemote))
+                        {
+                            R x, y, z;
+                            xchg_wait<R>(a, a.n_entries + osv, last_colour_tag(k - 1, meta & 0xffu), x, y, z);
+                            sx[slot].x = x;
+                            sx[slot].y = y;
+                            sx[slot].z = z;
+                        }
+                    }
+                }
+                if (first != 0xffffffffu)
+                {
+                    Real4<R> pp = sx[slot];
+                    if (project_vertex_contacts(s, first, n_contacts, pp, at_c, k == 0))
+                        sx[slot] = pp;
+                }
+                if constexpr (kExchange)
+                    if (osv != kRouteNone && (meta & kOsvFirstRemote))
+                    { // on to the first cluster of the sweep, contact or not: it waits for this step's tag
+                        Real4<R> const pp = sx[slot];
+                        push<R>(a, a.osv_first[osv], pp.x, pp.y, pp.z, tag);
+                    }
+            }
+        }
         else
-        { // ---- colour c of iteration k (gauss_seidel_solver.cpp:25-36)
+        { // ---- colour q - cs of iteration k (gauss_seidel_solver.cpp:32-35)
+            int32_t const nA = s_chunks[2 * c].n[0];
             if (round == 0)
                 stamp(0);
-            if (cur.ci >= 0)
-            { // cluster `cur` of the phase runs on thread (item + rot) % nt; the clusters that exchange come first
-                DevChunk const& ch = s_chunks[kParts * c + cur.part];
+            if (item_i >= 0)
+            { // cluster item_i of the phase runs on thread (item_i + rot) % nt; part 0 (clusters that exchange) first
+                bool const in_x    = item_i < nA;
+                DevChunk const& ch = s_chunks[2 * c + (in_x ? 0 : 1)];
                 uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
                 uint4 const* push_variant = nullptr;
-                int64_t const xq = kExchange && cur.x >= 0 ? static_cast<int64_t>(s_first[2 * c]) + cur.x : -1;
-                if (xq >= 0)
+                if (kExchange && cur_xq >= 0)
                 { // where its shared vertices go afterwards (static): in flight while the tets run
-                    push_variant = a.push + static_cast<int64_t>(k == K - 1 ? 1 : 0) * push_stride;
-                    w0           = __ldg(&push_variant[xq]);
-                    w1           = __ldg(&push_variant[a.n_xclusters + xq]);
+                    push_variant = a.push + static_cast<int64_t>(2 * (k == K - 1 ? 1 : 0) + cs) * push_stride;
+                    w0           = __ldg(&push_variant[cur_xq]);
+                    w1           = __ldg(&push_variant[a.n_xclusters + cur_xq]);
                 }
-                if (cur.s >= 0 && n_contacts > 0u)
-                    collide_cluster<R>(a, static_cast<int64_t>(s_first[2 * c + 1]) + cur.s, cw0, cw1, cfirst, n_contacts, sx,
-                                       at_c, k == 0);
-                run_cluster<R, kDict>(a, ch, cur.ci, head, sx, s_dict, k == 0, stamp, [&] {
-                    if constexpr (kExchange && sizeof(R) == 4)
-                        if (next_xq >= 0 && (npull.x & kPullValid))
-                            pull_request_early<R>(a, next_xq, npull, true, early);
-                    if (next_sq >= 0)
-                    { // first contacts of the surface vertices the next cluster touches first (written by the
-                      // detection, constant during the launch)
-                        nfirst[0] = (nw0.x & kPullValid) ? s.surf_first[nw0.y] : 0xffffffffu;
-                        nfirst[1] = (nw0.z & kPullValid) ? s.surf_first[nw0.w] : 0xffffffffu;
-                        nfirst[2] = (nw1.x & kPullValid) ? s.surf_first[nw1.y] : 0xffffffffu;
-                        nfirst[3] = (nw1.z & kPullValid) ? s.surf_first[nw1.w] : 0xffffffffu;
-                        nfirst_loaded = true;
-                    }
-                });
+                run_cluster<R, kDict>(a, ch, in_x ? item_i : item_i - nA, head, sx, s_dict, k == 0, stamp);
                 // ---- (3) shared vertices whose next touch is another region's go there first: a neighbour's
                 //          next step waits for them
-                if (xq >= 0)
-                    push_cluster<R>(a, push_variant, xq, w0, w1, sx, tag);
+                if (kExchange && cur_xq >= 0)
+                    push_cluster<R>(a, push_variant, cur_xq, w0, w1, sx, tag);
                 stamp(15);
             }
             stamp(6);
@@ -955,28 +808,15 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
 
         // ---- (4) the next cluster becomes the prepared one: its shared vertices are pulled now, before
         //          the barrier when it belongs to the next phase
-        cur = nxt;
-        if (nxt.ci >= 0)
+        item_i = has_next ? ni_next : -1;
+        cur_xq = -1;
+        if (has_next)
         {
-            head = nhead;
-            cw0  = nw0;
-            cw1  = nw1;
+            head   = nhead;
+            cur_xq = next_xq;
             if (kExchange && next_xq >= 0 && (npull.x & kPullValid))
-                pull_cluster<R>(a, a.pull + static_cast<int64_t>(nk > 0 ? 1 : 0) * pull_stride, next_xq, npull, early, sx,
-                                a.base + static_cast<uint32_t>(np), stamp);
-            if (next_sq >= 0)
-            {
-                if (!nfirst_loaded)
-                { // (this thread ran no cluster in this pass)
-                    nfirst[0] = (nw0.x & kPullValid) ? s.surf_first[nw0.y] : 0xffffffffu;
-                    nfirst[1] = (nw0.z & kPullValid) ? s.surf_first[nw0.w] : 0xffffffffu;
-                    nfirst[2] = (nw1.x & kPullValid) ? s.surf_first[nw1.y] : 0xffffffffu;
-                    nfirst[3] = (nw1.z & kPullValid) ? s.surf_first[nw1.w] : 0xffffffffu;
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    cfirst[e] = nfirst[e];
-            }
+                pull_cluster<R>(a, a.pull + static_cast<int64_t>(2 * (nk > 0 ? 1 : 0) + cs) * pull_stride, next_xq, npull,
+                                sx, a.base + static_cast<uint32_t>(np), stamp);
         }
         if (advance)
         {
@@ -1000,13 +840,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_substep_resident(Re
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevChunk* s_chunks = reinterpret_cast<DevChunk*>(smem_raw);
-    int32_t* s_first   = reinterpret_cast<int32_t*>(smem_raw + chunk_area_bytes(a.n_colours)); // {xfirst, sfirst} per colour
+    int32_t* s_xfirst  = reinterpret_cast<int32_t*>(smem_raw + chunk_area_bytes(a.n_colours));
     Real4<R>* s_dict   = reinterpret_cast<Real4<R>*>(smem_raw + chunk_area_bytes(a.n_colours) + xfirst_area_bytes(a.n_colours));
     Real4<R>* sx       = s_dict + (kDict ? kShapeWords * a.n_shapes : 0);
     // regions that exchange vertices come first in region_order (at most one per CTA: they must be
     // co-resident), the others follow and are handed out round-robin
     for (int32_t i = blockIdx.x; i < a.n_run; i += gridDim.x)
-        run_region<R, kTrace, kDict, kExchange>(a, a.region_order[i], sx, s_chunks, s_first, s_dict);
+        run_region<R, kTrace, kDict, kExchange>(a, a.region_order[i], sx, s_chunks, s_xfirst, s_dict);
 }
 
 template <typename T>
@@ -1035,11 +875,11 @@ template <typename R>
 struct ResidentPlan
 {
     ResidentArgs<R> args{};
-    PBuf<int32_t> region_order, loc_off, n_owned, chunk_xfirst, chunk_sfirst, osv_off, surf_off;
+    PBuf<int32_t> region_order, loc_off, n_owned, chunk_xfirst, osv_off, surf_off;
     PBuf<DevChunk> chunks;
-    PBuf<uint32_t> loc_vtx, osv_slot, osv_meta, osv_first, surf_slot, surf_index, error;
+    PBuf<uint32_t> loc_vtx, osv_slot, osv_meta, osv_first, surf_slot, surf_index, surf_osv, error;
     PBuf<uint2> tet_slots;
-    PBuf<uint4> pull, push, coll, box;
+    PBuf<uint4> pull, push, box;
     PBuf<long long> trace;
     int64_t trace_len = 0;
     int grid = 0, block = 0;
@@ -1208,8 +1048,7 @@ struct ResidentPlan
         surf_off.upload(xp.surf_off, st);
         surf_slot.upload(xp.surf_slot, st);
         surf_index.upload(xp.surf_index, st);
-        chunk_sfirst.upload(xp.chunk_sfirst, st);
-        coll.upload(pack4(xp.coll), st);
+        surf_osv.upload(xp.surf_osv, st);
         size_t const n_boxes = static_cast<size_t>(xp.n_entries) + static_cast<size_t>(xp.n_shared) + 1;
         box.upload(std::vector<uint4>(n_boxes * Xchg<R>::kWords, make_uint4(0u, 0u, 0u, 0u)), st);
         box_bytes = n_boxes * Xchg<R>::kWords * sizeof(uint4);
@@ -1218,7 +1057,6 @@ struct ResidentPlan
         // the big host arrays are on the device now
         std::vector<uint32_t>().swap(xp.pull);
         std::vector<uint32_t>().swap(xp.push);
-        std::vector<uint32_t>().swap(xp.coll);
         std::vector<uint16_t>().swap(xp.tet_slots);
 
         args.s            = d;
@@ -1251,10 +1089,7 @@ struct ResidentPlan
         args.surf_off     = surf_off.p;
         args.surf_slot    = surf_slot.p;
         args.surf_index   = surf_index.p;
-        args.chunk_sfirst = chunk_sfirst.p;
-        args.n_sclusters  = xp.n_sclusters;
-        args.coll_groups  = xp.coll_groups;
-        args.coll         = coll.p;
+        args.surf_osv     = surf_osv.p;
         args.box          = box.p;
         args.n_entries    = xp.n_entries;
         args.error        = error.p;
@@ -1263,9 +1098,9 @@ struct ResidentPlan
     }
 
     // tags consumed per substep launch
-    uint32_t steps_per_substep(int iterations) const
+    uint32_t steps_per_substep(int iterations, bool collide) const
     {
-        return 2u + static_cast<uint32_t>(iterations) * static_cast<uint32_t>(args.n_colours);
+        return 2u + static_cast<uint32_t>(iterations) * (static_cast<uint32_t>(args.n_colours) + (collide ? 1u : 0u));
     }
 
     // enqueue one substep; returns kernels launched
@@ -1284,7 +1119,7 @@ struct ResidentPlan
                                            params, smem, st);
         if (e != cudaSuccess)
             throw std::runtime_error(std::string("launch of the substep kernel: ") + cudaGetErrorString(e));
-        base += steps_per_substep(iterations);
+        base += steps_per_substep(iterations, collide);
         return 1;
     }
 

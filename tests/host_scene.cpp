@@ -226,8 +226,7 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
     ExchangePlan xp;
     if (!build_exchange_plan(h, cp, regions, world, xp))
         return -2;
-    int32_t const Rn = cp.n_regions, C = cp.n_colours, K = iterations;
-    bool const cs    = collide != 0;
+    int32_t const Rn = cp.n_regions, C = cp.n_colours, K = iterations, cs = collide ? 1 : 0;
     int64_t const V = h.n_vertices(), NX = xp.n_xclusters;
     if (Rn % world != 0)
         return -3;
@@ -262,7 +261,7 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
 
     // ---- the regions, phase by phase
     uint32_t const base = 1;
-    int32_t const n_phases = 2 + K * C;
+    int32_t const per_iteration = C + cs, n_phases = 2 + K * per_iteration;
     std::vector<std::vector<Box>> box(static_cast<size_t>(world),
                                       std::vector<Box>(static_cast<size_t>(xp.n_entries) + static_cast<size_t>(xp.n_shared)));
     std::vector<std::vector<uint64_t>> sx(static_cast<size_t>(Rn));
@@ -288,14 +287,15 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
         b.consumed = true;
         return b.value;
     };
-    auto last_colour_tag = [&](int32_t k, uint32_t lastc) { return base + 1u + static_cast<uint32_t>(k * C) + lastc; };
-    int64_t collisions_done = 0;
+    auto last_colour_tag = [&](int32_t k, uint32_t lastc) {
+        return base + 1u + static_cast<uint32_t>(k * per_iteration + cs) + lastc;
+    };
     for (int32_t r = 0; r < Rn; ++r)
         sx[static_cast<size_t>(r)].assign(static_cast<size_t>(xp.loc_off[r + 1] - xp.loc_off[r]), 0xdeadbeefdeadbeefull);
     for (int32_t p = 0; p < n_phases && !error; ++p)
     {
         uint32_t const tag = base + static_cast<uint32_t>(p);
-        int32_t const k = p == 0 ? 0 : (p - 1) / C, c = p == 0 ? 0 : (p - 1) % C;
+        int32_t const k = p == 0 ? 0 : (p - 1) / per_iteration, q = p == 0 ? 0 : (p - 1) % per_iteration;
         for (int32_t rr = 0; rr < Rn && !error; ++rr)
         {
             int32_t const r = reverse ? Rn - 1 - rr : rr;
@@ -306,8 +306,12 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
                 for (int32_t i = 0; i < xp.n_owned[r]; ++i)
                     s[static_cast<size_t>(i)] = mix(loc[i], 1);
                 for (int32_t i = xp.osv_off[r]; i < xp.osv_off[r + 1]; ++i)
-                    if (K > 0 && (xp.osv_meta[static_cast<size_t>(i)] & kOsvFirstRemote))
+                {
+                    uint32_t const meta = xp.osv_meta[static_cast<size_t>(i)];
+                    bool const to_me    = K == 0 || (cs && (meta & kOsvSurface));
+                    if (!to_me && (meta & kOsvFirstRemote))
                         push(r, xp.osv_first[static_cast<size_t>(i)], s[xp.osv_slot[static_cast<size_t>(i)]], tag);
+                }
             }
             else if (p == n_phases - 1)
             { // commit
@@ -321,20 +325,33 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
                 for (int32_t i = 0; i < xp.n_owned[r]; ++i)
                     result[loc[i]] = s[static_cast<size_t>(i)];
             }
+            else if (cs && q == 0)
+            { // collision step: owned surface vertices
+                for (int32_t i = xp.surf_off[r]; i < xp.surf_off[r + 1]; ++i)
+                {
+                    uint32_t const slot = xp.surf_slot[static_cast<size_t>(i)], o = xp.surf_osv[static_cast<size_t>(i)];
+                    uint32_t const meta = o == kRouteNone ? 0u : xp.osv_meta[o];
+                    if (o != kRouteNone && k > 0 && (meta & kOsvLastRemote))
+                        s[slot] = pull(r, xp.n_entries + o, last_colour_tag(k - 1, meta & 0xffu));
+                    if (loc[slot] >= static_cast<uint32_t>(V) || !surface[loc[slot]])
+                        error = -13;
+                    s[slot] = mix(s[slot], 77u + static_cast<uint64_t>(k));
+                    if (o != kRouteNone && (meta & kOsvFirstRemote))
+                        push(r, xp.osv_first[o], s[slot], tag);
+                }
+            }
             else
             { // colour step
-                int pv = k > 0 ? 1 : 0, qv = k == K - 1 ? 1 : 0;
-                size_t const E  = static_cast<size_t>(xp.entries);
-                int32_t seen_x = 0, seen_s = 0; // exchange / collision clusters of this step so far
-                for (int part = 0; part < kParts; ++part)
+                int32_t const c  = q - cs;
+                int pv           = 2 * (k > 0 ? 1 : 0) + cs, qv = 2 * (k == K - 1 ? 1 : 0) + cs;
+                size_t const E   = static_cast<size_t>(xp.entries);
+                for (int part = 0; part < 2; ++part)
                 {
-                    ChunkDesc const& d = cp.chunks[(static_cast<size_t>(c) * Rn + r) * kParts + part];
+                    ChunkDesc const& d = cp.chunks[(static_cast<size_t>(c) * Rn + r) * 2 + part];
                     for (int32_t i = 0; i < d.n[0] && !error; ++i)
                     {
-                        bool const exchanges = part < 2, collides = part % 2 == 0;
-                        int64_t const xq = exchanges ? xp.chunk_xfirst[static_cast<size_t>(c) * Rn + r] + seen_x++ : -1;
-                        int64_t const sq = collides ? xp.chunk_sfirst[static_cast<size_t>(c) * Rn + r] + seen_s++ : -1;
-                        if (exchanges)
+                        int64_t const xq = part == 0 ? xp.chunk_xfirst[static_cast<size_t>(c) * Rn + r] + i : -1;
+                        if (part == 0)
                             for (size_t e = 0; e < E; ++e)
                             {
                                 uint32_t const w = xp.pull[((pv * (E / 4) + e / 4) * static_cast<size_t>(NX) + xq) * 4 + e % 4];
@@ -342,20 +359,6 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
                                     break;
                                 uint32_t const dd = w >> 16 & 0xffu, entry = w >> 24 & 0xfu, slot = w & 0xffffu;
                                 s[slot] = pull(r, static_cast<uint32_t>(entry * NX + xq), dd == kPullPredict ? base : tag - dd);
-                            }
-                        if (collides && cs)
-                            for (int32_t e = 0; e < 2 * xp.coll_groups; ++e)
-                            { // contacts of the surface vertices this cluster touches first in the sweep
-                                size_t const at = ((static_cast<size_t>(e / 2)) * static_cast<size_t>(xp.n_sclusters) + sq) * 4 + 2 * (e % 2);
-                                uint32_t const w = xp.coll[at];
-                                if (!(w & kPullValid))
-                                    break;
-                                uint32_t const slot = w & 0xffffu;
-                                if (slot >= s.size() || !surface[loc[slot]])
-                                    error = -13;
-                                else
-                                    s[slot] = mix(s[slot], 77u + static_cast<uint64_t>(k));
-                                ++collisions_done;
                             }
                         int64_t bse = d.first;
                         for (int m = 0; m < kMaxCluster && i < d.n[m]; ++m)
@@ -374,7 +377,7 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
                                 project(pp, t);
                             bse += d.n[m];
                         }
-                        if (exchanges)
+                        if (part == 0)
                             for (size_t e = 0; e < E; ++e)
                             {
                                 size_t const at = ((qv * (E / 2) + e / 2) * static_cast<size_t>(NX) + xq) * 4 + 2 * (e % 2);
@@ -388,14 +391,6 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
             }
         }
     }
-    if (!error && cs)
-    { // every surface vertex was projected once per sweep
-        int64_t n_surface = 0;
-        for (char f : surface)
-            n_surface += f;
-        if (collisions_done != n_surface * K)
-            error = -15;
-    }
     if (error)
         return error;
     for (int64_t v = 0; v < V; ++v)
@@ -408,9 +403,9 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
         stats[2] = NX;
         stats[3] = xp.entries;
         stats[4] = xp.n_shared;
-        stats[5] = xp.n_pulls[1];
+        stats[5] = xp.n_pulls[2];
         stats[6] = xp.n_pushes[0];
-        stats[7] = xp.n_sclusters;
+        stats[7] = xp.quiet_steps;
         stats[8] = xp.max_local;
         stats[9] = cp.nt;
         for (int32_t c = 0; c < C && c < 16; ++c)

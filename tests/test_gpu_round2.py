@@ -63,10 +63,10 @@ def test_general_route_counter_stays_zero_on_a_mild_scene(sbs, scenes):
     assert sim.stats()["green_general_calls"] == 0
 
 
-@pytest.mark.parametrize("shape", [0, 1, 2])
+@pytest.mark.parametrize("shape", [0, 1])
 @pytest.mark.parametrize("precision", [64, 32])
 def test_region_shapes_against_the_reference(sbs, scenes, oracle, precision, shape):
-    """Pencils, compact blocks and slabs cut the same mesh differently and order the colours differently; each
+    """Pencils and compact blocks cut the same mesh differently and order the colours differently; each
     exports its own serial order, and the reference run in that order agrees (config 2 at a size that gives
     several regions, contacts through a raised floor)."""
     scene = scenes.config2(W=13, H=13, D=41)
@@ -76,8 +76,6 @@ def test_region_shapes_against_the_reference(sbs, scenes, oracle, precision, sha
     st = sim.stats()
     assert st["schedule"] == sbs.SCHED_PERSISTENT and st["n_regions"] > 4, sim.schedule_note()
     assert st["n_shared_vertices"] > 0 and st["pulls_per_sweep"] > 0
-    if shape != sbs.REGIONS_COMPACT:
-        assert st["quiet_colours"] >= (4 if shape == sbs.REGIONS_PENCILS else 6)
     ref = oracle.World()
     scene.instantiate(ref)
     ref.set_constraint_order(sim.constraint_order())

@@ -3,11 +3,11 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02_pytest_gpu.log )
 tail -4 gpurun_out/r02_pytest_gpu.log
-for shape in 0 1 2; do
+for shape in 0 1; do
 ( REGION_SHAPE=$shape timeout 300 python tools/quick_time.py config3 32 0 5 > gpurun_out/r02_time_config3_shape$shape.txt 2>&1 ); tail -2 gpurun_out/r02_time_config3_shape$shape.txt
 done
-( REGION_SHAPE=2 timeout 300 python tools/quick_time.py config2 32 0 5 > gpurun_out/r02_time_config2_shape2.txt 2>&1 ); tail -1 gpurun_out/r02_time_config2_shape2.txt
 ( timeout 300 python tools/quick_time.py config2 32 0 5 > gpurun_out/r02_time_config2.txt 2>&1 ); tail -1 gpurun_out/r02_time_config2.txt
+( timeout 300 python tools/quick_time.py config1 32 0 5 > gpurun_out/r02_time_config1.txt 2>&1 ); tail -1 gpurun_out/r02_time_config1.txt
 ( NB=4096 timeout 600 python tools/quick_time.py config4 32 0 4 > gpurun_out/r02_time_config4.txt 2>&1 ); tail -1 gpurun_out/r02_time_config4.txt
-( timeout 300 python tools/quick_time.py config5 32 0 4 > gpurun_out/r02_time_config5.txt 2>&1 ); tail -2 gpurun_out/r02_time_config5.txt
-( REGION_SHAPE=2 timeout 120 python tools/trace_steps.py config3 > gpurun_out/r02_trace_config3_slabs.txt 2>&1 ); tail -100 gpurun_out/r02_trace_config3_slabs.txt
+( timeout 300 python tools/quick_time.py config5 32 0 4 > gpurun_out/r02_time_config5.txt 2>&1 ); tail -2 gpurun_out/r02_time_config5.txt; head -c 600 gpurun_out/r02_time_config5.txt
+( REGION_SHAPE=0 timeout 120 python tools/trace_steps.py config3 > gpurun_out/r02_trace_config3_pencils.txt 2>&1 ); tail -100 gpurun_out/r02_trace_config3_pencils.txt
