@@ -790,6 +790,8 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
                         Touch4 const& next = tl[i + (t + 1) % n];
                         Touch4 const& prev = tl[i + (t + n - 1) % n];
                         Cluster& c         = clusters[me.cluster];
+                        if (!resident->push_first)
+                            continue;
                         if (next.region != me.region)
                             c.prio = 0;
                         else if (prev.region != me.region && (me.colour - prev.colour + C) % C == 1)

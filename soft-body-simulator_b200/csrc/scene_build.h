@@ -142,6 +142,7 @@ struct ResidentParams
                                  // grid (compact in the two other axes) instead of compact Morton blocks: with the
                                  // colour order that goes with it (a Gray code of the cell parities on a lattice)
                                  // every step that flips the parity along the pencil axis depends on no other region
+    bool push_first      = true; // clusters that push in their step first inside a chunk (A/B knob)
     int32_t bodies_per_region = 0; // ensembles (one_region_per_body): consecutive bodies grouped into one region so
                                    // that a colour step fills its warps; 0 = choose (about 160 clusters per step)
 };

@@ -484,7 +484,7 @@ __device__ __forceinline__ void push_cluster(ResidentArgs<R> const& a, uint4 con
 template <typename R, bool kDict, typename Stamp>
 __device__ __forceinline__ void run_cluster(ResidentArgs<R> const& a, DevChunk const& ch, int32_t i,
                                             ClusterHead<R, kDict> const& head, Real4<R>* sx, Real4<R> const* s_dict,
-                                            int first_iteration, Stamp&& stamp)
+                                            int first_iteration, R inv_dt2, Stamp&& stamp)
 {
     DeviceScene<R> const& s = a.s;
     // column layout: tet m of cluster i sits at first + n[0] + .. + n[m-1] + i
@@ -516,7 +516,7 @@ __device__ __forceinline__ void run_cluster(ResidentArgs<R> const& a, DevChunk c
             Real4<R> const mat = s_dict[kShapeWords * cur.shape + 3];
             mu                 = mat.x;
             lam                = mat.y;
-            at                 = mat.z / (a.dt * a.dt);
+            at                 = mat.z * inv_dt2; // alpha / dt^2 (green_constraint.cpp:134)
         }
         else
         {
@@ -614,6 +614,7 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
         return a.base + 1u + static_cast<uint32_t>(k * per_iteration + cs) + lastc;
     };
     R const at_c = s.collision_alpha / (dt * dt);
+    R const inv_dt2 = R(1) / (dt * dt);
     int64_t const pull_stride = static_cast<int64_t>(a.entries / 4) * a.n_xclusters; // records per pull variant
     int64_t const push_stride = static_cast<int64_t>(a.entries / 2) * a.n_xclusters;
 
@@ -796,7 +797,7 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
                     w0           = __ldg(&push_variant[cur_xq]);
                     w1           = __ldg(&push_variant[a.n_xclusters + cur_xq]);
                 }
-                run_cluster<R, kDict>(a, ch, in_x ? item_i : item_i - nA, head, sx, s_dict, k == 0, stamp);
+                run_cluster<R, kDict>(a, ch, in_x ? item_i : item_i - nA, head, sx, s_dict, k == 0, inv_dt2, stamp);
                 // ---- (3) shared vertices whose next touch is another region's go there first: a neighbour's
                 //          next step waits for them
                 if (kExchange && cur_xq >= 0)
