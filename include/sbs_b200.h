@@ -54,9 +54,10 @@ extern "C" {
 #define SBSB200_SCHED_PERSISTENT 2 /* resident schedule: one kernel per substep, every region's vertices in shared memory */
 
 /* region shape of the resident schedule (sbsb200_set_region_shape) */
-#define SBSB200_REGIONS_PENCILS 0 /* bundles of cell columns along the shortest axis (default): half of the colour
-                                   * steps of a sweep on a lattice then exchange nothing between regions */
-#define SBSB200_REGIONS_COMPACT 1 /* compact blocks in Morton order */
+#define SBSB200_REGIONS_PENCILS 0 /* bundles of cell columns along the shortest axis: half of the colour steps of a
+                                   * sweep on a lattice then exchange nothing between regions */
+#define SBSB200_REGIONS_COMPACT 1 /* compact blocks in Morton order (default: fewest shared vertices; measured faster
+                                   * on B200 for the 1M-tet block, profiles/r02_summary.md) */
 
 typedef struct sbsb200_ctx sbsb200_ctx;
 

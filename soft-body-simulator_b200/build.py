@@ -8,7 +8,10 @@ LIB = os.path.join(HERE, "lib", "libsbsb200.so")
 SOURCES = ["csrc/sbs_b200.cu", "csrc/scene_build.cpp"]
 HEADERS = ["csrc/scene_build.h", "csrc/xpbd_math.cuh", "csrc/xpbd_kernels.cuh", "csrc/xpbd_resident.cuh", "csrc/bvh.cuh", "csrc/grid_sdf.cuh",
            "../include/sbs_b200.h"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+# -ftz=true: denormals flush to zero in fp32 (they carry no information in this path); division and square root
+# stay IEEE (-prec-div / -prec-sqrt at their defaults): the full -use_fast_math build failed the fp32 parity of
+# an ill-conditioned scene (profiles/r02_summary.md)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ftz=true",
               "-Xcompiler", "-fPIC,-Wall", "-shared"]
 
 

@@ -114,7 +114,7 @@ struct sbsb200_ctx
     ColourClass dist_cc;
     RegionPlan plan;
     ExchangePlan xplan;          // resident schedule: who pulls and pushes which shared vertex when (host side)
-    int region_shape  = SBSB200_REGIONS_PENCILS;
+    int region_shape  = SBSB200_REGIONS_COMPACT;
     int trace_steps   = 0;       // development aid (sbsb200_debug_trace_steps)
     uint64_t general_calls0 = 0; // device counter of green_general calls when the scene was finalized
     std::vector<uint32_t> order; // exported serial order (insertion indices)
@@ -1141,7 +1141,7 @@ int sbsb200_set_broadphase(sbsb200_ctx* c, int mode)
 
 int sbsb200_set_region_shape(sbsb200_ctx* c, int shape)
 {
-    if (!c || shape < 0 || shape > 3) // TEMPORARY A/B: 2, 3 = pencils / compact without the push-first order
+    if (!c || (shape != SBSB200_REGIONS_PENCILS && shape != SBSB200_REGIONS_COMPACT))
         return fail(c, SBSB200_ERR_INVALID, "bad region shape");
     if (c->finalized)
         return fail(c, SBSB200_ERR_STATE, "scene already finalized");
@@ -1545,7 +1545,7 @@ int sbsb200_finalize(sbsb200_ctx* c)
                 int per_sm;
             };
             std::vector<Attempt> attempts;
-            if (c->region_shape % 2 != SBSB200_REGIONS_COMPACT)
+            if (c->region_shape == SBSB200_REGIONS_PENCILS)
                 attempts.push_back({true, 1});
             attempts.push_back({false, 1});
             attempts.push_back({false, 2});
@@ -1557,7 +1557,6 @@ int sbsb200_finalize(sbsb200_ctx* c)
                 ResidentParams rp = c->precision == SBSB200_FP32 ? ResidentPlan<float>::resident_params()
                                                                  : ResidentPlan<double>::resident_params();
                 rp.pencils     = at.pencils;
-                rp.push_first  = c->region_shape < 2;
                 rp.smem_bytes  = rp.smem_bytes / per_sm - (per_sm > 1 ? 4096 : 0);
                 rp.max_threads = per_sm == 1 ? 384 : 192;
                 int32_t n_regions = regions_for(c->sm_count, T, c->world);

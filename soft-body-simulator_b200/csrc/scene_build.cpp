@@ -601,9 +601,121 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
                 return clusters[a].body < clusters[b].body;
             return key[a] < key[b];
         });
+        if (!pencils)
+        { // Compact regions by recursive coordinate bisection: the set is cut across its longest axis into two parts
+          // whose tet counts are in the ratio of the region counts they receive, recursively.  Boxes have fewer
+          // shared vertices than ranges of a space-filling curve, and consecutive region numbers stay spatially
+          // compact (a rank of a decomposed scene takes a block of them).  The unit that is dealt out is a block of
+          // 2 x 2 x 2 cells of the cluster grid: on a lattice it holds one cluster of every colour, so every region
+          // has the same number of clusters in every colour step (a box with odd sides would have 6 x 6 x 6 clusters
+          // of one colour and 5 x 5 x 5 of another).
+            struct Block
+            {
+                int32_t body;
+                uint32_t bx, by, bz;
+                int64_t weight = 0;
+                double c[3]    = {0, 0, 0};
+                int32_t region = 0;
+            };
+            std::vector<uint32_t> by_block(clusters.size());
+            std::iota(by_block.begin(), by_block.end(), 0u);
+            auto const block_less = [&](uint32_t x, uint32_t y) {
+                Cluster const &p = clusters[x], &q = clusters[y];
+                if (p.body != q.body)
+                    return p.body < q.body;
+                if (p.cx / 2 != q.cx / 2)
+                    return p.cx / 2 < q.cx / 2;
+                if (p.cy / 2 != q.cy / 2)
+                    return p.cy / 2 < q.cy / 2;
+                return p.cz / 2 < q.cz / 2;
+            };
+            std::stable_sort(by_block.begin(), by_block.end(), block_less);
+            std::vector<Block> blocks;
+            std::vector<uint32_t> block_of(clusters.size(), 0);
+            for (size_t k = 0; k < by_block.size(); ++k)
+            {
+                Cluster const& cl = clusters[by_block[k]];
+                if (k == 0 || block_less(by_block[k - 1], by_block[k]))
+                {
+                    Block nb;
+                    nb.body = cl.body;
+                    nb.bx   = cl.cx / 2;
+                    nb.by   = cl.cy / 2;
+                    nb.bz   = cl.cz / 2;
+                    blocks.push_back(nb);
+                }
+                Block& bl = blocks.back();
+                block_of[by_block[k]] = static_cast<uint32_t>(blocks.size() - 1);
+                bl.weight += cl.count;
+                for (uint32_t p = cl.first; p < cl.first + cl.count; ++p)
+                    for (int a = 0; a < 4; ++a)
+                        for (int d = 0; d < 3; ++d)
+                            bl.c[d] += scene.x0[3 * static_cast<size_t>(scene.tets[4 * static_cast<size_t>(sorted[p]) + a]) + d];
+            }
+            for (Block& bl : blocks)
+                for (int d = 0; d < 3; ++d)
+                    bl.c[d] /= 4.0 * static_cast<double>(std::max<int64_t>(bl.weight, 1));
+            std::vector<uint32_t> order(blocks.size());
+            std::iota(order.begin(), order.end(), 0u);
+            struct Job
+            {
+                size_t begin, end;
+                int32_t r0, r1;
+            };
+            std::vector<Job> stack{{0, order.size(), 0, n_regions}};
+            while (!stack.empty())
+            {
+                Job const j = stack.back();
+                stack.pop_back();
+                if (j.r1 - j.r0 <= 1 || j.end - j.begin <= 1)
+                {
+                    for (size_t k = j.begin; k < j.end; ++k)
+                        blocks[order[k]].region = j.r0;
+                    continue;
+                }
+                double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+                int64_t weight = 0;
+                for (size_t k = j.begin; k < j.end; ++k)
+                {
+                    for (int d = 0; d < 3; ++d)
+                    {
+                        lo[d] = std::min(lo[d], blocks[order[k]].c[d]);
+                        hi[d] = std::max(hi[d], blocks[order[k]].c[d]);
+                    }
+                    weight += blocks[order[k]].weight;
+                }
+                int ax = 0;
+                for (int d = 1; d < 3; ++d)
+                    if (hi[d] - lo[d] > hi[ax] - lo[ax])
+                        ax = d;
+                int const b = (ax + 1) % 3, c = (ax + 2) % 3;
+                std::sort(order.begin() + static_cast<std::ptrdiff_t>(j.begin), order.begin() + static_cast<std::ptrdiff_t>(j.end),
+                          [&](uint32_t x, uint32_t y) {
+                              Block const &p = blocks[x], &q = blocks[y];
+                              if (p.c[ax] != q.c[ax])
+                                  return p.c[ax] < q.c[ax];
+                              if (p.c[b] != q.c[b])
+                                  return p.c[b] < q.c[b];
+                              if (p.c[c] != q.c[c])
+                                  return p.c[c] < q.c[c];
+                              return x < y;
+                          });
+                int32_t const left = (j.r1 - j.r0) / 2;
+                int64_t const want = weight * left / (j.r1 - j.r0);
+                int64_t seen_w     = 0;
+                size_t cut         = j.begin;
+                while (cut < j.end - 1 && seen_w + blocks[order[cut]].weight / 2 < want)
+                    seen_w += blocks[order[cut++]].weight;
+                cut = std::max(cut, j.begin + 1);
+                stack.push_back({j.begin, cut, j.r0, j.r0 + left});
+                stack.push_back({cut, j.end, j.r0 + left, j.r1});
+            }
+            for (size_t i = 0; i < clusters.size(); ++i)
+                clusters[i].region = blocks[block_of[i]].region;
+        }
         int64_t seen   = 0;
         int32_t region = 0;
-        for (size_t k = 0; k < idx.size(); ++k)
+        for (size_t k = 0; pencils && k < idx.size(); ++k)
         { // balanced by tet count; a pencil column is never split
             uint32_t const i = idx[k];
             bool const new_unit =

@@ -138,7 +138,7 @@ struct ResidentParams
     int32_t vertex_bytes = 16; // sizeof(Real4<R>)
     int32_t max_threads  = 512;
     bool rotate_items    = true; // clusters that exchange vertices on the warps with a sub-partition to themselves
-    bool pencils         = true; // regions = bundles of whole cluster columns along the shortest axis of the cluster
+    bool pencils         = false; // regions = bundles of whole cluster columns along the shortest axis of the cluster
                                  // grid (compact in the two other axes) instead of compact Morton blocks: with the
                                  // colour order that goes with it (a Gray code of the cell parities on a lattice)
                                  // every step that flips the parity along the pencil axis depends on no other region

@@ -204,6 +204,17 @@ SBS_HD void sym_eig3(R a00, R a11, R a22, R a01, R a02, R a12, R& l0, R& l1,
         swap_cols(l1, l2, v1, v2);
 }
 
+// 2^-n for small n >= 0, through the exponent field
+SBS_HD float pow2_neg(int n, float)
+{
+#ifdef __CUDA_ARCH__
+    return __int_as_float((127 - n) << 23);
+#else
+    return 1.0f / static_cast<float>(1 << n);
+#endif
+}
+SBS_HD double pow2_neg(int n, double) { return 1.0 / static_cast<double>(1 << n); }
+
 template <typename R>
 struct GreenOut
 {
@@ -352,41 +363,59 @@ SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3, Vec3<R> x
     R det      = dot(c0, n0);
     bool const inverted = det < R(0);
 
-    Vec3<R> pk0, pk1, pk2; // columns of P
     R psi;
+    R const nv = -abs_(V0s);
+    GreenOut<R> o;
 
-    // all singular values above the clamp <=> B = A - smin^2 I is positive definite
-    R const smin = R(0.577);
-    R const b00 = a00 - smin * smin, b11 = a11 - smin * smin, b22 = a22 - smin * smin;
-    R const m2  = b00 * b11 - a01 * a01;
-    R const m3  = b22 * m2 - a02 * (a02 * b11 - a01 * a12) + a12 * (a02 * a01 - b00 * a12);
     R const g00 = R(0.5) * a00 - R(0.5), g11 = R(0.5) * a11 - R(0.5), g22 = R(0.5) * a22 - R(0.5);
     R const g01 = R(0.5) * a01, g02 = R(0.5) * a02, g12 = R(0.5) * a12;
     R const e2n = g00 * g00 + g11 * g11 + g22 * g22 + R(2) * (g01 * g01 + g02 * g02 + g12 * g12);
-    if (!inverted && b00 > R(0) && m2 > R(0) && m3 > R(0) && e2n <= PolarSteps<R>::max_e2n)
+    // All singular values above the clamp <=> B = A - smin^2 I is positive definite.  Every eigenvalue of A is
+    // at least 1 - 2 |E_G|_F, so |E_G|_F^2 < 0.1112 (strains below a third) settles it without the minors;
+    // beyond that the three leading minors of B decide.
+    bool fast = !inverted && e2n <= PolarSteps<R>::max_e2n;
+    if (fast && e2n >= R(0.1112))
+    {
+        R const smin = R(0.577);
+        R const b00 = a00 - smin * smin, b11 = a11 - smin * smin, b22 = a22 - smin * smin;
+        R const m2  = b00 * b11 - a01 * a01;
+        R const m3  = b22 * m2 - a02 * (a02 * b11 - a01 * a12) + a12 * (a02 * a01 - b00 * a12);
+        fast        = b00 > R(0) && m2 > R(0) && m3 > R(0);
+    }
+    if (fast)
     {
         R const trg = g00 + g11 + g22;
-        // M = 2 mu E_G + lam tr(E_G) I ; P = F M
-        R const tm  = R(2) * mu;
-        R const lt  = lam * trg;
+        // H = -|V0| P DmInv^T = F N with N = (-|V0| M) DmInv^T, M = 2 mu E_G + lam tr(E_G) I  (:112-116)
+        R const tm  = R(2) * mu * nv;
+        R const lt  = lam * trg * nv;
         R const m00 = tm * g00 + lt, m11 = tm * g11 + lt, m22 = tm * g22 + lt;
         R const m01 = tm * g01, m02 = tm * g02, m12 = tm * g12;
-        pk0 = {c0.x * m00 + c1.x * m01 + c2.x * m02, c0.y * m00 + c1.y * m01 + c2.y * m02,
-               c0.z * m00 + c1.z * m01 + c2.z * m02};
-        pk1 = {c0.x * m01 + c1.x * m11 + c2.x * m12, c0.y * m01 + c1.y * m11 + c2.y * m12,
-               c0.z * m01 + c1.z * m11 + c2.z * m12};
-        pk2 = {c0.x * m02 + c1.x * m12 + c2.x * m22, c0.y * m02 + c1.y * m12 + c2.y * m22,
-               c0.z * m02 + c1.z * m12 + c2.z * m22};
-        // polar rotation by Newton: R <- (R + cof(R)/det(R)) / 2, columns q0 q1 q2
+        // N[k][c] = sum_j M[k][j] DmInv[c][j]
+        R const n00 = m00 * d00 + m01 * d01 + m02 * d02, n01 = m00 * d10 + m01 * d11 + m02 * d12,
+                n02 = m00 * d20 + m01 * d21 + m02 * d22;
+        R const n10 = m01 * d00 + m11 * d01 + m12 * d02, n11 = m01 * d10 + m11 * d11 + m12 * d12,
+                n12 = m01 * d20 + m11 * d21 + m12 * d22;
+        R const n20 = m02 * d00 + m12 * d01 + m22 * d02, n21 = m02 * d10 + m12 * d11 + m22 * d12,
+                n22 = m02 * d20 + m12 * d21 + m22 * d22;
+        o.f1 = {c0.x * n00 + c1.x * n10 + c2.x * n20, c0.y * n00 + c1.y * n10 + c2.y * n20,
+                c0.z * n00 + c1.z * n10 + c2.z * n20};
+        o.f2 = {c0.x * n01 + c1.x * n11 + c2.x * n21, c0.y * n01 + c1.y * n11 + c2.y * n21,
+                c0.z * n01 + c1.z * n11 + c2.z * n21};
+        o.f3 = {c0.x * n02 + c1.x * n12 + c2.x * n22, c0.y * n02 + c1.y * n12 + c2.y * n22,
+                c0.z * n02 + c1.z * n12 + c2.z * n22};
+        // Polar rotation by Newton, X <- (X + X^-T) / 2, carried as X = sigma U with sigma = 2^-it:
+        // U <- U + cof(U) / (sigma^2 det U) costs one fused multiply-add per entry and no scaling of U.
         Vec3<R> q0 = c0, q1 = c1, q2 = c2;
         int const steps = PolarSteps<R>::of(e2n);
+        R inv_sigma2    = R(1); // 4^it
 #pragma unroll 1
         for (int it = 0;;)
         {
-            R const h = div_(R(0.5), det);
-            q0        = {R(0.5) * q0.x + h * n0.x, R(0.5) * q0.y + h * n0.y, R(0.5) * q0.z + h * n0.z};
-            q1        = {R(0.5) * q1.x + h * n1.x, R(0.5) * q1.y + h * n1.y, R(0.5) * q1.z + h * n1.z};
-            q2        = {R(0.5) * q2.x + h * n2.x, R(0.5) * q2.y + h * n2.y, R(0.5) * q2.z + h * n2.z};
+            R const h = div_(inv_sigma2, det);
+            q0        = {q0.x + h * n0.x, q0.y + h * n0.y, q0.z + h * n0.z};
+            q1        = {q1.x + h * n1.x, q1.y + h * n1.y, q1.z + h * n1.z};
+            q2        = {q2.x + h * n2.x, q2.y + h * n2.y, q2.z + h * n2.z};
+            inv_sigma2 *= R(4);
             if (++it >= steps)
                 break;
             n0  = cross(q1, q2);
@@ -394,23 +423,24 @@ SBS_HD GreenOut<R> green_gradients(Vec3<R> x1, Vec3<R> x2, Vec3<R> x3, Vec3<R> x
             n2  = cross(q0, q1);
             det = dot(q0, n0);
         }
-        // tr(R E_G) with R[r][k] = q_k[r]
-        R const Etr = q0.x * g00 + q0.y * g01 + q0.z * g02 + q1.x * g01 + q1.y * g11 + q1.z * g12 + q2.x * g02 +
-                      q2.y * g12 + q2.z * g22;
+        // tr(R E_G) with R[r][k] = sigma q_k[r], sigma = 2^-steps = 1 / sqrt(inv_sigma2)
+        R const sigma = pow2_neg(steps, R(0));
+        R const Etr = sigma * (q0.x * g00 + q0.y * g01 + q0.z * g02 + q1.x * g01 + q1.y * g11 + q1.z * g12 +
+                               q2.x * g02 + q2.y * g12 + q2.z * g22);
         psi = mu * e2n + R(0.5) * lam * Etr * Etr;
     }
     else
+    {
+        Vec3<R> pk0, pk1, pk2; // columns of P
         green_general<R>(c0, c1, c2, a00, a11, a22, a01, a02, a12, inverted, mu, lam, pk0, pk1, pk2, psi);
-
-    // H = -|V0| P DmInv^T (:115-116): column c of H = -|V0| * sum_k P[:,k] DmInv[c][k]
-    R const nv = -abs_(V0s);
-    GreenOut<R> o;
-    o.f1 = {nv * (pk0.x * d00 + pk1.x * d01 + pk2.x * d02), nv * (pk0.y * d00 + pk1.y * d01 + pk2.y * d02),
-            nv * (pk0.z * d00 + pk1.z * d01 + pk2.z * d02)};
-    o.f2 = {nv * (pk0.x * d10 + pk1.x * d11 + pk2.x * d12), nv * (pk0.y * d10 + pk1.y * d11 + pk2.y * d12),
-            nv * (pk0.z * d10 + pk1.z * d11 + pk2.z * d12)};
-    o.f3 = {nv * (pk0.x * d20 + pk1.x * d21 + pk2.x * d22), nv * (pk0.y * d20 + pk1.y * d21 + pk2.y * d22),
-            nv * (pk0.z * d20 + pk1.z * d21 + pk2.z * d22)};
+        // H = -|V0| P DmInv^T (:115-116): column c of H = -|V0| * sum_k P[:,k] DmInv[c][k]
+        o.f1 = {nv * (pk0.x * d00 + pk1.x * d01 + pk2.x * d02), nv * (pk0.y * d00 + pk1.y * d01 + pk2.y * d02),
+                nv * (pk0.z * d00 + pk1.z * d01 + pk2.z * d02)};
+        o.f2 = {nv * (pk0.x * d10 + pk1.x * d11 + pk2.x * d12), nv * (pk0.y * d10 + pk1.y * d11 + pk2.y * d12),
+                nv * (pk0.z * d10 + pk1.z * d11 + pk2.z * d12)};
+        o.f3 = {nv * (pk0.x * d20 + pk1.x * d21 + pk2.x * d22), nv * (pk0.y * d20 + pk1.y * d21 + pk2.y * d22),
+                nv * (pk0.z * d20 + pk1.z * d21 + pk2.z * d22)};
+    }
     o.C  = abs_(V0s) * psi; // :133
     return o;
 }

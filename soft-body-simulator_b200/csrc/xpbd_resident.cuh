@@ -677,17 +677,33 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
         // ---- (2) the work of this pass
         if (p == 0)
         { // ---- predict (timestep.cpp:35-43): owned vertices; guests only need their inverse mass
-            for (int32_t i = tid; i < nl; i += nt)
+            // (four vertices per thread and trip: the index loads, then the state loads, are in flight together)
+            for (int32_t i0 = tid; i0 < nl; i0 += 4 * nt)
             {
-                uint32_t const gv = a.loc_vtx[l0 + i];
-                Real4<R> pp       = ld4(&s.pos[gv]);
-                if (i < no)
-                {
-                    Real4<R> const x = ld4(&s.prev[gv]);
-                    Real4<R> v       = ld4(&s.vel[gv]);
-                    predict_vertex(pp, x, v, dt);
-                }
-                sx[i] = pp;
+                uint32_t gv[4];
+                Real4<R> pp[4], x[4], v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    gv[e] = i0 + e * nt < nl ? a.loc_vtx[l0 + i0 + e * nt] : 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (i0 + e * nt < nl)
+                    {
+                        pp[e] = ld4(&s.pos[gv[e]]);
+                        if (i0 + e * nt < no)
+                        {
+                            x[e] = ld4(&s.prev[gv[e]]);
+                            v[e] = ld4(&s.vel[gv[e]]);
+                        }
+                    }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (i0 + e * nt < nl)
+                    {
+                        if (i0 + e * nt < no)
+                            predict_vertex(pp[e], x[e], v[e], dt);
+                        sx[i0 + e * nt] = pp[e];
+                    }
             }
             if constexpr (kExchange)
             {
@@ -725,15 +741,28 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
                 }
                 __syncthreads();
             }
-            for (int32_t i = tid; i < no; i += nt)
+            for (int32_t i0 = tid; i0 < no; i0 += 4 * nt)
             {
-                uint32_t const gv = a.loc_vtx[l0 + i];
-                Real4<R> const pp = sx[i];
-                Real4<R> xn       = ld4(&s.prev[gv]);
-                Real4<R> v        = ld4(&s.vel[gv]);
-                commit_vertex(pp, xn, v, dt);
-                st4(&s.vel[gv], v);
-                st4(&s.prev[gv], xn);
+                uint32_t gv[4];
+                Real4<R> xn[4], v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    gv[e] = i0 + e * nt < no ? a.loc_vtx[l0 + i0 + e * nt] : 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (i0 + e * nt < no)
+                    {
+                        xn[e] = ld4(&s.prev[gv[e]]);
+                        v[e]  = ld4(&s.vel[gv[e]]);
+                    }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (i0 + e * nt < no)
+                    {
+                        commit_vertex(sx[i0 + e * nt], xn[e], v[e], dt);
+                        st4(&s.vel[gv[e]], v[e]);
+                        st4(&s.prev[gv[e]], xn[e]);
+                    }
             }
             // tetrahedral_body_t::update_visual_model (tetrahedral_body.cpp:157-165), owned surface vertices
             for (int32_t i = tid; i < ns; i += nt)
