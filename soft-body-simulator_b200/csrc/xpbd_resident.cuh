@@ -546,6 +546,93 @@ __device__ __forceinline__ void run_cluster(ResidentArgs<R> const& a, DevChunk c
     }
 }
 
+// Predict (timestep.cpp:35-43) of the vertices a region owns, into its vertex table; guests only need their inverse
+// mass.  Out of line: the loops below want many registers for a short time (four vertices per thread and trip: the
+// index loads, then the state loads, are in flight together), which the colour steps must not pay for.
+template <typename R, int kBatch>
+__device__ __forceinline__ void predict_owned(Real4<R> const* pos, Real4<R> const* prev, Real4<R> const* vel,
+                                           uint32_t const* loc_vtx, R dt, Real4<R>* sx, int32_t nl, int32_t no)
+{
+    struct
+    {
+        Real4<R> const *pos, *prev, *vel;
+    } s{pos, prev, vel};
+    struct
+    {
+        uint32_t const* loc_vtx;
+    } a{loc_vtx};
+    int32_t const l0 = 0;
+    int const tid = threadIdx.x, nt = blockDim.x;
+    // (four vertices per thread and trip: the index loads, then the state loads, are in flight together)
+    for (int32_t i0 = tid; i0 < nl; i0 += kBatch * nt)
+    {
+        uint32_t gv[kBatch];
+        Real4<R> pp[kBatch], x[kBatch], v[kBatch];
+#pragma unroll
+        for (int e = 0; e < kBatch; ++e)
+            gv[e] = i0 + e * nt < nl ? a.loc_vtx[l0 + i0 + e * nt] : 0u;
+#pragma unroll
+        for (int e = 0; e < kBatch; ++e)
+            if (i0 + e * nt < nl)
+            {
+                pp[e] = ld4(&s.pos[gv[e]]);
+                if (i0 + e * nt < no)
+                {
+                    x[e] = ld4(&s.prev[gv[e]]);
+                    v[e] = ld4(&s.vel[gv[e]]);
+                }
+            }
+#pragma unroll
+        for (int e = 0; e < kBatch; ++e)
+            if (i0 + e * nt < nl)
+            {
+                if (i0 + e * nt < no)
+                    predict_vertex(pp[e], x[e], v[e], dt);
+                sx[i0 + e * nt] = pp[e];
+            }
+    }
+}
+
+// Commit (timestep.cpp:48-57) of the vertices a region owns, out of its vertex table.
+template <typename R, int kBatch>
+__device__ __forceinline__ void commit_owned(Real4<R>* prev, Real4<R>* vel, uint32_t const* loc_vtx, R dt,
+                                          Real4<R> const* sx, int32_t no)
+{
+    struct
+    {
+        Real4<R> *prev, *vel;
+    } s{prev, vel};
+    struct
+    {
+        uint32_t const* loc_vtx;
+    } a{loc_vtx};
+    int32_t const l0 = 0;
+    int const tid = threadIdx.x, nt = blockDim.x;
+    for (int32_t i0 = tid; i0 < no; i0 += kBatch * nt)
+    {
+        uint32_t gv[kBatch];
+        Real4<R> xn[kBatch], v[kBatch];
+#pragma unroll
+        for (int e = 0; e < kBatch; ++e)
+            gv[e] = i0 + e * nt < no ? a.loc_vtx[l0 + i0 + e * nt] : 0u;
+#pragma unroll
+        for (int e = 0; e < kBatch; ++e)
+            if (i0 + e * nt < no)
+            {
+                xn[e] = ld4(&s.prev[gv[e]]);
+                v[e]  = ld4(&s.vel[gv[e]]);
+            }
+#pragma unroll
+        for (int e = 0; e < kBatch; ++e)
+            if (i0 + e * nt < no)
+            {
+                commit_vertex(sx[i0 + e * nt], xn[e], v[e], dt);
+                st4(&s.vel[gv[e]], v[e]);
+                st4(&s.prev[gv[e]], xn[e]);
+            }
+    }
+}
+
 // kExchange = false: the launch runs regions that share no vertex with any other (ensembles, a body in one
 // region): no mailbox code at all.
 template <typename R, bool kTrace, bool kDict, bool kExchange>
@@ -677,34 +764,7 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
         // ---- (2) the work of this pass
         if (p == 0)
         { // ---- predict (timestep.cpp:35-43): owned vertices; guests only need their inverse mass
-            // (four vertices per thread and trip: the index loads, then the state loads, are in flight together)
-            for (int32_t i0 = tid; i0 < nl; i0 += 4 * nt)
-            {
-                uint32_t gv[4];
-                Real4<R> pp[4], x[4], v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    gv[e] = i0 + e * nt < nl ? a.loc_vtx[l0 + i0 + e * nt] : 0u;
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (i0 + e * nt < nl)
-                    {
-                        pp[e] = ld4(&s.pos[gv[e]]);
-                        if (i0 + e * nt < no)
-                        {
-                            x[e] = ld4(&s.prev[gv[e]]);
-                            v[e] = ld4(&s.vel[gv[e]]);
-                        }
-                    }
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (i0 + e * nt < nl)
-                    {
-                        if (i0 + e * nt < no)
-                            predict_vertex(pp[e], x[e], v[e], dt);
-                        sx[i0 + e * nt] = pp[e];
-                    }
-            }
+            predict_owned<R, 2>(s.pos, s.prev, s.vel, a.loc_vtx + l0, dt, sx, nl, no);
             if constexpr (kExchange)
             {
                 __syncthreads();
@@ -741,29 +801,7 @@ __device__ void run_region(ResidentArgs<R> const& a, int32_t region, Real4<R>* s
                 }
                 __syncthreads();
             }
-            for (int32_t i0 = tid; i0 < no; i0 += 4 * nt)
-            {
-                uint32_t gv[4];
-                Real4<R> xn[4], v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    gv[e] = i0 + e * nt < no ? a.loc_vtx[l0 + i0 + e * nt] : 0u;
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (i0 + e * nt < no)
-                    {
-                        xn[e] = ld4(&s.prev[gv[e]]);
-                        v[e]  = ld4(&s.vel[gv[e]]);
-                    }
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (i0 + e * nt < no)
-                    {
-                        commit_vertex(sx[i0 + e * nt], xn[e], v[e], dt);
-                        st4(&s.vel[gv[e]], v[e]);
-                        st4(&s.prev[gv[e]], xn[e]);
-                    }
-            }
+            commit_owned<R, 2>(s.prev, s.vel, a.loc_vtx + l0, dt, sx, no);
             // tetrahedral_body_t::update_visual_model (tetrahedral_body.cpp:157-165), owned surface vertices
             for (int32_t i = tid; i < ns; i += nt)
             {
