@@ -90,7 +90,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -362,6 +362,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the XPBD path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # (NCCL otherwise prints its version on stdout, next to the JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sbs = importlib.import_module("soft-body-simulator_b200")
     sc = importlib.import_module("soft-body-simulator_b200.scenes")

@@ -1557,6 +1557,15 @@ int sbsb200_finalize(sbsb200_ctx* c)
                 ResidentParams rp = c->precision == SBSB200_FP32 ? ResidentPlan<float>::resident_params()
                                                                  : ResidentPlan<double>::resident_params();
                 rp.pencils     = at.pencils;
+                if (ensemble)
+                { // few bodies per SM: one body per region, so that every SM has several independent regions to
+                  // interleave (the latency of a colour step does not shrink with the region); many: enough bodies
+                  // per region to fill the warps of a colour step (0 = about 160 clusters in the widest step)
+                    int64_t bodies = 0;
+                    for (auto const& b : h.bodies)
+                        bodies += (b.kind == BodyKind::tet && b.n_tets > 0);
+                    rp.bodies_per_region = bodies < 8 * static_cast<int64_t>(c->sm_count) ? 1 : 0;
+                }
                 rp.smem_bytes  = rp.smem_bytes / per_sm - (per_sm > 1 ? 4096 : 0);
                 rp.max_threads = per_sm == 1 ? 384 : 192;
                 int32_t n_regions = regions_for(c->sm_count, T, c->world);

@@ -982,9 +982,12 @@ struct ResidentPlan
     static void const* pick(int threads, bool dict, bool exchange, bool two_per_sm)
     {
 #define SBS_K(T, B, D, X) reinterpret_cast<void const*>(k_substep_resident<R, kTrace, T, B, D, X>)
+#ifndef SBS_ISLAND_MINBLOCKS
+#define SBS_ISLAND_MINBLOCKS 2
+#endif
         if (!exchange)
-            return dict ? (threads <= 256 ? SBS_K(256, 2, true, false) : SBS_K(384, 1, true, false))
-                        : (threads <= 256 ? SBS_K(256, 2, false, false) : SBS_K(384, 1, false, false));
+            return dict ? (threads <= 256 ? SBS_K(256, SBS_ISLAND_MINBLOCKS, true, false) : SBS_K(384, 1, true, false))
+                        : (threads <= 256 ? SBS_K(256, SBS_ISLAND_MINBLOCKS, false, false) : SBS_K(384, 1, false, false));
         if (two_per_sm && threads <= 192) // more exchanging regions than SMs: two CTAs per SM must be co-resident
             return dict ? SBS_K(192, 2, true, true) : SBS_K(192, 2, false, true);
         return dict ? (threads <= 256 ? SBS_K(256, 1, true, true) : SBS_K(384, 1, true, true))
