@@ -217,7 +217,11 @@ const char* sbsb200_schedule_note(const sbsb200_ctx* ctx);
  * substep kernel itself (no host-side exchange, no collective).  After finalize every rank maps
  * the other ranks' mailbox arrays: across processes through CUDA IPC handles (64 bytes each,
  * exchanged by any means — bench.py uses torch.distributed.all_gather), inside one process
- * through connect_peer_context.  The reference has no counterpart (it is single-threaded). */
+ * through connect_peer_context.  The reference has no counterpart (it is single-threaded).
+ * The substep kernels of the ranks wait for each other's pushes: in a single process enqueue sbsb200_step on EVERY
+ * rank before any call that blocks on one of them (synchronize, download, get_contacts, get_stats); a rank that
+ * waits alone runs out of its poll budget, and the blocking call reports SBSB200_ERR_CUDA (the flag is cleared, the
+ * state of that frame is lost). */
 int sbsb200_set_partition(sbsb200_ctx* ctx, int rank, int world);
 int sbsb200_get_mailbox_handle(sbsb200_ctx* ctx, void* handle64);
 int sbsb200_connect_peers(sbsb200_ctx* ctx, const void* handles /* world x 64 bytes */, int world);

@@ -41,6 +41,7 @@ struct BvhView
     Real4<R>* sphere;         // nodes of level l >= 1 at sphere[level_offset[l] + j]: (centre, radius);
                               // radius < 0: the node spans several bodies and always passes
     int32_t n_levels;         // levels 1 .. n_levels - 1 exist (level 0 = the leaves themselves)
+    int32_t n_bodies;         // key prefix of a body that is not handed to the cd system: n_bodies + its index
     int64_t level_offset[kBvhMaxLevels];
     int64_t level_count[kBvhMaxLevels];
     R lo[3], inv_extent[3];   // quantisation box of the Morton codes (tree quality only)
@@ -84,7 +85,11 @@ __global__ void __launch_bounds__(256) k_bvh_keys(DeviceScene<R> s, BvhView<R> b
         q[d]      = static_cast<uint32_t>(u < R(0) ? R(0) : u > R(1023) ? R(1023) : u);
     }
     uint32_t const morton = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
-    b.keys[i]    = (static_cast<uint64_t>(static_cast<uint32_t>(s.surf_body[i])) << 32) | morton;
+    // key prefix = the body; a body that is not handed to the cd system (surf_body = ~index) gets a prefix of its own
+    // beyond the others, so that the (partial) radix sort keeps every body's leaves together
+    int32_t const sb    = s.surf_body[i];
+    uint32_t const body = sb >= 0 ? static_cast<uint32_t>(sb) : static_cast<uint32_t>(b.n_bodies + ~sb);
+    b.keys[i]    = (static_cast<uint64_t>(body) << 32) | morton;
     b.leaf_in[i] = static_cast<uint32_t>(i);
 }
 

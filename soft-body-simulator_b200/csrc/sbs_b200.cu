@@ -486,8 +486,9 @@ struct Engine final : EngineBase
             bvh.level_count[0]  = Vs;
             bvh_sphere.alloc(static_cast<size_t>(std::max<int64_t>(offset, 1)));
             bvh_sort_end_bit = 33;
-            while (bvh_sort_end_bit < 64 && (uint64_t{1} << (bvh_sort_end_bit - 32)) < c.scene.bodies.size())
+            while (bvh_sort_end_bit < 64 && (uint64_t{1} << (bvh_sort_end_bit - 32)) < 2 * c.scene.bodies.size())
                 ++bvh_sort_end_bit;
+            bvh.n_bodies = static_cast<int32_t>(c.scene.bodies.size());
             CK(cub::DeviceRadixSort::SortPairs(nullptr, bvh_temp_bytes, bvh_keys.p, bvh_keys_sorted.p, bvh_leaf_in.p,
                                                bvh_leaf_surface.p, static_cast<int>(Vs), 0, 64, st));
             bvh_temp.alloc(bvh_temp_bytes);
@@ -832,6 +833,7 @@ struct Engine final : EngineBase
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out, surf_out.p, sizeof(float) * 6 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, c.stream));
         CK(cudaStreamSynchronize(c.stream));
+        check_persistent(c);
     }
 
     void eval_sdf(sbsb200_ctx& c, int body, int64_t n, double const* pts, double* sd, double* grad) override
@@ -946,6 +948,7 @@ struct Engine final : EngineBase
         uint32_t n = 0;
         CK(cudaMemcpyAsync(&n, contact_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
         CK(cudaStreamSynchronize(c.stream));
+        check_persistent(c);
         n                 = static_cast<uint32_t>(std::min<int64_t>(n, d.contact_cap));
         c.last_contacts   = n;
         int64_t const m   = std::min<int64_t>(n, cap);
