@@ -264,35 +264,52 @@ class Bench:
                 "general_route_projections": st1["green_general_calls"]}
 
     def end_to_end(self, steps):
-        """Through sbsb200_step_host_f32 with pinned HOST buffers: H2D of x, v, the frame, D2H of x, v per step."""
+        """Through the C ABI with pinned HOST buffers: H2D of x, v, the frame, D2H of x, v per step (float host buffers).
+        A rank of a decomposed body round-trips the vertices it owns (sbsb200_step_host_vertices_f32), every other
+        workload the whole body (sbsb200_step_host_f32)."""
         import numpy as np
         import torch
-        sim, scene, stream = self.sim, self.scene, self.env["stream"]
+        sim, scene = self.sim, self.scene
         S, K = scene.substeps, scene.iterations
         b0 = scene.tet_bodies()[0]
         body = scene.items[b0]
-        nV = body.x0.shape[0]
-        x_in = torch.from_numpy(body.x.astype(np.float32)).pin_memory()
-        v_in = torch.from_numpy((body.v if body.v is not None else np.zeros_like(body.x)).astype(np.float32)).pin_memory()
+        x0 = body.x.astype(np.float32)
+        v0 = (body.v if body.v is not None else np.zeros_like(body.x)).astype(np.float32)
+        owned = None
+        if self.decomposed:
+            owned = np.ascontiguousarray(np.nonzero(sim.vertex_ranks(self.ids[b0]) == self.env["rank"])[0], np.uint32)
+            x0, v0 = x0[owned], v0[owned]
+        nV = x0.shape[0]
+        x_in = torch.from_numpy(np.ascontiguousarray(x0)).pin_memory()
+        v_in = torch.from_numpy(np.ascontiguousarray(v0)).pin_memory()
         x_out = torch.empty((nV, 3), dtype=torch.float32).pin_memory()
         v_out = torch.empty((nV, 3), dtype=torch.float32).pin_memory()
         xin, vin, xo, vo = x_in.numpy(), v_in.numpy(), x_out.numpy(), v_out.numpy()
+
+        def frame(xin, vin, xo, vo):
+            if owned is None:
+                sim.step_host_f32(self.ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
+            else:
+                sim.step_host_vertices_f32(self.ids[b0], owned, xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
+
         for _ in range(2):
-            sim.step_host_f32(self.ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
+            frame(xin, vin, xo, vo)
             xin, xo = xo, xin
             vin, vo = vo, vin
         self.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            sim.step_host_f32(self.ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
+            frame(xin, vin, xo, vo)
             xin, xo = xo, xin              # next frame continues from the host copy: the two pinned
             vin, vo = vo, vin              # buffer pairs swap roles, nothing is copied on the host
         self.barrier()
         wall = self.max_over_ranks(time.perf_counter() - t0)
-        return {"seconds": wall, "steps": steps, "h2d_bytes_per_step": int(2 * nV * 12),
+        ids_bytes = 0 if owned is None else int(4 * nV)
+        return {"seconds": wall, "steps": steps, "h2d_bytes_per_step": int(2 * nV * 12) + ids_bytes,
                 "d2h_bytes_per_step": int(2 * nV * 12), "contacts_last_detection": sim.contact_count(),
-                "timing": "wall clock around sbsb200_step_host_f32 (float host buffers), max over ranks",
-                "bodies_round_tripped": 1}
+                "timing": "wall clock around sbsb200_step_host%s_f32 (float host buffers), max over ranks"
+                          % ("_vertices" if owned is not None else ""),
+                "bodies_round_tripped": 1, "vertices_round_tripped_this_rank": int(nV)}
 
     def roofline(self, res, peak, peaks_found, share=1):
         """Algorithmic bytes / CUDA-event time, per GPU.  share: ranks one body is cut over."""
@@ -440,8 +457,9 @@ def main():
                 rec["e2e"] = {"value": s5.n_tets * S * K * r["steps"] / r["seconds"], "unit": UNIT,
                               "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"],
                               "steps": r["steps"], "timing": r["timing"],
-                              "note": "every rank round-trips the body's x, v (float) through pinned host memory each frame; "
-                                      "a rank holds and returns valid state for the vertices it owns"}
+                              "vertices_round_tripped_rank0": r["vertices_round_tripped_this_rank"],
+                              "note": "every rank round-trips x, v (float) of the vertices it owns through pinned host "
+                                      "memory each frame (bytes are rank 0's)"}
             sub["decomposed"] = rec
             b.close()
         except Exception as exc:                      # a failing sub-record must not hide the headline

@@ -271,6 +271,13 @@ int sbsb200_step_host(sbsb200_ctx* ctx, int body, const double* x_in, const doub
 int sbsb200_step_host_f32(sbsb200_ctx* ctx, int body, const float* x_in, const float* v_in, double dt,
                           int substeps, int iterations, int detect_mode, float* x_out, float* v_out);
 
+/* The same for n listed vertices of the body only (body-local indices; x_in NULL = keep the device state): what a
+ * rank of a decomposed body exchanges with its host — the vertices it owns (sbsb200_get_vertex_ranks) — instead of
+ * the whole body.  x, v: 3*n floats each, in the order of `vertices`. */
+int sbsb200_step_host_vertices_f32(sbsb200_ctx* ctx, int body, int64_t n, const uint32_t* vertices,
+                                   const float* x_in, const float* v_in, double dt, int substeps, int iterations,
+                                   int detect_mode, float* x_out, float* v_out);
+
 int sbsb200_synchronize(sbsb200_ctx* ctx);
 
 /* Contacts of the most recent detection, as the arguments handed to
@@ -279,6 +286,11 @@ int sbsb200_synchronize(sbsb200_ctx* ctx);
  * Pass NULL buffers to query the count.  Returns the count (>= 0) or an error. */
 int64_t sbsb200_get_contacts(sbsb200_ctx* ctx, int64_t cap, int32_t* body, uint32_t* vertex,
                              int32_t* sdf_body, double* point, double* normal);
+
+/* Validation aid: the number of vertices whose position or velocity is NaN / Inf (one kernel over the committed
+ * state, synchronises).  The reference has no counterpart: it never checks.  Every sbsb200_step is also
+ * wrapped in NVTX ranges ("sbsb200_step", "detection", "substep") for Nsight tools. */
+int64_t sbsb200_count_non_finite(sbsb200_ctx* ctx);
 
 /* Development aid (resident schedule): sbsb200_debug_trace_steps(ctx, N) before finalize selects a kernel
  * build that records %clock64 stamps of the first N colour steps of every launch, 16 per (region, step);

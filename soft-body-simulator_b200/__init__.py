@@ -35,6 +35,7 @@ EXPORTS = [
     "sbsb200_set_partition", "sbsb200_get_mailbox_handle", "sbsb200_connect_peers", "sbsb200_connect_peer_context",
     "sbsb200_get_vertex_ranks", "sbsb200_set_broadphase", "sbsb200_get_surface_triangles", "sbsb200_download_surface",
     "sbsb200_set_region_shape", "sbsb200_set_masses", "sbsb200_step_host_f32", "sbsb200_debug_trace_steps",
+    "sbsb200_step_host_vertices_f32", "sbsb200_count_non_finite",
 ]
 
 
@@ -124,6 +125,10 @@ def load_library():
     L.sbsb200_set_masses.argtypes = [vp, C.c_int, C.c_int64, _u32p, _dp]
     _fp = C.POINTER(C.c_float)
     L.sbsb200_step_host_f32.argtypes = [vp, C.c_int, _fp, _fp, C.c_double, C.c_int, C.c_int, C.c_int, _fp, _fp]
+    L.sbsb200_step_host_vertices_f32.argtypes = [vp, C.c_int, C.c_int64, _u32p, _fp, _fp, C.c_double, C.c_int, C.c_int,
+                                                 C.c_int, _fp, _fp]
+    L.sbsb200_count_non_finite.argtypes = [vp]
+    L.sbsb200_count_non_finite.restype = C.c_int64
     L.sbsb200_debug_trace_steps.argtypes = [vp, C.c_int]
     L.sbsb200_debug_read_trace.argtypes = [vp, C.POINTER(C.c_int64), C.c_int64]
     L.sbsb200_debug_read_trace.restype = C.c_int64
@@ -354,6 +359,21 @@ class Simulation:
         self._ck(self._L.sbsb200_step_host_f32(self._h, body, f(x_in), f(v_in), dt, substeps, iterations,
                                                DETECT_PER_SUBSTEP if detect_every_substep else DETECT_PER_FRAME,
                                                f(x_out), f(v_out)))
+
+    def step_host_vertices_f32(self, body, vertices, x_in, v_in, dt, substeps, iterations, detect_every_substep, x_out,
+                               v_out):
+        """step_host_f32 for the listed vertices only: float32 arrays [n, 3] in the order of `vertices` (uint32)."""
+        fp = C.POINTER(C.c_float)
+        f = lambda a: None if a is None else a.ctypes.data_as(fp)
+        assert vertices.dtype == np.uint32 and vertices.flags["C_CONTIGUOUS"]
+        for a in (x_in, v_in, x_out, v_out):
+            assert a is None or (a.dtype == np.float32 and a.flags["C_CONTIGUOUS"] and a.shape[0] == vertices.shape[0])
+        self._ck(self._L.sbsb200_step_host_vertices_f32(
+            self._h, body, vertices.shape[0], vertices.ctypes.data_as(_u32p), f(x_in), f(v_in), dt, substeps, iterations,
+            DETECT_PER_SUBSTEP if detect_every_substep else DETECT_PER_FRAME, f(x_out), f(v_out)))
+
+    def count_non_finite(self):
+        return self._ck(self._L.sbsb200_count_non_finite(self._h))
 
     def contact_count(self):
         return self._ck(self._L.sbsb200_get_contacts(self._h, 0, None, None, None, None, None))

@@ -9,6 +9,8 @@
 #include "bvh.cuh"
 #include "xpbd_resident.cuh"
 
+#include <nvtx3/nvToolsExt.h> // header-only: ranges show up in Nsight tools, cost nothing otherwise
+
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -81,8 +83,12 @@ struct EngineBase
                               double const* v)                                             = 0;
     virtual void set_masses(sbsb200_ctx& c, int64_t first, int64_t n, uint32_t const* which, double const* m) = 0;
     virtual uint64_t general_route_calls()                                                  = 0;
+    virtual int64_t count_non_finite(sbsb200_ctx& c)                                        = 0;
     virtual void step_host_f32(sbsb200_ctx& c, int body, float const* x, float const* v, double dt, int substeps,
                                int iterations, int detect, float* x_out, float* v_out)      = 0;
+    virtual void step_host_vertices_f32(sbsb200_ctx& c, int body, int64_t n, uint32_t const* which, float const* x,
+                                        float const* v, double dt, int substeps, int iterations, int detect,
+                                        float* x_out, float* v_out)                         = 0;
     virtual int64_t contacts(sbsb200_ctx& c, int64_t cap, int32_t* body, uint32_t* vertex,
                              int32_t* sdf_body, double* point, double* normal)             = 0;
     virtual void invalidate_graphs()                                                       = 0;
@@ -569,6 +575,7 @@ struct Engine final : EngineBase
         auto detect_now = [&] {
             if (!collide)
                 return;
+            NvtxRange const range("detection");
             CK(cudaMemsetAsync(d.contact_count, 0, sizeof(uint32_t), st));
             if (bvh.n > 0)
             { // broadphase: (once per frame: keys -> sort) -> refit of the bounding spheres; the cull itself
@@ -610,7 +617,10 @@ struct Engine final : EngineBase
                 }
                 if (timed)
                     CK(cudaEventRecord(kev[kev_used].first, st));
-                launched += pp.substep(d, dt, iterations, collide, st);
+                {
+                    NvtxRange const range("substep (resident kernel)");
+                    launched += pp.substep(d, dt, iterations, collide, st);
+                }
                 if (timed)
                     CK(cudaEventRecord(kev[kev_used++].second, st));
             }
@@ -690,8 +700,15 @@ struct Engine final : EngineBase
         return launched;
     }
 
+    struct NvtxRange
+    {
+        explicit NvtxRange(char const* name) { nvtxRangePushA(name); }
+        ~NvtxRange() { nvtxRangePop(); }
+    };
+
     void step(sbsb200_ctx& c, double dt, int substeps, int iterations, int detect) override
     {
+        NvtxRange const range("sbsb200_step (timestep_t::step)");
         cudaStream_t st = c.stream;
         CK(cudaEventRecord(c.ev0, st));
         bool const legacy_stream = st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread;
@@ -781,7 +798,7 @@ struct Engine final : EngineBase
         CK(cudaMemcpyAsync(stage_x.p, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
         if (v)
             CK(cudaMemcpyAsync(stage_v.p, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
-        k_scatter_state<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(d, hb.v_offset, n, ids.p, stage_x.p,
+        k_scatter_state<R, double><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(d, hb.v_offset, n, ids.p, stage_x.p,
                                                                                      v ? stage_v.p : nullptr);
         ++c.kernels;
         if (d.n_surface > 0)
@@ -895,11 +912,77 @@ struct Engine final : EngineBase
         CK(cudaStreamSynchronize(c.stream));
     }
 
+    // validation aid: vertices whose position or velocity is NaN / Inf
+    int64_t count_non_finite(sbsb200_ctx& c) override
+    {
+        DevBuf<unsigned long long> n;
+        n.alloc(1);
+        CK(cudaMemsetAsync(n.p, 0, sizeof(unsigned long long), c.stream));
+        if (d.n_vertices > 0)
+        {
+            k_count_non_finite<R><<<static_cast<unsigned>((d.n_vertices + 255) / 256), 256, 0, c.stream>>>(d, n.p);
+            ++c.kernels;
+        }
+        unsigned long long h = 0;
+        CK(cudaMemcpyAsync(&h, n.p, sizeof h, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        check_persistent(c);
+        return static_cast<int64_t>(h);
+    }
+
     uint64_t general_route_calls() override
     {
         unsigned long long n = 0;
         CK(cudaMemcpyFromSymbol(&n, g_general_route_calls, sizeof n));
         return n;
+    }
+
+    // sbsb200_step_host_vertices_f32: only the listed vertices cross PCIe (a rank of a decomposed body round-trips
+    // the vertices it owns)
+    DevBuf<uint32_t> host_vertex_ids;
+    void step_host_vertices_f32(sbsb200_ctx& c, int body, int64_t n, uint32_t const* which, float const* x, float const* v,
+                                double dt, int substeps, int iterations, int detect, float* x_out, float* v_out) override
+    {
+        HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
+        ensure_staging(n);
+        if (host_vertex_ids.n < static_cast<size_t>(n))
+            host_vertex_ids.alloc(static_cast<size_t>(n));
+        float* sxf = reinterpret_cast<float*>(stage_x.p);
+        float* svf = reinterpret_cast<float*>(stage_v.p);
+        unsigned const grid = static_cast<unsigned>((n + 255) / 256);
+        if (n > 0)
+        {
+            CK(cudaMemcpyAsync(host_vertex_ids.p, which, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c.stream));
+            if (x)
+            {
+                CK(cudaMemcpyAsync(sxf, x, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+                if (v)
+                    CK(cudaMemcpyAsync(svf, v, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+                k_scatter_state<R, float><<<grid, 256, 0, c.stream>>>(d, hb.v_offset, n, host_vertex_ids.p, sxf,
+                                                                     v ? svf : nullptr);
+                ++c.kernels;
+                if (d.n_surface > 0)
+                {
+                    k_surface_gather<R><<<static_cast<unsigned>((d.n_surface + 255) / 256), 256, 0, c.stream>>>(d);
+                    ++c.kernels;
+                }
+            }
+        }
+        step(c, dt, substeps, iterations, detect);
+        ++c.frames;
+        if (n > 0 && (x_out || v_out))
+        {
+            k_gather_state<R, float><<<grid, 256, 0, c.stream>>>(d, hb.v_offset, n, host_vertex_ids.p,
+                                                                x_out ? sxf : nullptr, v_out ? svf : nullptr);
+            ++c.kernels;
+            CK(cudaGetLastError());
+            if (x_out)
+                CK(cudaMemcpyAsync(x_out, sxf, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c.stream));
+            if (v_out)
+                CK(cudaMemcpyAsync(v_out, svf, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c.stream));
+        }
+        CK(cudaStreamSynchronize(c.stream));
+        check_persistent(c);
     }
 
     // sbsb200_step_host_f32: the state crosses PCIe as floats (half the bytes of the double interface)
@@ -1968,6 +2051,47 @@ int sbsb200_step_host_f32(sbsb200_ctx* c, int body, const float* x_in, const flo
     });
 }
 
+
+int sbsb200_step_host_vertices_f32(sbsb200_ctx* c, int body, int64_t n, const uint32_t* vertices, const float* x_in,
+                                   const float* v_in, double dt, int substeps, int iterations, int detect_mode,
+                                   float* x_out, float* v_out)
+{
+    if (!c || n < 0 || (n > 0 && !vertices))
+        return fail(c, SBSB200_ERR_INVALID, "bad arguments");
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "step_host before finalize");
+    if (!is_tet_body(c, body))
+        return fail(c, SBSB200_ERR_INVALID, "not a tetrahedral body");
+    for (int64_t i = 0; i < n; ++i)
+        if (vertices[i] >= static_cast<uint64_t>(c->scene.bodies[static_cast<size_t>(body)].n_vertices))
+            return fail(c, SBSB200_ERR_INVALID, "vertex index out of range");
+    if (c->world > 1 && !c->engine->peers_connected())
+        return fail(c, SBSB200_ERR_STATE, "partitioned scene: connect the peers' mailboxes before stepping");
+    if (!(dt > 0.) || substeps <= 0 || iterations < 0 ||
+        (detect_mode != SBSB200_DETECT_PER_FRAME && detect_mode != SBSB200_DETECT_PER_SUBSTEP))
+        return fail(c, SBSB200_ERR_INVALID, "bad step arguments");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->step_host_vertices_f32(*c, body, n, vertices, x_in, v_in, dt, substeps, iterations, detect_mode, x_out,
+                                          v_out);
+        return SBSB200_OK;
+    });
+}
+
+int64_t sbsb200_count_non_finite(sbsb200_ctx* c)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "count_non_finite before finalize");
+    int64_t n    = 0;
+    int const rc = guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        n = c->engine->count_non_finite(*c);
+        return SBSB200_OK;
+    });
+    return rc < 0 ? rc : n;
+}
 
 int64_t sbsb200_debug_read_trace(sbsb200_ctx* c, int64_t* out, int64_t cap)
 {

@@ -474,10 +474,10 @@ k_unpack_state(DeviceScene<R> s, int64_t first, int64_t n, H const* __restrict__
 
 // the same for a handful of vertices (dragging a picked vertex between frames): x = xi = xn <- x[i] and,
 // when given, v <- v[i] for the listed vertices of one body; a null v leaves the velocity alone
-template <typename R>
+template <typename R, typename H>
 __global__ void __launch_bounds__(256)
 k_scatter_state(DeviceScene<R> s, int64_t first, int64_t n, uint32_t const* __restrict__ which,
-                double const* __restrict__ x, double const* __restrict__ v)
+                H const* __restrict__ x, H const* __restrict__ v)
 {
     int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i >= n)
@@ -491,6 +491,32 @@ k_scatter_state(DeviceScene<R> s, int64_t first, int64_t n, uint32_t const* __re
     st4(&s.prev[at], Real4<R>{p.x, p.y, p.z, R(0)});
     if (v)
         st4(&s.vel[at], Real4<R>{R(v[3 * i]), R(v[3 * i + 1]), R(v[3 * i + 2]), R(0)});
+}
+
+// ... and back: x and v of the listed vertices (sbsb200_step_host_vertices_f32)
+template <typename R, typename H>
+__global__ void __launch_bounds__(256)
+k_gather_state(DeviceScene<R> s, int64_t first, int64_t n, uint32_t const* __restrict__ which, H* __restrict__ x,
+               H* __restrict__ v)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    int64_t const at = first + which[i];
+    if (x)
+    {
+        Real4<R> const p = ld4(&s.prev[at]);
+        x[3 * i]         = H(p.x);
+        x[3 * i + 1]     = H(p.y);
+        x[3 * i + 2]     = H(p.z);
+    }
+    if (v)
+    {
+        Real4<R> const q = ld4(&s.vel[at]);
+        v[3 * i]         = H(q.x);
+        v[3 * i + 1]     = H(q.y);
+        v[3 * i + 2]     = H(q.z);
+    }
 }
 
 // particle_t::mass() of a handful of vertices (sbsb200_set_masses): the inverse mass rides in pos[].w
@@ -525,6 +551,23 @@ k_pack_state(DeviceScene<R> s, int64_t first, int64_t n, H* __restrict__ x, H* _
         v[3 * i + 1]     = H(q.y);
         v[3 * i + 2]     = H(q.z);
     }
+}
+
+// validation aid (sbsb200_count_non_finite): vertices whose committed position or velocity is not finite
+template <typename R>
+__global__ void __launch_bounds__(256) k_count_non_finite(DeviceScene<R> s, unsigned long long* __restrict__ count)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    bool bad        = false;
+    if (i < s.n_vertices)
+    {
+        Real4<R> const p = ld4(&s.prev[i]);
+        Real4<R> const v = ld4(&s.vel[i]);
+        bad = !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(v.x) && isfinite(v.y) && isfinite(v.z));
+    }
+    unsigned const n = __popc(__ballot_sync(0xffffffffu, bad));
+    if ((threadIdx.x & 31) == 0 && n)
+        atomicAdd(count, static_cast<unsigned long long>(n));
 }
 
 // sdf_model_t::evaluate at arbitrary points (sbsb200_eval_sdf): out = (distance, gradient) per point

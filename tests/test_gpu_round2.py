@@ -185,3 +185,42 @@ def test_resting_config3_golden(sbs, scenes, precision, schedule):
     xg, _ = sim.download(ids[0])
     xr, _ = ref.download(0)
     assert np.abs(xg - xr).max() <= TOL[precision] * scene.bbox_diagonal()
+
+
+def test_host_step_of_listed_vertices(sbs, scenes):
+    """sbsb200_step_host_vertices_f32 with all vertices listed equals sbsb200_step_host_f32; with a subset listed the
+    others keep their device state."""
+    scene = scenes.config1(W=5, H=4, D=7)
+    n = scene.items[0].x0.shape[0]
+    x0 = scene.items[0].x.astype(np.float32)
+    v0 = np.zeros_like(x0)
+    a = sbs.Simulation(0, 32)
+    ida = scene.instantiate(a)
+    xa, va = np.empty_like(x0), np.empty_like(x0)
+    a.step_host_f32(ida[0], x0, v0, scene.dt, 2, 3, False, xa, va)
+    b = sbs.Simulation(0, 32)
+    idb = scene.instantiate(b)
+    perm = np.ascontiguousarray(np.random.default_rng(3).permutation(n), np.uint32)
+    xb, vb = np.empty_like(x0), np.empty_like(x0)
+    b.step_host_vertices_f32(idb[0], perm, np.ascontiguousarray(x0[perm]), np.ascontiguousarray(v0[perm]), scene.dt, 2, 3,
+                             False, xb, vb)
+    assert np.array_equal(xb, xa[perm]) and np.array_equal(vb, va[perm])
+    few = np.ascontiguousarray(perm[:7])
+    xf, vf = np.empty((7, 3), np.float32), np.empty((7, 3), np.float32)
+    b.step_host_vertices_f32(idb[0], few, None, None, scene.dt, 2, 3, False, xf, vf)     # nothing uploaded: plain step
+    a.step(scene.dt, 2, 3)
+    x2, v2 = a.download(ida[0])
+    assert np.array_equal(xf, x2[few].astype(np.float32)) and np.array_equal(vf, v2[few].astype(np.float32))
+
+
+def test_non_finite_check(sbs, scenes):
+    """sbsb200_count_non_finite: zero on a healthy scene, the number of poisoned vertices after NaNs were uploaded."""
+    scene = scenes.config1(W=4, H=4, D=6)
+    sim = sbs.Simulation(0, 32)
+    ids = scene.instantiate(sim)
+    sim.step(scene.dt, 2, 2)
+    assert sim.count_non_finite() == 0
+    x = scene.items[0].x.copy()
+    x[[3, 17, 40]] = np.nan
+    sim.upload(ids[0], x)
+    assert sim.count_non_finite() == 3

@@ -67,3 +67,38 @@ def test_stepping_before_the_peers_are_connected_is_an_error(sbs, scenes):
     scene.instantiate(sim, partition=(0, 2))
     with pytest.raises(sbs.SbsError):
         sim.step(scene.dt, 1, 1)
+
+
+@pytest.mark.skipif(not _two_gpus(), reason="needs two GPUs")
+def test_owned_vertices_round_trip_through_the_host(sbs, scenes):
+    """sbsb200_step_host_vertices_f32 on the ranks of a decomposed body: every rank uploads and downloads only the
+    vertices it owns; two frames that way equal two frames with the state left on the devices."""
+    scene = scenes.config1(W=9, H=9, D=41)
+    ref = run_decomposed(sbs, scene, 32, 2, 2, devices=[0, 1])
+    sims = []
+    for r in range(2):
+        sim = sbs.Simulation(r, 32, schedule=sbs.SCHED_PERSISTENT)
+        sims.append((sim, scene.instantiate(sim, partition=(r, 2))))
+    sims[0][0].connect_peer_context(1, sims[1][0])
+    sims[1][0].connect_peer_context(0, sims[0][0])
+    ranks = sims[0][0].vertex_ranks(sims[0][1][0])
+    owned = [np.ascontiguousarray(np.nonzero(ranks == r)[0], np.uint32) for r in range(2)]
+    x = [scene.items[0].x.astype(np.float32)[o] for o in owned]
+    v = [np.zeros_like(a) for a in x]
+    import threading
+    for _ in range(2):
+        out = [(np.empty_like(x[r]), np.empty_like(v[r])) for r in range(2)]
+        # the call blocks until the rank's frame is done, and the ranks wait for each other: one host thread per rank
+        ts = [threading.Thread(target=lambda r=r: sims[r][0].step_host_vertices_f32(
+            sims[r][1][0], owned[r], x[r], v[r], scene.dt, scene.substeps, scene.iterations, False, out[r][0], out[r][1]))
+            for r in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        x = [o[0] for o in out]
+        v = [o[1] for o in out]
+    for r in range(2):
+        xr, vr = ref[r][0].download(ref[r][1][0])
+        assert np.array_equal(x[r], xr[owned[r]].astype(np.float32))
+        assert np.array_equal(v[r], vr[owned[r]].astype(np.float32))
