@@ -271,10 +271,12 @@ class Bench:
         import torch
         sim, scene = self.sim, self.scene
         S, K = scene.substeps, scene.iterations
-        b0 = scene.tet_bodies()[0]
-        body = scene.items[b0]
-        x0 = body.x.astype(np.float32)
-        v0 = (body.v if body.v is not None else np.zeros_like(body.x)).astype(np.float32)
+        bodies = scene.tet_bodies()
+        b0 = bodies[0]
+        x0 = np.concatenate([scene.items[b].x for b in bodies]).astype(np.float32)
+        v0 = np.concatenate([scene.items[b].v if scene.items[b].v is not None else np.zeros_like(scene.items[b].x)
+                             for b in bodies]).astype(np.float32)
+        all_bodies = len(bodies) > 1           # an ensemble crosses PCIe in one copy each way (SBSB200_ALL_BODIES)
         owned = None
         if self.decomposed:
             owned = np.ascontiguousarray(np.nonzero(sim.vertex_ranks(self.ids[b0]) == self.env["rank"])[0], np.uint32)
@@ -288,7 +290,8 @@ class Bench:
 
         def frame(xin, vin, xo, vo):
             if owned is None:
-                sim.step_host_f32(self.ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
+                sim.step_host_f32(-1 if all_bodies else self.ids[b0], xin, vin, scene.dt, S, K, scene.detect_every_substep,
+                                  xo, vo)
             else:
                 sim.step_host_vertices_f32(self.ids[b0], owned, xin, vin, scene.dt, S, K, scene.detect_every_substep, xo, vo)
 
@@ -309,7 +312,7 @@ class Bench:
                 "d2h_bytes_per_step": int(2 * nV * 12), "contacts_last_detection": sim.contact_count(),
                 "timing": "wall clock around sbsb200_step_host%s_f32 (float host buffers), max over ranks"
                           % ("_vertices" if owned is not None else ""),
-                "bodies_round_tripped": 1, "vertices_round_tripped_this_rank": int(nV)}
+                "bodies_round_tripped": len(bodies), "vertices_round_tripped_this_rank": int(nV)}
 
     def roofline(self, res, peak, peaks_found, share=1):
         """Algorithmic bytes / CUDA-event time, per GPU.  share: ranks one body is cut over."""
@@ -479,6 +482,14 @@ def main():
                                "ms_per_step": r4["ms_per_step"], "value": tets4 * S * K / (r4["ms_per_step"] * 1e-3),
                                "unit": UNIT, "gpu_launches": int(r4["launches"]), "contacts": r4["contacts"],
                                "roofline": b.roofline(r4, peak, bool(peaks))}
+            if not args.no_e2e:
+                r = b.end_to_end(3)
+                sub["ensemble"]["e2e"] = {"value": tets4 * S * K * r["steps"] / r["seconds"], "unit": UNIT,
+                                          "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                                          "d2h_bytes_per_step": r["d2h_bytes_per_step"], "steps": r["steps"],
+                                          "timing": r["timing"], "bodies_round_tripped_per_rank": r["bodies_round_tripped"],
+                                          "note": "every rank round-trips x, v (float) of all its bodies in one copy each "
+                                                  "way (SBSB200_ALL_BODIES; bytes are rank 0's)"}
             b.close()
         except Exception as exc:
             sub["ensemble"] = {"error": repr(exc)}

@@ -267,7 +267,10 @@ int sbsb200_step_host(sbsb200_ctx* ctx, int body, const double* x_in, const doub
                       double* v_out);
 
 /* The same with float host buffers: half the bytes over PCIe when the caller keeps its particles in single
- * precision (a renderer-side mirror); the device state has the context's precision either way. */
+ * precision (a renderer-side mirror); the device state has the context's precision either way.
+ * body = SBSB200_ALL_BODIES: every tetrahedral body at once, x / v concatenated in body order (an ensemble of
+ * bodies crosses PCIe in one copy each way instead of one per body). */
+#define SBSB200_ALL_BODIES (-1)
 int sbsb200_step_host_f32(sbsb200_ctx* ctx, int body, const float* x_in, const float* v_in, double dt,
                           int substeps, int iterations, int detect_mode, float* x_out, float* v_out);
 

@@ -989,8 +989,13 @@ struct Engine final : EngineBase
     void step_host_f32(sbsb200_ctx& c, int body, float const* x, float const* v, double dt, int substeps, int iterations,
                        int detect, float* x_out, float* v_out) override
     {
-        HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
-        int64_t const n    = hb.n_vertices;
+        // body < 0: every tet body, concatenated in body order (the global vertex order)
+        int64_t const first = body < 0 ? 0 : c.scene.bodies[static_cast<size_t>(body)].v_offset;
+        int64_t const n     = body < 0 ? d.n_vertices : c.scene.bodies[static_cast<size_t>(body)].n_vertices;
+        struct
+        {
+            int64_t v_offset;
+        } const hb{first};
         ensure_staging(n);
         float* sxf = reinterpret_cast<float*>(stage_x.p);
         float* svf = reinterpret_cast<float*>(stage_v.p);
@@ -2037,7 +2042,7 @@ int sbsb200_step_host_f32(sbsb200_ctx* c, int body, const float* x_in, const flo
         return fail(c, SBSB200_ERR_INVALID, "null argument");
     if (!c->finalized)
         return fail(c, SBSB200_ERR_STATE, "step_host before finalize");
-    if (!is_tet_body(c, body))
+    if (body != SBSB200_ALL_BODIES && !is_tet_body(c, body))
         return fail(c, SBSB200_ERR_INVALID, "not a tetrahedral body");
     if (c->world > 1 && !c->engine->peers_connected())
         return fail(c, SBSB200_ERR_STATE, "partitioned scene: connect the peers' mailboxes before stepping");

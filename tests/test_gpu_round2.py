@@ -224,3 +224,23 @@ def test_non_finite_check(sbs, scenes):
     x[[3, 17, 40]] = np.nan
     sim.upload(ids[0], x)
     assert sim.count_non_finite() == 3
+
+
+def test_host_step_of_all_bodies_at_once(sbs, scenes):
+    """body = SBSB200_ALL_BODIES: x, v of every tet body concatenated in body order, one copy each way."""
+    scene = scenes.config4(n_bodies=6, W=3, H=3, D=5)
+    bodies = scene.tet_bodies()
+    x0 = np.concatenate([scene.items[b].x for b in bodies]).astype(np.float32)
+    v0 = np.zeros_like(x0)
+    a = sbs.Simulation(0, 32)
+    ida = scene.instantiate(a)
+    for b in bodies:
+        a.upload(ida[b], scene.items[b].x.astype(np.float32).astype(np.float64))
+    a.step(scene.dt, 3, 3)
+    b_ = sbs.Simulation(0, 32)
+    scene.instantiate(b_)
+    xo, vo = np.empty_like(x0), np.empty_like(x0)
+    b_.step_host_f32(-1, x0, v0, scene.dt, 3, 3, False, xo, vo)
+    xa = np.concatenate([a.download(ida[b])[0] for b in bodies]).astype(np.float32)
+    va = np.concatenate([a.download(ida[b])[1] for b in bodies]).astype(np.float32)
+    assert np.array_equal(xo, xa) and np.array_equal(vo, va)
