@@ -27,6 +27,7 @@ namespace sbsb200 {
 
 constexpr int kBvhMaxLevels = 32;
 constexpr int kBvhLeafBlock = 256; // leaves fitted per CTA (levels 1..8 in shared memory)
+constexpr int kBvhTopNodes  = 1024; // level-8 nodes a CTA of k_detect_all can hold (262 144 surface vertices)
 
 template <typename R>
 struct BvhView
@@ -42,6 +43,8 @@ struct BvhView
                               // radius < 0: the node spans several bodies and always passes
     int32_t n_levels;         // levels 1 .. n_levels - 1 exist (level 0 = the leaves themselves)
     int32_t n_bodies;         // key prefix of a body that is not handed to the cd system: n_bodies + its index
+    int32_t top_in_detect;    // 1: levels 9.. are built by every CTA of k_detect_all in shared memory out of level 8 (at most
+                              // kBvhTopNodes nodes there): the refit is then free of its serial tail and of atomics
     int64_t level_offset[kBvhMaxLevels];
     int64_t level_count[kBvhMaxLevels];
     R lo[3], inv_extent[3];   // quantisation box of the Morton codes (tree quality only)
@@ -167,7 +170,9 @@ __global__ void __launch_bounds__(kBvhLeafBlock) k_bvh_fit(DeviceScene<R> s, Bvh
         __syncthreads();
         count = here;
     }
-    if (b.n_levels <= 9)
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        *s.contact_count = 0u; // (the detection that follows appends to the list; the previous substep is done with it)
+    if (b.n_levels <= 9 || b.top_in_detect)
         return;
     __threadfence();
     __syncthreads();
@@ -224,8 +229,11 @@ __device__ __forceinline__ bool sphere_reaches_sdf(typename DeviceScene<R>::Sdf 
 // (8 leaves); the levels below only feed the fit.
 constexpr int kBvhFirstLevel = 3;
 
+// s_top: levels 9.. built by this CTA in shared memory (null: they are in b.sphere like the others);
+// s_top_offset[l - 9]: where level l starts in it
 template <typename R>
-__device__ __forceinline__ uint32_t bvh_cull_mask(DeviceScene<R> const& s, BvhView<R> const& b, int64_t leaf)
+__device__ __forceinline__ uint32_t bvh_cull_mask(DeviceScene<R> const& s, BvhView<R> const& b, int64_t leaf,
+                                                  Real4<R> const* s_top, int32_t const* s_top_offset)
 {
     uint32_t mask = 0u;
     bool above    = false; // reached a node that spans several bodies: above the reference's per-body trees
@@ -235,7 +243,8 @@ __device__ __forceinline__ uint32_t bvh_cull_mask(DeviceScene<R> const& s, BvhVi
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             if (l0 + j < b.n_levels)
-                sph[j] = ld4(&b.sphere[b.level_offset[l0 + j] + (leaf >> (l0 + j))]);
+                sph[j] = s_top && l0 + j >= 9 ? s_top[s_top_offset[l0 + j - 9] + (leaf >> (l0 + j))]
+                                              : ld4(&b.sphere[b.level_offset[l0 + j] + (leaf >> (l0 + j))]);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             if (l0 + j < b.n_levels && !above)
@@ -260,6 +269,44 @@ __device__ __forceinline__ double as_real(double, int v) { return static_cast<do
 template <typename R>
 __global__ void __launch_bounds__(256) k_detect_all(DeviceScene<R> s, BvhView<R> b)
 {
+    // Levels 9.. of the sphere tree (at most a few hundred nodes) built here, by every CTA for itself, out of the level-8
+    // nodes the refit wrote: the refit kernel then has no serial tail, and the walk reads these levels from shared memory.
+    extern __shared__ __align__(16) unsigned char top_raw[];
+    __shared__ int32_t s_top_offset[kBvhMaxLevels];
+    Real4<R>* s_top = nullptr;
+    if (b.n > 0 && b.top_in_detect && b.n_levels > 9)
+    {
+        int32_t const n8 = static_cast<int32_t>(b.level_count[8]);
+        Real4<R>* lvl8   = reinterpret_cast<Real4<R>*>(top_raw);          // [n8] level 8, then levels 9.. one after the other
+        uint32_t* body8  = reinterpret_cast<uint32_t*>(lvl8 + 2 * n8 + 32); // body of the first leaf of every node, same layout
+        for (int32_t j = threadIdx.x; j < n8; j += blockDim.x)
+        {
+            lvl8[j]  = ld4(&b.sphere[b.level_offset[8] + j]);
+            body8[j] = static_cast<uint32_t>(b.keys_sorted[static_cast<int64_t>(j) << 8] >> 32);
+        }
+        __syncthreads();
+        int32_t below_at = 0, below_n = n8, at = n8;
+        for (int l = 9; l < b.n_levels; ++l)
+        {
+            int32_t const here = (below_n + 1) / 2;
+            if (threadIdx.x == 0)
+                s_top_offset[l - 9] = at;
+            for (int32_t j = threadIdx.x; j < here; j += blockDim.x)
+            {
+                bool const has_c = 2 * j + 1 < below_n;
+                uint32_t nb;
+                lvl8[at + j]  = fit_pair<R>(lvl8[below_at + 2 * j], body8[below_at + 2 * j], has_c,
+                                           lvl8[below_at + (has_c ? 2 * j + 1 : 2 * j)],
+                                           body8[below_at + (has_c ? 2 * j + 1 : 2 * j)], nb);
+                body8[at + j] = nb;
+            }
+            __syncthreads();
+            below_at = at;
+            below_n  = here;
+            at += here;
+        }
+        s_top = lvl8;
+    }
     int64_t const i   = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     bool const valid  = i < s.n_surface;
     int32_t n_mine    = 0;
@@ -271,7 +318,7 @@ __global__ void __launch_bounds__(256) k_detect_all(DeviceScene<R> s, BvhView<R>
         Real4<R> const q = ld4(&s.surf_pos[i]);
         p                = {q.x, q.y, q.z};
         body             = s.surf_body[i]; // negative: the body was not handed to the cd system
-        culled = b.n > 0 && body >= 0 ? bvh_cull_mask<R>(s, b, b.leaf_of_surface[i]) : 0u; // b.n == 0: no broadphase
+        culled = b.n > 0 && body >= 0 ? bvh_cull_mask<R>(s, b, b.leaf_of_surface[i], s_top, s_top_offset) : 0u; // b.n == 0: no broadphase
         for (int32_t k = 0; body >= 0 && k < s.n_sdf; ++k)
         {
             Vec3<R> g;

@@ -179,6 +179,7 @@ struct Engine final : EngineBase
     static constexpr int kBvhTopologyFrames = 8;
     int bvh_topology_valid_frames = 0; // 0: sort at the next detection
     int bvh_sort_end_bit          = 64; // key bits in use: 32 Morton bits + the bits of the body index
+    size_t bvh_top_bytes          = 0;  // shared memory of k_detect_all for the top of the sphere tree (BvhView::top_in_detect)
     ResidentPlan<R> pp; // resident schedule resources (may be inactive)
     // CUDA-event pairs around the launches of the dominant kernel (persistent schedule: the substep
     // kernel), folded into a running sum when the statistics are read
@@ -491,6 +492,11 @@ struct Engine final : EngineBase
             bvh.level_offset[0] = 0;
             bvh.level_count[0]  = Vs;
             bvh_sphere.alloc(static_cast<size_t>(std::max<int64_t>(offset, 1)));
+            bvh_top_bytes = (2 * static_cast<size_t>(bvh.level_count[8]) + 32) * (sizeof(Real4<R>) + sizeof(uint32_t));
+            bvh.top_in_detect =
+                bvh.n_levels > 9 && bvh.level_count[8] <= kBvhTopNodes && bvh_top_bytes <= 40 * 1024 ? 1 : 0;
+            if (!bvh.top_in_detect)
+                bvh_top_bytes = 0;
             bvh_sort_end_bit = 33;
             while (bvh_sort_end_bit < 64 && (uint64_t{1} << (bvh_sort_end_bit - 32)) < 2 * c.scene.bodies.size())
                 ++bvh_sort_end_bit;
@@ -576,7 +582,8 @@ struct Engine final : EngineBase
             if (!collide)
                 return;
             NvtxRange const range("detection");
-            CK(cudaMemsetAsync(d.contact_count, 0, sizeof(uint32_t), st));
+            if (bvh.n <= 0) // (with the broadphase the refit kernel zeroes the count)
+                CK(cudaMemsetAsync(d.contact_count, 0, sizeof(uint32_t), st));
             if (bvh.n > 0)
             { // broadphase: (once per frame: keys -> sort) -> refit of the bounding spheres; the cull itself
               // is the ancestor walk inside k_detect_all
@@ -595,7 +602,7 @@ struct Engine final : EngineBase
                 k_bvh_fit<R><<<static_cast<unsigned>((n + kBvhLeafBlock - 1) / kBvhLeafBlock), kBvhLeafBlock, 0, st>>>(d, bvh);
                 ++launched;
             }
-            k_detect_all<R><<<gridS, 256, 0, st>>>(d, bvh);
+            k_detect_all<R><<<gridS, 256, bvh_top_bytes, st>>>(d, bvh);
             ++launched;
         };
         if (detect == SBSB200_DETECT_PER_FRAME)
