@@ -1111,6 +1111,8 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
     }
     out.loc_vtx.assign(static_cast<size_t>(out.loc_off.back()), 0);
     std::vector<uint32_t> owner_slot(static_cast<size_t>(V), 0);
+    std::vector<uint32_t> guest_slot(guests.size(), 0); // parallel to guests
+    std::vector<int64_t> first_guest(static_cast<size_t>(Rn) + 1, 0);
     {
         std::vector<int32_t> cur(static_cast<size_t>(Rn), 0);
         for (int64_t v = 0; v < V; ++v)
@@ -1120,18 +1122,250 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
             out.loc_vtx[static_cast<size_t>(out.loc_off[static_cast<size_t>(r)] + cur[static_cast<size_t>(r)]++)] =
                 static_cast<uint32_t>(v);
         }
-        for (auto const& g : guests) // sorted by (region, vertex): the guest slots of a region are in vertex order
-            out.loc_vtx[static_cast<size_t>(out.loc_off[static_cast<size_t>(g.first)] + cur[static_cast<size_t>(g.first)]++)] =
-                g.second;
+        for (size_t g = 0; g < guests.size(); ++g) // sorted by (region, vertex)
+        {
+            guest_slot[g] = static_cast<uint32_t>(cur[static_cast<size_t>(guests[g].first)]++);
+            ++first_guest[static_cast<size_t>(guests[g].first) + 1];
+        }
+        for (int32_t r = 0; r < Rn; ++r)
+            first_guest[static_cast<size_t>(r) + 1] += first_guest[static_cast<size_t>(r)];
     }
-    auto const slot_of = [&](int32_t r, uint32_t v) -> uint32_t {
-        if (plan.vertex_owner[v] == r)
-            return owner_slot[v];
-        auto const it = std::lower_bound(guests.begin(), guests.end(), std::make_pair(r, v));
-        int64_t const first_guest =
-            std::lower_bound(guests.begin(), guests.end(), std::make_pair(r, 0u)) - guests.begin();
-        return static_cast<uint32_t>(out.n_owned[static_cast<size_t>(r)] + ((it - guests.begin()) - first_guest));
+    auto const guest_index = [&](int32_t r, uint32_t v) -> size_t {
+        return static_cast<size_t>(std::lower_bound(guests.begin() + first_guest[static_cast<size_t>(r)],
+                                                    guests.begin() + first_guest[static_cast<size_t>(r) + 1],
+                                                    std::make_pair(r, v)) -
+                                   guests.begin());
     };
+    auto const slot_of = [&](int32_t r, uint32_t v) -> uint32_t {
+        return plan.vertex_owner[v] == r ? owner_slot[v] : guest_slot[guest_index(r, v)];
+    };
+    // ---- slots spread over the shared-memory banks ---------------------------------------------------------
+    // A vertex slot is 16 bytes (fp32): the 32 banks form 8 columns, column = slot % 8, and a warp's 128-bit access
+    // costs as many wavefronts as the fullest column holds distinct slots (4 when 32 lanes spread evenly).  Which
+    // slots one warp instruction touches is static — lane = cluster of the step, instruction = (tet m of the cluster,
+    // corner a) — so the numbering inside the owned range and inside the guest range of every region is chosen
+    // to flatten those histograms (vertex order of a lattice put 12 wavefronts where 4 suffice: clusters of one
+    // colour are two cells apart, so their vertices fell into every other column).  Deterministic: every rank of a
+    // decomposed scene plans the same tables.
+    if (cp.nt > 0 && cp.nt % 32 == 0)
+    {
+        constexpr int kCols = 8;
+        int32_t const nt = cp.nt, rot = cp.rot, warps = nt / 32;
+        std::vector<int32_t> grp_off, grp_mem;      // groups of one region: local vertex numbers (current slots)
+        std::vector<int32_t> v_off, v_grp;          // vertex -> groups
+        std::vector<int32_t> col, hist, members[2][kCols];
+        for (int32_t r = 0; r < Rn; ++r)
+        {
+            int32_t const no = out.n_owned[static_cast<size_t>(r)];
+            int32_t const nl = out.loc_off[static_cast<size_t>(r) + 1] - out.loc_off[static_cast<size_t>(r)];
+            if (nl <= kCols)
+                continue;
+            // (1) the access groups of the region
+            grp_off.assign(1, 0);
+            grp_mem.clear();
+            for (int32_t c = 0; c < C; ++c)
+            {
+                ChunkDesc const* d = &cp.chunks[(static_cast<size_t>(c) * Rn + r) * 2];
+                int32_t const nA = d[0].n[0], nB = d[1].n[0], rounds = (nA + nB + nt - 1) / nt;
+                for (int32_t round = 0; round < rounds; ++round)
+                    for (int32_t w = 0; w < warps; ++w)
+                        for (int m = 0; m < kMaxCluster; ++m)
+                            for (int a = 0; a < 4; ++a)
+                            {
+                                for (int32_t lane = 0; lane < 32; ++lane)
+                                {
+                                    int32_t const tid  = 32 * w + lane;
+                                    int32_t const item = round * nt + (tid >= rot ? tid - rot : tid + nt - rot);
+                                    if (item >= nA + nB)
+                                        continue;
+                                    ChunkDesc const& ch = item < nA ? d[0] : d[1];
+                                    int32_t const ci    = item < nA ? item : item - nA;
+                                    if (ci >= ch.n[m])
+                                        continue;
+                                    int64_t pos = ch.first + ci;
+                                    for (int j = 0; j < m; ++j)
+                                        pos += ch.n[j];
+                                    uint32_t const v = scene.tets[4 * static_cast<size_t>(cp.storage_order[static_cast<size_t>(pos)]) + a];
+                                    grp_mem.push_back(static_cast<int32_t>(slot_of(r, v)));
+                                }
+                                if (static_cast<int32_t>(grp_mem.size()) - grp_off.back() >= 2)
+                                    grp_off.push_back(static_cast<int32_t>(grp_mem.size()));
+                                else
+                                    grp_mem.resize(static_cast<size_t>(grp_off.back()));
+                            }
+            }
+            int32_t const G = static_cast<int32_t>(grp_off.size()) - 1;
+            if (G == 0)
+                continue;
+            v_off.assign(static_cast<size_t>(nl) + 1, 0);
+            for (int32_t v : grp_mem)
+                ++v_off[static_cast<size_t>(v) + 1];
+            for (int32_t v = 0; v < nl; ++v)
+                v_off[static_cast<size_t>(v) + 1] += v_off[static_cast<size_t>(v)];
+            v_grp.assign(grp_mem.size(), 0);
+            {
+                std::vector<int32_t> cur(v_off.begin(), v_off.end() - 1);
+                for (int32_t g = 0; g < G; ++g)
+                    for (int32_t i = grp_off[static_cast<size_t>(g)]; i < grp_off[static_cast<size_t>(g) + 1]; ++i)
+                        v_grp[static_cast<size_t>(cur[static_cast<size_t>(grp_mem[static_cast<size_t>(i)])]++)] = g;
+            }
+            // (2) columns: start from the vertex order, improve by swaps inside the owned / guest range
+            col.assign(static_cast<size_t>(nl), 0);
+            hist.assign(static_cast<size_t>(G) * kCols, 0);
+            for (int32_t v = 0; v < nl; ++v)
+                col[static_cast<size_t>(v)] = v % kCols;
+            for (int32_t g = 0; g < G; ++g)
+                for (int32_t i = grp_off[static_cast<size_t>(g)]; i < grp_off[static_cast<size_t>(g) + 1]; ++i)
+                    ++hist[static_cast<size_t>(g) * kCols + col[static_cast<size_t>(grp_mem[static_cast<size_t>(i)])]];
+            auto const group_cost = [&](int32_t g) { // wavefronts first, sum of squares smooths the plateaus
+                int32_t const* h = &hist[static_cast<size_t>(g) * kCols];
+                int32_t mx = 0, sq = 0;
+                for (int k = 0; k < kCols; ++k)
+                {
+                    mx = std::max(mx, h[k]);
+                    sq += h[k] * h[k];
+                }
+                return 64 * mx + sq;
+            };
+            auto const wavefronts = [&]() {
+                int64_t n = 0;
+                for (int32_t g = 0; g < G; ++g)
+                    n += *std::max_element(&hist[static_cast<size_t>(g) * kCols], &hist[static_cast<size_t>(g) * kCols] + kCols);
+                return n;
+            };
+            for (int32_t g = 0; g < G; ++g)
+                out.bank_wavefronts_ideal += (grp_off[static_cast<size_t>(g) + 1] - grp_off[static_cast<size_t>(g)] + kCols - 1) / kCols;
+            out.bank_wavefronts_before += wavefronts();
+            // cost change of moving v from its column to column k
+            auto const move_delta = [&](int32_t v, int k) {
+                int32_t const from = col[static_cast<size_t>(v)];
+                int32_t d = 0;
+                for (int32_t i = v_off[static_cast<size_t>(v)]; i < v_off[static_cast<size_t>(v) + 1]; ++i)
+                {
+                    int32_t const g = v_grp[static_cast<size_t>(i)];
+                    int32_t* h      = &hist[static_cast<size_t>(g) * kCols];
+                    int32_t const before = group_cost(g);
+                    --h[from];
+                    ++h[k];
+                    d += group_cost(g) - before;
+                    ++h[from];
+                    --h[k];
+                }
+                return d;
+            };
+            auto const move = [&](int32_t v, int k) {
+                int32_t const from = col[static_cast<size_t>(v)];
+                for (int32_t i = v_off[static_cast<size_t>(v)]; i < v_off[static_cast<size_t>(v) + 1]; ++i)
+                {
+                    int32_t* h = &hist[static_cast<size_t>(v_grp[static_cast<size_t>(i)]) * kCols];
+                    --h[from];
+                    ++h[k];
+                }
+                col[static_cast<size_t>(v)] = k;
+            };
+            for (int range = 0; range < 2; ++range)
+                for (int k = 0; k < kCols; ++k)
+                    members[range][k].clear();
+            for (int32_t v = 0; v < nl; ++v)
+                members[v < no ? 0 : 1][col[static_cast<size_t>(v)]].push_back(v);
+            uint64_t rng = 0x9e3779b97f4a7c15ull ^ (static_cast<uint64_t>(r) * 0xbf58476d1ce4e5b9ull);
+            auto const next_random = [&]() {
+                rng ^= rng << 13;
+                rng ^= rng >> 7;
+                rng ^= rng << 17;
+                return rng;
+            };
+            constexpr int kPasses = 6, kCandidates = 6;
+            for (int pass = 0; pass < kPasses; ++pass)
+            {
+                int64_t improved = 0;
+                for (int32_t v = 0; v < nl; ++v)
+                {
+                    if (v_off[static_cast<size_t>(v)] == v_off[static_cast<size_t>(v) + 1])
+                        continue;
+                    int const range = v < no ? 0 : 1, from = col[static_cast<size_t>(v)];
+                    int best_k = -1;
+                    int32_t best_d = 0;
+                    for (int k = 0; k < kCols; ++k)
+                        if (k != from && !members[range][k].empty())
+                        {
+                            int32_t const d = move_delta(v, k);
+                            if (d < best_d)
+                            {
+                                best_d = d;
+                                best_k = k;
+                            }
+                        }
+                    if (best_k < 0)
+                        continue;
+                    // a partner out of column best_k takes v's column: the one that loses least
+                    move(v, best_k);
+                    std::vector<int32_t>& pool = members[range][best_k];
+                    size_t best_u = pool.size();
+                    int32_t best_total = 0;
+                    for (int t = 0; t < kCandidates; ++t)
+                    {
+                        size_t const ui = static_cast<size_t>(next_random() % pool.size());
+                        int32_t const total = best_d + move_delta(pool[ui], from);
+                        if (total < best_total)
+                        {
+                            best_total = total;
+                            best_u     = ui;
+                        }
+                    }
+                    if (best_u == pool.size())
+                    {
+                        move(v, from);
+                        continue;
+                    }
+                    int32_t const u = pool[best_u];
+                    move(u, from);
+                    pool[best_u] = v;
+                    std::vector<int32_t>& mine = members[range][from];
+                    *std::find(mine.begin(), mine.end(), v) = u;
+                    ++improved;
+                }
+                if (improved == 0)
+                    break;
+            }
+            out.bank_wavefronts += wavefronts();
+            // (3) new numbers: the slots of a column in rising order go to its vertices in rising order
+            {
+                std::vector<int32_t> new_slot(static_cast<size_t>(nl), 0);
+                for (int range = 0; range < 2; ++range)
+                {
+                    int32_t const lo = range == 0 ? 0 : no, hi = range == 0 ? no : nl;
+                    std::vector<int32_t> next(kCols, 0);
+                    for (int k = 0; k < kCols; ++k)
+                    {
+                        next[static_cast<size_t>(k)] = lo + ((k - lo) % kCols + kCols) % kCols;
+                        std::sort(members[range][k].begin(), members[range][k].end());
+                    }
+                    for (int k = 0; k < kCols; ++k)
+                        for (int32_t v : members[range][k])
+                        {
+                            new_slot[static_cast<size_t>(v)] = next[static_cast<size_t>(k)];
+                            next[static_cast<size_t>(k)] += kCols;
+                            if (new_slot[static_cast<size_t>(v)] >= hi)
+                            {
+                                out.why_not = "bank spreading lost a slot";
+                                return false;
+                            }
+                        }
+                }
+                for (int32_t i = 0; i < no; ++i) // loc_vtx still holds the owned vertices in vertex order
+                    owner_slot[out.loc_vtx[static_cast<size_t>(out.loc_off[static_cast<size_t>(r)] + i)]] =
+                        static_cast<uint32_t>(new_slot[static_cast<size_t>(i)]);
+                for (int64_t g = first_guest[static_cast<size_t>(r)]; g < first_guest[static_cast<size_t>(r) + 1]; ++g)
+                    guest_slot[static_cast<size_t>(g)] = static_cast<uint32_t>(new_slot[guest_slot[static_cast<size_t>(g)]]);
+            }
+        }
+    }
+    for (int64_t v = 0; v < V; ++v)
+        out.loc_vtx[static_cast<size_t>(out.loc_off[static_cast<size_t>(plan.vertex_owner[static_cast<size_t>(v)])]) +
+                    owner_slot[static_cast<size_t>(v)]] = static_cast<uint32_t>(v);
+    for (size_t g = 0; g < guests.size(); ++g)
+        out.loc_vtx[static_cast<size_t>(out.loc_off[static_cast<size_t>(guests[g].first)]) + guest_slot[g]] = guests[g].second;
     out.tet_slots.assign(4 * static_cast<size_t>(T), 0);
     for (int64_t pos = 0; pos < T; ++pos)
     {

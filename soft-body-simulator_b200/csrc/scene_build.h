@@ -258,6 +258,9 @@ struct ExchangePlan
     // statistics
     int64_t n_pulls[4] = {0, 0, 0, 0}, n_pushes[4] = {0, 0, 0, 0};
     std::vector<int64_t> pulls_by_colour; // [colour], variant: later sweep, no collision steps
+    // shared-memory wavefronts of the vertex accesses of one sweep (one warp instruction = one group of slots):
+    // with slots in vertex order, with the order build_exchange_plan chooses, and the lower bound (8 columns)
+    int64_t bank_wavefronts_before = 0, bank_wavefronts = 0, bank_wavefronts_ideal = 0;
     int32_t quiet_steps = 0;           // colours whose clusters pull nothing in any region (variant: later sweep, no
                                        // collision steps): steps that wait for no other region
     std::string why_not;

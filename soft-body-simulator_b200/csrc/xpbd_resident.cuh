@@ -48,6 +48,11 @@ constexpr uint32_t kBoxIndexMask = kRouteIndexMask;
 constexpr int kRankShift         = kRouteRankShift;
 constexpr int kMaxWorld          = 8;
 constexpr int kPollBudget     = 1 << 24;     // polls of one record before the kernel gives up
+#ifndef SBSB200_POLL_GENERATIONS
+#define SBSB200_POLL_GENERATIONS 3
+#endif
+constexpr int kPollGenerations = SBSB200_POLL_GENERATIONS; // polls of one record in flight (fp32 pulls of a cluster)
+constexpr unsigned kPollGap    = 128;                      // ns between two of them
 
 // true when the wait should be abandoned: budget exhausted (sets the error flag) or another thread
 // already gave up (checked every 1024 polls so that one lost update cannot stall the whole launch)
@@ -408,32 +413,56 @@ __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 con
             if (word[e] & kPullValid)
                 pending |= 1u << e;
         bool const full = pending == 0xfu;
+        // kGen generations of polls are in flight, kPollGap ns apart: a record that lands just after one poll passed
+        // is seen by the next one a fraction of a round trip later instead of a whole round trip later (a round trip
+        // through the L2 costs ~1 300 cycles under the store traffic of a step).
+        constexpr int kGen = Xchg<R>::kWords == 1 ? kPollGenerations : 1;
+        typename Xchg<R>::Raw raw[kGen][4];
+        if (pending)
+        {
+#pragma unroll
+            for (int g2 = 0; g2 < kGen; ++g2)
+            {
+                if (g2 > 0)
+                    __nanosleep(kPollGap);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (pending >> e & 1u)
+                        raw[g2][e] = Xchg<R>::fetch(a.box, (word[e] >> 24 & 0xfu) * nx + mine, a.world > 1);
+            }
+        }
         while (pending)
         {
-            typename Xchg<R>::Raw raw[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (pending >> e & 1u)
-                    raw[e] = Xchg<R>::fetch(a.box, (word[e] >> 24 & 0xfu) * nx + mine, a.world > 1);
+            for (int g2 = 0; g2 < kGen; ++g2)
+            {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (pending >> e & 1u)
-                {
-                    uint32_t const d = word[e] >> 16 & 0xffu;
-                    R x, y, z;
-                    if (Xchg<R>::decode(raw[e], d == kPullPredict ? a.base : tag - d, x, y, z))
+                for (int e = 0; e < 4; ++e)
+                    if (pending >> e & 1u)
                     {
-                        Real4<R>* dst = &sx[word[e] & 0xffffu];
-                        dst->x        = x;
-                        dst->y        = y;
-                        dst->z        = z;
-                        pending &= ~(1u << e);
+                        uint32_t const d = word[e] >> 16 & 0xffu;
+                        R x, y, z;
+                        if (Xchg<R>::decode(raw[g2][e], d == kPullPredict ? a.base : tag - d, x, y, z))
+                        {
+                            Real4<R>* dst = &sx[word[e] & 0xffffu];
+                            dst->x        = x;
+                            dst->y        = y;
+                            dst->z        = z;
+                            pending &= ~(1u << e);
+                        }
                     }
+                if (polls == 0)
+                    stamp(2);
+                if (!pending || poll_expired(a.error, ++polls))
+                {
+                    pending = 0;
+                    break;
                 }
-            if (polls == 0)
-                stamp(2);
-            if (pending && poll_expired(a.error, ++polls))
-                break;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (pending >> e & 1u)
+                        raw[g2][e] = Xchg<R>::fetch(a.box, (word[e] >> 24 & 0xfu) * nx + mine, a.world > 1);
+            }
         }
         if (!full || ++g >= groups)
             break;

@@ -408,8 +408,11 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
         stats[7] = xp.quiet_steps;
         stats[8] = xp.max_local;
         stats[9] = cp.nt;
-        for (int32_t c = 0; c < C && c < 16; ++c)
+        for (int32_t c = 0; c < C && c < 13; ++c)
             stats[10 + c] = xp.pulls_by_colour[static_cast<size_t>(c)];
+        stats[23] = xp.bank_wavefronts_before;
+        stats[24] = xp.bank_wavefronts;
+        stats[25] = xp.bank_wavefronts_ideal;
     }
     return 0;
 }
