@@ -1147,7 +1147,11 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
     // to flatten those histograms (vertex order of a lattice put 12 wavefronts where 4 suffice: clusters of one
     // colour are two cells apart, so their vertices fell into every other column).  Deterministic: every rank of a
     // decomposed scene plans the same tables.
+#ifndef SBSB200_NO_BANK_SPREAD
     if (cp.nt > 0 && cp.nt % 32 == 0)
+#else
+    if (false)
+#endif
     {
         constexpr int kCols = 8;
         int32_t const nt = cp.nt, rot = cp.rot, warps = nt / 32;
@@ -1217,16 +1221,6 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
             for (int32_t g = 0; g < G; ++g)
                 for (int32_t i = grp_off[static_cast<size_t>(g)]; i < grp_off[static_cast<size_t>(g) + 1]; ++i)
                     ++hist[static_cast<size_t>(g) * kCols + col[static_cast<size_t>(grp_mem[static_cast<size_t>(i)])]];
-            auto const group_cost = [&](int32_t g) { // wavefronts first, sum of squares smooths the plateaus
-                int32_t const* h = &hist[static_cast<size_t>(g) * kCols];
-                int32_t mx = 0, sq = 0;
-                for (int k = 0; k < kCols; ++k)
-                {
-                    mx = std::max(mx, h[k]);
-                    sq += h[k] * h[k];
-                }
-                return 64 * mx + sq;
-            };
             auto const wavefronts = [&]() {
                 int64_t n = 0;
                 for (int32_t g = 0; g < G; ++g)
@@ -1236,22 +1230,18 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
             for (int32_t g = 0; g < G; ++g)
                 out.bank_wavefronts_ideal += (grp_off[static_cast<size_t>(g) + 1] - grp_off[static_cast<size_t>(g)] + kCols - 1) / kCols;
             out.bank_wavefronts_before += wavefronts();
-            // cost change of moving v from its column to column k
-            auto const move_delta = [&](int32_t v, int k) {
-                int32_t const from = col[static_cast<size_t>(v)];
-                int32_t d = 0;
+            // The search minimises the sum over the groups of the squared column counts (flat histograms minimise it, and
+            // the change of a move is linear in the counts): moving v from column a to column k changes it by
+            // 2 * (S[k] - S[a] + deg(v)) with S = sum of the histograms of v's groups.
+            auto const column_sums = [&](int32_t v, int32_t* S) {
+                for (int k = 0; k < kCols; ++k)
+                    S[k] = 0;
                 for (int32_t i = v_off[static_cast<size_t>(v)]; i < v_off[static_cast<size_t>(v) + 1]; ++i)
                 {
-                    int32_t const g = v_grp[static_cast<size_t>(i)];
-                    int32_t* h      = &hist[static_cast<size_t>(g) * kCols];
-                    int32_t const before = group_cost(g);
-                    --h[from];
-                    ++h[k];
-                    d += group_cost(g) - before;
-                    ++h[from];
-                    --h[k];
+                    int32_t const* h = &hist[static_cast<size_t>(v_grp[static_cast<size_t>(i)]) * kCols];
+                    for (int k = 0; k < kCols; ++k)
+                        S[k] += h[k];
                 }
-                return d;
             };
             auto const move = [&](int32_t v, int k) {
                 int32_t const from = col[static_cast<size_t>(v)];
@@ -1266,8 +1256,13 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
             for (int range = 0; range < 2; ++range)
                 for (int k = 0; k < kCols; ++k)
                     members[range][k].clear();
+            std::vector<int32_t> at_in_pool(static_cast<size_t>(nl), 0);
             for (int32_t v = 0; v < nl; ++v)
-                members[v < no ? 0 : 1][col[static_cast<size_t>(v)]].push_back(v);
+            {
+                std::vector<int32_t>& pool = members[v < no ? 0 : 1][col[static_cast<size_t>(v)]];
+                at_in_pool[static_cast<size_t>(v)] = static_cast<int32_t>(pool.size());
+                pool.push_back(v);
+            }
             uint64_t rng = 0x9e3779b97f4a7c15ull ^ (static_cast<uint64_t>(r) * 0xbf58476d1ce4e5b9ull);
             auto const next_random = [&]() {
                 rng ^= rng << 13;
@@ -1275,26 +1270,25 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
                 rng ^= rng << 17;
                 return rng;
             };
-            constexpr int kPasses = 6, kCandidates = 6;
+            constexpr int kPasses = 5, kCandidates = 4;
             for (int pass = 0; pass < kPasses; ++pass)
             {
                 int64_t improved = 0;
                 for (int32_t v = 0; v < nl; ++v)
                 {
-                    if (v_off[static_cast<size_t>(v)] == v_off[static_cast<size_t>(v) + 1])
+                    int32_t const deg = v_off[static_cast<size_t>(v) + 1] - v_off[static_cast<size_t>(v)];
+                    if (deg == 0)
                         continue;
                     int const range = v < no ? 0 : 1, from = col[static_cast<size_t>(v)];
+                    int32_t S[kCols];
+                    column_sums(v, S);
                     int best_k = -1;
                     int32_t best_d = 0;
                     for (int k = 0; k < kCols; ++k)
-                        if (k != from && !members[range][k].empty())
+                        if (k != from && !members[range][k].empty() && S[k] - S[from] + deg < best_d)
                         {
-                            int32_t const d = move_delta(v, k);
-                            if (d < best_d)
-                            {
-                                best_d = d;
-                                best_k = k;
-                            }
+                            best_d = S[k] - S[from] + deg;
+                            best_k = k;
                         }
                     if (best_k < 0)
                         continue;
@@ -1306,7 +1300,11 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
                     for (int t = 0; t < kCandidates; ++t)
                     {
                         size_t const ui = static_cast<size_t>(next_random() % pool.size());
-                        int32_t const total = best_d + move_delta(pool[ui], from);
+                        int32_t const u = pool[ui];
+                        int32_t Su[kCols];
+                        column_sums(u, Su);
+                        int32_t const total =
+                            best_d + Su[from] - Su[best_k] + (v_off[static_cast<size_t>(u) + 1] - v_off[static_cast<size_t>(u)]);
                         if (total < best_total)
                         {
                             best_total = total;
@@ -1320,12 +1318,14 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
                     }
                     int32_t const u = pool[best_u];
                     move(u, from);
-                    pool[best_u] = v;
-                    std::vector<int32_t>& mine = members[range][from];
-                    *std::find(mine.begin(), mine.end(), v) = u;
+                    pool[best_u]                       = v;
+                    std::vector<int32_t>& mine         = members[range][from];
+                    mine[static_cast<size_t>(at_in_pool[static_cast<size_t>(v)])] = u;
+                    std::swap(at_in_pool[static_cast<size_t>(v)], at_in_pool[static_cast<size_t>(u)]);
+                    at_in_pool[static_cast<size_t>(v)] = static_cast<int32_t>(best_u);
                     ++improved;
                 }
-                if (improved == 0)
+                if (improved * 200 < nl)
                     break;
             }
             out.bank_wavefronts += wavefronts();
@@ -1538,6 +1538,11 @@ bool build_exchange_plan(HostScene const& scene, ClusterPlan const& cp, RegionPl
     }
     for (int32_t c = 0; c < C; ++c)
         out.quiet_steps += !colour_pulls[static_cast<size_t>(c)];
+    for (int64_t xq = 0; xq < nx; ++xq)
+    { // later sweep, collision steps present: how many records a cluster pulls / pushes in its step
+        ++out.pull_hist[std::min<size_t>(16, pulls[3 * static_cast<size_t>(nx) + xq].size())];
+        ++out.push_hist[std::min<size_t>(16, pushes[1 * static_cast<size_t>(nx) + xq].size() / 2)];
+    }
     size_t const E = static_cast<size_t>(out.entries);
     out.pull.assign(4 * E * static_cast<size_t>(nx), 0u);
     out.push.assign(4 * 2 * E * static_cast<size_t>(nx), 0u);

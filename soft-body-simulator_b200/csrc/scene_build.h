@@ -261,6 +261,8 @@ struct ExchangePlan
     // shared-memory wavefronts of the vertex accesses of one sweep (one warp instruction = one group of slots):
     // with slots in vertex order, with the order build_exchange_plan chooses, and the lower bound (8 columns)
     int64_t bank_wavefronts_before = 0, bank_wavefronts = 0, bank_wavefronts_ideal = 0;
+    int64_t pull_hist[17] = {}, push_hist[17] = {}; // exchange clusters by records pulled / pushed per step (variant: later
+                                                    // sweep / not the last sweep, collision steps present)
     int32_t quiet_steps = 0;           // colours whose clusters pull nothing in any region (variant: later sweep, no
                                        // collision steps): steps that wait for no other region
     std::string why_not;

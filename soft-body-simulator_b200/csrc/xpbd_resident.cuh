@@ -48,11 +48,16 @@ constexpr uint32_t kBoxIndexMask = kRouteIndexMask;
 constexpr int kRankShift         = kRouteRankShift;
 constexpr int kMaxWorld          = 8;
 constexpr int kPollBudget     = 1 << 24;     // polls of one record before the kernel gives up
+// Polls of one record in flight (fp32 pulls of a cluster), kPollGap ns apart.  Measured on config 3, one box, ms per frame
+// (profiles/r02_ab_polls.txt): 1 generation 4.00, 3 generations 4.32 (gap 128 ns) / 4.22 (gap 40 ns), 1 generation with
+// 300 ns of sleep between rounds 4.12, only the last record of a group polled while waiting 4.44 (5.43 with 3 generations).
+// On another box 1 and 3 generations both gave 4.00: more polls in flight never help and often hurt (every poll is a sector
+// request to the L2 slice that also has to take the neighbours' pushes), fewer polls see the record later.
 #ifndef SBSB200_POLL_GENERATIONS
-#define SBSB200_POLL_GENERATIONS 3
+#define SBSB200_POLL_GENERATIONS 1
 #endif
-constexpr int kPollGenerations = SBSB200_POLL_GENERATIONS; // polls of one record in flight (fp32 pulls of a cluster)
-constexpr unsigned kPollGap    = 128;                      // ns between two of them
+constexpr int kPollGenerations = SBSB200_POLL_GENERATIONS;
+constexpr unsigned kPollGap    = 128;
 
 // true when the wait should be abandoned: budget exhausted (sets the error flag) or another thread
 // already gave up (checked every 1024 polls so that one lost update cannot stall the whole launch)
@@ -413,13 +418,10 @@ __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 con
             if (word[e] & kPullValid)
                 pending |= 1u << e;
         bool const full = pending == 0xfu;
-        // kGen generations of polls are in flight, kPollGap ns apart: a record that lands just after one poll passed
-        // is seen by the next one a fraction of a round trip later instead of a whole round trip later (a round trip
-        // through the L2 costs ~1 300 cycles under the store traffic of a step).
+        // all polls of a group are in flight together (kPollGenerations of each, see there)
         constexpr int kGen = Xchg<R>::kWords == 1 ? kPollGenerations : 1;
-        typename Xchg<R>::Raw raw[kGen][4];
-        if (pending)
-        {
+        auto const poll_until_there = [&](uint32_t mask) {
+            typename Xchg<R>::Raw raw[kGen][4];
 #pragma unroll
             for (int g2 = 0; g2 < kGen; ++g2)
             {
@@ -427,43 +429,45 @@ __device__ __forceinline__ void pull_cluster(ResidentArgs<R> const& a, uint4 con
                     __nanosleep(kPollGap);
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (pending >> e & 1u)
+                    if (mask >> e & 1u)
                         raw[g2][e] = Xchg<R>::fetch(a.box, (word[e] >> 24 & 0xfu) * nx + mine, a.world > 1);
             }
-        }
-        while (pending)
-        {
-#pragma unroll
-            for (int g2 = 0; g2 < kGen; ++g2)
+            while (mask)
             {
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (pending >> e & 1u)
-                    {
-                        uint32_t const d = word[e] >> 16 & 0xffu;
-                        R x, y, z;
-                        if (Xchg<R>::decode(raw[g2][e], d == kPullPredict ? a.base : tag - d, x, y, z))
-                        {
-                            Real4<R>* dst = &sx[word[e] & 0xffffu];
-                            dst->x        = x;
-                            dst->y        = y;
-                            dst->z        = z;
-                            pending &= ~(1u << e);
-                        }
-                    }
-                if (polls == 0)
-                    stamp(2);
-                if (!pending || poll_expired(a.error, ++polls))
+                for (int g2 = 0; g2 < kGen; ++g2)
                 {
-                    pending = 0;
-                    break;
-                }
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (pending >> e & 1u)
-                        raw[g2][e] = Xchg<R>::fetch(a.box, (word[e] >> 24 & 0xfu) * nx + mine, a.world > 1);
+                    for (int e = 0; e < 4; ++e)
+                        if (mask >> e & 1u)
+                        {
+                            uint32_t const d = word[e] >> 16 & 0xffu;
+                            R x, y, z;
+                            if (Xchg<R>::decode(raw[g2][e], d == kPullPredict ? a.base : tag - d, x, y, z))
+                            {
+                                Real4<R>* dst = &sx[word[e] & 0xffffu];
+                                dst->x        = x;
+                                dst->y        = y;
+                                dst->z        = z;
+                                mask &= ~(1u << e);
+                            }
+                        }
+                    if (polls == 0)
+                        stamp(2);
+                    if (!mask || poll_expired(a.error, ++polls))
+                    {
+                        mask = 0;
+                        break;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (mask >> e & 1u)
+                            raw[g2][e] = Xchg<R>::fetch(a.box, (word[e] >> 24 & 0xfu) * nx + mine, a.world > 1);
+                }
             }
-        }
+        };
+        if (pending)
+            poll_until_there(pending);
         if (!full || ++g >= groups)
             break;
         w = __ldg(&pull_variant[static_cast<int64_t>(g) * a.n_xclusters + xq]);

@@ -3,6 +3,8 @@
 // the region plan can be tested on a CPU-only box.
 #include "../soft-body-simulator_b200/csrc/scene_build.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 using namespace sbsb200;
@@ -410,6 +412,14 @@ extern "C" int hs_exchange_emulate(int64_t nV, int64_t nT, const uint32_t* tets,
         stats[9] = cp.nt;
         for (int32_t c = 0; c < C && c < 13; ++c)
             stats[10 + c] = xp.pulls_by_colour[static_cast<size_t>(c)];
+        if (getenv("HS_PRINT_HIST"))
+        {
+            printf("pulls per cluster:");
+            for (int i = 0; i <= 16; ++i) printf(" %lld", static_cast<long long>(xp.pull_hist[i]));
+            printf("\npushes per cluster:");
+            for (int i = 0; i <= 16; ++i) printf(" %lld", static_cast<long long>(xp.push_hist[i]));
+            printf("\n");
+        }
         stats[23] = xp.bank_wavefronts_before;
         stats[24] = xp.bank_wavefronts;
         stats[25] = xp.bank_wavefronts_ideal;
