@@ -191,6 +191,16 @@ int sbsb200_finalize(sbsb200_ctx* ctx);
 /* Number of elastic constraints (green + distance), i.e. simulation_t::constraints().size(). */
 int64_t sbsb200_constraint_count(const sbsb200_ctx* ctx);
 
+/* simulation_t::remove_constraint (src/physics/simulation.cpp:34-39) for tetrahedron (Green) constraints, without
+ * re-planning the scene: `constraints` are insertion indices as counted at finalize (they do NOT shift when other
+ * constraints go, unlike the reference's swap-with-last positions; the C++ facade keeps the correspondence).  The
+ * removed tets keep their place in the schedule with rest volume zero, so the projection leaves them alone
+ * (gradient guard, green_constraint.cpp:67, :130-131); colours, regions and mailboxes stay as they are, the mesh
+ * boundary too (the reference does not touch the mesh either).  sbsb200_constraint_count and
+ * sbsb200_get_constraint_order afterwards describe the remaining constraints.  Distance constraints and constraint
+ * insertion need a new scene (SBSB200_ERR_INVALID here).  One small copy, one kernel, one synchronisation. */
+int sbsb200_remove_constraints(sbsb200_ctx* ctx, int64_t n, const uint32_t* constraints);
+
 /* The serial Gauss-Seidel order equivalent to the GPU schedule: order[i] = insertion index
  * (position in simulation_t::constraints_, src/physics/simulation.cpp:29-32) of the i-th
  * projected constraint.  Feeding this permutation to the reference/oracle reproduces the

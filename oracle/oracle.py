@@ -53,6 +53,7 @@ def lib():
         L.orc_set_body_collideable.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_constraint_count.argtypes = [C.c_void_p]
         L.orc_set_constraint_order.argtypes = [C.c_void_p, _u32p, C.c_int]
+        L.orc_remove_constraint.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_upload.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
         L.orc_download.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
         L.orc_set_mass.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
@@ -267,6 +268,11 @@ class World:
 
     def constraint_count(self):
         return lib().orc_constraint_count(self._h)
+
+    def remove_constraint(self, index):
+        """simulation_t::remove_constraint(index) (simulation.cpp:34-39): swapped with the last one and dropped."""
+        if lib().orc_remove_constraint(self._h, int(index)):
+            raise RuntimeError("orc_remove_constraint failed")
 
     def set_constraint_order(self, order):
         order = _u32(order)

@@ -56,6 +56,7 @@ def lib():
         L.ref_set_body_collideable.argtypes = [vp, C.c_int, C.c_int]
         L.ref_constraint_count.argtypes = [vp]
         L.ref_set_constraint_order.argtypes = [vp, _u32p, C.c_int]
+        L.ref_remove_constraint.argtypes = [vp, C.c_uint32]
         L.ref_upload.argtypes = [vp, C.c_int, _dp, _dp]
         L.ref_download.argtypes = [vp, C.c_int, _dp, _dp]
         L.ref_set_mass.argtypes = [vp, C.c_int, C.c_int, C.c_double]
@@ -149,6 +150,11 @@ class World:
 
     def constraint_count(self):
         return lib().ref_constraint_count(self._h)
+
+    def remove_constraint(self, index):
+        """simulation_t::remove_constraint(index): the reference swaps it with the last one and drops it."""
+        if lib().ref_remove_constraint(self._h, int(index)):
+            raise RuntimeError("ref_remove_constraint failed")
 
     def set_constraint_order(self, order):
         order = np.ascontiguousarray(order, dtype=np.uint32)

@@ -273,6 +273,16 @@ int ref_set_body_collideable(void* h, int body, int flag)
 
 int ref_constraint_count(void* h) { return static_cast<int>(static_cast<world*>(h)->sim.constraints().size()); }
 
+// simulation_t::remove_constraint (simulation.cpp:34-39), the reference's own code: swap with the last, drop it
+int ref_remove_constraint(void* h, uint32_t index)
+{
+    world* w = static_cast<world*>(h);
+    if (index >= w->sim.constraints().size())
+        return -1;
+    w->sim.remove_constraint(index);
+    return 0;
+}
+
 // the reference run "with constraints permuted": reorder simulation_t::constraints_
 int ref_set_constraint_order(void* h, const uint32_t* order, int n)
 {

@@ -1320,6 +1320,16 @@ int orc_step(orc_world* w, double dt, int substeps, int iterations, int detect_e
 
 int orc_constraint_count(const orc_world* w) { return w->nc; }
 
+/* simulation_t::remove_constraint (simulation.cpp:34-39): swap with the last constraint, drop it */
+int orc_remove_constraint(orc_world* w, uint32_t index)
+{
+    if (index >= (uint32_t)w->nc)
+        return -1;
+    w->cons[index] = w->cons[w->nc - 1];
+    --w->nc;
+    return 0;
+}
+
 int orc_set_constraint_order(orc_world* w, const uint32_t* order, int n)
 {
     if (n != w->nc)

@@ -115,6 +115,8 @@ int orc_constraint_count(const orc_world* w);
 /* Reorder simulation_t::constraints_ : new_order[i] = insertion index of the constraint
  * that must run i-th ("the reference run with constraints permuted into the same colour
  * order").  Must be a permutation of 0..count-1.  Returns 0 on success. */
+/* simulation_t::remove_constraint (src/physics/simulation.cpp:34-39): swap with the last, drop it */
+int orc_remove_constraint(orc_world* w, uint32_t index);
 int orc_set_constraint_order(orc_world* w, const uint32_t* new_order, int n);
 
 /* Overwrite state (x, v) of a body; xi = xn = x (x0 untouched).  3*nV doubles each; v may

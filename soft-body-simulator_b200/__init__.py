@@ -35,7 +35,7 @@ EXPORTS = [
     "sbsb200_set_partition", "sbsb200_get_mailbox_handle", "sbsb200_connect_peers", "sbsb200_connect_peer_context",
     "sbsb200_get_vertex_ranks", "sbsb200_set_broadphase", "sbsb200_get_surface_triangles", "sbsb200_download_surface",
     "sbsb200_set_region_shape", "sbsb200_set_masses", "sbsb200_step_host_f32", "sbsb200_debug_trace_steps",
-    "sbsb200_step_host_vertices_f32", "sbsb200_count_non_finite",
+    "sbsb200_step_host_vertices_f32", "sbsb200_count_non_finite", "sbsb200_remove_constraints",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library():
     L.sbsb200_get_surface_map.argtypes = [vp, C.c_int, _u32p, C.c_int64]
     L.sbsb200_get_surface_map.restype = C.c_int64
     L.sbsb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.sbsb200_remove_constraints.argtypes = [vp, C.c_int64, _u32p]
     L.sbsb200_schedule_note.argtypes = [vp]
     L.sbsb200_schedule_note.restype = C.c_char_p
     L.sbsb200_upload.argtypes = [vp, C.c_int, _dp, _dp]
@@ -317,6 +318,12 @@ class Simulation:
         s = Stats()
         self._ck(self._L.sbsb200_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def remove_constraints(self, ids):
+        """simulation_t::remove_constraint for tet constraints, by insertion index as counted at finalize; the scene
+        is not re-planned (sbsb200_remove_constraints)."""
+        a = np.ascontiguousarray(ids, np.uint32)
+        self._ck(self._L.sbsb200_remove_constraints(self._h, len(a), a.ctypes.data_as(_u32p)))
 
     def schedule_note(self):
         return self._L.sbsb200_schedule_note(self._h).decode()

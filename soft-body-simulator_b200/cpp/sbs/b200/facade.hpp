@@ -30,6 +30,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <unordered_map>
 #include <vector>
 
 #include "../../../../include/sbs_b200.h"
@@ -527,12 +528,9 @@ class simulation_t
         constraints_.push_back(std::move(constraint));
         invalidate();
     }
-    void remove_constraint(index_type const constraint_idx) // simulation.cpp:34-39: swap with the last
-    {
-        std::swap(constraints_.at(constraint_idx), constraints_.back());
-        constraints_.pop_back();
-        invalidate();
-    }
+    // simulation.cpp:34-39: swap with the last.  A Green constraint of a built device scene is taken out in place
+    // (sbsb200_remove_constraints: no re-planning); anything else rebuilds the device scene at the next step.
+    void remove_constraint(index_type constraint_idx);
 
     std::vector<std::vector<particle_t>> const& particles() const
     {
@@ -580,6 +578,7 @@ class simulation_t
     sbsb200_ctx* ctx_ = nullptr;
     std::vector<int> device_body_;  // simulation body index -> device body index (-1: not on the device)
     std::vector<body_t const*> built_bodies_; // the bodies the device scene was built from
+    std::vector<constraint_t const*> device_constraint_; // device insertion index -> constraint (null: removed in place)
     std::vector<std::vector<double>> device_mass_; // per body: the masses the device scene holds
     scalar_type device_collision_compliance_ = -1; // the value last pushed to the device
     bool dirty_        = true;      // scene description changed since the device scene was built
@@ -744,6 +743,27 @@ class timestep_t
 
 // ---- simulation_t: device plumbing ---------------------------------------------------------------
 
+inline void simulation_t::remove_constraint(index_type const constraint_idx)
+{
+    constraint_t const* gone = constraints_.at(constraint_idx).get();
+    bool in_place            = false;
+    if (!dirty_ && ctx_ && dynamic_cast<xpbd::green_constraint_t const*>(gone))
+    {
+        auto const it = std::find(device_constraint_.begin(), device_constraint_.end(), gone);
+        if (it != device_constraint_.end())
+        {
+            std::uint32_t const id = static_cast<std::uint32_t>(it - device_constraint_.begin());
+            in_place               = sbsb200_remove_constraints(ctx_, 1, &id) == SBSB200_OK;
+            if (in_place)
+                *it = nullptr;
+        }
+    }
+    std::swap(constraints_.at(constraint_idx), constraints_.back());
+    constraints_.pop_back();
+    if (!in_place)
+        invalidate();
+}
+
 inline void simulation_t::build_device()
 {
     if (ctx_)
@@ -863,6 +883,17 @@ inline void simulation_t::build_device()
                   "sbsb200_add_distance_constraints");
         }
     check(sbsb200_finalize(ctx_), "sbsb200_finalize");
+    // device numbering: the green constraints body by body, then the distance constraints
+    device_constraint_.clear();
+    for (std::size_t b = 0; b < bodies_.size(); ++b)
+        if (device_body_[b] >= 0 && dynamic_cast<tetrahedral_body_t const*>(bodies_[b].get()))
+            for (auto const& c : constraints_)
+                if (auto const* g = dynamic_cast<xpbd::green_constraint_t const*>(c.get()))
+                    if (g->body() == b)
+                        device_constraint_.push_back(c.get());
+    for (auto const& c : constraints_)
+        if (dynamic_cast<xpbd::distance_constraint_t const*>(c.get()))
+            device_constraint_.push_back(c.get());
     // the device scene was built from the particles' masses: nothing to push until the caller changes one
     device_mass_.assign(bodies_.size(), {});
     for (std::size_t b = 0; b < bodies_.size(); ++b)
@@ -972,18 +1003,14 @@ inline std::vector<index_type> simulation_t::device_constraint_order()
     std::vector<index_type> order(static_cast<std::size_t>(std::max<std::int64_t>(n, 0)));
     if (n > 0)
         check(sbsb200_get_constraint_order(ctx_, order.data(), n), "sbsb200_get_constraint_order");
-    // device numbering: the green constraints body by body, then the distance constraints; map to
-    // positions in constraints()
-    std::vector<index_type> device_to_host;
-    for (std::size_t b = 0; b < bodies_.size(); ++b)
-        if (device_body_[b] >= 0 && dynamic_cast<tetrahedral_body_t const*>(bodies_[b].get()))
-            for (std::size_t i = 0; i < constraints_.size(); ++i)
-                if (auto const* g = dynamic_cast<xpbd::green_constraint_t const*>(constraints_[i].get()))
-                    if (g->body() == b)
-                        device_to_host.push_back(static_cast<index_type>(i));
+    // device insertion index -> constraint -> its position in constraints() now
+    std::unordered_map<constraint_t const*, index_type> position;
     for (std::size_t i = 0; i < constraints_.size(); ++i)
-        if (dynamic_cast<xpbd::distance_constraint_t const*>(constraints_[i].get()))
-            device_to_host.push_back(static_cast<index_type>(i));
+        position.emplace(constraints_[i].get(), static_cast<index_type>(i));
+    std::vector<index_type> device_to_host(device_constraint_.size(), 0);
+    for (std::size_t i = 0; i < device_constraint_.size(); ++i)
+        if (device_constraint_[i])
+            device_to_host[i] = position.at(device_constraint_[i]);
     for (index_type& o : order)
         o = device_to_host.at(o);
     return order;

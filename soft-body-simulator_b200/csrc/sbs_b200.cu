@@ -82,6 +82,7 @@ struct EngineBase
     virtual void set_vertices(sbsb200_ctx& c, int body, int64_t n, uint32_t const* which, double const* x,
                               double const* v)                                             = 0;
     virtual void set_masses(sbsb200_ctx& c, int64_t first, int64_t n, uint32_t const* which, double const* m) = 0;
+    virtual bool remove_tets(sbsb200_ctx& c, std::vector<uint32_t> const& positions)       = 0;
     virtual uint64_t general_route_calls()                                                  = 0;
     virtual int64_t count_non_finite(sbsb200_ctx& c)                                        = 0;
     virtual void step_host_f32(sbsb200_ctx& c, int body, float const* x, float const* v, double dt, int substeps,
@@ -138,6 +139,11 @@ struct sbsb200_ctx
     int64_t n_surface     = 0;
     bool any_damping      = false;
     std::string schedule_note;
+    // sbsb200_remove_constraints: constraints taken out since finalize (by insertion index), and where a tet
+    // constraint sits in the device arrays (built at the first removal)
+    std::vector<char> removed;
+    std::vector<uint32_t> position_of_insertion;
+    int64_t n_removed = 0;
 };
 
 namespace {
@@ -181,6 +187,7 @@ struct Engine final : EngineBase
     int bvh_sort_end_bit          = 64; // key bits in use: 32 Morton bits + the bits of the body index
     size_t bvh_top_bytes          = 0;  // shared memory of k_detect_all for the top of the sphere tree (BvhView::top_in_detect)
     ResidentPlan<R> pp; // resident schedule resources (may be inactive)
+    int32_t n_base_shapes = 0; // rest-shape dictionary: records [n_base_shapes, 2 n_base_shapes) are the zero-volume twins
     // CUDA-event pairs around the launches of the dominant kernel (persistent schedule: the substep
     // kernel), folded into a running sum when the statistics are read
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
@@ -316,16 +323,30 @@ struct Engine final : EngineBase
                 }
                 shape[static_cast<size_t>(p)] = static_cast<uint8_t>(it->second);
             }
+            n_base_shapes = 0;
+            if (small && T > 0 && 2 * index.size() <= static_cast<size_t>(kMaxShapes))
+            { // a twin of every record with rest volume zero: what a removed constraint points at (remove_tets)
+                n_base_shapes      = static_cast<int32_t>(index.size());
+                size_t const words = records.size();
+                for (size_t w = 0; w < words; ++w)
+                {
+                    Real4<R> q = records[w];
+                    if (w % kShapeWords == 2)
+                        q.y = R(0);
+                    records.push_back(q);
+                }
+            }
+            int32_t const n_records = static_cast<int32_t>(records.size() / kShapeWords);
             if (small && T > 0)
             {
                 tet_shape.upload(shape, st);
                 shape_records.upload(records, st);
                 pp.d_tet_shape = tet_shape.p;
                 pp.d_shapes    = shape_records.p;
-                pp.n_shapes    = static_cast<int32_t>(index.size());
+                pp.n_shapes    = n_records;
                 d.tet_shape    = tet_shape.p;
                 d.shapes       = shape_records.p;
-                d.n_shapes     = static_cast<int32_t>(index.size());
+                d.n_shapes     = n_records;
             }
         }
         tet_v.upload(hv, st);
@@ -900,6 +921,28 @@ struct Engine final : EngineBase
 
     // particle_t::mass() of n vertices (first + which[i]): one staging copy, one kernel, one synchronisation.
     // The inverse mass rides in pos[].w; the resident kernel reads it at the start of every substep.
+    // simulation_t::remove_constraint (simulation.cpp:34-39) without re-planning: the tets at these storage positions
+    // get rest volume zero — per-tet record and, with a rest-shape dictionary, the zero-volume twin of their record.
+    // Then H = -|V0| P DmInv^T vanishes, the gradient guard (green_constraint.cpp:67, :130-131) returns before the
+    // multiplier or a position changes, and the schedule (colours, regions, mailboxes, captured graphs) stays valid.
+    bool remove_tets(sbsb200_ctx& c, std::vector<uint32_t> const& positions) override
+    {
+        if (positions.empty())
+            return true;
+        if (d.n_shapes > 0 && n_base_shapes == 0)
+            return false; // a dictionary without room for the twins: the caller rebuilds the scene
+        DevBuf<uint32_t> ids;
+        ids.alloc(positions.size());
+        CK(cudaMemcpyAsync(ids.p, positions.data(), sizeof(uint32_t) * positions.size(), cudaMemcpyHostToDevice, c.stream));
+        int64_t const n = static_cast<int64_t>(positions.size());
+        k_remove_tets<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(
+            tet_r2.p, d.n_shapes > 0 ? tet_shape.p : nullptr, n_base_shapes, ids.p, n);
+        ++c.kernels;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c.stream));
+        return true;
+    }
+
     void set_masses(sbsb200_ctx& c, int64_t first, int64_t n, uint32_t const* which, double const* m) override
     {
         if (n <= 0)
@@ -1720,7 +1763,61 @@ int sbsb200_finalize(sbsb200_ctx* c)
     });
 }
 
-int64_t sbsb200_constraint_count(const sbsb200_ctx* c) { return c ? static_cast<int64_t>(c->scene.n_constraints) : static_cast<int64_t>(SBSB200_ERR_INVALID); }
+int64_t sbsb200_constraint_count(const sbsb200_ctx* c)
+{
+    return c ? static_cast<int64_t>(c->scene.n_constraints) - c->n_removed : static_cast<int64_t>(SBSB200_ERR_INVALID);
+}
+
+int sbsb200_remove_constraints(sbsb200_ctx* c, int64_t n, const uint32_t* constraints)
+{
+    if (!c)
+        return SBSB200_ERR_INVALID;
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "sbsb200_remove_constraints: call after sbsb200_finalize");
+    if (n < 0 || (n > 0 && !constraints))
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    HostScene const& h = c->scene;
+    int64_t const T = h.n_tets(), N = h.n_constraints;
+    if (c->position_of_insertion.empty() && T > 0)
+    { // insertion index -> tet -> storage position; 0xffffffff: not a tet constraint
+        std::vector<uint32_t> position_of_tet(static_cast<size_t>(T), 0);
+        for (int64_t p = 0; p < T; ++p)
+            position_of_tet[c->green_plan.storage_order[static_cast<size_t>(p)]] = static_cast<uint32_t>(p);
+        c->position_of_insertion.assign(static_cast<size_t>(N), 0xffffffffu);
+        for (int64_t t = 0; t < T; ++t)
+            c->position_of_insertion[h.tet_insertion[static_cast<size_t>(t)]] = position_of_tet[static_cast<size_t>(t)];
+        c->removed.assign(static_cast<size_t>(N), 0);
+    }
+    std::vector<uint32_t> positions;
+    std::vector<char> seen(c->removed);
+    for (int64_t i = 0; i < n; ++i)
+    {
+        if (constraints[i] >= static_cast<uint64_t>(N) || c->position_of_insertion.empty() ||
+            c->position_of_insertion[constraints[i]] == 0xffffffffu)
+            return fail(c, SBSB200_ERR_INVALID,
+                        "sbsb200_remove_constraints: not a tetrahedron constraint of this scene (distance constraints "
+                        "need a rebuild)");
+        if (seen[constraints[i]])
+            return fail(c, SBSB200_ERR_INVALID, "sbsb200_remove_constraints: constraint removed twice");
+        seen[constraints[i]] = 1;
+        positions.push_back(c->position_of_insertion[constraints[i]]);
+    }
+    if (n == 0)
+        return SBSB200_OK;
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        if (!c->engine->remove_tets(*c, positions))
+            return fail(c, SBSB200_ERR_CAPACITY,
+                        "sbsb200_remove_constraints: the rest-shape dictionary has no room for zero-volume records; "
+                        "rebuild the scene without the constraints");
+        c->removed.swap(seen);
+        c->n_removed += n;
+        c->order.erase(std::remove_if(c->order.begin(), c->order.end(),
+                                      [&](uint32_t id) { return id < c->removed.size() && c->removed[id]; }),
+                       c->order.end());
+        return SBSB200_OK;
+    });
+}
 
 int sbsb200_get_constraint_order(const sbsb200_ctx* c, uint32_t* order, int64_t n)
 {

@@ -519,6 +519,22 @@ k_gather_state(DeviceScene<R> s, int64_t first, int64_t n, uint32_t const* __res
     }
 }
 
+// sbsb200_remove_constraints: rest volume zero for the tets at these storage positions (per-tet record, and the
+// zero-volume twin of their dictionary record when there is a dictionary)
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_remove_tets(Real4<R>* __restrict__ tet_r2, uint8_t* __restrict__ tet_shape, int32_t n_base_shapes,
+              uint32_t const* __restrict__ positions, int64_t n)
+{
+    int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    uint32_t const p = positions[i];
+    tet_r2[p].y      = R(0);
+    if (tet_shape && tet_shape[p] < n_base_shapes)
+        tet_shape[p] = static_cast<uint8_t>(tet_shape[p] + n_base_shapes);
+}
+
 // particle_t::mass() of a handful of vertices (sbsb200_set_masses): the inverse mass rides in pos[].w
 template <typename R>
 __global__ void __launch_bounds__(256)

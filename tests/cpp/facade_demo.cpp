@@ -23,7 +23,7 @@ int main(int argc, char** argv)
 {
     if (argc < 8)
     {
-        std::fprintf(stderr, "usage: %s W H D frames substeps iterations out.bin [32|64] [mesh|dynamic]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s W H D frames substeps iterations out.bin [32|64] [mesh|dynamic|remove]\n", argv[0]);
         return 2;
     }
     std::size_t const W = std::atoi(argv[1]), H = std::atoi(argv[2]), D = std::atoi(argv[3]);
@@ -96,6 +96,23 @@ int main(int argc, char** argv)
             timestep.step(simulation);
             if (f == 0) // main.cpp:158-165: pin a picked vertex by setting its mass to 0 between frames
                 simulation.particles()[beam_idx][0].mass() = 0.;
+            if (f == 0 && argc > 9 && std::string(argv[9]) == "remove")
+            { // Green constraints go between frames and nothing comes: the device scene is patched in place
+              // (sbsb200_remove_constraints); the serial order before and after goes to <out>.order
+                std::vector<sbs::index_type> const before = simulation.device_constraint_order();
+                for (sbs::index_type const gone : {5u, 17u, 40u, 17u})
+                    simulation.remove_constraint(gone); // simulation.cpp:34-39: the last one takes the place
+                std::vector<sbs::index_type> const after = simulation.device_constraint_order();
+                std::FILE* o = std::fopen((std::string(argv[7]) + ".order").c_str(), "wb");
+                if (!o)
+                    return 3;
+                std::uint32_t const counts[2] = {static_cast<std::uint32_t>(before.size()),
+                                                 static_cast<std::uint32_t>(after.size())};
+                std::fwrite(counts, sizeof(std::uint32_t), 2, o);
+                std::fwrite(before.data(), sizeof(sbs::index_type), before.size(), o);
+                std::fwrite(after.data(), sizeof(sbs::index_type), after.size(), o);
+                std::fclose(o);
+            }
             if (f == 0 && argc > 9 && std::string(argv[9]) == "dynamic")
             { // constraints come and go between frames: simulation.cpp:29-39 (remove = swap with the last)
                 simulation.remove_constraint(5);

@@ -131,3 +131,45 @@ def test_facade_constraints_added_and_removed_between_frames(sbs, scenes, oracle
     assert np.array_equal(xs2, xd) and np.array_equal(vs2, vd)       # facade == C ABI path, bit for bit
     tol = 1e-9 if precision == 64 else 1e-4
     assert np.abs(xd - xr2).max() <= tol * scene.bbox_diagonal()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [64, 32])
+def test_facade_constraints_removed_in_place(sbs, scenes, oracle, precision):
+    """simulation_t::remove_constraint of Green constraints between frames with nothing added: the facade patches the
+    device scene in place (sbsb200_remove_constraints) and keeps simulation.cpp:34-39's numbering (the last constraint
+    takes the place of the removed one).  Checked against the reference algorithm run with its own remove_constraint."""
+    demo = build_demo()
+    out = os.path.join(BUILD, "facade_%d_remove.bin" % precision)
+    W, H, D, frames, S, K = 4, 4, 12, 3, 2, 5
+    subprocess.check_call([demo, str(W), str(H), str(D), str(frames), str(S), str(K), out, str(precision), "remove"])
+    rows = np.fromfile(out, np.float64).reshape(-1, 9)
+    x0, xd = rows[:, 0:3], rows[:, 3:6]
+    raw = np.fromfile(out + ".order", np.uint32)
+    n0, n1 = int(raw[0]), int(raw[1])
+    before, after = raw[2:2 + n0], raw[2 + n0:2 + n0 + n1]
+    _, tets = scenes.bar_model(W, H, D)
+    assert n0 == len(tets) and n1 == n0 - 4 and sorted(after.tolist()) == list(range(n1))
+    floor = scenes.Sdf("plane", (0.0, 1.0, 0.0), (0.0, 0.0, 0.0), (-200.0, -5.0, -200.0, 200.0, 5.0, 200.0))
+    scene = scenes.Scene("facade_demo", [scenes.TetBody(x0=x0.copy(), tets=tets.astype(np.uint32), x=x0.copy()), floor],
+                         substeps=S, iterations=K)
+    ref = oracle.World()
+    scene.instantiate(ref)
+    ref.set_constraint_order(before)
+    labels = before.tolist()                     # position in simulation.constraints() of the constraint in slot j
+    ref.step(scene.dt, S, K, False)
+    ref.set_mass(0, 0, 0.0)
+    for gone in (5, 17, 40, 17):
+        last = len(labels) - 1
+        j = labels.index(gone)
+        ref.remove_constraint(j)                 # the oracle's list: its last slot moves into slot j
+        labels[j] = labels[-1]
+        labels.pop()
+        if gone != last:                         # the facade's list: position `last` became position `gone`
+            labels[labels.index(last)] = gone
+    ref.set_constraint_order(np.array([labels.index(q) for q in after.tolist()], np.uint32))
+    for _ in range(frames - 1):
+        ref.step(scene.dt, S, K, False)
+    xr, _ = ref.download(0)
+    tol = 1e-9 if precision == 64 else 1e-4
+    assert np.abs(xd - xr).max() <= tol * scene.bbox_diagonal()

@@ -244,3 +244,67 @@ def test_host_step_of_all_bodies_at_once(sbs, scenes):
     xa = np.concatenate([a.download(ida[b])[0] for b in bodies]).astype(np.float32)
     va = np.concatenate([a.download(ida[b])[1] for b in bodies]).astype(np.float32)
     assert np.array_equal(xo, xa) and np.array_equal(vo, va)
+
+
+def _remove_in_reference(world, labels, insertion_id):
+    """simulation_t::remove_constraint in a world whose constraint list was permuted: `labels[j]` = insertion index
+    of the constraint at position j.  The reference swaps the constraint with the last one and drops it."""
+    j = labels.index(insertion_id)
+    world.remove_constraint(j)
+    labels[j] = labels[-1]
+    labels.pop()
+
+
+@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("precision", [64, 32])
+def test_constraints_removed_in_place(sbs, scenes, oracle, precision, schedule):
+    """sbsb200_remove_constraints (simulation_t::remove_constraint, simulation.cpp:34-39, without re-planning):
+    after a first frame a tenth of the Green constraints goes; the following frames equal the reference
+    algorithm — its own remove_constraint, then the exported order of the remaining constraints — and differ
+    from the scene that kept them."""
+    scene = scenes.config1(W=5, H=5, D=9, seed=3)
+    sim = sbs.Simulation(0, precision, schedule=schedule)
+    ids = scene.instantiate(sim)
+    keep = sbs.Simulation(0, precision, schedule=schedule)
+    scene.instantiate(keep)
+    worlds = [oracle.World()]
+    try:
+        from oracle import ref as REF
+        if REF.available():
+            worlds.append(REF.World())            # the reference's own translation units
+    except ImportError:
+        pass
+    order0 = sim.constraint_order()
+    labels = []
+    for w in worlds:
+        scene.instantiate(w)
+        w.set_constraint_order(order0)
+        labels.append([int(i) for i in order0])
+    for w in [sim, keep] + worlds:
+        w.step(scene.dt, scene.substeps, scene.iterations, False)
+    n = sim.constraint_count()
+    rng = np.random.default_rng(5)
+    gone = rng.choice(n, n // 10, replace=False).astype(np.uint32)
+    sim.remove_constraints(gone[: len(gone) // 2])
+    sim.remove_constraints(gone[len(gone) // 2:])          # two batches
+    assert sim.constraint_count() == n - len(gone)
+    order1 = sim.constraint_order()
+    assert len(order1) == n - len(gone) and not set(order1.tolist()) & set(gone.tolist())
+    assert [i for i in order0.tolist() if i not in set(gone.tolist())] == order1.tolist()   # the schedule stayed
+    with pytest.raises(sbs.SbsError):
+        sim.remove_constraints(gone[:1])                     # twice
+    for w, lab in zip(worlds, labels):
+        for g in gone.tolist():
+            _remove_in_reference(w, lab, g)
+        w.set_constraint_order(np.array([lab.index(i) for i in order1.tolist()], np.uint32))
+    for _ in range(2):
+        for w in [sim, keep] + worlds:
+            w.step(scene.dt, scene.substeps, scene.iterations, False)
+    assert sim.stats()["schedule"] == schedule, sim.schedule_note()
+    xg, vg = sim.download(ids[0])
+    xk, _ = keep.download(ids[0])
+    diag = scene.bbox_diagonal()
+    for w in worlds:
+        xr, vr = w.download(0)
+        assert np.abs(xg - xr).max() <= TOL[precision] * diag, np.abs(xg - xr).max() / diag
+    assert np.abs(xg - xk).max() > 5 * TOL[32] * diag       # the removed constraints mattered (1.4e-3 of the diagonal)
