@@ -257,6 +257,11 @@ int sbsb200_download(sbsb200_ctx* ctx, int body, double* x, double* v);
  * (tetrahedral_body_t::update_visual_model, tetrahedral_body.cpp:157-165; normals as
  * tetrahedral_mesh_boundary.cpp:122-145, but summed from zero at every call). */
 int sbsb200_download_surface(sbsb200_ctx* ctx, int body, float* xyz_normal);
+/* The same with the reference's 9-float vertex (prepare_vertices_for_surface_rendering,
+ * tetrahedral_mesh_boundary.cpp:170-193): x, y, z, nx, ny, nz, r, g, b.  colours: 3 floats — the whole body in one
+ * colour, as geometry_t::set_color leaves it (n_colours = 1) — or 3 per surface vertex (n_colours = surface vertices). */
+int sbsb200_download_surface_rgb(sbsb200_ctx* ctx, int body, const float* colours, int64_t n_colours,
+                                 float* xyz_normal_rgb);
 /* particle_t::mass() = m (main.cpp:158-165 toggles 1 <-> 0 between frames). */
 int sbsb200_set_mass(sbsb200_ctx* ctx, int body, int64_t vertex, double mass);
 /* The same for n vertices of a body in one call (one copy, one synchronisation): what a host-side mirror of

@@ -36,6 +36,7 @@ EXPORTS = [
     "sbsb200_get_vertex_ranks", "sbsb200_set_broadphase", "sbsb200_get_surface_triangles", "sbsb200_download_surface",
     "sbsb200_set_region_shape", "sbsb200_set_masses", "sbsb200_step_host_f32", "sbsb200_debug_trace_steps",
     "sbsb200_step_host_vertices_f32", "sbsb200_count_non_finite", "sbsb200_remove_constraints",
+    "sbsb200_download_surface_rgb",
 ]
 
 
@@ -117,6 +118,7 @@ def load_library():
     L.sbsb200_get_surface_triangles.argtypes = [vp, C.c_int, _u32p, C.c_int64]
     L.sbsb200_get_surface_triangles.restype = C.c_int64
     L.sbsb200_download_surface.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    L.sbsb200_download_surface_rgb.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_float)]
     L.sbsb200_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.sbsb200_get_mailbox_handle.argtypes = [vp, C.c_char_p]
     L.sbsb200_connect_peers.argtypes = [vp, C.c_char_p, C.c_int]
@@ -312,6 +314,16 @@ class Simulation:
         n = len(self.surface_map(body))
         out = np.empty((max(n, 1), 6), np.float32)
         self._ck(self._L.sbsb200_download_surface(self._h, body, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out[:n]
+
+    def download_surface_rgb(self, body, colours):
+        """[n_surface_vertices, 9] float32: position, unit normal and colour — the reference's render vertex
+        (tetrahedral_mesh_boundary.cpp:170-193).  colours: one rgb triple or one per surface vertex."""
+        n = len(self.surface_map(body))
+        col = np.ascontiguousarray(colours, np.float32).reshape(-1, 3)
+        out = np.empty((max(n, 1), 9), np.float32)
+        fp = C.POINTER(C.c_float)
+        self._ck(self._L.sbsb200_download_surface_rgb(self._h, body, col.ctypes.data_as(fp), len(col), out.ctypes.data_as(fp)))
         return out[:n]
 
     def stats(self):

@@ -99,7 +99,8 @@ struct EngineBase
     virtual void set_peer_mailboxes(int rank, void* p)                                      = 0;
     virtual bool peers_connected()                                                          = 0;
     virtual void check_after_sync(sbsb200_ctx& c)                                           = 0;
-    virtual void download_surface(sbsb200_ctx& c, int body, float* out)                     = 0;
+    virtual void download_surface(sbsb200_ctx& c, int body, float* out, float const* colours = nullptr,
+                                  int64_t n_colours = 0)                                   = 0;
     virtual void eval_sdf(sbsb200_ctx& c, int body, int64_t n, double const* pts, double* sd, double* grad) = 0;
 };
 
@@ -859,24 +860,33 @@ struct Engine final : EngineBase
 
     void check_after_sync(sbsb200_ctx& c) override { check_persistent(c); }
 
-    void download_surface(sbsb200_ctx& c, int body, float* out) override
+    void download_surface(sbsb200_ctx& c, int body, float* out, float const* colours, int64_t n_colours) override
     {
         HostBody const& hb = c.scene.bodies[static_cast<size_t>(body)];
         int64_t const n    = static_cast<int64_t>(hb.surf_to_tet.size());
         int64_t const nt   = tri_offset[static_cast<size_t>(body) + 1] - tri_offset[static_cast<size_t>(body)];
         if (n == 0)
             return;
-        if (surf_out.n < static_cast<size_t>(6 * n))
-            surf_out.alloc(static_cast<size_t>(6 * n));
+        int64_t const width = colours ? 9 : 6; // floats per vertex
+        if (surf_out.n < static_cast<size_t>(width * n))
+            surf_out.alloc(static_cast<size_t>(width * n));
+        DevBuf<float> dcol;
+        if (colours)
+        {
+            dcol.alloc(static_cast<size_t>(3 * n_colours));
+            CK(cudaMemcpyAsync(dcol.p, colours, sizeof(float) * 3 * static_cast<size_t>(n_colours), cudaMemcpyHostToDevice,
+                               c.stream));
+        }
         CK(cudaMemsetAsync(surf_normal.p + hb.s_offset, 0, sizeof(Real4<R>) * static_cast<size_t>(n), c.stream));
         if (nt > 0)
             k_surface_normals<R><<<static_cast<unsigned>((nt + 255) / 256), 256, 0, c.stream>>>(
                 d, tri_offset[static_cast<size_t>(body)], nt, surf_tri.p, hb.s_offset, surf_normal.p);
-        k_surface_pack<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(d, hb.s_offset, n, surf_normal.p,
-                                                                                     surf_out.p);
+        k_surface_pack<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(
+            d, hb.s_offset, n, surf_normal.p, surf_out.p, colours ? dcol.p : nullptr, n_colours);
         c.kernels += 2;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(out, surf_out.p, sizeof(float) * 6 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(out, surf_out.p, sizeof(float) * static_cast<size_t>(width * n), cudaMemcpyDeviceToHost,
+                           c.stream));
         CK(cudaStreamSynchronize(c.stream));
         check_persistent(c);
     }
@@ -1861,6 +1871,24 @@ int sbsb200_download_surface(sbsb200_ctx* c, int body, float* out)
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
         c->engine->download_surface(*c, body, out);
+        return SBSB200_OK;
+    });
+}
+
+int sbsb200_download_surface_rgb(sbsb200_ctx* c, int body, const float* colours, int64_t n_colours, float* out)
+{
+    if (!c || !out || !colours)
+        return fail(c, SBSB200_ERR_INVALID, "null argument");
+    if (!c->finalized)
+        return fail(c, SBSB200_ERR_STATE, "download_surface_rgb before finalize");
+    if (!is_tet_body(c, body))
+        return fail(c, SBSB200_ERR_INVALID, "not a tetrahedral body");
+    int64_t const n = static_cast<int64_t>(c->scene.bodies[static_cast<size_t>(body)].surf_to_tet.size());
+    if (n_colours != 1 && n_colours != n)
+        return fail(c, SBSB200_ERR_INVALID, "download_surface_rgb: one colour, or one per surface vertex");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        c->engine->download_surface(*c, body, out, colours, n_colours);
         return SBSB200_OK;
     });
 }

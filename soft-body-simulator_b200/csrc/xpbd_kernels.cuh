@@ -431,10 +431,12 @@ k_surface_normals(DeviceScene<R> s, int64_t first_triangle, int64_t n_triangles,
     atomic_add3(&normal[first_surface + c], n.x, n.y, n.z);
 }
 // (x, y, z, nx, ny, nz) as floats, the vertex layout of the reference's renderer (renderer.cpp:484-542)
+// With `colour` (one rgb triple, or one per surface vertex) the record is the reference's 9-float vertex
+// (prepare_vertices_for_surface_rendering, tetrahedral_mesh_boundary.cpp:170-193): position, normal, colour.
 template <typename R>
 __global__ void __launch_bounds__(256)
 k_surface_pack(DeviceScene<R> s, int64_t first_surface, int64_t n, Real4<R> const* __restrict__ normal,
-               float* __restrict__ out)
+               float* __restrict__ out, float const* __restrict__ colour = nullptr, int64_t n_colours = 0)
 {
     int64_t const i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i >= n)
@@ -443,12 +445,20 @@ k_surface_pack(DeviceScene<R> s, int64_t first_surface, int64_t n, Real4<R> cons
     Real4<R> const m = ld4(&normal[first_surface + i]);
     R const len2     = m.x * m.x + m.y * m.y + m.z * m.z;
     R const inv      = len2 > R(0) ? R(1) / sqrt_(len2) : R(0);
-    out[6 * i]       = float(p.x);
-    out[6 * i + 1]   = float(p.y);
-    out[6 * i + 2]   = float(p.z);
-    out[6 * i + 3]   = float(m.x * inv);
-    out[6 * i + 4]   = float(m.y * inv);
-    out[6 * i + 5]   = float(m.z * inv);
+    int64_t const w  = colour ? 9 : 6;
+    out[w * i]       = float(p.x);
+    out[w * i + 1]   = float(p.y);
+    out[w * i + 2]   = float(p.z);
+    out[w * i + 3]   = float(m.x * inv);
+    out[w * i + 4]   = float(m.y * inv);
+    out[w * i + 5]   = float(m.z * inv);
+    if (colour)
+    {
+        float const* c = colour + (n_colours > 1 ? 3 * i : 0);
+        out[w * i + 6] = c[0];
+        out[w * i + 7] = c[1];
+        out[w * i + 8] = c[2];
+    }
 }
 
 // Host-format (3 doubles per vertex) <-> device layout.  Upload sets x = xi = xn and keeps the

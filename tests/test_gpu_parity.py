@@ -315,3 +315,24 @@ def test_surface_output_for_rendering(sbs, scenes, oracle):
     n /= np.linalg.norm(n, axis=1, keepdims=True)
     assert np.abs(out[:, 3:] - n).max() < 1e-4
     assert np.abs(np.linalg.norm(out[:, 3:], axis=1) - 1).max() < 1e-5
+
+
+def test_surface_output_with_colours(sbs, scenes):
+    """The reference's 9-float render vertex (prepare_vertices_for_surface_rendering,
+    tetrahedral_mesh_boundary.cpp:170-193): position, normal, colour — one colour for the body (geometry_t::set_color)
+    or one per surface vertex."""
+    scene = scenes.config1(W=4, H=4, D=6)
+    sim = sbs.Simulation(0, 32)
+    ids = scene.instantiate(sim)
+    sim.step(scene.dt, 2, 3)
+    plain = sim.download_surface(ids[0])
+    one = sim.download_surface_rgb(ids[0], (1.0, 1.0, 0.0))          # main.cpp:21: beam_geometry.set_color(255, 255, 0)
+    assert one.shape == (len(plain), 9)
+    # (the normals are summed with float atomics: the last bit depends on the order of the triangles)
+    same = lambda a: np.array_equal(a[:, :3], plain[:, :3]) and np.abs(a[:, 3:6] - plain[:, 3:]).max() < 1e-5
+    assert same(one) and np.array_equal(one[:, 6:], np.tile(np.float32([1, 1, 0]), (len(plain), 1)))
+    col = np.random.default_rng(0).random((len(plain), 3)).astype(np.float32)
+    each = sim.download_surface_rgb(ids[0], col)
+    assert same(each) and np.array_equal(each[:, 6:], col)
+    with pytest.raises(sbs.SbsError):
+        sim.download_surface_rgb(ids[0], col[:5])
