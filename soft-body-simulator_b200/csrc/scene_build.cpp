@@ -495,6 +495,19 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
     }
     out.n_clusters = static_cast<int64_t>(clusters.size());
 
+    // unique vertices per cluster
+    for (Cluster& c : clusters)
+    {
+        c.nv = 0;
+        for (uint32_t p = c.first; p < c.first + c.count; ++p)
+            for (int a = 0; a < 4; ++a)
+            {
+                uint32_t const v = scene.tets[4 * static_cast<size_t>(sorted[p]) + a];
+                if (std::find(c.verts, c.verts + c.nv, v) == c.verts + c.nv)
+                    c.verts[c.nv++] = v;
+            }
+    }
+
     // first-fit colouring in (body, raster) order; same-colour clusters must be vertex-disjoint
     {
         constexpr int kWords = 2; // up to 128 cluster colours
@@ -520,6 +533,101 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
             for (uint32_t p = c.first; p < c.first + c.count; ++p)
                 for (int a = 0; a < 4; ++a)
                     used[scene.tets[4 * static_cast<size_t>(sorted[p]) + a]][col >> 6] |= (1ull << (col & 63));
+        }
+    }
+
+    // Bodies that live in ONE region (ensembles, small scenes): colour classes of equal size.  A CTA has a thread — and its
+    // registers — for every cluster of its widest colour step, and first-fit on a lattice with odd sides is far from even
+    // (5 x 5 x 16 cells: 72, 72, 48, 48, 48, 48, 32, 32), so a third of the register file would sit idle in most steps.
+    // Kempe chains: inside a body, the clusters of two colours a, b form connected components (sharing a vertex), and
+    // swapping a and b inside one component keeps the colouring valid; components with a surplus of the fuller colour are
+    // swapped while that evens the two classes out.  Any valid colouring is a valid Gauss-Seidel order.
+#ifdef SBSB200_NO_COLOUR_BALANCE
+    if (false)
+#else
+    if ((one_region_per_body || n_regions <= 1) && out.n_colours > 1)
+#endif
+    {
+        int32_t const C = out.n_colours;
+        std::vector<int64_t> v_off(static_cast<size_t>(V) + 1, 0);
+        for (Cluster const& c : clusters)
+            for (uint32_t k = 0; k < c.nv; ++k)
+                ++v_off[static_cast<size_t>(c.verts[k]) + 1];
+        for (int64_t v = 0; v < V; ++v)
+            v_off[static_cast<size_t>(v) + 1] += v_off[static_cast<size_t>(v)];
+        std::vector<uint32_t> v_cl(static_cast<size_t>(v_off.back()));
+        {
+            std::vector<int64_t> cur(v_off.begin(), v_off.end() - 1);
+            for (size_t ci = 0; ci < clusters.size(); ++ci)
+                for (uint32_t k = 0; k < clusters[ci].nv; ++k)
+                    v_cl[static_cast<size_t>(cur[clusters[ci].verts[k]]++)] = static_cast<uint32_t>(ci);
+        }
+        std::vector<uint32_t> stamp(clusters.size(), 0), queue, comp;
+        uint32_t epoch = 0;
+        std::vector<int32_t> cnt(static_cast<size_t>(C));
+        for (size_t b0 = 0; b0 < clusters.size();)
+        { // clusters are sorted by body
+            size_t b1 = b0;
+            while (b1 < clusters.size() && clusters[b1].body == clusters[b0].body)
+                ++b1;
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (size_t ci = b0; ci < b1; ++ci)
+                ++cnt[static_cast<size_t>(clusters[ci].colour)];
+            std::vector<int32_t> by_count(static_cast<size_t>(C));
+            for (int round = 0; round < 8 * C; ++round)
+            { // the fullest colour against the emptiest one first; when their components are too coarse, the next pairs
+                std::iota(by_count.begin(), by_count.end(), 0);
+                std::stable_sort(by_count.begin(), by_count.end(),
+                                 [&](int32_t x, int32_t y) { return cnt[static_cast<size_t>(x)] > cnt[static_cast<size_t>(y)]; });
+                bool changed = false;
+                for (int32_t ia = 0; ia < C && !changed; ++ia)
+                    for (int32_t ib = C - 1; ib > ia && !changed; --ib)
+                    {
+                        int32_t const a = by_count[static_cast<size_t>(ia)], b = by_count[static_cast<size_t>(ib)];
+                        if (cnt[static_cast<size_t>(a)] - cnt[static_cast<size_t>(b)] < 2)
+                            break;
+                        ++epoch;
+                        for (size_t seed = b0; seed < b1; ++seed)
+                        {
+                            if (stamp[seed] == epoch || (clusters[seed].colour != a && clusters[seed].colour != b))
+                                continue;
+                            comp.clear();
+                            queue.assign(1, static_cast<uint32_t>(seed));
+                            stamp[seed] = epoch;
+                            int32_t surplus = 0; // clusters of colour a minus clusters of colour b in the component
+                            while (!queue.empty())
+                            {
+                                uint32_t const ci = queue.back();
+                                queue.pop_back();
+                                comp.push_back(ci);
+                                surplus += clusters[ci].colour == a ? 1 : -1;
+                                for (uint32_t k = 0; k < clusters[ci].nv; ++k)
+                                    for (int64_t e = v_off[clusters[ci].verts[k]];
+                                         e < v_off[static_cast<size_t>(clusters[ci].verts[k]) + 1]; ++e)
+                                    {
+                                        uint32_t const cj = v_cl[static_cast<size_t>(e)];
+                                        if (stamp[cj] != epoch && (clusters[cj].colour == a || clusters[cj].colour == b))
+                                        {
+                                            stamp[cj] = epoch;
+                                            queue.push_back(cj);
+                                        }
+                                    }
+                            }
+                            int32_t const diff = cnt[static_cast<size_t>(a)] - cnt[static_cast<size_t>(b)];
+                            if (surplus > 0 && std::abs(diff - 2 * surplus) < diff)
+                            {
+                                for (uint32_t ci : comp)
+                                    clusters[ci].colour = clusters[ci].colour == a ? b : a;
+                                cnt[static_cast<size_t>(a)] -= surplus;
+                                cnt[static_cast<size_t>(b)] += surplus;
+                                changed = true;
+                            }
+                        }
+                    }
+                if (!changed)
+                    break;
+            }
+            b0 = b1;
         }
     }
 
@@ -729,18 +837,6 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
     else
         out.n_regions = 1;
 
-    // unique vertices per cluster
-    for (Cluster& c : clusters)
-    {
-        c.nv = 0;
-        for (uint32_t p = c.first; p < c.first + c.count; ++p)
-            for (int a = 0; a < 4; ++a)
-            {
-                uint32_t const v = scene.tets[4 * static_cast<size_t>(sorted[p]) + a];
-                if (std::find(c.verts, c.verts + c.nv, v) == c.verts + c.nv)
-                    c.verts[c.nv++] = v;
-            }
-    }
     for (Cluster const& c : clusters)
         for (uint32_t m = 0; m < c.count; ++m)
             out.tet_region[sorted[c.first + m]] = c.region;
