@@ -536,16 +536,17 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
         }
     }
 
-    // Bodies that live in ONE region (ensembles, small scenes): colour classes of equal size.  A CTA has a thread — and its
+    // Ensembles (whole bodies per region): colour classes of equal size inside every body.  A CTA has a thread — and its
     // registers — for every cluster of its widest colour step, and first-fit on a lattice with odd sides is far from even
     // (5 x 5 x 16 cells: 72, 72, 48, 48, 48, 48, 32, 32), so a third of the register file would sit idle in most steps.
     // Kempe chains: inside a body, the clusters of two colours a, b form connected components (sharing a vertex), and
     // swapping a and b inside one component keeps the colouring valid; components with a surplus of the fuller colour are
-    // swapped while that evens the two classes out.  Any valid colouring is a valid Gauss-Seidel order.
+    // swapped while that evens the two classes out.  Any valid colouring is a valid Gauss-Seidel order.  (A single body in one
+    // region keeps its first-fit colours: its steps are as long as five tets in a row whatever their width.)
 #ifdef SBSB200_NO_COLOUR_BALANCE
     if (false)
 #else
-    if ((one_region_per_body || n_regions <= 1) && out.n_colours > 1)
+    if (one_region_per_body && out.n_colours > 1)
 #endif
     {
         int32_t const C = out.n_colours;

@@ -155,12 +155,9 @@ def test_clustered_colouring_of_lattices(hostscene, oracle, dims, bodies, region
             # 6x6x17: 50 clusters in every colour step of a body once the classes are balanced -> three bodies fill 160
             # threads, when their vertices fit the shared memory on offer
             assert group == min(3, smem // (len(pos) * 16))
-    if (per_body or regions <= 1) and nc == 8:
-        # bodies that live in one region: colour classes of equal size (Kempe chains), so the widest colour step of a
-        # region — what a CTA needs threads and registers for — is close to the mean (first-fit: 128 of 735 cells for
-        # 8x8x16, 72 of 400 for 6x6x17)
-        per_region = group if per_body else 1
-        assert mch.value <= per_region * (n_cells / 8 + 3), (mch.value, per_region, n_cells)
+        # ensembles: colour classes of equal size inside every body (Kempe chains), so the widest colour step of a
+        # region — what a CTA needs threads and registers for — is close to the mean (first-fit: 72 of 400 cells for 6x6x17)
+        assert mch.value <= group * (n_cells / 8 + 3), (mch.value, group, n_cells)
 
 
 def test_clustered_colouring_of_an_irregular_mesh(hostscene):
