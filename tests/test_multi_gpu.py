@@ -102,3 +102,41 @@ def test_owned_vertices_round_trip_through_the_host(sbs, scenes):
         xr, vr = ref[r][0].download(ref[r][1][0])
         assert np.array_equal(x[r], xr[owned[r]].astype(np.float32))
         assert np.array_equal(v[r], vr[owned[r]].astype(np.float32))
+
+
+@pytest.mark.skipif(not _two_gpus(), reason="needs two GPUs")
+def test_constraints_removed_in_place_on_every_rank(sbs, scenes, oracle):
+    """sbsb200_remove_constraints on a decomposed body: every rank takes the same constraints out of its copy of the
+    scene; the exchange plan stays as it is.  Against the reference algorithm with its own remove_constraint."""
+    scene = scenes.config1(W=9, H=9, D=41, bottom=0.0)
+    sims = run_decomposed(sbs, scene, 32, 2, 1, devices=[0, 1])
+    order0 = sims[0][0].constraint_order()
+    ref = oracle.World()
+    scene.instantiate(ref)
+    ref.set_constraint_order(order0)
+    labels = [int(i) for i in order0]
+    ref.step(scene.dt, scene.substeps, scene.iterations, scene.detect_every_substep)
+    n = sims[0][0].constraint_count()
+    gone = np.random.default_rng(9).choice(n, n // 20, replace=False).astype(np.uint32)
+    for sim, _ in sims:
+        sim.remove_constraints(gone)
+    order1 = sims[0][0].constraint_order()
+    assert np.array_equal(order1, sims[1][0].constraint_order()) and len(order1) == n - len(gone)
+    for g in gone.tolist():
+        j = labels.index(g)
+        ref.remove_constraint(j)
+        labels[j] = labels[-1]
+        labels.pop()
+    ref.set_constraint_order(np.array([labels.index(i) for i in order1.tolist()], np.uint32))
+    for sim, _ in sims:
+        sim.step(scene.dt, scene.substeps, scene.iterations, scene.detect_every_substep)
+    for sim, _ in sims:
+        sim.synchronize()
+    ref.step(scene.dt, scene.substeps, scene.iterations, scene.detect_every_substep)
+    xr, _ = ref.download(0)
+    ranks = sims[0][0].vertex_ranks(sims[0][1][0])
+    x = np.empty_like(xr)
+    for r, (sim, ids) in enumerate(sims):
+        xs, _ = sim.download(ids[0])
+        x[ranks == r] = xs[ranks == r]
+    assert np.abs(x - xr).max() <= 1e-4 * scene.bbox_diagonal()
