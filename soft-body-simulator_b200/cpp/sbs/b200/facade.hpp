@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "../../../../include/sbs_b200.h"
+#include "../common/node.h"
 
 namespace sbs {
 
@@ -447,10 +448,87 @@ class contact_handler_t : public collision::contact_handler_t
 } // namespace xpbd
 
 // include/sbs/physics/body.h:16-46
+} // namespace physics
+
+namespace common {
+
+// include/sbs/common/mesh.h:13-40: what a renderer draws
+class shared_vertex_surface_mesh_i : public renderable_node_t
+{
+  public:
+    struct vertex_type
+    {
+        vec3 position, normal;
+        std::array<float, 3> color{{0.f, 0.f, 0.f}};
+    };
+    struct triangle_type
+    {
+        std::array<std::uint32_t, 3> vertices;
+    };
+    virtual std::size_t triangle_count() const         = 0;
+    virtual std::size_t vertex_count() const           = 0;
+    virtual vertex_type vertex(std::size_t vi) const   = 0;
+    virtual triangle_type triangle(std::size_t f) const = 0;
+};
+
+} // namespace common
+
+namespace physics {
+
+// include/sbs/physics/tetrahedral_mesh_boundary.h: the boundary surface of a tetrahedral body.  Triangles, the
+// surface -> tetrahedral-mesh vertex map (tetrahedral_mesh_boundary.cpp:49-58, :65-120) and, after every
+// tetrahedral_body_t::update_visual_model, positions and normals come from the device (sbsb200_get_surface_map,
+// _get_surface_triangles, _download_surface: boundary gather and normals are kernels, nothing is recomputed here).
+class tetrahedral_mesh_boundary_t : public common::shared_vertex_surface_mesh_i
+{
+  public:
+    using vertex_type   = common::shared_vertex_surface_mesh_i::vertex_type;
+    using triangle_type = common::shared_vertex_surface_mesh_i::triangle_type;
+    std::size_t triangle_count() const override { return triangles_.size(); }
+    std::size_t vertex_count() const override { return vertices_.size(); }
+    vertex_type vertex(std::size_t vi) const override { return vertices_.at(vi); }
+    triangle_type triangle(std::size_t f) const override { return triangles_.at(f); }
+    vertex_type& mutable_vertex(std::size_t vi) { return vertices_.at(vi); }
+    triangle_type& mutable_triangle(std::size_t f) { return triangles_.at(f); }
+    std::vector<index_type> const& surface_to_tetrahedral_mesh_index_map() const { return to_tet_; }
+    index_type from_surface_vertex(std::size_t vi) const { return to_tet_.at(vi); }
+    // tetrahedral_mesh_boundary.cpp:170-208: (x, y, z, nx, ny, nz, r, g, b) per vertex, three indices per triangle
+    void prepare_vertices_for_rendering() override
+    {
+        std::vector<float> buffer;
+        buffer.reserve(9 * vertices_.size());
+        for (vertex_type const& v : vertices_)
+        {
+            for (int d = 0; d < 3; ++d)
+                buffer.push_back(static_cast<float>(v.position[d]));
+            for (int d = 0; d < 3; ++d)
+                buffer.push_back(static_cast<float>(v.normal[d]));
+            for (int d = 0; d < 3; ++d)
+                buffer.push_back(v.color[static_cast<std::size_t>(d)]);
+        }
+        transfer_vertices_for_rendering(std::move(buffer));
+    }
+    void prepare_indices_for_rendering() override
+    {
+        std::vector<std::uint32_t> buffer;
+        buffer.reserve(3 * triangles_.size());
+        for (triangle_type const& t : triangles_)
+            buffer.insert(buffer.end(), t.vertices.begin(), t.vertices.end());
+        transfer_indices_for_rendering(std::move(buffer));
+    }
+
+  private:
+    friend class tetrahedral_body_t;
+    std::vector<vertex_type> vertices_;
+    std::vector<triangle_type> triangles_;
+    std::vector<index_type> to_tet_;
+};
+
 class body_t
 {
   public:
     using collision_model_type = collision::collision_model_t;
+    using visual_model_type    = common::shared_vertex_surface_mesh_i;
     body_t(simulation_t& simulation, index_type id) : id_(id), simulation_(simulation) {}
     virtual ~body_t() = default;
     virtual collision_model_type const& collision_model() const = 0;
@@ -555,6 +633,14 @@ class simulation_t
     int precision = SBSB200_FP32;      // SBSB200_FP64 = validation build
     int detect_mode = SBSB200_DETECT_PER_FRAME; // timestep.cpp:29-30
     sbsb200_ctx* context() { return ctx_; }
+    // the device scene (built now if the description changed) and the device index of a body (-1: not on the device)
+    sbsb200_ctx* ensure_device()
+    {
+        if (dirty_ || !ctx_)
+            build_device();
+        return ctx_;
+    }
+    int device_body(index_type body) const { return device_body_.at(body); }
     void device_step(scalar_type dt, std::size_t substeps, std::size_t iterations);
     // the serial constraint order equivalent to the device schedule (sbsb200_get_constraint_order)
     std::vector<index_type> device_constraint_order();
@@ -603,9 +689,42 @@ class tetrahedral_body_t : public body_t
                 {static_cast<index_type>(geometry.indices[i]), static_cast<index_type>(geometry.indices[i + 1]),
                  static_cast<index_type>(geometry.indices[i + 2]), static_cast<index_type>(geometry.indices[i + 3])}});
         collision_model_.id() = id;
+        colors_               = geometry.colors;
     }
     collision_model_type const& collision_model() const override { return collision_model_; }
     collision_model_type& collision_model() override { return collision_model_; }
+    // tetrahedral_body.cpp:85-119, :157-165.  The boundary lives on the device: it is fetched when first asked for
+    // (which builds the device scene if need be), update_visual_model() refreshes positions and normals from the
+    // surface copy of the last step.  Colours follow the reference: surface vertex i takes colour i of the geometry
+    // (tetrahedral_body.cpp:66-78).
+    tetrahedral_mesh_boundary_t const& surface_mesh()
+    {
+        fetch_boundary();
+        return visual_model_;
+    }
+    visual_model_type& visual_model()
+    {
+        fetch_boundary();
+        return visual_model_;
+    }
+    void update_visual_model()
+    {
+        fetch_boundary();
+        sbsb200_ctx* ctx = simulation().ensure_device();
+        int const db     = simulation().device_body(id());
+        std::vector<float> out(6 * std::max<std::size_t>(1, visual_model_.vertices_.size()));
+        int const rc = sbsb200_download_surface(ctx, db, out.data());
+        if (rc < 0)
+            throw b200::error(rc, std::string("sbsb200_download_surface: ") + sbsb200_last_error(ctx));
+        for (std::size_t i = 0; i < visual_model_.vertices_.size(); ++i)
+        {
+            visual_model_.vertices_[i].position = vec3(out[6 * i], out[6 * i + 1], out[6 * i + 2]);
+            visual_model_.vertices_[i].normal   = vec3(out[6 * i + 3], out[6 * i + 4], out[6 * i + 5]);
+        }
+        visual_model_.mark_vertices_dirty();
+    }
+    void update_collision_model() {} // the sphere tree is refitted on the device at every detection (bvh.cuh)
+    void update_physical_model() {}  // tetrahedral_body.cpp:116-119: no-op
     void transform(affine3 const& affine) override // tetrahedral_body.cpp:121-132: x0, xi, xn and x
     {
         for (particle_t& p : simulation().particles().at(id()))
@@ -619,7 +738,33 @@ class tetrahedral_body_t : public body_t
     tetrahedron_set_t const& physical_model() const { return physical_model_; }
 
   private:
+    void fetch_boundary()
+    {
+        if (fetched_)
+            return;
+        sbsb200_ctx* ctx = simulation().ensure_device();
+        int const db     = simulation().device_body(id());
+        std::int64_t const nv = sbsb200_get_surface_map(ctx, db, nullptr, 0);
+        std::int64_t const ni = sbsb200_get_surface_triangles(ctx, db, nullptr, 0);
+        if (nv < 0 || ni < 0)
+            throw b200::error(static_cast<int>(nv < 0 ? nv : ni), "sbs-b200: no boundary for this body on the device");
+        visual_model_.to_tet_.resize(static_cast<std::size_t>(nv));
+        std::vector<std::uint32_t> tri(static_cast<std::size_t>(ni));
+        sbsb200_get_surface_map(ctx, db, visual_model_.to_tet_.data(), nv);
+        sbsb200_get_surface_triangles(ctx, db, tri.data(), ni);
+        visual_model_.triangles_.resize(tri.size() / 3);
+        for (std::size_t f = 0; f < visual_model_.triangles_.size(); ++f)
+            visual_model_.triangles_[f].vertices = {{tri[3 * f], tri[3 * f + 1], tri[3 * f + 2]}};
+        visual_model_.vertices_.assign(static_cast<std::size_t>(nv), tetrahedral_mesh_boundary_t::vertex_type{});
+        for (std::size_t i = 0; i < visual_model_.vertices_.size() && 3 * i + 2 < colors_.size(); ++i)
+            visual_model_.vertices_[i].color = {{colors_[3 * i] / 255.f, colors_[3 * i + 1] / 255.f, colors_[3 * i + 2] / 255.f}};
+        visual_model_.set_as_physically_simulated_body();
+        fetched_ = true;
+    }
     tetrahedron_set_t physical_model_;
+    tetrahedral_mesh_boundary_t visual_model_;
+    std::vector<std::uint8_t> colors_;
+    bool fetched_ = false;
     collision::point_bvh_model_t collision_model_;
 };
 

@@ -23,7 +23,7 @@ int main(int argc, char** argv)
 {
     if (argc < 8)
     {
-        std::fprintf(stderr, "usage: %s W H D frames substeps iterations out.bin [32|64] [mesh|dynamic|remove]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s W H D frames substeps iterations out.bin [32|64] [mesh|dynamic|remove|surface]\n", argv[0]);
         return 2;
     }
     std::size_t const W = std::atoi(argv[1]), H = std::atoi(argv[2]), D = std::atoi(argv[3]);
@@ -120,6 +120,26 @@ int main(int argc, char** argv)
                 simulation.add_constraint(std::make_unique<sbs::physics::xpbd::distance_constraint_t>(
                     1e-4, 0., simulation, beam_idx, beam_idx, 1, last));
             }
+        }
+
+        if (argc > 9 && std::string(argv[9]) == "surface")
+        { // what the reference's renderer consumes (renderer.cpp:484-542): the body's visual model, refreshed from the
+          // device, as the 9-float vertex buffer and the index buffer of tetrahedral_mesh_boundary.cpp:170-208
+            beam.update_visual_model();
+            sbs::common::shared_vertex_surface_mesh_i& mesh = beam.visual_model();
+            mesh.prepare_vertices_for_rendering();
+            mesh.prepare_indices_for_rendering();
+            std::FILE* o = std::fopen((std::string(argv[7]) + ".surface").c_str(), "wb");
+            if (!o)
+                return 3;
+            std::uint32_t const counts[2] = {static_cast<std::uint32_t>(mesh.vertex_count()),
+                                             static_cast<std::uint32_t>(mesh.triangle_count())};
+            std::fwrite(counts, sizeof(std::uint32_t), 2, o);
+            std::fwrite(mesh.get_cpu_vertex_buffer().data(), sizeof(float), mesh.get_cpu_vertex_buffer().size(), o);
+            std::fwrite(mesh.get_cpu_index_buffer().data(), sizeof(std::uint32_t), mesh.get_cpu_index_buffer().size(), o);
+            std::fwrite(beam.surface_mesh().surface_to_tetrahedral_mesh_index_map().data(), sizeof(sbs::index_type),
+                        mesh.vertex_count(), o);
+            std::fclose(o);
         }
 
         auto const& ps = static_cast<sbs::physics::simulation_t const&>(simulation).particles()[beam_idx];

@@ -173,3 +173,36 @@ def test_facade_constraints_removed_in_place(sbs, scenes, oracle, precision):
     xr, _ = ref.download(0)
     tol = 1e-9 if precision == 64 else 1e-4
     assert np.abs(xd - xr).max() <= tol * scene.bbox_diagonal()
+
+
+@pytest.mark.gpu
+def test_facade_visual_model_for_a_renderer(sbs, scenes):
+    """tetrahedral_body_t::visual_model() / update_visual_model() / prepare_*_for_rendering (tetrahedral_body.cpp:85-119,
+    :157-165; tetrahedral_mesh_boundary.cpp:170-208) on the facade: the 9-float vertex buffer and the index buffer a
+    renderer consumes, filled from the device, equal what the C ABI hands out for the same scene."""
+    demo = build_demo()
+    out = os.path.join(BUILD, "facade_32_surface.bin")
+    W, H, D, frames, S, K = 4, 4, 12, 2, 2, 5
+    subprocess.check_call([demo, str(W), str(H), str(D), str(frames), str(S), str(K), out, "32", "surface"])
+    rows = np.fromfile(out, np.float64).reshape(-1, 9)
+    x0 = rows[:, 0:3]
+    raw = np.fromfile(out + ".surface", np.uint32)
+    nv, nt = int(raw[0]), int(raw[1])
+    vbuf = raw[2:2 + 9 * nv].view(np.float32).reshape(nv, 9)
+    ibuf = raw[2 + 9 * nv:2 + 9 * nv + 3 * nt].reshape(nt, 3)
+    s2t = raw[2 + 9 * nv + 3 * nt:2 + 9 * nv + 3 * nt + nv]
+    _, tets = scenes.bar_model(W, H, D)
+    floor = scenes.Sdf("plane", (0.0, 1.0, 0.0), (0.0, 0.0, 0.0), (-200.0, -5.0, -200.0, 200.0, 5.0, 200.0))
+    scene = scenes.Scene("facade_demo", [scenes.TetBody(x0=x0.copy(), tets=tets.astype(np.uint32), x=x0.copy()), floor],
+                         substeps=S, iterations=K)
+    sim = sbs.Simulation(0, 32)
+    ids = scene.instantiate(sim)
+    for f in range(frames):
+        sim.step(scene.dt, S, K, False)
+        if f == 0:
+            sim.set_mass(ids[0], 0, 0.0)
+    assert np.array_equal(s2t, sim.surface_map(ids[0])) and np.array_equal(ibuf, sim.surface_triangles(ids[0]).reshape(-1, 3))
+    ref = sim.download_surface_rgb(ids[0], (1.0, 1.0, 0.0))       # the demo's beam_geometry.set_color(255, 255, 0)
+    assert np.array_equal(vbuf[:, :3], ref[:, :3]) and np.array_equal(vbuf[:, 6:], ref[:, 6:])
+    assert np.abs(vbuf[:, 3:6] - ref[:, 3:6]).max() < 1e-5          # normals: float atomics, order-dependent last bit
+    assert np.abs(np.linalg.norm(vbuf[:, 3:6], axis=1) - 1).max() < 1e-5
