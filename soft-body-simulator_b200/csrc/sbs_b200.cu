@@ -1709,13 +1709,10 @@ int sbsb200_finalize(sbsb200_ctx* c)
                                                                  : ResidentPlan<double>::resident_params();
                 rp.pencils     = at.pencils;
                 if (ensemble)
-                { // few bodies per SM: one body per region, so that every SM has several independent regions to
-                  // interleave (the latency of a colour step does not shrink with the region); many: enough bodies
-                  // per region to fill the warps of a colour step (0 = about 160 clusters in the widest step)
-                    int64_t bodies = 0;
-                    for (auto const& b : h.bodies)
-                        bodies += (b.kind == BodyKind::tet && b.n_tets > 0);
-                    rp.bodies_per_region = bodies < 8 * static_cast<int64_t>(c->sm_count) ? 1 : 0;
+                { // bodies per region: chosen by build_cluster_plan for the least idle capacity of the SMs (few bodies
+                  // per SM come out as one body per region, so that every SM has independent regions to interleave)
+                    rp.bodies_per_region = 0;
+                    rp.sm_count          = c->sm_count;
                 }
                 rp.smem_bytes  = rp.smem_bytes / per_sm - (per_sm > 1 ? 4096 : 0);
                 rp.max_threads = per_sm == 1 ? 384 : 192;

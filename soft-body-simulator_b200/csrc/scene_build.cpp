@@ -657,6 +657,37 @@ void build_cluster_plan(HostScene const& scene, int32_t n_regions, bool one_regi
                         most_vertices = std::max<int64_t>(most_vertices, hb.n_vertices);
                 int64_t const fit = resident->smem_bytes / (most_vertices * resident->vertex_bytes);
                 group = static_cast<int32_t>(std::max<int64_t>(1, std::min<int64_t>((160 + widest / 2) / widest, fit)));
+                if (resident->sm_count > 0)
+                { // Whole regions are dealt to the resident CTAs in rounds, and the last round is as long as the others
+                  // however few CTAs take part: what counts is the capacity an SM has to provide, rounds x CTAs per SM
+                  // x bodies per region, against the bodies it really has.  Measured (profiles/r02_ab_bodies_per_region.txt):
+                  // the frame time follows that capacity — 4 096 bodies of 50 clusters per step: five per region = 3 rounds
+                  // x 2 CTAs x 5 = 30 against 36 with three per region, 17.3 ms against 19.4; 2 048 bodies: seven per region
+                  // (one CTA of 352 threads per SM) = 2 x 1 x 7 = 14 against 16 with one per region, 9.0 ms against 10.6 —
+                  // times a factor for the shapes that ran slower per body: 7, 10 warps (uneven over the four
+                  // sub-partitions) and the 168-register instantiation above 256 threads.  Every SM must get a region;
+                  // ties go to the smaller regions.
+                    static double const warp_factor[13] = {1, 1, 1, 1, 1, 1, 1, 1.12, 1, 1.1, 1.2, 1.1, 1.1};
+                    double best = 1e300;
+                    group       = 1;
+                    for (int32_t g = 1; g <= fit; ++g)
+                    {
+                        int64_t const nt = std::max<int64_t>(64, (static_cast<int64_t>(g) * widest + 31) / 32 * 32);
+                        if (nt > 384)
+                            break;
+                        int64_t const ctas    = nt > 256 ? 1 : std::max<int64_t>(1, std::min<int64_t>(65536 / (128 * nt), 2048 / nt));
+                        int64_t const regions = (nb + g - 1) / g;
+                        if (g > 1 && regions < resident->sm_count)
+                            break;
+                        int64_t const slots   = ctas * resident->sm_count;
+                        double const capacity = static_cast<double>((regions + slots - 1) / slots * ctas * g) * warp_factor[nt / 32];
+                        if (capacity < best - 1e-9)
+                        {
+                            best  = capacity;
+                            group = g;
+                        }
+                    }
+                }
             }
         }
         out.n_regions = std::max<int32_t>(1, (nb + group - 1) / group);

@@ -144,7 +144,9 @@ struct ResidentParams
                                  // every step that flips the parity along the pencil axis depends on no other region
     bool push_first      = true; // clusters that push in their step first inside a chunk (A/B knob)
     int32_t bodies_per_region = 0; // ensembles (one_region_per_body): consecutive bodies grouped into one region so
-                                   // that a colour step fills its warps; 0 = choose (about 160 clusters per step)
+                                   // that a colour step fills its warps; 0 = choose (about 160 clusters per step, or,
+                                   // when sm_count is given, the size that leaves the SMs the least idle capacity)
+    int32_t sm_count = 0;          // SMs the regions are dealt to (0: unknown)
 };
 
 // Which thread runs cluster i of a (colour, region) step.  Warp w of a CTA issues on sub-partition w % 4,
