@@ -490,7 +490,8 @@ __device__ __forceinline__ void push_cluster(ResidentArgs<R> const& a, uint4 con
         Real4<R> p[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-            p[e] = sx[slot[e] & 0xffffu]; // slot 0 when the entry is empty: a harmless read
+            if (slot[e] & kPullValid) // (an empty entry names slot 0, which another thread may be writing in this step)
+                p[e] = sx[slot[e] & 0xffffu];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (slot[e] & kPullValid)

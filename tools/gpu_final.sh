@@ -16,8 +16,8 @@ done
 ( timeout 400 ncu --set full --cache-control none --clock-control none --import-source on -k regex:k_substep_resident -s 25 -c 1 -f -o gpurun_out/r02_full_k_substep_resident python bench.py --steps 1 --warmup 2 --no-cpu-baseline --no-e2e --no-sub > gpurun_out/r02_bench_under_ncu_full.log 2>&1 )
 ( REGION_SHAPE=1 timeout 120 python tools/trace_steps.py config3 > gpurun_out/r02_final_trace_config3_compact.txt 2>&1 )
 ( REGION_SHAPE=0 timeout 120 python tools/trace_steps.py config3 > gpurun_out/r02_final_trace_config3_pencils.txt 2>&1 )
-( timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_round2.py -q -x -k "region_shapes and 32-1" > gpurun_out/r02_sanitizer_memcheck.txt 2>&1; echo "exit $?" >> gpurun_out/r02_sanitizer_memcheck.txt )
-( timeout 400 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_round2.py -q -x -k "general_route_counter" > gpurun_out/r02_sanitizer_racecheck.txt 2>&1; echo "exit $?" >> gpurun_out/r02_sanitizer_racecheck.txt )
+( timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_round2.py tests/test_gpu_parity.py -q -x -k "region_shapes and 32-1 or removed_in_place and 32 or surface_output_with_colours or ensemble_of_independent" > gpurun_out/r02_sanitizer_memcheck.txt 2>&1; echo "exit $?" >> gpurun_out/r02_sanitizer_memcheck.txt )
+( timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_round2.py tests/test_gpu_parity.py -q -x -k "general_route_counter or ensemble_of_independent or region_shapes and 32" > gpurun_out/r02_sanitizer_racecheck.txt 2>&1; echo "exit $?" >> gpurun_out/r02_sanitizer_racecheck.txt )
 ( timeout 300 python tools/time_remove.py > gpurun_out/r02_time_remove_constraints.txt 2>&1 )
 ( timeout 60 ./tools/bench_die.bin > gpurun_out/r02_microbench_die_homes.txt 2>&1 )
-tail -3 gpurun_out/r02_final_pytest_gpu.log; tail -3 gpurun_out/r02_final_smoke.txt; cut -c1-300 gpurun_out/r02_final_bench.json; tail -3 gpurun_out/r02_sanitizer_memcheck.txt gpurun_out/r02_sanitizer_racecheck.txt; ls -la gpurun_out/*.ncu-rep
+tail -3 gpurun_out/r02_final_pytest_gpu.log; tail -3 gpurun_out/r02_final_smoke.txt; cut -c1-300 gpurun_out/r02_final_bench.json; tail -n 3 gpurun_out/r02_sanitizer_memcheck.txt; tail -n 3 gpurun_out/r02_sanitizer_racecheck.txt; ls -la gpurun_out/*.ncu-rep
