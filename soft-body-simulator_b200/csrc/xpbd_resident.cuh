@@ -489,9 +489,10 @@ __device__ __forceinline__ void push_cluster(ResidentArgs<R> const& a, uint4 con
         uint32_t const route[4] = {w0.y, w0.w, w1.y, w1.w};
         Real4<R> p[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (slot[e] & kPullValid) // (an empty entry names slot 0, which another thread may be writing in this step)
-                p[e] = sx[slot[e] & 0xffffu];
+        for (int e = 0; e < 4; ++e) // an empty entry re-reads the first one (it would name slot 0, which another thread may
+                                    // be writing in this step); the loads stay unconditional, which the register
+                                    // allocation of the 384-thread instantiation depends on (48 bytes of spills otherwise)
+            p[e] = sx[((slot[e] & kPullValid) ? slot[e] : slot[0]) & 0xffffu];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (slot[e] & kPullValid)
