@@ -126,6 +126,48 @@ extern "C" int hs_cluster_plan(int64_t nV, int64_t nT, const uint32_t* tets, con
 
 // decomposition over `world` ranks of a single lattice body: per-tet region and per-region rank, as
 // the library plans it (regions_for / build_cluster_plan / region_rank); returns the region count
+// bodies per region the planner picks for an ensemble of n_bodies copies of one mesh on sm_count SMs (ResidentParams::sm_count)
+extern "C" int hs_ensemble_group(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int n_bodies, int sm_count,
+                                 int32_t* n_regions, int32_t* threads)
+{
+    HostScene h;
+    for (int b = 0; b < n_bodies; ++b)
+    {
+        HostBody hb;
+        hb.v_offset   = h.n_vertices();
+        hb.n_vertices = nV;
+        hb.t_offset   = h.n_tets();
+        hb.n_tets     = nT;
+        for (int64_t i = 0; i < nV; ++i)
+        {
+            h.x0.push_back(x0[3 * i] + 1000.0 * b);
+            h.x0.push_back(x0[3 * i + 1]);
+            h.x0.push_back(x0[3 * i + 2]);
+            h.mass.push_back(1.0);
+        }
+        for (int64_t t = 0; t < nT; ++t)
+        {
+            for (int a = 0; a < 4; ++a)
+                h.tets.push_back(static_cast<uint32_t>(hb.v_offset + tets[4 * t + a]));
+            h.tet_insertion.push_back(h.n_constraints++);
+            h.tet_material.push_back(0);
+        }
+        h.bodies.push_back(hb);
+    }
+    ResidentParams rp;
+    rp.smem_bytes  = 208 * 1024;
+    rp.max_threads = 384;
+    rp.sm_count    = sm_count;
+    ClusterPlan cp;
+    RegionPlan regions;
+    build_cluster_plan(h, 0, true, cp, &rp, &regions);
+    if (!cp.why_not.empty() || !cluster_plan_is_valid(h, cp))
+        return -1;
+    *n_regions = cp.n_regions;
+    *threads   = cp.nt;
+    return (n_bodies + cp.n_regions - 1) / cp.n_regions;
+}
+
 extern "C" int hs_partition(int64_t nV, int64_t nT, const uint32_t* tets, const double* x0, int sm_count, int world,
                             int32_t* tet_region, int32_t* region_rank_out, int cap_regions)
 {

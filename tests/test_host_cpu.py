@@ -160,6 +160,26 @@ def test_clustered_colouring_of_lattices(hostscene, oracle, dims, bodies, region
         assert mch.value <= group * (n_cells / 8 + 3), (mch.value, group, n_cells)
 
 
+@pytest.mark.parametrize("bodies,group,threads", [(4096, 5, 256), (3000, 7, 352), (2048, 7, 352), (1024, 1, 64), (512, 1, 64),
+                                                   (40, 1, 64)])
+def test_ensemble_regions_are_sized_for_the_least_idle_capacity(hostscene, oracle, bodies, group, threads):
+    """Ensembles on 148 SMs: regions are dealt to the resident CTAs in rounds, so the planner picks the number of bodies
+    per region that leaves the SMs the least idle capacity — rounds x CTAs per SM x bodies per region
+    (scene_build.cpp; measured in profiles/r02_ab_bodies_per_region.txt): 4 096 bodies of 6x6x17 -> five per region
+    (3 rounds x 2 CTAs x 5 = 30 for 27.7 bodies per SM), 2 048 -> seven (one 352-thread CTA per SM, 2 rounds = 14 for
+    13.8), few bodies per SM -> one per region."""
+    pos, tets = oracle.bar_model(6, 6, 17)
+    tets = np.ascontiguousarray(tets, np.uint32)
+    x0 = pos.astype(np.float64)
+    nr, nt = C.c_int32(0), C.c_int32(0)
+    hostscene.hs_ensemble_group.argtypes = [C.c_int64, C.c_int64, u32p, dp, C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int32)]
+    g = hostscene.hs_ensemble_group(len(pos), len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), bodies, 148,
+                                    C.byref(nr), C.byref(nt))
+    assert (g, nt.value) == (group, threads), (g, nr.value, nt.value)
+    assert nr.value == -(-bodies // group)
+
+
 def test_clustered_colouring_of_an_irregular_mesh(hostscene):
     """Random Delaunay-like soup: a fan of tets around shared vertices, unequal cluster sizes."""
     rng = np.random.default_rng(5)
