@@ -250,6 +250,26 @@ def test_exchange_plan_reproduces_the_serial_sweep(hostscene, oracle, dims, bodi
         assert st["shared"] > 0 and st["pulls"] == st["pushes"] > 0
 
 
+@pytest.mark.parametrize("dims,bodies,regions,per_body", [((21, 21, 51), 1, 39, 0), ((9, 9, 25), 1, 8, 0), ((6, 6, 17), 24, 0, 1)])
+def test_vertex_slots_are_spread_over_the_shared_memory_banks(hostscene, oracle, dims, bodies, regions, per_body):
+    """A warp's 128-bit access to the vertex table costs as many wavefronts as the fullest of the eight 16-byte bank
+    columns holds distinct slots.  build_exchange_plan numbers the slots of a region so that the accesses of every warp
+    instruction (lane = cluster of the step, instruction = tet m / corner) spread over the columns: vertex order of a
+    lattice costs 2-3 times the ideal, the chosen order stays within 1.3 times (and the protocol emulation above runs on
+    the renumbered tables)."""
+    pos, tets = oracle.bar_model(*dims)
+    tets = np.ascontiguousarray(tets, np.uint32)
+    x0 = pos.astype(np.float64)
+    st = np.zeros(26, np.int64)
+    rc = hostscene.hs_exchange_emulate(len(pos), len(tets), tets.ctypes.data_as(u32p), x0.ctypes.data_as(dp), bodies,
+                                       regions, 1, per_body, 2, 1, 0, 0, st.ctypes.data_as(i64p))
+    assert rc == 0
+    before, after, ideal = int(st[23]), int(st[24]), int(st[25])
+    assert ideal > 0 and after >= ideal
+    assert after <= 1.3 * ideal, (before, after, ideal)
+    assert before >= 1.6 * ideal, (before, after, ideal)       # what the renumbering is for
+
+
 def test_pencil_regions_leave_half_of_the_colour_steps_without_exchange(hostscene, oracle):
     """Regions = bundles of cell columns along the shortest axis, colours ordered as a Gray code of the cell
     parities: the steps that flip the parity along the pencil axis pull (practically) nothing from other
