@@ -624,6 +624,23 @@ class simulation_t
     std::vector<std::unique_ptr<body_t>> const& bodies() const { return bodies_; }
     std::vector<std::unique_ptr<body_t>>& bodies() { return bodies_; } // replaced bodies are noticed at the next step
     std::vector<std::unique_ptr<constraint_t>> const& constraints() const { return constraints_; }
+    // simulation.h:31: handed out mutable, the list may change behind the facade's back — if it did, the device scene
+    // is rebuilt from it at the next step (add_constraint / remove_constraint are the cheap ways)
+    std::vector<std::unique_ptr<constraint_t>>& constraints()
+    {
+        constraints_handed_out_ = true; // compared with what the device scene was built from at the next step
+        return constraints_;
+    }
+    // simulation.h:24, :32-33.  The reference's contact handler fills this list at every detection and
+    // timestep_t::step clears it before returning (timestep.cpp:68), so between steps it is empty there too; on the
+    // device the contacts are a compacted list the step consumes (read them with sbsb200_get_contacts).  Adding a
+    // collision constraint by hand has no device counterpart.
+    std::vector<std::unique_ptr<constraint_t>> const& collision_constraints() const { return collision_constraints_; }
+    void add_collision_constraint(std::unique_ptr<constraint_t>)
+    {
+        throw std::logic_error("sbs-b200: collision constraints are created by the detection on the device "
+                               "(timestep_t::step); there is no CPU path");
+    }
     std::unique_ptr<collision::cd_system_t> const& collision_detection_system() const { return cd_system_; }
     xpbd::simulation_parameters_t const& simulation_parameters() const { return simulation_parameters_; }
     xpbd::simulation_parameters_t& simulation_parameters() { return simulation_parameters_; }
@@ -659,6 +676,8 @@ class simulation_t
     std::vector<std::vector<particle_t>> particles_;
     std::vector<std::unique_ptr<body_t>> bodies_;
     std::vector<std::unique_ptr<constraint_t>> constraints_;
+    std::vector<std::unique_ptr<constraint_t>> collision_constraints_; // always empty between steps (timestep.cpp:68)
+    bool constraints_handed_out_ = false; // constraints() was handed out mutable since the last step
     std::unique_ptr<collision::cd_system_t> cd_system_;
     xpbd::simulation_parameters_t simulation_parameters_;
     sbsb200_ctx* ctx_ = nullptr;
@@ -1120,6 +1139,20 @@ inline void simulation_t::device_step(scalar_type dt, std::size_t substeps, std:
     std::vector<body_t const*> now;
     for (auto const& b : bodies_)
         now.push_back(b.get());
+    if (constraints_handed_out_ && !dirty_)
+    { // the caller had the list in hand: still the constraints the device scene holds, in any order?
+        std::vector<constraint_t const*> have, built;
+        for (auto const& c : constraints_)
+            have.push_back(c.get());
+        for (constraint_t const* c : device_constraint_)
+            if (c)
+                built.push_back(c);
+        std::sort(have.begin(), have.end());
+        std::sort(built.begin(), built.end());
+        if (have != built)
+            invalidate();
+    }
+    constraints_handed_out_ = false;
     if (dirty_ || !ctx_ || now != built_bodies_)
     {
         refresh_host();
