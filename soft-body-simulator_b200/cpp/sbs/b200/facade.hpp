@@ -377,6 +377,16 @@ class sdf_model_t : public collision_model_t
         m.triangles_    = std::move(triangles);
         return m;
     }
+    // sdf_model.cpp:52-75.  On the host only the plane is evaluated (signed distance and gradient as
+    // Eigen::Hyperplane gives them, :57-61); the other shapes are sampled where the detection samples them:
+    // simulation_t::evaluate_sdf(body, p) asks the device (sbsb200_eval_sdf).
+    std::pair<scalar_type, vec3> evaluate(vec3 const& p) const
+    {
+        if (shape_ != shape_t::plane)
+            throw std::logic_error("sbs-b200: sdf_model_t::evaluate on the host covers planes; use "
+                                   "simulation_t::evaluate_sdf for the shapes the device samples");
+        return {a_[0] * p[0] + a_[1] * p[1] + a_[2] * p[2] + d_, a_};
+    }
     shape_t shape() const { return shape_; }
     vec3 const& a() const { return a_; }
     vec3 const& b() const { return b_; }
@@ -404,11 +414,48 @@ class point_bvh_model_t : public collision_model_t
     model_type_t model_type() const override { return model_type_t::bvh; }
 };
 
-// include/sbs/physics/collision/contact.h:60-64
+// include/sbs/physics/collision/contact.h:11-58
+class contact_t
+{
+  public:
+    enum class type_t { surface_particle_to_sdf };
+    contact_t(type_t contact_type, index_type body1, index_type body2, vec3 const& contact_point, vec3 const& contact_normal)
+        : type_(contact_type), bodies_{body1, body2}, point_(contact_point), normal_(contact_normal)
+    {
+    }
+    type_t type() const { return type_; }
+    vec3 const& point() const { return point_; }
+    vec3 const& normal() const { return normal_; }
+    index_type b1() const { return bodies_[0]; }
+    index_type b2() const { return bodies_[1]; }
+
+  private:
+    type_t type_;
+    index_type bodies_[2];
+    vec3 point_, normal_;
+};
+class surface_mesh_particle_to_sdf_contact_t : public contact_t
+{
+  public:
+    surface_mesh_particle_to_sdf_contact_t(contact_t::type_t contact_type, index_type body1, index_type body2,
+                                           vec3 const& contact_point, vec3 const& contact_normal, index_type vi)
+        : contact_t(contact_type, body1, body2, contact_point, contact_normal), vi_(vi)
+    {
+    }
+    index_type vi() const { return vi_; } // surface vertex of body b1 (tetrahedral_mesh_boundary_t numbering)
+    index_type& vi() { return vi_; }
+
+  private:
+    index_type vi_;
+};
+
+// include/sbs/physics/collision/contact.h:60-64.  The device turns contacts into collision constraints itself
+// (xpbd/contact_handler.cpp:14-54); simulation_t::contacts() lists what it found at the last detection.
 class contact_handler_t
 {
   public:
     virtual ~contact_handler_t() = default;
+    virtual void handle(contact_t const&) {}
 };
 
 // include/sbs/physics/collision/cd_system.h:19-47
@@ -421,6 +468,10 @@ class cd_system_t
     std::unique_ptr<contact_handler_t> const& contact_handler() const { return contact_handler_; }
     std::unique_ptr<contact_handler_t>& contact_handler() { return contact_handler_; }
     void use_contact_handler(std::unique_ptr<contact_handler_t> h) { contact_handler_ = std::move(h); }
+    // cd_system.h:36-38: refit and pair loop — both happen on the device inside timestep_t::step
+    // (k_bvh_fit, k_detect_all); calling them on the facade changes nothing
+    virtual void update(simulation_t const&) {}
+    virtual void execute() {}
 
   private:
     std::vector<collision_model_t*> collision_objects_;
@@ -658,6 +709,11 @@ class simulation_t
         return ctx_;
     }
     int device_body(index_type body) const { return device_body_.at(body); }
+    // what the reference hands to contact_handler_t::handle at a detection (bvh_model.cpp:66-96): the contacts of the
+    // most recent detection on the device (sbsb200_get_contacts), bodies as simulation body indices, vi as surface vertex
+    std::vector<collision::surface_mesh_particle_to_sdf_contact_t> contacts();
+    // sdf_model_t::evaluate of an environment body as the detection samples it (sbsb200_eval_sdf)
+    std::pair<scalar_type, vec3> evaluate_sdf(index_type body, vec3 const& p);
     void device_step(scalar_type dt, std::size_t substeps, std::size_t iterations);
     // the serial constraint order equivalent to the device schedule (sbsb200_get_constraint_order)
     std::vector<index_type> device_constraint_order();
@@ -1171,6 +1227,59 @@ inline void simulation_t::device_step(scalar_type dt, std::size_t substeps, std:
     check(sbsb200_step(ctx_, dt, static_cast<int>(substeps), static_cast<int>(iterations), detect_mode),
           "sbsb200_step");
     host_stale_ = true;
+}
+
+inline std::vector<collision::surface_mesh_particle_to_sdf_contact_t> simulation_t::contacts()
+{
+    std::vector<collision::surface_mesh_particle_to_sdf_contact_t> out;
+    if (dirty_ || !ctx_)
+        return out; // nothing has been detected on a device scene yet
+    std::int64_t const n = sbsb200_get_contacts(ctx_, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (n < 0)
+        throw b200::error(static_cast<int>(n), std::string("sbsb200_get_contacts: ") + sbsb200_last_error(ctx_));
+    std::vector<std::int32_t> body(static_cast<std::size_t>(n)), sdf(static_cast<std::size_t>(n));
+    std::vector<std::uint32_t> vertex(static_cast<std::size_t>(n));
+    std::vector<double> point(3 * static_cast<std::size_t>(n)), normal(3 * static_cast<std::size_t>(n));
+    if (n > 0)
+        check(static_cast<int>(sbsb200_get_contacts(ctx_, n, body.data(), vertex.data(), sdf.data(), point.data(), normal.data())),
+              "sbsb200_get_contacts");
+    std::vector<index_type> host_of_device;
+    for (std::size_t b = 0; b < device_body_.size(); ++b)
+        if (device_body_[b] >= 0)
+        {
+            host_of_device.resize(std::max<std::size_t>(host_of_device.size(), static_cast<std::size_t>(device_body_[b]) + 1), 0);
+            host_of_device[static_cast<std::size_t>(device_body_[b])] = static_cast<index_type>(b);
+        }
+    std::unordered_map<index_type, std::unordered_map<index_type, index_type>> surface_of; // body -> tet vertex -> surface vertex
+    for (std::int64_t i = 0; i < n; ++i)
+    {
+        index_type const b1 = host_of_device.at(static_cast<std::size_t>(body[static_cast<std::size_t>(i)]));
+        index_type const b2 = host_of_device.at(static_cast<std::size_t>(sdf[static_cast<std::size_t>(i)]));
+        auto it = surface_of.find(b1);
+        if (it == surface_of.end())
+        {
+            it = surface_of.emplace(b1, std::unordered_map<index_type, index_type>{}).first;
+            std::int64_t const ns = sbsb200_get_surface_map(ctx_, device_body_[b1], nullptr, 0);
+            std::vector<std::uint32_t> map(static_cast<std::size_t>(std::max<std::int64_t>(ns, 0)));
+            if (ns > 0)
+                sbsb200_get_surface_map(ctx_, device_body_[b1], map.data(), ns);
+            for (std::size_t sv = 0; sv < map.size(); ++sv)
+                it->second.emplace(map[sv], static_cast<index_type>(sv));
+        }
+        std::size_t const k = 3 * static_cast<std::size_t>(i);
+        out.emplace_back(collision::contact_t::type_t::surface_particle_to_sdf, b1, b2, vec3(point[k], point[k + 1], point[k + 2]),
+                         vec3(normal[k], normal[k + 1], normal[k + 2]), it->second.at(vertex[static_cast<std::size_t>(i)]));
+    }
+    return out;
+}
+
+inline std::pair<scalar_type, vec3> simulation_t::evaluate_sdf(index_type body, vec3 const& p)
+{
+    sbsb200_ctx* ctx = ensure_device();
+    double const pt[3] = {p[0], p[1], p[2]};
+    double sd = 0., grad[3] = {0., 0., 0.};
+    check(sbsb200_eval_sdf(ctx, device_body_.at(body), 1, pt, &sd, grad), "sbsb200_eval_sdf");
+    return {sd, vec3(grad[0], grad[1], grad[2])};
 }
 
 inline std::vector<index_type> simulation_t::device_constraint_order()

@@ -140,6 +140,26 @@ int main(int argc, char** argv)
             std::fwrite(beam.surface_mesh().surface_to_tetrahedral_mesh_index_map().data(), sizeof(sbs::index_type),
                         mesh.vertex_count(), o);
             std::fclose(o);
+            // the contacts of the last detection as contact_handler_t::handle would have seen them (contact.h:11-58),
+            // and the floor's signed distance at a point, on the host (sdf_model.cpp:57-61) and as the device samples it
+            auto const contacts = simulation.contacts();
+            std::FILE* c = std::fopen((std::string(argv[7]) + ".contacts").c_str(), "wb");
+            if (!c)
+                return 3;
+            for (auto const& k : contacts)
+            {
+                double const row[9] = {static_cast<double>(k.b1()), static_cast<double>(k.b2()), static_cast<double>(k.vi()),
+                                       k.point().x(), k.point().y(), k.point().z(), k.normal().x(), k.normal().y(), k.normal().z()};
+                std::fwrite(row, sizeof(double), 9, c);
+            }
+            sbs::vec3 const probe{0.3, 1.25, -2.};
+            auto const& floor = *dynamic_cast<sbs::physics::environment_body_t*>(simulation.bodies()[floor_idx].get());
+            auto const on_host   = floor.sdf().evaluate(probe);
+            auto const on_device = simulation.evaluate_sdf(floor_idx, probe);
+            double const tail[9] = {-1., on_host.first, on_device.first, on_host.second.x(), on_host.second.y(), on_host.second.z(),
+                                    on_device.second.x(), on_device.second.y(), on_device.second.z()};
+            std::fwrite(tail, sizeof(double), 9, c);
+            std::fclose(c);
         }
 
         auto const& ps = static_cast<sbs::physics::simulation_t const&>(simulation).particles()[beam_idx];

@@ -182,7 +182,7 @@ def test_facade_visual_model_for_a_renderer(sbs, scenes):
     renderer consumes, filled from the device, equal what the C ABI hands out for the same scene."""
     demo = build_demo()
     out = os.path.join(BUILD, "facade_32_surface.bin")
-    W, H, D, frames, S, K = 4, 4, 12, 2, 2, 5
+    W, H, D, frames, S, K = 4, 4, 12, 24, 2, 5          # long enough for the beam to reach the floor
     subprocess.check_call([demo, str(W), str(H), str(D), str(frames), str(S), str(K), out, "32", "surface"])
     rows = np.fromfile(out, np.float64).reshape(-1, 9)
     x0 = rows[:, 0:3]
@@ -206,3 +206,15 @@ def test_facade_visual_model_for_a_renderer(sbs, scenes):
     assert np.array_equal(vbuf[:, :3], ref[:, :3]) and np.array_equal(vbuf[:, 6:], ref[:, 6:])
     assert np.abs(vbuf[:, 3:6] - ref[:, 3:6]).max() < 1e-5          # normals: float atomics, order-dependent last bit
     assert np.abs(np.linalg.norm(vbuf[:, 3:6], axis=1) - 1).max() < 1e-5
+    # simulation_t::contacts(): what contact_handler_t::handle would have seen at the last detection (contact.h:11-58)
+    rows = np.fromfile(out + ".contacts", np.float64).reshape(-1, 9)
+    tail, rows = rows[-1], rows[:-1]
+    body, vertex, sdf_body, point, normal = sim.contacts()
+    assert len(rows) == len(body) > 0
+    mine = sorted((int(s2t[int(r[2])]), tuple(np.round(r[3:9], 12))) for r in rows)
+    theirs = sorted((int(v), tuple(np.round(np.concatenate([p, n]), 12))) for v, p, n in zip(vertex, point, normal))
+    assert mine == theirs
+    assert set(rows[:, 0].astype(int)) == {0} and set(rows[:, 1].astype(int)) == {1}     # beam, floor: simulation body indices
+    # sdf_model_t::evaluate on the host (plane) and as the device samples it: y = 1.25 above the floor, gradient +y
+    assert tail[0] == -1 and abs(tail[1] - 1.25) < 1e-12 and abs(tail[2] - 1.25) < 1e-12
+    assert np.allclose(tail[3:6], (0, 1, 0)) and np.allclose(tail[6:9], (0, 1, 0))
