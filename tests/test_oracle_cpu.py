@@ -142,3 +142,33 @@ def test_detect_every_substep_equals_repeated_single_substep_frames(oracle, scen
     for _ in range(4):
         b.step(0.004, 1, 3, False)
     assert np.array_equal(a.download(0)[0], b.download(0)[0])
+
+
+def test_remove_constraint_matches_the_reference(oracle, scenes):
+    """simulation_t::remove_constraint (simulation.cpp:34-39: swap with the last, drop it) in the C restatement against the
+    reference's own method through oracle/_ref: a tenth of the constraints goes after the first frame, two more frames."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    scene = scenes.config1(W=5, H=5, D=9, seed=3)
+    worlds = [oracle.World(), R.World()]
+    for w in worlds:
+        scene.instantiate(w)
+        w.step(scene.dt, scene.substeps, scene.iterations, False)
+    n = worlds[0].constraint_count()
+    assert n == worlds[1].constraint_count()
+    gone = np.random.default_rng(5).choice(n, n // 10, replace=False)
+    for w in worlds:
+        for k, g in enumerate(sorted(gone.tolist(), reverse=True)):     # positions stay valid when removed from the back
+            w.remove_constraint(g)
+        assert w.constraint_count() == n - len(gone)
+        for _ in range(2):
+            w.step(scene.dt, scene.substeps, scene.iterations, False)
+    xa, va = worlds[0].download(0)
+    xb, vb = worlds[1].download(0)
+    assert np.abs(xa - xb).max() <= 1e-12 * scene.bbox_diagonal()
+    keep = oracle.World()
+    scene.instantiate(keep)
+    for _ in range(3):
+        keep.step(scene.dt, scene.substeps, scene.iterations, False)
+    assert np.abs(keep.download(0)[0] - xa).max() > 1e-4 * scene.bbox_diagonal()     # the constraints mattered
